@@ -1,0 +1,179 @@
+/*
+ * qm_b200.h — C ABI of the B200-native state-vector engine that sits beneath
+ * Quromorphic.jl's src/Quantum simulator API.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, and returns
+ * an int32 status (0 = QM_OK).  Nothing here names a torch/CUDA type: the Julia
+ * host binds these with `ccall` (see INTEGRATION.md and
+ * quromorphic.jl_b200/julia/B200QSim.jl), the Python harness with ctypes.
+ *
+ * Conventions at this boundary:
+ *   - qubit arguments are 0-based BIT positions of the amplitude index
+ *     (reference qubit t  <->  bit t-1, QSim.jl:56-58, :304).  The host shim
+ *     converts t -> t-1 and applies the reference's non-adjacent-control index
+ *     map (QSim.jl:181-197) before calling; the kernels are textbook.
+ *   - a 2x2 matrix is 8 doubles in Julia's Matrix{ComplexF64} memory order
+ *     (column-major, interleaved):  re U11, im U11, re U21, im U21,
+ *                                   re U12, im U12, re U22, im U22.
+ *   - amplitudes are interleaved (re, im) doubles, amplitude i at doubles
+ *     [2i, 2i+1] — exactly Vector{ComplexF64} memory (QSim.jl:33-37).
+ *   - host buffers belong to the caller and are never retained after return.
+ *   - gate calls enqueue (they are fused into HBM passes at the next flush);
+ *     readouts, download and qm_sync flush and synchronise.
+ *   - a handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef QM_B200_H
+#define QM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QM_ABI_VERSION 1
+
+/* status codes */
+enum {
+    QM_OK              = 0,
+    QM_ERR_ARG         = 1,  /* bad argument (range, null, c == t, ...)        */
+    QM_ERR_CUDA        = 2,  /* CUDA runtime/driver error (see qm_last_error) */
+    QM_ERR_NOMEM       = 3,  /* device or host allocation failed              */
+    QM_ERR_NO_DEVICE   = 4,  /* no CUDA device: there is NO CPU fallback      */
+    QM_ERR_STATE       = 5,  /* call not valid for this handle's mode         */
+    QM_ERR_COMM        = 6   /* NCCL / peer-memory failure                    */
+};
+
+/* gate kinds of the wire format (qm_gate.kind) */
+enum {
+    QM_GATE_U2      = 0,  /* 1-qubit 2x2 `m` on bit q0            — replaces u2!         QSim.jl:52-63   */
+    QM_GATE_CU2     = 1,  /* control bit q0, target bit q1, `m`   — replaces controlled! QSim.jl:175-203 */
+    QM_GATE_SWAP    = 2,  /* exchange bits q0 and q1              — replaces swap!       QSim.jl:262-275 */
+    QM_GATE_U2_SLOT = 3   /* batched only: 2x2 on bit q0 taken per state from slot q1 of `per_state_mats` */
+};
+
+/* measurement bases for qm_measure */
+enum { QM_BASIS_Z = 0, QM_BASIS_X = 1, QM_BASIS_Y = 2 };
+
+/* qm_set_option keys */
+enum {
+    QM_OPT_EAGER      = 0,  /* 1: run every gate call at once with the unfused kernels (default 0: queue + fuse) */
+    QM_OPT_TILE_BITS  = 1,  /* fused pass tile size m (default 12: 4096 amplitudes, 64 KiB of shared memory)     */
+    QM_OPT_LOW_BITS   = 2,  /* contiguous low bits every tile keeps (default 5: 512-byte rows)                    */
+    QM_OPT_FUSE       = 3,  /* 0: planner emits one pass per gate (debug), 1: fuse (default)                      */
+    QM_OPT_REMAP      = 4,  /* 1: planner may relabel qubits inside a pass (logical->physical permutation)        */
+    QM_OPT_PIPELINE   = 5   /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel (default)           */
+};
+
+typedef struct qm_state qm_state;
+
+/* One gate of a circuit.  80 bytes, no padding surprises: 4 x int32 + 8 x double. */
+typedef struct qm_gate {
+    int32_t kind;   /* QM_GATE_*                                   */
+    int32_t q0;     /* target (U2), control (CU2), first bit (SWAP) */
+    int32_t q1;     /* target (CU2), second bit (SWAP), slot (U2_SLOT) */
+    int32_t flags;  /* reserved, must be 0                          */
+    double  m[8];   /* 2x2 matrix, Julia memory order (unused for SWAP/U2_SLOT) */
+} qm_gate;
+
+/* Counters since creation (or the last qm_counters_reset). */
+typedef struct qm_counters_t {
+    uint64_t gates;          /* gates accepted                                  */
+    uint64_t passes;         /* fused HBM passes launched                       */
+    uint64_t launches;       /* kernels launched (all kinds)                    */
+    uint64_t bytes_hbm;      /* algorithmic HBM bytes of those passes/readouts  */
+    uint64_t bytes_link;     /* bytes sent over NVLink by remaps (this rank)    */
+    double   ms_device;      /* CUDA-event time of the last flushed circuit     */
+    double   ms_plan;        /* host planning time of the last flushed circuit  */
+} qm_counters_t;
+
+/* ---- lifetime -------------------------------------------------------------------- */
+
+/* statevector(n, m) for `batch` independent registers on CUDA device `device`
+ * (QSim.jl:33-37: zeros, then amplitude `basis_index` = 1).  batch >= 1. */
+int32_t qm_create(int32_t n_qubits, uint64_t basis_index, int32_t batch, int32_t device,
+                  qm_state** out);
+int32_t qm_destroy(qm_state* st);
+/* back to |basis_index> for every register of the batch */
+int32_t qm_reset(qm_state* st, uint64_t basis_index);
+int32_t qm_set_option(qm_state* st, int32_t key, int64_t value);
+int32_t qm_num_qubits(const qm_state* st, int32_t* n_qubits, int32_t* batch);
+
+/* ---- host <-> device state (B200State(v) / Vector{ComplexF64}(st)) ----------------- */
+int32_t qm_upload(qm_state* st, const double* host_interleaved, uint64_t n_amps, int32_t batch_idx);
+int32_t qm_download(qm_state* st, double* host_interleaved, uint64_t n_amps, int32_t batch_idx);
+
+/* ---- gates ----------------------------------------------------------------------------
+ * qm_apply_u2          replaces u2!          QSim.jl:52-63  (and h!,x!,y!,z!,rx!,ry!,rz!  :81-172)
+ * qm_apply_controlled  replaces controlled!  QSim.jl:175-203 (and cnot!,crx!,cry!,crz!    :205-260)
+ * qm_apply_swap        replaces swap!        QSim.jl:262-275
+ * qm_apply_circuit     a gate list, fused into as few HBM passes as the planner finds
+ * qm_apply_batched     a gate list applied to every register of the batch; QM_GATE_U2_SLOT
+ *                      gates take their matrix from per_state_mats[b][slot][8] (host, doubles)
+ */
+int32_t qm_apply_u2(qm_state* st, int32_t t0, const double U[8]);
+int32_t qm_apply_controlled(qm_state* st, int32_t c0, int32_t t0, const double V[8]);
+int32_t qm_apply_swap(qm_state* st, int32_t a0, int32_t b0);
+int32_t qm_apply_circuit(qm_state* st, const qm_gate* gates, int32_t ngates);
+int32_t qm_apply_batched(qm_state* st, const qm_gate* gates, int32_t ngates,
+                         const double* per_state_mats, int32_t nslots);
+
+/* ---- readouts -------------------------------------------------------------------------
+ * qm_probs          replaces mp               QSim.jl:293  (out: 2^n doubles per register, host)
+ * qm_measure        replaces measure_z/x/y    QSim.jl:297-330: (p0,p1) of bit t0 after the basis
+ *                   rotation, summing only probabilities > threshold (reference: 1e-10, strict;
+ *                   threshold < 0 disables the test).  batch_idx selects the register.
+ * qm_expect_z_all   all-qubit measure_z in ONE pass: out[2q] = p0, out[2q+1] = p1 for q = 0..n-1,
+ *                   for every register of the batch (out: batch * 2n doubles, host)
+ * qm_expect_all     same for basis X or Y (one pass per qubit)
+ * qm_reduced_density  statevector_to_density_matrix + partial_trace, QSim.jl:39-41 and
+ *                   QInfo.jl:381-405, without ever forming rho: keep_low=1 keeps B = the low k
+ *                   qubits (partial_trace(..., 1)), keep_low=0 keeps A = the high k qubits
+ *                   (partial_trace(..., 2)).  out: 2^k x 2^k ComplexF64, column-major interleaved.
+ * qm_sample         nshots basis-state indices by inverse CDF over abs2(psi) with the
+ *                   counter-based generator documented in DESIGN.md (bit-exact vs the oracle)
+ * qm_norm2          sum of abs2 (no threshold)
+ */
+int32_t qm_probs(qm_state* st, double* out_host, int32_t batch_idx);
+int32_t qm_measure(qm_state* st, int32_t basis, int32_t t0, double threshold, int32_t batch_idx,
+                   double out[2]);
+int32_t qm_expect_z_all(qm_state* st, double threshold, double* out_host);
+int32_t qm_expect_all(qm_state* st, int32_t basis, double threshold, double* out_host);
+int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k, int32_t batch_idx,
+                           double* out_colmajor);
+int32_t qm_sample(qm_state* st, uint64_t seed, int32_t nshots, int32_t batch_idx, uint64_t* out);
+int32_t qm_norm2(qm_state* st, int32_t batch_idx, double* out);
+
+/* ---- sharded registers (one process per GPU; high-order qubits global) -----------------
+ * qm_dist_unique_id  fills a 128-byte NCCL unique id (rank 0 calls it, the host broadcasts it)
+ * qm_create_dist     rank `rank` of `world` (power of two) holds the amplitudes whose top
+ *                    log2(world) index bits equal `rank`; n_qubits is the GLOBAL register size.
+ * Gates, readouts and counters then work on the global register; global-qubit gates are
+ * remapped by an in-place chunked all-to-all over NVLink.
+ */
+int32_t qm_dist_unique_id(uint8_t id_out[128]);
+int32_t qm_create_dist(int32_t n_qubits, uint64_t basis_index, int32_t device, int32_t rank,
+                       int32_t world, const uint8_t nccl_id[128], qm_state** out);
+
+/* ---- host-only planner introspection (works without a GPU; used by the CPU tests) ------
+ * Plans `gates` for an n-qubit register with the given tile/low-bit sizes and `global_bits`
+ * top qubits sharded; writes a flat int32 description of the passes into `out` (layout in
+ * DESIGN.md §planner) and the number of int32 written into *out_len.  Returns QM_ERR_ARG
+ * if cap is too small (then *out_len = needed). */
+int32_t qm_plan_describe(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
+                         int32_t allow_remap, const qm_gate* gates, int32_t ngates,
+                         int32_t* out, int64_t cap, int64_t* out_len);
+
+/* ---- misc ---------------------------------------------------------------------------- */
+int32_t qm_sync(qm_state* st);
+int32_t qm_last_error(char* buf, int32_t cap);
+int32_t qm_counters(qm_state* st, qm_counters_t* out);
+int32_t qm_counters_reset(qm_state* st);
+int32_t qm_abi_version(void);
+/* device-side view for harnesses that time on the library's stream (no ownership transfer) */
+int32_t qm_device_ptr(qm_state* st, void** amps, void** cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QM_B200_H */
