@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — the reservoir hot path on B200, measured as BASELINE.json asks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N = 1 : config C3 — 30-qubit ComplexF64 random reservoir circuit, depth 200 (8,900 gates), fused
+        gate passes on one B200; one step = the whole circuit from |0...0> plus the all-qubit <Z>
+        readout.
+N > 1 : config C4 — sharded register, 2^33 amplitudes (128 GiB) per GPU (34 q @ 2, 35 q @ 4,
+        36 q @ 8), one step = encoding layer + one C3-style layer + all-qubit <Z> readout.
+
+`value`  = gate applications per second in units of one gate over 2^30 amplitudes (at N = 1 this is
+           plain gates/s of the 30-qubit circuit; at 36 q one gate counts 64), device-timed with the
+           state resident in HBM.
+`e2e`    = the same metric through the public C-ABI calls with HOST buffers, wall clock: qm_reset,
+           qm_apply_circuit(host gate array) (planning + pass-program upload + kernels) and
+           qm_expect_z_all (device -> host readout) all inside the timed region.
+`roofline` is for the dominant kernel k_fused_pass: 32 * 2^n bytes per launch (16 read + 16 written
+           per amplitude) over its mean launch duration from CUDA events on the
+           launching stream, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` is oracle/qsim_oracle.c (matrix-free OpenMP restatement of the reference's
+           arithmetic; the Julia reference itself cannot run here) on this box's host cores over a
+           bounded sample of the same circuit.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C3_QUBITS, C3_DEPTH, C3_SEED = 30, 200, 3001
+SHARD_QUBITS = 33
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(n, gates, budget_s, threads=None):
+    """time the oracle on a prefix of `gates` at n qubits: returns (gates/s, ngates, threads, seconds)"""
+    import numpy as np
+    from oracle import oracle as O
+    if threads:
+        O.set_threads(threads)
+    s = O.statevector(n, 0)
+    O.apply_circuit(s, gates[:1].copy())            # touch pages / warm up
+    s = O.statevector(n, 0)
+    t0 = time.perf_counter()
+    done = 0
+    chunk = 4
+    while done < len(gates):
+        O.apply_circuit(s, np.ascontiguousarray(gates[done:done + chunk]))
+        done += min(chunk, len(gates) - done)
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, O.num_threads(), dt
+
+
+def pick_cpu_qubits(n):
+    """largest register <= n whose state (16 * 2^n bytes) fits comfortably in host memory"""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    while n > 20 and (16 << n) * 1.5 > avail:
+        n -= 1
+    return n
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU restatement of the reference's own arithmetic on the host cores."""
+    if rank != 0:
+        return
+    import numpy as np
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    n_full = C3_QUBITS if args.gpus == 1 else SHARD_QUBITS + (args.gpus.bit_length() - 1)
+    gates = pkg.circuits.c3_circuit(n=n_full, depth=2, seed=C3_SEED) if args.gpus == 1 else \
+        pkg.circuits.c4_step(n_full, 0)
+    n_cpu = pick_cpu_qubits(min(n_full, 30))
+    if n_cpu != n_full:   # same gate sequence restricted to the qubits that fit in host memory
+        gates = pkg.circuits.c3_circuit(n=n_cpu, depth=2, seed=C3_SEED)
+    budget = 6.0
+    vals = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        gps, ng, thr, dt = cpu_sample(n_cpu, gates, budget)
+        if i >= args.warmup:
+            vals.append((gps, ng, dt))
+    gps = sum(v[1] for v in vals) / sum(v[2] for v in vals)
+    scale = 2.0 ** (n_cpu - 30)                    # convert to units of one gate over 2^30 amplitudes
+    value = gps * scale
+    sample = "first %d gates of the %d-qubit circuit per step (state 16*2^%d B), %d threads" % (vals[0][1], n_cpu, n_cpu, thr)
+    line = {
+        "impl": "reference", "metric": "gates_per_sec", "value": value, "unit": "gates/s (one gate over 2^30 amplitudes)",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(v[2] for v in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, n_full),
+        "cpu_baseline": {"value": value, "unit": "gates/s (one gate over 2^30 amplitudes)", "cores": thr,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "gates/s (one gate over 2^30 amplitudes)", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(ngpus, n):
+    if ngpus == 1:
+        return {"workload": "C3: %d-qubit ComplexF64 random reservoir circuit, depth %d, fused gate passes, "
+                            "all-qubit <Z> readout" % (n, C3_DEPTH),
+                "n_qubits": n, "depth": C3_DEPTH, "seed": C3_SEED, "state_bytes": 16 << n,
+                "l2": "state (16 GiB) is far larger than the 126 MB L2; no flush needed"}
+    return {"workload": "C4: %d-qubit reservoir step sharded over %d B200 (2^%d amplitudes per GPU), global qubits "
+                        "remapped by in-place all-to-all over NVLink" % (n, ngpus, SHARD_QUBITS),
+            "n_qubits": n, "amps_per_gpu_log2": SHARD_QUBITS, "seed": 3601,
+            "l2": "shard (128 GiB) is far larger than L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--qubits", type=int, default=0, help="override the register size (testing)")
+    ap.add_argument("--depth", type=int, default=C3_DEPTH)
+    ap.add_argument("--tile-bits", type=int, default=0)
+    ap.add_argument("--low-bits", type=int, default=-1)
+    ap.add_argument("--max-cost", type=float, default=-1)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    L = pkg._lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    if world > 1:
+        from bench_dist import run_dist            # sharded path (C4)
+        run_dist(args, pkg, rank, world, local_rank)
+        return
+
+    torch.cuda.set_device(0)
+    n = args.qubits or C3_QUBITS
+    gates = pkg.circuits.c3_circuit(n=n, depth=args.depth, seed=C3_SEED)
+    ngates = len(gates)
+    st = pkg.B200State(n, 0)
+    if args.tile_bits:
+        st.set_option(L.OPT_TILE_BITS, args.tile_bits)
+    if args.low_bits >= 0:
+        st.set_option(L.OPT_LOW_BITS, args.low_bits)
+    if args.max_cost >= 0:
+        st.set_option(L.OPT_MAX_COST, int(args.max_cost))
+    import ctypes as C
+    amps, stream = C.c_void_p(), C.c_void_p()
+    L.check(L.lib().qm_device_ptr(st._h, C.byref(amps), C.byref(stream)))
+    ext = torch.cuda.ExternalStream(stream.value)
+    zout = np.empty((n, 2))
+
+    def step():
+        st.reset(0)
+        st.apply_circuit(gates)
+        return st.expect_z_all()
+
+    for _ in range(args.warmup):
+        step()
+    st.sync()
+
+    # ---- device-timed region: K steps, events on the library's own stream ----
+    st.counters_reset()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    pass_ms, npasses = 0.0, 0
+    t_wall0 = time.perf_counter()
+    e0.record(ext)
+    for _ in range(args.steps):
+        z = step()
+        c = st.counters()
+        pass_ms += c["ms_device"]
+    e1.record(ext)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    c = st.counters()
+    npasses = c["passes"]
+    unit = "gates/s (one gate over 2^30 amplitudes)"
+    scale = 2.0 ** (n - 30)
+    value = args.steps * ngates / (dev_ms * 1e-3) * scale
+    e2e = args.steps * ngates / wall * scale
+
+    hbm_peak, peak_kind = peaks()
+    bytes_per_launch = 32.0 * (1 << n)
+    avg_pass_ms = pass_ms / max(npasses, 1)
+    achieved = bytes_per_launch / (avg_pass_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_fused_pass", "achieved": achieved, "peak": hbm_peak, "peak_kind": peak_kind,
+            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_pass_ms, "launches": npasses,
+            "gates_per_pass": args.steps * ngates / max(npasses, 1),
+            "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    line = {
+        "metric": "gates_per_sec", "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(1, n),
+        "roofline": roof, "clocks": clocks,
+        "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": c["bytes_h2d"] / args.steps,
+                "d2h_bytes_per_step": c["bytes_d2h"] / args.steps, "ms_per_step": 1e3 * wall / args.steps},
+        "gpu_launches": int(c["launches"]), "gates_per_step": ngates,
+        "readout_z0": [float(z[0][0]), float(z[0][1])],
+    }
+    if args.depth != C3_DEPTH or n != C3_QUBITS:
+        line["config"]["workload"] += " [NON-DEFAULT size: depth %d, %d qubits]" % (args.depth, n)
+    st.close()
+    del st
+    torch.cuda.empty_cache()
+
+    if not args.no_cpu:
+        n_cpu = pick_cpu_qubits(n)
+        cg = gates if n_cpu == n else pkg.circuits.c3_circuit(n=n_cpu, depth=2, seed=C3_SEED)
+        gps, ng, thr, dt = cpu_sample(n_cpu, cg, 15.0)
+        line["cpu_baseline"] = {"value": gps * 2.0 ** (n_cpu - 30), "unit": unit, "cores": thr, "kind": "port",
+                                "sample": "first %d gates of the same circuit at %d qubits from |0..0> "
+                                          "(%.1f s of oracle/qsim_oracle.c, OpenMP)" % (ng, n_cpu, dt)}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,7 +62,8 @@ enum {
     QM_OPT_LOW_BITS   = 2,  /* contiguous low bits every tile keeps (default 5: 512-byte rows)                    */
     QM_OPT_FUSE       = 3,  /* 0: planner emits one pass per gate (debug), 1: fuse (default)                      */
     QM_OPT_REMAP      = 4,  /* 1: planner may relabel qubits inside a pass (logical->physical permutation)        */
-    QM_OPT_PIPELINE   = 5   /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel (default)           */
+    QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel                     */
+    QM_OPT_MAX_COST   = 6   /* planner: cap on a pass's arithmetic, in FP64 FMAs per amplitude (0 = no cap)       */
 };
 
 typedef struct qm_state qm_state;
@@ -83,6 +84,8 @@ typedef struct qm_counters_t {
     uint64_t launches;       /* kernels launched (all kinds)                    */
     uint64_t bytes_hbm;      /* algorithmic HBM bytes of those passes/readouts  */
     uint64_t bytes_link;     /* bytes sent over NVLink by remaps (this rank)    */
+    uint64_t bytes_h2d;      /* host->device bytes copied (pass programs, slots, uploads) */
+    uint64_t bytes_d2h;      /* device->host bytes copied (readouts, downloads)  */
     double   ms_device;      /* CUDA-event time of the last flushed circuit     */
     double   ms_plan;        /* host planning time of the last flushed circuit  */
 } qm_counters_t;
@@ -137,6 +140,10 @@ int32_t qm_apply_batched(qm_state* st, const qm_gate* gates, int32_t ngates,
 int32_t qm_probs(qm_state* st, double* out_host, int32_t batch_idx);
 int32_t qm_measure(qm_state* st, int32_t basis, int32_t t0, double threshold, int32_t batch_idx,
                    double out[2]);
+/* qm_measure with the caller's own rotation matrix R (Julia passes H or rx_gate(pi/2) so that the
+ * matrix bits are the host's; R == NULL means no rotation, i.e. the Z basis) */
+int32_t qm_measure_with(qm_state* st, int32_t t0, const double* R, double threshold, int32_t batch_idx,
+                        double out[2]);
 int32_t qm_expect_z_all(qm_state* st, double threshold, double* out_host);
 int32_t qm_expect_all(qm_state* st, int32_t basis, double threshold, double* out_host);
 int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k, int32_t batch_idx,
@@ -163,6 +170,13 @@ int32_t qm_create_dist(int32_t n_qubits, uint64_t basis_index, int32_t device, i
 int32_t qm_plan_describe(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
                          int32_t allow_remap, const qm_gate* gates, int32_t ngates,
                          int32_t* out, int64_t cap, int64_t* out_len);
+
+/* The same plan as a flat gate list in execution order (wire format on physical bits, after
+ * merging): applying `out` one gate at a time must equal applying `gates` in their given order.
+ * pass_of[i] receives the pass index of out[i] (may be NULL). */
+int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
+                      double max_cost, const qm_gate* gates, int32_t ngates, qm_gate* out,
+                      int32_t* pass_of, int32_t cap, int32_t* out_len);
 
 /* ---- misc ---------------------------------------------------------------------------- */
 int32_t qm_sync(qm_state* st);

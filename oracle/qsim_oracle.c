@@ -272,11 +272,14 @@ void orc_reduced_density(const double* s, int n, int keep_low, int k, double* ou
 
 /* ---- sampler (no reference counterpart: "parity unpinned"; this file DEFINES it) --------------
  * Shot s draws u_s = (splitmix64(seed + s) >> 11) * 2^-53 and returns the first index whose
- * cumulative probability exceeds u_s * total, where the cumulative sum is taken over a fixed
- * 3-level structure: leaves of 4096 consecutive probabilities summed left to right, then groups
- * of 4096 leaves summed left to right, and so on.  The search descends level by level,
- * subtracting the prefix it skipped.  Every sum is an IEEE double add in that order, so the GPU
- * kernel reproduces it bit for bit. */
+ * cumulative probability exceeds u_s * total.  The cumulative sum is taken over a fixed 4-level
+ * structure of 4096-ary "leaves".  A leaf sum is defined the way a 32-lane warp computes it:
+ * lane l adds elements l, l+32, l+64, ... left to right, then the 32 lane sums are combined by an
+ * xor butterfly (offsets 16, 8, 4, 2, 1; IEEE addition is commutative, so every lane ends with the
+ * same bits).  Level k+1 applies the same rule to the level-k sums.  The search descends level by
+ * level with plain left-to-right partial sums, subtracting the prefix it skipped.  Every
+ * operation is a single IEEE double add/multiply in a fixed order, so the GPU kernel
+ * (quromorphic.jl_b200/csrc/kernels.cuh k_leafsum / k_sample) reproduces it bit for bit. */
 static inline uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -286,47 +289,55 @@ static inline uint64_t splitmix64(uint64_t x) {
 uint64_t orc_splitmix64(uint64_t x) { return splitmix64(x); }
 
 #define LEAF 4096ull
+/* leaf sum over elements [lo, lo + LEAF) of either abs2(amplitudes) or a double array; elements
+ * at or beyond n count as 0 */
+static double leaf_sum(const cplx* a, const double* v, uint64_t lo, uint64_t n) {
+    double lane[32];
+    for (int l = 0; l < 32; ++l) {
+        double acc = 0.0;
+        for (uint64_t j = 0; j < LEAF / 32; ++j) {
+            uint64_t i = lo + 32 * j + (uint64_t)l;
+            double x = 0.0;
+            if (i < n) x = a ? abs2(a[i]) : v[i];
+            acc += x;
+        }
+        lane[l] = acc;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        double nxt[32];
+        for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ o];
+        memcpy(lane, nxt, sizeof(lane));
+    }
+    return lane[0];
+}
+
 void orc_sample(const double* s, int n, uint64_t seed, int nshots, uint64_t* out) {
     const cplx* a = (const cplx*)s;
     uint64_t N = 1ull << n;
-    /* level sums */
     uint64_t n1 = (N + LEAF - 1) / LEAF, n2 = (n1 + LEAF - 1) / LEAF, n3 = (n2 + LEAF - 1) / LEAF;
     double* s1 = (double*)malloc(sizeof(double) * n1);
     double* s2 = (double*)malloc(sizeof(double) * n2);
     double* s3 = (double*)malloc(sizeof(double) * n3);
 #pragma omp parallel for schedule(static) if (n >= 16)
-    for (uint64_t c = 0; c < n1; ++c) {
-        double acc = 0.0; uint64_t hi = (c + 1) * LEAF < N ? (c + 1) * LEAF : N;
-        for (uint64_t i = c * LEAF; i < hi; ++i) acc += abs2(a[i]);
-        s1[c] = acc;
-    }
-    for (uint64_t c = 0; c < n2; ++c) {
-        double acc = 0.0; uint64_t hi = (c + 1) * LEAF < n1 ? (c + 1) * LEAF : n1;
-        for (uint64_t i = c * LEAF; i < hi; ++i) acc += s1[i];
-        s2[c] = acc;
-    }
+    for (uint64_t c = 0; c < n1; ++c) s1[c] = leaf_sum(a, 0, c * LEAF, N);
+    for (uint64_t c = 0; c < n2; ++c) s2[c] = leaf_sum(0, s1, c * LEAF, n1);
+    for (uint64_t c = 0; c < n3; ++c) s3[c] = leaf_sum(0, s2, c * LEAF, n2);
     double total = 0.0;
-    for (uint64_t c = 0; c < n3; ++c) {
-        double acc = 0.0; uint64_t hi = (c + 1) * LEAF < n2 ? (c + 1) * LEAF : n2;
-        for (uint64_t i = c * LEAF; i < hi; ++i) acc += s2[i];
-        s3[c] = acc;
-    }
     for (uint64_t c = 0; c < n3; ++c) total += s3[c];
     for (int sh = 0; sh < nshots; ++sh) {
         double u = (double)(splitmix64(seed + (uint64_t)sh) >> 11) * 0x1.0p-53;
         double r = u * total;
-        /* level 3 */
         uint64_t i3 = 0; double acc = 0.0;
-        for (; i3 + 1 < n3; ++i3) { if (acc + s3[i3] > r) break; acc += s3[i3]; }
+        for (; i3 + 1 < n3; ++i3) { double t = acc + s3[i3]; if (t > r) break; acc = t; }
         r -= acc; acc = 0.0;
         uint64_t i2 = i3 * LEAF, e2 = (i3 + 1) * LEAF < n2 ? (i3 + 1) * LEAF : n2;
-        for (; i2 + 1 < e2; ++i2) { if (acc + s2[i2] > r) break; acc += s2[i2]; }
+        for (; i2 + 1 < e2; ++i2) { double t = acc + s2[i2]; if (t > r) break; acc = t; }
         r -= acc; acc = 0.0;
         uint64_t i1 = i2 * LEAF, e1 = (i2 + 1) * LEAF < n1 ? (i2 + 1) * LEAF : n1;
-        for (; i1 + 1 < e1; ++i1) { if (acc + s1[i1] > r) break; acc += s1[i1]; }
+        for (; i1 + 1 < e1; ++i1) { double t = acc + s1[i1]; if (t > r) break; acc = t; }
         r -= acc; acc = 0.0;
         uint64_t i0 = i1 * LEAF, e0 = (i1 + 1) * LEAF < N ? (i1 + 1) * LEAF : N;
-        for (; i0 + 1 < e0; ++i0) { double p = abs2(a[i0]); if (acc + p > r) break; acc += p; }
+        for (; i0 + 1 < e0; ++i0) { double t = acc + abs2(a[i0]); if (t > r) break; acc = t; }
         out[sh] = i0;
     }
     free(s1); free(s2); free(s3);

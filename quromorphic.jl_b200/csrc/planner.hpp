@@ -1,0 +1,386 @@
+// planner.hpp — host-side pass planner of the B200 state-vector engine (no CUDA in this file).
+//
+// Turns a gate list (include/qm_b200.h qm_gate, 0-based textbook bits) into a sequence of
+//   * fused HBM passes: every pass names a TILE of m index bits (the L lowest bits, so that
+//     every row of a tile is 2^L contiguous amplitudes, plus m-L higher bits) and a list of
+//     register-block GROUPS; each group names <= 3 tile bits held in registers and the gates
+//     ("subs") applied while they are there, and
+//   * (sharded registers only) REMAP steps that exchange the global qubits with the top local
+//     ones by an all-to-all.
+//
+// What the reference does instead: one dense 2^n x 2^n kron operator and a matrix-vector
+// product per gate (QSim.jl:52-63, :175-203).  The algebra below only uses facts about that
+// operator: a gate touches the amplitudes pairwise along its target bit; a control bit or a
+// diagonal target never needs to be resident in the tile (it is a predicate / a phase), and two
+// gates commute when every qubit they share is acted on diagonally by both.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/qm_b200.h"
+
+namespace qm {
+
+static const int kMaxTileBits = 13;
+static const int kBlockBits = 3;        // amplitudes per thread = 2^3
+static const int kMaxSubsPerPass = 160;
+
+// ---- device-visible encodings (plain structs, copied byte for byte) -----------------------
+enum { SUB_MAT = 0, SUB_DIAG = 1 };
+
+struct DevSub {
+    int32_t  kind;       // SUB_MAT | SUB_DIAG
+    int32_t  b;          // MAT: block bit 0..2 of the target.  DIAG: 0..2 block bit, 3 tile-local bit, 4 outer bit
+    uint32_t cmask_blk;  // control bits among the block bits (bit i = block bit i)
+    uint32_t cmask_loc;  // control bits among the other tile-local bits
+    uint64_t cmask_out;  // control bits outside the tile (mask on the global amplitude index)
+    uint32_t tmask_loc;  // DIAG b==3: tile-local mask of the target bit
+    int32_t  slot;       // >= 0: matrix comes from per-state slot (batched), else -1
+    uint64_t tmask_out;  // DIAG b==4: global-index mask of the target bit
+    double   m[8];       // U11 U21 U12 U22 (re, im) — Julia memory order
+    uint64_t pad_;
+};
+static_assert(sizeof(DevSub) == 112, "DevSub layout");
+
+struct DevGroup {
+    int32_t  nsub, sub_off;
+    uint32_t rbmask[3];  // tile-local masks of the block bits (0 = unused)
+    int32_t  nfree;      // m - (number of block bits)
+    uint8_t  fpos[16];   // tile-local bit position of thread-index bit j
+    uint32_t pad_[2];
+};
+static_assert(sizeof(DevGroup) == 48, "DevGroup layout");
+
+struct DevPass {
+    int32_t m, L, nhigh, ngroups;
+    int32_t nsubs, total_bytes, flags, pad_;
+    int32_t hb[16];      // physical bit of tile-local bit L + j
+};
+static_assert(sizeof(DevPass) == 96, "DevPass layout");
+
+// ---- planner-side structures ---------------------------------------------------------------
+struct LGate {           // lowered gate on PHYSICAL index bits
+    int target;
+    int ctrl;            // -1 = none
+    bool diag;
+    int slot;            // -1 = none
+    double m[8];
+};
+
+struct PlanSub { LGate g; };
+struct PlanGroup { std::vector<int> rb; std::vector<LGate> subs; };
+struct PlanPass {
+    int m = 0, L = 0;
+    std::vector<int> hb;
+    std::vector<PlanGroup> groups;
+    int ngates = 0;
+    double cost = 0.0;   // estimated DFMA-equivalents per amplitude
+};
+struct PlanStep {
+    int kind = 0;        // 0 = pass, 1 = remap (swap global bits with the top local bits)
+    PlanPass pass;
+};
+
+struct PlanOptions {
+    int n_local = 0;     // index bits resident on this rank
+    int n_global = 0;    // sharded (rank) bits above them
+    int tile_bits = 12;
+    int low_bits = 5;
+    bool fuse = true;
+    int window = 768;    // look-ahead, in gates
+    double max_cost = 1e30;
+};
+
+inline bool mat_is_diag(const double* m) { return m[2] == 0.0 && m[3] == 0.0 && m[4] == 0.0 && m[5] == 0.0; }
+inline bool mat_is_identity(const double* m) {
+    return mat_is_diag(m) && m[0] == 1.0 && m[1] == 0.0 && m[6] == 1.0 && m[7] == 0.0;
+}
+
+// C = A * B for 2x2 complex in Julia order (U11 U21 U12 U22)
+inline void mat_mul(const double* A, const double* B, double* C) {
+    auto at = [](const double* M, int r, int c, double& re, double& im) { re = M[(c * 2 + r) * 2]; im = M[(c * 2 + r) * 2 + 1]; };
+    double out[8];
+    for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 2; ++c) {
+            double sr = 0, si = 0;
+            for (int k = 0; k < 2; ++k) {
+                double ar, ai, br, bi; at(A, r, k, ar, ai); at(B, k, c, br, bi);
+                sr += ar * br - ai * bi; si += ar * bi + ai * br;
+            }
+            out[(c * 2 + r) * 2] = sr; out[(c * 2 + r) * 2 + 1] = si;
+        }
+    memcpy(C, out, sizeof(out));
+}
+
+static const double kXmat[8] = { 0, 0, 1, 0, 1, 0, 0, 0 };
+
+// Lower wire gates to LGates on physical bits (perm[logical] = physical), merging runs of
+// uncontrolled 1-qubit gates on the same qubit into one matrix when `fuse` is set.
+inline int lower_gates(const qm_gate* gates, int ng, int nbits, const int* perm, bool fuse,
+                       std::vector<LGate>& out) {
+    std::vector<int> pending(nbits, -1);   // index in `out` of a still-mergeable 1q gate per physical bit
+    auto touch = [&](int bit) { pending[bit] = -1; };
+    for (int i = 0; i < ng; ++i) {
+        const qm_gate& w = gates[i];
+        switch (w.kind) {
+        case QM_GATE_U2: case QM_GATE_U2_SLOT: {
+            if (w.q0 < 0 || w.q0 >= nbits) return QM_ERR_ARG;
+            int t = perm ? perm[w.q0] : w.q0;
+            LGate g; g.target = t; g.ctrl = -1; g.slot = (w.kind == QM_GATE_U2_SLOT) ? w.q1 : -1;
+            memcpy(g.m, w.m, sizeof(g.m));
+            g.diag = (g.slot < 0) && mat_is_diag(g.m);
+            if (fuse && g.slot < 0 && pending[t] >= 0) {
+                LGate& p = out[pending[t]];
+                mat_mul(g.m, p.m, p.m);                 // later gate multiplies from the left
+                p.diag = mat_is_diag(p.m);
+            } else {
+                out.push_back(g);
+                pending[t] = (g.slot < 0 && fuse) ? (int)out.size() - 1 : -1;
+            }
+            break;
+        }
+        case QM_GATE_CU2: {
+            if (w.q0 < 0 || w.q0 >= nbits || w.q1 < 0 || w.q1 >= nbits || w.q0 == w.q1) return QM_ERR_ARG;
+            LGate g; g.ctrl = perm ? perm[w.q0] : w.q0; g.target = perm ? perm[w.q1] : w.q1; g.slot = -1;
+            memcpy(g.m, w.m, sizeof(g.m)); g.diag = mat_is_diag(g.m);
+            touch(g.ctrl); touch(g.target);
+            out.push_back(g);
+            break;
+        }
+        case QM_GATE_SWAP: {
+            if (w.q0 < 0 || w.q0 >= nbits || w.q1 < 0 || w.q1 >= nbits) return QM_ERR_ARG;
+            if (w.q0 == w.q1) break;                    // swap!(s,q,q) is a no-op, QSim.jl:266-268
+            int a = perm ? perm[w.q0] : w.q0, b = perm ? perm[w.q1] : w.q1;
+            touch(a); touch(b);
+            for (int k = 0; k < 3; ++k) {               // three CNOTs, QSim.jl:270-272
+                LGate g; g.ctrl = (k == 1) ? b : a; g.target = (k == 1) ? a : b; g.slot = -1; g.diag = false;
+                memcpy(g.m, kXmat, sizeof(g.m));
+                out.push_back(g);
+            }
+            break;
+        }
+        default: return QM_ERR_ARG;
+        }
+    }
+    // drop merged identities (e.g. X*X): exact no-ops
+    if (fuse) {
+        size_t w = 0;
+        for (size_t i = 0; i < out.size(); ++i)
+            if (!(out[i].ctrl < 0 && out[i].slot < 0 && mat_is_identity(out[i].m))) out[w++] = out[i];
+        out.resize(w);
+    }
+    return QM_OK;
+}
+
+inline double gate_cost(const LGate& g) {
+    double c = g.diag ? 4.0 : 8.0;     // DFMA-equivalents per amplitude
+    return g.ctrl >= 0 ? 0.5 * c : c;
+}
+
+// Commutation-aware pull: walk the not-yet-done gates in order; take a gate when no earlier
+// skipped gate blocks it and its (non-diagonal) target is allowed.  allowed(target, dry) may
+// extend the allowed set on the fly (used for the <=3-bit register blocks).
+template <class Allowed>
+inline void pull(const std::vector<LGate>& g, const std::vector<char>& done, size_t first, int window,
+                 uint64_t all_bits, double max_cost, int max_take, Allowed&& allowed, std::vector<int>& taken) {
+    uint64_t blockedN = 0, blockedD = 0;
+    int scanned = 0; double cost = 0;
+    for (size_t i = first; i < g.size() && scanned < window; ++i) {
+        if (done[i]) continue;
+        ++scanned;
+        const LGate& x = g[i];
+        uint64_t tm = 1ull << x.target, cm = x.ctrl >= 0 ? (1ull << x.ctrl) : 0ull;
+        uint64_t actsN = x.diag ? 0ull : tm, actsD = cm | (x.diag ? tm : 0ull);
+        bool free_ = !((actsN | actsD) & blockedN) && !(actsN & blockedD);
+        bool take = false;
+        if (free_ && (int)taken.size() < max_take && cost + gate_cost(x) <= max_cost)
+            take = x.diag || allowed(x.target);
+        if (take) { taken.push_back((int)i); cost += gate_cost(x); }
+        else {
+            blockedN |= actsN; blockedD |= actsD;
+            if ((blockedN & all_bits) == all_bits) break;
+        }
+    }
+}
+
+struct Planner {
+    PlanOptions opt;
+    std::vector<LGate> gates;
+    std::vector<char> done;
+    size_t first = 0;
+
+    int total_bits() const { return opt.n_local + opt.n_global; }
+
+    // non-diagonal targets still pending on global (sharded) bits?
+    bool pending_global_target() const {
+        for (size_t i = first; i < gates.size(); ++i)
+            if (!done[i] && !gates[i].diag && gates[i].target >= opt.n_local) return true;
+        return false;
+    }
+
+    std::vector<int> tile_bits_for(const std::vector<int>& hb, int L) const {
+        std::vector<int> t; for (int i = 0; i < L; ++i) t.push_back(i);
+        t.insert(t.end(), hb.begin(), hb.end()); return t;
+    }
+
+    int count_with(uint64_t tilemask) const {
+        std::vector<int> taken;
+        pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, kMaxSubsPerPass,
+             [&](int t) { return (tilemask >> t) & 1; }, taken);
+        return (int)taken.size();
+    }
+
+    // choose the high tile bits for the next pass
+    void choose_tile(int m, int L, std::vector<int>& hb_best, int& best) const {
+        const int nl = opt.n_local, nh = m - L;
+        hb_best.clear(); best = -1;
+        if (nh <= 0) { best = count_with((1ull << L) - 1); return; }
+        uint64_t low = (1ull << L) - 1;
+        auto try_set = [&](const std::vector<int>& hb) {
+            uint64_t mask = low; for (int b : hb) mask |= 1ull << b;
+            int c = count_with(mask);
+            if (c > best) { best = c; hb_best = hb; }
+        };
+        // (1) greedy: the first nh distinct non-diagonal high local targets in dependency order
+        {
+            std::vector<int> hb; uint64_t have = low;
+            std::vector<int> taken;
+            pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, 1e30, 1 << 30,
+                 [&](int t) {
+                     if (t >= nl) return false;
+                     if ((have >> t) & 1) return true;
+                     if ((int)hb.size() < nh) { hb.push_back(t); have |= 1ull << t; return true; }
+                     return false;
+                 }, taken);
+            for (int b = L; b < nl && (int)hb.size() < nh; ++b) if (!((have >> b) & 1)) { hb.push_back(b); have |= 1ull << b; }
+            std::sort(hb.begin(), hb.end());
+            try_set(hb);
+        }
+        // (2) contiguous windows
+        for (int a = L; a + nh <= nl; ++a) {
+            std::vector<int> hb; for (int j = 0; j < nh; ++j) hb.push_back(a + j);
+            try_set(hb);
+        }
+    }
+
+    // Build the next pass.  Returns false when nothing can be pulled (only global targets left).
+    bool next_pass(PlanPass& P) {
+        while (first < gates.size() && done[first]) ++first;
+        if (first >= gates.size()) return false;
+        const int nl = opt.n_local;
+        int m = std::min(opt.tile_bits, nl); if (m > kMaxTileBits) m = kMaxTileBits;
+        int L = std::min(opt.low_bits, m);
+        std::vector<int> hb; int best = 0;
+        if (!opt.fuse) {
+            // debug mode: one gate per pass
+            const LGate& x = gates[first];
+            if (!x.diag && x.target >= nl) return false;
+            if (m > L) {
+                for (int b = L; b < nl && (int)hb.size() < m - L; ++b) hb.push_back(b);
+                if (!x.diag && x.target >= L && std::find(hb.begin(), hb.end(), x.target) == hb.end()) hb.back() = x.target;
+                std::sort(hb.begin(), hb.end());
+            }
+            P = PlanPass(); P.m = m; P.L = L; P.hb = hb;
+            PlanGroup G; if (!x.diag) G.rb.push_back(x.target);
+            G.subs.push_back(x); P.groups.push_back(G); P.ngates = 1; P.cost = gate_cost(x);
+            done[first] = 1;
+            return true;
+        }
+        choose_tile(m, L, hb, best);
+        if (best <= 0) return false;
+        uint64_t tilemask = (1ull << L) - 1; for (int b : hb) tilemask |= 1ull << b;
+        std::vector<int> taken;
+        pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, kMaxSubsPerPass,
+             [&](int t) { return (tilemask >> t) & 1; }, taken);
+        P = PlanPass(); P.m = m; P.L = L; P.hb = hb; P.ngates = (int)taken.size();
+        std::vector<LGate> pg; pg.reserve(taken.size());
+        for (int i : taken) { pg.push_back(gates[i]); done[i] = 1; P.cost += gate_cost(gates[i]); }
+        // register-block groups: same pull with an allowed set that grows up to 3 bits
+        std::vector<char> d2(pg.size(), 0); size_t f2 = 0;
+        while (true) {
+            while (f2 < pg.size() && d2[f2]) ++f2;
+            if (f2 >= pg.size()) break;
+            PlanGroup G; uint64_t have = 0;
+            std::vector<int> tk;
+            pull(pg, d2, f2, 1 << 30, (1ull << total_bits()) - 1, 1e30, 1 << 30,
+                 [&](int t) {
+                     if ((have >> t) & 1) return true;
+                     if ((int)G.rb.size() < kBlockBits) { G.rb.push_back(t); have |= 1ull << t; return true; }
+                     return false;
+                 }, tk);
+            for (int i : tk) { G.subs.push_back(pg[i]); d2[i] = 1; }
+            std::sort(G.rb.begin(), G.rb.end());
+            P.groups.push_back(G);
+        }
+        return true;
+    }
+};
+
+// physical bit -> tile-local bit (or -1)
+inline int tile_local_of(const PlanPass& P, int phys) {
+    if (phys < P.L) return phys;
+    for (size_t j = 0; j < P.hb.size(); ++j) if (P.hb[j] == phys) return P.L + (int)j;
+    return -1;
+}
+
+// Encode one pass into the byte blob the kernel reads: DevPass | DevGroup[] | DevSub[]
+inline void encode_pass(const PlanPass& P, std::vector<unsigned char>& blob) {
+    DevPass hp; memset(&hp, 0, sizeof(hp));
+    hp.m = P.m; hp.L = P.L; hp.nhigh = (int)P.hb.size(); hp.ngroups = (int)P.groups.size();
+    for (size_t j = 0; j < P.hb.size(); ++j) hp.hb[j] = P.hb[j];
+    std::vector<DevGroup> dg; std::vector<DevSub> ds;
+    for (const PlanGroup& G : P.groups) {
+        DevGroup g; memset(&g, 0, sizeof(g));
+        g.sub_off = (int)ds.size(); g.nsub = (int)G.subs.size();
+        uint32_t blockmask = 0; int rbl[3] = { -1, -1, -1 };
+        for (size_t i = 0; i < G.rb.size(); ++i) { rbl[i] = tile_local_of(P, G.rb[i]); g.rbmask[i] = 1u << rbl[i]; blockmask |= g.rbmask[i]; }
+        g.nfree = P.m - (int)G.rb.size();
+        // thread-index bit order: the three lowest thread bits must give distinct 16-byte bank
+        // groups under the layout slot = i ^ ((i >> 3) & 7): bit k of the slot's low 3 bits is
+        // i_k ^ i_{k+3}, so pick a free bit from {k, k+3} for k = 0, 1, 2.
+        std::vector<int> order; uint32_t used = blockmask;
+        for (int k = 0; k < 3; ++k) {
+            int pick = -1;
+            if (k < P.m && !((used >> k) & 1)) pick = k;
+            else if (k + 3 < P.m && !((used >> (k + 3)) & 1)) pick = k + 3;
+            if (pick >= 0) { order.push_back(pick); used |= 1u << pick; }
+        }
+        for (int b = 0; b < P.m; ++b) if (!((used >> b) & 1)) { order.push_back(b); used |= 1u << b; }
+        for (size_t j = 0; j < order.size() && j < 16; ++j) g.fpos[j] = (uint8_t)order[j];
+        for (const LGate& x : G.subs) {
+            DevSub s; memset(&s, 0, sizeof(s));
+            s.slot = x.slot; memcpy(s.m, x.m, sizeof(s.m));
+            if (x.ctrl >= 0) {
+                int cl = tile_local_of(P, x.ctrl);
+                if (cl < 0) s.cmask_out = 1ull << x.ctrl;
+                else {
+                    int bi = -1; for (int i = 0; i < 3; ++i) if (rbl[i] == cl) bi = i;
+                    if (bi >= 0) s.cmask_blk = 1u << bi; else s.cmask_loc = 1u << cl;
+                }
+            }
+            int tl = tile_local_of(P, x.target);
+            int bi = -1; if (tl >= 0) for (int i = 0; i < 3; ++i) if (rbl[i] == tl) bi = i;
+            if (!x.diag) { s.kind = SUB_MAT; s.b = bi; }
+            else {
+                s.kind = SUB_DIAG;
+                if (bi >= 0) s.b = bi;
+                else if (tl >= 0) { s.b = 3; s.tmask_loc = 1u << tl; }
+                else { s.b = 4; s.tmask_out = 1ull << x.target; }
+            }
+            ds.push_back(s);
+        }
+        dg.push_back(g);
+    }
+    hp.nsubs = (int)ds.size();
+    hp.total_bytes = (int)(sizeof(DevPass) + dg.size() * sizeof(DevGroup) + ds.size() * sizeof(DevSub));
+    size_t off = blob.size();
+    blob.resize(off + (size_t)hp.total_bytes);
+    memcpy(&blob[off], &hp, sizeof(hp)); off += sizeof(hp);
+    if (!dg.empty()) memcpy(&blob[off], dg.data(), dg.size() * sizeof(DevGroup));
+    off += dg.size() * sizeof(DevGroup);
+    if (!ds.empty()) memcpy(&blob[off], ds.data(), ds.size() * sizeof(DevSub));
+}
+
+}  // namespace qm

@@ -1,0 +1,672 @@
+// qm_api.cu — the C ABI of include/qm_b200.h: state handle, gate queue, pass launches, readouts.
+// There is NO CPU fallback here: without a CUDA device every state-creating call returns
+// QM_ERR_NO_DEVICE.  The only GPU-free entry points are the planner introspection and version.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/qm_b200.h"
+#include "dist.hpp"
+#include "kernels.cuh"
+#include "planner.hpp"
+#include "state.hpp"
+
+using namespace qm;
+
+static thread_local char g_err[512] = "";
+int set_err(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+
+int ensure_dev(void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return QM_OK;
+    if (*p) CU(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    size_t c = need < 4096 ? 4096 : need;
+    CU(cudaMalloc(p, c)); *cap = c;
+    return QM_OK;
+}
+int ensure_pinned(void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return QM_OK;
+    if (*p) CU(cudaFreeHost(*p));
+    *p = nullptr; *cap = 0;
+    size_t c = need < 4096 ? 4096 : need;
+    CU(cudaMallocHost(p, c)); *cap = c;
+    return QM_OK;
+}
+
+
+static int grid_for(uint64_t work_items, int threads, int sms, int per_sm) {
+    uint64_t blocks = (work_items + threads - 1) / threads;
+    uint64_t cap = (uint64_t)sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+static int create_common(int n, uint64_t basis, int batch, int device, int rank, int world, qm_state** out) {
+    if (!out) return set_err(QM_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n < 1 || n > 62) return set_err(QM_ERR_ARG, "n_qubits %d out of range", n);
+    if (batch < 1) return set_err(QM_ERR_ARG, "batch must be >= 1");
+    int g = 0; while ((1 << g) < world) ++g;
+    if ((1 << g) != world || rank < 0 || rank >= world) return set_err(QM_ERR_ARG, "world must be a power of two, 0 <= rank < world");
+    if (g >= n) return set_err(QM_ERR_ARG, "more ranks than amplitudes");
+    if (world > 1 && batch != 1) return set_err(QM_ERR_ARG, "sharded registers are not batched");
+    if (basis >> n) return set_err(QM_ERR_ARG, "basis index out of range");   // statevector(n,m): BoundsError, QSim.jl:35
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return set_err(QM_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return set_err(QM_ERR_ARG, "device %d of %d", device, ndev);
+    CU(cudaSetDevice(device));
+    qm_state* st = new qm_state();
+    st->n = n; st->g = g; st->nl = n - g; st->rank = rank; st->world = world; st->batch = batch; st->device = device;
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    st->sms = prop.multiProcessorCount;
+    st->perm.resize(n); for (int i = 0; i < n; ++i) st->perm[i] = i;
+    size_t bytes = (size_t)total_amps(st) * 16;
+    cudaError_t e = cudaMalloc((void**)&st->amp, bytes);
+    if (e != cudaSuccess) { delete st; return set_err(QM_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    CU(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&st->ev0)); CU(cudaEventCreate(&st->ev1));
+    CU(cudaEventCreateWithFlags(&st->ev_stage, cudaEventDisableTiming));
+    *out = st;
+    return qm_reset(st, basis);
+}
+
+extern "C" int32_t qm_create(int32_t n, uint64_t basis, int32_t batch, int32_t device, qm_state** out) {
+    return create_common(n, basis, batch, device, 0, 1, out);
+}
+
+extern "C" int32_t qm_destroy(qm_state* st) {
+    if (!st) return QM_OK;
+    cudaSetDevice(st->device);
+    if (st->stream) cudaStreamSynchronize(st->stream);
+    if (st->dist) { dist_destroy(st->dist); st->dist = nullptr; }
+    cudaFree(st->amp); cudaFree(st->d_blob); cudaFree(st->d_scratch); cudaFree(st->d_slots);
+    cudaFreeHost(st->h_blob); cudaFreeHost(st->h_scratch);
+    if (st->ev0) cudaEventDestroy(st->ev0);
+    if (st->ev1) cudaEventDestroy(st->ev1);
+    if (st->ev_stage) cudaEventDestroy(st->ev_stage);
+    if (st->stream) cudaStreamDestroy(st->stream);
+    delete st;
+    return QM_OK;
+}
+
+extern "C" int32_t qm_reset(qm_state* st, uint64_t basis) {
+    if (!st) return set_err(QM_ERR_ARG, "null state");
+    if (basis >> st->n) return set_err(QM_ERR_ARG, "basis index out of range");
+    CU(cudaSetDevice(st->device));
+    st->queue.clear();
+    for (int i = 0; i < st->n; ++i) st->perm[i] = i;
+    CU(cudaMemsetAsync(st->amp, 0, (size_t)total_amps(st) * 16, st->stream));
+    uint64_t owner = st->g ? (basis >> st->nl) : 0;
+    if ((int)owner == st->rank) {
+        uint64_t local = basis & (local_amps(st) - 1);
+        k_set_basis<<<(st->batch + 255) / 256, 256, 0, st->stream>>>(st->amp, local_amps(st), st->batch, local);
+        CU(cudaGetLastError());
+        st->ctr.launches++;
+    }
+    return QM_OK;
+}
+
+extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
+    if (!st) return set_err(QM_ERR_ARG, "null state");
+    switch (key) {
+    case QM_OPT_EAGER: st->eager = value != 0; break;
+    case QM_OPT_TILE_BITS:
+        if (value < 4 || value > kMaxTileBits) return set_err(QM_ERR_ARG, "tile bits must be in [4, %d]", kMaxTileBits);
+        st->tile_bits = (int)value; break;
+    case QM_OPT_LOW_BITS:
+        if (value < 0 || value > 8) return set_err(QM_ERR_ARG, "low bits must be in [0, 8]");
+        st->low_bits = (int)value; break;
+    case QM_OPT_FUSE: st->fuse = value != 0; break;
+    case QM_OPT_REMAP: st->remap = value != 0; break;
+    case QM_OPT_PIPELINE: st->pipeline = value != 0; break;
+    case QM_OPT_MAX_COST: st->max_cost = (double)value; break;
+    default: return set_err(QM_ERR_ARG, "unknown option %d", key);
+    }
+    return QM_OK;
+}
+
+extern "C" int32_t qm_num_qubits(const qm_state* st, int32_t* n, int32_t* batch) {
+    if (!st) return set_err(QM_ERR_ARG, "null state");
+    if (n) *n = st->n;
+    if (batch) *batch = st->batch;
+    return QM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gate execution
+// ---------------------------------------------------------------------------------------------
+static int launch_1q(qm_state* st, int tbit, int cbit, const double* m) {
+    // physical bits; control on a sharded bit is a rank predicate, target must be local
+    uint64_t cmask = 0;
+    if (cbit >= st->nl) { if (!((st->rank >> (cbit - st->nl)) & 1)) return QM_OK; }
+    else if (cbit >= 0) cmask = 1ull << cbit;
+    Mat2 U; memcpy(U.v, m, sizeof(U.v));
+    uint64_t npairs = total_amps(st) >> 1;
+    int grid = grid_for(npairs, 256, st->sms, 16);
+    k_apply_1q<<<grid, 256, 0, st->stream>>>(st->amp, npairs, tbit, cmask, U);
+    CU(cudaGetLastError());
+    st->ctr.launches++;
+    st->ctr.bytes_hbm += (cbit >= 0 && cbit < st->nl ? 16ull : 32ull) * total_amps(st);
+    return QM_OK;
+}
+
+static int launch_pass(qm_state* st, const unsigned char* d_pass, const PlanPass& P, const double* d_slots, int nslots) {
+    const int m = P.m;
+    uint64_t ntiles = total_amps(st) >> m;
+    size_t smem = ((size_t)16 << m) + ((size_t)8 << P.hb.size());
+    const int threads = 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(k_fused_pass<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    int per_sm = (int)((220 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
+    uint64_t cap = (uint64_t)st->sms * per_sm;
+    int grid = (int)(ntiles < cap ? ntiles : cap);
+    uint64_t rank_or = st->g ? ((uint64_t)st->rank << st->nl) : 0;
+    k_fused_pass<256><<<grid, threads, smem, st->stream>>>(st->amp, d_pass, d_slots, nslots, ntiles, st->nl, rank_or);
+    CU(cudaGetLastError());
+    st->ctr.launches++; st->ctr.passes++;
+    st->ctr.bytes_hbm += 32ull * total_amps(st);
+    return QM_OK;
+}
+
+// run `gates` (logical qubits) now: plan, upload the pass programs, launch
+static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const double* d_slots, int nslots) {
+    if (ngates <= 0) return QM_OK;
+    CU(cudaSetDevice(st->device));
+    auto t0 = std::chrono::steady_clock::now();
+    if (st->eager) {
+        std::vector<LGate> lg;
+        int rc = lower_gates(gates, ngates, st->n, st->perm.data(), false, lg);
+        if (rc) return set_err(rc, "bad gate in circuit");
+        for (const LGate& x : lg) {
+            if (x.slot >= 0) return set_err(QM_ERR_STATE, "per-state slot gates need the fused path");
+            if (x.target >= st->nl) {
+                if (!x.diag) return set_err(QM_ERR_STATE, "eager mode cannot apply a non-diagonal gate to a sharded qubit");
+                // diagonal on a global bit: a rank-dependent scalar on the controlled half
+                return set_err(QM_ERR_STATE, "eager mode does not handle diagonal gates on sharded qubits");
+            }
+            QM_TRY(launch_1q(st, x.target, x.ctrl, x.m));
+        }
+        st->ctr.gates += ngates;
+        return QM_OK;
+    }
+    Planner pl;
+    pl.opt.n_local = st->nl; pl.opt.n_global = st->g;
+    pl.opt.tile_bits = st->tile_bits; pl.opt.low_bits = st->low_bits; pl.opt.fuse = st->fuse;
+    if (st->max_cost > 0) pl.opt.max_cost = st->max_cost < 8.0 ? 8.0 : st->max_cost;
+    std::vector<PlanPass> passes;          // of the current segment (between remaps)
+    std::vector<unsigned char> blob;
+    std::vector<size_t> offs;
+    int pos = 0;                           // wire gates consumed so far
+    bool first_event = true;
+    while (pos < ngates) {
+        // plan everything that is left under the current qubit map
+        pl.gates.clear(); pl.done.clear(); pl.first = 0;
+        int rc = lower_gates(gates + pos, ngates - pos, st->n, st->perm.data(), st->fuse, pl.gates);
+        if (rc) return set_err(rc, "bad gate in circuit (index >= %d)", pos);
+        pl.done.assign(pl.gates.size(), 0);
+        passes.clear(); blob.clear(); offs.clear();
+        PlanPass P;
+        while (pl.next_pass(P)) {
+            offs.push_back(blob.size());
+            encode_pass(P, blob);
+            while (blob.size() % 16) blob.push_back(0);
+            passes.push_back(P);
+        }
+        bool leftover = false;
+        for (size_t i = pl.first; i < pl.gates.size(); ++i) if (!pl.done[i]) { leftover = true; break; }
+        if (leftover && st->g == 0) return set_err(QM_ERR_STATE, "planner could not place a gate (internal error)");
+        // upload + launch
+        if (!passes.empty()) {
+            QM_TRY(ENSURE_DEV(st, d_blob, blob.size()));
+            if (st->h_blob_cap < blob.size() || true) CU(cudaEventSynchronize(st->ev_stage));   // staging buffer free?
+            QM_TRY(ENSURE_PIN(st, h_blob, blob.size()));
+            memcpy(st->h_blob, blob.data(), blob.size());
+            if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
+            CU(cudaMemcpyAsync(st->d_blob, st->h_blob, blob.size(), cudaMemcpyHostToDevice, st->stream));
+            st->ctr.bytes_h2d += blob.size();
+            CU(cudaEventRecord(st->ev_stage, st->stream));
+            for (size_t i = 0; i < passes.size(); ++i) QM_TRY(launch_pass(st, st->d_blob + offs[i], passes[i], d_slots, nslots));
+        }
+        if (!leftover) break;
+        // sharded: the remaining gates need a non-diagonal target on a global qubit.  The lowered
+        // list does not map 1:1 to wire gates (merging), so the remap path re-plans from the wire
+        // gates that are not finished yet — handled by dist_remap_and_continue.
+        return set_err(QM_ERR_STATE, "gate on a sharded qubit needs a remap (use the dist path)");
+    }
+    if (!first_event) { CU(cudaEventRecord(st->ev1, st->stream)); st->ev_pending = true; }
+    st->ctr.gates += ngates;
+    st->ctr.ms_plan = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return QM_OK;
+}
+
+static int flush(qm_state* st) {
+    if (st->queue.empty()) return QM_OK;
+    std::vector<qm_gate> q; q.swap(st->queue);
+    return run_circuit(st, q.data(), (int)q.size(), nullptr, 0);
+}
+
+static int enqueue(qm_state* st, const qm_gate& g) {
+    st->queue.push_back(g);
+    if (st->eager || st->queue.size() >= 65536) return flush(st);
+    return QM_OK;
+}
+
+static int check_bit(const qm_state* st, int b, const char* what) {
+    if (b < 0 || b >= st->n) return set_err(QM_ERR_ARG, "Qubit index out of range (%s bit %d, n = %d)", what, b, st->n);
+    return QM_OK;
+}
+
+extern "C" int32_t qm_apply_u2(qm_state* st, int32_t t0, const double U[8]) {
+    if (!st || !U) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(check_bit(st, t0, "target"));
+    qm_gate g; g.kind = QM_GATE_U2; g.q0 = t0; g.q1 = 0; g.flags = 0; memcpy(g.m, U, sizeof(g.m));
+    return enqueue(st, g);
+}
+
+extern "C" int32_t qm_apply_controlled(qm_state* st, int32_t c0, int32_t t0, const double V[8]) {
+    if (!st || !V) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(check_bit(st, c0, "control")); QM_TRY(check_bit(st, t0, "target"));
+    if (c0 == t0) return set_err(QM_ERR_ARG, "Control and target cannot be the same qubit");
+    qm_gate g; g.kind = QM_GATE_CU2; g.q0 = c0; g.q1 = t0; g.flags = 0; memcpy(g.m, V, sizeof(g.m));
+    return enqueue(st, g);
+}
+
+extern "C" int32_t qm_apply_swap(qm_state* st, int32_t a0, int32_t b0) {
+    if (!st) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(check_bit(st, a0, "first")); QM_TRY(check_bit(st, b0, "second"));
+    if (a0 == b0) return QM_OK;
+    qm_gate g; memset(&g, 0, sizeof(g)); g.kind = QM_GATE_SWAP; g.q0 = a0; g.q1 = b0;
+    return enqueue(st, g);
+}
+
+static int validate_gates(const qm_state* st, const qm_gate* gates, int ng, int nslots) {
+    for (int i = 0; i < ng; ++i) {
+        const qm_gate& g = gates[i];
+        switch (g.kind) {
+        case QM_GATE_U2: QM_TRY(check_bit(st, g.q0, "target")); break;
+        case QM_GATE_U2_SLOT:
+            QM_TRY(check_bit(st, g.q0, "target"));
+            if (g.q1 < 0 || g.q1 >= nslots) return set_err(QM_ERR_ARG, "gate %d: slot %d of %d", i, g.q1, nslots);
+            break;
+        case QM_GATE_CU2:
+            QM_TRY(check_bit(st, g.q0, "control")); QM_TRY(check_bit(st, g.q1, "target"));
+            if (g.q0 == g.q1) return set_err(QM_ERR_ARG, "Control and target cannot be the same qubit (gate %d)", i);
+            break;
+        case QM_GATE_SWAP: QM_TRY(check_bit(st, g.q0, "first")); QM_TRY(check_bit(st, g.q1, "second")); break;
+        default: return set_err(QM_ERR_ARG, "gate %d: unknown kind %d", i, g.kind);
+        }
+    }
+    return QM_OK;
+}
+
+extern "C" int32_t qm_apply_circuit(qm_state* st, const qm_gate* gates, int32_t ngates) {
+    if (!st || (!gates && ngates > 0) || ngates < 0) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(validate_gates(st, gates, ngates, 0));
+    QM_TRY(flush(st));
+    if (st->dist) return dist_run_circuit(st, gates, ngates);
+    return run_circuit(st, gates, ngates, nullptr, 0);
+}
+
+extern "C" int32_t qm_apply_batched(qm_state* st, const qm_gate* gates, int32_t ngates, const double* per_state_mats,
+                                    int32_t nslots) {
+    if (!st || (!gates && ngates > 0) || ngates < 0 || nslots < 0) return set_err(QM_ERR_ARG, "null argument");
+    if (nslots > 0 && !per_state_mats) return set_err(QM_ERR_ARG, "per_state_mats is null");
+    if (st->dist) return set_err(QM_ERR_STATE, "sharded registers are not batched");
+    QM_TRY(validate_gates(st, gates, ngates, nslots));
+    QM_TRY(flush(st));
+    if (st->eager) return set_err(QM_ERR_STATE, "batched application needs the fused path");
+    CU(cudaSetDevice(st->device));
+    size_t bytes = (size_t)st->batch * nslots * 8 * sizeof(double);
+    if (bytes) {
+        QM_TRY(ENSURE_DEV(st, d_slots, bytes));
+        // the caller's buffer is pageable and must not be retained: the copy below returns only
+        // when the bytes have left the host buffer
+        CU(cudaMemcpyAsync(st->d_slots, per_state_mats, bytes, cudaMemcpyHostToDevice, st->stream));
+        st->ctr.bytes_h2d += bytes;
+    }
+    return run_circuit(st, gates, ngates, bytes ? st->d_slots : nullptr, nslots);
+}
+
+// ---------------------------------------------------------------------------------------------
+// state transfer
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t qm_sync(qm_state* st) {
+    if (!st) return set_err(QM_ERR_ARG, "null state");
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    CU(cudaStreamSynchronize(st->stream));
+    if (st->ev_pending) {
+        float ms = 0.f; CU(cudaEventElapsedTime(&ms, st->ev0, st->ev1));
+        st->ctr.ms_device = ms; st->ev_pending = false;
+    }
+    return QM_OK;
+}
+
+extern "C" int32_t qm_upload(qm_state* st, const double* host, uint64_t n_amps, int32_t batch_idx) {
+    if (!st || !host) return set_err(QM_ERR_ARG, "null argument");
+    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
+    if (n_amps != local_amps(st)) return set_err(QM_ERR_ARG, "expected %llu amplitudes (this rank's shard)", (unsigned long long)local_amps(st));
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    if (st->dist) QM_TRY(dist_canonicalize(st));
+    CU(cudaMemcpyAsync(st->amp + ((uint64_t)batch_idx << st->nl), host, (size_t)n_amps * 16, cudaMemcpyHostToDevice, st->stream));
+    st->ctr.bytes_h2d += n_amps * 16;
+    CU(cudaStreamSynchronize(st->stream));
+    return QM_OK;
+}
+
+extern "C" int32_t qm_download(qm_state* st, double* host, uint64_t n_amps, int32_t batch_idx) {
+    if (!st || !host) return set_err(QM_ERR_ARG, "null argument");
+    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
+    if (n_amps != local_amps(st)) return set_err(QM_ERR_ARG, "expected %llu amplitudes (this rank's shard)", (unsigned long long)local_amps(st));
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    if (st->dist) QM_TRY(dist_canonicalize(st));
+    CU(cudaMemcpyAsync(host, st->amp + ((uint64_t)batch_idx << st->nl), (size_t)n_amps * 16, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += n_amps * 16;
+    QM_TRY(qm_sync(st));
+    return QM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// readouts
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t qm_probs(qm_state* st, double* out_host, int32_t batch_idx) {
+    if (!st || !out_host) return set_err(QM_ERR_ARG, "null argument");
+    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    if (st->dist) QM_TRY(dist_canonicalize(st));
+    uint64_t N = local_amps(st);
+    QM_TRY(ENSURE_DEV(st, d_scratch, (size_t)N * 8));
+    k_probs<<<grid_for(N, 256, st->sms, 16), 256, 0, st->stream>>>(st->amp + ((uint64_t)batch_idx << st->nl), N, st->d_scratch);
+    CU(cudaGetLastError());
+    st->ctr.launches++; st->ctr.bytes_hbm += 24ull * N;
+    CU(cudaMemcpyAsync(out_host, st->d_scratch, (size_t)N * 8, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += N * 8;
+    return qm_sync(st);
+}
+
+// all-qubit z marginals of every register into st->h_scratch: [batch][nl][2] then [batch] totals
+static int zstats(qm_state* st, double thr, double** h_pairs, double** h_tot) {
+    const int nl = st->nl;
+    int cb = nl < kZMaxChunkBits ? nl : kZMaxChunkBits;
+    int rest = nl - cb;                                    // chunk-index bits per register
+    int ctas_log2 = rest < 10 ? rest : 10; if (st->batch > 64 && ctas_log2 > 3) ctas_log2 = rest < 3 ? rest : 3;
+    int hbits = rest - ctas_log2;
+    if (hbits > kZMaxHi) { ctas_log2 = rest - kZMaxHi; hbits = kZMaxHi; }
+    uint64_t nctas = (uint64_t)st->batch << ctas_log2;
+    if (nctas > 0x7fffffffull) return set_err(QM_ERR_ARG, "register too large for the readout grid");
+    size_t part_bytes = (size_t)nctas * kZVals * 8;
+    size_t out_doubles = (size_t)st->batch * nl * 2 + st->batch;
+    QM_TRY(ENSURE_DEV(st, d_scratch, part_bytes + out_doubles * 8));
+    QM_TRY(ENSURE_PIN(st, h_scratch, out_doubles * 8));
+    double* d_part = st->d_scratch;
+    double* d_out = st->d_scratch + (size_t)nctas * kZVals;
+    double* d_tot = d_out + (size_t)st->batch * nl * 2;
+    k_zpartial<<<(unsigned)nctas, kZThreads, 0, st->stream>>>(st->amp, nl, cb, hbits, ctas_log2, thr, d_part);
+    CU(cudaGetLastError());
+    k_zfinal<<<st->batch, 256, 0, st->stream>>>(d_part, nl, cb, hbits, ctas_log2, d_out, d_tot);
+    CU(cudaGetLastError());
+    st->ctr.launches += 2; st->ctr.bytes_hbm += 16ull * total_amps(st);
+    CU(cudaMemcpyAsync(st->h_scratch, d_out, out_doubles * 8, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += out_doubles * 8;
+    QM_TRY(qm_sync(st));
+    *h_pairs = st->h_scratch; *h_tot = st->h_scratch + (size_t)st->batch * nl * 2;
+    return QM_OK;
+}
+
+extern "C" int32_t qm_expect_z_all(qm_state* st, double threshold, double* out_host) {
+    if (!st || !out_host) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    double *pairs, *tot;
+    QM_TRY(zstats(st, threshold, &pairs, &tot));
+    if (st->dist) return dist_finish_z(st, pairs, tot, out_host);
+    memcpy(out_host, pairs, (size_t)st->batch * st->nl * 2 * sizeof(double));
+    return QM_OK;
+}
+
+extern "C" int32_t qm_norm2(qm_state* st, int32_t batch_idx, double* out) {
+    if (!st || !out) return set_err(QM_ERR_ARG, "null argument");
+    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    double *pairs, *tot;
+    QM_TRY(zstats(st, -1.0, &pairs, &tot));
+    if (st->dist) return dist_finish_norm(st, tot[0], out);
+    *out = tot[batch_idx];
+    return QM_OK;
+}
+
+static const double kHmat[8] = { 0.7071067811865475, 0, 0.7071067811865475, 0, 0.7071067811865475, 0, -0.7071067811865475, 0 };
+
+static int measure_one(qm_state* st, int basis, int t0, double thr, int batch_idx, const double* R, double out[2]) {
+    (void)basis;
+    int tb = st->perm[t0];
+    if (tb >= st->nl) return set_err(QM_ERR_STATE, "internal: measurement target is not local");
+    Mat2 U; int identity = (R == nullptr);
+    if (R) memcpy(U.v, R, sizeof(U.v)); else memset(&U, 0, sizeof(U));
+    uint64_t npairs = local_amps(st) >> 1;
+    int blocks = grid_for(npairs, 256, st->sms, 8); if (blocks > kMeasBlocks) blocks = kMeasBlocks;
+    QM_TRY(ENSURE_DEV(st, d_scratch, (size_t)(2 * kMeasBlocks + 2) * 8));
+    QM_TRY(ENSURE_PIN(st, h_scratch, 64));
+    const double2* base = st->amp + ((uint64_t)batch_idx << st->nl);
+    k_measure_rot<<<blocks, 256, 0, st->stream>>>(base, npairs, tb, U, identity, thr, st->d_scratch);
+    CU(cudaGetLastError());
+    k_pair_final<<<1, 256, 0, st->stream>>>(st->d_scratch, blocks, st->d_scratch + 2 * kMeasBlocks);
+    CU(cudaGetLastError());
+    st->ctr.launches += 2; st->ctr.bytes_hbm += 16ull * local_amps(st);
+    CU(cudaMemcpyAsync(st->h_scratch, st->d_scratch + 2 * kMeasBlocks, 16, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += 16;
+    QM_TRY(qm_sync(st));
+    out[0] = st->h_scratch[0]; out[1] = st->h_scratch[1];
+    return QM_OK;
+}
+
+// rx_gate(pi/2) exactly as QSim.jl:119-121 builds it: c = cos(pi/4), s = sin(pi/4); [c -is; -is c].
+// The host shim may pass its own matrix through qm_measure_with (bit-identical to Julia's); this
+// default is what the C library uses for QM_BASIS_Y.
+static void y_rotation(double R[8]) {
+    const double c = cos(0.78539816339744830962), s = sin(0.78539816339744830962);
+    R[0] = c; R[1] = 0; R[2] = 0; R[3] = -s; R[4] = 0; R[5] = -s; R[6] = c; R[7] = 0;
+}
+
+extern "C" int32_t qm_measure(qm_state* st, int32_t basis, int32_t t0, double threshold, int32_t batch_idx, double out[2]) {
+    if (!st || !out) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(check_bit(st, t0, "target"));
+    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
+    if (basis < QM_BASIS_Z || basis > QM_BASIS_Y) return set_err(QM_ERR_ARG, "unknown basis %d", basis);
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    double R[8];
+    const double* Rp = nullptr;
+    if (basis == QM_BASIS_X) Rp = kHmat;
+    else if (basis == QM_BASIS_Y) { y_rotation(R); Rp = R; }
+    if (st->dist) return dist_measure(st, t0, threshold, Rp, out);
+    return measure_one(st, basis, t0, threshold, batch_idx, Rp, out);
+}
+
+extern "C" int32_t qm_measure_with(qm_state* st, int32_t t0, const double* R, double threshold, int32_t batch_idx, double out[2]) {
+    if (!st || !out) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(check_bit(st, t0, "target"));
+    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    if (st->dist) return dist_measure(st, t0, threshold, R, out);
+    return measure_one(st, R ? QM_BASIS_X : QM_BASIS_Z, t0, threshold, batch_idx, R, out);
+}
+
+extern "C" int32_t qm_expect_all(qm_state* st, int32_t basis, double threshold, double* out_host) {
+    if (!st || !out_host) return set_err(QM_ERR_ARG, "null argument");
+    if (basis == QM_BASIS_Z) return qm_expect_z_all(st, threshold, out_host);
+    for (int b = 0; b < st->batch; ++b)
+        for (int q = 0; q < st->n; ++q)
+            QM_TRY(qm_measure(st, basis, q, threshold, b, out_host + ((size_t)b * st->n + q) * 2));
+    return QM_OK;
+}
+
+extern "C" int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k, int32_t batch_idx, double* out) {
+    if (!st || !out) return set_err(QM_ERR_ARG, "null argument");
+    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
+    if (k < 1 || k >= st->n || k > 10) return set_err(QM_ERR_ARG, "Dimension mismatch: k = %d of n = %d (1 <= k < n, k <= 10)", k, st->n);
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    if (st->dist) return dist_reduced_density(st, keep_low, k, out);
+    const uint32_t d = 1u << k, T = d < 16 ? d : 16, tiles = d / T;
+    const uint64_t R = 1ull << (st->nl - k);
+    uint64_t xchunks = R / kRedXC; if (xchunks < 1) xchunks = 1; if (xchunks > 592) { xchunks = 512; }
+    while (R % xchunks) --xchunks;
+    uint64_t x_per = R / xchunks;
+    size_t entries = (size_t)d * d;
+    QM_TRY(ENSURE_DEV(st, d_scratch, (xchunks + 1) * entries * 16));
+    QM_TRY(ENSURE_PIN(st, h_scratch, entries * 16));
+    double2* d_part = reinterpret_cast<double2*>(st->d_scratch);
+    double2* d_out = d_part + xchunks * entries;
+    dim3 grid((unsigned)xchunks, tiles * tiles);
+    k_reduced_partial<<<grid, 256, 0, st->stream>>>(st->amp + ((uint64_t)batch_idx << st->nl), st->nl, k, keep_low ? 1 : 0, x_per, d_part);
+    CU(cudaGetLastError());
+    k_reduced_final<<<(unsigned)((entries + 255) / 256), 256, 0, st->stream>>>(d_part, (uint32_t)xchunks, (uint32_t)entries, d_out);
+    CU(cudaGetLastError());
+    st->ctr.launches += 2; st->ctr.bytes_hbm += 16ull * local_amps(st);
+    CU(cudaMemcpyAsync(st->h_scratch, d_out, entries * 16, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += entries * 16;
+    QM_TRY(qm_sync(st));
+    memcpy(out, st->h_scratch, entries * 16);
+    return QM_OK;
+}
+
+extern "C" int32_t qm_sample(qm_state* st, uint64_t seed, int32_t nshots, int32_t batch_idx, uint64_t* out) {
+    if (!st || (!out && nshots > 0) || nshots < 0) return set_err(QM_ERR_ARG, "null argument");
+    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
+    if (st->dist) return set_err(QM_ERR_STATE, "sampling a sharded register is not implemented");
+    if (nshots == 0) return QM_OK;
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    const uint64_t N = local_amps(st);
+    const uint64_t n1 = (N + kLeaf - 1) / kLeaf, n2 = (n1 + kLeaf - 1) / kLeaf, n3 = (n2 + kLeaf - 1) / kLeaf;
+    size_t need = (n1 + n2 + n3) * 8 + (size_t)nshots * 8 + 64;
+    QM_TRY(ENSURE_DEV(st, d_scratch, need));
+    QM_TRY(ENSURE_PIN(st, h_scratch, (size_t)nshots * 8));
+    double* s1 = st->d_scratch; double* s2 = s1 + n1; double* s3 = s2 + n2;
+    uint64_t* d_out = reinterpret_cast<uint64_t*>(s3 + n3);
+    const double2* base = st->amp + ((uint64_t)batch_idx << st->nl);
+    k_leafsum<true><<<(unsigned)((n1 * 32 + 255) / 256), 256, 0, st->stream>>>(base, N, n1, s1);
+    k_leafsum<false><<<(unsigned)((n2 * 32 + 255) / 256), 256, 0, st->stream>>>(s1, n1, n2, s2);
+    k_leafsum<false><<<(unsigned)((n3 * 32 + 255) / 256), 256, 0, st->stream>>>(s2, n2, n3, s3);
+    k_sample<<<(nshots + 127) / 128, 128, 0, st->stream>>>(base, N, s1, n1, s2, n2, s3, n3, seed, nshots, d_out);
+    CU(cudaGetLastError());
+    st->ctr.launches += 4; st->ctr.bytes_hbm += 16ull * N;
+    CU(cudaMemcpyAsync(st->h_scratch, d_out, (size_t)nshots * 8, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += (size_t)nshots * 8;
+    QM_TRY(qm_sync(st));
+    memcpy(out, st->h_scratch, (size_t)nshots * 8);
+    return QM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t qm_last_error(char* buf, int32_t cap) {
+    if (!buf || cap <= 0) return QM_ERR_ARG;
+    snprintf(buf, (size_t)cap, "%s", g_err);
+    return QM_OK;
+}
+extern "C" int32_t qm_counters(qm_state* st, qm_counters_t* out) {
+    if (!st || !out) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(qm_sync(st));
+    *out = st->ctr;
+    return QM_OK;
+}
+extern "C" int32_t qm_counters_reset(qm_state* st) {
+    if (!st) return set_err(QM_ERR_ARG, "null state");
+    memset(&st->ctr, 0, sizeof(st->ctr));
+    return QM_OK;
+}
+extern "C" int32_t qm_abi_version(void) { return QM_ABI_VERSION; }
+extern "C" int32_t qm_device_ptr(qm_state* st, void** amps, void** stream) {
+    if (!st) return set_err(QM_ERR_ARG, "null state");
+    if (amps) *amps = st->amp;
+    if (stream) *stream = st->stream;
+    return QM_OK;
+}
+
+// Planner introspection (host only).  Flat int32 layout, per step:
+//   [kind(0 pass | 1 remap), ngates, m, L, nhigh, hb[0..nhigh), ngroups, {nrb, rb[0..nrb), nsub}*ngroups]
+extern "C" int32_t qm_plan_describe(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
+                                    int32_t allow_remap, const qm_gate* gates, int32_t ngates, int32_t* out,
+                                    int64_t cap, int64_t* out_len) {
+    (void)allow_remap;
+    if (!gates || !out_len || n_qubits < 1 || global_bits < 0 || global_bits >= n_qubits) return set_err(QM_ERR_ARG, "bad argument");
+    Planner pl;
+    pl.opt.n_local = n_qubits - global_bits; pl.opt.n_global = global_bits;
+    pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
+    int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
+    if (rc) return set_err(rc, "bad gate");
+    pl.done.assign(pl.gates.size(), 0);
+    std::vector<int32_t> v;
+    PlanPass P;
+    while (pl.next_pass(P)) {
+        v.push_back(0); v.push_back(P.ngates); v.push_back(P.m); v.push_back(P.L); v.push_back((int)P.hb.size());
+        for (int b : P.hb) v.push_back(b);
+        v.push_back((int)P.groups.size());
+        for (const PlanGroup& G : P.groups) {
+            v.push_back((int)G.rb.size()); for (int b : G.rb) v.push_back(b);
+            v.push_back((int)G.subs.size());
+        }
+    }
+    int left = 0; for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) ++left;
+    if (left) { v.push_back(1); v.push_back(left); }
+    *out_len = (int64_t)v.size();
+    if ((int64_t)v.size() > cap || !out) return set_err(QM_ERR_ARG, "output too small: need %lld", (long long)v.size());
+    memcpy(out, v.data(), v.size() * sizeof(int32_t));
+    return QM_OK;
+}
+
+extern "C" int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
+                                 double max_cost, const qm_gate* gates, int32_t ngates, qm_gate* out,
+                                 int32_t* pass_of, int32_t cap, int32_t* out_len) {
+    if (!gates || !out_len || n_qubits < 1 || global_bits < 0 || global_bits >= n_qubits) return set_err(QM_ERR_ARG, "bad argument");
+    Planner pl;
+    pl.opt.n_local = n_qubits - global_bits; pl.opt.n_global = global_bits;
+    pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
+    if (max_cost > 0) pl.opt.max_cost = max_cost < 8.0 ? 8.0 : max_cost;
+    int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
+    if (rc) return set_err(rc, "bad gate");
+    pl.done.assign(pl.gates.size(), 0);
+    std::vector<qm_gate> v; std::vector<int32_t> po;
+    PlanPass P; int pi = 0;
+    while (pl.next_pass(P)) {
+        for (const PlanGroup& G : P.groups)
+            for (const LGate& x : G.subs) {
+                qm_gate w; memset(&w, 0, sizeof(w));
+                if (x.ctrl >= 0) { w.kind = QM_GATE_CU2; w.q0 = x.ctrl; w.q1 = x.target; }
+                else if (x.slot >= 0) { w.kind = QM_GATE_U2_SLOT; w.q0 = x.target; w.q1 = x.slot; }
+                else { w.kind = QM_GATE_U2; w.q0 = x.target; }
+                memcpy(w.m, x.m, sizeof(w.m));
+                // every non-diagonal target must be resident in the tile
+                if (!x.diag && tile_local_of(P, x.target) < 0) return set_err(QM_ERR_STATE, "planner placed a non-diagonal target outside its tile");
+                v.push_back(w); po.push_back(pi);
+            }
+        ++pi;
+    }
+    *out_len = (int32_t)v.size();
+    if ((int32_t)v.size() > cap || !out) return set_err(QM_ERR_ARG, "output too small: need %d", (int)v.size());
+    memcpy(out, v.data(), v.size() * sizeof(qm_gate));
+    if (pass_of) memcpy(pass_of, po.data(), po.size() * sizeof(int32_t));
+    return QM_OK;
+}

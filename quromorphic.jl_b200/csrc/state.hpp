@@ -1,0 +1,63 @@
+// state.hpp — the handle behind qm_state* and the small helpers shared by qm_api.cu and dist.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <vector>
+
+#include "../../include/qm_b200.h"
+#include "planner.hpp"
+
+struct DistCtx;
+
+int set_err(int code, const char* fmt, ...);
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return set_err( \
+    (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? QM_ERR_NO_DEVICE : \
+    (e_ == cudaErrorMemoryAllocation ? QM_ERR_NOMEM : QM_ERR_CUDA), "%s failed: %s (%s:%d)", #x, \
+    cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define QM_TRY(x) do { int rc_ = (x); if (rc_ != QM_OK) return rc_; } while (0)
+
+struct qm_state {
+    int n = 0;            // global qubits
+    int nl = 0;           // local index bits
+    int g = 0;            // sharded (rank) bits
+    int rank = 0, world = 1;
+    int batch = 1;
+    int device = 0;
+    int sms = 148;
+    double2* amp = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
+    bool ev_pending = false;
+    // options
+    bool eager = false, fuse = true, remap = false, pipeline = false;
+    int tile_bits = 12, low_bits = 5;
+    double max_cost = 0.0;   // per-pass DFMA-equivalents per amplitude (0 = unlimited)
+    // queue
+    std::vector<qm_gate> queue;
+    // logical -> physical qubit map (identity unless a sharded remap happened)
+    std::vector<int> perm;
+    // device/host scratch
+    unsigned char* d_blob = nullptr; size_t d_blob_cap = 0;
+    unsigned char* h_blob = nullptr; size_t h_blob_cap = 0;
+    double* d_scratch = nullptr; size_t d_scratch_cap = 0;   // partial sums
+    double* h_scratch = nullptr; size_t h_scratch_cap = 0;   // pinned
+    double* d_slots = nullptr; size_t d_slots_cap = 0;
+    qm_counters_t ctr{};
+    DistCtx* dist = nullptr;
+};
+
+int ensure_dev(void** p, size_t* cap, size_t need);
+int ensure_pinned(void** p, size_t* cap, size_t need);
+#define ENSURE_DEV(st, field, need) ensure_dev((void**)&(st)->field, &(st)->field##_cap, (need))
+#define ENSURE_PIN(st, field, need) ensure_pinned((void**)&(st)->field, &(st)->field##_cap, (need))
+
+static inline uint64_t local_amps(const qm_state* st) { return 1ull << st->nl; }
+static inline uint64_t total_amps(const qm_state* st) { return (uint64_t)st->batch << st->nl; }
+
+// implemented in qm_api.cu, used by dist.cu
+int qm_run_local_circuit(qm_state* st, const qm_gate* gates, int ngates, int* consumed);
+int qm_zstats(qm_state* st, double thr, double** h_pairs, double** h_tot);
+int qm_measure_local(qm_state* st, int phys_bit, double thr, const double* R, double out[2]);

@@ -1,0 +1,289 @@
+"""qsim.py — host-side mirror of the reference's QSim API over the B200 engine.
+
+Same function names as /root/reference/src/Quantum/QSim.jl with the `!` dropped (Python has no
+bang identifiers): statevector, nb, id_, u2, h, x, y, z, rx, ry, rz, controlled, cnot, crx, cry,
+crz, swap, mp, measure_z, measure_x, measure_y, prstate, and the exported constants X, Y, Z, I2.
+Qubit arguments are the reference's 1-based indices; the state is a device-resident `B200State`
+(the third "method family" next to Vector{ComplexF64} and Matrix{ComplexF64}).
+The Julia shim quromorphic.jl_b200/julia/B200QSim.jl is the same code in the reference's own
+language; this module is what can be executed and tested in an image without Julia.
+
+Everything numerical happens in libqm_b200.so (CUDA, sm_100a).  This module only
+  * builds the 2x2 gate matrices on the host with the reference's own expressions
+    (QSim.jl:10-17, :114-148) so the engine receives the same bits Julia would pass,
+  * converts t -> t-1 and applies the reference's index map for non-adjacent controlled gates
+    (QSim.jl:181-197; `mode="reference"`, default) or passes (c, t) through (`mode="corrected"`),
+  * performs the reference's argument checks in the reference's order and raises QSimError
+    (standing in for Julia's ErrorException).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+# ---- constants, QSim.jl:8-17 -------------------------------------------------------------------
+c1 = np.complex128(1)
+im_F64 = np.complex128(1j)
+I2 = np.array([[1, 0], [0, 1]], dtype=np.complex128)
+H = np.complex128(1 / np.sqrt(2)) * np.array([[1, 1], [1, -1]], dtype=np.complex128)
+X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+Y = np.array([[0, -im_F64], [im_F64, 0]], dtype=np.complex128)
+Z = np.array([[1, 0], [0, -1]], dtype=np.complex128)
+
+# rotation caches, QSim.jl:25-27 (kept host-side; the engine takes matrices by value)
+RX_CACHE, RY_CACHE, RZ_CACHE = {}, {}, {}
+
+
+class QSimError(RuntimeError):
+    """Julia's ErrorException at this boundary (test_QSim.jl:351-372 pins only the type)."""
+
+
+def id_(n):
+    """id(n), QSim.jl:29-31"""
+    return np.array([[c1]]) if n == 0 else np.eye(1 << n, dtype=np.complex128)
+
+
+def _rot(cache, theta, sigma):
+    th = float(theta)
+    g = cache.get(th)
+    if g is None:
+        c = np.complex128(np.cos(th / 2))
+        s = np.complex128(np.sin(th / 2))
+        g = c * I2 - im_F64 * s * sigma
+        cache[th] = g
+    return g
+
+
+def rx_gate(theta): return _rot(RX_CACHE, theta, X)     # QSim.jl:114-124
+def ry_gate(theta): return _rot(RY_CACHE, theta, Y)     # QSim.jl:126-136
+def rz_gate(theta): return _rot(RZ_CACHE, theta, Z)     # QSim.jl:138-148
+
+
+def effective_control_target(c, t):
+    """What controlled!(s, c, t, V) really acts on (QSim.jl:181-197): with b = max(c, t) the 4x4
+    block sits on qubits (b-1, b); c < t puts the control on b-1, c > t on b."""
+    b = max(c, t)
+    return (b - 1, b) if c < t else (b, b - 1)
+
+
+class B200State:
+    """Device-resident state vector(s): the drop-in for Vector{ComplexF64} (QSim.jl:33-37).
+
+    B200State(n, m)        == statevector(n, m)
+    B200State.from_numpy(v) uploads a host vector; .to_numpy() downloads it.
+    batch > 1 holds `batch` independent n-qubit registers evolved in lockstep.
+    mode: "reference" reproduces the reference's non-adjacent controlled-gate behaviour,
+          "corrected" applies the textbook gate on (c, t).
+    """
+
+    def __init__(self, n, m=0, batch=1, device=0, mode="reference", threshold=1e-10, _handle=None):
+        assert mode in ("reference", "corrected")
+        self.n, self.batch, self.device, self.mode, self.threshold = int(n), int(batch), device, mode, threshold
+        if _handle is not None:
+            self._h = _handle
+            return
+        h = L._vp()
+        if m < 0 or m >= (1 << n):
+            raise QSimError("BoundsError: basis index %d out of range for %d qubits" % (m, n))
+        L.check(L.lib().qm_create(self.n, int(m), self.batch, int(device), C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def from_numpy(cls, v, **kw):
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        n = int(round(np.log2(len(v))))
+        if (1 << n) != len(v):
+            raise QSimError("state length must be a power of two")
+        st = cls(n, 0, **kw)
+        st.upload(v)
+        return st
+
+    def upload(self, v, batch_idx=0):
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        L.check(L.lib().qm_upload(self._h, L.dptr(v), len(v), batch_idx))
+
+    def to_numpy(self, batch_idx=0):
+        out = np.empty(self.local_len, dtype=np.complex128)
+        L.check(L.lib().qm_download(self._h, L.dptr(out), len(out), batch_idx))
+        return out
+
+    @property
+    def local_len(self):
+        return 1 << self.n
+
+    def __len__(self):
+        return 1 << self.n
+
+    def set_option(self, key, value):
+        L.check(L.lib().qm_set_option(self._h, key, int(value)))
+
+    def reset(self, m=0):
+        L.check(L.lib().qm_reset(self._h, int(m)))
+
+    def sync(self):
+        L.check(L.lib().qm_sync(self._h))
+
+    def counters(self):
+        c = L.Counters()
+        L.check(L.lib().qm_counters(self._h, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in L.Counters._fields_}
+
+    def counters_reset(self):
+        L.check(L.lib().qm_counters_reset(self._h))
+
+    def apply_circuit(self, gates):
+        """gates: numpy structured array of _lib.GATE_DTYPE, 0-based textbook bits (wire format)."""
+        assert gates.dtype == L.GATE_DTYPE and gates.flags["C_CONTIGUOUS"]
+        L.check(L.lib().qm_apply_circuit(self._h, gates.ctypes.data, len(gates)))
+        return self
+
+    def apply_batched(self, gates, per_state_mats):
+        """per_state_mats: float64 array [batch, nslots, 8]"""
+        assert gates.dtype == L.GATE_DTYPE and gates.flags["C_CONTIGUOUS"]
+        p = np.ascontiguousarray(per_state_mats, dtype=np.float64)
+        assert p.ndim == 3 and p.shape[0] == self.batch and p.shape[2] == 8
+        L.check(L.lib().qm_apply_batched(self._h, gates.ctypes.data, len(gates), L.dptr(p), p.shape[1]))
+        return self
+
+    def expect_z_all(self, threshold=None):
+        """[batch, n, 2] array of (p0, p1) — all-qubit measure_z in one pass."""
+        out = np.empty((self.batch, self.n, 2), dtype=np.float64)
+        thr = self.threshold if threshold is None else threshold
+        L.check(L.lib().qm_expect_z_all(self._h, thr, L.dptr(out)))
+        return out if self.batch > 1 else out[0]
+
+    def reduced_density(self, keep_low, k, batch_idx=0):
+        d = 1 << k
+        out = np.empty(d * d, dtype=np.complex128)
+        L.check(L.lib().qm_reduced_density(self._h, 1 if keep_low else 0, k, batch_idx, L.dptr(out)))
+        return out.reshape(d, d).T.copy()          # column-major -> numpy [i, j]
+
+    def sample(self, seed, nshots, batch_idx=0):
+        out = np.empty(nshots, dtype=np.uint64)
+        L.check(L.lib().qm_sample(self._h, int(seed), nshots, batch_idx, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def norm2(self, batch_idx=0):
+        v = C.c_double()
+        L.check(L.lib().qm_norm2(self._h, batch_idx, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().qm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- the reference's functions --------------------------------------------------------------------
+
+def statevector(n, m, **kw):
+    """statevector(n, m), QSim.jl:33-37"""
+    return B200State(n, m, **kw)
+
+
+def nb(s):
+    """nb(s), QSim.jl:48"""
+    return s.n
+
+
+def _range1(s, t):
+    # reference: `t <= q || error(...)` (QSim.jl:54); it does not test t >= 1 and fails later with a
+    # different exception — the shim rejects it here with the same ErrorException.
+    if not (1 <= t <= s.n):
+        raise QSimError("Qubit index out of range")
+
+
+def u2(s, t, U):
+    """u2!(s, t, U), QSim.jl:52-63"""
+    _range1(s, t)
+    m = L.mat8(U)
+    L.check(L.lib().qm_apply_u2(s._h, t - 1, L.dptr(m)))
+    return s
+
+
+def h(s, t): return u2(s, t, H)                      # QSim.jl:81-83
+def x(s, t): return u2(s, t, X)                      # QSim.jl:89-91
+def y(s, t): return u2(s, t, Y)                      # QSim.jl:97-99
+def z(s, t): return u2(s, t, Z)                      # QSim.jl:105-107
+def rx(s, t, theta): return u2(s, t, rx_gate(theta))  # QSim.jl:150-152
+def ry(s, t, theta): return u2(s, t, ry_gate(theta))  # QSim.jl:158-160
+def rz(s, t, theta): return u2(s, t, rz_gate(theta))  # QSim.jl:166-168
+
+
+def controlled(s, c, t, V):
+    """controlled!(s, c, t, V), QSim.jl:175-203.  Checks in the reference's order: range, then c == t."""
+    if not (c <= s.n and t <= s.n) or c < 1 or t < 1:
+        raise QSimError("Qubit index out of range")
+    if c == t:
+        raise QSimError("Control and target cannot be the same qubit")
+    ce, te = effective_control_target(c, t) if s.mode == "reference" else (c, t)
+    m = L.mat8(V)
+    L.check(L.lib().qm_apply_controlled(s._h, ce - 1, te - 1, L.dptr(m)))
+    return s
+
+
+def cnot(s, c, t): return controlled(s, c, t, X)                     # QSim.jl:205-207
+def crx(s, c, t, theta): return controlled(s, c, t, rx_gate(theta))  # QSim.jl:238-240
+def cry(s, c, t, theta): return controlled(s, c, t, ry_gate(theta))  # QSim.jl:246-248
+def crz(s, c, t, theta): return controlled(s, c, t, rz_gate(theta))  # QSim.jl:254-256
+
+
+def swap(s, q1, q2):
+    """swap!(s, q1, q2), QSim.jl:262-275: range check, no-op when equal, else cnot!(q1,q2); cnot!(q2,q1);
+    cnot!(q1,q2) — each through controlled!, so the reference mode inherits its index map."""
+    if not (q1 <= s.n and q2 <= s.n) or q1 < 1 or q2 < 1:
+        raise QSimError("Qubit index out of range")
+    if q1 == q2:
+        return s
+    cnot(s, q1, q2)
+    cnot(s, q2, q1)
+    cnot(s, q1, q2)
+    return s
+
+
+def mp(s, batch_idx=0):
+    """mp(s) = abs2.(s), QSim.jl:293"""
+    out = np.empty(1 << s.n, dtype=np.float64)
+    L.check(L.lib().qm_probs(s._h, L.dptr(out), batch_idx))
+    return out
+
+
+def _measure(s, t, R, batch_idx):
+    if not (1 <= t <= s.n):
+        raise QSimError("Qubit index out of range")
+    out = np.empty(2, dtype=np.float64)
+    Rp = L.dptr(L.mat8(R)) if R is not None else None
+    L.check(L.lib().qm_measure_with(s._h, t - 1, Rp, s.threshold, batch_idx, L.dptr(out)))
+    return (float(out[0]), float(out[1]))
+
+
+def measure_z(s, t, batch_idx=0):
+    """measure_z(s, t), QSim.jl:297-318: (p0, p1), summing only probabilities > 1e-10."""
+    return _measure(s, t, None, batch_idx)
+
+
+def measure_x(s, t, batch_idx=0):
+    """measure_x(s, t) = measure_z(h!(copy(s), t), t), QSim.jl:320-324 (no copy is made: the kernel
+    rotates each amplitude pair in registers)."""
+    return _measure(s, t, H, batch_idx)
+
+
+def measure_y(s, t, batch_idx=0):
+    """measure_y(s, t) = measure_z(rx!(copy(s), t, pi/2), t), QSim.jl:326-330"""
+    return _measure(s, t, rx_gate(np.pi / 2), batch_idx)
+
+
+def prstate(s, batch_idx=0, file=None):
+    """prstate(s), QSim.jl:367-373: '|bits⟩: amplitude' for abs(a) > 1e-10, MSB-first bit string."""
+    v = s.to_numpy(batch_idx)
+    for i in range(len(v)):
+        a = v[i]
+        if abs(a) > 1e-10:
+            print("|" + format(i, "b").rjust(s.n, "0") + "⟩: " + repr(complex(a)), file=file)

@@ -1,0 +1,122 @@
+"""CPU-only checks of the boundary: the C-ABI library loads, exports every symbol include/qm_b200.h
+declares, refuses loudly without a GPU (no CPU fallback), and the host-side planner's reordering is
+algebraically exact (verified by replaying its execution order on the CPU oracle)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "qm_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(qm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg._lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 28
+    for s in syms:
+        assert hasattr(lib, s), s
+        assert s in pkg._lib.SIGNATURES, "ctypes signature missing for " + s
+    assert lib.qm_abi_version() == 1
+
+
+def test_gate_struct_layout(pkg):
+    assert pkg._lib.GATE_DTYPE.itemsize == 80 and O.GATE_DTYPE == pkg._lib.GATE_DTYPE
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.QMError) as e:
+        pkg.B200State(4, 0)
+    assert e.value.code == pkg._lib.QM_ERR_NO_DEVICE
+
+
+def test_matrix_memory_order(pkg):
+    U = np.array([[1 + 2j, 3 + 4j], [5 + 6j, 7 + 8j]])
+    assert list(pkg._lib.mat8(U)) == [1, 2, 5, 6, 3, 4, 7, 8]     # U11 U21 U12 U22, Julia column-major
+
+
+def test_host_gate_matrices_match_reference_expressions(pkg):
+    Q = pkg.qsim
+    from oracle import literal as L
+    for th in (0.0, 0.3, np.pi / 2, np.pi, -2.2, 7.0):
+        assert np.array_equal(Q.rx_gate(th), L.rx_gate(th))
+        assert np.array_equal(Q.ry_gate(th), L.ry_gate(th))
+        assert np.array_equal(Q.rz_gate(th), L.rz_gate(th))
+    assert np.array_equal(Q.H, L.H) and np.array_equal(Q.Y, L.Y)
+    assert Q.rx_gate(0.3) is Q.rx_gate(0.3)                      # memoised like RX_CACHE (QSim.jl:116-118)
+    assert Q.id_(0).shape == (1, 1) and Q.id_(2).shape == (4, 4)  # test_QSim.jl:327-340
+
+
+def test_effective_control_target_matches_oracle(pkg):
+    for c in range(1, 8):
+        for t in range(1, 8):
+            if c != t:
+                assert pkg.qsim.effective_control_target(c, t) == O.effective_ct(c, t)
+
+
+def random_circuit(pkg, n, ngates, seed):
+    rng = np.random.default_rng(seed)
+    gl = pkg.circuits.GateList(n)
+    Q = pkg.qsim
+    for _ in range(ngates):
+        k = rng.integers(0, 9)
+        t = int(rng.integers(1, n + 1))
+        c = int(rng.integers(1, n + 1))
+        th = float(rng.uniform(-np.pi, np.pi))
+        if k == 0: gl.h(t)
+        elif k == 1: gl.rx(t, th)
+        elif k == 2: gl.ry(t, th)
+        elif k == 3: gl.rz(t, th)
+        elif k == 4: gl.u2(t, Q.X)
+        elif k == 5: gl.u2(t, Q.Z)
+        elif c != t:
+            if k == 6: gl.cnot(c, t)
+            elif k == 7: gl.crz(c, t, th)
+            else: gl.controlled(c, t, Q.ry_gate(th))
+    return gl.array()
+
+
+@pytest.mark.parametrize("n,tile,low,cost", [(6, 12, 5, 0), (10, 6, 2, 0), (12, 8, 3, 0), (14, 12, 5, 40.0),
+                                             (13, 7, 0, 0), (9, 4, 1, 8.0)])
+def test_planner_order_is_exact_on_cpu(pkg, n, tile, low, cost):
+    gates = random_circuit(pkg, n, 300, 1000 + n)
+    order, pass_of = pkg._lib.plan_gates(n, gates, 0, tile, low, cost)
+    assert len(order) <= len(gates) and len(order) > 0
+    assert np.all(np.diff(pass_of) >= 0)
+    s = O.random_state(n, 5)
+    ref = O.apply_circuit(s.copy(), gates)
+    got = O.apply_circuit(s.copy(), order)
+    assert np.max(np.abs(got - ref)) < 1e-13
+
+
+def test_planner_c3_fuses_many_gates_per_pass(pkg):
+    gates = pkg.circuits.c3_circuit(n=30, depth=20)
+    order, pass_of = pkg._lib.plan_gates(30, gates, 0, 12, 5, 0.0)
+    npass = pass_of[-1] + 1
+    assert len(gates) == 20 * 30 + 10 * 15 + 10 * 14
+    assert npass < len(gates) / 20
+
+
+def test_planner_leaves_global_targets_for_remap(pkg):
+    n, g = 10, 2
+    gl = pkg.circuits.GateList(n, mode="corrected")
+    gl.rx(3, 0.4); gl.rz(10, 0.3); gl.cnot(10, 2); gl.rx(9, 0.2); gl.h(1)
+    out = np.zeros(4096, dtype=np.int32); ln = C.c_int64()
+    a = gl.array()
+    pkg._lib.check(pkg._lib.lib().qm_plan_describe(n, g, 6, 3, 0, a.ctypes.data, len(a),
+                                                   out.ctypes.data_as(C.POINTER(C.c_int32)), len(out), C.byref(ln)))
+    v = out[:ln.value]
+    # the diagonal rz on global qubit 10 and the cnot controlled by it run locally; only rx(9) is left
+    assert v[-2] == 1 and v[-1] == 1

@@ -1,0 +1,268 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libqm_b200.so), against the
+CPU oracle on the same seeded inputs.  Tolerance for ComplexF64 amplitudes and readouts: 1e-12
+relative to the largest magnitude (BASELINE.json north_star); permutation gates and the seeded
+sampler are compared bit for bit."""
+import types
+
+import numpy as np
+import pytest
+
+import ref_known_answers as KA
+from oracle import literal as LIT
+from oracle import oracle as O
+from test_abi_cpu import random_circuit
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def engine_backend(pkg, **opts):
+    Q, QI = pkg.qsim, pkg.qinfo
+    B = types.SimpleNamespace()
+    B.Error = pkg.QSimError
+
+    def sv(n, m):
+        s = Q.statevector(n, m)
+        for k, v in opts.items():
+            s.set_option(k, v)
+        return s
+    B.statevector = sv
+    B.nb, B.mp = Q.nb, Q.mp
+    B.to_numpy = lambda s: s.to_numpy()
+    for name in ("h", "x", "y", "z", "rx", "ry", "rz", "cnot", "crx", "cry", "crz", "swap",
+                 "measure_z", "measure_x", "measure_y"):
+        setattr(B, name, getattr(Q, name))
+
+    def reduced(psi, keep_low, k):
+        s = pkg.B200State.from_numpy(np.asarray(psi, dtype=np.complex128))
+        n = s.n
+        dB = (1 << k) if keep_low else (1 << (n - k))
+        return QI.partial_trace(s, (1 << n) // dB, dB, 1 if keep_low else 2)
+    B.reduced = reduced
+    B.entropy = QI.von_neumann_entropy
+    return B
+
+
+@pytest.mark.parametrize("check", KA.ALL_QSIM, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("eager", [0, 1])
+def test_reference_known_answers_through_the_engine(pkg, check, eager):
+    check(engine_backend(pkg, **{pkg._lib.OPT_EAGER: eager}))
+
+
+def test_reference_partial_trace_known_answers_through_the_engine(pkg):
+    KA.check_partial_trace(engine_backend(pkg))
+
+
+def test_prstate_format(pkg, capsys):
+    s = pkg.qsim.statevector(2, 0)
+    pkg.qsim.h(s, 1)
+    pkg.qsim.prstate(s)                                   # test_QSim.jl:319-321 (no throw) + QSim.jl:371 format
+    out = capsys.readouterr().out.strip().splitlines()
+    assert out[0].startswith("|00⟩: ") and out[1].startswith("|01⟩: ")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 9, 12, 13, 14, 17, 20])
+@pytest.mark.parametrize("mode", ["fused", "nofuse", "eager"])
+def test_random_circuit_matches_oracle(pkg, n, mode):
+    gates = random_circuit(pkg, n, 120 if n > 14 else 250, 77 + n)
+    psi0 = O.random_state(n, 11 + n)
+    st = pkg.B200State.from_numpy(psi0)
+    if mode == "eager":
+        st.set_option(pkg._lib.OPT_EAGER, 1)
+    if mode == "nofuse":
+        st.set_option(pkg._lib.OPT_FUSE, 0)
+    st.apply_circuit(gates)
+    got = st.to_numpy()
+    ref = O.apply_circuit(psi0.copy(), gates)
+    assert rel_err(got, ref) < RTOL
+    c = st.counters()
+    assert c["launches"] > 0 and c["gates"] == len(gates)
+
+
+@pytest.mark.parametrize("tile,low", [(4, 0), (6, 2), (8, 3), (10, 5), (11, 4), (12, 5), (12, 6), (13, 5)])
+def test_tile_shapes(pkg, tile, low):
+    n = 15
+    gates = random_circuit(pkg, n, 300, 5 * tile + low)
+    psi0 = O.random_state(n, tile)
+    st = pkg.B200State.from_numpy(psi0)
+    st.set_option(pkg._lib.OPT_TILE_BITS, tile)
+    st.set_option(pkg._lib.OPT_LOW_BITS, low)
+    st.apply_circuit(gates)
+    assert rel_err(st.to_numpy(), O.apply_circuit(psi0.copy(), gates)) < RTOL
+
+
+def test_every_control_target_pair_reference_semantics(pkg):
+    """every ordered (c, t) on 6 qubits through the QSim-shaped API: equals the literal dense-kron
+    restatement, i.e. the reference's behaviour for non-adjacent pairs included (QSim.jl:181-197)"""
+    n, Q = 6, pkg.qsim
+    V = LIT.ry_gate(0.77) @ LIT.rz_gate(-0.4)
+    for c in range(1, n + 1):
+        for t in range(1, n + 1):
+            if c == t:
+                continue
+            psi0 = O.random_state(n, 100 * c + t)
+            s = pkg.B200State.from_numpy(psi0)
+            Q.controlled(s, c, t, V)
+            assert rel_err(s.to_numpy(), LIT.controlled(psi0.copy(), c, t, V)) < RTOL, (c, t)
+            s2 = pkg.B200State.from_numpy(psi0, mode="corrected")
+            Q.controlled(s2, c, t, V)
+            assert rel_err(s2.to_numpy(), O.controlled(psi0.copy(), c, t, V, quirk=False)) < RTOL
+
+
+@pytest.mark.parametrize("eager", [0, 1])
+def test_permutation_gates_are_bit_exact(pkg, eager):
+    n, Q = 11, pkg.qsim
+    psi0 = O.random_state(n, 31337)
+    s = pkg.B200State.from_numpy(psi0)
+    s.set_option(pkg._lib.OPT_EAGER, eager)
+    ref = psi0.copy()
+    for (c, t) in ((1, 2), (5, 4), (11, 10), (3, 9), (10, 1)):
+        Q.cnot(s, c, t); O.cnot(ref, c, t)
+    Q.x(s, 7); O.x(ref, 7)
+    Q.swap(s, 2, 9); O.swap(ref, 2, 9)
+    Q.swap(s, 4, 4); O.swap(ref, 4, 4)
+    assert np.array_equal(s.to_numpy(), ref)
+
+
+@pytest.mark.parametrize("n", [1, 3, 8, 13, 14, 18, 22])
+def test_readouts_match_oracle(pkg, n):
+    Q = pkg.qsim
+    psi = O.random_state(n, 900 + n)
+    if n >= 3:
+        psi[5] = 1e-6            # probability 1e-12: dropped by the 1e-10 threshold (QSim.jl:308)
+    s = pkg.B200State.from_numpy(psi)
+    z = s.expect_z_all()
+    zr = O.expect_z_all(psi, 1e-10)
+    assert np.max(np.abs(z - zr)) < RTOL
+    z0 = s.expect_z_all(threshold=-1.0)
+    assert np.max(np.abs(z0 - O.expect_z_all(psi, -1.0))) < RTOL
+    assert abs(s.norm2() - O.norm2(psi)) < RTOL
+    for t in sorted({1, (n + 1) // 2, n}):
+        assert Q.measure_z(s, t) == pytest.approx(O.measure_z(psi, t), rel=RTOL, abs=1e-15)
+        assert Q.measure_x(s, t) == pytest.approx(O.measure_x(psi, t), rel=RTOL, abs=1e-15)
+        assert Q.measure_y(s, t) == pytest.approx(O.measure_y(psi, t), rel=RTOL, abs=1e-15)
+    if n <= 18:
+        assert np.array_equal(Q.mp(s), O.mp(psi))          # abs2 is computed with the same three operations
+
+
+@pytest.mark.parametrize("n,k", [(2, 1), (5, 2), (8, 4), (12, 4), (12, 6), (16, 4), (16, 8), (20, 4)])
+def test_reduced_density_matches_oracle(pkg, n, k):
+    psi = O.random_state(n, 17 * n + k)
+    s = pkg.B200State.from_numpy(psi)
+    for keep_low in (True, False):
+        got = s.reduced_density(keep_low, k)
+        ref = O.reduced_density(psi, keep_low, k)
+        assert np.max(np.abs(got - ref)) < RTOL
+        assert abs(np.trace(got).real - 1.0) < 1e-12
+        assert pkg.qinfo.von_neumann_entropy(got) == pytest.approx(LIT.von_neumann_entropy(ref), abs=1e-9)
+
+
+@pytest.mark.parametrize("n", [1, 5, 12, 13, 19, 24])
+def test_sampler_is_bit_exact(pkg, n):
+    psi = O.random_state(n, 555 + n)
+    s = pkg.B200State.from_numpy(psi)
+    for seed in (0, 12345):
+        assert np.array_equal(s.sample(seed, 257), O.sample(psi, seed, 257))
+
+
+def test_sampler_skewed_distribution(pkg):
+    n = 16
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[40000] = np.sqrt(0.75); psi[3] = 0.5j
+    s = pkg.B200State.from_numpy(psi)
+    got = s.sample(7, 1000)
+    assert np.array_equal(got, O.sample(psi, 7, 1000))
+    assert set(got.tolist()) == {3, 40000}
+
+
+def test_batched_registers_match_per_state_oracle(pkg):
+    n, B, T = 10, 37, 3
+    C = pkg.circuits
+    gates = C.c2_step_gates(n, seed=1603)
+    w = [C.SplitMix64(5).uniform() for _ in range(n)]
+    st = pkg.B200State(n, 0, batch=B)
+    refs = [O.statevector(n, 0) for _ in range(B)]
+    for t in range(T):
+        enc = C.c2_encoding(B, n, t, w)
+        st.apply_batched(gates, enc)
+        z = st.expect_z_all()
+        for b in range(B):
+            g = gates.copy()
+            for i in range(len(g)):
+                if g[i]["kind"] == pkg._lib.GATE_U2_SLOT:
+                    g[i]["m"] = enc[b, g[i]["q1"]]; g[i]["kind"] = pkg._lib.GATE_U2; g[i]["q1"] = 0
+            O.apply_circuit(refs[b], g)
+            assert np.max(np.abs(z[b] - O.expect_z_all(refs[b], 1e-10))) < RTOL
+    for b in (0, 17, B - 1):
+        assert rel_err(st.to_numpy(b), refs[b]) < RTOL
+
+
+def test_c1_reservoir_prefix_matches_literal_reference_algorithm(pkg):
+    """config C1 at a size the literal dense-kron restatement can run (n = 8, T = 5), including the
+    deliberately non-adjacent crz!(n, 1, gamma)."""
+    n, T, Q = 8, 5, pkg.qsim
+    u, w, layer, gamma = pkg.circuits.c1_inputs(n, T)
+    s = Q.statevector(n, 0)
+    ref = LIT.statevector(n, 0)
+    for t in range(T):
+        for q in range(1, n + 1):
+            Q.ry(s, q, np.pi * u[t] * w[q - 1]); LIT.u2(ref, q, LIT.ry_gate(np.pi * u[t] * w[q - 1]))
+        for q in range(1, n + 1):
+            Q.rx(s, q, layer[q - 1][0]); LIT.u2(ref, q, LIT.rx_gate(layer[q - 1][0]))
+            Q.rz(s, q, layer[q - 1][1]); LIT.u2(ref, q, LIT.rz_gate(layer[q - 1][1]))
+        for q in range(1, n):
+            Q.cnot(s, q, q + 1); LIT.cnot(ref, q, q + 1)
+        Q.crz(s, n, 1, gamma); LIT.controlled(ref, n, 1, LIT.rz_gate(gamma))
+        for q in range(1, n + 1):
+            assert Q.measure_z(s, q) == pytest.approx(LIT.measure_z(ref, q), rel=RTOL, abs=1e-15)
+    assert rel_err(s.to_numpy(), ref) < RTOL
+
+
+def test_c3_layers_at_24_qubits_match_oracle(pkg):
+    n = 24
+    gates = pkg.circuits.c3_circuit(n=n, depth=6)
+    st = pkg.B200State(n, 0)
+    st.apply_circuit(gates)
+    ref = O.apply_circuit(O.statevector(n, 0), gates)
+    assert rel_err(st.to_numpy(), ref) < RTOL
+    assert np.max(np.abs(st.expect_z_all() - O.expect_z_all(ref, 1e-10))) < RTOL
+
+
+def test_large_register_properties_28_qubits(pkg):
+    """size-independent properties at a size the oracle would need minutes for: unitarity (norm),
+    circuit followed by its inverse returns the start state, X^2 = identity bit-exactly."""
+    n, Q = 28, pkg.qsim
+    gates = pkg.circuits.c3_circuit(n=n, depth=4, seed=99)
+    st = pkg.B200State(n, 5)
+    st.apply_circuit(gates)
+    assert abs(st.norm2() - 1.0) < 1e-12
+    inv = gates[::-1].copy()
+    for i in range(len(inv)):
+        U = inv[i]["m"].view(np.complex128).reshape(2, 2).T          # numpy [row, col]
+        inv[i]["m"] = pkg._lib.mat8(U.conj().T)
+    st.apply_circuit(inv)
+    z = st.expect_z_all(threshold=-1.0)
+    want = np.array([[0.0, 1.0] if (5 >> q) & 1 else [1.0, 0.0] for q in range(n)])
+    assert np.max(np.abs(z - want)) < 1e-12
+    samp = st.sample(1, 16)
+    assert np.all(samp == 5)
+
+
+def test_argument_errors(pkg):
+    L = pkg._lib
+    st = pkg.B200State(3, 0)
+    m = L.mat8(np.eye(2))
+    assert L.lib().qm_apply_u2(st._h, 3, L.dptr(m)) == L.QM_ERR_ARG
+    assert "out of range" in L.last_error()
+    assert L.lib().qm_apply_controlled(st._h, 1, 1, L.dptr(m)) == L.QM_ERR_ARG
+    assert "same qubit" in L.last_error()
+    with pytest.raises(pkg.QMError):
+        st.reduced_density(True, 3)
+    with pytest.raises(pkg.QSimError):
+        pkg.B200State(3, 8)
+    with pytest.raises(AssertionError):
+        pkg.qinfo.partial_trace(st, 4, 4, 1)            # QInfo.jl:382 "Dimension mismatch"
