@@ -20,7 +20,8 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
-def engine_backend(pkg, **opts):
+def engine_backend(pkg, opts=None):
+    opts = opts or {}
     Q, QI = pkg.qsim, pkg.qinfo
     B = types.SimpleNamespace()
     B.Error = pkg.QSimError
@@ -50,7 +51,7 @@ def engine_backend(pkg, **opts):
 @pytest.mark.parametrize("check", KA.ALL_QSIM, ids=lambda f: f.__name__)
 @pytest.mark.parametrize("eager", [0, 1])
 def test_reference_known_answers_through_the_engine(pkg, check, eager):
-    check(engine_backend(pkg, **{pkg._lib.OPT_EAGER: eager}))
+    check(engine_backend(pkg, {pkg._lib.OPT_EAGER: eager}))
 
 
 def test_reference_partial_trace_known_answers_through_the_engine(pkg):
