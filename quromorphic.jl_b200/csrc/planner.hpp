@@ -91,6 +91,9 @@ struct PlanOptions {
     bool fuse = true;
     int window = 768;    // look-ahead, in gates
     double max_cost = 1e30;
+    int max_runs = 99;   // runs of consecutive high tile bits a pass may use (TMA tensor maps: 3)
+    int max_subs = kMaxSubsPerPass;
+    int max_groups = 1 << 30;
 };
 
 inline bool mat_is_diag(const double* m) { return m[2] == 0.0 && m[3] == 0.0 && m[4] == 0.0 && m[5] == 0.0; }
@@ -227,7 +230,7 @@ struct Planner {
 
     int count_with(uint64_t tilemask) const {
         std::vector<int> taken;
-        pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, kMaxSubsPerPass,
+        pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, opt.max_subs,
              [&](int t) { return (tilemask >> t) & 1; }, taken);
         return (int)taken.size();
     }
@@ -239,6 +242,8 @@ struct Planner {
         if (nh <= 0) { best = count_with((1ull << L) - 1); return; }
         uint64_t low = (1ull << L) - 1;
         auto try_set = [&](const std::vector<int>& hb) {
+            int runs = 0; for (size_t i = 0; i < hb.size(); ++i) if (i == 0 || hb[i] != hb[i - 1] + 1) ++runs;
+            if (runs > opt.max_runs) return;
             uint64_t mask = low; for (int b : hb) mask |= 1ull << b;
             int c = count_with(mask);
             if (c > best) { best = c; hb_best = hb; }
@@ -291,28 +296,39 @@ struct Planner {
         choose_tile(m, L, hb, best);
         if (best <= 0) return false;
         uint64_t tilemask = (1ull << L) - 1; for (int b : hb) tilemask |= 1ull << b;
-        std::vector<int> taken;
-        pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, kMaxSubsPerPass,
-             [&](int t) { return (tilemask >> t) & 1; }, taken);
-        P = PlanPass(); P.m = m; P.L = L; P.hb = hb; P.ngates = (int)taken.size();
-        std::vector<LGate> pg; pg.reserve(taken.size());
-        for (int i : taken) { pg.push_back(gates[i]); done[i] = 1; P.cost += gate_cost(gates[i]); }
-        // register-block groups: same pull with an allowed set that grows up to 3 bits
-        std::vector<char> d2(pg.size(), 0); size_t f2 = 0;
+        int max_take = opt.max_subs;
         while (true) {
-            while (f2 < pg.size() && d2[f2]) ++f2;
-            if (f2 >= pg.size()) break;
-            PlanGroup G; uint64_t have = 0;
-            std::vector<int> tk;
-            pull(pg, d2, f2, 1 << 30, (1ull << total_bits()) - 1, 1e30, 1 << 30,
-                 [&](int t) {
-                     if ((have >> t) & 1) return true;
-                     if ((int)G.rb.size() < kBlockBits) { G.rb.push_back(t); have |= 1ull << t; return true; }
-                     return false;
-                 }, tk);
-            for (int i : tk) { G.subs.push_back(pg[i]); d2[i] = 1; }
-            std::sort(G.rb.begin(), G.rb.end());
-            P.groups.push_back(G);
+            std::vector<int> taken;
+            pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, max_take,
+                 [&](int t) { return (tilemask >> t) & 1; }, taken);
+            P = PlanPass(); P.m = m; P.L = L; P.hb = hb; P.ngates = (int)taken.size();
+            std::vector<LGate> pg; pg.reserve(taken.size());
+            for (int i : taken) { pg.push_back(gates[i]); P.cost += gate_cost(gates[i]); }
+            // register-block groups: same pull with an allowed set that grows up to 3 bits
+            std::vector<char> d2(pg.size(), 0); size_t f2 = 0;
+            while (true) {
+                while (f2 < pg.size() && d2[f2]) ++f2;
+                if (f2 >= pg.size()) break;
+                PlanGroup G; uint64_t have = 0;
+                std::vector<int> tk;
+                pull(pg, d2, f2, 1 << 30, (1ull << total_bits()) - 1, 1e30, 1 << 30,
+                     [&](int t) {
+                         if ((have >> t) & 1) return true;
+                         if ((int)G.rb.size() < kBlockBits) { G.rb.push_back(t); have |= 1ull << t; return true; }
+                         return false;
+                     }, tk);
+                for (int i : tk) { G.subs.push_back(pg[i]); d2[i] = 1; }
+                std::sort(G.rb.begin(), G.rb.end());
+                P.groups.push_back(G);
+            }
+            if ((int)P.groups.size() > opt.max_groups && taken.size() > 1) {
+                // too many register-block groups for the kernel's program buffer: take fewer gates
+                max_take = (int)((double)taken.size() * opt.max_groups / (double)P.groups.size());
+                if (max_take < 1) max_take = 1;
+                continue;
+            }
+            for (int i : taken) done[i] = 1;
+            break;
         }
         return true;
     }

@@ -10,6 +10,7 @@
 
 #include "../../include/qm_b200.h"
 #include "dist.hpp"
+#include "fused_tma.cuh"
 #include "kernels.cuh"
 #include "planner.hpp"
 #include "state.hpp"
@@ -182,6 +183,159 @@ static int launch_pass(qm_state* st, const unsigned char* d_pass, const PlanPass
     return QM_OK;
 }
 
+// ---- v2: persistent TMA-pipelined pass -------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// runs of consecutive bits in hb (ascending)
+static int hb_runs(const std::vector<int>& hb, int start[8], int len[8]) {
+    int nr = 0;
+    for (size_t i = 0; i < hb.size(); ++i) {
+        if (nr > 0 && hb[i] == start[nr - 1] + len[nr - 1]) { len[nr - 1]++; continue; }
+        if (nr == 8) return 99;
+        start[nr] = hb[i]; len[nr] = 1; ++nr;
+    }
+    return nr;
+}
+
+// can this pass go through the TMA kernel?
+static bool v2_eligible(const qm_state* st, const PlanPass& P) {
+    if (!st->pipeline || !get_encode()) return false;
+    if (P.m != 11 && P.m != 12) return false;
+    if (P.L < 3 || P.L > 8) return false;
+    int rs[8], rl[8];
+    int nr = hb_runs(P.hb, rs, rl);
+    if (nr > 3) return false;
+    for (int i = 0; i < nr; ++i) if (rl[i] > 8) return false;
+    if ((int)P.groups.size() > kV2MaxGroups) return false;
+    size_t nsub = 0; for (const PlanGroup& G : P.groups) nsub += G.subs.size();
+    if (nsub > (size_t)kV2MaxSubs) return false;
+    if ((total_amps(st) >> 3) > 0x7fffffffull) return false;      // TMA coordinates are int32
+    return true;
+}
+
+static void encode_v2(const PlanPass& P, V2Program& out) {
+    memset(&out, 0, sizeof(out));
+    out.ngroups = (int)P.groups.size();
+    int nsub = 0;
+    const int nwarp_bits = P.m - 3 - 5;
+    for (size_t gi = 0; gi < P.groups.size(); ++gi) {
+        const PlanGroup& G = P.groups[gi];
+        V2Group& g = out.groups[gi];
+        int rbl[3] = { -1, -1, -1 }; uint32_t blockmask = 0; int nrb = 0;
+        for (size_t i = 0; i < G.rb.size(); ++i) { rbl[nrb] = tile_local_of(P, G.rb[i]); blockmask |= 1u << rbl[nrb]; ++nrb; }
+        // always three block bits: pad with tile bits no gate of this group targets (highest first)
+        for (int b = P.m - 1; b >= 0 && nrb < 3; --b) if (!((blockmask >> b) & 1)) { rbl[nrb++] = b; blockmask |= 1u << b; }
+        std::sort(rbl, rbl + 3);
+        for (int i = 0; i < 3; ++i) g.rbmask[i] = (uint16_t)(1u << rbl[i]);
+        // thread-index bit order (see planner.hpp encode_pass for the bank argument)
+        std::vector<int> order; uint32_t used = blockmask;
+        for (int k = 0; k < 3; ++k) {
+            int pick = -1;
+            if (!((used >> k) & 1)) pick = k; else if (!((used >> (k + 3)) & 1)) pick = k + 3;
+            if (pick >= 0) { order.push_back(pick); used |= 1u << pick; }
+        }
+        for (int b = 0; b < P.m; ++b) if (!((used >> b) & 1)) { order.push_back(b); used |= 1u << b; }
+        for (int lane = 0; lane < 32; ++lane) {
+            uint32_t v = 0; for (int j = 0; j < 5; ++j) if ((lane >> j) & 1) v |= 1u << order[j];
+            out.lane_tab[gi][lane] = (uint16_t)v;
+        }
+        for (int w = 0; w < (1 << nwarp_bits); ++w) {
+            uint32_t v = 0; for (int j = 0; j < nwarp_bits; ++j) if ((w >> j) & 1) v |= 1u << order[5 + j];
+            out.warp_tab[gi][w] = (uint16_t)v;
+        }
+        g.sub_off = (uint16_t)nsub; g.nsub = (uint16_t)G.subs.size();
+        for (const LGate& x : G.subs) {
+            V2Sub& S = out.subs[nsub++];
+            S.slot = x.slot; S.has_slot = x.slot >= 0;
+            if (x.ctrl >= 0) {
+                int cl = tile_local_of(P, x.ctrl);
+                if (cl < 0) S.cm_out = 1ull << x.ctrl;
+                else {
+                    int bi = -1; for (int i = 0; i < 3; ++i) if (rbl[i] == cl) bi = i;
+                    if (bi >= 0) S.cm_blk = (uint8_t)(1u << bi); else S.cm_loc = 1u << cl;
+                }
+            }
+            int tl = tile_local_of(P, x.target);
+            int bi = -1; if (tl >= 0) for (int i = 0; i < 3; ++i) if (rbl[i] == tl) bi = i;
+            const double* m = x.m;
+            if (x.diag) {
+                S.kind = V2_DIAG;
+                if (bi >= 0) S.b = (uint8_t)bi;
+                else if (tl >= 0) { S.b = 3; S.t_loc = 1u << tl; }
+                else { S.b = 4; S.t_out = 1ull << x.target; }
+                S.c[0] = m[0]; S.c[1] = m[1]; S.c[2] = m[6]; S.c[3] = m[7];
+            } else {
+                S.b = (uint8_t)bi;
+                const bool all_real = m[1] == 0 && m[3] == 0 && m[5] == 0 && m[7] == 0;
+                const bool is_x = all_real && m[0] == 0 && m[6] == 0 && m[2] == 1 && m[4] == 1;
+                const bool xform = m[1] == 0 && m[7] == 0 && m[2] == 0 && m[4] == 0;
+                if (x.slot >= 0) { S.kind = V2_MAT; }
+                else if (is_x) S.kind = V2_PERMX;
+                else if (all_real) { S.kind = V2_MATR; S.c[0] = m[0]; S.c[1] = m[2]; S.c[2] = m[4]; S.c[3] = m[6]; }
+                else if (xform) { S.kind = V2_MATX; S.c[0] = m[0]; S.c[1] = m[3]; S.c[2] = m[5]; S.c[3] = m[6]; }
+                else { S.kind = V2_MAT; memcpy(S.c, m, sizeof(S.c)); }
+            }
+        }
+    }
+    out.nsubs = nsub;
+}
+
+template <int M, int STAGES>
+static int launch_v2_t(qm_state* st, const CUtensorMap& tm, const V2Program* d_prog, const double* d_slots, const V2Launch& lp) {
+    constexpr int threads = (1 << (M - 3)) + 32;
+    constexpr size_t smem = (size_t)STAGES * (16u << M) + sizeof(V2Program) + 2 * STAGES * 8 + 1024;
+    static bool attr = false;
+    if (!attr) { CU(cudaFuncSetAttribute(k_fused_tma<M, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const int per_sm = M >= 12 ? 1 : 2;
+    uint64_t cap = (uint64_t)st->sms * per_sm;
+    int grid = (int)(lp.ntiles < cap ? lp.ntiles : cap);
+    k_fused_tma<M, STAGES><<<grid, threads, smem, st->stream>>>(tm, d_prog, d_slots, lp);
+    CU(cudaGetLastError());
+    return QM_OK;
+}
+
+static int launch_pass_v2(qm_state* st, const V2Program* d_prog, const PlanPass& P, const double* d_slots, int nslots) {
+    // tensor map: dim0 = one 128-byte row (8 amplitudes = 16 doubles); dim1 = row index over the whole
+    // array (the box takes 2^(L-3) consecutive rows at the tile's base); dims 2..4 = the runs of high
+    // tile bits (size 2^len, stride 16 * 2^start bytes), unused dims have size 1.
+    int rs[8], rl[8];
+    const int nr = hb_runs(P.hb, rs, rl);
+    const uint64_t amps = total_amps(st);
+    cuuint64_t gdim[5] = { 16, amps >> 3, 1, 1, 1 };
+    cuuint64_t gstr[4] = { 128, 128, 128, 128 };
+    cuuint32_t box[5] = { 16, 1u << (P.L - 3), 1, 1, 1 };
+    cuuint32_t estr[5] = { 1, 1, 1, 1, 1 };
+    for (int i = 0; i < nr; ++i) { gdim[2 + i] = 1ull << rl[i]; gstr[1 + i] = 16ull << rs[i]; box[2 + i] = 1u << rl[i]; }
+    // strides of unused trailing dims: keep them multiples of the previous ones
+    for (int i = nr; i < 3; ++i) gstr[1 + i] = (i == 0) ? 128 : gstr[i];
+    CUtensorMap tm;
+    CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, st->amp, gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(QM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    V2Launch lp; memset(&lp, 0, sizeof(lp));
+    lp.ntiles = amps >> P.m; lp.reg_bits = st->nl; lp.L = P.L; lp.nh = (int)P.hb.size();
+    for (size_t j = 0; j < P.hb.size(); ++j) lp.hb[j] = P.hb[j];
+    lp.rank_or = st->g ? ((uint64_t)st->rank << st->nl) : 0; lp.nslots = nslots;
+    if (P.m == 11) QM_TRY((launch_v2_t<11, 3>(st, tm, d_prog, d_slots, lp)));
+    else QM_TRY((launch_v2_t<12, 3>(st, tm, d_prog, d_slots, lp)));
+    st->ctr.launches++; st->ctr.passes++;
+    st->ctr.bytes_hbm += 32ull * amps;
+    return QM_OK;
+}
+
 // run `gates` (logical qubits) now: plan, upload the pass programs, launch
 static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const double* d_slots, int nslots) {
     if (ngates <= 0) return QM_OK;
@@ -207,6 +361,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     pl.opt.n_local = st->nl; pl.opt.n_global = st->g;
     pl.opt.tile_bits = st->tile_bits; pl.opt.low_bits = st->low_bits; pl.opt.fuse = st->fuse;
     if (st->max_cost > 0) pl.opt.max_cost = st->max_cost < 8.0 ? 8.0 : st->max_cost;
+    if (st->pipeline) { pl.opt.max_runs = 3; pl.opt.max_subs = kV2MaxSubs; pl.opt.max_groups = kV2MaxGroups; }
     std::vector<PlanPass> passes;          // of the current segment (between remaps)
     std::vector<unsigned char> blob;
     std::vector<size_t> offs;
@@ -220,9 +375,17 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         pl.done.assign(pl.gates.size(), 0);
         passes.clear(); blob.clear(); offs.clear();
         PlanPass P;
+        std::vector<char> use_v2;
         while (pl.next_pass(P)) {
             offs.push_back(blob.size());
-            encode_pass(P, blob);
+            if (v2_eligible(st, P)) {
+                blob.resize(blob.size() + sizeof(V2Program));
+                encode_v2(P, *reinterpret_cast<V2Program*>(&blob[offs.back()]));
+                use_v2.push_back(1);
+            } else {
+                encode_pass(P, blob);
+                use_v2.push_back(0);
+            }
             while (blob.size() % 16) blob.push_back(0);
             passes.push_back(P);
         }
@@ -239,7 +402,10 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             CU(cudaMemcpyAsync(st->d_blob, st->h_blob, blob.size(), cudaMemcpyHostToDevice, st->stream));
             st->ctr.bytes_h2d += blob.size();
             CU(cudaEventRecord(st->ev_stage, st->stream));
-            for (size_t i = 0; i < passes.size(); ++i) QM_TRY(launch_pass(st, st->d_blob + offs[i], passes[i], d_slots, nslots));
+            for (size_t i = 0; i < passes.size(); ++i) {
+                if (use_v2[i]) QM_TRY(launch_pass_v2(st, reinterpret_cast<const V2Program*>(st->d_blob + offs[i]), passes[i], d_slots, nslots));
+                else QM_TRY(launch_pass(st, st->d_blob + offs[i], passes[i], d_slots, nslots));
+            }
         }
         if (!leftover) break;
         // sharded: the remaining gates need a non-diagonal target on a global qubit.  The lowered

@@ -32,7 +32,7 @@ struct qm_state {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
     bool ev_pending = false;
     // options
-    bool eager = false, fuse = true, remap = false, pipeline = false;
+    bool eager = false, fuse = true, remap = false, pipeline = true;
     int tile_bits = 12, low_bits = 5;
     double max_cost = 0.0;   // per-pass DFMA-equivalents per amplitude (0 = unlimited)
     // queue

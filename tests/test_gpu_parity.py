@@ -84,12 +84,15 @@ def test_random_circuit_matches_oracle(pkg, n, mode):
     assert c["launches"] > 0 and c["gates"] == len(gates)
 
 
-@pytest.mark.parametrize("tile,low", [(4, 0), (6, 2), (8, 3), (10, 5), (11, 4), (12, 5), (12, 6), (13, 5)])
-def test_tile_shapes(pkg, tile, low):
+@pytest.mark.parametrize("pipe", [0, 1])
+@pytest.mark.parametrize("tile,low", [(4, 0), (6, 2), (8, 3), (10, 5), (11, 3), (11, 4), (11, 5), (12, 3), (12, 5),
+                                      (12, 6), (12, 8), (13, 5)])
+def test_tile_shapes(pkg, tile, low, pipe):
     n = 15
     gates = random_circuit(pkg, n, 300, 5 * tile + low)
     psi0 = O.random_state(n, tile)
     st = pkg.B200State.from_numpy(psi0)
+    st.set_option(pkg._lib.OPT_PIPELINE, pipe)
     st.set_option(pkg._lib.OPT_TILE_BITS, tile)
     st.set_option(pkg._lib.OPT_LOW_BITS, low)
     st.apply_circuit(gates)
@@ -223,10 +226,13 @@ def test_c1_reservoir_prefix_matches_literal_reference_algorithm(pkg):
     assert rel_err(s.to_numpy(), ref) < RTOL
 
 
-def test_c3_layers_at_24_qubits_match_oracle(pkg):
+@pytest.mark.parametrize("tile,cost", [(12, 0), (11, 0), (12, 48), (11, 24)])
+def test_c3_layers_at_24_qubits_match_oracle(pkg, tile, cost):
     n = 24
     gates = pkg.circuits.c3_circuit(n=n, depth=6)
     st = pkg.B200State(n, 0)
+    st.set_option(pkg._lib.OPT_TILE_BITS, tile)
+    st.set_option(pkg._lib.OPT_MAX_COST, cost)
     st.apply_circuit(gates)
     ref = O.apply_circuit(O.statevector(n, 0), gates)
     assert rel_err(st.to_numpy(), ref) < RTOL

@@ -20,15 +20,18 @@ def main():
     ap.add_argument("--lows", default="5")
     ap.add_argument("--costs", default="0,32,64,128")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--pipes", default="1")
     args = ap.parse_args()
     pkg = ge.load_package()
     L = pkg._lib
     n = args.qubits
     gates = pkg.circuits.c3_circuit(n=n, depth=args.depth)
     st = pkg.B200State(n, 0)
-    for tile, low, cost in itertools.product([int(x) for x in args.tiles.split(",")],
-                                             [int(x) for x in args.lows.split(",")],
-                                             [int(x) for x in args.costs.split(",")]):
+    for pipe, tile, low, cost in itertools.product([int(x) for x in args.pipes.split(",")],
+                                                   [int(x) for x in args.tiles.split(",")],
+                                                   [int(x) for x in args.lows.split(",")],
+                                                   [int(x) for x in args.costs.split(",")]):
+        st.set_option(L.OPT_PIPELINE, pipe)
         st.set_option(L.OPT_TILE_BITS, tile)
         st.set_option(L.OPT_LOW_BITS, low)
         st.set_option(L.OPT_MAX_COST, cost)
@@ -43,7 +46,7 @@ def main():
         ms = best["ms_device"]
         per = ms / best["passes"]
         gbs = 32.0 * (1 << n) / (per * 1e-3) / 1e9
-        print(json.dumps({"tile": tile, "low": low, "max_cost": cost, "passes": best["passes"], "ms_total": round(ms, 2),
+        print(json.dumps({"pipe": pipe, "tile": tile, "low": low, "max_cost": cost, "passes": best["passes"], "ms_total": round(ms, 2),
                           "ms_per_pass": round(per, 3), "hbm_gbs": round(gbs, 1), "gates_per_s": round(len(gates) / ms * 1e3, 1),
                           "plan_ms": round(best["ms_plan"], 2)}), flush=True)
     st.close()
