@@ -46,6 +46,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     } while (!ok);
 }
+// producer-side wait: back off between probes so the spinning lane does not eat issue slots of the
+// compute warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
                                             int c3, int c4) {
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -62,26 +74,35 @@ __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// ---- specialised gate kinds (chosen on the host from the matrix bits) -------------------------
-enum {
-    V2_MAT = 0,    // general complex 2x2                         16 FMA-class ops per pair
-    V2_MATR = 1,   // all four entries real (ry, H, Z*ry ...)        8
-    V2_MATX = 2,   // real diagonal, imaginary off-diagonal (rx, Y)  8
-    V2_PERMX = 3,  // exactly X: exchange the pair, no arithmetic    0   (x!, cnot!, swap!: bit-exact)
-    V2_DIAG = 4    // diagonal (rz, z, crz ...)                      4 per amplitude
-};
+// ---- gate kinds: every body is IN PLACE -----------------------------------------------------------
+// A 2x2 update written as  a0' = u11 a0 + u12 a1, a1' = u21 a0 + u22 a1  needs both old values while
+// it produces both new ones; inside an interpreter loop the compiler then parks results in fresh
+// registers and copies the whole 32-register block at every loop edge (measured with ncu: 46 % of
+// all executed instructions were IMAD.MOV/MOV, FP64 13 %).  So the engine never does that.  Every
+// unitary 2x2 is applied as real plane rotations written as three shears ("lifting"):
+//        x += t1*y ;   y = s1*x + (+-y) ;   x = t2*y + (+-x)
+// each FMA overwrites an operand that is dead after it, the two signs are XOR masks on the high
+// word (ALU pipe), and a rotation costs 3 FP64 ops per real pair instead of 4.  The host
+// (qm_api.cu) derives the coefficients and checks the reconstruction to a few ulp:
+//   V2_ROT   real orthogonal 2x2 (ry, H ...): lift on (a0.x, a1.x) and on (a0.y, a1.y)
+//   V2_ROTX  real diagonal / imaginary off-diagonal (rx, Y ...): lift on (a0.x, a1.y), mirrored on (a0.y, a1.x)
+//   V2_PHASE unit-modulus diagonal (rz, z, crz ...): lift on (a.x, a.y) of each amplitude
+//   V2_PERMX exactly X (x!, cnot!, swap!): xor exchange of the pair, bit-exact, no arithmetic
+// A general unitary is sent as PHASE * ROT * PHASE (9 FP64 ops per amplitude against 8 for the
+// direct form, but in place).  A non-unitary matrix makes its pass take the v1 kernel.
+enum { V2_ROT = 0, V2_ROTX = 1, V2_PHASE = 2, V2_PERMX = 3 };
 
 struct V2Sub {              // 96 bytes
-    uint8_t  kind;          // V2_*
-    uint8_t  b;             // block bit 0..2 of the target; V2_DIAG: 3 = tile-local bit, 4 = outer bit
-    uint8_t  cm_blk;        // control bits among the block bits
-    uint8_t  has_slot;
+    uint8_t  op;            // opcode (see v2_run_subs); for a thread-level PHASE: the opcode when the target bit is 0
+    uint8_t  op_hi;         // thread-level PHASE: the opcode when the target bit is 1
+    uint8_t  cm_blk;        // (informational) control bit among the block bits
+    uint8_t  flags;         // bit 0: per-state slot coefficients, bit 1: thread-level/outer control, bit 2: thread-level PHASE
     uint32_t cm_loc;        // control bits among the tile-local (thread) bits
-    uint32_t t_loc;         // V2_DIAG b == 3: tile-local mask of the target
+    uint32_t t_loc;         // fam 1: tile-local mask of the target
     int32_t  slot;
     uint64_t cm_out;        // control bits outside the tile
-    uint64_t t_out;         // V2_DIAG b == 4: outer mask of the target
-    double   c[8];          // MAT: U11 U21 U12 U22 (re, im) ; MATR: u11 u21 u12 u22 ; MATX: p s r q ; DIAG: d0 (re,im), d1 (re,im)
+    uint64_t t_out;         // fam 1: outer mask of the target
+    double   c[8];          // t1 s1 t2 (set 0), t1 s1 t2 (set 1: PHASE, target bit = 1)
 };
 static_assert(sizeof(V2Sub) == 96, "V2Sub layout");
 
@@ -103,95 +124,55 @@ struct V2Program {
 };
 static_assert(sizeof(V2Program) % 16 == 0, "V2Program must be copyable in 16-byte units");
 
-template <int B>
-__device__ __forceinline__ void v2_mat(double2 (&a)[8], const double* __restrict__ m, uint32_t cm) {
-    const double2 u11 = make_double2(m[0], m[1]), u21 = make_double2(m[2], m[3]);
-    const double2 u12 = make_double2(m[4], m[5]), u22 = make_double2(m[6], m[7]);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k & (1 << B)) continue;
-        if ((k & cm) == cm) {
-            const double2 a0 = a[k], a1 = a[k | (1 << B)];
-            a[k] = cfma(u12, a1, cmul(u11, a0));
-            a[k | (1 << B)] = cfma(u22, a1, cmul(u21, a0));
-        }
-    }
-}
-template <int B>
-__device__ __forceinline__ void v2_matr(double2 (&a)[8], const double* __restrict__ c, uint32_t cm) {
-    const double u11 = c[0], u21 = c[1], u12 = c[2], u22 = c[3];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k & (1 << B)) continue;
-        if ((k & cm) == cm) {
-            const double2 a0 = a[k], a1 = a[k | (1 << B)];
-            a[k] = make_double2(fma(u12, a1.x, u11 * a0.x), fma(u12, a1.y, u11 * a0.y));
-            a[k | (1 << B)] = make_double2(fma(u22, a1.x, u21 * a0.x), fma(u22, a1.y, u21 * a0.y));
-        }
-    }
-}
-// u11 = p, u21 = i s, u12 = i r, u22 = q
-template <int B>
-__device__ __forceinline__ void v2_matx(double2 (&a)[8], const double* __restrict__ c, uint32_t cm) {
-    const double p = c[0], s = c[1], r = c[2], q = c[3];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k & (1 << B)) continue;
-        if ((k & cm) == cm) {
-            const double2 a0 = a[k], a1 = a[k | (1 << B)];
-            a[k] = make_double2(fma(-r, a1.y, p * a0.x), fma(r, a1.x, p * a0.y));
-            a[k | (1 << B)] = make_double2(fma(-s, a0.y, q * a1.x), fma(s, a0.x, q * a1.y));
-        }
-    }
-}
-template <int B>
-__device__ __forceinline__ void v2_permx(double2 (&a)[8], uint32_t cm) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k & (1 << B)) continue;
-        if ((k & cm) == cm) { const double2 t = a[k]; a[k] = a[k | (1 << B)]; a[k | (1 << B)] = t; }
-    }
+// The gate bodies and their dispatch live in v2_dispatch.inc (generated by tools/gen_v2_dispatch.py):
+// one inline-PTX block, `brx.idx.uni` on the warp-uniform opcode, every body a straight run of in-place
+// DFMAs (or xor exchanges for X) on the 16 amplitude registers.  Opcodes:
+//   [0, 36)   ROT   sign variant 0..3   x 9 (B, CB)        [36, 54)  ROTX  sign variant 0, 3  x 9
+//   [54, 90)  PHASE (sg bit0, sg bit1) in 00 03 30 33  x 9  [90, 99)  PERMX x 9
+//   [99, 107) PHASE on a thread-level / outer bit (coefficient set picked per thread): sign 0, 3  x 4 (CB)
+// sign variant: bit 0 -> the middle shear takes -y, bit 1 -> the last shear takes -x (operand negations).
+#include "v2_dispatch.inc"
+static const int kV2OpThr = 99;
+__host__ __device__ inline int v2_bc_index(int B, int CB) {     // position of (B, CB) among the 9 legal pairs
+    int i = 0;
+    for (int b = 0; b < 3; ++b) for (int c = -1; c < 3; ++c) { if (c == b) continue; if (b == B && c == CB) return i; ++i; }
+    return 0;
 }
 
 __device__ __forceinline__ void v2_run_subs(double2 (&a)[8], const V2Program* __restrict__ P, const V2Group& G, uint32_t loc,
                                             uint64_t gbase, const double* __restrict__ slot_base) {
     const int s0 = G.sub_off, s1 = s0 + G.nsub;
+    const V2Sub* S = &P->subs[s0];
+    uint4 hdr = *reinterpret_cast<const uint4*>(S);         // op | op_hi << 8 | cm_blk << 16 | flags << 24, cm_loc, t_loc, slot
     for (int s = s0; s < s1; ++s) {
-        const V2Sub& S = P->subs[s];
-        if ((loc & S.cm_loc) != S.cm_loc) continue;
-        if ((gbase & S.cm_out) != S.cm_out) continue;
-        const uint32_t cm = S.cm_blk;
-        switch (S.kind) {
-        case V2_MAT: {
-            const double* m = S.has_slot ? (slot_base + (size_t)S.slot * 8) : S.c;
-            switch (S.b) { case 0: v2_mat<0>(a, m, cm); break; case 1: v2_mat<1>(a, m, cm); break; default: v2_mat<2>(a, m, cm); }
-            break;
-        }
-        case V2_MATR:
-            switch (S.b) { case 0: v2_matr<0>(a, S.c, cm); break; case 1: v2_matr<1>(a, S.c, cm); break; default: v2_matr<2>(a, S.c, cm); }
-            break;
-        case V2_MATX:
-            switch (S.b) { case 0: v2_matx<0>(a, S.c, cm); break; case 1: v2_matx<1>(a, S.c, cm); break; default: v2_matx<2>(a, S.c, cm); }
-            break;
-        case V2_PERMX:
-            switch (S.b) { case 0: v2_permx<0>(a, cm); break; case 1: v2_permx<1>(a, cm); break; default: v2_permx<2>(a, cm); }
-            break;
-        default: {   // V2_DIAG
-            const double2 d0 = make_double2(S.c[0], S.c[1]), d1 = make_double2(S.c[2], S.c[3]);
-            if (S.b < 3) {
-                const int b = S.b;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if ((k & cm) == cm) a[k] = cmul(((k >> b) & 1) ? d1 : d0, a[k]);
-            } else {
-                const bool bit = (S.b == 3) ? ((loc & S.t_loc) != 0) : ((gbase & S.t_out) != 0);
-                const double2 d = bit ? d1 : d0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if ((k & cm) == cm) a[k] = cmul(d, a[k]);
+        const V2Sub* cur = S;
+        const uint4 h = hdr;
+        // coefficients of this sub (they arrive while the header is decoded) and the header of the next one
+        const double2 q0 = *reinterpret_cast<const double2*>(&cur->c[0]);
+        const double2 q1 = *reinterpret_cast<const double2*>(&cur->c[2]);
+        const double2 q2 = *reinterpret_cast<const double2*>(&cur->c[4]);
+        if (s + 1 < s1) { S = cur + 1; hdr = *reinterpret_cast<const uint4*>(S); }
+        double c0 = q0.x, c1 = q0.y, c2 = q1.x, c3 = q1.y, c4 = q2.x, c5 = q2.y;
+        uint32_t op = h.x & 0xffu;
+        const uint32_t flags = h.x >> 24;
+        if (flags) {
+            if (flags & 2u) {                                            // thread-level or outer control
+                if ((loc & h.y) != h.y) continue;
+                if ((gbase & cur->cm_out) != cur->cm_out) continue;
+            }
+            if (flags & 1u) {                                            // per-state coefficients
+                const double* g = slot_base + (size_t)h.w * 8;
+                c0 = g[0]; c1 = g[1]; c2 = g[2]; c3 = g[3]; c4 = g[4]; c5 = g[5];
+            }
+            if (flags & 4u) {                                            // PHASE on a bit this thread sees as a constant
+                const bool bit = h.z ? ((loc & h.z) != 0) : ((gbase & cur->t_out) != 0);
+                if (bit) { c0 = c3; c1 = c4; c2 = c5; op = (h.x >> 8) & 0xffu; }
             }
         }
-        }
+        asm volatile(V2_DISPATCH_PTX
+                     : "+d"(a[0].x), "+d"(a[0].y), "+d"(a[1].x), "+d"(a[1].y), "+d"(a[2].x), "+d"(a[2].y), "+d"(a[3].x), "+d"(a[3].y),
+                       "+d"(a[4].x), "+d"(a[4].y), "+d"(a[5].x), "+d"(a[5].y), "+d"(a[6].x), "+d"(a[6].y), "+d"(a[7].x), "+d"(a[7].y)
+                     : "d"(c0), "d"(c1), "d"(c2), "d"(c3), "d"(c4), "d"(c5), "r"(op));
     }
 }
 
@@ -259,7 +240,7 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const V2Program* __restric
             for (uint64_t i = 0; i < my_tiles; ++i) {
                 const int s = (int)(i % STAGES);
                 const uint32_t ph = (uint32_t)((i / STAGES) & 1);
-                mbar_wait(&computed[s], ph);
+                mbar_wait_sleep(&computed[s], ph);
                 const uint64_t base = tile_base(first + i * step, gb, br);
                 tma_store_5d(&tmap, stage_base + (size_t)s * TILE_BYTES, 0, (int)(base >> 3), 0, 0, 0);
                 tma_commit();

@@ -62,11 +62,19 @@ static_assert(sizeof(DevPass) == 96, "DevPass layout");
 
 // ---- planner-side structures ---------------------------------------------------------------
 struct LGate {           // lowered gate on PHYSICAL index bits
-    int target;
-    int ctrl;            // -1 = none
-    bool diag;
-    int slot;            // -1 = none
-    double m[8];
+    int target = 0;
+    int ctrl = -1;       // -1 = none
+    bool diag = false;
+    int slot = -1;       // -1 = none, else index into the per-state (sub)slot table
+    int skind = -1;      // slot gates: lifting kind of the (sub)slot (lifting.hpp LK_*)
+    bool liftable = true;  // has an in-place lifting form (lifting.hpp); false -> its pass uses the v1 kernel
+    double m[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+};
+
+// how the caller's per-state slots map onto (sub)slots: slot s -> count[s] consecutive subslots
+// starting at first[s], each of lifting kind kind[first[s] + i] (general unitaries take three)
+struct SlotMap {
+    std::vector<int> first, count, kind;
 };
 
 struct PlanSub { LGate g; };
@@ -122,7 +130,7 @@ static const double kXmat[8] = { 0, 0, 1, 0, 1, 0, 0, 0 };
 // Lower wire gates to LGates on physical bits (perm[logical] = physical), merging runs of
 // uncontrolled 1-qubit gates on the same qubit into one matrix when `fuse` is set.
 inline int lower_gates(const qm_gate* gates, int ng, int nbits, const int* perm, bool fuse,
-                       std::vector<LGate>& out) {
+                       std::vector<LGate>& out, const SlotMap* slots = nullptr) {
     std::vector<int> pending(nbits, -1);   // index in `out` of a still-mergeable 1q gate per physical bit
     auto touch = [&](int bit) { pending[bit] = -1; };
     for (int i = 0; i < ng; ++i) {
@@ -134,7 +142,15 @@ inline int lower_gates(const qm_gate* gates, int ng, int nbits, const int* perm,
             LGate g; g.target = t; g.ctrl = -1; g.slot = (w.kind == QM_GATE_U2_SLOT) ? w.q1 : -1;
             memcpy(g.m, w.m, sizeof(g.m));
             g.diag = (g.slot < 0) && mat_is_diag(g.m);
-            if (fuse && g.slot < 0 && pending[t] >= 0) {
+            if (g.slot >= 0 && slots) {
+                // one LGate per subslot, in application order
+                const int s0 = slots->first[g.slot], cnt = slots->count[g.slot];
+                for (int i = 0; i < cnt; ++i) {
+                    LGate h = g; h.slot = s0 + i; h.skind = slots->kind[s0 + i]; h.diag = (h.skind == 2);
+                    out.push_back(h);
+                }
+                pending[t] = -1;
+            } else if (fuse && g.slot < 0 && pending[t] >= 0) {
                 LGate& p = out[pending[t]];
                 mat_mul(g.m, p.m, p.m);                 // later gate multiplies from the left
                 p.diag = mat_is_diag(p.m);

@@ -3,6 +3,7 @@
 // QM_ERR_NO_DEVICE.  The only GPU-free entry points are the planner introspection and version.
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <math.h>
 #include <stdio.h>
 #include <chrono>
 #include <string>
@@ -12,6 +13,7 @@
 #include "dist.hpp"
 #include "fused_tma.cuh"
 #include "kernels.cuh"
+#include "lifting.hpp"
 #include "planner.hpp"
 #include "state.hpp"
 
@@ -219,7 +221,11 @@ static bool v2_eligible(const qm_state* st, const PlanPass& P) {
     if (nr > 3) return false;
     for (int i = 0; i < nr; ++i) if (rl[i] > 8) return false;
     if ((int)P.groups.size() > kV2MaxGroups) return false;
-    size_t nsub = 0; for (const PlanGroup& G : P.groups) nsub += G.subs.size();
+    size_t nsub = 0;
+    for (const PlanGroup& G : P.groups) {
+        nsub += G.subs.size();
+        for (const LGate& x : G.subs) if (!x.liftable) return false;
+    }
     if (nsub > (size_t)kV2MaxSubs) return false;
     if ((total_amps(st) >> 3) > 0x7fffffffull) return false;      // TMA coordinates are int32
     return true;
@@ -258,34 +264,36 @@ static void encode_v2(const PlanPass& P, V2Program& out) {
         g.sub_off = (uint16_t)nsub; g.nsub = (uint16_t)G.subs.size();
         for (const LGate& x : G.subs) {
             V2Sub& S = out.subs[nsub++];
-            S.slot = x.slot; S.has_slot = x.slot >= 0;
+            S.slot = x.slot; S.flags = x.slot >= 0 ? 1 : 0;
+            int CB = -1;
             if (x.ctrl >= 0) {
                 int cl = tile_local_of(P, x.ctrl);
-                if (cl < 0) S.cm_out = 1ull << x.ctrl;
+                if (cl < 0) { S.cm_out = 1ull << x.ctrl; S.flags |= 2; }
                 else {
                     int bi = -1; for (int i = 0; i < 3; ++i) if (rbl[i] == cl) bi = i;
-                    if (bi >= 0) S.cm_blk = (uint8_t)(1u << bi); else S.cm_loc = 1u << cl;
+                    if (bi >= 0) { S.cm_blk = (uint8_t)(1u << bi); CB = bi; } else { S.cm_loc = 1u << cl; S.flags |= 2; }
                 }
             }
             int tl = tile_local_of(P, x.target);
             int bi = -1; if (tl >= 0) for (int i = 0; i < 3; ++i) if (rbl[i] == tl) bi = i;
-            const double* m = x.m;
-            if (x.diag) {
-                S.kind = V2_DIAG;
-                if (bi >= 0) S.b = (uint8_t)bi;
-                else if (tl >= 0) { S.b = 3; S.t_loc = 1u << tl; }
-                else { S.b = 4; S.t_out = 1ull << x.target; }
-                S.c[0] = m[0]; S.c[1] = m[1]; S.c[2] = m[6]; S.c[3] = m[7];
+            LiftCoef Lc; memset(&Lc, 0, sizeof(Lc));
+            const int kind = x.slot >= 0 ? x.skind : lift_classify(x.m, Lc);   // liftable was checked by v2_eligible
+            memcpy(S.c, &Lc, sizeof(Lc));
+            // static sign variants: sg = (mk[0] ? 1 : 0) | (mk[1] ? 2 : 0); per-state slots are built for sg 0
+            const int sgA = (Lc.mk[0] ? 1 : 0) | (Lc.mk[1] ? 2 : 0), sgB = (Lc.mk[2] ? 1 : 0) | (Lc.mk[3] ? 2 : 0);
+            if (kind == LK_PHASE && bi < 0) {
+                S.flags |= 4;
+                S.op = (uint8_t)(kV2OpThr + (sgA == 3 ? 4 : 0) + (CB + 1));
+                S.op_hi = (uint8_t)(kV2OpThr + (sgB == 3 ? 4 : 0) + (CB + 1));
+                if (tl >= 0) S.t_loc = 1u << tl; else S.t_out = 1ull << x.target;
             } else {
-                S.b = (uint8_t)bi;
-                const bool all_real = m[1] == 0 && m[3] == 0 && m[5] == 0 && m[7] == 0;
-                const bool is_x = all_real && m[0] == 0 && m[6] == 0 && m[2] == 1 && m[4] == 1;
-                const bool xform = m[1] == 0 && m[7] == 0 && m[2] == 0 && m[4] == 0;
-                if (x.slot >= 0) { S.kind = V2_MAT; }
-                else if (is_x) S.kind = V2_PERMX;
-                else if (all_real) { S.kind = V2_MATR; S.c[0] = m[0]; S.c[1] = m[2]; S.c[2] = m[4]; S.c[3] = m[6]; }
-                else if (xform) { S.kind = V2_MATX; S.c[0] = m[0]; S.c[1] = m[3]; S.c[2] = m[5]; S.c[3] = m[6]; }
-                else { S.kind = V2_MAT; memcpy(S.c, m, sizeof(S.c)); }
+                const int bc = v2_bc_index(bi, CB);
+                int base;
+                if (kind == LK_ROT) base = sgA * 9;
+                else if (kind == LK_ROTX) base = 36 + (sgA == 3 ? 9 : 0);
+                else if (kind == LK_PHASE) base = 54 + ((sgA == 3 ? 2 : 0) + (sgB == 3 ? 1 : 0)) * 9;
+                else base = 90;
+                S.op = (uint8_t)(base + bc);
             }
         }
     }
@@ -337,7 +345,8 @@ static int launch_pass_v2(qm_state* st, const V2Program* d_prog, const PlanPass&
 }
 
 // run `gates` (logical qubits) now: plan, upload the pass programs, launch
-static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const double* d_slots, int nslots) {
+static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const double* d_slots, int nslots,
+                       const SlotMap* smap = nullptr, const double* d_slots_lift = nullptr) {
     if (ngates <= 0) return QM_OK;
     CU(cudaSetDevice(st->device));
     auto t0 = std::chrono::steady_clock::now();
@@ -370,8 +379,9 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     while (pos < ngates) {
         // plan everything that is left under the current qubit map
         pl.gates.clear(); pl.done.clear(); pl.first = 0;
-        int rc = lower_gates(gates + pos, ngates - pos, st->n, st->perm.data(), st->fuse, pl.gates);
+        int rc = lower_gates(gates + pos, ngates - pos, st->n, st->perm.data(), st->fuse, pl.gates, smap);
         if (rc) return set_err(rc, "bad gate in circuit (index >= %d)", pos);
+        if (st->pipeline) prepare_for_lifting(pl.gates);
         pl.done.assign(pl.gates.size(), 0);
         passes.clear(); blob.clear(); offs.clear();
         PlanPass P;
@@ -403,7 +413,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             st->ctr.bytes_h2d += blob.size();
             CU(cudaEventRecord(st->ev_stage, st->stream));
             for (size_t i = 0; i < passes.size(); ++i) {
-                if (use_v2[i]) QM_TRY(launch_pass_v2(st, reinterpret_cast<const V2Program*>(st->d_blob + offs[i]), passes[i], d_slots, nslots));
+                if (use_v2[i]) QM_TRY(launch_pass_v2(st, reinterpret_cast<const V2Program*>(st->d_blob + offs[i]), passes[i], d_slots_lift, nslots));
                 else QM_TRY(launch_pass(st, st->d_blob + offs[i], passes[i], d_slots, nslots));
             }
         }
@@ -496,15 +506,83 @@ extern "C" int32_t qm_apply_batched(qm_state* st, const qm_gate* gates, int32_t 
     QM_TRY(flush(st));
     if (st->eager) return set_err(QM_ERR_STATE, "batched application needs the fused path");
     CU(cudaSetDevice(st->device));
-    size_t bytes = (size_t)st->batch * nslots * 8 * sizeof(double);
-    if (bytes) {
-        QM_TRY(ENSURE_DEV(st, d_slots, bytes));
-        // the caller's buffer is pageable and must not be retained: the copy below returns only
-        // when the bytes have left the host buffer
-        CU(cudaMemcpyAsync(st->d_slots, per_state_mats, bytes, cudaMemcpyHostToDevice, st->stream));
-        st->ctr.bytes_h2d += bytes;
+    if (nslots == 0) return run_circuit(st, gates, ngates, nullptr, 0);
+    // Per-state matrices -> (sub)slots.  The v2 kernel's sign variants are static, so a slot stays ONE
+    // subslot only when every state's matrix has the same lifting kind with plain signs (ry(theta),
+    // 0 <= theta < pi, is the reservoir-encoding case).  Otherwise every state's matrix is sent as
+    //   sqrt(R) sqrt(R) * Y * sqrt(L) sqrt(L)      (R, L unit-modulus diagonals, Y = [c -s; s c], c, s >= 0)
+    // five subslots whose lifts all have plain signs for any angle.  Both forms are uploaded:
+    // matrices for the v1 kernel, lifting coefficients for v2.
+    const int B = st->batch;
+    SlotMap sm; sm.first.resize(nslots); sm.count.resize(nslots);
+    bool all_liftable = true;
+    std::vector<int> kinds(nslots);
+    auto plain_kind = [](const double* m) {
+        LiftCoef L; int k = lift_classify(m, L);
+        if (k == LK_PERMX) return (int)LK_NONE;
+        if (k != LK_NONE && (L.mk[0] | L.mk[1] | L.mk[2] | L.mk[3])) return (int)LK_NONE;
+        return k;
+    };
+    for (int s = 0; s < nslots; ++s) {
+        int k0 = plain_kind(per_state_mats + (size_t)s * 8);
+        for (int b = 1; b < B && k0 != LK_NONE; ++b)
+            if (plain_kind(per_state_mats + ((size_t)b * nslots + s) * 8) != k0) k0 = LK_NONE;
+        kinds[s] = k0;
+        sm.first[s] = (int)sm.kind.size(); sm.count[s] = (k0 == LK_NONE) ? 5 : 1;
+        if (k0 == LK_NONE) { const int ks[5] = { LK_PHASE, LK_PHASE, LK_ROT, LK_PHASE, LK_PHASE }; sm.kind.insert(sm.kind.end(), ks, ks + 5); }
+        else sm.kind.push_back(k0);
     }
-    return run_circuit(st, gates, ngates, bytes ? st->d_slots : nullptr, nslots);
+    const int nsub = (int)sm.kind.size();
+    std::vector<double> mats((size_t)B * nsub * 8), lifts((size_t)B * nsub * 8, 0.0);
+    static const double I8[8] = { 1, 0, 0, 0, 0, 0, 1, 0 };
+    for (int b = 0; b < B; ++b)
+        for (int s = 0; s < nslots; ++s) {
+            const double* m = per_state_mats + ((size_t)b * nslots + s) * 8;
+            double* mo = &mats[((size_t)b * nsub + sm.first[s]) * 8];
+            double* lo = &lifts[((size_t)b * nsub + sm.first[s]) * 8];
+            if (kinds[s] != LK_NONE) {
+                memcpy(mo, m, 64);
+                LiftCoef L; lift_classify(m, L); memcpy(lo, &L, 64);
+                continue;
+            }
+            double f[3][8];
+            if (!decompose_unitary(m, f)) {
+                all_liftable = false;      // v1 only: the first subslot carries the matrix, the rest are identities
+                memcpy(mo, m, 64); for (int i = 1; i < 5; ++i) memcpy(mo + 8 * i, I8, 64);
+                continue;
+            }
+            double piece[5][8];
+            for (int side = 0; side < 2; ++side) {          // f[0] = right phase, f[2] = left phase
+                const double* d = f[side == 0 ? 0 : 2];
+                double h[8] = { 1, 0, 0, 0, 0, 0, 1, 0 };
+                unit_sqrt(d[0], d[1], h[0], h[1]); unit_sqrt(d[6], d[7], h[6], h[7]);
+                memcpy(piece[side == 0 ? 0 : 3], h, 64); memcpy(piece[side == 0 ? 1 : 4], h, 64);
+            }
+            memcpy(piece[2], f[1], 64);
+            for (int i = 0; i < 5; ++i) {
+                memcpy(mo + 8 * i, piece[i], 64);
+                LiftCoef L; const int k = lift_classify(piece[i], L);
+                // an identity piece classifies as PHASE with zero shears; a rotation by exactly 0 is diagonal -> PHASE too
+                if (k != sm.kind[sm.first[s] + i] || (L.mk[0] | L.mk[1] | L.mk[2] | L.mk[3])) {
+                    if (i == 2 && k == LK_PHASE && !(L.mk[0] | L.mk[1] | L.mk[2] | L.mk[3])) { memset(&L, 0, sizeof(L)); }  // identity rotation: zero shears
+                    else all_liftable = false;
+                }
+                memcpy(lo + 8 * i, &L, 64);
+            }
+        }
+    if (!all_liftable) for (size_t i = 0; i < sm.kind.size(); ++i) sm.kind[i] = LK_NONE;
+    const size_t bytes = mats.size() * sizeof(double);
+    QM_TRY(ENSURE_DEV(st, d_slots, 2 * bytes));
+    // pageable host vectors: these copies return when the bytes have left the host buffers
+    CU(cudaMemcpyAsync(st->d_slots, mats.data(), bytes, cudaMemcpyHostToDevice, st->stream));
+    CU(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(st->d_slots) + bytes, lifts.data(), bytes, cudaMemcpyHostToDevice, st->stream));
+    CU(cudaStreamSynchronize(st->stream));
+    st->ctr.bytes_h2d += 2 * bytes;
+    const bool saved = st->pipeline;
+    if (!all_liftable) st->pipeline = false;
+    int rc = run_circuit(st, gates, ngates, st->d_slots, nsub, &sm, st->d_slots + mats.size());
+    st->pipeline = saved;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
