@@ -193,9 +193,17 @@ inline int lower_gates(const qm_gate* gates, int ng, int nbits, const int* perm,
     return QM_OK;
 }
 
+// Planner cost model, in FP64 FMA issue slots per amplitude as the v2 kernel spends them: a rotation
+// or a phase is three shears per real pair = 3 per amplitude, a controlled gate touches half of the
+// amplitudes, an X/CNOT moves data without arithmetic; every gate also pays ~1 for its dispatch.
+// A general 2x2 (v1 kernel, or before it is split into phase*rot*phase) costs 8.
 inline double gate_cost(const LGate& g) {
-    double c = g.diag ? 4.0 : 8.0;     // DFMA-equivalents per amplitude
-    return g.ctrl >= 0 ? 0.5 * c : c;
+    const bool is_x = !g.diag && g.m[0] == 0 && g.m[1] == 0 && g.m[6] == 0 && g.m[7] == 0 && g.m[2] == 1 && g.m[3] == 0 &&
+                      g.m[4] == 1 && g.m[5] == 0;
+    const bool real_or_rx = (g.m[1] == 0 && g.m[7] == 0) && ((g.m[3] == 0 && g.m[5] == 0) || (g.m[2] == 0 && g.m[4] == 0));
+    double c = is_x ? 0.5 : (g.diag || real_or_rx || g.slot >= 0) ? 3.0 : 8.0;
+    if (g.ctrl >= 0) c *= 0.5;
+    return c + 1.0;
 }
 
 // Commutation-aware pull: walk the not-yet-done gates in order; take a gate when no earlier

@@ -369,7 +369,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     Planner pl;
     pl.opt.n_local = st->nl; pl.opt.n_global = st->g;
     pl.opt.tile_bits = st->tile_bits; pl.opt.low_bits = st->low_bits; pl.opt.fuse = st->fuse;
-    if (st->max_cost > 0) pl.opt.max_cost = st->max_cost < 8.0 ? 8.0 : st->max_cost;
+    if (st->max_cost > 0) pl.opt.max_cost = st->max_cost < 9.0 ? 9.0 : st->max_cost;
     if (st->pipeline) { pl.opt.max_runs = 3; pl.opt.max_subs = kV2MaxSubs; pl.opt.max_groups = kV2MaxGroups; }
     std::vector<PlanPass> passes;          // of the current segment (between remaps)
     std::vector<unsigned char> blob;
@@ -888,7 +888,7 @@ extern "C" int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t 
     Planner pl;
     pl.opt.n_local = n_qubits - global_bits; pl.opt.n_global = global_bits;
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
-    if (max_cost > 0) pl.opt.max_cost = max_cost < 8.0 ? 8.0 : max_cost;
+    if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
     pl.done.assign(pl.gates.size(), 0);

@@ -34,7 +34,7 @@ struct qm_state {
     // options
     bool eager = false, fuse = true, remap = false, pipeline = true;
     int tile_bits = 12, low_bits = 5;
-    double max_cost = 0.0;   // per-pass DFMA-equivalents per amplitude (0 = unlimited)
+    double max_cost = 32.0;  // per-pass cap of the planner cost model (planner.hpp gate_cost); 0 = unlimited
     // queue
     std::vector<qm_gate> queue;
     // logical -> physical qubit map (identity unless a sharded remap happened)

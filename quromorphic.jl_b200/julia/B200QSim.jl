@@ -1,0 +1,184 @@
+# B200QSim.jl — Julia host shim: the third "method family" of Quromorphic.QSim / QInfo.
+#
+# The reference dispatches every function on the state's concrete type and ships two families,
+# Vector{ComplexF64} and Matrix{ComplexF64} (src/Quantum/QSim.jl:52-383).  This file adds a third,
+# `B200State`, whose methods are one `ccall` each into libqm_b200.so (include/qm_b200.h).  User code
+# written against QSim keeps working after `s = statevector(n, m)` is replaced by
+# `s = B200State(n, m)`.
+#
+# STATUS: Julia is not installed in the build image or on the GPU box, so this file has been
+# reviewed against include/qm_b200.h but NEVER EXECUTED.  The same ABI is exercised by the Python
+# mirror quromorphic.jl_b200/qsim.py, which is what tests/ run.  Every conversion below (1-based
+# qubit -> 0-based bit, the reference's control map, argument checks and their order) is the same
+# code as in qsim.py, where it is tested.
+module B200QSim
+
+using Quromorphic.QSim: H, X, Y, Z, I2, rx_gate, ry_gate, rz_gate
+import Quromorphic.QSim: nb, u2!, h!, x!, y!, z!, rx!, ry!, rz!, controlled!, cnot!, crx!, cry!, crz!,
+                          swap!, mp, measure_z, measure_x, measure_y, prstate
+import Quromorphic.QInfo: partial_trace, entanglement_entropy, von_neumann_entropy
+
+export B200State, expect_z_all, reduced_density, sample, apply_circuit!, QMGate
+
+const LIB = get(ENV, "QM_B200_LIB", joinpath(@__DIR__, "..", "libqm_b200.so"))
+
+# struct qm_gate (80 bytes): kind, q0, q1, flags, m[8]
+struct QMGate
+    kind::Int32
+    q0::Int32
+    q1::Int32
+    flags::Int32
+    m::NTuple{8,Float64}
+end
+
+mutable struct B200State
+    handle::Ptr{Cvoid}
+    n::Int
+    batch::Int
+    mode::Symbol          # :reference reproduces controlled!'s index map (QSim.jl:181-197); :corrected does not
+    threshold::Float64    # measure_z's probability cut (QSim.jl:308)
+end
+
+function lasterror()
+    buf = Vector{UInt8}(undef, 512)
+    ccall((:qm_last_error, LIB), Int32, (Ptr{UInt8}, Int32), buf, 512)
+    unsafe_string(pointer(buf))
+end
+
+check(rc) = rc == 0 ? nothing : error(lasterror())      # ErrorException, like the reference
+
+"""
+    B200State(n, m = 0; batch = 1, device = 0, mode = :reference, threshold = 1e-10)
+
+`statevector(n, m)` (QSim.jl:33-37) on the GPU.
+"""
+function B200State(n::Int, m::Int = 0; batch::Int = 1, device::Int = 0, mode::Symbol = :reference,
+                   threshold::Float64 = 1e-10)
+    0 <= m < (1 << n) || throw(BoundsError())            # statevector(n, m) indexes s[m+1]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qm_create, LIB), Int32, (Int32, UInt64, Int32, Int32, Ptr{Ptr{Cvoid}}), n, m, batch, device, h))
+    st = B200State(h[], n, batch, mode, threshold)
+    finalizer(s -> (s.handle != C_NULL && ccall((:qm_destroy, LIB), Int32, (Ptr{Cvoid},), s.handle); s.handle = C_NULL), st)
+    st
+end
+
+"upload: `B200State(v)`"
+function B200State(v::Vector{ComplexF64}; kw...)
+    n = round(Int, log2(length(v)))
+    (1 << n) == length(v) || error("state length must be a power of two")
+    st = B200State(n, 0; kw...)
+    check(ccall((:qm_upload, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, UInt64, Int32), st.handle, v, length(v), 0))
+    st
+end
+
+"download: `Vector{ComplexF64}(st)`"
+function Base.Vector{ComplexF64}(st::B200State; batch_idx::Int = 0)
+    v = Vector{ComplexF64}(undef, 1 << st.n)
+    check(ccall((:qm_download, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, UInt64, Int32), st.handle, v, length(v), batch_idx))
+    v
+end
+Base.length(st::B200State) = 1 << st.n
+nb(st::B200State) = st.n                                  # QSim.jl:48
+
+# ---- gates ------------------------------------------------------------------------------------
+# A Matrix{ComplexF64} 2x2 is already the 8 doubles the ABI wants (column-major, interleaved).
+function u2!(s::B200State, t::Int, U::Matrix{ComplexF64})  # QSim.jl:52-63
+    1 <= t <= s.n || error("Qubit index out of range")
+    check(ccall((:qm_apply_u2, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{ComplexF64}), s.handle, t - 1, U))
+    s
+end
+h!(s::B200State, t::Int) = u2!(s, t, H)
+x!(s::B200State, t::Int) = u2!(s, t, X)
+y!(s::B200State, t::Int) = u2!(s, t, Y)
+z!(s::B200State, t::Int) = u2!(s, t, Z)
+rx!(s::B200State, t::Int, theta::Real) = u2!(s, t, rx_gate(theta))
+ry!(s::B200State, t::Int, theta::Real) = u2!(s, t, ry_gate(theta))
+rz!(s::B200State, t::Int, theta::Real) = u2!(s, t, rz_gate(theta))
+
+"what controlled!(s, c, t, V) really acts on (QSim.jl:181-197): qubits (b-1, b), b = max(c, t)"
+effective_ct(c::Int, t::Int) = (b = max(c, t); c < t ? (b - 1, b) : (b, b - 1))
+
+function controlled!(s::B200State, c::Int, t::Int, V::Matrix{ComplexF64})   # QSim.jl:175-203
+    (c <= s.n && t <= s.n && c >= 1 && t >= 1) || error("Qubit index out of range")   # :177 (range first)
+    c == t && error("Control and target cannot be the same qubit")                    # :178
+    ce, te = s.mode === :reference ? effective_ct(c, t) : (c, t)
+    check(ccall((:qm_apply_controlled, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{ComplexF64}), s.handle, ce - 1, te - 1, V))
+    s
+end
+cnot!(s::B200State, c::Int, t::Int) = controlled!(s, c, t, X)
+crx!(s::B200State, c::Int, t::Int, theta::Real) = controlled!(s, c, t, rx_gate(theta))
+cry!(s::B200State, c::Int, t::Int, theta::Real) = controlled!(s, c, t, ry_gate(theta))
+crz!(s::B200State, c::Int, t::Int, theta::Real) = controlled!(s, c, t, rz_gate(theta))
+
+function swap!(s::B200State, q1::Int, q2::Int)            # QSim.jl:262-275
+    (q1 <= s.n && q2 <= s.n && q1 >= 1 && q2 >= 1) || error("Qubit index out of range")
+    q1 == q2 && return s
+    cnot!(s, q1, q2); cnot!(s, q2, q1); cnot!(s, q1, q2)
+    s
+end
+
+"apply a whole gate list (0-based textbook bits, the wire format) in as few HBM passes as possible"
+function apply_circuit!(s::B200State, gates::Vector{QMGate})
+    check(ccall((:qm_apply_circuit, LIB), Int32, (Ptr{Cvoid}, Ptr{QMGate}, Int32), s.handle, gates, length(gates)))
+    s
+end
+
+# ---- readouts -----------------------------------------------------------------------------------
+function mp(s::B200State; batch_idx::Int = 0)             # QSim.jl:293
+    p = Vector{Float64}(undef, 1 << s.n)
+    check(ccall((:qm_probs, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), s.handle, p, batch_idx))
+    p
+end
+
+function _measure(s::B200State, t::Int, R::Union{Nothing,Matrix{ComplexF64}}, batch_idx::Int)
+    1 <= t <= s.n || error("Qubit index out of range")
+    out = Vector{Float64}(undef, 2)
+    Rp = R === nothing ? Ptr{ComplexF64}(C_NULL) : pointer(R)
+    GC.@preserve R check(ccall((:qm_measure_with, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{ComplexF64}, Float64, Int32, Ptr{Float64}),
+                               s.handle, t - 1, Rp, s.threshold, batch_idx, out))
+    (out[1], out[2])
+end
+measure_z(s::B200State, t::Int; batch_idx::Int = 0) = _measure(s, t, nothing, batch_idx)          # QSim.jl:297-318
+measure_x(s::B200State, t::Int; batch_idx::Int = 0) = _measure(s, t, H, batch_idx)                # QSim.jl:320-324
+measure_y(s::B200State, t::Int; batch_idx::Int = 0) = _measure(s, t, rx_gate(π / 2), batch_idx)   # QSim.jl:326-330
+
+"all-qubit measure_z in one pass: 2 x n x batch array of (p0, p1)"
+function expect_z_all(s::B200State; threshold::Float64 = s.threshold)
+    out = Array{Float64}(undef, 2, s.n, s.batch)
+    check(ccall((:qm_expect_z_all, LIB), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}), s.handle, threshold, out))
+    out
+end
+
+function prstate(s::B200State)                            # QSim.jl:367-373, after a download
+    v = Vector{ComplexF64}(s)
+    for i in 0:(length(v) - 1)
+        a = v[i + 1]
+        abs(a) > 1e-10 && println("|", lpad(string(i, base = 2), s.n, '0'), "⟩: ", a)
+    end
+end
+
+# ---- QInfo --------------------------------------------------------------------------------------
+"2^k x 2^k reduced density matrix straight from psi; keep_low keeps B (the low k qubits)"
+function reduced_density(s::B200State, keep_low::Bool, k::Int; batch_idx::Int = 0)
+    d = 1 << k
+    rho = Matrix{ComplexF64}(undef, d, d)                 # column-major, as the ABI writes it
+    check(ccall((:qm_reduced_density, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{ComplexF64}), s.handle, keep_low ? 1 : 0, k, batch_idx, rho))
+    rho
+end
+
+"partial_trace(statevector_to_density_matrix(s), dim_A, dim_B, subsystem) without forming rho (QInfo.jl:381-405)"
+function partial_trace(s::B200State, dim_A::Int, dim_B::Int, subsystem::Int)
+    @assert dim_A * dim_B == (1 << s.n) "Dimension mismatch"
+    kA, kB = round(Int, log2(dim_A)), round(Int, log2(dim_B))
+    @assert (1 << kA) == dim_A && (1 << kB) == dim_B "Dimension mismatch"
+    subsystem == 1 ? reduced_density(s, true, kB) : reduced_density(s, false, kA)
+end
+entanglement_entropy(s::B200State, dim_A::Int, dim_B::Int) = von_neumann_entropy(partial_trace(s, dim_A, dim_B, 2))
+
+function sample(s::B200State, seed::Integer, nshots::Int; batch_idx::Int = 0)
+    out = Vector{UInt64}(undef, nshots)
+    check(ccall((:qm_sample, LIB), Int32, (Ptr{Cvoid}, UInt64, Int32, Int32, Ptr{UInt64}), s.handle, seed, nshots, batch_idx, out))
+    out
+end
+
+end # module
