@@ -88,6 +88,7 @@ typedef struct qm_counters_t {
     uint64_t bytes_d2h;      /* device->host bytes copied (readouts, downloads)  */
     double   ms_device;      /* CUDA-event time of the last flushed circuit     */
     double   ms_plan;        /* host planning time of the last flushed circuit  */
+    double   ms_remap;       /* CUDA-event time spent in global-qubit remaps (all-to-all) since reset */
 } qm_counters_t;
 
 /* ---- lifetime -------------------------------------------------------------------- */

@@ -27,7 +27,7 @@ class Counters(C.Structure):
     _fields_ = [("gates", C.c_uint64), ("passes", C.c_uint64), ("launches", C.c_uint64),
                 ("bytes_hbm", C.c_uint64), ("bytes_link", C.c_uint64), ("bytes_h2d", C.c_uint64),
                 ("bytes_d2h", C.c_uint64), ("ms_device", C.c_double),
-                ("ms_plan", C.c_double)]
+                ("ms_plan", C.c_double), ("ms_remap", C.c_double)]
 
 
 class QMError(RuntimeError):

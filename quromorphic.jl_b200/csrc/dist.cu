@@ -1,17 +1,200 @@
-// dist.cu — sharded registers (placeholder until the single-GPU path is measured)
+// dist.cu — sharded registers.  Rank r of G = 2^g holds the 2^(n-g) amplitudes whose top g index bits
+// equal r.  Everything that does not need a non-diagonal target on a global qubit runs locally (a
+// control or a diagonal target on a global qubit is a rank predicate / rank-dependent phase inside
+// the ordinary kernels).  When the planner runs out of local work, the g global qubits are exchanged
+// with the top g local ones: viewed as [2^g chunks][2^(n-2g)], chunk j of rank r trades places with
+// chunk r of rank j — an all-to-all done IN PLACE through a small staging ring, because a 2^33
+// amplitude shard (128 GiB) leaves no room for an out-of-place copy on a 180 GB part.
+// NCCL (grouped ncclSend/ncclRecv over NVLink 5 / NVSwitch) is dlopen'ed on first use.
 #include "dist.hpp"
 
-struct DistCtx { int unused; };
+#include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
 
-int dist_destroy(DistCtx* d) { delete d; return QM_OK; }
-int dist_run_circuit(qm_state*, const qm_gate*, int) { return set_err(QM_ERR_STATE, "sharded path not built"); }
-int dist_canonicalize(qm_state*) { return QM_OK; }
-int dist_finish_z(qm_state*, const double*, const double*, double*) { return set_err(QM_ERR_STATE, "sharded path not built"); }
-int dist_finish_norm(qm_state*, double, double*) { return set_err(QM_ERR_STATE, "sharded path not built"); }
-int dist_measure(qm_state*, int, double, const double*, double*) { return set_err(QM_ERR_STATE, "sharded path not built"); }
-int dist_reduced_density(qm_state*, int, int, double*) { return set_err(QM_ERR_STATE, "sharded path not built"); }
+using namespace qm;
 
-extern "C" int32_t qm_dist_unique_id(uint8_t*) { return set_err(QM_ERR_STATE, "sharded path not built"); }
-extern "C" int32_t qm_create_dist(int32_t, uint64_t, int32_t, int32_t, int32_t, const uint8_t*, qm_state**) {
-    return set_err(QM_ERR_STATE, "sharded path not built");
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { kNcclSum = 0, kNcclFloat64 = 8 };
+
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.h) return QM_OK;
+    const char* names[] = { getenv("QM_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+    void* h = nullptr;
+    for (const char* nm : names) { if (nm && *nm) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; } }
+    if (!h) return set_err(QM_ERR_COMM, "cannot dlopen libnccl.so.2 (set QM_NCCL_LIB): %s", dlerror());
+#define LOADSYM(field, sym) do { *(void**)(&g_nccl.field) = dlsym(h, sym); if (!g_nccl.field) return set_err(QM_ERR_COMM, "libnccl: missing %s", sym); } while (0)
+    LOADSYM(GetUniqueId, "ncclGetUniqueId"); LOADSYM(CommInitRank, "ncclCommInitRank"); LOADSYM(CommDestroy, "ncclCommDestroy");
+    LOADSYM(Send, "ncclSend"); LOADSYM(Recv, "ncclRecv"); LOADSYM(AllReduce, "ncclAllReduce");
+    LOADSYM(GroupStart, "ncclGroupStart"); LOADSYM(GroupEnd, "ncclGroupEnd"); LOADSYM(GetErrorString, "ncclGetErrorString");
+#undef LOADSYM
+    g_nccl.h = h;
+    return QM_OK;
+}
+#define NC(x) do { int r_ = (x); if (r_ != 0) return set_err(QM_ERR_COMM, "%s failed: %s", #x, g_nccl.GetErrorString(r_)); } while (0)
+
+struct DistCtx {
+    ncclComm_t comm = nullptr;
+    double2* stage = nullptr; size_t stage_amps = 0;     // (world - 1) x sub-chunk
+    double* d_small = nullptr;                           // all-reduce scratch
+    bool swapped = false;                                // layout B: global qubits currently sit on the top local bits
+};
+
+int dist_destroy(DistCtx* d) {
+    if (!d) return QM_OK;
+    if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    cudaFree(d->stage); cudaFree(d->d_small);
+    delete d;
+    return QM_OK;
+}
+
+extern "C" int32_t qm_dist_unique_id(uint8_t id_out[128]) {
+    if (!id_out) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(nccl_load());
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, id.internal, 128);
+    return QM_OK;
+}
+
+extern "C" int32_t qm_create_dist(int32_t n, uint64_t basis, int32_t device, int32_t rank, int32_t world,
+                                  const uint8_t nccl_id[128], qm_state** out) {
+    if (!nccl_id || !out) return set_err(QM_ERR_ARG, "null argument");
+    if (world < 2) return set_err(QM_ERR_ARG, "world must be >= 2 (use qm_create for one GPU)");
+    QM_TRY(nccl_load());
+    QM_TRY(qm_create_common(n, basis, 1, device, rank, world, out));
+    qm_state* st = *out;
+    if (2 * st->g > st->n) { qm_destroy(st); *out = nullptr; return set_err(QM_ERR_ARG, "register too small for %d ranks", world); }
+    DistCtx* d = new DistCtx();
+    ncclUniqueId id; memcpy(id.internal, nccl_id, 128);
+    int r = g_nccl.CommInitRank(&d->comm, world, id, rank);
+    if (r != 0) { delete d; qm_destroy(st); *out = nullptr; return set_err(QM_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
+    // staging ring: (world - 1) sub-chunks of at most 2^24 amplitudes (256 MiB) each
+    const uint64_t chunk = 1ull << (st->nl - st->g);
+    uint64_t sub = chunk < (1ull << 24) ? chunk : (1ull << 24);
+    d->stage_amps = sub;
+    CU(cudaMalloc((void**)&d->stage, (size_t)(world - 1) * sub * 16));
+    CU(cudaMalloc((void**)&d->d_small, 4096 * sizeof(double)));
+    st->dist = d;
+    return QM_OK;
+}
+
+int dist_remap(qm_state* st, std::vector<LGate>* gates, std::vector<char>* done) {
+    DistCtx* d = st->dist;
+    if (!d) return set_err(QM_ERR_STATE, "not a sharded register");
+    CU(cudaSetDevice(st->device));
+    const int g = st->g, nl = st->nl, W = st->world, r = st->rank;
+    const uint64_t chunk = 1ull << (nl - g), sub = d->stage_amps;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, st->stream));
+    for (uint64_t off = 0; off < chunk; off += sub) {
+        NC(g_nccl.GroupStart());
+        int slot = 0;
+        for (int j = 0; j < W; ++j) {
+            if (j == r) continue;
+            NC(g_nccl.Send(st->amp + (uint64_t)j * chunk + off, (size_t)sub * 2, kNcclFloat64, j, d->comm, st->stream));
+            NC(g_nccl.Recv(d->stage + (uint64_t)slot * sub, (size_t)sub * 2, kNcclFloat64, j, d->comm, st->stream));
+            ++slot;
+        }
+        NC(g_nccl.GroupEnd());
+        slot = 0;
+        for (int j = 0; j < W; ++j) {
+            if (j == r) continue;
+            CU(cudaMemcpyAsync(st->amp + (uint64_t)j * chunk + off, d->stage + (uint64_t)slot * sub, (size_t)sub * 16,
+                               cudaMemcpyDeviceToDevice, st->stream));
+            ++slot;
+        }
+    }
+    CU(cudaEventRecord(e1, st->stream));
+    st->remap_events.push_back(std::make_pair(e0, e1));
+    st->ctr.bytes_link += (uint64_t)(W - 1) * chunk * 16;
+    st->ctr.bytes_hbm += 2ull * (uint64_t)(W - 1) * chunk * 16 * 2;      // send read + stage write, stage read + place write
+    st->ctr.launches += (uint64_t)((chunk + sub - 1) / sub);
+    d->swapped = !d->swapped;
+    for (int q = 0; q < st->n; ++q) st->perm[q] = dist_swap_bit(st->perm[q], nl, g);
+    if (gates)
+        for (size_t i = 0; i < gates->size(); ++i) {
+            if (done && (*done)[i]) continue;
+            LGate& x = (*gates)[i];
+            x.target = dist_swap_bit(x.target, nl, g);
+            if (x.ctrl >= 0) x.ctrl = dist_swap_bit(x.ctrl, nl, g);
+        }
+    return QM_OK;
+}
+
+int dist_canonicalize(qm_state* st) {
+    if (!st->dist || !st->dist->swapped) return QM_OK;
+    return dist_remap(st, nullptr, nullptr);
+}
+
+// sum `count` doubles over the ranks (host in/out); goes through a small device buffer
+static int allreduce_host(qm_state* st, double* v, int count) {
+    DistCtx* d = st->dist;
+    if (count > 4096) return set_err(QM_ERR_ARG, "allreduce too large");
+    CU(cudaMemcpyAsync(d->d_small, v, count * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+    NC(g_nccl.AllReduce(d->d_small, d->d_small, (size_t)count, kNcclFloat64, kNcclSum, d->comm, st->stream));
+    CU(cudaMemcpyAsync(v, d->d_small, count * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
+    CU(cudaStreamSynchronize(st->stream));
+    return QM_OK;
+}
+
+// pairs: local [nl][2] (p0, p1) per physical local bit, tot: local kept mass.  out: [n][2] per LOGICAL qubit.
+int dist_finish_z(qm_state* st, const double* pairs, const double* tot, double* out_host) {
+    const int n = st->n, nl = st->nl, g = st->g;
+    std::vector<double> v(n + 1, 0.0);
+    for (int b = 0; b < nl; ++b) v[b] = pairs[2 * b + 1];                       // kept mass with physical bit b set
+    for (int j = 0; j < g; ++j) v[nl + j] = ((st->rank >> j) & 1) ? tot[0] : 0.0;
+    v[n] = tot[0];
+    QM_TRY(allreduce_host(st, v.data(), n + 1));
+    for (int q = 0; q < n; ++q) {
+        const double p1 = v[st->perm[q]];
+        out_host[2 * q] = v[n] - p1; out_host[2 * q + 1] = p1;
+    }
+    return QM_OK;
+}
+
+int dist_finish_norm(qm_state* st, double local_tot, double* out) {
+    double v = local_tot;
+    QM_TRY(allreduce_host(st, &v, 1));
+    *out = v;
+    return QM_OK;
+}
+
+int dist_measure(qm_state* st, int t0, double thr, const double* R, double out[2]) {
+    int tb = st->perm[t0];
+    if (tb >= st->nl && R) {            // a rotated basis needs the pair on one rank: bring the qubit home
+        QM_TRY(dist_remap(st, nullptr, nullptr));
+        tb = st->perm[t0];
+    }
+    double v[2];
+    if (tb < st->nl) QM_TRY(qm_measure_phys(st, tb, thr, 0, R, v));
+    else {
+        double *pairs, *tot;
+        QM_TRY(qm_zstats(st, thr, &pairs, &tot));
+        const bool set = (st->rank >> (tb - st->nl)) & 1;
+        v[0] = set ? 0.0 : tot[0]; v[1] = set ? tot[0] : 0.0;
+    }
+    QM_TRY(allreduce_host(st, v, 2));
+    out[0] = v[0]; out[1] = v[1];
+    return QM_OK;
+}
+
+int dist_reduced_density(qm_state*, int, int, double*) {
+    return set_err(QM_ERR_STATE, "reduced density of a sharded register is not implemented (gather the kept qubits first)");
 }

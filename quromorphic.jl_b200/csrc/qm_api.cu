@@ -54,7 +54,7 @@ static int grid_for(uint64_t work_items, int threads, int sms, int per_sm) {
 // ---------------------------------------------------------------------------------------------
 // lifetime
 // ---------------------------------------------------------------------------------------------
-static int create_common(int n, uint64_t basis, int batch, int device, int rank, int world, qm_state** out) {
+int qm_create_common(int n, uint64_t basis, int batch, int device, int rank, int world, qm_state** out) {
     if (!out) return set_err(QM_ERR_ARG, "out is null");
     *out = nullptr;
     if (n < 1 || n > 62) return set_err(QM_ERR_ARG, "n_qubits %d out of range", n);
@@ -85,7 +85,7 @@ static int create_common(int n, uint64_t basis, int batch, int device, int rank,
 }
 
 extern "C" int32_t qm_create(int32_t n, uint64_t basis, int32_t batch, int32_t device, qm_state** out) {
-    return create_common(n, basis, batch, device, 0, 1, out);
+    return qm_create_common(n, basis, batch, device, 0, 1, out);
 }
 
 extern "C" int32_t qm_destroy(qm_state* st) {
@@ -374,15 +374,13 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     std::vector<PlanPass> passes;          // of the current segment (between remaps)
     std::vector<unsigned char> blob;
     std::vector<size_t> offs;
-    int pos = 0;                           // wire gates consumed so far
     bool first_event = true;
-    while (pos < ngates) {
-        // plan everything that is left under the current qubit map
-        pl.gates.clear(); pl.done.clear(); pl.first = 0;
-        int rc = lower_gates(gates + pos, ngates - pos, st->n, st->perm.data(), st->fuse, pl.gates, smap);
-        if (rc) return set_err(rc, "bad gate in circuit (index >= %d)", pos);
-        if (st->pipeline) prepare_for_lifting(pl.gates);
-        pl.done.assign(pl.gates.size(), 0);
+    // lower once under the current logical->physical map; a remap later relabels what is left
+    int rc = lower_gates(gates, ngates, st->n, st->perm.data(), st->fuse, pl.gates, smap);
+    if (rc) return set_err(rc, "bad gate in circuit");
+    if (st->pipeline) prepare_for_lifting(pl.gates);
+    pl.done.assign(pl.gates.size(), 0);
+    while (true) {
         passes.clear(); blob.clear(); offs.clear();
         PlanPass P;
         std::vector<char> use_v2;
@@ -405,7 +403,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         // upload + launch
         if (!passes.empty()) {
             QM_TRY(ENSURE_DEV(st, d_blob, blob.size()));
-            if (st->h_blob_cap < blob.size() || true) CU(cudaEventSynchronize(st->ev_stage));   // staging buffer free?
+            CU(cudaEventSynchronize(st->ev_stage));      // pinned staging buffer free again?
             QM_TRY(ENSURE_PIN(st, h_blob, blob.size()));
             memcpy(st->h_blob, blob.data(), blob.size());
             if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
@@ -418,10 +416,10 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             }
         }
         if (!leftover) break;
-        // sharded: the remaining gates need a non-diagonal target on a global qubit.  The lowered
-        // list does not map 1:1 to wire gates (merging), so the remap path re-plans from the wire
-        // gates that are not finished yet — handled by dist_remap_and_continue.
-        return set_err(QM_ERR_STATE, "gate on a sharded qubit needs a remap (use the dist path)");
+        // sharded register: what is left needs a non-diagonal target on a global qubit.  Exchange the
+        // global qubits with the top local ones (all-to-all over NVLink) and relabel the pending gates.
+        if (passes.empty() && !pl.pending_global_target()) return set_err(QM_ERR_STATE, "planner stalled (internal error)");
+        QM_TRY(dist_remap(st, &pl.gates, &pl.done));
     }
     if (!first_event) { CU(cudaEventRecord(st->ev1, st->stream)); st->ev_pending = true; }
     st->ctr.gates += ngates;
@@ -493,7 +491,6 @@ extern "C" int32_t qm_apply_circuit(qm_state* st, const qm_gate* gates, int32_t 
     if (!st || (!gates && ngates > 0) || ngates < 0) return set_err(QM_ERR_ARG, "null argument");
     QM_TRY(validate_gates(st, gates, ngates, 0));
     QM_TRY(flush(st));
-    if (st->dist) return dist_run_circuit(st, gates, ngates);
     return run_circuit(st, gates, ngates, nullptr, 0);
 }
 
@@ -597,6 +594,12 @@ extern "C" int32_t qm_sync(qm_state* st) {
         float ms = 0.f; CU(cudaEventElapsedTime(&ms, st->ev0, st->ev1));
         st->ctr.ms_device = ms; st->ev_pending = false;
     }
+    for (auto& pr : st->remap_events) {
+        float ms = 0.f; CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        st->ctr.ms_remap += ms;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    st->remap_events.clear();
     return QM_OK;
 }
 
@@ -646,7 +649,7 @@ extern "C" int32_t qm_probs(qm_state* st, double* out_host, int32_t batch_idx) {
 }
 
 // all-qubit z marginals of every register into st->h_scratch: [batch][nl][2] then [batch] totals
-static int zstats(qm_state* st, double thr, double** h_pairs, double** h_tot) {
+int qm_zstats(qm_state* st, double thr, double** h_pairs, double** h_tot) {
     const int nl = st->nl;
     int cb = nl < kZMaxChunkBits ? nl : kZMaxChunkBits;
     int rest = nl - cb;                                    // chunk-index bits per register
@@ -679,7 +682,7 @@ extern "C" int32_t qm_expect_z_all(qm_state* st, double threshold, double* out_h
     QM_TRY(flush(st));
     CU(cudaSetDevice(st->device));
     double *pairs, *tot;
-    QM_TRY(zstats(st, threshold, &pairs, &tot));
+    QM_TRY(qm_zstats(st, threshold, &pairs, &tot));
     if (st->dist) return dist_finish_z(st, pairs, tot, out_host);
     memcpy(out_host, pairs, (size_t)st->batch * st->nl * 2 * sizeof(double));
     return QM_OK;
@@ -691,7 +694,7 @@ extern "C" int32_t qm_norm2(qm_state* st, int32_t batch_idx, double* out) {
     QM_TRY(flush(st));
     CU(cudaSetDevice(st->device));
     double *pairs, *tot;
-    QM_TRY(zstats(st, -1.0, &pairs, &tot));
+    QM_TRY(qm_zstats(st, -1.0, &pairs, &tot));
     if (st->dist) return dist_finish_norm(st, tot[0], out);
     *out = tot[batch_idx];
     return QM_OK;
@@ -699,9 +702,7 @@ extern "C" int32_t qm_norm2(qm_state* st, int32_t batch_idx, double* out) {
 
 static const double kHmat[8] = { 0.7071067811865475, 0, 0.7071067811865475, 0, 0.7071067811865475, 0, -0.7071067811865475, 0 };
 
-static int measure_one(qm_state* st, int basis, int t0, double thr, int batch_idx, const double* R, double out[2]) {
-    (void)basis;
-    int tb = st->perm[t0];
+int qm_measure_phys(qm_state* st, int tb, double thr, int batch_idx, const double* R, double out[2]) {
     if (tb >= st->nl) return set_err(QM_ERR_STATE, "internal: measurement target is not local");
     Mat2 U; int identity = (R == nullptr);
     if (R) memcpy(U.v, R, sizeof(U.v)); else memset(&U, 0, sizeof(U));
@@ -742,7 +743,7 @@ extern "C" int32_t qm_measure(qm_state* st, int32_t basis, int32_t t0, double th
     if (basis == QM_BASIS_X) Rp = kHmat;
     else if (basis == QM_BASIS_Y) { y_rotation(R); Rp = R; }
     if (st->dist) return dist_measure(st, t0, threshold, Rp, out);
-    return measure_one(st, basis, t0, threshold, batch_idx, Rp, out);
+    return qm_measure_phys(st, st->perm[t0], threshold, batch_idx, Rp, out);
 }
 
 extern "C" int32_t qm_measure_with(qm_state* st, int32_t t0, const double* R, double threshold, int32_t batch_idx, double out[2]) {
@@ -752,7 +753,7 @@ extern "C" int32_t qm_measure_with(qm_state* st, int32_t t0, const double* R, do
     QM_TRY(flush(st));
     CU(cudaSetDevice(st->device));
     if (st->dist) return dist_measure(st, t0, threshold, R, out);
-    return measure_one(st, R ? QM_BASIS_X : QM_BASIS_Z, t0, threshold, batch_idx, R, out);
+    return qm_measure_phys(st, st->perm[t0], threshold, batch_idx, R, out);
 }
 
 extern "C" int32_t qm_expect_all(qm_state* st, int32_t basis, double threshold, double* out_host) {
@@ -894,6 +895,8 @@ extern "C" int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t 
     pl.done.assign(pl.gates.size(), 0);
     std::vector<qm_gate> v; std::vector<int32_t> po;
     PlanPass P; int pi = 0;
+    const int nl_ = n_qubits - global_bits;
+    for (int guard = 0; guard < 4 * ngates + 8; ++guard) {
     while (pl.next_pass(P)) {
         for (const PlanGroup& G : P.groups)
             for (const LGate& x : G.subs) {
@@ -907,6 +910,20 @@ extern "C" int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t 
                 v.push_back(w); po.push_back(pi);
             }
         ++pi;
+    }
+    bool left = false;
+    for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) { left = true; break; }
+    if (!left) break;
+    if (global_bits == 0) return set_err(QM_ERR_STATE, "planner stalled");
+    // what the sharded engine does here: exchange global and top local bits, relabel the pending gates.
+    // The remap is reported as a pseudo-gate of kind -1 (q0 = local bit base, q1 = number of bits).
+    qm_gate mk; memset(&mk, 0, sizeof(mk)); mk.kind = -1; mk.q0 = nl_ - global_bits; mk.q1 = global_bits;
+    v.push_back(mk); po.push_back(pi);
+    for (size_t i = 0; i < pl.gates.size(); ++i) {
+        if (pl.done[i]) continue;
+        pl.gates[i].target = dist_swap_bit(pl.gates[i].target, nl_, global_bits);
+        if (pl.gates[i].ctrl >= 0) pl.gates[i].ctrl = dist_swap_bit(pl.gates[i].ctrl, nl_, global_bits);
+    }
     }
     *out_len = (int32_t)v.size();
     if ((int32_t)v.size() > cap || !out) return set_err(QM_ERR_ARG, "output too small: need %d", (int)v.size());

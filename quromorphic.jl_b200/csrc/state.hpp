@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 #include <vector>
 
 #include "../../include/qm_b200.h"
@@ -46,6 +47,7 @@ struct qm_state {
     double* h_scratch = nullptr; size_t h_scratch_cap = 0;   // pinned
     double* d_slots = nullptr; size_t d_slots_cap = 0;
     qm_counters_t ctr{};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> remap_events;   // resolved into ctr.ms_remap at the next sync
     DistCtx* dist = nullptr;
 };
 
@@ -58,6 +60,6 @@ static inline uint64_t local_amps(const qm_state* st) { return 1ull << st->nl; }
 static inline uint64_t total_amps(const qm_state* st) { return (uint64_t)st->batch << st->nl; }
 
 // implemented in qm_api.cu, used by dist.cu
-int qm_run_local_circuit(qm_state* st, const qm_gate* gates, int ngates, int* consumed);
+int qm_create_common(int n, uint64_t basis, int batch, int device, int rank, int world, qm_state** out);
 int qm_zstats(qm_state* st, double thr, double** h_pairs, double** h_tot);
-int qm_measure_local(qm_state* st, int phys_bit, double thr, const double* R, double out[2]);
+int qm_measure_phys(qm_state* st, int phys_bit, double thr, int batch_idx, const double* R, double out[2]);

@@ -90,6 +90,23 @@ class B200State:
         self._h = h
 
     @classmethod
+    def create_dist(cls, n, rank, world, nccl_id, m=0, device=0, mode="reference", threshold=1e-10):
+        """this rank's shard of a register sharded over `world` GPUs (one process per GPU); nccl_id is the
+        128-byte id from unique_id(), broadcast by the host"""
+        h = L._vp()
+        idb = (C.c_uint8 * 128).from_buffer_copy(bytes(nccl_id))
+        L.check(L.lib().qm_create_dist(int(n), int(m), int(device), int(rank), int(world), idb, C.byref(h)))
+        st = cls(n, m, 1, device, mode, threshold, _handle=h)
+        st.world, st.rank = world, rank
+        return st
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        L.check(L.lib().qm_dist_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
     def from_numpy(cls, v, **kw):
         v = np.ascontiguousarray(v, dtype=np.complex128)
         n = int(round(np.log2(len(v))))
@@ -110,7 +127,8 @@ class B200State:
 
     @property
     def local_len(self):
-        return 1 << self.n
+        w = getattr(self, "world", 1)
+        return (1 << self.n) // w
 
     def __len__(self):
         return 1 << self.n

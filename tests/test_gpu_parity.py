@@ -273,3 +273,22 @@ def test_argument_errors(pkg):
         pkg.B200State(3, 8)
     with pytest.raises(AssertionError):
         pkg.qinfo.partial_trace(st, 4, 4, 1)            # QInfo.jl:382 "Dimension mismatch"
+
+
+@pytest.mark.parametrize("n", [14, 23])
+def test_sharded_two_gpus(pkg, n):
+    """needs >= 2 GPUs on the box (skipped otherwise): 2 ranks, one GPU each, NCCL remaps inside the engine"""
+    import os, socket, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    here = os.path.dirname(os.path.abspath(__file__))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(here, "gpu_dist_worker.py"), str(n)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert all("GPU_DIST_OK" in o for o in outs), "\n".join(outs)
