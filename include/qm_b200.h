@@ -163,6 +163,13 @@ int32_t qm_dist_unique_id(uint8_t id_out[128]);
 int32_t qm_create_dist(int32_t n_qubits, uint64_t basis_index, int32_t device, int32_t rank,
                        int32_t world, const uint8_t nccl_id[128], qm_state** out);
 
+/* Optional, after qm_create_dist: map the other ranks' shards into this process (CUDA IPC) so that the
+ * global<->local exchange is ONE kernel doing loads/stores over NVLink peer memory instead of NCCL
+ * send/recv through a staging ring.  Every rank exports 64 bytes, the host all-gathers them
+ * (world x 64 bytes, rank-major) and every rank imports.  If the import fails the engine keeps NCCL. */
+int32_t qm_dist_ipc_export(qm_state* st, uint8_t handle_out[64]);
+int32_t qm_dist_ipc_import(qm_state* st, const uint8_t* handles);
+
 /* ---- host-only planner introspection (works without a GPU; used by the CPU tests) ------
  * Plans `gates` for an n-qubit register with the given tile/low-bit sizes and `global_bits`
  * top qubits sharded; writes a flat int32 description of the passes into `out` (layout in

@@ -65,6 +65,8 @@ SIGNATURES = {
     "qm_dist_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),
     "qm_create_dist": (C.c_int32, [C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_uint8), C.POINTER(_vp)]),
+    "qm_dist_ipc_export": (C.c_int32, [_vp, C.POINTER(C.c_uint8)]),
+    "qm_dist_ipc_import": (C.c_int32, [_vp, C.POINTER(C.c_uint8)]),
     "qm_plan_describe": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int32,
                                      C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
     "qm_plan_gates": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _vp,

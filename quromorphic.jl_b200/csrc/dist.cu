@@ -48,7 +48,44 @@ static int nccl_load() {
 }
 #define NC(x) do { int r_ = (x); if (r_ != 0) return set_err(QM_ERR_COMM, "%s failed: %s", #x, g_nccl.GetErrorString(r_)); } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// K7  global<->local qubit exchange over peer memory.  Chunk j of rank r trades places with chunk r
+// of rank j.  Every rank runs ONE kernel: for each peer it owns half of the chunk pair (the lower
+// rank the first half, the higher rank the second), loads its own 16 bytes and the peer's 16 bytes
+// (a load over NVLink), and stores them crosswise (a store over NVLink).  In place, no staging, both
+// link directions busy; each amplitude pair is touched by exactly one thread of one rank.
+// Ranks are fenced before and after by a one-element NCCL all-reduce on the same stream (the kernel
+// itself never waits on another GPU).
+// ---------------------------------------------------------------------------------------------
+struct PeerPtrs { double2* p[16]; };
+
+__global__ void __launch_bounds__(512)
+k_remap_swap(double2* __restrict__ mine, PeerPtrs peers, int rank, int world, unsigned long long chunk) {
+    const unsigned long long half = chunk >> 1;
+    const unsigned long long per_peer = half;                      // amplitudes this rank moves per peer
+    const unsigned long long total = per_peer * (unsigned long long)(world - 1);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 4 * stride) {
+        double2 a[4], b[4]; unsigned long long mo[4], po[4]; double2* pp[4]; bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned long long ii = i + (unsigned long long)u * stride;
+            ok[u] = ii < total;
+            const unsigned long long q = ok[u] ? ii : 0;
+            int j = (int)(q / per_peer); const unsigned long long o = q % per_peer;
+            if (j >= rank) ++j;                                    // skip myself
+            const unsigned long long off = (rank < j ? 0ull : half) + o;
+            mo[u] = (unsigned long long)j * chunk + off; po[u] = (unsigned long long)rank * chunk + off; pp[u] = peers.p[j];
+            if (ok[u]) { a[u] = mine[mo[u]]; b[u] = pp[u][po[u]]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (ok[u]) { mine[mo[u]] = b[u]; pp[u][po[u]] = a[u]; }
+    }
+}
+
 struct DistCtx {
+    double2* peer[16] = { nullptr };                    // IPC-mapped shards of the other ranks (null: NCCL path)
+    bool have_peers = false;
     ncclComm_t comm = nullptr;
     double2* stage = nullptr; size_t stage_amps = 0;     // (world - 1) x sub-chunk
     double* d_small = nullptr;                           // all-reduce scratch
@@ -57,6 +94,7 @@ struct DistCtx {
 
 int dist_destroy(DistCtx* d) {
     if (!d) return QM_OK;
+    for (int j = 0; j < 16; ++j) if (d->peer[j]) cudaIpcCloseMemHandle(d->peer[j]);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     cudaFree(d->stage); cudaFree(d->d_small);
     delete d;
@@ -102,6 +140,20 @@ int dist_remap(qm_state* st, std::vector<LGate>* gates, std::vector<char>* done)
     const uint64_t chunk = 1ull << (nl - g), sub = d->stage_amps;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    if (d->have_peers && chunk >= 2) {
+        // fence, one exchange kernel over peer memory, fence
+        NC(g_nccl.AllReduce(d->d_small, d->d_small, 1, kNcclFloat64, kNcclSum, d->comm, st->stream));
+        CU(cudaEventRecord(e0, st->stream));
+        PeerPtrs pp; for (int j = 0; j < 16; ++j) pp.p[j] = d->peer[j];
+        const uint64_t total = (chunk >> 1) * (uint64_t)(W - 1);
+        uint64_t blocks = (total + 512ull * 4 - 1) / (512ull * 4);
+        const uint64_t cap = (uint64_t)st->sms * 4; if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
+        k_remap_swap<<<(unsigned)blocks, 512, 0, st->stream>>>(st->amp, pp, r, W, chunk);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e1, st->stream));
+        NC(g_nccl.AllReduce(d->d_small, d->d_small, 1, kNcclFloat64, kNcclSum, d->comm, st->stream));
+        st->ctr.launches += 1;
+    } else {
     CU(cudaEventRecord(e0, st->stream));
     for (uint64_t off = 0; off < chunk; off += sub) {
         NC(g_nccl.GroupStart());
@@ -122,10 +174,11 @@ int dist_remap(qm_state* st, std::vector<LGate>* gates, std::vector<char>* done)
         }
     }
     CU(cudaEventRecord(e1, st->stream));
+    st->ctr.launches += (uint64_t)((chunk + sub - 1) / sub);
+    }
     st->remap_events.push_back(std::make_pair(e0, e1));
     st->ctr.bytes_link += (uint64_t)(W - 1) * chunk * 16;
     st->ctr.bytes_hbm += 2ull * (uint64_t)(W - 1) * chunk * 16 * 2;      // send read + stage write, stage read + place write
-    st->ctr.launches += (uint64_t)((chunk + sub - 1) / sub);
     d->swapped = !d->swapped;
     for (int q = 0; q < st->n; ++q) st->perm[q] = dist_swap_bit(st->perm[q], nl, g);
     if (gates)
@@ -197,4 +250,38 @@ int dist_measure(qm_state* st, int t0, double thr, const double* R, double out[2
 
 int dist_reduced_density(qm_state*, int, int, double*) {
     return set_err(QM_ERR_STATE, "reduced density of a sharded register is not implemented (gather the kept qubits first)");
+}
+
+// ---- peer-memory mapping (CUDA IPC): every rank exports its shard, the host all-gathers the 64-byte
+// handles, every rank imports the others'.  Optional: without it the remap goes through NCCL.
+extern "C" int32_t qm_dist_ipc_export(qm_state* st, uint8_t handle_out[64]) {
+    if (!st || !st->dist || !handle_out) return set_err(QM_ERR_ARG, "not a sharded register");
+    CU(cudaSetDevice(st->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, st->amp));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &h, 64);
+    return QM_OK;
+}
+
+extern "C" int32_t qm_dist_ipc_import(qm_state* st, const uint8_t* handles /* [world][64] */) {
+    if (!st || !st->dist || !handles) return set_err(QM_ERR_ARG, "not a sharded register");
+    if (st->world > 16) return set_err(QM_ERR_ARG, "at most 16 ranks");
+    CU(cudaSetDevice(st->device));
+    DistCtx* d = st->dist;
+    for (int j = 0; j < st->world; ++j) {
+        if (j == st->rank) continue;
+        cudaIpcMemHandle_t h; memcpy(&h, handles + 64 * j, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int k = 0; k < 16; ++k) if (d->peer[k]) { cudaIpcCloseMemHandle(d->peer[k]); d->peer[k] = nullptr; }
+            d->have_peers = false;
+            return set_err(QM_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s — remaps stay on NCCL", j, cudaGetErrorString(e));
+        }
+        d->peer[j] = reinterpret_cast<double2*>(p);
+    }
+    d->have_peers = true;
+    return QM_OK;
 }

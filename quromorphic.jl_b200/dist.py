@@ -25,4 +25,20 @@ def sharded_state(n, m=0, **kw):
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
     box = [B200State.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
-    return B200State.create_dist(n, rank, world, box[0], m=m, device=local_rank, **kw)
+    st = B200State.create_dist(n, rank, world, box[0], m=m, device=local_rank, **kw)
+    if os.environ.get("QM_DIST_P2P", "1") != "0":
+        # peer-memory exchange: all-gather the CUDA IPC handles of the shards, map them
+        import ctypes as C
+        from . import _lib as L
+        mine = (C.c_uint8 * 64)()
+        L.check(L.lib().qm_dist_ipc_export(st._h, mine))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine))
+        blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+        rc = L.lib().qm_dist_ipc_import(st._h, blob)
+        st.p2p = (rc == 0)
+        oks = [None] * world
+        dist.all_gather_object(oks, st.p2p)
+        if not all(oks):
+            raise RuntimeError("CUDA IPC mapping failed on some rank (%s): set QM_DIST_P2P=0 to use NCCL" % L.last_error())
+    return st
