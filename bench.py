@@ -164,7 +164,10 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(ngpus, n):
+def workload_config(ngpus, n, c4=False):
+    if ngpus == 1 and c4:
+        return {"workload": "C4 base: %d-qubit reservoir step on one B200 (2^%d amplitudes), no exchange" % (n, n),
+                "n_qubits": n, "amps_per_gpu_log2": n, "seed": 3601, "l2": "state is far larger than L2"}
     if ngpus == 1:
         return {"workload": "C3: %d-qubit ComplexF64 random reservoir circuit, depth %d, fused gate passes, "
                             "all-qubit <Z> readout" % (n, C3_DEPTH),
@@ -188,6 +191,8 @@ def main():
     ap.add_argument("--low-bits", type=int, default=-1)
     ap.add_argument("--max-cost", type=float, default=-1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c4"],
+                    help="auto: C3 at N = 1, C4 at N > 1; c4 at N = 1 runs the 33-qubit weak-scaling base")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,7 +210,7 @@ def main():
     L = pkg._lib
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    if world > 1:
+    if world > 1 or args.workload == "c4":
         from bench_dist import run_dist            # sharded path (C4)
         run_dist(args, pkg, rank, world, local_rank)
         return

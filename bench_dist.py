@@ -19,10 +19,12 @@ def run_dist(args, pkg, rank, world, local_rank):
     from bench import SHARD_QUBITS, ClockSampler, peaks, workload_config
     L = pkg._lib
     torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    single = world == 1                      # the 33-qubit weak-scaling base: same step, one GPU, no exchange
+    if not single:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g = world.bit_length() - 1
     n = args.qubits or (SHARD_QUBITS + g)
-    st = pkg.dist.sharded_state(n, 0)
+    st = pkg.B200State(n, 0) if single else pkg.dist.sharded_state(n, 0)
     if args.tile_bits:
         st.set_option(L.OPT_TILE_BITS, args.tile_bits)
     if args.max_cost >= 0:
@@ -45,7 +47,8 @@ def run_dist(args, pkg, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
+    if not single:
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0.record(ext)
@@ -55,12 +58,14 @@ def run_dist(args, pkg, rank, world, local_rank):
         pass_ms += st.counters()["ms_device"]
     e1.record(ext)
     torch.cuda.synchronize()
-    dist.barrier()
+    if not single:
+        dist.barrier()
     wall = time.perf_counter() - t0
     dev_ms = e0.elapsed_time(e1)
     c = st.counters()
     t = torch.tensor([dev_ms, wall, c["ms_remap"], pass_ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if not single:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall, ms_remap, pass_ms = (float(x) for x in t.tolist())
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
@@ -76,7 +81,7 @@ def run_dist(args, pkg, rank, world, local_rank):
             "metric": "gates_per_sec", "value": ngates / (dev_ms * 1e-3) * scale, "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, n),
+            "config": workload_config(world, n, c4=True),
             "roofline": {"bound": "hbm", "kernel": "k_fused_tma", "achieved": achieved, "peak": hbm_peak, "peak_kind": peak_kind,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
                          "bytes_per_launch": 32.0 * (1 << nl), "launches": npasses, "per": "GPU"},
@@ -95,4 +100,5 @@ def run_dist(args, pkg, rank, world, local_rank):
             line["config"]["workload"] += " [NON-DEFAULT size: %d qubits]" % n
         print(json.dumps(line), flush=True)
     st.close()
-    dist.destroy_process_group()
+    if not single:
+        dist.destroy_process_group()
