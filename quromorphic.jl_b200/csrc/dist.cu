@@ -59,11 +59,15 @@ static int nccl_load() {
 // ---------------------------------------------------------------------------------------------
 struct PeerPtrs { double2* p[16]; };
 
+// Work is cut into 64 KiB segments that are dealt round-robin over the peers, and every rank starts
+// its round at a different peer ((rank + 1 + k) mod world), so at any moment each GPU's NVLink ingress
+// is fed by all the others evenly instead of everyone hammering the same peer.
 __global__ void __launch_bounds__(512)
 k_remap_swap(double2* __restrict__ mine, PeerPtrs peers, int rank, int world, unsigned long long chunk) {
     const unsigned long long half = chunk >> 1;
-    const unsigned long long per_peer = half;                      // amplitudes this rank moves per peer
-    const unsigned long long total = per_peer * (unsigned long long)(world - 1);
+    const unsigned long long SEG = half < 4096ull ? half : 4096ull;       // amplitudes per segment (64 KiB)
+    const unsigned long long segs_per_peer = half / SEG;
+    const unsigned long long total = half * (unsigned long long)(world - 1);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 4 * stride) {
         double2 a[4], b[4]; unsigned long long mo[4], po[4]; double2* pp[4]; bool ok[4];
@@ -72,8 +76,10 @@ k_remap_swap(double2* __restrict__ mine, PeerPtrs peers, int rank, int world, un
             const unsigned long long ii = i + (unsigned long long)u * stride;
             ok[u] = ii < total;
             const unsigned long long q = ok[u] ? ii : 0;
-            int j = (int)(q / per_peer); const unsigned long long o = q % per_peer;
-            if (j >= rank) ++j;                                    // skip myself
+            const unsigned long long sg = q / SEG, within = q % SEG;
+            const int k = (int)(sg % (unsigned long long)(world - 1));             // which peer, round-robin
+            const unsigned long long o = (sg / (unsigned long long)(world - 1)) * SEG + within;
+            int j = rank + 1 + k; if (j >= world) j -= world;                      // rank-rotated peer order
             const unsigned long long off = (rank < j ? 0ull : half) + o;
             mo[u] = (unsigned long long)j * chunk + off; po[u] = (unsigned long long)rank * chunk + off; pp[u] = peers.p[j];
             if (ok[u]) { a[u] = mine[mo[u]]; b[u] = pp[u][po[u]]; }
@@ -81,6 +87,7 @@ k_remap_swap(double2* __restrict__ mine, PeerPtrs peers, int rank, int world, un
 #pragma unroll
         for (int u = 0; u < 4; ++u) if (ok[u]) { mine[mo[u]] = b[u]; pp[u][po[u]] = a[u]; }
     }
+    (void)segs_per_peer;
 }
 
 struct DistCtx {
