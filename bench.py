@@ -15,7 +15,7 @@ N > 1 : config C4 — sharded register, 2^33 amplitudes (128 GiB) per GPU (34 q 
 `e2e`    = the same metric through the public C-ABI calls with HOST buffers, wall clock: qm_reset,
            qm_apply_circuit(host gate array) (planning + pass-program upload + kernels) and
            qm_expect_z_all (device -> host readout) all inside the timed region.
-`roofline` is for the dominant kernel k_fused_pass: 32 * 2^n bytes per launch (16 read + 16 written
+`roofline` is for the dominant kernel k_fused_tma: 32 * 2^n bytes per launch (16 read + 16 written
            per amplitude) over its mean launch duration from CUDA events on the
            launching stream, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
 `cpu_baseline` is oracle/qsim_oracle.c (matrix-free OpenMP restatement of the reference's
@@ -267,11 +267,19 @@ def main():
     e2e = args.steps * ngates / wall * scale
 
     hbm_peak, peak_kind = peaks()
+    traffic = None
+    try:    # dram__bytes_read.sum + dram__bytes_write.sum of one k_fused_tma launch (ncu --set full capture)
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)["k_fused_tma"]
+            if t["n_qubits"] == n:
+                traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        pass
     bytes_per_launch = 32.0 * (1 << n)
     avg_pass_ms = pass_ms / max(npasses, 1)
     achieved = bytes_per_launch / (avg_pass_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_fused_pass", "achieved": achieved, "peak": hbm_peak, "peak_kind": peak_kind,
-            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+    roof = {"bound": "hbm", "kernel": "k_fused_tma", "achieved": achieved, "peak": hbm_peak, "peak_kind": peak_kind,
+            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
             "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_pass_ms, "launches": npasses,
             "gates_per_pass": args.steps * ngates / max(npasses, 1),
             "frac_of_nominal_8TBs": achieved / 8000.0}

@@ -6,6 +6,6 @@ circuits.py (the synthetic reservoir workloads), julia/B200QSim.jl (the same hos
 The directory name contains a dot, so it is imported through __graft_entry__.load_package() under
 the module name `quromorphic_jl_b200`.
 """
-from . import _lib, circuits, dist, qinfo, qsim  # noqa: F401
+from . import _lib, circuits, dist, qinfo, qsim, reservoir  # noqa: F401
 from ._lib import QMError  # noqa: F401
 from .qsim import B200State, QSimError  # noqa: F401

@@ -209,6 +209,10 @@ static const int kZMaxChunkBits = 13;
 static const int kZMaxHi = 10;
 static const int kZVals = kZMaxChunkBits + kZMaxHi + 1;
 
+// FAST: chunk of exactly 2^13 amplitudes (registers of >= 13 qubits).  Element `it*256 + tid` of a chunk
+// has index bits 0..7 = tid and bits 8..12 = it, so with the 32-iteration loop unrolled the bit tests
+// fold away at compile time: 32 independent 128-bit loads in flight per thread, ~4 adds per amplitude.
+template <bool FAST>
 __global__ void __launch_bounds__(kZThreads)
 k_zpartial(const double2* __restrict__ amp, int reg_bits, int cb, int hbits, int ctas_per_reg_log2, double thr,
            double* __restrict__ partial) {
@@ -224,16 +228,41 @@ k_zpartial(const double2* __restrict__ amp, int reg_bits, int cb, int hbits, int
     for (uint32_t c = 0; c < (1u << hbits); ++c) {
         double ctot = 0.0;
         const double2* __restrict__ p = base + ((uint64_t)c << cb);
-        for (uint32_t idx = threadIdx.x; idx < csize; idx += kZThreads) {
-            const double pr = abs2_exact(p[idx]);
-            const double v = pr > thr ? pr : 0.0;
-            ctot += v;
+        if (FAST) {
+            double v[32];
 #pragma unroll
-            for (int b = 0; b < kZMaxChunkBits; ++b) s1[b] += ((idx >> b) & 1u) ? v : 0.0;
+            for (int it = 0; it < 32; ++it) {
+                const double pr = abs2_exact(p[it * kZThreads + threadIdx.x]);
+                v[it] = pr > thr ? pr : 0.0;
+            }
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {           // bits 8..12 of the index = bits of `it`
+                double acc = 0.0;
+#pragma unroll
+                for (int it = 0; it < 32; ++it) if ((it >> b) & 1) acc += v[it];
+                s1[8 + b] += acc;
+            }
+#pragma unroll
+            for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+                for (int it = 0; it < w; ++it) v[it] += v[it + w];
+            ctot = v[0];
+        } else {
+            for (uint32_t idx = threadIdx.x; idx < csize; idx += kZThreads) {
+                const double pr = abs2_exact(p[idx]);
+                const double v = pr > thr ? pr : 0.0;
+                ctot += v;
+#pragma unroll
+                for (int b = 0; b < kZMaxChunkBits; ++b) s1[b] += ((idx >> b) & 1u) ? v : 0.0;
+            }
         }
         tot += ctot;
 #pragma unroll
         for (int b = 0; b < kZMaxHi; ++b) hi[b] += ((c >> b) & 1u) ? ctot : 0.0;
+    }
+    if (FAST) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) s1[b] = ((threadIdx.x >> b) & 1u) ? tot : 0.0;   // bits 0..7 = bits of tid
     }
     // block reduction: butterfly inside the warp, then warp 0 adds the warp results in order
     __shared__ double red[kZThreads / 32][kZVals];

@@ -665,7 +665,8 @@ int qm_zstats(qm_state* st, double thr, double** h_pairs, double** h_tot) {
     double* d_part = st->d_scratch;
     double* d_out = st->d_scratch + (size_t)nctas * kZVals;
     double* d_tot = d_out + (size_t)st->batch * nl * 2;
-    k_zpartial<<<(unsigned)nctas, kZThreads, 0, st->stream>>>(st->amp, nl, cb, hbits, ctas_log2, thr, d_part);
+    if (cb == kZMaxChunkBits) k_zpartial<true><<<(unsigned)nctas, kZThreads, 0, st->stream>>>(st->amp, nl, cb, hbits, ctas_log2, thr, d_part);
+    else k_zpartial<false><<<(unsigned)nctas, kZThreads, 0, st->stream>>>(st->amp, nl, cb, hbits, ctas_log2, thr, d_part);
     CU(cudaGetLastError());
     k_zfinal<<<st->batch, 256, 0, st->stream>>>(d_part, nl, cb, hbits, ctas_log2, d_out, d_tot);
     CU(cudaGetLastError());

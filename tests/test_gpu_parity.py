@@ -292,3 +292,96 @@ def test_sharded_two_gpus(pkg, n):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert all("GPU_DIST_OK" in o for o in outs), "\n".join(outs)
+
+
+def test_c2_batched_full_size_4096_registers_of_16_qubits(pkg):
+    """config C2 at BASELINE.json's size: 4096 independent 16-qubit registers (4 GiB) evolved in lockstep with
+    per-state encodings.  A sample of registers is checked against the per-state oracle, all of them through
+    the norm (unitarity)."""
+    n, B, T = 16, 4096, 2
+    C = pkg.circuits
+    gates = C.c2_step_gates(n, seed=1603)
+    assert len(gates) == 63
+    w = [C.SplitMix64(7).uniform() for _ in range(n)]
+    st = pkg.B200State(n, 0, batch=B)
+    sample = [0, 1, 777, 2048, 4095]
+    refs = {b: O.statevector(n, 0) for b in sample}
+    for t in range(T):
+        enc = C.c2_encoding(B, n, t, w)
+        st.apply_batched(gates, enc)
+        z = st.expect_z_all()
+        assert z.shape == (B, n, 2)
+        assert np.max(np.abs(z.sum(axis=2) - 1.0)) < 1e-5          # kept mass: the 1e-10 threshold (QSim.jl:308) drops ~4e-7 at 16 qubits
+        for b in sample:
+            g = gates.copy()
+            for i in range(len(g)):
+                if g[i]["kind"] == pkg._lib.GATE_U2_SLOT:
+                    g[i]["m"] = enc[b, g[i]["q1"]]; g[i]["kind"] = pkg._lib.GATE_U2; g[i]["q1"] = 0
+            O.apply_circuit(refs[b], g)
+            assert np.max(np.abs(z[b] - O.expect_z_all(refs[b], 1e-10))) < RTOL
+    for b in sample:
+        assert rel_err(st.to_numpy(b), refs[b]) < RTOL
+    c = st.counters()
+    assert c["passes"] >= 2 * T
+
+
+def test_batched_general_per_state_unitaries(pkg):
+    """per-state slots holding arbitrary unitaries (phase * rotation * phase path) and a non-unitary one (v1 path)"""
+    n, B = 12, 9
+    rng = np.random.default_rng(5)
+    gl = pkg.circuits.GateList(n)
+    gl.slot(3, 0); gl.cnot(3, 4); gl.slot(12, 1); gl.h(1); gl.slot(1, 0)
+    gates = gl.array()
+    for unitary in (True, False):
+        mats = np.empty((B, 2, 8))
+        Us = []
+        for b in range(B):
+            row = []
+            for s in range(2):
+                M = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+                if unitary:
+                    M, _ = np.linalg.qr(M)
+                row.append(M); mats[b, s] = pkg._lib.mat8(M)
+            Us.append(row)
+        st = pkg.B200State(n, 5, batch=B)
+        st.apply_batched(gates, mats)
+        for b in (0, 4, B - 1):
+            ref = O.statevector(n, 5)
+            O.u2(ref, 3, Us[b][0]); O.cnot(ref, 3, 4); O.u2(ref, 12, Us[b][1]); O.h(ref, 1); O.u2(ref, 1, Us[b][0])
+            assert rel_err(st.to_numpy(b), ref) < 1e-11
+
+
+def test_c5_lsm_driven_reservoir_with_qinfo_readouts(pkg):
+    """config C5 at a size the oracle follows step by step (12 qubits, T = 6): LSM states drive the encoding,
+    readouts are all-qubit <Z> plus the von Neumann entropies of the low-4 / high-4 reduced density matrices."""
+    R = pkg.reservoir
+    n, T, k = 12, 6, 4
+    rng = np.random.default_rng(2001)
+    lsm = R.LSMNet(rng.uniform(-1, 1, size=(50, 3)), 0.05 * rng.normal(size=(50, 50)), leak_rate=0.3)
+    drive = lsm.collect_states(rng.uniform(0, 1, size=(3, T)))[:n]          # LSM.jl:49-57
+    qr = R.QuantumReservoir(n, entropy_k=k)
+    feats = qr.collect_states(drive)
+    assert feats.shape == (n + 2, T)
+    ref = O.statevector(n, 0)
+    for t in range(T):
+        O.apply_circuit(ref, qr.step_gates(drive[:, t]))
+        z = O.expect_z_all(ref, 1e-10)
+        assert np.max(np.abs(feats[:n, t] - (z[:, 0] - z[:, 1]))) < RTOL
+        SB = LIT.von_neumann_entropy(O.reduced_density(ref, True, k))
+        SA = LIT.von_neumann_entropy(O.reduced_density(ref, False, k))
+        assert feats[n, t] == pytest.approx(SB, abs=1e-9) and feats[n + 1, t] == pytest.approx(SA, abs=1e-9)
+    # ridge readout on the quantum features (LSM.jl:59-72 analogue) reproduces a linear target of them
+    target = (0.3 * feats[0] - 0.2 * feats[5])[None, :]
+    Wout, bout = R.ridge_readout(feats, target, reg=1e-10)
+    assert np.max(np.abs(Wout @ feats + bout[:, None] - target)) < 1e-6
+
+
+def test_c5_at_20_qubits_properties(pkg):
+    n, k = 20, 4
+    qr = pkg.reservoir.QuantumReservoir(n, entropy_k=k)
+    rng = np.random.default_rng(3)
+    for t in range(3):
+        f = qr.step(rng.uniform(0, 1, size=n))
+        assert np.all(np.abs(f[:n]) <= 1 + 1e-12) and 0 <= f[n] <= k + 1e-9 and 0 <= f[n + 1] <= k + 1e-9
+    rho = pkg.qinfo.partial_trace(qr.state, 1 << (n - k), 1 << k, 1)
+    assert abs(np.trace(rho).real - 1) < 1e-12 and np.max(np.abs(rho - rho.conj().T)) < 1e-15
