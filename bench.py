@@ -74,7 +74,7 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
@@ -84,12 +84,16 @@ class ClockSampler:
                 sm.append(float(parts[1])); mx.append(float(parts[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(parts[3]))
+            except ValueError:
+                pass
             for nm, val in zip(names, parts[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         os.unlink(self.f.name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def cpu_sample(n, gates, budget_s, threads=None):

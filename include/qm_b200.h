@@ -179,12 +179,26 @@ int32_t qm_plan_describe(int32_t n_qubits, int32_t global_bits, int32_t tile_bit
                          int32_t allow_remap, const qm_gate* gates, int32_t ngates,
                          int32_t* out, int64_t cap, int64_t* out_len);
 
+/* qm_plan_describe with the engine's own planner settings: a cap on a pass's arithmetic (0 = none) and
+ * the limits of the persistent TMA kernel (pipeline != 0). */
+int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
+                            double max_cost, int32_t pipeline, const qm_gate* gates, int32_t ngates,
+                            int32_t* out, int64_t cap, int64_t* out_len);
+
 /* The same plan as a flat gate list in execution order (wire format on physical bits, after
  * merging): applying `out` one gate at a time must equal applying `gates` in their given order.
  * pass_of[i] receives the pass index of out[i] (may be NULL). */
 int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
                       double max_cost, const qm_gate* gates, int32_t ngates, qm_gate* out,
                       int32_t* pass_of, int32_t cap, int32_t* out_len);
+
+/* TEST INFRASTRUCTURE, host only: plans `gates` as the engine does for its TMA kernel, encodes every pass
+ * into the kernel's program format and walks the encoded programs over the host vector `state`
+ * (2^n_qubits interleaved amplitudes, 11 <= n_qubits <= 24) with a scalar restatement of the kernel's
+ * interpreter.  Lets the CPU tests check planner + encoder against the oracle without a GPU.  Not a
+ * fallback: no other entry point calls it. */
+int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
+                        const qm_gate* gates, int32_t ngates, double* state_interleaved, int32_t* n_passes);
 
 /* ---- misc ---------------------------------------------------------------------------- */
 int32_t qm_sync(qm_state* st);

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libqm_b200.so")
+# QM_B200_LIB: an alternative build of the same ABI (A/B timing of kernel versions in tools/sweep.py)
+SO_PATH = os.environ.get("QM_B200_LIB") or os.path.join(HERE, "libqm_b200.so")
 
 QM_OK, QM_ERR_ARG, QM_ERR_CUDA, QM_ERR_NOMEM, QM_ERR_NO_DEVICE, QM_ERR_STATE, QM_ERR_COMM = range(7)
 GATE_U2, GATE_CU2, GATE_SWAP, GATE_U2_SLOT = 0, 1, 2, 3
@@ -69,8 +70,11 @@ SIGNATURES = {
     "qm_dist_ipc_import": (C.c_int32, [_vp, C.POINTER(C.c_uint8)]),
     "qm_plan_describe": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int32,
                                      C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
+    "qm_plan_describe_ex": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, _vp,
+                                        C.c_int32, C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
     "qm_plan_gates": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _vp,
                                   C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+    "qm_plan_emulate": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _dp, C.POINTER(C.c_int32)]),
     "qm_sync": (C.c_int32, [_vp]),
     "qm_last_error": (C.c_int32, [C.c_char_p, C.c_int32]),
     "qm_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),
@@ -91,6 +95,8 @@ def lib():
                               "(nvcc, sm_100a).  There is no CPU fallback." % SO_PATH)
         l = C.CDLL(SO_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if not hasattr(l, name) and "QM_B200_LIB" in os.environ:
+                continue
             f = getattr(l, name)
             f.restype = res
             f.argtypes = args
@@ -130,3 +136,39 @@ def plan_gates(n, gates, global_bits=0, tile_bits=12, low_bits=5, max_cost=0.0):
     check(lib().qm_plan_gates(n, global_bits, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates),
                               out.ctypes.data, po.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(ln)))
     return out[:ln.value].copy(), po[:ln.value].copy()
+
+
+def plan_describe(n, gates, global_bits=0, tile_bits=12, low_bits=5, max_cost=0.0, pipeline=1):
+    """host-only: the planner's passes as a list of dicts {ngates, m, L, hb, groups: [(rb, nsub)]}"""
+    cap = 64 * len(gates) + 1024
+    out = np.zeros(cap, dtype=np.int32)
+    ln = C.c_int64()
+    check(lib().qm_plan_describe_ex(n, global_bits, tile_bits, low_bits, max_cost, pipeline, gates.ctypes.data,
+                                    len(gates), out.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(ln)))
+    v, i, steps = out[:ln.value].tolist(), 0, []
+    while i < len(v):
+        if v[i] == 1:
+            steps.append({"remap_left": v[i + 1]})
+            i += 2
+            continue
+        ng, m, L, nh = v[i + 1:i + 5]
+        hb = v[i + 5:i + 5 + nh]
+        i += 5 + nh
+        G = v[i]
+        i += 1
+        groups = []
+        for _ in range(G):
+            nrb = v[i]
+            rb = v[i + 1:i + 1 + nrb]
+            groups.append((rb, v[i + 1 + nrb]))
+            i += 2 + nrb
+        steps.append({"ngates": ng, "m": m, "L": L, "hb": hb, "groups": groups})
+    return steps
+
+
+def plan_emulate(n, gates, psi, tile_bits=12, low_bits=5, max_cost=0.0):
+    """host-only test helper: the planned + encoded pass programs walked over psi (complex128, length 2^n)"""
+    out = np.ascontiguousarray(psi, dtype=np.complex128).copy()
+    npass = C.c_int32()
+    check(lib().qm_plan_emulate(n, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates), dptr(out), C.byref(npass)))
+    return out, npass.value

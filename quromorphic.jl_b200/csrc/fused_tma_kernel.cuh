@@ -1,0 +1,235 @@
+// fused_tma_kernel.cuh — the kernel template of the fused TMA pass (see fused_tma.cuh for the design and the
+// program layout).  Included only by the per-shape translation units fused_m12.cu / fused_m11.cu.
+#pragma once
+#include "fused_tma.cuh"
+#include "state.hpp"
+#include "v4_dispatch.inc"
+
+namespace qm {
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+// producer-side wait: back off between probes so the spinning lane does not eat issue slots of the
+// compute warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(1024);
+    }
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(tm), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ uint64_t ldp64(uint64_t pa) {
+    uint64_t v;
+    asm volatile("ld.param.u64 %0, [%1];" : "=l"(v) : "l"(pa));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldp32(uint64_t pa) {
+    uint32_t v;
+    asm volatile("ld.param.u32 %0, [%1];" : "=r"(v) : "l"(pa));
+    return v;
+}
+
+
+template <int M, int TEAMS, int STAGES>
+__global__ void __launch_bounds__(TEAMS * (1 << (M - 4)) + kV4ProducerThreads, 1)
+k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4Program P, const double* __restrict__ slots,
+            const V4Launch lp) {
+    constexpr int TEAM = 1 << (M - kV4BlockBits);          // threads of one team
+    constexpr int NCOMP = TEAMS * TEAM;
+    constexpr uint32_t TILE_BYTES = 16u << M;
+    static_assert(TEAMS <= STAGES && NCOMP % 128 == 0 && TEAM % 32 == 0, "team shape");
+    extern __shared__ unsigned char smem_dyn[];
+    // [stages][TILE_BYTES] | lane_tab, warp_tab | gate records | barriers ; SWIZZLE_128B needs the stages 1024-byte aligned
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* stage_base = smem;
+    unsigned char* tabs = smem + (size_t)STAGES * TILE_BYTES;
+    unsigned char* recs = tabs + kV4TabBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(recs + sizeof(V4Rec) * kV4MaxRecs);
+    uint64_t* computed = full + 2 * STAGES;
+    // full[] holds TWO barriers per stage, used alternately (use k = i / STAGES of a stage takes barrier
+    // s + STAGES * (k & 1), parity (k >> 1) & 1).  With one barrier a parity wait cannot tell "use k has
+    // landed" from "use k-1 has not landed yet", and a team CAN get there: tile i and tile i + STAGES of a
+    // stage belong to different teams, TMA loads complete out of order, and a team that finishes a light
+    // tile before an earlier tile's load has landed would sail through the wait for the following use of
+    // that stage (seen on B200 as rare wrong amplitudes or a hang with cheap passes).
+
+    const int tid = threadIdx.x;
+    uint64_t pa;                                  // param-space address of the program
+    asm("cvta.to.param.u64 %0, %1;" : "=l"(pa) : "l"(&P));
+    // index tables -> shared memory (the rows of the groups in use)
+    {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tabs);
+        const int nl = P.ngroups * 16, nw = P.ngroups * 4;       // 32-bit words of lane_tab / warp_tab in use
+        for (int i = tid; i < nl; i += NCOMP + kV4ProducerThreads) dst[i] = ldp32(pa + offsetof(V4Program, lane_tab) + 4u * i);
+        for (int i = tid; i < nw; i += NCOMP + kV4ProducerThreads) dst[kV4MaxGroups * 16 + i] = ldp32(pa + offsetof(V4Program, warp_tab) + 4u * i);
+    }
+    {   // gate records -> shared memory (the interpreter reads them with 16-byte broadcasts)
+        uint64_t* dst = reinterpret_cast<uint64_t*>(recs);
+        const int n8 = P.nrecs * 8;
+        for (int i = tid; i < n8; i += NCOMP + kV4ProducerThreads) dst[i] = ldp64(pa + offsetof(V4Program, recs) + 8u * i);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&full[STAGES + s], 1); mbar_init(&computed[s], TEAM / 32); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int tbits = lp.reg_bits - M;
+    const uint64_t first = blockIdx.x, step = gridDim.x;
+    const uint64_t ntiles = lp.ntiles;
+    const uint64_t my_tiles = first < ntiles ? (ntiles - first + step - 1) / step : 0;
+
+    auto tile_base = [&](uint64_t tile_id, uint64_t& gbase_out, uint64_t& breg_out) -> uint64_t {
+        const uint64_t breg = tile_id >> tbits;
+        uint64_t base = (tile_id & ((1ull << tbits) - 1ull)) << lp.L;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {           // open a gap of run_len zero bits at run_start
+            const uint64_t lo = base & ((1ull << lp.run_start[j]) - 1ull);
+            base = ((base >> lp.run_start[j]) << (lp.run_start[j] + lp.run_len[j])) | lo;
+        }
+        gbase_out = base | lp.rank_or; breg_out = breg;
+        return (breg << lp.reg_bits) + base;      // amplitude index of the tile's first element in the whole array
+    };
+
+    if (tid >= NCOMP) {
+        // ===================== producer warpgroup: one elected lane drives TMA =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid == NCOMP) {
+            uint64_t gb, br;
+            const uint64_t pro = my_tiles < (uint64_t)STAGES ? my_tiles : (uint64_t)STAGES;
+            for (uint64_t i = 0; i < pro; ++i) {
+                const uint64_t base = tile_base(first + i * step, gb, br);
+                mbar_arrive_expect_tx(&full[i], TILE_BYTES);
+                tma_load_5d(stage_base + i * TILE_BYTES, &tmap, &full[i], 0, (int)(base >> 3), 0, 0, 0);
+            }
+            for (uint64_t i = 0; i < my_tiles; ++i) {
+                const int s = (int)(i % STAGES);
+                const uint32_t ph = (uint32_t)((i / STAGES) & 1);
+                mbar_wait_sleep(&computed[s], ph);
+                const uint64_t base = tile_base(first + i * step, gb, br);
+                tma_store_5d(&tmap, stage_base + (size_t)s * TILE_BYTES, 0, (int)(base >> 3), 0, 0, 0);
+                tma_commit();
+                const uint64_t nxt = i + STAGES;
+                if (nxt < my_tiles) {
+                    tma_wait_read0();            // the store has read the buffer: safe to overwrite
+                    const uint64_t nbase = tile_base(first + nxt * step, gb, br);
+                    uint64_t* fb = &full[s + STAGES * (int)((nxt / STAGES) & 1)];
+                    mbar_arrive_expect_tx(fb, TILE_BYTES);
+                    tma_load_5d(stage_base + (size_t)s * TILE_BYTES, &tmap, fb, 0, (int)(nbase >> 3), 0, 0, 0);
+                }
+            }
+            tma_wait_all0();
+        }
+        return;
+    }
+
+    // ================================ compute teams ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int team = tid / TEAM, ttid = tid % TEAM;
+    const int lane = ttid & 31, warp = ttid >> 5;
+    const int ngroups = P.ngroups, n_outer = P.n_outer;
+    const uint32_t ctx_const = P.ctx_const | kV4CtxAlways;
+    const uint64_t opk0 = P.outer_pack[0], opk1 = P.outer_pack[1];
+    const uint32_t stage_s = smem_u32(stage_base);
+    const uint32_t lane_s = smem_u32(tabs) + 2u * lane, warp_s = smem_u32(tabs) + 2u * (kV4MaxGroups * 32 + warp);
+    int s = team % STAGES; uint32_t k = 0;        // stage and use count of the stage (tile i: s = i % STAGES, k = i / STAGES)
+    uint64_t tile_id = first + (uint64_t)team * step;
+#pragma unroll 1
+    for (uint32_t i = team; i < (uint32_t)my_tiles; i += TEAMS, tile_id += (uint64_t)TEAMS * step) {
+        uint64_t gbase, breg;
+        tile_base(tile_id, gbase, breg);
+        // outer part of the context word: the index bits outside the tile that some gate of this pass
+        // uses as a control or as the target of a diagonal gate
+        uint32_t octx = ctx_const;
+        {
+            uint64_t pk = opk0;
+            for (int j = 0; j < n_outer; ++j) {
+                octx |= (uint32_t)((gbase >> (pk & 63ull)) & 1ull) << (kV4CtxOuter + j);
+                pk >>= 6;
+                if (j == 9) pk = opk1;
+            }
+        }
+        const double* slot_base = slots ? slots + (size_t)breg * lp.nslots * 8 : nullptr;
+        const uint32_t tile_s = stage_s + (uint32_t)s * TILE_BYTES;
+        mbar_wait(&full[s + STAGES * (int)(k & 1u)], (k >> 1) & 1u);
+#pragma unroll 1
+        for (int gi = 0; gi < ngroups; ++gi) {
+            const uint64_t ga = pa + offsetof(V4Program, groups) + 32u * gi;
+            const uint64_t g01 = ldp64(ga), g23 = ldp64(ga + 8);
+            const uint32_t gw = ldp32(ga + 16);
+            uint32_t v, vw;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(lane_s + 64u * gi));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(vw) : "r"(warp_s + 16u * gi));
+            v |= vw;
+            // the swizzle slot(i) = i ^ ((i >> 3) & 7) is linear over xor, so the sixteen addresses of the
+            // register block are the thread's base xor the (swizzled) block-bit offsets
+            const uint32_t b0 = (v ^ ((v >> 3) & 7u)) << 4;
+            const uint32_t ctx = v | octx;
+            uint32_t rp = smem_u32(recs) + (gw - (uint32_t)offsetof(V4Program, recs));
+            asm volatile(V4_GROUP_PTX
+                         : "+r"(rp)
+                         : "r"(ctx), "l"(slot_base), "r"(tile_s), "r"(b0), "r"((uint32_t)g01), "r"((uint32_t)(g01 >> 32)),
+                           "r"((uint32_t)g23), "r"((uint32_t)(g23 >> 32))
+                         : "memory");
+            if (gi + 1 < ngroups) bar_sync_named(1 + team, TEAM);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&computed[s]);
+        s += TEAMS; if (s >= STAGES) { s -= STAGES; ++k; }
+    }
+}
+
+template <int M, int TEAMS, int STAGES>
+static int launch_v4_t(cudaStream_t stream, int sms, const CUtensorMap& tm, const V4Program& prog, const double* d_slots,
+                       const V4Launch& lp) {
+    constexpr int threads = TEAMS * (1 << (M - kV4BlockBits)) + kV4ProducerThreads;
+    constexpr size_t smem = (size_t)STAGES * (16u << M) + kV4TabBytes + sizeof(V4Rec) * kV4MaxRecs + 3 * STAGES * 8 + 1024;
+    static bool attr = false;
+    if (!attr) { CU(cudaFuncSetAttribute(k_fused_tma<M, TEAMS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const uint64_t cap = (uint64_t)sms;
+    const int grid = (int)(lp.ntiles < cap ? lp.ntiles : cap);
+    k_fused_tma<M, TEAMS, STAGES><<<grid, threads, smem, stream>>>(tm, prog, d_slots, lp);
+    CU(cudaGetLastError());
+    return QM_OK;
+}
+
+}  // namespace qm

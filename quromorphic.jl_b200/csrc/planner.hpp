@@ -24,7 +24,7 @@
 namespace qm {
 
 static const int kMaxTileBits = 13;
-static const int kBlockBits = 3;        // amplitudes per thread = 2^3
+static const int kBlockBits = 3;        // general (v1) kernel: amplitudes per thread = 2^3
 static const int kMaxSubsPerPass = 160;
 
 // ---- device-visible encodings (plain structs, copied byte for byte) -----------------------
@@ -78,7 +78,11 @@ struct SlotMap {
 };
 
 struct PlanSub { LGate g; };
-struct PlanGroup { std::vector<int> rb; std::vector<LGate> subs; };
+struct PlanGroup {
+    std::vector<int> rb;     // register-block bits (physical)
+    std::vector<int> wb;     // tile bits that must be warp-uniform for this group (controls that are not block bits)
+    std::vector<LGate> subs;
+};
 struct PlanPass {
     int m = 0, L = 0;
     std::vector<int> hb;
@@ -100,8 +104,12 @@ struct PlanOptions {
     int window = 768;    // look-ahead, in gates
     double max_cost = 1e30;
     int max_runs = 99;   // runs of consecutive high tile bits a pass may use (TMA tensor maps: 3)
+    int max_run_len = 99;  // ... a run longer than this counts as several (TMA box dimension <= 256: 8)
     int max_subs = kMaxSubsPerPass;
     int max_groups = 1 << 30;
+    int max_outer = 64;  // distinct bits outside the tile a pass may use as controls / diagonal targets
+    int block_bits = kBlockBits;     // register-block bits of a group (3: general kernel, 4: TMA kernel)
+    bool warp_uniform_ctrl = false;  // controls inside the tile must be block bits or one of the (m - block_bits - 5) warp-index bits
 };
 
 inline bool mat_is_diag(const double* m) { return m[2] == 0.0 && m[3] == 0.0 && m[4] == 0.0 && m[5] == 0.0; }
@@ -207,12 +215,15 @@ inline double gate_cost(const LGate& g) {
 }
 
 // Commutation-aware pull: walk the not-yet-done gates in order; take a gate when no earlier
-// skipped gate blocks it and its (non-diagonal) target is allowed.  allowed(target, dry) may
-// extend the allowed set on the fly (used for the <=3-bit register blocks).
+// skipped gate blocks it and allowed(gate) accepts it (the pass level asks for the non-diagonal target
+// to be in the tile; the group level grows the <= 3-bit register block and the warp-uniform set).
+// `tile_mask` / `max_outer`: a pass may use at most max_outer distinct bits outside tile_mask as controls
+// or diagonal targets (the kernel keeps them in a 32-bit per-thread context word).
 template <class Allowed>
 inline void pull(const std::vector<LGate>& g, const std::vector<char>& done, size_t first, int window,
-                 uint64_t all_bits, double max_cost, int max_take, Allowed&& allowed, std::vector<int>& taken) {
-    uint64_t blockedN = 0, blockedD = 0;
+                 uint64_t all_bits, double max_cost, int max_take, Allowed&& allowed, std::vector<int>& taken,
+                 uint64_t tile_mask = ~0ull, int max_outer = 64) {
+    uint64_t blockedN = 0, blockedD = 0, outer_used = 0;
     int scanned = 0; double cost = 0;
     for (size_t i = first; i < g.size() && scanned < window; ++i) {
         if (done[i]) continue;
@@ -222,9 +233,11 @@ inline void pull(const std::vector<LGate>& g, const std::vector<char>& done, siz
         uint64_t actsN = x.diag ? 0ull : tm, actsD = cm | (x.diag ? tm : 0ull);
         bool free_ = !((actsN | actsD) & blockedN) && !(actsN & blockedD);
         bool take = false;
-        if (free_ && (int)taken.size() < max_take && cost + gate_cost(x) <= max_cost)
-            take = x.diag || allowed(x.target);
-        if (take) { taken.push_back((int)i); cost += gate_cost(x); }
+        const uint64_t ob = (cm | (x.diag ? tm : 0ull)) & ~tile_mask;
+        if (free_ && (int)taken.size() < max_take && cost + gate_cost(x) <= max_cost &&
+            __builtin_popcountll(outer_used | ob) <= max_outer)
+            take = allowed(x);
+        if (take) { taken.push_back((int)i); cost += gate_cost(x); outer_used |= ob; }
         else {
             blockedN |= actsN; blockedD |= actsD;
             if ((blockedN & all_bits) == all_bits) break;
@@ -255,7 +268,7 @@ struct Planner {
     int count_with(uint64_t tilemask) const {
         std::vector<int> taken;
         pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, opt.max_subs,
-             [&](int t) { return (tilemask >> t) & 1; }, taken);
+             [&](const LGate& x) { return x.diag || ((tilemask >> x.target) & 1); }, taken, tilemask, opt.max_outer);
         return (int)taken.size();
     }
 
@@ -266,7 +279,12 @@ struct Planner {
         if (nh <= 0) { best = count_with((1ull << L) - 1); return; }
         uint64_t low = (1ull << L) - 1;
         auto try_set = [&](const std::vector<int>& hb) {
-            int runs = 0; for (size_t i = 0; i < hb.size(); ++i) if (i == 0 || hb[i] != hb[i - 1] + 1) ++runs;
+            // runs of consecutive bits, a run being cut after max_run_len bits (one TMA box dimension holds <= 256)
+            int runs = 0, len = 0;
+            for (size_t i = 0; i < hb.size(); ++i) {
+                if (i == 0 || hb[i] != hb[i - 1] + 1 || len == opt.max_run_len) { ++runs; len = 0; }
+                ++len;
+            }
             if (runs > opt.max_runs) return;
             uint64_t mask = low; for (int b : hb) mask |= 1ull << b;
             int c = count_with(mask);
@@ -277,7 +295,9 @@ struct Planner {
             std::vector<int> hb; uint64_t have = low;
             std::vector<int> taken;
             pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, 1e30, 1 << 30,
-                 [&](int t) {
+                 [&](const LGate& x) {
+                     if (x.diag) return true;
+                     const int t = x.target;
                      if (t >= nl) return false;
                      if ((have >> t) & 1) return true;
                      if ((int)hb.size() < nh) { hb.push_back(t); have |= 1ull << t; return true; }
@@ -313,6 +333,8 @@ struct Planner {
             }
             P = PlanPass(); P.m = m; P.L = L; P.hb = hb;
             PlanGroup G; if (!x.diag) G.rb.push_back(x.target);
+            if (opt.warp_uniform_ctrl && x.ctrl >= 0 && (x.ctrl < L || std::find(hb.begin(), hb.end(), x.ctrl) != hb.end()))
+                G.rb.push_back(x.ctrl);
             G.subs.push_back(x); P.groups.push_back(G); P.ngates = 1; P.cost = gate_cost(x);
             done[first] = 1;
             return true;
@@ -324,7 +346,7 @@ struct Planner {
         while (true) {
             std::vector<int> taken;
             pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, max_take,
-                 [&](int t) { return (tilemask >> t) & 1; }, taken);
+                 [&](const LGate& x) { return x.diag || ((tilemask >> x.target) & 1); }, taken, tilemask, opt.max_outer);
             P = PlanPass(); P.m = m; P.L = L; P.hb = hb; P.ngates = (int)taken.size();
             std::vector<LGate> pg; pg.reserve(taken.size());
             for (int i : taken) { pg.push_back(gates[i]); P.cost += gate_cost(gates[i]); }
@@ -333,16 +355,31 @@ struct Planner {
             while (true) {
                 while (f2 < pg.size() && d2[f2]) ++f2;
                 if (f2 >= pg.size()) break;
-                PlanGroup G; uint64_t have = 0;
+                // A group holds <= block_bits register-block bits (every non-diagonal target) and, when the
+                // kernel wants warp-uniform control predicates (opt.warp_uniform_ctrl), every control inside
+                // the tile is either a block bit or one of the tile bits pinned to the warp index.
+                PlanGroup G; uint64_t have = 0, wset = 0;
+                const int bb = opt.block_bits;
+                const int wcap = m > bb + 5 ? m - bb - 5 : 0;
                 std::vector<int> tk;
                 pull(pg, d2, f2, 1 << 30, (1ull << total_bits()) - 1, 1e30, 1 << 30,
-                     [&](int t) {
-                         if ((have >> t) & 1) return true;
-                         if ((int)G.rb.size() < kBlockBits) { G.rb.push_back(t); have |= 1ull << t; return true; }
-                         return false;
+                     [&](const LGate& x) {
+                         uint64_t h2 = have, w2 = wset;
+                         if (!x.diag && !((h2 >> x.target) & 1)) {
+                             if (__builtin_popcountll(h2) >= bb) return false;
+                             h2 |= 1ull << x.target; w2 &= ~(1ull << x.target);
+                         }
+                         if (opt.warp_uniform_ctrl && x.ctrl >= 0 && ((tilemask >> x.ctrl) & 1) &&
+                             !(((h2 | w2) >> x.ctrl) & 1)) {
+                             if (__builtin_popcountll(w2) < wcap) w2 |= 1ull << x.ctrl;
+                             else if (__builtin_popcountll(h2) < bb) h2 |= 1ull << x.ctrl;
+                             else return false;
+                         }
+                         have = h2; wset = w2;
+                         return true;
                      }, tk);
                 for (int i : tk) { G.subs.push_back(pg[i]); d2[i] = 1; }
-                std::sort(G.rb.begin(), G.rb.end());
+                for (int b = 0; b < 64; ++b) { if ((have >> b) & 1) G.rb.push_back(b); if ((wset >> b) & 1) G.wb.push_back(b); }
                 P.groups.push_back(G);
             }
             if ((int)P.groups.size() > opt.max_groups && taken.size() > 1) {

@@ -11,6 +11,7 @@
 
 #include "../../include/qm_b200.h"
 #include "dist.hpp"
+#include "emulate.hpp"
 #include "fused_tma.cuh"
 #include "kernels.cuh"
 #include "lifting.hpp"
@@ -200,11 +201,11 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// runs of consecutive bits in hb (ascending)
+// runs of consecutive bits in hb (ascending), cut after 8 bits: one TMA box dimension holds at most 256 elements
 static int hb_runs(const std::vector<int>& hb, int start[8], int len[8]) {
     int nr = 0;
     for (size_t i = 0; i < hb.size(); ++i) {
-        if (nr > 0 && hb[i] == start[nr - 1] + len[nr - 1]) { len[nr - 1]++; continue; }
+        if (nr > 0 && hb[i] == start[nr - 1] + len[nr - 1] && len[nr - 1] < 8) { len[nr - 1]++; continue; }
         if (nr == 8) return 99;
         start[nr] = hb[i]; len[nr] = 1; ++nr;
     }
@@ -212,7 +213,7 @@ static int hb_runs(const std::vector<int>& hb, int start[8], int len[8]) {
 }
 
 // can this pass go through the TMA kernel?
-static bool v2_eligible(const qm_state* st, const PlanPass& P) {
+static bool v4_eligible(const qm_state* st, const PlanPass& P) {
     if (!st->pipeline || !get_encode()) return false;
     if (P.m != 11 && P.m != 12) return false;
     if (P.L < 3 || P.L > 8) return false;
@@ -220,39 +221,65 @@ static bool v2_eligible(const qm_state* st, const PlanPass& P) {
     int nr = hb_runs(P.hb, rs, rl);
     if (nr > 3) return false;
     for (int i = 0; i < nr; ++i) if (rl[i] > 8) return false;
-    if ((int)P.groups.size() > kV2MaxGroups) return false;
-    size_t nsub = 0;
+    if ((int)P.groups.size() > kV4MaxGroups) return false;
+    size_t nrec = P.groups.size();
     for (const PlanGroup& G : P.groups) {
-        nsub += G.subs.size();
-        for (const LGate& x : G.subs) if (!x.liftable) return false;
+        if ((int)G.rb.size() > kV4BlockBits) return false;
+        for (const LGate& x : G.subs) { if (!x.liftable) return false; nrec += 1 + (x.slot >= 0) + (x.ctrl >= 0); }
     }
-    if (nsub > (size_t)kV2MaxSubs) return false;
+    if (nrec > (size_t)kV4MaxRecs) return false;
     if ((total_amps(st) >> 3) > 0x7fffffffull) return false;      // TMA coordinates are int32
     return true;
 }
 
-static void encode_v2(const PlanPass& P, V2Program& out) {
-    memset(&out, 0, sizeof(out));
+// PlanPass -> V4Program (layout in fused_tma.cuh).  Returns false when the pass breaks a limit of the
+// kernel that the planner is supposed to respect (context bits, warp-uniform controls); the caller then
+// falls back to the general kernel.
+static bool encode_v4(const PlanPass& P, V4Program& out) {
+    memset(&out, 0, offsetof(V4Program, recs));
     out.ngroups = (int)P.groups.size();
-    int nsub = 0;
-    const int nwarp_bits = P.m - 3 - 5;
+    int outer_of[64]; for (int i = 0; i < 64; ++i) outer_of[i] = -1;
+    int n_outer = 0, nrec = 0;
+    bool ok = true;
+    // context bit of a physical index bit that is not a register-block bit of the current group
+    auto ctx_bit = [&](int phys) -> uint32_t {
+        const int tl = tile_local_of(P, phys);
+        if (tl >= 0) return 1u << tl;
+        if (outer_of[phys] < 0) {
+            if (n_outer >= kV4MaxOuter) { ok = false; return 0u; }
+            outer_of[phys] = n_outer;
+            out.outer_pack[n_outer / 10] |= (uint64_t)phys << (6 * (n_outer % 10));
+            ++n_outer;
+        }
+        return 1u << (kV4CtxOuter + outer_of[phys]);
+    };
+    const int NB = kV4BlockBits;
+    const int nwarp_bits = P.m - NB - 5;
     for (size_t gi = 0; gi < P.groups.size(); ++gi) {
         const PlanGroup& G = P.groups[gi];
-        V2Group& g = out.groups[gi];
-        int rbl[3] = { -1, -1, -1 }; uint32_t blockmask = 0; int nrb = 0;
-        for (size_t i = 0; i < G.rb.size(); ++i) { rbl[nrb] = tile_local_of(P, G.rb[i]); blockmask |= 1u << rbl[nrb]; ++nrb; }
-        // always three block bits: pad with tile bits no gate of this group targets (highest first)
-        for (int b = P.m - 1; b >= 0 && nrb < 3; --b) if (!((blockmask >> b) & 1)) { rbl[nrb++] = b; blockmask |= 1u << b; }
-        std::sort(rbl, rbl + 3);
-        for (int i = 0; i < 3; ++i) g.rbmask[i] = (uint16_t)(1u << rbl[i]);
-        // thread-index bit order (see planner.hpp encode_pass for the bank argument)
-        std::vector<int> order; uint32_t used = blockmask;
+        V4Group& g = out.groups[gi];
+        int rbl[NB]; for (int i = 0; i < NB; ++i) rbl[i] = -1;
+        uint32_t blockmask = 0; int nrb = 0;
+        for (size_t i = 0; i < G.rb.size() && nrb < NB; ++i) { rbl[nrb] = tile_local_of(P, G.rb[i]); blockmask |= 1u << rbl[nrb]; ++nrb; }
+        // always four block bits: pad with tile bits no gate of this group targets (highest first)
+        for (int b = P.m - 1; b >= 0 && nrb < NB; --b) if (!((blockmask >> b) & 1)) { rbl[nrb++] = b; blockmask |= 1u << b; }
+        std::sort(rbl, rbl + NB);
+        for (int i = 0; i < NB; ++i) { const uint32_t mk = 1u << rbl[i]; g.s[i] = (mk ^ ((mk >> 3) & 7u)) << 4; }
+        // Thread-index bit order.  The three lowest thread bits must give distinct 16-byte bank groups under
+        // slot = i ^ ((i >> 3) & 7): bit k of the slot's low 3 bits is i_k ^ i_{k+3}, so pick a free bit from
+        // {k, k+3} for k = 0, 1, 2.  Bits the planner pinned to the warp index (controls that are not block
+        // bits) go last.
+        uint32_t wmask = 0;
+        for (int b : G.wb) { const int tl = tile_local_of(P, b); if (tl >= 0 && !((blockmask >> tl) & 1)) wmask |= 1u << tl; }
+        std::vector<int> order; uint32_t used = blockmask | wmask;
         for (int k = 0; k < 3; ++k) {
             int pick = -1;
             if (!((used >> k) & 1)) pick = k; else if (!((used >> (k + 3)) & 1)) pick = k + 3;
             if (pick >= 0) { order.push_back(pick); used |= 1u << pick; }
         }
         for (int b = 0; b < P.m; ++b) if (!((used >> b) & 1)) { order.push_back(b); used |= 1u << b; }
+        for (int b = 0; b < P.m; ++b) if ((wmask >> b) & 1) order.push_back(b);
+        if ((int)order.size() != P.m - NB || __builtin_popcount(wmask) > nwarp_bits) { ok = false; break; }
         for (int lane = 0; lane < 32; ++lane) {
             uint32_t v = 0; for (int j = 0; j < 5; ++j) if ((lane >> j) & 1) v |= 1u << order[j];
             out.lane_tab[gi][lane] = (uint16_t)v;
@@ -261,60 +288,66 @@ static void encode_v2(const PlanPass& P, V2Program& out) {
             uint32_t v = 0; for (int j = 0; j < nwarp_bits; ++j) if ((w >> j) & 1) v |= 1u << order[5 + j];
             out.warp_tab[gi][w] = (uint16_t)v;
         }
-        g.sub_off = (uint16_t)nsub; g.nsub = (uint16_t)G.subs.size();
+        g.rec_off = (uint32_t)(offsetof(V4Program, recs) + (size_t)nrec * sizeof(V4Rec));
         for (const LGate& x : G.subs) {
-            V2Sub& S = out.subs[nsub++];
-            S.slot = x.slot; S.flags = x.slot >= 0 ? 1 : 0;
-            int CB = -1;
+            if (nrec + 4 > kV4MaxRecs) { ok = false; break; }
+            int CB = -1; uint32_t cm = 0;
             if (x.ctrl >= 0) {
-                int cl = tile_local_of(P, x.ctrl);
-                if (cl < 0) { S.cm_out = 1ull << x.ctrl; S.flags |= 2; }
+                const int cl = tile_local_of(P, x.ctrl);
+                int bi = -1; if (cl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == cl) bi = i;
+                if (bi >= 0) CB = bi;
                 else {
-                    int bi = -1; for (int i = 0; i < 3; ++i) if (rbl[i] == cl) bi = i;
-                    if (bi >= 0) { S.cm_blk = (uint8_t)(1u << bi); CB = bi; } else { S.cm_loc = 1u << cl; S.flags |= 2; }
+                    cm = ctx_bit(x.ctrl);
+                    if (cl >= 0 && !((wmask >> cl) & 1)) ok = false;      // the control predicate must be warp-uniform
                 }
             }
-            int tl = tile_local_of(P, x.target);
-            int bi = -1; if (tl >= 0) for (int i = 0; i < 3; ++i) if (rbl[i] == tl) bi = i;
+            if (cm) {                          // a control outside the register block: a CTRL record in front
+                V4Rec& R = out.recs[nrec++]; memset(&R, 0, sizeof(R));
+                R.op = V4_OP_CTRL; R.cm = cm; R.aux = (uint32_t)sizeof(V4Rec) * (x.slot >= 0 ? 3u : 2u);
+            }
+            if (x.slot >= 0) {                 // per-state coefficients: a SLOT record in front of the gate
+                V4Rec& R = out.recs[nrec++]; memset(&R, 0, sizeof(R));
+                R.op = V4_OP_SLOT; R.aux = (uint32_t)x.slot;
+            }
+            V4Rec& S = out.recs[nrec++]; memset(&S, 0, sizeof(S));
+            const int tl = tile_local_of(P, x.target);
+            int bi = -1; if (tl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == tl) bi = i;
+            if (!x.diag && bi < 0) ok = false;
             LiftCoef Lc; memset(&Lc, 0, sizeof(Lc));
-            const int kind = x.slot >= 0 ? x.skind : lift_classify(x.m, Lc);   // liftable was checked by v2_eligible
-            memcpy(S.c, &Lc, sizeof(Lc));
+            const int kind = x.slot >= 0 ? x.skind : lift_classify(x.m, Lc);   // liftable was checked by v4_eligible
+            double cc[6]; memcpy(cc, Lc.c, sizeof(cc));
             // static sign variants: sg = (mk[0] ? 1 : 0) | (mk[1] ? 2 : 0); per-state slots are built for sg 0
             const int sgA = (Lc.mk[0] ? 1 : 0) | (Lc.mk[1] ? 2 : 0), sgB = (Lc.mk[2] ? 1 : 0) | (Lc.mk[3] ? 2 : 0);
             if (kind == LK_PHASE && bi < 0) {
-                S.flags |= 4;
-                S.op = (uint8_t)(kV2OpThr + (sgA == 3 ? 4 : 0) + (CB + 1));
-                S.op_hi = (uint8_t)(kV2OpThr + (sgB == 3 ? 4 : 0) + (CB + 1));
-                if (tl >= 0) S.t_loc = 1u << tl; else S.t_out = 1ull << x.target;
+                // the target bit is constant for the thread: pick one of two coefficient sets
+                S.tm = ctx_bit(x.target);
+                int variant;
+                if (sgA == sgB && (sgA == 0 || sgA == 3)) variant = sgA == 3 ? 1 : 0;
+                else {                          // halves with different signs (z!): plain complex multiply by d0 / d1
+                    variant = 2;
+                    cc[0] = x.m[0]; cc[1] = x.m[1]; cc[2] = 0; cc[3] = x.m[6]; cc[4] = x.m[7]; cc[5] = 0;
+                }
+                S.op = (uint32_t)(V4_OP_THR + variant * (NB + 1) + (CB + 1));
             } else {
-                const int bc = v2_bc_index(bi, CB);
+                const int bc = v4_bc_index(bi, CB);
                 int base;
-                if (kind == LK_ROT) base = sgA * 9;
-                else if (kind == LK_ROTX) base = 36 + (sgA == 3 ? 9 : 0);
-                else if (kind == LK_PHASE) base = 54 + ((sgA == 3 ? 2 : 0) + (sgB == 3 ? 1 : 0)) * 9;
-                else base = 90;
-                S.op = (uint8_t)(base + bc);
+                if (kind == LK_ROT) base = sgA * V4_NBC;
+                else if (kind == LK_ROTX) base = V4_OP_ROTX + (sgA == 3 ? V4_NBC : 0);
+                else if (kind == LK_PHASE) base = V4_OP_PHASE + ((sgA == 3 ? 2 : 0) + (sgB == 3 ? 1 : 0)) * V4_NBC;
+                else base = V4_OP_PERMX;
+                S.op = (uint32_t)(base + bc);
             }
+            for (int q = 0; q < 3; ++q) { S.c[2 * q] = cc[q]; S.c[2 * q + 1] = cc[3 + q]; }     // pairwise {set 0, set 1}
         }
+        if (!ok) break;
+        V4Rec& E = out.recs[nrec++]; memset(&E, 0, sizeof(E));
+        E.op = V4_OP_END;
     }
-    out.nsubs = nsub;
+    out.nrecs = nrec; out.n_outer = n_outer; out.ctx_const = 0;
+    return ok;
 }
 
-template <int M, int STAGES>
-static int launch_v2_t(qm_state* st, const CUtensorMap& tm, const V2Program* d_prog, const double* d_slots, const V2Launch& lp) {
-    constexpr int threads = (1 << (M - 3)) + 32;
-    constexpr size_t smem = (size_t)STAGES * (16u << M) + sizeof(V2Program) + 2 * STAGES * 8 + 1024;
-    static bool attr = false;
-    if (!attr) { CU(cudaFuncSetAttribute(k_fused_tma<M, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    const int per_sm = M >= 12 ? 1 : 2;
-    uint64_t cap = (uint64_t)st->sms * per_sm;
-    int grid = (int)(lp.ntiles < cap ? lp.ntiles : cap);
-    k_fused_tma<M, STAGES><<<grid, threads, smem, st->stream>>>(tm, d_prog, d_slots, lp);
-    CU(cudaGetLastError());
-    return QM_OK;
-}
-
-static int launch_pass_v2(qm_state* st, const V2Program* d_prog, const PlanPass& P, const double* d_slots, int nslots) {
+static int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const double* d_slots, int nslots) {
     // tensor map: dim0 = one 128-byte row (8 amplitudes = 16 doubles); dim1 = row index over the whole
     // array (the box takes 2^(L-3) consecutive rows at the tile's base); dims 2..4 = the runs of high
     // tile bits (size 2^len, stride 16 * 2^start bytes), unused dims have size 1.
@@ -333,12 +366,14 @@ static int launch_pass_v2(qm_state* st, const V2Program* d_prog, const PlanPass&
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(QM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    V2Launch lp; memset(&lp, 0, sizeof(lp));
-    lp.ntiles = amps >> P.m; lp.reg_bits = st->nl; lp.L = P.L; lp.nh = (int)P.hb.size();
-    for (size_t j = 0; j < P.hb.size(); ++j) lp.hb[j] = P.hb[j];
+    V4Launch lp; memset(&lp, 0, sizeof(lp));
+    lp.ntiles = amps >> P.m; lp.reg_bits = st->nl; lp.L = P.L;
+    for (int i = 0; i < 3; ++i) { lp.run_start[i] = i < nr ? rs[i] : 0; lp.run_len[i] = i < nr ? rl[i] : 0; }
     lp.rank_or = st->g ? ((uint64_t)st->rank << st->nl) : 0; lp.nslots = nslots;
-    if (P.m == 11) QM_TRY((launch_v2_t<11, 3>(st, tm, d_prog, d_slots, lp)));
-    else QM_TRY((launch_v2_t<12, 3>(st, tm, d_prog, d_slots, lp)));
+    if (P.m == 11) QM_TRY(launch_v4_m11(st->stream, st->sms, tm, prog, d_slots, lp));
+    else QM_TRY(launch_v4_m12(st->stream, st->sms, tm, prog, d_slots, lp));
+    // the program crosses the host link with the launch: counted as host->device bytes
+    st->ctr.bytes_h2d += offsetof(V4Program, recs) + (size_t)prog.nrecs * sizeof(V4Rec);
     st->ctr.launches++; st->ctr.passes++;
     st->ctr.bytes_hbm += 32ull * amps;
     return QM_OK;
@@ -370,48 +405,64 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     pl.opt.n_local = st->nl; pl.opt.n_global = st->g;
     pl.opt.tile_bits = st->tile_bits; pl.opt.low_bits = st->low_bits; pl.opt.fuse = st->fuse;
     if (st->max_cost > 0) pl.opt.max_cost = st->max_cost < 9.0 ? 9.0 : st->max_cost;
-    if (st->pipeline) { pl.opt.max_runs = 3; pl.opt.max_subs = kV2MaxSubs; pl.opt.max_groups = kV2MaxGroups; }
     std::vector<PlanPass> passes;          // of the current segment (between remaps)
     std::vector<unsigned char> blob;
     std::vector<size_t> offs;
+    std::vector<V4Program> v4progs;
     bool first_event = true;
     // lower once under the current logical->physical map; a remap later relabels what is left
     int rc = lower_gates(gates, ngates, st->n, st->perm.data(), st->fuse, pl.gates, smap);
     if (rc) return set_err(rc, "bad gate in circuit");
-    if (st->pipeline) prepare_for_lifting(pl.gates);
+    // The TMA kernel takes the circuit when tiles of 2^11 / 2^12 amplitudes fit a register and every gate has
+    // an in-place lifting form; otherwise the whole circuit is planned for the general kernel (3-bit blocks).
+    bool tma = st->pipeline && get_encode() && (st->tile_bits == 11 || st->tile_bits == 12) && st->nl >= st->tile_bits &&
+               st->low_bits >= 3 && (total_amps(st) >> 3) <= 0x7fffffffull;
+    if (tma) {
+        std::vector<LGate> lifted = pl.gates;
+        prepare_for_lifting(lifted);
+        for (const LGate& x : lifted) if (!x.liftable) { tma = false; break; }
+        if (tma) pl.gates.swap(lifted);
+    }
+    if (tma) {
+        pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
+        pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
+        if (smap) pl.opt.max_subs = (kV4MaxRecs - kV4MaxGroups) / 2;      // every per-state gate takes two records
+    }
     pl.done.assign(pl.gates.size(), 0);
     while (true) {
-        passes.clear(); blob.clear(); offs.clear();
+        passes.clear(); blob.clear(); offs.clear(); v4progs.clear();
         PlanPass P;
-        std::vector<char> use_v2;
+        std::vector<int> v4_of;                 // pass -> index into v4progs, or -1 (general kernel, program in the blob)
         while (pl.next_pass(P)) {
             offs.push_back(blob.size());
-            if (v2_eligible(st, P)) {
-                blob.resize(blob.size() + sizeof(V2Program));
-                encode_v2(P, *reinterpret_cast<V2Program*>(&blob[offs.back()]));
-                use_v2.push_back(1);
-            } else {
-                encode_pass(P, blob);
-                use_v2.push_back(0);
+            bool v3 = false;
+            if (tma && v4_eligible(st, P)) {
+                v4progs.emplace_back();
+                if (encode_v4(P, v4progs.back())) v3 = true; else v4progs.pop_back();
             }
+            if (v3) v4_of.push_back((int)v4progs.size() - 1);
+            else if (tma) return set_err(QM_ERR_STATE, "planner produced a pass the TMA kernel cannot run (internal error)");
+            else { encode_pass(P, blob); v4_of.push_back(-1); }
             while (blob.size() % 16) blob.push_back(0);
             passes.push_back(P);
         }
         bool leftover = false;
         for (size_t i = pl.first; i < pl.gates.size(); ++i) if (!pl.done[i]) { leftover = true; break; }
         if (leftover && st->g == 0) return set_err(QM_ERR_STATE, "planner could not place a gate (internal error)");
-        // upload + launch
+        // upload (general-kernel programs only; the TMA kernel takes its program as a launch parameter) + launch
         if (!passes.empty()) {
-            QM_TRY(ENSURE_DEV(st, d_blob, blob.size()));
-            CU(cudaEventSynchronize(st->ev_stage));      // pinned staging buffer free again?
-            QM_TRY(ENSURE_PIN(st, h_blob, blob.size()));
-            memcpy(st->h_blob, blob.data(), blob.size());
             if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
-            CU(cudaMemcpyAsync(st->d_blob, st->h_blob, blob.size(), cudaMemcpyHostToDevice, st->stream));
-            st->ctr.bytes_h2d += blob.size();
-            CU(cudaEventRecord(st->ev_stage, st->stream));
+            if (!blob.empty()) {
+                QM_TRY(ENSURE_DEV(st, d_blob, blob.size()));
+                CU(cudaEventSynchronize(st->ev_stage));      // pinned staging buffer free again?
+                QM_TRY(ENSURE_PIN(st, h_blob, blob.size()));
+                memcpy(st->h_blob, blob.data(), blob.size());
+                CU(cudaMemcpyAsync(st->d_blob, st->h_blob, blob.size(), cudaMemcpyHostToDevice, st->stream));
+                st->ctr.bytes_h2d += blob.size();
+                CU(cudaEventRecord(st->ev_stage, st->stream));
+            }
             for (size_t i = 0; i < passes.size(); ++i) {
-                if (use_v2[i]) QM_TRY(launch_pass_v2(st, reinterpret_cast<const V2Program*>(st->d_blob + offs[i]), passes[i], d_slots_lift, nslots));
+                if (v4_of[i] >= 0) QM_TRY(launch_pass_v4(st, v4progs[v4_of[i]], passes[i], d_slots_lift, nslots));
                 else QM_TRY(launch_pass(st, st->d_blob + offs[i], passes[i], d_slots, nslots));
             }
         }
@@ -857,12 +908,21 @@ extern "C" int32_t qm_plan_describe(int32_t n_qubits, int32_t global_bits, int32
                                     int32_t allow_remap, const qm_gate* gates, int32_t ngates, int32_t* out,
                                     int64_t cap, int64_t* out_len) {
     (void)allow_remap;
+    return qm_plan_describe_ex(n_qubits, global_bits, tile_bits, low_bits, 0.0, 0, gates, ngates, out, cap, out_len);
+}
+
+extern "C" int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
+                                       double max_cost, int32_t pipeline, const qm_gate* gates, int32_t ngates,
+                                       int32_t* out, int64_t cap, int64_t* out_len) {
     if (!gates || !out_len || n_qubits < 1 || global_bits < 0 || global_bits >= n_qubits) return set_err(QM_ERR_ARG, "bad argument");
     Planner pl;
     pl.opt.n_local = n_qubits - global_bits; pl.opt.n_global = global_bits;
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
+    if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
+    if (pipeline) { pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups; pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits; }
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
+    if (pipeline) prepare_for_lifting(pl.gates);
     pl.done.assign(pl.gates.size(), 0);
     std::vector<int32_t> v;
     PlanPass P;
@@ -930,5 +990,36 @@ extern "C" int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t 
     if ((int32_t)v.size() > cap || !out) return set_err(QM_ERR_ARG, "output too small: need %d", (int)v.size());
     memcpy(out, v.data(), v.size() * sizeof(qm_gate));
     if (pass_of) memcpy(pass_of, po.data(), po.size() * sizeof(int32_t));
+    return QM_OK;
+}
+
+// TEST INFRASTRUCTURE (host only, see emulate.hpp): plan `gates` exactly as the engine would for the TMA
+// kernel, encode every pass and walk the encoded programs over a host state vector.
+extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
+                                   const qm_gate* gates, int32_t ngates, double* state, int32_t* n_passes) {
+    if (!gates || !state || n_qubits < 11 || n_qubits > 24 || (tile_bits != 11 && tile_bits != 12) || tile_bits > n_qubits ||
+        low_bits < 3 || low_bits > 8)
+        return set_err(QM_ERR_ARG, "bad argument");
+    Planner pl;
+    pl.opt.n_local = n_qubits; pl.opt.n_global = 0;
+    pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
+    if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
+    pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
+    pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
+    int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
+    if (rc) return set_err(rc, "bad gate");
+    prepare_for_lifting(pl.gates);
+    for (const LGate& x : pl.gates) if (!x.liftable) return set_err(QM_ERR_STATE, "a gate has no lifting form");
+    pl.done.assign(pl.gates.size(), 0);
+    std::vector<V4Program> prog(1);
+    PlanPass P; int np = 0;
+    while (pl.next_pass(P)) {
+        if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
+        if (!emulate_v4(prog[0], P, reinterpret_cast<EmuAmp*>(state), n_qubits, 0, nullptr))
+            return set_err(QM_ERR_STATE, "pass %d: malformed program (opcode / non-uniform control predicate)", np);
+        ++np;
+    }
+    for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) return set_err(QM_ERR_STATE, "planner left a gate behind");
+    if (n_passes) *n_passes = np;
     return QM_OK;
 }

@@ -1,0 +1,241 @@
+#!/usr/bin/env python
+"""Generates quromorphic.jl_b200/csrc/v4_dispatch.inc: one register-block GROUP of the fused TMA pass as ONE
+inline-PTX block — address arithmetic, the 16 amplitude loads, the gate interpreter ("threaded code") and
+the 16 stores.
+
+Design notes (all measured on B200, see profiles/ and DESIGN.md):
+  * 16 amplitudes (4 index bits) per thread.  With 8 the per-gate overhead of an interpreter — fetching the
+    gate record, the indexed jump, the wait for the coefficients — cost more warp time than the FP64 work
+    it dispatched (ncu: 46 % of stall samples in the gate bodies outside DFMA against 21 % on DFMA, FP64
+    pipe 26 % busy).  Doubling the block doubles the FMAs behind every dispatch (48 per full-cost gate in
+    16 independent chains), and a 12-bit tile is covered by 3 groups instead of 4.
+  * Every gate body ends with its own dispatch of the next record (`brx.idx.uni`: the opcode is
+    warp-uniform), so there is no loop counter (the list ends with an END record), no flag decoding and no
+    branch back.  The next record's header is fetched at the top of a body, its coefficient pairs in between
+    the three shear steps (see LOAD_PAIR).
+  * Records are read from shared memory (16-byte broadcasts).  Reading them with LDC from the kernel-parameter
+    constant bank takes the load off the LSU (tools/microbench/ldc_bench.cu: a warp-uniform 64-byte record
+    costs 8 LSU wavefronts) but the constant-cache latency (~80 cycles hit, more on a miss with 16 warps at
+    different places of a 15 KB program) made every variant tried slower: 27.8 ms against 21.7 ms per
+    compute-bound pass at 30 qubits.
+  * A control that is not a register-block bit has its own record in front of the gate (CTRL): the planner
+    keeps such controls on warp-index bits or outside the tile, so the predicate is warp-uniform and the warp
+    either runs the next record or jumps over it.  Gate bodies themselves carry no predicate.
+
+A record is 64 bytes:  u32 op, cm, tm, aux;  f64 c0, c3, c1, c4, c2, c5.
+  cm   CTRL: context bits that must all be set          tm   THR: context bit selecting the coefficient set
+  aux  SLOT: per-state coefficient slot;  CTRL: bytes from this record to the one after the controlled gate
+Operands:  %0 shared address of the current record ("+r")   %1 context word   %2 per-state coefficient base ("l")
+           %3 shared address of the tile buffer      %4 the thread's swizzled byte offset in the tile
+           %5..%8 swizzled byte offsets of the four block bits
+Opcodes (must match encode_v4 in qm_api.cu), NBC = 16 legal (B, CB) pairs:
+   ROT   sign variant 0..3 x NBC      ROTX  sign variant 0, 3 x NBC      PHASE (sg set 0, sg set 1) in 00 03 30 33 x NBC
+   PERMX x NBC       THR (lift sg 0, lift sg 3, complex multiply) x 5 (CB = -1, 0..3)       SLOT   CTRL   END
+"""
+import os
+
+NB = 4                      # block bits
+NA = 1 << NB                # amplitudes per thread
+BCS = [(B, CB) for B in range(NB) for CB in range(-1, NB) if CB != B]
+NBC = len(BCS)              # 16
+
+
+def X(k): return "x%d" % k
+def Y(k): return "y%d" % k
+
+
+# coefficient registers: set 0 = (c0, c1, c2) = (t1, s1, t2); set 1 = (c3, c4, c5).  In a record they are stored
+# pairwise, {c0, c3} {c1, c4} {c2, c5}: a lift uses t1 only in its first shear, s1 in the second, t2 in the third,
+# so the NEXT record's {c0, c3} can be fetched as soon as the first shears of this body have issued, and so on —
+# the coefficient latency hides behind the remaining FMAs without a second register set.
+C = ["c%d" % i for i in range(6)]
+LOAD_PAIR = ["ld.shared.v2.f64 {c0, c3}, [%0+16];", "ld.shared.v2.f64 {c1, c4}, [%0+32];", "ld.shared.v2.f64 {c2, c5}, [%0+48];"]
+
+
+def lift_steps(x, y, t1, s1, t2, sg):
+    """the three shears of one real pair, as three lists of instructions (dependent in this order)"""
+    a = ["fma.rn.f64 %s, %s, %s, %s;" % (x, t1, y, x)]
+    if sg & 1:
+        b = ["neg.f64 ng, %s;" % y, "fma.rn.f64 %s, %s, %s, ng;" % (y, s1, x)]
+    else:
+        b = ["fma.rn.f64 %s, %s, %s, %s;" % (y, s1, x, y)]
+    if sg & 2:
+        c = ["neg.f64 ng, %s;" % x, "fma.rn.f64 %s, %s, %s, ng;" % (x, t2, y)]
+    else:
+        c = ["fma.rn.f64 %s, %s, %s, %s;" % (x, t2, y, x)]
+    return a, b, c
+
+
+def interleave(chains, pre=(None, None, None)):
+    """step-major order: step 1 of every chain, then step 2, then step 3; after step j the next record's
+    j-th coefficient pair is loaded; pre[j] = instructions that must precede step j (coefficient selects)"""
+    out = []
+    for step in range(3):
+        if pre[step]:
+            out += pre[step]
+        for ch in chains:
+            out += ch[step]
+        out.append(LOAD_PAIR[step])
+    return out
+
+
+def ctrl_ok(k, CB):
+    return CB < 0 or (k >> CB) & 1
+
+
+def body_rot(B, CB, sg):
+    ch = []
+    for k in range(NA):
+        if not ctrl_ok(k, CB) or (k >> B) & 1:
+            continue
+        k1 = k | (1 << B)
+        ch.append(lift_steps(X(k), X(k1), C[0], C[1], C[2], sg))
+        ch.append(lift_steps(Y(k), Y(k1), C[0], C[1], C[2], sg))
+    return interleave(ch)
+
+
+def body_rotx(B, CB, sg):
+    ch = []
+    for k in range(NA):
+        if not ctrl_ok(k, CB) or (k >> B) & 1:
+            continue
+        k1 = k | (1 << B)
+        ch.append(lift_steps(X(k), Y(k1), C[0], C[1], C[2], sg))
+        ch.append(lift_steps(Y(k), X(k1), "n0", "n1", "n2", sg))
+    return interleave(ch, (["neg.f64 n0, c0;"], ["neg.f64 n1, c1;"], ["neg.f64 n2, c2;"]))
+
+
+def body_phase(B, CB, sg0, sg1):
+    ch = []
+    for k in range(NA):
+        if not ctrl_ok(k, CB):
+            continue
+        if (k >> B) & 1:
+            ch.append(lift_steps(X(k), Y(k), C[3], C[4], C[5], sg1))
+        else:
+            ch.append(lift_steps(X(k), Y(k), C[0], C[1], C[2], sg0))
+    return interleave(ch)
+
+
+def body_permx(B, CB):
+    o = list(LOAD_PAIR)
+    for k in range(NA):
+        if not ctrl_ok(k, CB) or (k >> B) & 1:
+            continue
+        k1 = k | (1 << B)
+        for a, b in ((X(k), X(k1)), (Y(k), Y(k1))):
+            o += ["xor.b64 %s, %s, %s;" % (a, a, b), "xor.b64 %s, %s, %s;" % (b, b, a), "xor.b64 %s, %s, %s;" % (a, a, b)]
+    return o
+
+
+# THR: the thread picks coefficient set 1 when its context has the target bit (htm is read before the header
+# prefetch overwrites it; the selects sit right before the step that uses them)
+THR_PHI = ["and.b32 t, %1, htm;", "setp.ne.u32 phi, t, 0;"]
+
+
+def body_thr_lift(CB, sg):
+    ch = [lift_steps(X(k), Y(k), C[0], C[1], C[2], sg) for k in range(NA) if ctrl_ok(k, CB)]
+    return interleave(ch, (["selp.f64 c0, c3, c0, phi;"], ["selp.f64 c1, c4, c1, phi;"], ["selp.f64 c2, c5, c2, phi;"]))
+
+
+def body_thr_mul(CB):
+    """(x, y) <- (cr x - ci y, ci x + cr y) with cr = c0, ci = c1: any unit phase, no sign variants"""
+    o = ["selp.f64 c0, c3, c0, phi;", "selp.f64 c1, c4, c1, phi;", "neg.f64 n1, c1;"]
+    ks = [k for k in range(NA) if ctrl_ok(k, CB)]
+    for h in range(0, len(ks), 4):
+        kk = ks[h:h + 4]
+        o += ["mul.f64 tm%d, c1, %s;" % (k & 3, X(k)) for k in kk]
+        o += ["mul.f64 %s, c0, %s;" % (X(k), X(k)) for k in kk]
+        o += ["fma.rn.f64 %s, n1, %s, %s;" % (X(k), Y(k), X(k)) for k in kk]
+        o += ["fma.rn.f64 %s, c0, %s, tm%d;" % (Y(k), Y(k), k & 3) for k in kk]
+    return o + LOAD_PAIR
+
+
+# every body: advance to the next record, fetch its header, run, (the coefficient pairs are fetched inside the
+# body), jump.  The pointer is advanced BEFORE the loads that use it: an add after them has to wait until the
+# loads have read their address register.
+ADVANCE_HDR = ["add.u32 %0, %0, 64;", "ld.shared.v4.u32 {hop, hcm, htm, hax}, [%0];"]
+DISPATCH = ["brx.idx.uni hop, V4T;"]
+
+
+def addresses(tag):
+    """off_k (k < 8) = b0 xor the swizzled offsets of the low three block bits set in k; the address of
+    amplitude k is tile + off_(k & 7), xor the fourth block bit's offset for k >= 8.  Only eight offsets stay
+    live across the gate loop (sixteen addresses did not fit the register budget and were spilled)."""
+    if tag == "setup":
+        o = ["mov.b32 o0, %4;"]
+        for k in range(1, 8):
+            low = k & -k
+            o.append("xor.b32 o%d, o%d, %%%d;" % (k, k ^ low, 5 + low.bit_length() - 1))
+        return o
+    o = []
+    for k in range(NA):
+        if k < 8:
+            o.append("add.u32 ad, o%d, %%3;" % k)
+        else:
+            o += ["xor.b32 ad, o%d, %%8;" % (k & 7), "add.u32 ad, ad, %3;"]
+        if tag == "load":
+            o.append("ld.shared.v2.f64 {x%d, y%d}, [ad];" % (k, k))
+        else:
+            o.append("st.shared.v2.f64 [ad], {x%d, y%d};" % (k, k))
+    return o
+
+
+def main():
+    bodies = []          # (instructions before the header prefetch, main instructions)
+    for sg in range(4):
+        bodies += [([], body_rot(B, CB, sg)) for B, CB in BCS]
+    op_rotx = len(bodies)
+    for sg in (0, 3):
+        bodies += [([], body_rotx(B, CB, sg)) for B, CB in BCS]
+    op_phase = len(bodies)
+    for s0, s1 in ((0, 0), (0, 3), (3, 0), (3, 3)):
+        bodies += [([], body_phase(B, CB, s0, s1)) for B, CB in BCS]
+    op_permx = len(bodies)
+    bodies += [([], body_permx(B, CB)) for B, CB in BCS]
+    op_thr = len(bodies)
+    for kind in (0, 3, "mul"):
+        for CB in range(-1, NB):
+            bodies.append((THR_PHI, body_thr_mul(CB) if kind == "mul" else body_thr_lift(CB, kind)))
+    n_gate_ops = len(bodies)
+    OP_SLOT, OP_CTRL, OP_END = n_gate_ops, n_gate_ops + 1, n_gate_ops + 2
+    nops = n_gate_ops + 3
+    lines = ["{", ".reg .f64 x<%d>, y<%d>, c<6>, ng, n0, n1, n2, tm<4>;" % (NA, NA), ".reg .b32 hop, hcm, htm, hax, t, ad, o<8>;",
+             ".reg .pred pact, phi;", ".reg .b64 sa;",
+             "V4T: .branchtargets " + ", ".join("V4L%d" % i for i in range(nops)) + ";"]
+    lines += addresses("setup") + addresses("load")
+    lines += ["ld.shared.v4.u32 {hop, hcm, htm, hax}, [%0];"] + LOAD_PAIR + DISPATCH
+    for i, (pre, b) in enumerate(bodies):
+        lines.append("V4L%d:" % i)
+        lines += pre + ADVANCE_HDR + b + DISPATCH
+    # SLOT (aux = slot index): all six coefficients of the record that follows come from the per-state table
+    lines.append("V4L%d:" % OP_SLOT)
+    lines += ["mul.wide.u32 sa, hax, 64;", "add.u64 sa, sa, %2;"] + ADVANCE_HDR
+    lines += ["ld.global.nc.v2.f64 {c0, c1}, [sa];", "ld.global.nc.v2.f64 {c2, c3}, [sa+16];",
+              "ld.global.nc.v2.f64 {c4, c5}, [sa+32];"] + DISPATCH
+    # CTRL (cm = context bits that must be set, aux = bytes to the record after the controlled gate): the
+    # planner keeps such controls warp-uniform, so the whole warp either runs the next record or skips it
+    lines.append("V4L%d:" % OP_CTRL)
+    lines += ["and.b32 t, %1, hcm;", "setp.eq.u32 pact, t, hcm;", "selp.u32 t, 64, hax, pact;", "add.u32 %0, %0, t;",
+              "ld.shared.v4.u32 {hop, hcm, htm, hax}, [%0];"] + LOAD_PAIR + DISPATCH
+    lines.append("V4L%d:" % OP_END)
+    lines += addresses("store")
+    lines.append("}")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = os.path.join(here, "..", "quromorphic.jl_b200", "csrc", "v4_dispatch.inc")
+    defs = ("#define V4_NUM_OPS %d\n#define V4_NBC %d\n#define V4_OP_ROTX %d\n#define V4_OP_PHASE %d\n#define V4_OP_PERMX %d\n"
+            "#define V4_OP_THR %d\n#define V4_OP_SLOT %d\n#define V4_OP_CTRL %d\n#define V4_OP_END %d\n"
+            % (nops, NBC, op_rotx, op_phase, op_permx, op_thr, OP_SLOT, OP_CTRL, OP_END))
+    with open(os.path.join(os.path.dirname(out), "v4_ops.inc"), "w") as f:
+        f.write("// GENERATED by tools/gen_v4_dispatch.py — do not edit.  Opcode numbering of the gate interpreter.\n" + defs)
+    with open(out, "w") as f:
+        f.write("// GENERATED by tools/gen_v4_dispatch.py — do not edit.  %d gate bodies + SLOT + CTRL + END, threaded dispatch.\n" % n_gate_ops)
+        f.write("#define V4_GROUP_PTX \\\n")
+        for ln in lines:
+            f.write('    "%s\\n\\t" \\\n' % ln)
+        f.write('    ""\n')
+    print("wrote", out, "ops", nops, "ptx lines", len(lines))
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--costs", default="0,32,64,128")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--pipes", default="1")
+    ap.add_argument("--clocks", action="store_true", help="sample nvidia-smi clocks / power while a configuration runs")
+    ap.add_argument("--reset", action="store_true", help="reset to |0..0> before every repetition")
     args = ap.parse_args()
     pkg = ge.load_package()
     L = pkg._lib
@@ -36,19 +38,27 @@ def main():
         st.set_option(L.OPT_LOW_BITS, low)
         st.set_option(L.OPT_MAX_COST, cost)
         best = None
-        for _ in range(args.reps + 1):
-            st.reset(0)
+        sampler = None
+        if args.clocks:
+            from bench import ClockSampler
+            sampler = ClockSampler(0)
+            sampler.start()
+        for r in range(args.reps + 1):
+            if r == 0 or args.reset:      # by default the state keeps evolving: dense amplitudes, realistic power draw
+                st.reset(0)
             st.counters_reset()
             st.apply_circuit(gates)
             c = st.counters()
             if best is None or c["ms_device"] < best["ms_device"]:
                 best = c
+        clk = sampler.stop() if sampler else {}
         ms = best["ms_device"]
         per = ms / best["passes"]
         gbs = 32.0 * (1 << n) / (per * 1e-3) / 1e9
         print(json.dumps({"pipe": pipe, "tile": tile, "low": low, "max_cost": cost, "passes": best["passes"], "ms_total": round(ms, 2),
                           "ms_per_pass": round(per, 3), "hbm_gbs": round(gbs, 1), "gates_per_s": round(len(gates) / ms * 1e3, 1),
-                          "plan_ms": round(best["ms_plan"], 2)}), flush=True)
+                          "plan_ms": round(best["ms_plan"], 2), "sm_mhz": clk.get("sm_mhz"), "power_w": clk.get("power_w"),
+                          "reasons": clk.get("reasons")}), flush=True)
     st.close()
 
 
