@@ -168,6 +168,13 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+ALT_MAX_COST = 96          # planner cost cap of the secondary "deep fusion" measurement (engine default: 32)
+
+
+def st_max_cost(args):
+    return int(args.max_cost) if args.max_cost >= 0 else 32
+
+
 def workload_config(ngpus, n, c4=False):
     if ngpus == 1 and c4:
         return {"workload": "C4 base: %d-qubit reservoir step on one B200 (2^%d amplitudes), no exchange" % (n, n),
@@ -195,6 +202,7 @@ def main():
     ap.add_argument("--low-bits", type=int, default=-1)
     ap.add_argument("--max-cost", type=float, default=-1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-alt", action="store_true", help="skip the deep-fusion secondary measurement")
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c4"],
                     help="auto: C3 at N = 1, C4 at N > 1; c4 at N = 1 runs the 33-qubit weak-scaling base")
     args = ap.parse_args()
@@ -301,6 +309,32 @@ def main():
     }
     if args.depth != C3_DEPTH or n != C3_QUBITS:
         line["config"]["workload"] += " [NON-DEFAULT size: depth %d, %d qubits]" % (args.depth, n)
+    line["config"]["planner_max_cost"] = st_max_cost(args)
+
+    # ---- same workload with deeper fusion (fewer, FP64-heavier passes): the other end of the trade-off ----
+    if not args.no_alt:
+        st.set_option(L.OPT_MAX_COST, ALT_MAX_COST)
+        step(); st.sync()
+        st.counters_reset()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        tw = time.perf_counter()
+        a0.record(ext)
+        alt_pass_ms = 0.0
+        for _ in range(2):
+            step()
+            alt_pass_ms += st.counters()["ms_device"]
+        a1.record(ext)
+        torch.cuda.synchronize()
+        tw = time.perf_counter() - tw
+        ca = st.counters()
+        alt_ms = a0.elapsed_time(a1)
+        alt_ach = bytes_per_launch / (alt_pass_ms / max(ca["passes"], 1) * 1e-3) / 1e9
+        line["deep_fusion"] = {"planner_max_cost": ALT_MAX_COST, "value": 2 * ngates / (alt_ms * 1e-3) * scale,
+                               "e2e": 2 * ngates / tw * scale, "unit": unit, "steps": 2,
+                               "gates_per_pass": 2 * ngates / max(ca["passes"], 1),
+                               "avg_launch_ms": alt_pass_ms / max(ca["passes"], 1),
+                               "roofline_achieved_gbs": alt_ach, "roofline_frac": alt_ach / hbm_peak}
     st.close()
     del st
     torch.cuda.empty_cache()

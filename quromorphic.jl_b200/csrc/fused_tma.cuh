@@ -59,10 +59,10 @@ static const int kV4MaxRecs = 240;     // gate records + SLOT / CTRL prefixes + 
 static const int kV4MaxGroups = 48;
 static const int kV4MaxSubs = 96;
 
-struct V4Rec {              // 64 bytes, read by the PTX interpreter with 16-byte shared-memory broadcasts
+struct V4Rec {              // 64 bytes, read by the PTX interpreter with shared-memory broadcasts
     uint32_t op;            // opcode
-    uint32_t cm;            // CTRL: context bits that must all be set (a control outside the register block)
     uint32_t tm;            // THR: context bit selecting the coefficient set
+    uint32_t cm;            // CTRL: context bits that must all be set (a control outside the register block)
     uint32_t aux;           // SLOT: per-state slot index;  CTRL: bytes to the record after the controlled gate
     double   c[6];          // pairwise {t1, t1'} {s1, s1'} {t2, t2'} (set 0, set 1)  |  THR multiply: {cr, cr'} {ci, ci'} -
 };

@@ -77,12 +77,13 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     constexpr uint32_t TILE_BYTES = 16u << M;
     static_assert(TEAMS <= STAGES && NCOMP % 128 == 0 && TEAM % 32 == 0, "team shape");
     extern __shared__ unsigned char smem_dyn[];
-    // [stages][TILE_BYTES] | lane_tab, warp_tab | gate records | barriers ; SWIZZLE_128B needs the stages 1024-byte aligned
+    // [stages][TILE_BYTES] | lane_tab, warp_tab | gate records | per-team slot bases | barriers ; SWIZZLE_128B needs the stages 1024-byte aligned
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* stage_base = smem;
     unsigned char* tabs = smem + (size_t)STAGES * TILE_BYTES;
     unsigned char* recs = tabs + kV4TabBytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(recs + sizeof(V4Rec) * kV4MaxRecs);
+    uint64_t* slot_bases = reinterpret_cast<uint64_t*>(recs + sizeof(V4Rec) * kV4MaxRecs);     // one per team
+    uint64_t* full = slot_bases + 8;
     uint64_t* computed = full + 2 * STAGES;
     // full[] holds TWO barriers per stage, used alternately (use k = i / STAGES of a stage takes barrier
     // s + STAGES * (k & 1), parity (k >> 1) & 1).  With one barrier a parity wait cannot tell "use k has
@@ -169,13 +170,13 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     const uint32_t ctx_const = P.ctx_const | kV4CtxAlways;
     const uint64_t opk0 = P.outer_pack[0], opk1 = P.outer_pack[1];
     const uint32_t stage_s = smem_u32(stage_base);
+    const uint32_t slot_s = smem_u32(slot_bases) + 8u * team;
     const uint32_t lane_s = smem_u32(tabs) + 2u * lane, warp_s = smem_u32(tabs) + 2u * (kV4MaxGroups * 32 + warp);
     int s = team % STAGES; uint32_t k = 0;        // stage and use count of the stage (tile i: s = i % STAGES, k = i / STAGES)
-    uint64_t tile_id = first + (uint64_t)team * step;
 #pragma unroll 1
-    for (uint32_t i = team; i < (uint32_t)my_tiles; i += TEAMS, tile_id += (uint64_t)TEAMS * step) {
+    for (uint32_t i = team; i < (uint32_t)my_tiles; i += TEAMS) {
         uint64_t gbase, breg;
-        tile_base(tile_id, gbase, breg);
+        tile_base((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x, gbase, breg);
         // outer part of the context word: the index bits outside the tile that some gate of this pass
         // uses as a control or as the target of a diagonal gate
         uint32_t octx = ctx_const;
@@ -187,9 +188,10 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
                 if (j == 9) pk = opk1;
             }
         }
-        const double* slot_base = slots ? slots + (size_t)breg * lp.nslots * 8 : nullptr;
+        if (slots && ttid == 0) slot_bases[team] = (uint64_t)(slots + (size_t)breg * lp.nslots * 8);
         const uint32_t tile_s = stage_s + (uint32_t)s * TILE_BYTES;
         mbar_wait(&full[s + STAGES * (int)(k & 1u)], (k >> 1) & 1u);
+        if (slots) bar_sync_named(1 + team, TEAM);       // the team sees its slot base
 #pragma unroll 1
         for (int gi = 0; gi < ngroups; ++gi) {
             const uint64_t ga = pa + offsetof(V4Program, groups) + 32u * gi;
@@ -206,7 +208,7 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
             uint32_t rp = smem_u32(recs) + (gw - (uint32_t)offsetof(V4Program, recs));
             asm volatile(V4_GROUP_PTX
                          : "+r"(rp)
-                         : "r"(ctx), "l"(slot_base), "r"(tile_s), "r"(b0), "r"((uint32_t)g01), "r"((uint32_t)(g01 >> 32)),
+                         : "r"(ctx), "r"(slot_s), "r"(tile_s), "r"(b0), "r"((uint32_t)g01), "r"((uint32_t)(g01 >> 32)),
                            "r"((uint32_t)g23), "r"((uint32_t)(g23 >> 32))
                          : "memory");
             if (gi + 1 < ngroups) bar_sync_named(1 + team, TEAM);
@@ -222,7 +224,7 @@ template <int M, int TEAMS, int STAGES>
 static int launch_v4_t(cudaStream_t stream, int sms, const CUtensorMap& tm, const V4Program& prog, const double* d_slots,
                        const V4Launch& lp) {
     constexpr int threads = TEAMS * (1 << (M - kV4BlockBits)) + kV4ProducerThreads;
-    constexpr size_t smem = (size_t)STAGES * (16u << M) + kV4TabBytes + sizeof(V4Rec) * kV4MaxRecs + 3 * STAGES * 8 + 1024;
+    constexpr size_t smem = (size_t)STAGES * (16u << M) + kV4TabBytes + sizeof(V4Rec) * kV4MaxRecs + 64 + 3 * STAGES * 8 + 1024;
     static bool attr = false;
     if (!attr) { CU(cudaFuncSetAttribute(k_fused_tma<M, TEAMS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     const uint64_t cap = (uint64_t)sms;

@@ -120,3 +120,27 @@ def test_planner_leaves_global_targets_for_remap(pkg):
     v = out[:ln.value]
     # the diagonal rz on global qubit 10 and the cnot controlled by it run locally; only rx(9) is left
     assert v[-2] == 1 and v[-1] == 1
+
+
+@pytest.mark.parametrize("n,tile,low,cost,seed", [(13, 11, 5, 0, 1), (14, 12, 5, 24.0, 2), (15, 12, 3, 64.0, 3), (15, 11, 3, 0, 4),
+                                                  (14, 12, 8, 32.0, 5), (15, 11, 4, 40.0, 6), (16, 12, 6, 96.0, 7)])
+def test_encoded_pass_programs_emulated_on_cpu(pkg, n, tile, low, cost, seed):
+    """planner + encoder of the TMA kernel, checked without a GPU: the encoded pass programs (the bytes the kernel
+    is launched with) are walked over a host vector by the scalar emulation in csrc/emulate.hpp (test
+    infrastructure) and must reproduce the oracle; a control predicate that is not warp-uniform, an unknown opcode
+    or a pass the kernel could not take is an error"""
+    gates = random_circuit(pkg, n, 300, 4000 + 17 * seed)
+    psi0 = O.random_state(n, seed)
+    got, npass = pkg._lib.plan_emulate(n, gates, psi0, tile_bits=tile, low_bits=low, max_cost=cost)
+    ref = O.apply_circuit(psi0.copy(), gates)
+    assert npass > 0
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
+def test_encoded_c3_programs_emulated_on_cpu(pkg):
+    n = 16
+    gates = pkg.circuits.c3_circuit(n=n, depth=8)
+    for tile, cost in ((12, 0.0), (11, 24.0), (12, 48.0)):
+        got, npass = pkg._lib.plan_emulate(n, gates, O.statevector(n, 0), tile_bits=tile, max_cost=cost)
+        ref = O.apply_circuit(O.statevector(n, 0), gates)
+        assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12

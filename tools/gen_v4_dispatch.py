@@ -22,10 +22,10 @@ Design notes (all measured on B200, see profiles/ and DESIGN.md):
     keeps such controls on warp-index bits or outside the tile, so the predicate is warp-uniform and the warp
     either runs the next record or jumps over it.  Gate bodies themselves carry no predicate.
 
-A record is 64 bytes:  u32 op, cm, tm, aux;  f64 c0, c3, c1, c4, c2, c5.
+A record is 64 bytes:  u32 op, tm, cm, aux;  f64 c0, c3, c1, c4, c2, c5.
   cm   CTRL: context bits that must all be set          tm   THR: context bit selecting the coefficient set
   aux  SLOT: per-state coefficient slot;  CTRL: bytes from this record to the one after the controlled gate
-Operands:  %0 shared address of the current record ("+r")   %1 context word   %2 per-state coefficient base ("l")
+Operands:  %0 shared address of the current record ("+r")   %1 context word   %2 shared address of the per-state coefficient base
            %3 shared address of the tile buffer      %4 the thread's swizzled byte offset in the tile
            %5..%8 swizzled byte offsets of the four block bits
 Opcodes (must match encode_v4 in qm_api.cu), NBC = 16 legal (B, CB) pairs:
@@ -140,40 +140,40 @@ def body_thr_lift(CB, sg):
 
 def body_thr_mul(CB):
     """(x, y) <- (cr x - ci y, ci x + cr y) with cr = c0, ci = c1: any unit phase, no sign variants"""
-    o = ["selp.f64 c0, c3, c0, phi;", "selp.f64 c1, c4, c1, phi;", "neg.f64 n1, c1;"]
+    o = ["selp.f64 c0, c3, c0, phi;", "selp.f64 c1, c4, c1, phi;", "neg.f64 n1, c1;", LOAD_PAIR[2]]
     ks = [k for k in range(NA) if ctrl_ok(k, CB)]
-    for h in range(0, len(ks), 4):
-        kk = ks[h:h + 4]
-        o += ["mul.f64 tm%d, c1, %s;" % (k & 3, X(k)) for k in kk]
+    for h in range(0, len(ks), 2):
+        kk = ks[h:h + 2]
+        o += ["mul.f64 tm%d, c1, %s;" % (k & 1, X(k)) for k in kk]
         o += ["mul.f64 %s, c0, %s;" % (X(k), X(k)) for k in kk]
         o += ["fma.rn.f64 %s, n1, %s, %s;" % (X(k), Y(k), X(k)) for k in kk]
-        o += ["fma.rn.f64 %s, c0, %s, tm%d;" % (Y(k), Y(k), k & 3) for k in kk]
-    return o + LOAD_PAIR
+        o += ["fma.rn.f64 %s, c0, %s, tm%d;" % (Y(k), Y(k), k & 1) for k in kk]
+    return o + LOAD_PAIR[:2]
 
 
 # every body: advance to the next record, fetch its header, run, (the coefficient pairs are fetched inside the
 # body), jump.  The pointer is advanced BEFORE the loads that use it: an add after them has to wait until the
 # loads have read their address register.
-ADVANCE_HDR = ["add.u32 %0, %0, 64;", "ld.shared.v4.u32 {hop, hcm, htm, hax}, [%0];"]
+ADVANCE_HDR = ["add.u32 %0, %0, 64;", "ld.shared.v2.u32 {hop, htm}, [%0];"]
 DISPATCH = ["brx.idx.uni hop, V4T;"]
 
 
 def addresses(tag):
-    """off_k (k < 8) = b0 xor the swizzled offsets of the low three block bits set in k; the address of
-    amplitude k is tile + off_(k & 7), xor the fourth block bit's offset for k >= 8.  Only eight offsets stay
-    live across the gate loop (sixteen addresses did not fit the register budget and were spilled)."""
+    """off_j (j < 4) = b0 xor the swizzled offsets of the low two block bits set in j; the address of amplitude
+    k is tile + (off_(k & 3) xor the offsets of block bits 2 and 3 as set in k).  Only four offsets stay live
+    across the gate loop (sixteen addresses did not fit the register budget and were spilled)."""
     if tag == "setup":
-        o = ["mov.b32 o0, %4;"]
-        for k in range(1, 8):
-            low = k & -k
-            o.append("xor.b32 o%d, o%d, %%%d;" % (k, k ^ low, 5 + low.bit_length() - 1))
-        return o
+        return ["mov.b32 o0, %4;", "xor.b32 o1, o0, %5;", "xor.b32 o2, o0, %6;", "xor.b32 o3, o1, %6;"]
     o = []
     for k in range(NA):
-        if k < 8:
-            o.append("add.u32 ad, o%d, %%3;" % k)
-        else:
-            o += ["xor.b32 ad, o%d, %%8;" % (k & 7), "add.u32 ad, ad, %3;"]
+        src = "o%d" % (k & 3)
+        if k & 4:
+            o.append("xor.b32 ad, %s, %%7;" % src)
+            src = "ad"
+        if k & 8:
+            o.append("xor.b32 ad, %s, %%8;" % src)
+            src = "ad"
+        o.append("add.u32 ad, %s, %%3;" % src)
         if tag == "load":
             o.append("ld.shared.v2.f64 {x%d, y%d}, [ad];" % (k, k))
         else:
@@ -200,24 +200,25 @@ def main():
     n_gate_ops = len(bodies)
     OP_SLOT, OP_CTRL, OP_END = n_gate_ops, n_gate_ops + 1, n_gate_ops + 2
     nops = n_gate_ops + 3
-    lines = ["{", ".reg .f64 x<%d>, y<%d>, c<6>, ng, n0, n1, n2, tm<4>;" % (NA, NA), ".reg .b32 hop, hcm, htm, hax, t, ad, o<8>;",
-             ".reg .pred pact, phi;", ".reg .b64 sa;",
+    lines = ["{", ".reg .f64 x<%d>, y<%d>, c<6>, ng, n0, n1, n2, tm<2>;" % (NA, NA), ".reg .b32 hop, hcm, htm, hax, t, ad, o<4>;",
+             ".reg .pred pact, phi;", ".reg .b64 sa, sb;",
              "V4T: .branchtargets " + ", ".join("V4L%d" % i for i in range(nops)) + ";"]
     lines += addresses("setup") + addresses("load")
-    lines += ["ld.shared.v4.u32 {hop, hcm, htm, hax}, [%0];"] + LOAD_PAIR + DISPATCH
+    lines += ["ld.shared.v2.u32 {hop, htm}, [%0];"] + LOAD_PAIR + DISPATCH
     for i, (pre, b) in enumerate(bodies):
         lines.append("V4L%d:" % i)
         lines += pre + ADVANCE_HDR + b + DISPATCH
-    # SLOT (aux = slot index): all six coefficients of the record that follows come from the per-state table
+    # SLOT (aux = slot index): all six coefficients of the record that follows come from the per-state table,
+    # whose base address for this tile's register sits in shared memory at %2
     lines.append("V4L%d:" % OP_SLOT)
-    lines += ["mul.wide.u32 sa, hax, 64;", "add.u64 sa, sa, %2;"] + ADVANCE_HDR
+    lines += ["ld.shared.u32 t, [%0+12];", "ld.shared.u64 sa, [%2];", "mul.wide.u32 sb, t, 64;", "add.u64 sa, sa, sb;"] + ADVANCE_HDR
     lines += ["ld.global.nc.v2.f64 {c0, c1}, [sa];", "ld.global.nc.v2.f64 {c2, c3}, [sa+16];",
               "ld.global.nc.v2.f64 {c4, c5}, [sa+32];"] + DISPATCH
     # CTRL (cm = context bits that must be set, aux = bytes to the record after the controlled gate): the
     # planner keeps such controls warp-uniform, so the whole warp either runs the next record or skips it
     lines.append("V4L%d:" % OP_CTRL)
-    lines += ["and.b32 t, %1, hcm;", "setp.eq.u32 pact, t, hcm;", "selp.u32 t, 64, hax, pact;", "add.u32 %0, %0, t;",
-              "ld.shared.v4.u32 {hop, hcm, htm, hax}, [%0];"] + LOAD_PAIR + DISPATCH
+    lines += ["ld.shared.v2.u32 {hcm, hax}, [%0+8];", "and.b32 t, %1, hcm;", "setp.eq.u32 pact, t, hcm;", "selp.u32 t, 64, hax, pact;",
+              "add.u32 %0, %0, t;", "ld.shared.v2.u32 {hop, htm}, [%0];"] + LOAD_PAIR + DISPATCH
     lines.append("V4L%d:" % OP_END)
     lines += addresses("store")
     lines.append("}")
