@@ -152,6 +152,20 @@ int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k, int32_t ba
 int32_t qm_sample(qm_state* st, uint64_t seed, int32_t nshots, int32_t batch_idx, uint64_t* out);
 int32_t qm_norm2(qm_state* st, int32_t batch_idx, double* out);
 
+/* ---- density matrices (the Matrix{ComplexF64} methods of QSim.jl) ----------------------------
+ * rho on q qubits is a register of 2q qubits holding vec(rho) in Julia's column-major Matrix memory:
+ * amplitude r + c 2^q = rho[r, c].  rho <- op rho op' (u2!  QSim.jl:67-79, controlled!  :209-232) is then
+ * qm_apply_u2(t0, U) + qm_apply_u2(q + t0, conj(U)) (same for qm_apply_controlled): the host shim issues
+ * both, the planner fuses them like any other gates.  density_matrix(q, m) = qm_create(2q, m (2^q + 1)).
+ * qm_dm_from_state  replaces statevector_to_density_matrix  QSim.jl:39-41  (rho[r,c] = s[r] conj(s[c]))
+ * qm_dm_diag        replaces mp(rho) = real.(diag(rho))      QSim.jl:295   (out: 2^q doubles, host)
+ * qm_dm_measure     replaces measure_z / measure_x / measure_y of rho  QSim.jl:332-365: diagonal of R rho R'
+ *                   summed by bit t0, entries <= threshold dropped; R == NULL is the Z basis
+ */
+int32_t qm_dm_from_state(qm_state* sv, qm_state* rho);
+int32_t qm_dm_diag(qm_state* rho, double* out_host);
+int32_t qm_dm_measure(qm_state* rho, int32_t t0, const double* R, double threshold, double out[2]);
+
 /* ---- sharded registers (one process per GPU; high-order qubits global) -----------------
  * qm_dist_unique_id  fills a 128-byte NCCL unique id (rank 0 calls it, the host broadcasts it)
  * qm_create_dist     rank `rank` of `world` (power of two) holds the amplitudes whose top

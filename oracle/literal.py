@@ -188,3 +188,90 @@ def entanglement_entropy(rho_AB, dim_A, dim_B):
     """QInfo.jl:178-182"""
     rho_AB = (rho_AB + rho_AB.conj().T) / 2
     return von_neumann_entropy(partial_trace(rho_AB, dim_A, dim_B, 2))
+
+
+# ---- the Matrix{ComplexF64} (density matrix) methods, literally: op * rho * op' --------------------
+
+def density_matrix(n, m):
+    """density_matrix(n, m), QSim.jl:43-46: s * s' of the basis state"""
+    s = statevector(n, m)
+    return np.outer(s, np.conj(s))
+
+
+def _op_1q(q, t, U):
+    """kron(id(r), kron(U, id(l))), QSim.jl:71-73"""
+    return np.kron(id_(q - t), np.kron(np.asarray(U, dtype=np.complex128), id_(t - 1)))
+
+
+def u2_dm(rho, t, U):
+    """u2!(rho, t, U), QSim.jl:67-79"""
+    q = int(round(np.log2(rho.shape[0])))
+    if not t <= q:
+        raise RuntimeError("Qubit index out of range")
+    op = _op_1q(q, t, U)
+    return op @ rho @ op.conj().T
+
+
+def controlled_dm(rho, c, t, V):
+    """controlled!(rho, c, t, V), QSim.jl:209-232 — the 4x4 block sits directly above `mid`, as in the vector method"""
+    q = int(round(np.log2(rho.shape[0])))
+    if not (c <= q and t <= q):
+        raise RuntimeError("Qubit index out of range")
+    if c == t:
+        raise RuntimeError("Control and target cannot be the same qubit")
+    a, b = min(c, t), max(c, t)
+    left, right = id_(q - b), id_(a - 1)
+    mid = id_(b - a - 1) if (b - a - 1) > 0 else np.ones((1, 1), dtype=np.complex128)
+    V = np.asarray(V, dtype=np.complex128)
+    P0 = np.array([[1, 0], [0, 0]], dtype=np.complex128)
+    P1 = np.array([[0, 0], [0, 1]], dtype=np.complex128)
+    if c < t:
+        U2 = np.kron(id_(1), P0) + np.kron(V, P1)
+    else:
+        U2 = np.kron(P0, id_(1)) + np.kron(P1, V)
+    op = np.kron(left, np.kron(U2, np.kron(mid, right)))
+    return op @ rho @ op.conj().T
+
+
+def swap_dm(rho, q1, q2):
+    """swap!(rho, q1, q2), QSim.jl:277-290"""
+    q = int(round(np.log2(rho.shape[0])))
+    if not (q1 <= q and q2 <= q):
+        raise RuntimeError("Qubit index out of range")
+    if q1 == q2:
+        return rho
+    rho = controlled_dm(rho, q1, q2, X)
+    rho = controlled_dm(rho, q2, q1, X)
+    return controlled_dm(rho, q1, q2, X)
+
+
+def mp_dm(rho):
+    """mp(rho) = real.(diag(rho)), QSim.jl:295"""
+    return np.real(np.diag(rho)).copy()
+
+
+def measure_z_dm(rho, t, threshold=1e-10):
+    """measure_z(rho, t), QSim.jl:332-352"""
+    q = int(round(np.log2(rho.shape[0])))
+    if not t <= q:
+        raise RuntimeError("Qubit index out of range")
+    probs = np.real(np.diag(rho))
+    p0 = p1 = 0.0
+    mask = 1 << (t - 1)
+    for i in range(len(probs)):
+        if probs[i] > threshold:
+            if (i & mask) == 0:
+                p0 += probs[i]
+            else:
+                p1 += probs[i]
+    return (p0, p1)
+
+
+def measure_x_dm(rho, t, threshold=1e-10):
+    """measure_x(rho, t), QSim.jl:354-358"""
+    return measure_z_dm(u2_dm(rho.copy(), t, H), t, threshold)
+
+
+def measure_y_dm(rho, t, threshold=1e-10):
+    """measure_y(rho, t), QSim.jl:360-364"""
+    return measure_z_dm(u2_dm(rho.copy(), t, rx_gate(np.pi / 2)), t, threshold)

@@ -8,4 +8,4 @@ the module name `quromorphic_jl_b200`.
 """
 from . import _lib, circuits, dist, qinfo, qsim, reservoir  # noqa: F401
 from ._lib import QMError  # noqa: F401
-from .qsim import B200State, QSimError  # noqa: F401
+from .qsim import B200Density, B200State, QSimError  # noqa: F401

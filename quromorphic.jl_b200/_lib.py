@@ -63,6 +63,9 @@ SIGNATURES = {
     "qm_reduced_density": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp]),
     "qm_sample": (C.c_int32, [_vp, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
     "qm_norm2": (C.c_int32, [_vp, C.c_int32, _dp]),
+    "qm_dm_from_state": (C.c_int32, [_vp, _vp]),
+    "qm_dm_diag": (C.c_int32, [_vp, _dp]),
+    "qm_dm_measure": (C.c_int32, [_vp, C.c_int32, _dp, C.c_double, _dp]),
     "qm_dist_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),
     "qm_create_dist": (C.c_int32, [C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_uint8), C.POINTER(_vp)]),

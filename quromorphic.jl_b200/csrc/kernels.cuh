@@ -7,6 +7,7 @@
 //   k_zpartial/final  K5: all-qubit thresholded marginals in one read (measure_z, QSim.jl:297-318)
 //   k_measure_rot     K5: single-qubit marginal after a basis rotation (measure_x/y, QSim.jl:320-330)
 //   k_probs           mp = abs2.(s), QSim.jl:293
+//   k_dm_*            density-matrix methods on vec(rho): outer product, diagonal, marginals (QSim.jl:39-41, :295, :332-365)
 //   k_reduced_*       K6: psi -> reduced density matrix (QSim.jl:39-41 + QInfo.jl:381-405)
 //   k_leafsum/k_sample K8: inverse-CDF sampler (defined in oracle/qsim_oracle.c; no reference counterpart)
 //
@@ -364,6 +365,64 @@ k_pair_final(const double* __restrict__ partial, int nblocks, double* __restrict
         __syncthreads();
     }
     if (threadIdx.x == 0) { out2[0] = sh0[0]; out2[1] = sh1[0]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Density-matrix methods by vectorisation: rho on q qubits lives in the engine as the
+// 2q-qubit vector vec(rho), amplitude r + c 2^q = rho[r, c] (Julia's column-major Matrix memory), so
+// rho <- op rho op' (QSim.jl:67-79, :209-232) is `op` on the row bits and conj(op) on the column bits —
+// the same fused passes.  Only these three small kernels are specific to it.
+//   k_dm_outer   statevector_to_density_matrix, QSim.jl:39-41: rho[r, c] = s[r] conj(s[c])
+//   k_dm_diag    mp(rho) = real.(diag(rho)), QSim.jl:295
+//   k_dm_measure measure_z / measure_x / measure_y of rho (QSim.jl:332-365): diagonal of R rho R' summed by
+//                bit t, entries <= threshold dropped; the 2x2 block of rho in (row bit t, column bit t) is
+//                rotated in registers, no copy of rho is made
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_dm_outer(const double2* __restrict__ sv, int q, double2* __restrict__ rho) {
+    const uint64_t n = 1ull << (2 * q), rm = (1ull << q) - 1ull;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double2 a = sv[i & rm], b = sv[i >> q];
+        rho[i] = make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -(a.x * b.y)));       // a * conj(b)
+    }
+}
+__global__ void __launch_bounds__(256)
+k_dm_diag(const double2* __restrict__ rho, int q, double* __restrict__ out) {
+    const uint64_t d = 1ull << q;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d; i += stride) out[i] = rho[i * (d + 1ull)].x;
+}
+__global__ void __launch_bounds__(256)
+k_dm_measure(const double2* __restrict__ rho, int q, int tbit, Mat2 R, int identity, double thr, double* __restrict__ partial) {
+    const double2 u11 = make_double2(R.v[0], R.v[1]), u21 = make_double2(R.v[2], R.v[3]);
+    const double2 u12 = make_double2(R.v[4], R.v[5]), u22 = make_double2(R.v[6], R.v[7]);
+    const uint64_t d = 1ull << q, tm = 1ull << tbit, npairs = d >> 1;
+    double p0 = 0.0, p1 = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < npairs; j += stride) {
+        const uint64_t i0 = insert0(j, tbit), i1 = i0 | tm;
+        double q0, q1;
+        if (identity) { q0 = rho[i0 * (d + 1ull)].x; q1 = rho[i1 * (d + 1ull)].x; }
+        else {
+            const double2 b00 = rho[i0 + i0 * d], b10 = rho[i1 + i0 * d], b01 = rho[i0 + i1 * d], b11 = rho[i1 + i1 * d];
+            // (R B R')[s, s] = sum_ab R[s,a] B[a,b] conj(R[s,b]);  w_s,b = sum_a R[s,a] B[a,b]
+            const double2 w00 = cfma(u12, b10, cmul(u11, b00)), w01 = cfma(u12, b11, cmul(u11, b01));
+            const double2 w10 = cfma(u22, b10, cmul(u21, b00)), w11 = cfma(u22, b11, cmul(u21, b01));
+            q0 = (w00.x * u11.x + w00.y * u11.y) + (w01.x * u12.x + w01.y * u12.y);          // Re(w conj(u))
+            q1 = (w10.x * u21.x + w10.y * u21.y) + (w11.x * u22.x + w11.y * u22.y);
+        }
+        p0 += q0 > thr ? q0 : 0.0;
+        p1 += q1 > thr ? q1 : 0.0;
+    }
+    __shared__ double sh0[256], sh1[256];
+    sh0[threadIdx.x] = p0; sh1[threadIdx.x] = p1;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) { sh0[threadIdx.x] += sh0[threadIdx.x + w]; sh1[threadIdx.x] += sh1[threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sh0[0]; partial[2 * blockIdx.x + 1] = sh1[0]; }
 }
 
 __global__ void __launch_bounds__(256)

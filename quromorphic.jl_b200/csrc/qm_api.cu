@@ -847,6 +847,73 @@ extern "C" int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k,
     return QM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// density matrices as 2q-qubit registers (vec(rho), column-major): see kernels.cuh k_dm_*
+// ---------------------------------------------------------------------------------------------
+static int dm_check(qm_state* st, int* q) {
+    if (!st) return set_err(QM_ERR_ARG, "null state");
+    if (st->dist || st->batch != 1) return set_err(QM_ERR_STATE, "density-matrix calls need a single unsharded register");
+    if (st->n & 1) return set_err(QM_ERR_ARG, "a density matrix on q qubits is a register of 2q qubits (got %d)", st->n);
+    *q = st->n / 2;
+    return QM_OK;
+}
+
+extern "C" int32_t qm_dm_from_state(qm_state* sv, qm_state* rho) {
+    int q = 0;
+    QM_TRY(dm_check(rho, &q));
+    if (!sv || sv->dist || sv->batch != 1 || sv->n != q || sv->device != rho->device)
+        return set_err(QM_ERR_ARG, "source must be an unsharded %d-qubit register on the same device", q);
+    QM_TRY(flush(sv)); QM_TRY(flush(rho));
+    CU(cudaSetDevice(rho->device));
+    CU(cudaStreamSynchronize(sv->stream));
+    for (int i = 0; i < rho->n; ++i) rho->perm[i] = i;
+    k_dm_outer<<<grid_for(total_amps(rho), 256, rho->sms, 16), 256, 0, rho->stream>>>(sv->amp, q, rho->amp);
+    CU(cudaGetLastError());
+    rho->ctr.launches++; rho->ctr.bytes_hbm += 16ull * total_amps(rho);
+    return QM_OK;
+}
+
+extern "C" int32_t qm_dm_diag(qm_state* rho, double* out_host) {
+    int q = 0;
+    QM_TRY(dm_check(rho, &q));
+    if (!out_host) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(flush(rho));
+    CU(cudaSetDevice(rho->device));
+    const uint64_t d = 1ull << q;
+    QM_TRY(ENSURE_DEV(rho, d_scratch, (size_t)d * 8));
+    k_dm_diag<<<grid_for(d, 256, rho->sms, 16), 256, 0, rho->stream>>>(rho->amp, q, rho->d_scratch);
+    CU(cudaGetLastError());
+    rho->ctr.launches++; rho->ctr.bytes_hbm += 16ull * d;
+    CU(cudaMemcpyAsync(out_host, rho->d_scratch, (size_t)d * 8, cudaMemcpyDeviceToHost, rho->stream));
+    rho->ctr.bytes_d2h += d * 8;
+    return qm_sync(rho);
+}
+
+extern "C" int32_t qm_dm_measure(qm_state* rho, int32_t t0, const double* R, double threshold, double out[2]) {
+    int q = 0;
+    QM_TRY(dm_check(rho, &q));
+    if (!out) return set_err(QM_ERR_ARG, "null argument");
+    if (t0 < 0 || t0 >= q) return set_err(QM_ERR_ARG, "Qubit index out of range (target bit %d, q = %d)", t0, q);
+    QM_TRY(flush(rho));
+    CU(cudaSetDevice(rho->device));
+    Mat2 U; const int identity = (R == nullptr);
+    if (R) memcpy(U.v, R, sizeof(U.v)); else memset(&U, 0, sizeof(U));
+    const uint64_t npairs = (1ull << q) >> 1;
+    int blocks = grid_for(npairs, 256, rho->sms, 8); if (blocks > kMeasBlocks) blocks = kMeasBlocks;
+    QM_TRY(ENSURE_DEV(rho, d_scratch, (size_t)(2 * kMeasBlocks + 2) * 8));
+    QM_TRY(ENSURE_PIN(rho, h_scratch, 64));
+    k_dm_measure<<<blocks, 256, 0, rho->stream>>>(rho->amp, q, t0, U, identity, threshold, rho->d_scratch);
+    CU(cudaGetLastError());
+    k_pair_final<<<1, 256, 0, rho->stream>>>(rho->d_scratch, blocks, rho->d_scratch + 2 * kMeasBlocks);
+    CU(cudaGetLastError());
+    rho->ctr.launches += 2; rho->ctr.bytes_hbm += 64ull << q;
+    CU(cudaMemcpyAsync(rho->h_scratch, rho->d_scratch + 2 * kMeasBlocks, 16, cudaMemcpyDeviceToHost, rho->stream));
+    rho->ctr.bytes_d2h += 16;
+    QM_TRY(qm_sync(rho));
+    out[0] = rho->h_scratch[0]; out[1] = rho->h_scratch[1];
+    return QM_OK;
+}
+
 extern "C" int32_t qm_sample(qm_state* st, uint64_t seed, int32_t nshots, int32_t batch_idx, uint64_t* out) {
     if (!st || (!out && nshots > 0) || nshots < 0) return set_err(QM_ERR_ARG, "null argument");
     if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");

@@ -181,4 +181,77 @@ function sample(s::B200State, seed::Integer, nshots::Int; batch_idx::Int = 0)
     out
 end
 
+# ---- density matrices: the Matrix{ComplexF64} methods (QSim.jl:67-79, :209-232, :277-290, :295, :332-365) ----
+# rho on q qubits is a 2q-qubit register holding vec(rho) (column-major, as Julia stores the Matrix):
+# rho <- op rho op' is `op` on the row bits and conj(op) on the column bits.
+struct B200Density
+    vec::B200State          # the 2q-qubit register (mode = :corrected: the index map is applied here)
+    q::Int
+    mode::Symbol
+end
+density_matrix(q::Int, m::Int; mode = :reference, kw...) =
+    B200Density(B200State(2q, m * ((1 << q) + 1); mode = :corrected, kw...), q, mode)      # QSim.jl:43-46
+function statevector_to_density_matrix(s::B200State)                                          # QSim.jl:39-41
+    rho = density_matrix(s.n, 0; mode = s.mode)
+    check(ccall((:qm_dm_from_state, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), s.handle, rho.vec.handle))
+    rho
+end
+nb(rho::B200Density) = rho.q
+function u2!(rho::B200Density, t::Int, U::Matrix{ComplexF64})                                 # QSim.jl:67-79
+    1 <= t <= rho.q || error("Qubit index out of range")
+    Uc = conj(U)
+    check(ccall((:qm_apply_u2, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{ComplexF64}), rho.vec.handle, t - 1, U))
+    check(ccall((:qm_apply_u2, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{ComplexF64}), rho.vec.handle, rho.q + t - 1, Uc))
+    rho
+end
+function controlled!(rho::B200Density, c::Int, t::Int, V::Matrix{ComplexF64})                 # QSim.jl:209-232
+    (c <= rho.q && t <= rho.q && c >= 1 && t >= 1) || error("Qubit index out of range")
+    c == t && error("Control and target cannot be the same qubit")
+    ce, te = rho.mode === :reference ? effective_ct(c, t) : (c, t)
+    Vc = conj(V)
+    check(ccall((:qm_apply_controlled, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{ComplexF64}), rho.vec.handle, ce - 1, te - 1, V))
+    check(ccall((:qm_apply_controlled, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{ComplexF64}), rho.vec.handle, rho.q + ce - 1, rho.q + te - 1, Vc))
+    rho
+end
+for (f, U) in ((:h!, :H), (:x!, :X), (:y!, :Y), (:z!, :Z))
+    @eval $f(rho::B200Density, t::Int) = u2!(rho, t, $U)
+end
+rx!(rho::B200Density, t::Int, theta::Real) = u2!(rho, t, rx_gate(theta))
+ry!(rho::B200Density, t::Int, theta::Real) = u2!(rho, t, ry_gate(theta))
+rz!(rho::B200Density, t::Int, theta::Real) = u2!(rho, t, rz_gate(theta))
+cnot!(rho::B200Density, c::Int, t::Int) = controlled!(rho, c, t, X)
+crx!(rho::B200Density, c::Int, t::Int, theta::Real) = controlled!(rho, c, t, rx_gate(theta))
+cry!(rho::B200Density, c::Int, t::Int, theta::Real) = controlled!(rho, c, t, ry_gate(theta))
+crz!(rho::B200Density, c::Int, t::Int, theta::Real) = controlled!(rho, c, t, rz_gate(theta))
+function swap!(rho::B200Density, q1::Int, q2::Int)                                            # QSim.jl:277-290
+    (q1 <= rho.q && q2 <= rho.q && q1 >= 1 && q2 >= 1) || error("Qubit index out of range")
+    q1 == q2 && return rho
+    cnot!(rho, q1, q2); cnot!(rho, q2, q1); cnot!(rho, q1, q2)
+    rho
+end
+function mp(rho::B200Density)                                                                 # QSim.jl:295
+    p = Vector{Float64}(undef, 1 << rho.q)
+    check(ccall((:qm_dm_diag, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), rho.vec.handle, p))
+    p
+end
+function _measure(rho::B200Density, t::Int, R::Union{Nothing,Matrix{ComplexF64}})
+    1 <= t <= rho.q || error("Qubit index out of range")
+    out = Vector{Float64}(undef, 2)
+    Rp = R === nothing ? Ptr{ComplexF64}(C_NULL) : pointer(R)
+    GC.@preserve R check(ccall((:qm_dm_measure, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{ComplexF64}, Float64, Ptr{Float64}),
+                               rho.vec.handle, t - 1, Rp, rho.vec.threshold, out))
+    (out[1], out[2])
+end
+measure_z(rho::B200Density, t::Int) = _measure(rho, t, nothing)          # QSim.jl:332-352
+measure_x(rho::B200Density, t::Int) = _measure(rho, t, H)                # QSim.jl:354-358
+measure_y(rho::B200Density, t::Int) = _measure(rho, t, rx_gate(π / 2))   # QSim.jl:360-364
+Base.Matrix{ComplexF64}(rho::B200Density) = reshape(Vector{ComplexF64}(rho.vec), 1 << rho.q, 1 << rho.q)
+function prstate(rho::B200Density)                                       # QSim.jl:375-383
+    p = mp(rho)
+    for i in 0:(length(p) - 1)
+        abs(p[i + 1]) > 1e-10 && println("|", lpad(string(i, base = 2), rho.q, '0'), "⟩ : ", p[i + 1])
+    end
+    nothing
+end
+
 end # module

@@ -199,6 +199,62 @@ class B200State:
             pass
 
 
+class B200Density:
+    """Device-resident density matrix: the drop-in for the Matrix{ComplexF64} methods of QSim.jl
+    (u2! :67-79, controlled! :209-232, swap! :277-290, mp :295, measure_z/x/y :332-365, prstate :375-383).
+
+    rho on q qubits lives in the engine as the 2q-qubit register vec(rho) in Julia's column-major Matrix
+    memory (amplitude r + c 2^q = rho[r, c]); `rho <- op rho op'` is `op` on the row bits and conj(op) on
+    the column bits, fused by the planner like any other gates.  q <= 16 on one B200 (4^16 x 16 B = 64 GiB).
+    """
+
+    def __init__(self, q, m=0, device=0, mode="reference", threshold=1e-10):
+        if m < 0 or m >= (1 << q):
+            raise QSimError("BoundsError: basis index %d out of range for %d qubits" % (m, q))
+        self.q, self.mode, self.threshold = int(q), mode, threshold
+        self.vec = B200State(2 * q, m * ((1 << q) + 1), device=device, mode="corrected", threshold=threshold)
+
+    @classmethod
+    def from_statevector(cls, s):
+        """statevector_to_density_matrix(s) = s * s', QSim.jl:39-41, formed on the device"""
+        rho = cls(s.n, 0, device=s.device, mode=s.mode, threshold=s.threshold)
+        L.check(L.lib().qm_dm_from_state(s._h, rho.vec._h))
+        return rho
+
+    @classmethod
+    def from_numpy(cls, M, **kw):
+        M = np.asarray(M, dtype=np.complex128)
+        q = int(round(np.log2(M.shape[0])))
+        if M.shape != (1 << q, 1 << q):
+            raise QSimError("density matrix must be 2^q x 2^q")
+        rho = cls(q, 0, **kw)
+        rho.vec.upload(np.ascontiguousarray(M.T).reshape(-1))       # column-major
+        return rho
+
+    def to_numpy(self):
+        d = 1 << self.q
+        return self.vec.to_numpy().reshape(d, d).T.copy()
+
+    def set_option(self, key, value):
+        self.vec.set_option(key, value)
+
+    def counters(self):
+        return self.vec.counters()
+
+    def close(self):
+        self.vec.close()
+
+
+def density_matrix(n, m, **kw):
+    """density_matrix(n, m) = |m><m| on n qubits (QSim.jl:43-46)"""
+    return B200Density(n, m, **kw)
+
+
+def statevector_to_density_matrix(s):
+    """statevector_to_density_matrix(s), QSim.jl:39-41"""
+    return B200Density.from_statevector(s)
+
+
 # ---- the reference's functions --------------------------------------------------------------------
 
 def statevector(n, m, **kw):
@@ -207,8 +263,8 @@ def statevector(n, m, **kw):
 
 
 def nb(s):
-    """nb(s), QSim.jl:48"""
-    return s.n
+    """nb(s), QSim.jl:48 (Matrix: round(Int, log2(size(rho, 1))))"""
+    return s.q if isinstance(s, B200Density) else s.n
 
 
 def _range1(s, t):
@@ -219,7 +275,15 @@ def _range1(s, t):
 
 
 def u2(s, t, U):
-    """u2!(s, t, U), QSim.jl:52-63"""
+    """u2!(s, t, U), QSim.jl:52-63;  u2!(rho, t, U) = op rho op', QSim.jl:67-79"""
+    if isinstance(s, B200Density):
+        if not (1 <= t <= s.q):
+            raise QSimError("Qubit index out of range")
+        U = np.asarray(U, dtype=np.complex128)
+        m, mc = L.mat8(U), L.mat8(np.conj(U))
+        L.check(L.lib().qm_apply_u2(s.vec._h, t - 1, L.dptr(m)))                 # op on the row index
+        L.check(L.lib().qm_apply_u2(s.vec._h, s.q + t - 1, L.dptr(mc)))          # conj(op) on the column index
+        return s
     _range1(s, t)
     m = L.mat8(U)
     L.check(L.lib().qm_apply_u2(s._h, t - 1, L.dptr(m)))
@@ -236,13 +300,20 @@ def rz(s, t, theta): return u2(s, t, rz_gate(theta))  # QSim.jl:166-168
 
 
 def controlled(s, c, t, V):
-    """controlled!(s, c, t, V), QSim.jl:175-203.  Checks in the reference's order: range, then c == t."""
-    if not (c <= s.n and t <= s.n) or c < 1 or t < 1:
+    """controlled!(s, c, t, V), QSim.jl:175-203 (Matrix: :209-232, the same 4x4 block placement).  Checks in
+    the reference's order: range, then c == t."""
+    n = nb(s)
+    if not (c <= n and t <= n) or c < 1 or t < 1:
         raise QSimError("Qubit index out of range")
     if c == t:
         raise QSimError("Control and target cannot be the same qubit")
     ce, te = effective_control_target(c, t) if s.mode == "reference" else (c, t)
     m = L.mat8(V)
+    if isinstance(s, B200Density):
+        mc = L.mat8(np.conj(np.asarray(V, dtype=np.complex128)))
+        L.check(L.lib().qm_apply_controlled(s.vec._h, ce - 1, te - 1, L.dptr(m)))
+        L.check(L.lib().qm_apply_controlled(s.vec._h, s.q + ce - 1, s.q + te - 1, L.dptr(mc)))
+        return s
     L.check(L.lib().qm_apply_controlled(s._h, ce - 1, te - 1, L.dptr(m)))
     return s
 
@@ -255,8 +326,9 @@ def crz(s, c, t, theta): return controlled(s, c, t, rz_gate(theta))  # QSim.jl:2
 
 def swap(s, q1, q2):
     """swap!(s, q1, q2), QSim.jl:262-275: range check, no-op when equal, else cnot!(q1,q2); cnot!(q2,q1);
-    cnot!(q1,q2) — each through controlled!, so the reference mode inherits its index map."""
-    if not (q1 <= s.n and q2 <= s.n) or q1 < 1 or q2 < 1:
+    cnot!(q1,q2) — each through controlled!, so the reference mode inherits its index map (Matrix: :277-290)."""
+    n = nb(s)
+    if not (q1 <= n and q2 <= n) or q1 < 1 or q2 < 1:
         raise QSimError("Qubit index out of range")
     if q1 == q2:
         return s
@@ -267,17 +339,24 @@ def swap(s, q1, q2):
 
 
 def mp(s, batch_idx=0):
-    """mp(s) = abs2.(s), QSim.jl:293"""
+    """mp(s) = abs2.(s), QSim.jl:293;  mp(rho) = real.(diag(rho)), QSim.jl:295"""
+    if isinstance(s, B200Density):
+        out = np.empty(1 << s.q, dtype=np.float64)
+        L.check(L.lib().qm_dm_diag(s.vec._h, L.dptr(out)))
+        return out
     out = np.empty(1 << s.n, dtype=np.float64)
     L.check(L.lib().qm_probs(s._h, L.dptr(out), batch_idx))
     return out
 
 
 def _measure(s, t, R, batch_idx):
-    if not (1 <= t <= s.n):
+    if not (1 <= t <= nb(s)):
         raise QSimError("Qubit index out of range")
     out = np.empty(2, dtype=np.float64)
     Rp = L.dptr(L.mat8(R)) if R is not None else None
+    if isinstance(s, B200Density):       # QSim.jl:332-365: diagonal of R rho R' by bit t, entries <= 1e-10 dropped
+        L.check(L.lib().qm_dm_measure(s.vec._h, t - 1, Rp, s.threshold, L.dptr(out)))
+        return (float(out[0]), float(out[1]))
     L.check(L.lib().qm_measure_with(s._h, t - 1, Rp, s.threshold, batch_idx, L.dptr(out)))
     return (float(out[0]), float(out[1]))
 
@@ -299,7 +378,14 @@ def measure_y(s, t, batch_idx=0):
 
 
 def prstate(s, batch_idx=0, file=None):
-    """prstate(s), QSim.jl:367-373: '|bits⟩: amplitude' for abs(a) > 1e-10, MSB-first bit string."""
+    """prstate(s), QSim.jl:367-373: '|bits⟩: amplitude' for abs(a) > 1e-10, MSB-first bit string;
+    prstate(rho), QSim.jl:375-383: '|bits⟩ : probability' from mp(rho)."""
+    if isinstance(s, B200Density):
+        p = mp(s)
+        for i in range(len(p)):
+            if abs(p[i]) > 1e-10:
+                print("|" + format(i, "b").rjust(s.q, "0") + "⟩ : " + repr(float(p[i])), file=file)
+        return None
     v = s.to_numpy(batch_idx)
     for i in range(len(v)):
         a = v[i]

@@ -146,3 +146,32 @@ def test_circuit_runner_equals_call_sequence():
     O.h(ref, 3); O.cnot(ref, 3, 6, quirk=False); O.rx(ref, 8, 0.3); O.swap(ref, 2, 7, quirk=False)
     O.crz(ref, 7, 1, 1.1, quirk=False)
     assert np.array_equal(got, ref)
+
+
+def test_literal_density_matrix_methods_agree_with_vector_methods():
+    """the literal Matrix methods (op rho op', QSim.jl:67-79, :209-232) on a pure state equal the outer product of
+    the literal vector methods' result — for every gate kind and every ordered (c, t), non-adjacent pairs included"""
+    from oracle import literal as LIT
+    q = 4
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=1 << q) + 1j * rng.normal(size=1 << q)
+    v /= np.linalg.norm(v)
+    for t in range(1, q + 1):
+        for U in (LIT.H, LIT.X, LIT.Y, LIT.Z, LIT.rx_gate(0.7), LIT.ry_gate(-1.1), LIT.rz_gate(2.3)):
+            w = LIT.u2(v.copy(), t, U)
+            assert np.max(np.abs(LIT.u2_dm(np.outer(v, v.conj()), t, U) - np.outer(w, w.conj()))) < 1e-14
+    for c in range(1, q + 1):
+        for t in range(1, q + 1):
+            if c == t:
+                continue
+            for V in (LIT.X, LIT.rz_gate(0.9), LIT.ry_gate(0.4)):
+                w = LIT.controlled(v.copy(), c, t, V)
+                assert np.max(np.abs(LIT.controlled_dm(np.outer(v, v.conj()), c, t, V) - np.outer(w, w.conj()))) < 1e-14
+            w = LIT.swap(v.copy(), c, t)
+            assert np.max(np.abs(LIT.swap_dm(np.outer(v, v.conj()), c, t) - np.outer(w, w.conj()))) < 1e-14
+    rho = np.outer(v, v.conj())
+    for t in range(1, q + 1):
+        assert LIT.measure_z_dm(rho, t) == pytest.approx(LIT.measure_z(v, t), abs=1e-14)
+        assert LIT.measure_x_dm(rho, t) == pytest.approx(LIT.measure_x(v, t), abs=1e-14)
+        assert LIT.measure_y_dm(rho, t) == pytest.approx(LIT.measure_y(v, t), abs=1e-14)
+    assert np.max(np.abs(LIT.mp_dm(rho) - LIT.mp(v))) < 1e-15
