@@ -17,7 +17,7 @@ SO_PATH = os.environ.get("QM_B200_LIB") or os.path.join(HERE, "libqm_b200.so")
 QM_OK, QM_ERR_ARG, QM_ERR_CUDA, QM_ERR_NOMEM, QM_ERR_NO_DEVICE, QM_ERR_STATE, QM_ERR_COMM = range(7)
 GATE_U2, GATE_CU2, GATE_SWAP, GATE_U2_SLOT = 0, 1, 2, 3
 BASIS_Z, BASIS_X, BASIS_Y = 0, 1, 2
-OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_REMAP, OPT_PIPELINE, OPT_MAX_COST = range(7)
+OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_REMAP, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES = range(8)
 
 GATE_DTYPE = np.dtype([("kind", np.int32), ("q0", np.int32), ("q1", np.int32), ("flags", np.int32),
                        ("m", np.float64, (8,))])
@@ -78,6 +78,7 @@ SIGNATURES = {
     "qm_plan_gates": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _vp,
                                   C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "qm_plan_emulate": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _dp, C.POINTER(C.c_int32)]),
+    "qm_pass_times": (C.c_int32, [_vp, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
     "qm_sync": (C.c_int32, [_vp]),
     "qm_last_error": (C.c_int32, [C.c_char_p, C.c_int32]),
     "qm_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),

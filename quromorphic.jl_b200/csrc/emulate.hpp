@@ -46,8 +46,11 @@ inline bool emulate_v4(const V4Program& prog, const PlanPass& P, EmuAmp* amp, in
     const int m = P.m, NB = kV4BlockBits, NA = 1 << NB;
     const int nthreads = 1 << (m - NB);
     std::vector<int> tbit(m);                       // tile-local bit -> physical bit
-    for (int b = 0; b < P.L; ++b) tbit[b] = b;
-    for (size_t j = 0; j < P.hb.size(); ++j) tbit[P.L + j] = P.hb[j];
+    if (!P.tl.empty()) { for (int b = 0; b < m; ++b) tbit[b] = P.tl[b]; }
+    else {
+        for (int b = 0; b < P.L; ++b) tbit[b] = b;
+        for (size_t j = 0; j < P.hb.size(); ++j) tbit[P.L + j] = P.hb[j];
+    }
     uint64_t tilemask = 0; for (int b = 0; b < m; ++b) tilemask |= 1ull << tbit[b];
     const uint64_t ntiles = 1ull << (nl - m);
     std::vector<EmuAmp> tile(1u << m);

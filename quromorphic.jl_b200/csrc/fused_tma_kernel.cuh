@@ -82,7 +82,7 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     unsigned char* stage_base = smem;
     unsigned char* tabs = smem + (size_t)STAGES * TILE_BYTES;
     unsigned char* recs = tabs + kV4TabBytes;
-    uint64_t* slot_bases = reinterpret_cast<uint64_t*>(recs + sizeof(V4Rec) * kV4MaxRecs);     // one per team
+    uint64_t* slot_bases = reinterpret_cast<uint64_t*>(recs + sizeof(V4Rec) * kV4MaxRecs);     // two per team (tile parity)
     uint64_t* full = slot_bases + 8;
     uint64_t* computed = full + 2 * STAGES;
     // full[] holds TWO barriers per stage, used alternately (use k = i / STAGES of a stage takes barrier
@@ -130,6 +130,9 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
         return (breg << lp.reg_bits) + base;      // amplitude index of the tile's first element in the whole array
     };
 
+    // the tile's base row goes into TMA coordinate lp.rowdim, the other coordinates are 0
+#define TMA_COORDS(b) const int tr_ = (int)((b) >> 3), tc1 = lp.rowdim == 1 ? tr_ : 0, tc2 = lp.rowdim == 2 ? tr_ : 0, \
+                      tc3 = lp.rowdim == 3 ? tr_ : 0, tc4 = lp.rowdim == 4 ? tr_ : 0
     if (tid >= NCOMP) {
         // ===================== producer warpgroup: one elected lane drives TMA =====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
@@ -139,14 +142,15 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
             for (uint64_t i = 0; i < pro; ++i) {
                 const uint64_t base = tile_base(first + i * step, gb, br);
                 mbar_arrive_expect_tx(&full[i], TILE_BYTES);
-                tma_load_5d(stage_base + i * TILE_BYTES, &tmap, &full[i], 0, (int)(base >> 3), 0, 0, 0);
+                TMA_COORDS(base);
+                tma_load_5d(stage_base + i * TILE_BYTES, &tmap, &full[i], 0, tc1, tc2, tc3, tc4);
             }
             for (uint64_t i = 0; i < my_tiles; ++i) {
                 const int s = (int)(i % STAGES);
                 const uint32_t ph = (uint32_t)((i / STAGES) & 1);
                 mbar_wait_sleep(&computed[s], ph);
                 const uint64_t base = tile_base(first + i * step, gb, br);
-                tma_store_5d(&tmap, stage_base + (size_t)s * TILE_BYTES, 0, (int)(base >> 3), 0, 0, 0);
+                { TMA_COORDS(base); tma_store_5d(&tmap, stage_base + (size_t)s * TILE_BYTES, 0, tc1, tc2, tc3, tc4); }
                 tma_commit();
                 const uint64_t nxt = i + STAGES;
                 if (nxt < my_tiles) {
@@ -154,7 +158,8 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
                     const uint64_t nbase = tile_base(first + nxt * step, gb, br);
                     uint64_t* fb = &full[s + STAGES * (int)((nxt / STAGES) & 1)];
                     mbar_arrive_expect_tx(fb, TILE_BYTES);
-                    tma_load_5d(stage_base + (size_t)s * TILE_BYTES, &tmap, fb, 0, (int)(nbase >> 3), 0, 0, 0);
+                    TMA_COORDS(nbase);
+                    tma_load_5d(stage_base + (size_t)s * TILE_BYTES, &tmap, fb, 0, tc1, tc2, tc3, tc4);
                 }
             }
             tma_wait_all0();
@@ -170,7 +175,7 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     const uint32_t ctx_const = P.ctx_const | kV4CtxAlways;
     const uint64_t opk0 = P.outer_pack[0], opk1 = P.outer_pack[1];
     const uint32_t stage_s = smem_u32(stage_base);
-    const uint32_t slot_s = smem_u32(slot_bases) + 8u * team;
+    uint32_t slot_s = smem_u32(slot_bases) + 16u * team;
     const uint32_t lane_s = smem_u32(tabs) + 2u * lane, warp_s = smem_u32(tabs) + 2u * (kV4MaxGroups * 32 + warp);
     int s = team % STAGES; uint32_t k = 0;        // stage and use count of the stage (tile i: s = i % STAGES, k = i / STAGES)
 #pragma unroll 1
@@ -188,7 +193,13 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
                 if (j == 9) pk = opk1;
             }
         }
-        if (slots && ttid == 0) slot_bases[team] = (uint64_t)(slots + (size_t)breg * lp.nslots * 8);
+        // per-state coefficient base of this tile's register, double-buffered by tile parity: the first thread of
+        // the team may already be here while slower warps still read the previous tile's entry
+        slot_s ^= 8u;
+        if (slots && ttid == 0) {
+            const uint64_t sb = (uint64_t)(slots + (size_t)breg * lp.nslots * 8);
+            asm volatile("st.shared.u64 [%0], %1;" ::"r"(slot_s), "l"(sb) : "memory");
+        }
         const uint32_t tile_s = stage_s + (uint32_t)s * TILE_BYTES;
         mbar_wait(&full[s + STAGES * (int)(k & 1u)], (k >> 1) & 1u);
         if (slots) bar_sync_named(1 + team, TEAM);       // the team sees its slot base

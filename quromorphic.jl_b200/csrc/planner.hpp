@@ -85,7 +85,13 @@ struct PlanGroup {
 };
 struct PlanPass {
     int m = 0, L = 0;
-    std::vector<int> hb;
+    std::vector<int> hb;     // the tile's index bits above the L low ones, ascending
+    // TMA kernel only (empty otherwise): the order of the tile's bits in SHARED MEMORY.  tl[p] = index bit at
+    // tile-local position p; positions 0-2 are always bits 0-2 (one 128-byte row), then come the segments
+    // segs[] = (first bit, length) in the order chosen by choose_tile_layout().  Without it tile-local position
+    // p is bit p for p < L and hb[p - L] above.
+    std::vector<int> tl;
+    std::vector<std::pair<int, int>> segs;
     std::vector<PlanGroup> groups;
     int ngates = 0;
     double cost = 0.0;   // estimated DFMA-equivalents per amplitude
@@ -109,6 +115,7 @@ struct PlanOptions {
     int max_groups = 1 << 30;
     int max_outer = 64;  // distinct bits outside the tile a pass may use as controls / diagonal targets
     int block_bits = kBlockBits;     // register-block bits of a group (3: general kernel, 4: TMA kernel)
+    double group_cost = 0.0;         // budget units one register-block group costs on top of its gates (TMA kernel: 38)
     bool warp_uniform_ctrl = false;  // controls inside the tile must be block bits or one of the (m - block_bits - 5) warp-index bits
 };
 
@@ -287,7 +294,12 @@ struct Planner {
             }
             if (runs > opt.max_runs) return;
             uint64_t mask = low; for (int b : hb) mask |= 1ull << b;
-            int c = count_with(mask);
+            int c;
+            if (opt.group_cost > 0) {       // what the pass built on this tile would really take
+                PlanPass tmp; std::vector<int> tk;
+                build_pass(m, L, hb, tmp, tk);
+                c = (int)tk.size();
+            } else c = count_with(mask);
             if (c > best) { best = c; hb_best = hb; }
         };
         // (1) greedy: the first nh distinct non-diagonal high local targets in dependency order
@@ -341,16 +353,33 @@ struct Planner {
         }
         choose_tile(m, L, hb, best);
         if (best <= 0) return false;
+        std::vector<int> taken;
+        build_pass(m, L, hb, P, taken);
+        for (int i : taken) done[i] = 1;
+        return !taken.empty();
+    }
+
+    // Build the pass for a given tile: pull gates, form register-block groups, keep the leading groups that fit
+    // the budget.  `taken` receives the indices (into `gates`) of the gates of the pass; nothing is marked done.
+    //
+    // Budget (opt.max_cost) = sum of gate costs + opt.group_cost per group.  Measured on B200 at 30 qubits
+    // (tools/pass_model.py): a pass costs about 1.2 ms + 1.9 ms per group + 0.05 ms per cost unit against 5.9 ms
+    // of HBM time, i.e. one register-block group is worth ~38 cost units — a pass with ONE well-filled group stays
+    // on the HBM roofline, a second group almost never does.
+    void build_pass(int m, int L, const std::vector<int>& hb, PlanPass& P, std::vector<int>& taken_out) const {
         uint64_t tilemask = (1ull << L) - 1; for (int b : hb) tilemask |= 1ull << b;
+        const double gate_budget = opt.max_cost > opt.group_cost + 1.0 ? opt.max_cost - opt.group_cost : 1.0;
         int max_take = opt.max_subs;
+        taken_out.clear();
         while (true) {
             std::vector<int> taken;
-            pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, max_take,
+            pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, gate_budget, max_take,
                  [&](const LGate& x) { return x.diag || ((tilemask >> x.target) & 1); }, taken, tilemask, opt.max_outer);
-            P = PlanPass(); P.m = m; P.L = L; P.hb = hb; P.ngates = (int)taken.size();
+            P = PlanPass(); P.m = m; P.L = L; P.hb = hb;
             std::vector<LGate> pg; pg.reserve(taken.size());
-            for (int i : taken) { pg.push_back(gates[i]); P.cost += gate_cost(gates[i]); }
-            // register-block groups: same pull with an allowed set that grows up to 3 bits
+            for (int i : taken) pg.push_back(gates[i]);
+            std::vector<std::vector<int>> gidx;      // per group: indices into pg
+            // register-block groups: same pull with an allowed set that grows up to block_bits bits
             std::vector<char> d2(pg.size(), 0); size_t f2 = 0;
             while (true) {
                 while (f2 < pg.size() && d2[f2]) ++f2;
@@ -381,6 +410,7 @@ struct Planner {
                 for (int i : tk) { G.subs.push_back(pg[i]); d2[i] = 1; }
                 for (int b = 0; b < 64; ++b) { if ((have >> b) & 1) G.rb.push_back(b); if ((wset >> b) & 1) G.wb.push_back(b); }
                 P.groups.push_back(G);
+                gidx.push_back(tk);
             }
             if ((int)P.groups.size() > opt.max_groups && taken.size() > 1) {
                 // too many register-block groups for the kernel's program buffer: take fewer gates
@@ -388,18 +418,81 @@ struct Planner {
                 if (max_take < 1) max_take = 1;
                 continue;
             }
-            for (int i : taken) done[i] = 1;
+            // keep the leading groups that fit the budget (the first one is cut to fit if it has to be)
+            double est = 0.0; size_t keep = 0;
+            for (size_t g = 0; g < P.groups.size(); ++g) {
+                double gc = opt.group_cost;
+                for (const LGate& x : P.groups[g].subs) gc += gate_cost(x);
+                if (g > 0 && est + gc > opt.max_cost) break;
+                bool cut = false;
+                if (g == 0 && gc > opt.max_cost) {
+                    double c = opt.group_cost; size_t nk = 0;
+                    for (const LGate& x : P.groups[0].subs) { if (nk > 0 && c + gate_cost(x) > opt.max_cost) break; c += gate_cost(x); ++nk; }
+                    P.groups[0].subs.resize(nk); gidx[0].resize(nk);
+                    gc = c; cut = true;
+                }
+                est += gc; keep = g + 1;
+                if (cut) break;
+            }
+            P.groups.resize(keep); gidx.resize(keep);
+            P.cost = 0.0; P.ngates = 0;
+            for (size_t g = 0; g < keep; ++g)
+                for (size_t j = 0; j < gidx[g].size(); ++j) { taken_out.push_back(taken[gidx[g][j]]); P.cost += gate_cost(pg[gidx[g][j]]); ++P.ngates; }
             break;
         }
-        return true;
     }
 };
 
 // physical bit -> tile-local bit (or -1)
 inline int tile_local_of(const PlanPass& P, int phys) {
+    if (!P.tl.empty()) {
+        for (size_t p = 0; p < P.tl.size(); ++p) if (P.tl[p] == phys) return (int)p;
+        return -1;
+    }
     if (phys < P.L) return phys;
     for (size_t j = 0; j < P.hb.size(); ++j) if (P.hb[j] == phys) return P.L + (int)j;
     return -1;
+}
+
+// TMA kernel: choose the order of the tile's segments in shared memory.  A tile is moved by one 5-d TMA box:
+// dim0 = bits 0-2 (one 128-byte row), the other dims are the segment "bits 3..L-1" and the <= 3 runs of high
+// bits (a run longer than 8 bits is cut: a box dimension holds <= 256).  Their order is free, and it decides
+// which index bits sit at shared-memory address bits 7-9, the ones the 128-byte swizzle xors into the 16-byte
+// chunk index.  A quarter-warp is conflict-free when its three lowest lane bits reach three independent chunk
+// bits, i.e. for k = 0, 1, 2 one of the tile-local positions {k, k + 3} is neither a register-block bit nor
+// pinned to the warp index.  With bits 3 and 4 always at positions 3 and 4, a register block on low qubits
+// (say bits 1-4) left two-way conflicts on every LDS/STS.128 (measured: such passes took 9-13 ms against 6).
+// All orders are tried (<= 24) and the one with the most conflict-free groups wins.
+inline void choose_tile_layout(PlanPass& P) {
+    std::vector<std::pair<int, int>> segs;
+    if (P.L > 3) segs.push_back({ 3, P.L - 3 });
+    for (size_t i = 0; i < P.hb.size(); ++i) {
+        const bool cont = i > 0 && P.hb[i] == P.hb[i - 1] + 1 && segs.back().second < 8;
+        if (cont) segs.back().second++; else segs.push_back({ P.hb[i], 1 });
+    }
+    std::vector<int> idx(segs.size()); for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+    std::vector<int> best_idx = idx; int best_score = -1;
+    do {
+        int pos_bit[6] = { 0, 1, 2, -1, -1, -1 }; int p = 3;
+        for (int si : idx) for (int j = 0; j < segs[si].second && p < 6; ++j) pos_bit[p++] = segs[si].first + j;
+        int score = 0;
+        for (const PlanGroup& G : P.groups) {
+            auto busy = [&](int bit) {
+                if (bit < 0) return true;
+                for (int b : G.rb) if (b == bit) return true;
+                for (int b : G.wb) if (b == bit) return true;
+                return false;
+            };
+            int ok = 0;
+            for (int k = 0; k < 3; ++k) if (!busy(pos_bit[k]) || !busy(pos_bit[k + 3])) ++ok;
+            // block bits not named by the planner are padded from the top positions: they never touch 0-5 unless m is tiny
+            score += ok;
+        }
+        if (score > best_score) { best_score = score; best_idx = idx; }
+    } while (std::next_permutation(idx.begin(), idx.end()));
+    P.segs.clear(); P.tl.clear();
+    for (int b = 0; b < 3 && b < P.m; ++b) P.tl.push_back(b);
+    for (int si : best_idx) { P.segs.push_back(segs[si]); for (int j = 0; j < segs[si].second; ++j) P.tl.push_back(segs[si].first + j); }
 }
 
 // Encode one pass into the byte blob the kernel reads: DevPass | DevGroup[] | DevSub[]

@@ -135,6 +135,7 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
     case QM_OPT_REMAP: st->remap = value != 0; break;
     case QM_OPT_PIPELINE: st->pipeline = value != 0; break;
     case QM_OPT_MAX_COST: st->max_cost = (double)value; break;
+    case QM_OPT_TIME_PASSES: st->time_passes = value != 0; break;
     default: return set_err(QM_ERR_ARG, "unknown option %d", key);
     }
     return QM_OK;
@@ -217,10 +218,8 @@ static bool v4_eligible(const qm_state* st, const PlanPass& P) {
     if (!st->pipeline || !get_encode()) return false;
     if (P.m != 11 && P.m != 12) return false;
     if (P.L < 3 || P.L > 8) return false;
-    int rs[8], rl[8];
-    int nr = hb_runs(P.hb, rs, rl);
-    if (nr > 3) return false;
-    for (int i = 0; i < nr; ++i) if (rl[i] > 8) return false;
+    if (P.tl.size() != (size_t)P.m || P.segs.size() > 4) return false;
+    for (const auto& sg : P.segs) if (sg.second > 8) return false;
     if ((int)P.groups.size() > kV4MaxGroups) return false;
     size_t nrec = P.groups.size();
     for (const PlanGroup& G : P.groups) {
@@ -351,23 +350,33 @@ static int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P
     // tensor map: dim0 = one 128-byte row (8 amplitudes = 16 doubles); dim1 = row index over the whole
     // array (the box takes 2^(L-3) consecutive rows at the tile's base); dims 2..4 = the runs of high
     // tile bits (size 2^len, stride 16 * 2^start bytes), unused dims have size 1.
-    int rs[8], rl[8];
-    const int nr = hb_runs(P.hb, rs, rl);
+    // dim0 = one 128-byte row; the other dims are P.segs in their shared-memory order.  The segment "bits 3..L-1"
+    // is the dim that spans the whole array in rows (its coordinate selects the tile: base >> 3); the runs of high
+    // bits are dims of size 2^len and stride 16 * 2^start bytes at coordinate 0.
     const uint64_t amps = total_amps(st);
-    cuuint64_t gdim[5] = { 16, amps >> 3, 1, 1, 1 };
+    cuuint64_t gdim[5] = { 16, 1, 1, 1, 1 };
     cuuint64_t gstr[4] = { 128, 128, 128, 128 };
-    cuuint32_t box[5] = { 16, 1u << (P.L - 3), 1, 1, 1 };
+    cuuint32_t box[5] = { 16, 1, 1, 1, 1 };
     cuuint32_t estr[5] = { 1, 1, 1, 1, 1 };
-    for (int i = 0; i < nr; ++i) { gdim[2 + i] = 1ull << rl[i]; gstr[1 + i] = 16ull << rs[i]; box[2 + i] = 1u << rl[i]; }
-    // strides of unused trailing dims: keep them multiples of the previous ones
-    for (int i = nr; i < 3; ++i) gstr[1 + i] = (i == 0) ? 128 : gstr[i];
+    int rowdim = -1, nd = 1;
+    for (const auto& sg : P.segs) {
+        if (sg.first == 3 && sg.first < P.L) { rowdim = nd; gdim[nd] = amps >> 3; gstr[nd - 1] = 128; box[nd] = 1u << sg.second; }
+        else { gdim[nd] = 1ull << sg.second; gstr[nd - 1] = 16ull << sg.first; box[nd] = 1u << sg.second; }
+        ++nd;
+    }
+    if (rowdim < 0) {           // L == 3: no row segment; a dim of box 1 carries the tile's base row
+        if (nd >= 5) return set_err(QM_ERR_STATE, "tile layout needs more than 5 TMA dimensions (internal error)");
+        rowdim = nd; gdim[nd] = amps >> 3; gstr[nd - 1] = 128; box[nd] = 1; ++nd;
+    }
     CUtensorMap tm;
     CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, st->amp, gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(QM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    int rs[8], rl[8];
+    const int nr = hb_runs(P.hb, rs, rl);
     V4Launch lp; memset(&lp, 0, sizeof(lp));
-    lp.ntiles = amps >> P.m; lp.reg_bits = st->nl; lp.L = P.L;
+    lp.ntiles = amps >> P.m; lp.reg_bits = st->nl; lp.L = P.L; lp.rowdim = rowdim;
     for (int i = 0; i < 3; ++i) { lp.run_start[i] = i < nr ? rs[i] : 0; lp.run_len[i] = i < nr ? rl[i] : 0; }
     lp.rank_or = st->g ? ((uint64_t)st->rank << st->nl) : 0; lp.nslots = nslots;
     if (P.m == 11) QM_TRY(launch_v4_m11(st->stream, st->sms, tm, prog, d_slots, lp));
@@ -426,6 +435,8 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     if (tma) {
         pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
         pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
+        pl.opt.group_cost = kV4GroupCost;
+        if (st->max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
         if (smap) pl.opt.max_subs = (kV4MaxRecs - kV4MaxGroups) / 2;      // every per-state gate takes two records
     }
     pl.done.assign(pl.gates.size(), 0);
@@ -436,6 +447,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         while (pl.next_pass(P)) {
             offs.push_back(blob.size());
             bool v3 = false;
+            if (tma) choose_tile_layout(P);
             if (tma && v4_eligible(st, P)) {
                 v4progs.emplace_back();
                 if (encode_v4(P, v4progs.back())) v3 = true; else v4progs.pop_back();
@@ -462,8 +474,17 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
                 CU(cudaEventRecord(st->ev_stage, st->stream));
             }
             for (size_t i = 0; i < passes.size(); ++i) {
+                cudaEvent_t ea = nullptr, eb = nullptr;
+                if (st->time_passes) { CU(cudaEventCreate(&ea)); CU(cudaEventCreate(&eb)); CU(cudaEventRecord(ea, st->stream)); }
                 if (v4_of[i] >= 0) QM_TRY(launch_pass_v4(st, v4progs[v4_of[i]], passes[i], d_slots_lift, nslots));
                 else QM_TRY(launch_pass(st, st->d_blob + offs[i], passes[i], d_slots, nslots));
+                if (st->time_passes) {
+                    CU(cudaEventRecord(eb, st->stream));
+                    st->pass_events.push_back(ea); st->pass_events.push_back(eb);
+                    st->pass_desc.push_back((float)passes[i].groups.size());
+                    st->pass_desc.push_back((float)passes[i].ngates);
+                    st->pass_desc.push_back((float)passes[i].cost);
+                }
             }
         }
         if (!leftover) break;
@@ -986,7 +1007,12 @@ extern "C" int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, in
     pl.opt.n_local = n_qubits - global_bits; pl.opt.n_global = global_bits;
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
     if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
-    if (pipeline) { pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups; pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits; }
+    if (pipeline) {
+        pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
+        pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
+        pl.opt.group_cost = kV4GroupCost;
+        if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
+    }
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
     if (pipeline) prepare_for_lifting(pl.gates);
@@ -1073,6 +1099,8 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
     pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
     pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
+    pl.opt.group_cost = kV4GroupCost;
+    if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
     prepare_for_lifting(pl.gates);
@@ -1081,6 +1109,7 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     std::vector<V4Program> prog(1);
     PlanPass P; int np = 0;
     while (pl.next_pass(P)) {
+        choose_tile_layout(P);
         if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
         if (!emulate_v4(prog[0], P, reinterpret_cast<EmuAmp*>(state), n_qubits, 0, nullptr))
             return set_err(QM_ERR_STATE, "pass %d: malformed program (opcode / non-uniform control predicate)", np);
@@ -1088,5 +1117,21 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     }
     for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) return set_err(QM_ERR_STATE, "planner left a gate behind");
     if (n_passes) *n_passes = np;
+    return QM_OK;
+}
+
+// Diagnostics (QM_OPT_TIME_PASSES): per fused pass since the last call {ms, groups, gates, planner cost}.
+extern "C" int32_t qm_pass_times(qm_state* st, float* out, int32_t cap_passes, int32_t* n_passes) {
+    if (!st || !n_passes) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(qm_sync(st));
+    const int n = (int)(st->pass_events.size() / 2);
+    *n_passes = n;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, st->pass_events[2 * i], st->pass_events[2 * i + 1]));
+        if (out && i < cap_passes) { out[4 * i] = ms; out[4 * i + 1] = st->pass_desc[3 * i]; out[4 * i + 2] = st->pass_desc[3 * i + 1]; out[4 * i + 3] = st->pass_desc[3 * i + 2]; }
+        cudaEventDestroy(st->pass_events[2 * i]); cudaEventDestroy(st->pass_events[2 * i + 1]);
+    }
+    st->pass_events.clear(); st->pass_desc.clear();
     return QM_OK;
 }

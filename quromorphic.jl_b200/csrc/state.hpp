@@ -34,8 +34,11 @@ struct qm_state {
     bool ev_pending = false;
     // options
     bool eager = false, fuse = true, remap = false, pipeline = true;
+    bool time_passes = false;   // QM_OPT_TIME_PASSES: CUDA events around every fused pass (diagnostics, tools/pass_model.py)
+    std::vector<cudaEvent_t> pass_events;      // 2 per timed pass, resolved by qm_pass_times
+    std::vector<float> pass_desc;              // per timed pass: groups, records, planner cost
     int tile_bits = 12, low_bits = 5;
-    double max_cost = 32.0;  // per-pass cap of the planner cost model (planner.hpp gate_cost); 0 = unlimited
+    double max_cost = 86.0;  // per-pass budget of the planner cost model (gate costs + 38 per register-block group); 0 = unlimited
     // queue
     std::vector<qm_gate> queue;
     // logical -> physical qubit map (identity unless a sharded remap happened)

@@ -147,6 +147,13 @@ class B200State:
         L.check(L.lib().qm_counters(self._h, C.byref(c)))
         return {k: getattr(c, k) for k, _ in L.Counters._fields_}
 
+    def pass_times(self, cap=65536):
+        """diagnostics (OPT_TIME_PASSES): array [npasses, 4] of {ms, groups, gates, planner cost}"""
+        out = np.zeros((cap, 4), dtype=np.float32)
+        n = C.c_int32()
+        L.check(L.lib().qm_pass_times(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
     def counters_reset(self):
         L.check(L.lib().qm_counters_reset(self._h))
 

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""tools/pass_model.py — per-pass times of a C3 prefix against what the planner knew about each pass (groups,
+gates, cost): the data behind the planner's cost cap."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--qubits", type=int, default=30)
+    ap.add_argument("--depth", type=int, default=30)
+    ap.add_argument("--costs", default="32,48,64")
+    a = ap.parse_args()
+    pkg = ge.load_package()
+    L = pkg._lib
+    gates = pkg.circuits.c3_circuit(n=a.qubits, depth=a.depth)
+    st = pkg.B200State(a.qubits, 0)
+    st.apply_circuit(gates); st.sync()                # dense state
+    st.set_option(L.OPT_TIME_PASSES, 1)
+    for cost in [int(x) for x in a.costs.split(",")]:
+        st.set_option(L.OPT_MAX_COST, cost)
+        st.apply_circuit(gates); st.pass_times()      # warm
+        st.apply_circuit(gates)
+        t = st.pass_times()
+        ms, groups, ng, pc = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
+        A = np.stack([np.ones_like(ms), groups, pc - ng], axis=1)      # ms ~ c0 + c1 groups + c2 (FP64 ops per amplitude)
+        coef, *_ = np.linalg.lstsq(A, ms, rcond=None)
+        desc = L.plan_describe(a.qubits, gates, max_cost=float(cost))
+        if len(desc) == len(ms):
+            for i in np.argsort(-ms)[:3]:
+                print("   slow pass %d: %.2f ms" % (i, ms[i]), desc[i], flush=True)
+            for i in np.argsort(ms)[:2]:
+                print("   fast pass %d: %.2f ms" % (i, ms[i]), desc[i], flush=True)
+        print(json.dumps({"max_cost": cost, "passes": len(ms), "ms_mean": float(ms.mean()), "ms_min": float(ms.min()), "ms_max": float(ms.max()),
+                          "ms_p10": float(np.percentile(ms, 10)), "ms_p90": float(np.percentile(ms, 90)),
+                          "fit_ms = c0 + c1*groups + c2*fp64_per_amp": [float(x) for x in coef],
+                          "by_groups": {int(g): [int((groups == g).sum()), float(ms[groups == g].mean())] for g in np.unique(groups)}}), flush=True)
+    st.close()
+
+
+if __name__ == "__main__":
+    main()
