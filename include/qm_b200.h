@@ -215,6 +215,11 @@ int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, 
 int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
                         const qm_gate* gates, int32_t ngates, double* state_interleaved, int32_t* n_passes);
 
+/* host-only introspection: record counts of the encoded pass programs by family:
+ * hist[0..8] = ROT, ROTX, PHASE, PERMX, THR, SLOT, CTRL records, register-block groups, passes */
+int32_t qm_plan_ophist(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
+                       const qm_gate* gates, int32_t ngates, int64_t hist[9]);
+
 /* ---- misc ---------------------------------------------------------------------------- */
 int32_t qm_sync(qm_state* st);
 int32_t qm_last_error(char* buf, int32_t cap);

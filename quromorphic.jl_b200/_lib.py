@@ -79,6 +79,7 @@ SIGNATURES = {
                                   C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "qm_plan_emulate": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _dp, C.POINTER(C.c_int32)]),
     "qm_pass_times": (C.c_int32, [_vp, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
+    "qm_plan_ophist": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, C.POINTER(C.c_int64)]),
     "qm_sync": (C.c_int32, [_vp]),
     "qm_last_error": (C.c_int32, [C.c_char_p, C.c_int32]),
     "qm_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),
@@ -176,3 +177,10 @@ def plan_emulate(n, gates, psi, tile_bits=12, low_bits=5, max_cost=0.0):
     npass = C.c_int32()
     check(lib().qm_plan_emulate(n, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates), dptr(out), C.byref(npass)))
     return out, npass.value
+
+
+def plan_ophist(n, gates, tile_bits=12, low_bits=5, max_cost=0.0):
+    """host-only: records of the encoded pass programs by family"""
+    h = (C.c_int64 * 9)()
+    check(lib().qm_plan_ophist(n, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates), h))
+    return dict(zip(("ROT", "ROTX", "PHASE", "PERMX", "THR", "SLOT", "CTRL", "groups", "passes"), list(h)))

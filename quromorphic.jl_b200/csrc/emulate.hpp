@@ -35,7 +35,7 @@ inline bool emu_decode(uint32_t op, int& fam, int& var, int& B, int& CB) {
     if (op < (uint32_t)V4_OP_PHASE) { fam = 1; var = (op - V4_OP_ROTX) / V4_NBC; bc((op - V4_OP_ROTX) % V4_NBC); return true; }
     if (op < (uint32_t)V4_OP_PERMX) { fam = 2; var = (op - V4_OP_PHASE) / V4_NBC; bc((op - V4_OP_PHASE) % V4_NBC); return true; }
     if (op < (uint32_t)V4_OP_THR) { fam = 3; var = 0; bc(op - V4_OP_PERMX); return true; }
-    if (op < (uint32_t)V4_OP_SLOT) { fam = 4; var = (op - V4_OP_THR) / (kV4BlockBits + 1); B = -1; CB = (int)((op - V4_OP_THR) % (kV4BlockBits + 1)) - 1; return true; }
+    if (op < (uint32_t)V4_NUM_GATE_OPS) { fam = 4; var = (op - V4_OP_THR) / (kV4BlockBits + 1); B = -1; CB = (int)((op - V4_OP_THR) % (kV4BlockBits + 1)) - 1; return true; }
     return false;
 }
 
@@ -91,21 +91,19 @@ inline bool emulate_v4(const V4Program& prog, const PlanPass& P, EmuAmp* amp, in
                         for (int l = 0; l < nl_; ++l) for (int q = 0; q < 6; ++q) c[l][q] = slot_lifts[(size_t)R->aux * 8 + q];
                         preloaded = true; continue;
                     }
-                    if (R->op == (uint32_t)V4_OP_CTRL) {
-                        const bool act0 = (ctx[0] & R->cm) == R->cm;
-                        for (int l = 0; l < nl_; ++l) if (((ctx[l] & R->cm) == R->cm) != act0) return false;   // must be warp-uniform
-                        if (!act0) {        // jump over the controlled gate (and its SLOT prefix)
-                            if (R->aux < 2 * sizeof(V4Rec) || R->aux % sizeof(V4Rec)) return false;
-                            R += R->aux / sizeof(V4Rec) - 1;
-                        }
-                        continue;
-                    }
                     // records hold the coefficients pairwise: {c0, c3} {c1, c4} {c2, c5}
                     if (!preloaded) for (int l = 0; l < nl_; ++l) for (int q = 0; q < 3; ++q) { c[l][q] = R->c[2 * q]; c[l][3 + q] = R->c[2 * q + 1]; }
                     preloaded = false;
                     int fam, var, B, CB;
-                    if (!emu_decode(R->op, fam, var, B, CB)) return false;
-                    if (R->cm) return false;
+                    uint32_t op = R->op;
+                    bool active = true;
+                    if (op >= (uint32_t)V4_NUM_GATE_OPS && op < (uint32_t)V4_OP_SLOT) {       // controlled entry
+                        op -= V4_NUM_GATE_OPS;
+                        active = (ctx[0] & R->cm) == R->cm;
+                        for (int l = 0; l < nl_; ++l) if (((ctx[l] & R->cm) == R->cm) != active) return false;   // must be warp-uniform
+                    } else if (R->cm) return false;
+                    if (!emu_decode(op, fam, var, B, CB)) return false;
+                    if (!active) continue;
                     for (int l = 0; l < nl_; ++l) {
                         EmuAmp* x = a[l]; double* cc = c[l];
                         auto ok = [&](int k) { return CB < 0 || ((k >> CB) & 1); };

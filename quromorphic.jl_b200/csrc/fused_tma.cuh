@@ -55,7 +55,7 @@ static const int kV4BlockBits = 4;     // amplitudes per thread = 16
 static const int kV4CtxOuter = 13;     // context word: bits [0, 13) tile-local index bits of the thread, [13, 31) outer bits, bit 31 = 1
 static const int kV4MaxOuter = 31 - kV4CtxOuter;
 static const uint32_t kV4CtxAlways = 0x80000000u;
-static const int kV4MaxRecs = 240;     // gate records + SLOT / CTRL prefixes + one END per group
+static const int kV4MaxRecs = 240;     // gate records + SLOT prefixes + one END per group
 static const int kV4MaxGroups = 48;
 static const int kV4MaxSubs = 96;
 // planner budget units one register-block group costs on top of its gates (tools/pass_model.py: a pass takes about
@@ -65,8 +65,8 @@ static const double kV4GroupCost = 38.0;
 struct V4Rec {              // 64 bytes, read by the PTX interpreter with shared-memory broadcasts
     uint32_t op;            // opcode
     uint32_t tm;            // THR: context bit selecting the coefficient set
-    uint32_t cm;            // CTRL: context bits that must all be set (a control outside the register block)
-    uint32_t aux;           // SLOT: per-state slot index;  CTRL: bytes to the record after the controlled gate
+    uint32_t cm;            // controlled entry: context bits that must all be set (a control outside the register block)
+    uint32_t aux;           // SLOT: per-state slot index
     double   c[6];          // pairwise {t1, t1'} {s1, s1'} {t2, t2'} (set 0, set 1)  |  THR multiply: {cr, cr'} {ci, ci'} -
 };
 static_assert(sizeof(V4Rec) == 64, "V4Rec layout");

@@ -224,7 +224,7 @@ static bool v4_eligible(const qm_state* st, const PlanPass& P) {
     size_t nrec = P.groups.size();
     for (const PlanGroup& G : P.groups) {
         if ((int)G.rb.size() > kV4BlockBits) return false;
-        for (const LGate& x : G.subs) { if (!x.liftable) return false; nrec += 1 + (x.slot >= 0) + (x.ctrl >= 0); }
+        for (const LGate& x : G.subs) { if (!x.liftable) return false; nrec += 1 + (x.slot >= 0); }
     }
     if (nrec > (size_t)kV4MaxRecs) return false;
     if ((total_amps(st) >> 3) > 0x7fffffffull) return false;      // TMA coordinates are int32
@@ -300,10 +300,6 @@ static bool encode_v4(const PlanPass& P, V4Program& out) {
                     if (cl >= 0 && !((wmask >> cl) & 1)) ok = false;      // the control predicate must be warp-uniform
                 }
             }
-            if (cm) {                          // a control outside the register block: a CTRL record in front
-                V4Rec& R = out.recs[nrec++]; memset(&R, 0, sizeof(R));
-                R.op = V4_OP_CTRL; R.cm = cm; R.aux = (uint32_t)sizeof(V4Rec) * (x.slot >= 0 ? 3u : 2u);
-            }
             if (x.slot >= 0) {                 // per-state coefficients: a SLOT record in front of the gate
                 V4Rec& R = out.recs[nrec++]; memset(&R, 0, sizeof(R));
                 R.op = V4_OP_SLOT; R.aux = (uint32_t)x.slot;
@@ -336,6 +332,7 @@ static bool encode_v4(const PlanPass& P, V4Program& out) {
                 else base = V4_OP_PERMX;
                 S.op = (uint32_t)(base + bc);
             }
+            if (cm) { S.op += V4_NUM_GATE_OPS; S.cm = cm; }      // a control outside the register block: the body's controlled entry
             for (int q = 0; q < 3; ++q) { S.c[2 * q] = cc[q]; S.c[2 * q + 1] = cc[3 + q]; }     // pairwise {set 0, set 1}
         }
         if (!ok) break;
@@ -435,7 +432,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     if (tma) {
         pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
         pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
-        pl.opt.group_cost = kV4GroupCost;
+        pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
         if (st->max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
         if (smap) pl.opt.max_subs = (kV4MaxRecs - kV4MaxGroups) / 2;      // every per-state gate takes two records
     }
@@ -1010,7 +1007,7 @@ extern "C" int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, in
     if (pipeline) {
         pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
         pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
-        pl.opt.group_cost = kV4GroupCost;
+        pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
         if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
     }
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
@@ -1099,7 +1096,7 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
     pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
     pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
-    pl.opt.group_cost = kV4GroupCost;
+    pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
     if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
@@ -1133,5 +1130,43 @@ extern "C" int32_t qm_pass_times(qm_state* st, float* out, int32_t cap_passes, i
         cudaEventDestroy(st->pass_events[2 * i]); cudaEventDestroy(st->pass_events[2 * i + 1]);
     }
     st->pass_events.clear(); st->pass_desc.clear();
+    return QM_OK;
+}
+
+// Host-only introspection: plans and encodes `gates` as for the TMA kernel and counts the records by family:
+// hist[0..7] = ROT, ROTX, PHASE, PERMX, THR, SLOT, gates entered through the controlled entry, groups; hist[8] = passes.
+extern "C" int32_t qm_plan_ophist(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
+                                  const qm_gate* gates, int32_t ngates, int64_t hist[9]) {
+    if (!gates || !hist || n_qubits < 11 || (tile_bits != 11 && tile_bits != 12) || tile_bits > n_qubits) return set_err(QM_ERR_ARG, "bad argument");
+    Planner pl;
+    pl.opt.n_local = n_qubits; pl.opt.n_global = 0;
+    pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
+    if (max_cost > 0) pl.opt.max_cost = max_cost;
+    pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
+    pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
+    pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
+    if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
+    int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
+    if (rc) return set_err(rc, "bad gate");
+    prepare_for_lifting(pl.gates);
+    pl.done.assign(pl.gates.size(), 0);
+    for (int i = 0; i < 9; ++i) hist[i] = 0;
+    std::vector<V4Program> prog(1);
+    PlanPass P;
+    while (pl.next_pass(P)) {
+        choose_tile_layout(P);
+        if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass cannot be encoded");
+        hist[8]++; hist[7] += prog[0].ngroups;
+        for (int i = 0; i < prog[0].nrecs; ++i) {
+            uint32_t op = prog[0].recs[i].op;
+            if (op >= (uint32_t)V4_NUM_GATE_OPS && op < (uint32_t)V4_OP_SLOT) { op -= V4_NUM_GATE_OPS; hist[6]++; }
+            if (op < (uint32_t)V4_OP_ROTX) hist[0]++;
+            else if (op < (uint32_t)V4_OP_PHASE) hist[1]++;
+            else if (op < (uint32_t)V4_OP_PERMX) hist[2]++;
+            else if (op < (uint32_t)V4_OP_THR) hist[3]++;
+            else if (op < (uint32_t)V4_NUM_GATE_OPS) hist[4]++;
+            else if (op == (uint32_t)V4_OP_SLOT) hist[5]++;
+        }
+    }
     return QM_OK;
 }

@@ -123,7 +123,9 @@ def test_planner_leaves_global_targets_for_remap(pkg):
 
 
 @pytest.mark.parametrize("n,tile,low,cost,seed", [(13, 11, 5, 0, 1), (14, 12, 5, 24.0, 2), (15, 12, 3, 64.0, 3), (15, 11, 3, 0, 4),
-                                                  (14, 12, 8, 32.0, 5), (15, 11, 4, 40.0, 6), (16, 12, 6, 96.0, 7)])
+                                                  (14, 12, 8, 32.0, 5), (15, 11, 4, 40.0, 6), (16, 12, 6, 96.0, 7),
+                                                  (16, 12, 5, 86.0, 8), (16, 11, 5, 86.0, 9), (15, 12, 5, 120.0, 10),
+                                                  (16, 11, 5, 250.0, 11), (14, 11, 3, 60.0, 12), (16, 12, 7, 180.0, 13)])
 def test_encoded_pass_programs_emulated_on_cpu(pkg, n, tile, low, cost, seed):
     """planner + encoder of the TMA kernel, checked without a GPU: the encoded pass programs (the bytes the kernel
     is launched with) are walked over a host vector by the scalar emulation in csrc/emulate.hpp (test
@@ -140,7 +142,7 @@ def test_encoded_pass_programs_emulated_on_cpu(pkg, n, tile, low, cost, seed):
 def test_encoded_c3_programs_emulated_on_cpu(pkg):
     n = 16
     gates = pkg.circuits.c3_circuit(n=n, depth=8)
-    for tile, cost in ((12, 0.0), (11, 24.0), (12, 48.0)):
+    for tile, cost in ((12, 0.0), (11, 24.0), (12, 48.0), (12, 86.0), (11, 86.0), (12, 130.0), (11, 250.0)):
         got, npass = pkg._lib.plan_emulate(n, gates, O.statevector(n, 0), tile_bits=tile, max_cost=cost)
         ref = O.apply_circuit(O.statevector(n, 0), gates)
         assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12

@@ -18,19 +18,22 @@ Design notes (all measured on B200, see profiles/ and DESIGN.md):
     costs 8 LSU wavefronts) but the constant-cache latency (~80 cycles hit, more on a miss with 16 warps at
     different places of a 15 KB program) made every variant tried slower: 27.8 ms against 21.7 ms per
     compute-bound pass at 30 qubits.
-  * A control that is not a register-block bit has its own record in front of the gate (CTRL): the planner
-    keeps such controls on warp-index bits or outside the tile, so the predicate is warp-uniform and the warp
-    either runs the next record or jumps over it.  Gate bodies themselves carry no predicate.
+  * Every body has a second, CONTROLLED entry for a control that is not a register-block bit: it tests the record's
+    control mask against the thread's context word and either falls into the body or jumps to one shared skip
+    block.  The planner keeps such controls on warp-index bits or outside the tile, so the predicate is
+    warp-uniform.  (A separate CTRL record in front of the gate cost a whole extra dispatch — and a pass costs
+    ~0.2 ms per dispatched record at 30 qubits whatever the record does, tools/pass_model.py.)
 
 A record is 64 bytes:  u32 op, tm, cm, aux;  f64 c0, c3, c1, c4, c2, c5.
-  cm   CTRL: context bits that must all be set          tm   THR: context bit selecting the coefficient set
-  aux  SLOT: per-state coefficient slot;  CTRL: bytes from this record to the one after the controlled gate
+  cm   controlled entry: context bits that must all be set          tm   THR: context bit selecting the coefficient set
+  aux  SLOT: per-state coefficient slot
 Operands:  %0 shared address of the current record ("+r")   %1 context word   %2 shared address of the per-state coefficient base
            %3 shared address of the tile buffer      %4 the thread's swizzled byte offset in the tile
            %5..%8 swizzled byte offsets of the four block bits
 Opcodes (must match encode_v4 in qm_api.cu), NBC = 16 legal (B, CB) pairs:
    ROT   sign variant 0..3 x NBC      ROTX  sign variant 0, 3 x NBC      PHASE (sg set 0, sg set 1) in 00 03 30 33 x NBC
-   PERMX x NBC       THR (lift sg 0, lift sg 3, complex multiply) x 5 (CB = -1, 0..3)       SLOT   CTRL   END
+   PERMX x NBC       THR (lift sg 0, lift sg 3, complex multiply) x 5 (CB = -1, 0..3);   + V4_NUM_GATE_OPS: controlled entry
+   SLOT   END
 """
 import os
 
@@ -198,39 +201,42 @@ def main():
         for CB in range(-1, NB):
             bodies.append((THR_PHI, body_thr_mul(CB) if kind == "mul" else body_thr_lift(CB, kind)))
     n_gate_ops = len(bodies)
-    OP_SLOT, OP_CTRL, OP_END = n_gate_ops, n_gate_ops + 1, n_gate_ops + 2
-    nops = n_gate_ops + 3
+    # opcode k < n_gate_ops: plain entry of body k; n_gate_ops + k: its CONTROLLED entry (the record's cm = context
+    # bits that must all be set; the planner keeps such controls warp-uniform, so the warp runs the body or skips it)
+    OP_SLOT, OP_END = 2 * n_gate_ops, 2 * n_gate_ops + 1
+    nops = 2 * n_gate_ops + 2
+    targets = ["V4L%d" % i for i in range(n_gate_ops)] + ["V4C%d" % i for i in range(n_gate_ops)] + ["V4L%d" % OP_SLOT, "V4L%d" % OP_END]
     lines = ["{", ".reg .f64 x<%d>, y<%d>, c<6>, ng, n0, n1, n2, tm<2>;" % (NA, NA), ".reg .b32 hop, hcm, htm, hax, t, ad, o<4>;",
              ".reg .pred pact, phi;", ".reg .b64 sa, sb;",
-             "V4T: .branchtargets " + ", ".join("V4L%d" % i for i in range(nops)) + ";"]
+             "V4T: .branchtargets " + ", ".join(targets) + ";"]
     lines += addresses("setup") + addresses("load")
     lines += ["ld.shared.v2.u32 {hop, htm}, [%0];"] + LOAD_PAIR + DISPATCH
     for i, (pre, b) in enumerate(bodies):
+        lines.append("V4C%d:" % i)
+        lines += ["ld.shared.u32 hcm, [%0+8];", "and.b32 t, %1, hcm;", "setp.eq.u32 pact, t, hcm;", "@!pact bra.uni V4SKIP;"]
         lines.append("V4L%d:" % i)
         lines += pre + ADVANCE_HDR + b + DISPATCH
+    # a controlled gate whose control is off: on to the next record (header, all coefficient pairs, jump)
+    lines.append("V4SKIP:")
+    lines += ADVANCE_HDR + LOAD_PAIR + DISPATCH
     # SLOT (aux = slot index): all six coefficients of the record that follows come from the per-state table,
     # whose base address for this tile's register sits in shared memory at %2
     lines.append("V4L%d:" % OP_SLOT)
     lines += ["ld.shared.u32 t, [%0+12];", "ld.shared.u64 sa, [%2];", "mul.wide.u32 sb, t, 64;", "add.u64 sa, sa, sb;"] + ADVANCE_HDR
     lines += ["ld.global.nc.v2.f64 {c0, c1}, [sa];", "ld.global.nc.v2.f64 {c2, c3}, [sa+16];",
               "ld.global.nc.v2.f64 {c4, c5}, [sa+32];"] + DISPATCH
-    # CTRL (cm = context bits that must be set, aux = bytes to the record after the controlled gate): the
-    # planner keeps such controls warp-uniform, so the whole warp either runs the next record or skips it
-    lines.append("V4L%d:" % OP_CTRL)
-    lines += ["ld.shared.v2.u32 {hcm, hax}, [%0+8];", "and.b32 t, %1, hcm;", "setp.eq.u32 pact, t, hcm;", "selp.u32 t, 64, hax, pact;",
-              "add.u32 %0, %0, t;", "ld.shared.v2.u32 {hop, htm}, [%0];"] + LOAD_PAIR + DISPATCH
     lines.append("V4L%d:" % OP_END)
     lines += addresses("store")
     lines.append("}")
     here = os.path.dirname(os.path.abspath(__file__))
     out = os.path.join(here, "..", "quromorphic.jl_b200", "csrc", "v4_dispatch.inc")
     defs = ("#define V4_NUM_OPS %d\n#define V4_NBC %d\n#define V4_OP_ROTX %d\n#define V4_OP_PHASE %d\n#define V4_OP_PERMX %d\n"
-            "#define V4_OP_THR %d\n#define V4_OP_SLOT %d\n#define V4_OP_CTRL %d\n#define V4_OP_END %d\n"
-            % (nops, NBC, op_rotx, op_phase, op_permx, op_thr, OP_SLOT, OP_CTRL, OP_END))
+            "#define V4_OP_THR %d\n#define V4_NUM_GATE_OPS %d\n#define V4_OP_SLOT %d\n#define V4_OP_END %d\n"
+            % (nops, NBC, op_rotx, op_phase, op_permx, op_thr, n_gate_ops, OP_SLOT, OP_END))
     with open(os.path.join(os.path.dirname(out), "v4_ops.inc"), "w") as f:
         f.write("// GENERATED by tools/gen_v4_dispatch.py — do not edit.  Opcode numbering of the gate interpreter.\n" + defs)
     with open(out, "w") as f:
-        f.write("// GENERATED by tools/gen_v4_dispatch.py — do not edit.  %d gate bodies + SLOT + CTRL + END, threaded dispatch.\n" % n_gate_ops)
+        f.write("// GENERATED by tools/gen_v4_dispatch.py — do not edit.  %d gate bodies (plain + controlled entry) + SLOT + END, threaded dispatch.\n" % n_gate_ops)
         f.write("#define V4_GROUP_PTX \\\n")
         for ln in lines:
             f.write('    "%s\\n\\t" \\\n' % ln)

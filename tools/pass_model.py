@@ -25,11 +25,13 @@ def main():
     st = pkg.B200State(a.qubits, 0)
     st.apply_circuit(gates); st.sync()                # dense state
     st.set_option(L.OPT_TIME_PASSES, 1)
+    allrows = []
     for cost in [int(x) for x in a.costs.split(",")]:
         st.set_option(L.OPT_MAX_COST, cost)
         st.apply_circuit(gates); st.pass_times()      # warm
         st.apply_circuit(gates)
         t = st.pass_times()
+        allrows.append(t.astype(np.float64))
         ms, groups, ng, pc = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
         A = np.stack([np.ones_like(ms), groups, pc - ng], axis=1)      # ms ~ c0 + c1 groups + c2 (FP64 ops per amplitude)
         coef, *_ = np.linalg.lstsq(A, ms, rcond=None)
@@ -43,6 +45,15 @@ def main():
                           "ms_p10": float(np.percentile(ms, 10)), "ms_p90": float(np.percentile(ms, 90)),
                           "fit_ms = c0 + c1*groups + c2*fp64_per_amp": [float(x) for x in coef],
                           "by_groups": {int(g): [int((groups == g).sum()), float(ms[groups == g].mean())] for g in np.unique(groups)}}), flush=True)
+    # one model over all budgets, on the passes that are clearly not HBM-bound: ms ~ a + g*groups + s*gates + f*fp64
+    if allrows:
+        R = np.concatenate(allrows)
+        R = R[R[:, 0] > 6.6]
+        A = np.stack([np.ones(len(R)), R[:, 1], R[:, 2], R[:, 3] - R[:, 2]], axis=1)
+        coef, res, *_ = np.linalg.lstsq(A, R[:, 0], rcond=None)
+        pred = A @ coef
+        print(json.dumps({"compute_bound_passes": int(len(R)), "fit_ms = a + g*groups + s*gates + f*fp64_per_amp": [float(x) for x in coef],
+                          "rms_residual_ms": float(np.sqrt(np.mean((pred - R[:, 0]) ** 2)))}), flush=True)
     st.close()
 
 
