@@ -158,3 +158,50 @@ def c2_encoding(batch, n, t, w, seed0=1601):
         for q in range(n):
             out[b, q] = L.mat8(Q.ry_gate(np.pi * u * w[q]))
     return out
+
+
+# ---- gate-list files: one circuit, identical bits for every consumer ----------------
+# Binary form: 16-byte header  b"QMGATES1" | u32 n_qubits | u32 n_gates  (little endian), then n_gates records of the
+# 80-byte wire format (include/qm_b200.h qm_gate: i32 kind, q0, q1, flags; f64 m[8]).
+# Text form: "# qmgates 1 <n_qubits> <n_gates>" then one line per gate: kind q0 q1 and the eight matrix doubles as
+# C99 hex floats (float.hex()), so that no consumer ever parses a decimal.
+GATEFILE_MAGIC = b"QMGATES1"
+
+
+def save_gates(path, n_qubits, gates, text=False):
+    """write a gate list (wire format: 0-based textbook bits) to `path`"""
+    assert gates.dtype == L.GATE_DTYPE
+    if text:
+        with open(path, "w") as f:
+            f.write("# qmgates 1 %d %d\n" % (n_qubits, len(gates)))
+            for g in gates:
+                f.write("%d %d %d %s\n" % (g["kind"], g["q0"], g["q1"], " ".join(float(x).hex() for x in g["m"])))
+        return
+    with open(path, "wb") as f:
+        f.write(GATEFILE_MAGIC)
+        f.write(np.array([n_qubits, len(gates)], dtype="<u4").tobytes())
+        f.write(np.ascontiguousarray(gates).tobytes())
+
+
+def load_gates(path):
+    """-> (n_qubits, gates); accepts both forms"""
+    with open(path, "rb") as f:
+        head = f.read(8)
+        if head == GATEFILE_MAGIC:
+            n, ng = (int(x) for x in np.frombuffer(f.read(8), dtype="<u4"))
+            raw = f.read()
+            if len(raw) != ng * L.GATE_DTYPE.itemsize:
+                raise ValueError("%s: expected %d gate records, file holds %d bytes" % (path, ng, len(raw)))
+            return n, np.frombuffer(raw, dtype=L.GATE_DTYPE).copy()
+    with open(path, "r") as f:
+        first = f.readline().split()
+        if first[:3] != ["#", "qmgates", "1"]:
+            raise ValueError("%s: not a qmgates file" % path)
+        n, ng = int(first[3]), int(first[4])
+        gates = np.zeros(ng, dtype=L.GATE_DTYPE)
+        for i in range(ng):
+            t = f.readline().split()
+            if len(t) != 11:
+                raise ValueError("%s: gate %d: expected 11 fields" % (path, i))
+            gates[i] = (int(t[0]), int(t[1]), int(t[2]), 0, [float.fromhex(x) for x in t[3:]])
+        return n, gates

@@ -123,6 +123,17 @@ function apply_circuit!(s::B200State, gates::Vector{QMGate})
     s
 end
 
+"read a gate-list file written by circuits.save_gates (binary form: b\"QMGATES1\" | u32 n | u32 ngates | 80-byte records)"
+function load_gates(path::AbstractString)
+    open(path, "r") do io
+        read(io, 8) == Vector{UInt8}("QMGATES1") || error("not a QMGATES1 file")
+        n = Int(ltoh(read(io, UInt32))); ng = Int(ltoh(read(io, UInt32)))
+        gates = Vector{QMGate}(undef, ng)
+        read!(io, gates)
+        (n, gates)
+    end
+end
+
 # ---- readouts -----------------------------------------------------------------------------------
 function mp(s::B200State; batch_idx::Int = 0)             # QSim.jl:293
     p = Vector{Float64}(undef, 1 << s.n)

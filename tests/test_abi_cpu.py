@@ -146,3 +146,18 @@ def test_encoded_c3_programs_emulated_on_cpu(pkg):
         got, npass = pkg._lib.plan_emulate(n, gates, O.statevector(n, 0), tile_bits=tile, max_cost=cost)
         ref = O.apply_circuit(O.statevector(n, 0), gates)
         assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
+def test_gate_list_files_round_trip_bit_exactly(pkg, tmp_path):
+    """the on-disk circuit forms (binary and hex-float text) give back the identical 80-byte records"""
+    C = pkg.circuits
+    gates = C.c3_circuit(n=12, depth=3)
+    for text in (False, True):
+        path = str(tmp_path / ("c.qmg" if not text else "c.qmg.txt"))
+        C.save_gates(path, 12, gates, text=text)
+        n, back = C.load_gates(path)
+        assert n == 12 and back.dtype == gates.dtype and back.tobytes() == gates.tobytes()
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.qmg"
+        bad.write_bytes(b"QMGATES1" + np.array([12, 5], dtype="<u4").tobytes() + b"x" * 7)
+        C.load_gates(str(bad))
