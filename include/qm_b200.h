@@ -58,12 +58,12 @@ enum { QM_BASIS_Z = 0, QM_BASIS_X = 1, QM_BASIS_Y = 2 };
 /* qm_set_option keys */
 enum {
     QM_OPT_EAGER      = 0,  /* 1: run every gate call at once with the unfused kernels (default 0: queue + fuse) */
-    QM_OPT_TILE_BITS  = 1,  /* fused pass tile size m (default 12: 4096 amplitudes, 64 KiB of shared memory)     */
+    QM_OPT_TILE_BITS  = 1,  /* fused pass tile size m: 11 or 12 for the TMA kernel; default 0 = automatic (12) */
     QM_OPT_LOW_BITS   = 2,  /* contiguous low bits every tile keeps (default 5: 512-byte rows)                    */
     QM_OPT_FUSE       = 3,  /* 0: planner emits one pass per gate (debug), 1: fuse (default)                      */
     QM_OPT_REMAP      = 4,  /* 1: planner may relabel qubits inside a pass (logical->physical permutation)        */
     QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel                     */
-    QM_OPT_MAX_COST   = 6,  /* planner: cap on a pass's arithmetic, in FP64 FMAs per amplitude (0 = no cap)       */
+    QM_OPT_MAX_COST   = 6,  /* planner: budget of a pass = gate costs (FP64 FMAs per amplitude + 1) + 38 per register-block group; default 90, 0 = no cap */
     QM_OPT_TIME_PASSES = 7  /* 1: CUDA events around every fused pass, read back with qm_pass_times (diagnostics) */
 };
 

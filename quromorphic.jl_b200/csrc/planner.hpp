@@ -281,12 +281,13 @@ struct Planner {
     }
 
     // choose the high tile bits for the next pass
-    void choose_tile(int m, int L, std::vector<int>& hb_best, int& best) const {
+    // tmask_best: the bits non-diagonal targets may use in the chosen pass (all tile bits, or one 4-bit block)
+    void choose_tile(int m, int L, std::vector<int>& hb_best, int& best, uint64_t& tmask_best) const {
         const int nl = opt.n_local, nh = m - L;
-        hb_best.clear(); best = -1;
+        hb_best.clear(); best = -1; tmask_best = ~0ull;
         if (nh <= 0) { best = count_with((1ull << L) - 1); return; }
         uint64_t low = (1ull << L) - 1;
-        auto try_set = [&](const std::vector<int>& hb) {
+        auto try_set = [&](const std::vector<int>& hb, uint64_t tmask = ~0ull) {
             // runs of consecutive bits, a run being cut after max_run_len bits (one TMA box dimension holds <= 256)
             int runs = 0, len = 0;
             for (size_t i = 0; i < hb.size(); ++i) {
@@ -298,10 +299,10 @@ struct Planner {
             int c;
             if (opt.group_cost > 0) {       // what the pass built on this tile would really take
                 PlanPass tmp; std::vector<int> tk;
-                build_pass(m, L, hb, tmp, tk);
+                build_pass(m, L, hb, tmp, tk, tmask);
                 c = (int)tk.size();
             } else c = count_with(mask);
-            if (c > best) { best = c; hb_best = hb; }
+            if (c > best) { best = c; hb_best = hb; tmask_best = tmask; }
         };
         // (1) greedy: the first nh distinct non-diagonal high local targets in dependency order
         {
@@ -324,6 +325,20 @@ struct Planner {
         for (int a = L; a + nh <= nl; ++a) {
             std::vector<int> hb; for (int j = 0; j < nh; ++j) hb.push_back(a + j);
             try_set(hb);
+        }
+        // (3) group-aware budget: a pass is essentially ONE register block, so every window of block_bits
+        // consecutive qubits is tried as that block directly (targets restricted to it), the rest of the tile
+        // being filler; the greedy grouping inside a wider tile often settles on a worse block
+        if (opt.group_cost > 0 && nh >= opt.block_bits) {
+            for (int a = 0; a + opt.block_bits <= nl; ++a) {
+                uint64_t w = 0; for (int j = 0; j < opt.block_bits; ++j) w |= 1ull << (a + j);
+                std::vector<int> hb;
+                for (int b = L; b < nl; ++b) if ((w >> b) & 1) hb.push_back(b);
+                for (int b = L; b < nl && (int)hb.size() < nh; ++b) if (!((w >> b) & 1)) hb.push_back(b);
+                if ((int)hb.size() != nh) continue;
+                std::sort(hb.begin(), hb.end());
+                try_set(hb, w);
+            }
         }
     }
 
@@ -352,10 +367,11 @@ struct Planner {
             done[first] = 1;
             return true;
         }
-        choose_tile(m, L, hb, best);
+        uint64_t tmask = ~0ull;
+        choose_tile(m, L, hb, best, tmask);
         if (best <= 0) return false;
         std::vector<int> taken;
-        build_pass(m, L, hb, P, taken);
+        build_pass(m, L, hb, P, taken, tmask);
         for (int i : taken) done[i] = 1;
         if (opt.retile && !taken.empty()) retile(P);
         return !taken.empty();
@@ -424,15 +440,17 @@ struct Planner {
     // (tools/pass_model.py): a pass costs about 1.2 ms + 1.9 ms per group + 0.05 ms per cost unit against 5.9 ms
     // of HBM time, i.e. one register-block group is worth ~38 cost units — a pass with ONE well-filled group stays
     // on the HBM roofline, a second group almost never does.
-    void build_pass(int m, int L, const std::vector<int>& hb, PlanPass& P, std::vector<int>& taken_out) const {
+    void build_pass(int m, int L, const std::vector<int>& hb, PlanPass& P, std::vector<int>& taken_out,
+                    uint64_t target_mask = ~0ull) const {
         uint64_t tilemask = (1ull << L) - 1; for (int b : hb) tilemask |= 1ull << b;
+        const uint64_t tgt = tilemask & target_mask;
         const double gate_budget = opt.max_cost > opt.group_cost + 1.0 ? opt.max_cost - opt.group_cost : 1.0;
         int max_take = opt.max_subs;
         taken_out.clear();
         while (true) {
             std::vector<int> taken;
             pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, gate_budget, max_take,
-                 [&](const LGate& x) { return x.diag || ((tilemask >> x.target) & 1); }, taken, tilemask, opt.max_outer);
+                 [&](const LGate& x) { return x.diag || ((tgt >> x.target) & 1); }, taken, tilemask, opt.max_outer);
             P = PlanPass(); P.m = m; P.L = L; P.hb = hb;
             std::vector<LGate> pg; pg.reserve(taken.size());
             for (int i : taken) pg.push_back(gates[i]);

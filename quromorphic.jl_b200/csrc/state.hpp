@@ -37,7 +37,7 @@ struct qm_state {
     bool time_passes = false;   // QM_OPT_TIME_PASSES: CUDA events around every fused pass (diagnostics, tools/pass_model.py)
     std::vector<cudaEvent_t> pass_events;      // 2 per timed pass, resolved by qm_pass_times
     std::vector<float> pass_desc;              // per timed pass: groups, records, planner cost
-    int tile_bits = 12, low_bits = 5;
+    int tile_bits = 0, low_bits = 5;     // tile_bits 0 = automatic (12)
     double max_cost = 90.0;  // per-pass budget of the planner cost model (gate costs + 38 per register-block group); 0 = unlimited
     // queue
     std::vector<qm_gate> queue;
