@@ -158,7 +158,10 @@ def body_thr_mul(CB):
 # body), jump.  The pointer is advanced BEFORE the loads that use it: an add after them has to wait until the
 # loads have read their address register.
 ADVANCE_HDR = ["add.u32 %0, %0, 64;", "ld.shared.v2.u32 {hop, htm}, [%0];"]
-DISPATCH = ["brx.idx.uni hop, V4T;"]
+# One shared dispatcher: with a `brx.idx` at the end of every body ptxas emitted a private 384-entry table of BRA
+# instructions per site (58k of 70k SASS instructions, ~1 MB of code) and instruction-fetch stalls tripled.
+SHARED_DISPATCH = os.environ.get("QM_V4_SHARED_DISPATCH", "1") == "1"
+DISPATCH = ["bra.uni V4DISP;"] if SHARED_DISPATCH else ["brx.idx.uni hop, V4T;"]
 
 
 def addresses(tag):
@@ -210,12 +213,17 @@ def main():
              ".reg .pred pact, phi;", ".reg .b64 sa, sb;",
              "V4T: .branchtargets " + ", ".join(targets) + ";"]
     lines += addresses("setup") + addresses("load")
-    lines += ["ld.shared.v2.u32 {hop, htm}, [%0];"] + LOAD_PAIR + DISPATCH
+    lines += ["ld.shared.v2.u32 {hop, htm}, [%0];"] + LOAD_PAIR
+    lines += ["V4DISP:", "brx.idx.uni hop, V4T;"] if SHARED_DISPATCH else DISPATCH
     for i, (pre, b) in enumerate(bodies):
-        lines.append("V4C%d:" % i)
-        lines += ["ld.shared.u32 hcm, [%0+8];", "and.b32 t, %1, hcm;", "setp.eq.u32 pact, t, hcm;", "@!pact bra.uni V4SKIP;"]
         lines.append("V4L%d:" % i)
         lines += pre + ADVANCE_HDR + b + DISPATCH
+    # controlled entries: small stubs kept apart from the bodies (a stub falling through into its body made ptxas
+    # clone the bodies: 70k instead of 16k SASS instructions, and the instruction cache felt it)
+    for i in range(n_gate_ops):
+        lines.append("V4C%d:" % i)
+        lines += ["ld.shared.u32 hcm, [%0+8];", "and.b32 t, %1, hcm;", "setp.eq.u32 pact, t, hcm;", "@!pact bra.uni V4SKIP;",
+                  "bra.uni V4L%d;" % i]
     # a controlled gate whose control is off: on to the next record (header, all coefficient pairs, jump)
     lines.append("V4SKIP:")
     lines += ADVANCE_HDR + LOAD_PAIR + DISPATCH
