@@ -63,7 +63,7 @@ enum {
     QM_OPT_FUSE       = 3,  /* 0: planner emits one pass per gate (debug), 1: fuse (default)                      */
     QM_OPT_REMAP      = 4,  /* 1: planner may relabel qubits inside a pass (logical->physical permutation)        */
     QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel                     */
-    QM_OPT_MAX_COST   = 6,  /* planner: budget of a pass = gate costs (FP64 FMAs per amplitude + 1) + 38 per register-block group; default 90, 0 = no cap */
+    QM_OPT_MAX_COST   = 6,  /* planner: budget of a pass = gate costs (FP64 FMAs per amplitude + 1) + 18 per register-block group (planner.hpp gate_cost); default 85, 0 = no cap */
     QM_OPT_TIME_PASSES = 7  /* 1: CUDA events around every fused pass, read back with qm_pass_times (diagnostics) */
 };
 
@@ -226,7 +226,8 @@ int32_t qm_last_error(char* buf, int32_t cap);
 int32_t qm_counters(qm_state* st, qm_counters_t* out);
 int32_t qm_counters_reset(qm_state* st);
 int32_t qm_abi_version(void);
-/* diagnostics (QM_OPT_TIME_PASSES): per fused pass since the last call, 4 floats {ms, groups, gates, planner cost};
+/* diagnostics (QM_OPT_TIME_PASSES): per fused pass since the last call, 8 floats {ms, groups, gates, planner cost,
+ * records with full FP64 cost, with a control in the register block (half cost), xor exchanges, thread-constant phases};
  * *n_passes receives the number of passes timed, at most cap_passes are written */
 int32_t qm_pass_times(qm_state* st, float* out, int32_t cap_passes, int32_t* n_passes);
 /* device-side view for harnesses that time on the library's stream (no ownership transfer) */

@@ -58,9 +58,9 @@ static const uint32_t kV4CtxAlways = 0x80000000u;
 static const int kV4MaxRecs = 240;     // gate records + SLOT prefixes + one END per group
 static const int kV4MaxGroups = 48;
 static const int kV4MaxSubs = 96;
-// planner budget units one register-block group costs on top of its gates (tools/pass_model.py: a pass takes about
-// 1.2 ms + 1.9 ms per group + 0.05 ms per unit of gate cost at 30 qubits, against 5.9 ms of HBM time)
-static const double kV4GroupCost = 38.0;
+// planner budget units (0.05 ms at 30 qubits) one register-block group costs on top of its gates, and the fixed cost
+// of a pass; see planner.hpp gate_cost for the fit
+static const double kV4GroupCost = 18.0;
 
 struct V4Rec {              // 64 bytes, read by the PTX interpreter with shared-memory broadcasts
     uint32_t op;            // opcode

@@ -209,17 +209,19 @@ inline int lower_gates(const qm_gate* gates, int ng, int nbits, const int* perm,
     return QM_OK;
 }
 
-// Planner cost model, in FP64 FMA issue slots per amplitude as the v2 kernel spends them: a rotation
-// or a phase is three shears per real pair = 3 per amplitude, a controlled gate touches half of the
-// amplitudes, an X/CNOT moves data without arithmetic; every gate also pays ~1 for its dispatch.
-// A general 2x2 (v1 kernel, or before it is split into phase*rot*phase) costs 8.
+// Planner cost model.  One unit = 0.05 ms of a pass at 30 qubits on B200 (it scales with the register size, the
+// ratios do not).  Fitted on per-pass CUDA-event times (tools/pass_model.py, ~300 compute-bound passes, rms 0.4 ms):
+//     pass ms = 2.04 + 0.89 per register-block group + 0.229 per full-cost record (an uncontrolled rotation or
+//     phase: 0.194 ms is the FP64 pipe at peak) + 0.091 per record whose control is a register-block bit
+//     + 0.136 per xor exchange (x!, cnot!) + 0.246 per thread-constant phase
+// against ~5.6 ms of HBM time.  A matrix that needs phase * rotation * phase is three records.
 inline double gate_cost(const LGate& g) {
     const bool is_x = !g.diag && g.m[0] == 0 && g.m[1] == 0 && g.m[6] == 0 && g.m[7] == 0 && g.m[2] == 1 && g.m[3] == 0 &&
                       g.m[4] == 1 && g.m[5] == 0;
     const bool real_or_rx = (g.m[1] == 0 && g.m[7] == 0) && ((g.m[3] == 0 && g.m[5] == 0) || (g.m[2] == 0 && g.m[4] == 0));
-    double c = is_x ? 0.5 : (g.diag || real_or_rx || g.slot >= 0) ? 3.0 : 8.0;
-    if (g.ctrl >= 0) c *= 0.5;
-    return c + 1.0;
+    if (is_x) return 2.7;
+    const double records = (g.diag || real_or_rx || g.slot >= 0) ? 1.0 : 3.0;
+    return records * (g.ctrl >= 0 ? 2.5 : 4.6);
 }
 
 // Commutation-aware pull: walk the not-yet-done gates in order; take a gate when no earlier
@@ -242,7 +244,7 @@ inline void pull(const std::vector<LGate>& g, const std::vector<char>& done, siz
         bool free_ = !((actsN | actsD) & blockedN) && !(actsN & blockedD);
         bool take = false;
         const uint64_t ob = (cm | (x.diag ? tm : 0ull)) & ~tile_mask;
-        if (free_ && (int)taken.size() < max_take && cost + gate_cost(x) <= max_cost &&
+        if (free_ && (int)taken.size() < max_take && (taken.empty() || cost + gate_cost(x) <= max_cost) &&
             __builtin_popcountll(outer_used | ob) <= max_outer)
             take = allowed(x);
         if (take) { taken.push_back((int)i); cost += gate_cost(x); outer_used |= ob; }

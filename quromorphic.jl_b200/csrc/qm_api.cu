@@ -436,7 +436,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
         pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
         pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
-        if (st->max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
+        if (st->max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 5.0) pl.opt.max_cost = kV4GroupCost + 5.0;
         if (smap) pl.opt.max_subs = (kV4MaxRecs - kV4MaxGroups) / 2;      // every per-state gate takes two records
     }
     pl.done.assign(pl.gates.size(), 0);
@@ -484,6 +484,20 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
                     st->pass_desc.push_back((float)passes[i].groups.size());
                     st->pass_desc.push_back((float)passes[i].ngates);
                     st->pass_desc.push_back((float)passes[i].cost);
+                    // records by kind: full-cost FP64 (uncontrolled or context-controlled), half-cost (control in the
+                    // register block), xor exchanges, thread-constant phases
+                    float kinds[4] = { 0, 0, 0, 0 };
+                    if (v4_of[i] >= 0) {
+                        const V4Program& pr = v4progs[v4_of[i]];
+                        for (int r = 0; r < pr.nrecs; ++r) {
+                            uint32_t op = pr.recs[r].op;
+                            if (op >= (uint32_t)V4_NUM_GATE_OPS) { if (op >= (uint32_t)V4_OP_SLOT) continue; op -= V4_NUM_GATE_OPS; }
+                            int fam, var, B, CB;
+                            if (!emu_decode(op, fam, var, B, CB)) continue;
+                            if (fam == 3) kinds[2] += 1; else if (fam == 4) kinds[3] += 1; else if (CB >= 0) kinds[1] += 1; else kinds[0] += 1;
+                        }
+                    }
+                    for (int q = 0; q < 4; ++q) st->pass_desc.push_back(kinds[q]);
                 }
             }
         }
@@ -1011,7 +1025,7 @@ extern "C" int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, in
         pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
         pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
         pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
-        if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
+        if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 5.0) pl.opt.max_cost = kV4GroupCost + 5.0;
     }
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
@@ -1100,7 +1114,7 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
     pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
     pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
-    if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
+    if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 5.0) pl.opt.max_cost = kV4GroupCost + 5.0;
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
     prepare_for_lifting(pl.gates);
@@ -1120,7 +1134,7 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     return QM_OK;
 }
 
-// Diagnostics (QM_OPT_TIME_PASSES): per fused pass since the last call {ms, groups, gates, planner cost}.
+// Diagnostics (QM_OPT_TIME_PASSES): per fused pass since the last call {ms, groups, gates, planner cost, records: full, half, xor, thr}.
 extern "C" int32_t qm_pass_times(qm_state* st, float* out, int32_t cap_passes, int32_t* n_passes) {
     if (!st || !n_passes) return set_err(QM_ERR_ARG, "null argument");
     QM_TRY(qm_sync(st));
@@ -1129,7 +1143,7 @@ extern "C" int32_t qm_pass_times(qm_state* st, float* out, int32_t cap_passes, i
     for (int i = 0; i < n; ++i) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, st->pass_events[2 * i], st->pass_events[2 * i + 1]));
-        if (out && i < cap_passes) { out[4 * i] = ms; out[4 * i + 1] = st->pass_desc[3 * i]; out[4 * i + 2] = st->pass_desc[3 * i + 1]; out[4 * i + 3] = st->pass_desc[3 * i + 2]; }
+        if (out && i < cap_passes) { out[8 * i] = ms; for (int q = 0; q < 7; ++q) out[8 * i + 1 + q] = st->pass_desc[7 * i + q]; }
         cudaEventDestroy(st->pass_events[2 * i]); cudaEventDestroy(st->pass_events[2 * i + 1]);
     }
     st->pass_events.clear(); st->pass_desc.clear();
@@ -1148,7 +1162,7 @@ extern "C" int32_t qm_plan_ophist(int32_t n_qubits, int32_t tile_bits, int32_t l
     pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
     pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
     pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
-    if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 9.0) pl.opt.max_cost = kV4GroupCost + 9.0;
+    if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 5.0) pl.opt.max_cost = kV4GroupCost + 5.0;
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
     prepare_for_lifting(pl.gates);

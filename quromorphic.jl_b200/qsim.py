@@ -148,8 +148,8 @@ class B200State:
         return {k: getattr(c, k) for k, _ in L.Counters._fields_}
 
     def pass_times(self, cap=65536):
-        """diagnostics (OPT_TIME_PASSES): array [npasses, 4] of {ms, groups, gates, planner cost}"""
-        out = np.zeros((cap, 4), dtype=np.float32)
+        """diagnostics (OPT_TIME_PASSES): array [npasses, 8] of {ms, groups, gates, planner cost, records: full, half, xor, thr}"""
+        out = np.zeros((cap, 8), dtype=np.float32)
         n = C.c_int32()
         L.check(L.lib().qm_pass_times(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
         return out[:min(n.value, cap)].copy()

@@ -54,6 +54,11 @@ def main():
         pred = A @ coef
         print(json.dumps({"compute_bound_passes": int(len(R)), "fit_ms = a + g*groups + s*gates + f*fp64_per_amp": [float(x) for x in coef],
                           "rms_residual_ms": float(np.sqrt(np.mean((pred - R[:, 0]) ** 2)))}), flush=True)
+        A = np.stack([np.ones(len(R)), R[:, 1], R[:, 4], R[:, 5], R[:, 6], R[:, 7]], axis=1)
+        coef, res, *_ = np.linalg.lstsq(A, R[:, 0], rcond=None)
+        pred = A @ coef
+        print(json.dumps({"fit_ms = a + g*groups + full + half + xor + thr (per record)": [float(x) for x in coef],
+                          "rms_residual_ms": float(np.sqrt(np.mean((pred - R[:, 0]) ** 2)))}), flush=True)
     st.close()
 
 
