@@ -63,7 +63,7 @@ enum {
     QM_OPT_FUSE       = 3,  /* 0: planner emits one pass per gate (debug), 1: fuse (default)                      */
     QM_OPT_REMAP      = 4,  /* 1: planner may relabel qubits inside a pass (logical->physical permutation)        */
     QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel                     */
-    QM_OPT_MAX_COST   = 6,  /* planner: budget of a pass = gate costs (FP64 FMAs per amplitude + 1) + 18 per register-block group (planner.hpp gate_cost); default 85, 0 = no cap */
+    QM_OPT_MAX_COST   = 6,  /* planner: budget of a pass = gate costs (FP64 FMAs per amplitude + 1) + 18 per register-block group (planner.hpp gate_cost); default 75, 0 = no cap */
     QM_OPT_TIME_PASSES = 7  /* 1: CUDA events around every fused pass, read back with qm_pass_times (diagnostics) */
 };
 

@@ -38,7 +38,7 @@ struct qm_state {
     std::vector<cudaEvent_t> pass_events;      // 2 per timed pass, resolved by qm_pass_times
     std::vector<float> pass_desc;              // per timed pass: groups, records, planner cost
     int tile_bits = 0, low_bits = 5;     // tile_bits 0 = automatic (12)
-    double max_cost = 85.0;  // per-pass budget of the planner cost model (gate costs + 18 per register-block group, planner.hpp); 0 = unlimited
+    double max_cost = 75.0;  // per-pass budget of the planner cost model (gate costs + 18 per register-block group, planner.hpp); 0 = unlimited
     // queue
     std::vector<qm_gate> queue;
     // logical -> physical qubit map (identity unless a sharded remap happened)
