@@ -7,7 +7,7 @@ on that small matrix on the host, exactly as QInfo.jl does (eigen-decomposition,
 """
 import numpy as np
 
-from .qsim import B200State
+from .qsim import B200Density, B200State
 
 
 def partial_trace(s, dim_A, dim_B, subsystem, batch_idx=0):
@@ -63,3 +63,101 @@ def min_entropy(rho):
     """QInfo.jl:353-357"""
     rho = (rho + rho.conj().T) / 2
     return float(-np.log2(np.max(np.linalg.eigvalsh(rho))))
+
+
+# ---- the remaining QInfo measures (SURVEY.md §8f N4): host post-processing of SMALL matrices, as in the reference.
+# They take numpy matrices — a reduced density matrix returned by the engine (partial_trace / reduced_density) or
+# B200Density.to_numpy() — so that every QInfo function of the reference has its counterpart.
+
+def _herm(rho):
+    rho = np.asarray(rho, dtype=np.complex128)
+    return (rho + rho.conj().T) / 2
+
+
+def _herm_pow(rho, alpha):
+    w, v = np.linalg.eigh(rho)
+    return (v * np.power(w.astype(np.complex128), alpha)) @ v.conj().T
+
+
+def partial_trace_matrix(rho, dim_A, dim_B, subsystem):
+    """partial_trace(rho, dim_A, dim_B, subsystem) of a host matrix, QInfo.jl:381-405 (A = high-order factor)"""
+    rho = np.asarray(rho, dtype=np.complex128)
+    if rho.shape != (dim_A * dim_B, dim_A * dim_B):
+        raise AssertionError("Dimension mismatch")
+    r = _herm(rho).reshape(dim_A, dim_B, dim_A, dim_B)
+    return np.einsum("kikj->ij", r) if subsystem == 1 else np.einsum("iljl->ij", r)
+
+
+def _joint(x):
+    """a joint state given as a host matrix, a B200Density, or a (pure) B200State"""
+    if isinstance(x, B200Density):
+        return x.to_numpy()
+    if isinstance(x, B200State):
+        v = x.to_numpy()
+        return np.outer(v, v.conj())
+    return np.asarray(x, dtype=np.complex128)
+
+
+def quantum_mutual_information(rho_AB, dim_A, dim_B):
+    """QInfo.jl:68-73: S(A) + S(B) - S(AB)"""
+    r = _herm(_joint(rho_AB))
+    return (von_neumann_entropy(partial_trace_matrix(r, dim_A, dim_B, 2)) + von_neumann_entropy(partial_trace_matrix(r, dim_A, dim_B, 1))
+            - von_neumann_entropy(r))
+
+
+def conditional_quantum_entropy(rho_AB, dim_A, dim_B):
+    """QInfo.jl:91-95: S(AB) - S(B)"""
+    r = _herm(_joint(rho_AB))
+    return von_neumann_entropy(r) - von_neumann_entropy(partial_trace_matrix(r, dim_A, dim_B, 1))
+
+
+def coherent_information(rho_AB, dim_A, dim_B):
+    """QInfo.jl:113-117: S(B) - S(AB)"""
+    r = _herm(_joint(rho_AB))
+    return von_neumann_entropy(partial_trace_matrix(r, dim_A, dim_B, 1)) - von_neumann_entropy(r)
+
+
+def relative_entropy(rho, sigma):
+    """QInfo.jl:134-138: Tr(rho log2 rho) - Tr(rho log2 sigma)"""
+    rho, sigma = _herm(rho), _herm(sigma)
+    return float(np.real(np.trace(rho @ matrix_log2(rho)) - np.trace(rho @ matrix_log2(sigma))))
+
+
+def holevo_information(states, probs):
+    """QInfo.jl:155-160"""
+    assert abs(sum(probs) - 1.0) < 1e-10, "Probabilities must sum to 1"
+    avg = sum(p * np.asarray(r, dtype=np.complex128) for p, r in zip(probs, states))
+    return von_neumann_entropy(avg) - sum(p * von_neumann_entropy(np.asarray(r, dtype=np.complex128)) for p, r in zip(probs, states))
+
+
+def quantum_relative_renyi_entropy(rho, sigma, alpha):
+    """QInfo.jl:222-227"""
+    assert alpha != 1.0, "Relative Rényi entropy undefined for α=1"
+    rho, sigma = _herm(rho), _herm(sigma)
+    return float((1 / (alpha - 1)) * np.log2(np.real(np.trace(_herm_pow(rho, alpha) @ _herm_pow(sigma, 1 - alpha)))))
+
+
+def quantum_fisher_information(psi, dpsi):
+    """QInfo.jl:244-246: 4 (<dpsi|dpsi> - |<psi|dpsi>|^2)"""
+    psi, dpsi = np.asarray(psi, dtype=np.complex128), np.asarray(dpsi, dtype=np.complex128)
+    return float(4 * np.real(np.vdot(dpsi, dpsi) - abs(np.vdot(psi, dpsi)) ** 2))
+
+
+def l1_norm_coherence(rho):
+    """QInfo.jl:262-272: sum of |rho_ij| over i != j"""
+    r = _herm(_joint(rho))
+    return float(np.sum(np.abs(r)) - np.sum(np.abs(np.diag(r))))
+
+
+def fidelity(rho, sigma):
+    """QInfo.jl:289-294: (Tr sqrt(sqrt(rho) sigma sqrt(rho)))^2"""
+    rho, sigma = _herm(_joint(rho)), _herm(_joint(sigma))
+    sr = _herm_pow(rho, 0.5)
+    w = np.linalg.eigvalsh(_herm(sr @ sigma @ sr))
+    return float(np.real(np.sum(np.sqrt(w.astype(np.complex128)))) ** 2)
+
+
+def trace_distance(rho, sigma):
+    """QInfo.jl:311-316: half the sum of |eigenvalues| of rho - sigma"""
+    d = _herm(_joint(rho)) - _herm(_joint(sigma))
+    return float(0.5 * np.sum(np.abs(np.linalg.eigvalsh(d))))

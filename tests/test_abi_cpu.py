@@ -161,3 +161,44 @@ def test_gate_list_files_round_trip_bit_exactly(pkg, tmp_path):
         bad = tmp_path / "bad.qmg"
         bad.write_bytes(b"QMGATES1" + np.array([12, 5], dtype="<u4").tobytes() + b"x" * 7)
         C.load_gates(str(bad))
+
+
+def test_host_qinfo_measures_match_reference_known_answers(pkg):
+    """the QInfo measures that stay on the host (small matrices), against the assertions of test/test_QInfo.jl"""
+    QI = pkg.qinfo
+    ap = lambda v: pytest.approx(v, abs=1e-10)
+    bell = np.array([1, 0, 0, 1]) / np.sqrt(2)
+    rho_bell = np.outer(bell, bell).astype(np.complex128)
+    assert QI.quantum_mutual_information(rho_bell, 2, 2) == ap(2.0)                       # TI:61-64
+    assert QI.quantum_mutual_information(np.diag([0.5, 0.5, 0, 0]).astype(complex), 2, 2) == ap(0.0)   # TI:67-71
+    assert QI.conditional_quantum_entropy(rho_bell, 2, 2) == ap(-1.0)                     # TI:76-79
+    assert QI.conditional_quantum_entropy(np.diag([1.0, 0, 0, 0]).astype(complex), 2, 2) == ap(0.0)    # TI:82-86
+    assert QI.coherent_information(rho_bell, 2, 2) == ap(1.0)                             # TI:91-94
+    rho, sig = np.diag([0.7, 0.3]).astype(complex), np.diag([0.5, 0.5]).astype(complex)
+    D = QI.relative_entropy(rho, sig)                                                     # TI:99-110
+    assert D >= 0 and QI.relative_entropy(rho, rho) == ap(0.0)
+    assert D == ap(0.7 * np.log2(0.7 / 0.5) + 0.3 * np.log2(0.3 / 0.5))
+    r1, r2 = np.diag([1.0, 0]).astype(complex), np.diag([0, 1.0]).astype(complex)
+    assert QI.holevo_information([r1, r2], [0.5, 0.5]) == ap(1.0)                         # TI:115-121
+    assert QI.holevo_information([r1, r1], [0.5, 0.5]) == ap(0.0)                         # TI:124-125
+    assert QI.quantum_relative_renyi_entropy(rho, sig, 2.0) >= 0                          # TI:149-150
+    assert QI.quantum_relative_renyi_entropy(rho, rho, 2.0) == ap(0.0)                    # TI:153
+    with pytest.raises(AssertionError):
+        QI.quantum_relative_renyi_entropy(rho, sig, 1.0)                                  # TI:156
+    th = np.pi / 4                                                                        # TI:161-167
+    assert QI.quantum_fisher_information([np.cos(th / 2), np.sin(th / 2)], [-np.sin(th / 2) / 2, np.cos(th / 2) / 2]) == ap(1.0)
+    assert QI.quantum_fisher_information([1.0, 0.0], [0.0, 0.0]) == ap(0.0)               # TI:170-172
+    assert QI.l1_norm_coherence(np.full((2, 2), 0.5, dtype=complex)) == ap(1.0)           # TI:177-178
+    assert QI.l1_norm_coherence(rho) == ap(0.0)                                           # TI:181-182
+    assert QI.l1_norm_coherence(np.array([[0.6, 0.2], [0.2, 0.4]], dtype=complex)) == ap(0.4)   # TI:185-186
+    assert QI.l1_norm_coherence(np.array([[0.5, 0.3j], [-0.3j, 0.5]])) == ap(0.6)         # TI:326-329
+    sw = np.diag([0.3, 0.7]).astype(complex)
+    assert QI.fidelity(rho, rho) == ap(1.0)                                               # TI:191-192
+    assert QI.fidelity(rho, sw) == pytest.approx(0.84, abs=0.01)                          # TI:195-198
+    assert QI.fidelity(r1, r2) == ap(0.0) and QI.fidelity(r1, r1) == ap(1.0)              # TI:201-206
+    assert QI.trace_distance(rho, rho) == ap(0.0) and QI.trace_distance(rho, sw) == ap(0.4)     # TI:211-218
+    assert QI.trace_distance(r1, r2) == ap(1.0)                                           # TI:221-223
+    # GHZ on 3 qubits, 2 x 4 split (TI:298-308): the reduced state of the first factor is mixed
+    ghz = np.zeros(8); ghz[0] = ghz[7] = 1 / np.sqrt(2)
+    rA = QI.partial_trace_matrix(np.outer(ghz, ghz), 2, 4, 2)
+    assert rA.shape == (2, 2) and QI.von_neumann_entropy(rA) > 0
