@@ -71,8 +71,6 @@ inline bool emulate_v4(const V4Program& prog, const PlanPass& P, EmuAmp* amp, in
             uint32_t bm[kV4BlockBits];
             for (int j = 0; j < NB; ++j) { const uint32_t u = G.s[j] >> 4; bm[j] = u ^ ((u >> 3) & 7u); }
             for (int w0 = 0; w0 < nthreads; w0 += 32) {
-                int warp_active = -1;           // per record the predicate must agree over the warp: checked below
-                (void)warp_active;
                 // the 32 lanes of a warp walk the record list together (the kernel's branches are .uni)
                 const V4Rec* R = reinterpret_cast<const V4Rec*>(reinterpret_cast<const unsigned char*>(&prog) + G.rec_off);
                 EmuAmp a[32][16]; uint32_t ctx[32], v[32];
