@@ -202,3 +202,24 @@ def test_host_qinfo_measures_match_reference_known_answers(pkg):
     ghz = np.zeros(8); ghz[0] = ghz[7] = 1 / np.sqrt(2)
     rA = QI.partial_trace_matrix(np.outer(ghz, ghz), 2, 4, 2)
     assert rA.shape == (2, 2) and QI.von_neumann_entropy(rA) > 0
+
+
+def test_default_budget_packs_one_full_group_per_pass_on_c3(pkg):
+    """planner quality guard (host only): at the engine's default budget the C3 workload at 30 qubits must come out
+    as passes of ONE register-block group holding >= 12 gates on average (a second group never hides
+    behind HBM time), every pass must be encodable for the TMA kernel, and tiles must be rebuilt around their targets
+    (>= 128 contiguous amplitudes per row)"""
+    L = pkg._lib
+    gates = pkg.circuits.c3_circuit(n=30, depth=20)
+    plan = L.plan_describe(30, gates, max_cost=75.0)
+    ng = np.array([p["ngates"] for p in plan]); G = np.array([len(p["groups"]) for p in plan])
+    assert ng.sum() >= 0.95 * len(gates) and ng.mean() >= 12.0
+    assert G.mean() <= 1.1 and G.max() <= 2
+    assert min(p["L"] for p in plan) >= 5 and np.mean([p["L"] for p in plan]) >= 7
+    for p in plan:
+        for rb, _ in p["groups"]:
+            assert len(rb) <= 4
+    h = L.plan_ophist(30, gates, max_cost=75.0)          # raises if a pass cannot be encoded
+    assert h["passes"] == len(plan)
+    deep = L.plan_describe(30, gates, max_cost=0.0)
+    assert len(deep) < len(plan) / 3
