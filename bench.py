@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--low-bits", type=int, default=-1)
     ap.add_argument("--max-cost", type=float, default=-1)
+    ap.add_argument("--short-pct", type=int, default=-1, help="QM_OPT_SHORT_PCT (default 180; 100 = off)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-alt", action="store_true", help="skip the deep-fusion secondary measurement")
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c4"],
@@ -238,6 +239,8 @@ def main():
         st.set_option(L.OPT_LOW_BITS, args.low_bits)
     if args.max_cost >= 0:
         st.set_option(L.OPT_MAX_COST, int(args.max_cost))
+    if args.short_pct >= 0:
+        st.set_option(L.OPT_SHORT_PCT, args.short_pct)
     import ctypes as C
     amps, stream = C.c_void_p(), C.c_void_p()
     L.check(L.lib().qm_device_ptr(st._h, C.byref(amps), C.byref(stream)))

@@ -29,6 +29,8 @@ def run_dist(args, pkg, rank, world, local_rank):
         st.set_option(L.OPT_TILE_BITS, args.tile_bits)
     if args.max_cost >= 0:
         st.set_option(L.OPT_MAX_COST, int(args.max_cost))
+    if args.short_pct >= 0:
+        st.set_option(L.OPT_SHORT_PCT, args.short_pct)
     amps, stream = C.c_void_p(), C.c_void_p()
     L.check(L.lib().qm_device_ptr(st._h, C.byref(amps), C.byref(stream)))
     ext = torch.cuda.ExternalStream(stream.value)
@@ -95,6 +97,7 @@ def run_dist(args, pkg, rank, world, local_rank):
             "gpu_launches": int(c["launches"]) * world, "gates_per_step": ngates / args.steps,
             "gates_per_sec_absolute": ngates / (dev_ms * 1e-3), "n_qubits": n,
             "readout_z0": [float(z[0][0]), float(z[0][1])],
+            "passes_per_step": npasses / args.steps,
         }
         if n != SHARD_QUBITS + g:
             line["config"]["workload"] += " [NON-DEFAULT size: %d qubits]" % n

@@ -17,7 +17,7 @@ SO_PATH = os.environ.get("QM_B200_LIB") or os.path.join(HERE, "libqm_b200.so")
 QM_OK, QM_ERR_ARG, QM_ERR_CUDA, QM_ERR_NOMEM, QM_ERR_NO_DEVICE, QM_ERR_STATE, QM_ERR_COMM = range(7)
 GATE_U2, GATE_CU2, GATE_SWAP, GATE_U2_SLOT = 0, 1, 2, 3
 BASIS_Z, BASIS_X, BASIS_Y = 0, 1, 2
-OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_REMAP, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES = range(8)
+OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_REMAP, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = range(9)
 
 GATE_DTYPE = np.dtype([("kind", np.int32), ("q0", np.int32), ("q1", np.int32), ("flags", np.int32),
                        ("m", np.float64, (8,))])

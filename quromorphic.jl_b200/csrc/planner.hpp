@@ -117,6 +117,9 @@ struct PlanOptions {
     int block_bits = kBlockBits;     // register-block bits of a group (3: general kernel, 4: TMA kernel)
     bool retile = false;             // rebuild the tile around the targets once the gates of a pass are known (TMA kernel)
     double group_cost = 0.0;         // budget units one register-block group costs on top of its gates (TMA kernel: 38)
+    double short_mult = 1e9;         // circuits shorter than the window may use up to short_mult x the budget (Planner::budget_for_pending)
+    double hbm_units = 114.0;        // fitted pass model in budget units (0.05 ms at 30 qubits): HBM time of a pass,
+    double fixed_units = 41.0;       // compute-side time = fixed_units + group_cost per group + gate costs
     bool warp_uniform_ctrl = false;  // controls inside the tile must be block bits or one of the (m - block_bits - 5) warp-index bits
 };
 
@@ -260,6 +263,8 @@ struct Planner {
     std::vector<LGate> gates;
     std::vector<char> done;
     size_t first = 0;
+    double budget_now = 0.0;         // budget of the passes being built (budget_for_pending)
+    bool budget_fixed = false, mode_known = false, short_circuit = false;
 
     int total_bits() const { return opt.n_local + opt.n_global; }
 
@@ -370,8 +375,9 @@ struct Planner {
             return true;
         }
         uint64_t tmask = ~0ull;
+        if (!budget_fixed) budget_now = budget_for_pending();
         choose_tile(m, L, hb, best, tmask);
-        if (best <= 0) return false;
+        if (best <= 0) { budget_fixed = false; return false; }     // end of a stretch (a remap follows): choose again
         std::vector<int> taken;
         build_pass(m, L, hb, P, taken, tmask);
         for (int i : taken) done[i] = 1;
@@ -442,11 +448,52 @@ struct Planner {
     // (tools/pass_model.py): a pass costs about 1.2 ms + 1.9 ms per group + 0.05 ms per cost unit against 5.9 ms
     // of HBM time, i.e. one register-block group is worth ~38 cost units — a pass with ONE well-filled group stays
     // on the HBM roofline, a second group almost never does.
+    //
+    // Short circuits: the budget keeps a pass at HBM time, which is the right trade when the circuit is deep enough
+    // to fill one register block per pass (C3: 13-14 gates).  A reservoir step is not — 2-4 gates per qubit, then a
+    // readout — so every block leaves most of the HBM time idle, yet each block costs a whole pass.  When the whole
+    // circuit fits the look-ahead window, the planner therefore plans what is pending at a few multiples of the
+    // budget and keeps the one the fitted pass model (PlanOptions::hbm_units etc.) says finishes first: typically two
+    // blocks per pass at ~1.3x the pass time instead of twice the passes.  Deep circuits keep the budget as it is.
+    double predicted_units(const PlanPass& P) const {
+        return std::max(opt.hbm_units, opt.fixed_units + opt.group_cost * (double)P.groups.size() + P.cost);
+    }
+
+    double budget_for_pending() {
+        if (opt.group_cost <= 0 || opt.short_mult <= 1.0 || opt.max_cost > 1e20) { budget_fixed = true; return opt.max_cost; }
+        if (!mode_known) {
+            size_t pending = 0;
+            for (size_t i = first; i < gates.size(); ++i) pending += !done[i];
+            short_circuit = (int)pending < opt.window;
+            mode_known = true;
+        }
+        budget_fixed = true;
+        if (!short_circuit) return opt.max_cost;
+        static const double mults[] = {1.0, 1.35, 1.8, 2.5, 4.0, 1e9};
+        double best_t = 1e300, best_b = opt.max_cost;
+        for (double mu : mults) {
+            if (mu > opt.short_mult) mu = opt.short_mult;
+            Planner trial = *this;
+            trial.budget_now = std::min(mu * opt.max_cost, 1e30);
+            double t = 0.0, work = 0.0; PlanPass P;
+            while (trial.next_pass(P)) { t += predicted_units(P); work += P.cost; }
+            if (work <= 0.0) break;
+            if (t / work < 0.99 * best_t) { best_t = t / work; best_b = trial.budget_now; }
+            if (mu >= opt.short_mult) break;
+        }
+        return best_b;
+    }
+
     void build_pass(int m, int L, const std::vector<int>& hb, PlanPass& P, std::vector<int>& taken_out,
                     uint64_t target_mask = ~0ull) const {
+        build_pass_at(budget_now > 0 ? budget_now : opt.max_cost, m, L, hb, P, taken_out, target_mask);
+    }
+
+    void build_pass_at(double max_cost, int m, int L, const std::vector<int>& hb, PlanPass& P, std::vector<int>& taken_out,
+                       uint64_t target_mask = ~0ull) const {
         uint64_t tilemask = (1ull << L) - 1; for (int b : hb) tilemask |= 1ull << b;
         const uint64_t tgt = tilemask & target_mask;
-        const double gate_budget = opt.max_cost > opt.group_cost + 1.0 ? opt.max_cost - opt.group_cost : 1.0;
+        const double gate_budget = max_cost > opt.group_cost + 1.0 ? max_cost - opt.group_cost : 1.0;
         int max_take = opt.max_subs;
         taken_out.clear();
         while (true) {
@@ -501,11 +548,11 @@ struct Planner {
             for (size_t g = 0; g < P.groups.size(); ++g) {
                 double gc = opt.group_cost;
                 for (const LGate& x : P.groups[g].subs) gc += gate_cost(x);
-                if (g > 0 && est + gc > opt.max_cost) break;
+                if (g > 0 && est + gc > max_cost) break;
                 bool cut = false;
-                if (g == 0 && gc > opt.max_cost) {
+                if (g == 0 && gc > max_cost) {
                     double c = opt.group_cost; size_t nk = 0;
-                    for (const LGate& x : P.groups[0].subs) { if (nk > 0 && c + gate_cost(x) > opt.max_cost) break; c += gate_cost(x); ++nk; }
+                    for (const LGate& x : P.groups[0].subs) { if (nk > 0 && c + gate_cost(x) > max_cost) break; c += gate_cost(x); ++nk; }
                     P.groups[0].subs.resize(nk); gidx[0].resize(nk);
                     gc = c; cut = true;
                 }

@@ -136,6 +136,9 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
     case QM_OPT_PIPELINE: st->pipeline = value != 0; break;
     case QM_OPT_MAX_COST: st->max_cost = (double)value; break;
     case QM_OPT_TIME_PASSES: st->time_passes = value != 0; break;
+    case QM_OPT_SHORT_PCT:
+        if (value != 0 && value < 100) return set_err(QM_ERR_ARG, "short-circuit per cent must be 0 (no limit) or >= 100");
+        st->short_mult = value == 0 ? 1e9 : (double)value / 100.0; break;
     default: return set_err(QM_ERR_ARG, "unknown option %d", key);
     }
     return QM_OK;
@@ -414,6 +417,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     pl.opt.n_local = st->nl; pl.opt.n_global = st->g;
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = st->low_bits; pl.opt.fuse = st->fuse;
     if (st->max_cost > 0) pl.opt.max_cost = st->max_cost < 9.0 ? 9.0 : st->max_cost;
+    pl.opt.short_mult = st->short_mult;
     std::vector<PlanPass> passes;          // of the current segment (between remaps)
     std::vector<unsigned char> blob;
     std::vector<size_t> offs;

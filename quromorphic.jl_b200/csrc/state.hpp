@@ -38,6 +38,7 @@ struct qm_state {
     std::vector<cudaEvent_t> pass_events;      // 2 per timed pass, resolved by qm_pass_times
     std::vector<float> pass_desc;              // per timed pass: groups, records, planner cost
     int tile_bits = 0, low_bits = 5;     // tile_bits 0 = automatic (12)
+    double short_mult = 1e9;    // QM_OPT_SHORT_PCT / 100 (planner.hpp budget_for_pending); 1e9 = no limit
     double max_cost = 75.0;  // per-pass budget of the planner cost model (gate costs + 18 per register-block group, planner.hpp); 0 = unlimited
     // queue
     std::vector<qm_gate> queue;

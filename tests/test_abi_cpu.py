@@ -223,3 +223,26 @@ def test_default_budget_packs_one_full_group_per_pass_on_c3(pkg):
     assert h["passes"] == len(plan)
     deep = L.plan_describe(30, gates, max_cost=0.0)
     assert len(deep) < len(plan) / 3
+
+
+def test_short_circuit_is_planned_at_the_budget_that_finishes_first(pkg):
+    """A reservoir step (C4: 2-3 gates per qubit, then a readout) cannot fill one register block per pass; a circuit
+    shorter than the look-ahead window is planned at the multiple of the budget the pass model says finishes first
+    (planner.hpp budget_for_pending): the 33-qubit step must come out in <= 5 passes instead of 10-11 and the batched
+    16-qubit step (C2) in <= 3 instead of 7, a deep circuit (C3) must keep its single-block passes, and the encoded
+    programs of such steps must reproduce the oracle (host emulation, consecutive steps on one register)"""
+    L = pkg._lib
+    for s in range(3):
+        plan = L.plan_describe(33, pkg.circuits.c4_step(33, s), max_cost=75.0)
+        assert sum(p["ngates"] for p in plan) >= 75
+        assert len(plan) <= 5 and max(len(p["groups"]) for p in plan) >= 2
+    assert len(L.plan_describe(16, pkg.circuits.c2_step_gates(16), max_cost=75.0)) <= 3
+    n = 15
+    psi = O.random_state(n, 77)
+    ref = psi.copy()
+    for s in range(3):
+        gates = pkg.circuits.c4_step(n, s)
+        psi, npass = L.plan_emulate(n, gates, psi, max_cost=75.0)
+        ref = O.apply_circuit(ref, gates)
+        assert npass <= 2
+        assert np.max(np.abs(psi - ref)) / np.max(np.abs(ref)) < 1e-12
