@@ -16,7 +16,7 @@ using namespace qm;
 
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { kNcclSum = 0, kNcclFloat64 = 8 };
+enum { kNcclSum = 0, kNcclUint64 = 5, kNcclFloat64 = 8 };
 
 struct NcclApi {
     void* h = nullptr;
@@ -26,6 +26,7 @@ struct NcclApi {
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -40,7 +41,7 @@ static int nccl_load() {
     if (!h) return set_err(QM_ERR_COMM, "cannot dlopen libnccl.so.2 (set QM_NCCL_LIB): %s", dlerror());
 #define LOADSYM(field, sym) do { *(void**)(&g_nccl.field) = dlsym(h, sym); if (!g_nccl.field) return set_err(QM_ERR_COMM, "libnccl: missing %s", sym); } while (0)
     LOADSYM(GetUniqueId, "ncclGetUniqueId"); LOADSYM(CommInitRank, "ncclCommInitRank"); LOADSYM(CommDestroy, "ncclCommDestroy");
-    LOADSYM(Send, "ncclSend"); LOADSYM(Recv, "ncclRecv"); LOADSYM(AllReduce, "ncclAllReduce");
+    LOADSYM(Send, "ncclSend"); LOADSYM(Recv, "ncclRecv"); LOADSYM(AllReduce, "ncclAllReduce"); LOADSYM(AllGather, "ncclAllGather");
     LOADSYM(GroupStart, "ncclGroupStart"); LOADSYM(GroupEnd, "ncclGroupEnd"); LOADSYM(GetErrorString, "ncclGetErrorString");
 #undef LOADSYM
     g_nccl.h = h;
@@ -255,8 +256,66 @@ int dist_measure(qm_state* st, int t0, double thr, const double* R, double out[2
     return QM_OK;
 }
 
-int dist_reduced_density(qm_state*, int, int, double*) {
-    return set_err(QM_ERR_STATE, "reduced density of a sharded register is not implemented (gather the kept qubits first)");
+// Reduced density of a sharded register.  Keeping the LOW k qubits: once they sit on local bits 0..k-1 every rank
+// holds whole rows of Psi (A = the other qubits, rank bits included), so rho_B is the sum over ranks of the local
+// Psi^T conj(Psi) — the single-device kernel on the shard, then one all-reduce of 4^k entries (QInfo.jl:385-391
+// with rho = psi psi').  Keeping the HIGH k qubits would need products of amplitudes that live on different ranks;
+// the kept qubits are first swapped with the low ones (bit-exact exchanges through the ordinary circuit path,
+// remaps included), which turns the request into the case above with the same index order, and swapped back.
+int dist_reduced_density(qm_state* st, int keep_low, int k, double* out) {
+    DistCtx* d = st->dist;
+    if (k > st->nl) return set_err(QM_ERR_ARG, "Dimension mismatch: k = %d exceeds the %d local bits of a sharded register", k, st->nl);
+    if (!keep_low) {
+        if (2 * k > st->n) return set_err(QM_ERR_ARG, "sharded register: keeping the high k qubits needs k <= n/2 (k = %d, n = %d)", k, st->n);
+        for (int j = 0; j < k; ++j) QM_TRY(qm_apply_swap(st, st->n - k + j, j));
+        const int rc = dist_reduced_density(st, 1, k, out);
+        for (int j = 0; j < k; ++j) QM_TRY(qm_apply_swap(st, st->n - k + j, j));     // queued; runs with the next circuit
+        return rc;
+    }
+    QM_TRY(qm_flush(st));
+    CU(cudaSetDevice(st->device));
+    bool home = true; for (int j = 0; j < k; ++j) home = home && st->perm[j] == j;
+    if (!home) {
+        QM_TRY(dist_canonicalize(st));
+        for (int j = 0; j < k; ++j) if (st->perm[j] != j) return set_err(QM_ERR_STATE, "kept qubit %d is not on its home bit", j);
+    }
+    double2* d_out = nullptr;
+    QM_TRY(qm_reduced_local(st, 1, k, 0, &d_out));
+    const size_t entries = (size_t)1 << (2 * k);
+    NC(g_nccl.AllReduce(d_out, d_out, entries * 2, kNcclFloat64, kNcclSum, d->comm, st->stream));
+    CU(cudaMemcpyAsync(st->h_scratch, d_out, entries * 16, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += entries * 16;
+    QM_TRY(qm_sync(st));
+    memcpy(out, st->h_scratch, entries * 16);
+    return QM_OK;
+}
+
+// Sampler of a sharded register, bit for bit the single-device one (oracle/qsim_oracle.c orc_sample): in canonical
+// layout the leaves (4096 consecutive amplitudes) of rank r are leaves r * 2^(nl-12) ... of the whole register.  Every
+// rank sums its own leaves, the level-1 array is all-gathered (<= 2^(n-12) doubles: 128 MiB at 36 qubits), every rank
+// rebuilds the upper levels and walks every shot down to its leaf identically; the rank that owns the leaf finishes
+// inside it, the others contribute 0 to a sum over ranks.
+int dist_sample(qm_state* st, uint64_t seed, int nshots, uint64_t* out) {
+    DistCtx* d = st->dist;
+    if (st->nl < 12) return set_err(QM_ERR_STATE, "sampling a sharded register needs >= 12 local bits");
+    QM_TRY(qm_flush(st));
+    CU(cudaSetDevice(st->device));
+    QM_TRY(dist_canonicalize(st));
+    const uint64_t n1l = local_amps(st) >> 12, n1 = n1l * (uint64_t)st->world;
+    const uint64_t n2 = (n1 + 4095) >> 12, n3 = (n2 + 4095) >> 12;
+    QM_TRY(ENSURE_DEV(st, d_scratch, (n1 + n2 + n3) * 8 + (size_t)nshots * 8 + 64));
+    QM_TRY(ENSURE_PIN(st, h_scratch, (size_t)nshots * 8));
+    double* s1 = st->d_scratch;
+    uint64_t* d_out = reinterpret_cast<uint64_t*>(s1 + n1 + n2 + n3);
+    QM_TRY(qm_sample_leaves(st, 0, s1 + (uint64_t)st->rank * n1l));
+    NC(g_nccl.AllGather(s1 + (uint64_t)st->rank * n1l, s1, (size_t)n1l, kNcclFloat64, d->comm, st->stream));
+    QM_TRY(qm_sample_descend(st, 0, s1, n1, (uint64_t)st->rank * n1l, seed, nshots, s1 + n1, d_out));
+    NC(g_nccl.AllReduce(d_out, d_out, (size_t)nshots, kNcclUint64, kNcclSum, d->comm, st->stream));
+    CU(cudaMemcpyAsync(st->h_scratch, d_out, (size_t)nshots * 8, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += (size_t)nshots * 8;
+    QM_TRY(qm_sync(st));
+    memcpy(out, st->h_scratch, (size_t)nshots * 8);
+    return QM_OK;
 }
 
 // ---- peer-memory mapping (CUDA IPC): every rank exports its shard, the host all-gathers the 64-byte

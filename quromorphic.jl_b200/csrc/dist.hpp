@@ -14,6 +14,7 @@ int  dist_finish_z(qm_state* st, const double* pairs, const double* tot, double*
 int  dist_finish_norm(qm_state* st, double local_tot, double* out);
 int  dist_measure(qm_state* st, int t0, double thr, const double* R, double out[2]);
 int  dist_reduced_density(qm_state* st, int keep_low, int k, double* out);
+int  dist_sample(qm_state* st, uint64_t seed, int nshots, uint64_t* out);
 
 // pure index logic of a remap, shared by the GPU path and the host-only planner introspection:
 // physical bit b in [nl-g, nl) <-> b + g

@@ -520,7 +520,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 __global__ void __launch_bounds__(128)
 k_sample(const double2* __restrict__ amp, uint64_t N, const double* __restrict__ s1, uint64_t n1,
          const double* __restrict__ s2, uint64_t n2, const double* __restrict__ s3, uint64_t n3,
-         uint64_t seed, int nshots, uint64_t* __restrict__ out) {
+         uint64_t seed, int nshots, uint64_t* __restrict__ out, uint64_t leaf_lo, uint64_t leaf_cnt) {
     const int sh = blockIdx.x * blockDim.x + threadIdx.x;
     if (sh >= nshots) return;
     double total = 0.0;
@@ -536,8 +536,12 @@ k_sample(const double2* __restrict__ amp, uint64_t N, const double* __restrict__
     uint64_t i1 = i2 * kLeaf, e1 = (i2 + 1) * kLeaf < n1 ? (i2 + 1) * kLeaf : n1;
     for (; i1 + 1 < e1; ++i1) { const double t = __dadd_rn(acc, s1[i1]); if (t > r) break; acc = t; }
     r = __dadd_rn(r, -acc); acc = 0.0;
+    // sharded registers: `amp` is this rank's slice (leaves leaf_lo .. leaf_lo + leaf_cnt of the whole register, N
+    // amplitudes in all); the rank that owns the leaf finishes the descent, the others report 0 (summed over ranks)
+    if (i1 < leaf_lo || i1 >= leaf_lo + leaf_cnt) { out[sh] = 0; return; }
+    const double2* a = amp - leaf_lo * kLeaf;
     uint64_t i0 = i1 * kLeaf, e0 = (i1 + 1) * kLeaf < N ? (i1 + 1) * kLeaf : N;
-    for (; i0 + 1 < e0; ++i0) { const double t = __dadd_rn(acc, abs2_exact(amp[i0])); if (t > r) break; acc = t; }
+    for (; i0 + 1 < e0; ++i0) { const double t = __dadd_rn(acc, abs2_exact(a[i0])); if (t > r) break; acc = t; }
     out[sh] = i0;
 }
 

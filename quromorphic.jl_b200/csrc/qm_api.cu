@@ -856,13 +856,7 @@ extern "C" int32_t qm_expect_all(qm_state* st, int32_t basis, double threshold, 
     return QM_OK;
 }
 
-extern "C" int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k, int32_t batch_idx, double* out) {
-    if (!st || !out) return set_err(QM_ERR_ARG, "null argument");
-    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
-    if (k < 1 || k >= st->n || k > 10) return set_err(QM_ERR_ARG, "Dimension mismatch: k = %d of n = %d (1 <= k < n, k <= 10)", k, st->n);
-    QM_TRY(flush(st));
-    CU(cudaSetDevice(st->device));
-    if (st->dist) return dist_reduced_density(st, keep_low, k, out);
+int qm_reduced_local(qm_state* st, int keep_low, int k, int batch_idx, double2** d_out_p) {
     const uint32_t d = 1u << k, T = d < 16 ? d : 16, tiles = d / T;
     const uint64_t R = 1ull << (st->nl - k);
     uint64_t xchunks = R / kRedXC; if (xchunks < 1) xchunks = 1; if (xchunks > 592) { xchunks = 512; }
@@ -879,6 +873,20 @@ extern "C" int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k,
     k_reduced_final<<<(unsigned)((entries + 255) / 256), 256, 0, st->stream>>>(d_part, (uint32_t)xchunks, (uint32_t)entries, d_out);
     CU(cudaGetLastError());
     st->ctr.launches += 2; st->ctr.bytes_hbm += 16ull * local_amps(st);
+    *d_out_p = d_out;
+    return QM_OK;
+}
+
+extern "C" int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k, int32_t batch_idx, double* out) {
+    if (!st || !out) return set_err(QM_ERR_ARG, "null argument");
+    if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
+    if (k < 1 || k >= st->n || k > 10) return set_err(QM_ERR_ARG, "Dimension mismatch: k = %d of n = %d (1 <= k < n, k <= 10)", k, st->n);
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    if (st->dist) return dist_reduced_density(st, keep_low, k, out);
+    double2* d_out = nullptr;
+    QM_TRY(qm_reduced_local(st, keep_low, k, batch_idx, &d_out));
+    const size_t entries = (size_t)1 << (2 * k);
     CU(cudaMemcpyAsync(st->h_scratch, d_out, entries * 16, cudaMemcpyDeviceToHost, st->stream));
     st->ctr.bytes_d2h += entries * 16;
     QM_TRY(qm_sync(st));
@@ -953,27 +961,49 @@ extern "C" int32_t qm_dm_measure(qm_state* rho, int32_t t0, const double* R, dou
     return QM_OK;
 }
 
+int qm_flush(qm_state* st) { return flush(st); }
+
+int qm_sample_leaves(qm_state* st, int batch_idx, double* d_s1_local) {
+    const uint64_t N = local_amps(st), n1 = (N + kLeaf - 1) / kLeaf;
+    k_leafsum<true><<<(unsigned)((n1 * 32 + 255) / 256), 256, 0, st->stream>>>(st->amp + ((uint64_t)batch_idx << st->nl), N, n1, d_s1_local);
+    CU(cudaGetLastError());
+    st->ctr.launches += 1; st->ctr.bytes_hbm += 16ull * N;
+    return QM_OK;
+}
+
+// d_levels: room for n2 + n3 doubles (the upper levels, rebuilt from the full level-1 array on every rank alike)
+int qm_sample_descend(qm_state* st, int batch_idx, const double* d_s1, uint64_t n1, uint64_t leaf_lo, uint64_t seed, int nshots,
+                      double* d_levels, uint64_t* d_out) {
+    const uint64_t n2 = (n1 + kLeaf - 1) / kLeaf, n3 = (n2 + kLeaf - 1) / kLeaf;
+    if (n3 > kLeaf) return set_err(QM_ERR_ARG, "register too large for the sampler");
+    double* s2 = d_levels; double* s3 = s2 + n2;
+    k_leafsum<false><<<(unsigned)((n2 * 32 + 255) / 256), 256, 0, st->stream>>>(d_s1, n1, n2, s2);
+    k_leafsum<false><<<(unsigned)((n3 * 32 + 255) / 256), 256, 0, st->stream>>>(s2, n2, n3, s3);
+    const uint64_t Nloc = local_amps(st), leaf_cnt = (Nloc + kLeaf - 1) / kLeaf;
+    const uint64_t Ntot = st->dist ? (1ull << st->n) : Nloc;
+    k_sample<<<(nshots + 127) / 128, 128, 0, st->stream>>>(st->amp + ((uint64_t)batch_idx << st->nl), Ntot, d_s1, n1, s2, n2, s3, n3,
+                                                          seed, nshots, d_out, leaf_lo, leaf_cnt);
+    CU(cudaGetLastError());
+    st->ctr.launches += 3;
+    return QM_OK;
+}
+
 extern "C" int32_t qm_sample(qm_state* st, uint64_t seed, int32_t nshots, int32_t batch_idx, uint64_t* out) {
     if (!st || (!out && nshots > 0) || nshots < 0) return set_err(QM_ERR_ARG, "null argument");
     if (batch_idx < 0 || batch_idx >= st->batch) return set_err(QM_ERR_ARG, "batch index out of range");
-    if (st->dist) return set_err(QM_ERR_STATE, "sampling a sharded register is not implemented");
     if (nshots == 0) return QM_OK;
     QM_TRY(flush(st));
     CU(cudaSetDevice(st->device));
+    if (st->dist) return dist_sample(st, seed, nshots, out);
     const uint64_t N = local_amps(st);
     const uint64_t n1 = (N + kLeaf - 1) / kLeaf, n2 = (n1 + kLeaf - 1) / kLeaf, n3 = (n2 + kLeaf - 1) / kLeaf;
     size_t need = (n1 + n2 + n3) * 8 + (size_t)nshots * 8 + 64;
     QM_TRY(ENSURE_DEV(st, d_scratch, need));
     QM_TRY(ENSURE_PIN(st, h_scratch, (size_t)nshots * 8));
-    double* s1 = st->d_scratch; double* s2 = s1 + n1; double* s3 = s2 + n2;
-    uint64_t* d_out = reinterpret_cast<uint64_t*>(s3 + n3);
-    const double2* base = st->amp + ((uint64_t)batch_idx << st->nl);
-    k_leafsum<true><<<(unsigned)((n1 * 32 + 255) / 256), 256, 0, st->stream>>>(base, N, n1, s1);
-    k_leafsum<false><<<(unsigned)((n2 * 32 + 255) / 256), 256, 0, st->stream>>>(s1, n1, n2, s2);
-    k_leafsum<false><<<(unsigned)((n3 * 32 + 255) / 256), 256, 0, st->stream>>>(s2, n2, n3, s3);
-    k_sample<<<(nshots + 127) / 128, 128, 0, st->stream>>>(base, N, s1, n1, s2, n2, s3, n3, seed, nshots, d_out);
-    CU(cudaGetLastError());
-    st->ctr.launches += 4; st->ctr.bytes_hbm += 16ull * N;
+    double* s1 = st->d_scratch;
+    uint64_t* d_out = reinterpret_cast<uint64_t*>(s1 + n1 + n2 + n3);
+    QM_TRY(qm_sample_leaves(st, batch_idx, s1));
+    QM_TRY(qm_sample_descend(st, batch_idx, s1, n1, 0, seed, nshots, s1 + n1, d_out));
     CU(cudaMemcpyAsync(st->h_scratch, d_out, (size_t)nshots * 8, cudaMemcpyDeviceToHost, st->stream));
     st->ctr.bytes_d2h += (size_t)nshots * 8;
     QM_TRY(qm_sync(st));

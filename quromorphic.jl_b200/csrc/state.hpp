@@ -67,3 +67,11 @@ static inline uint64_t total_amps(const qm_state* st) { return (uint64_t)st->bat
 int qm_create_common(int n, uint64_t basis, int batch, int device, int rank, int world, qm_state** out);
 int qm_zstats(qm_state* st, double thr, double** h_pairs, double** h_tot);
 int qm_measure_phys(qm_state* st, int phys_bit, double thr, int batch_idx, const double* R, double out[2]);
+// reduced density of this device's 2^nl amplitudes (kernels enqueued on st->stream, result [4^k] double2 on the device)
+int qm_reduced_local(qm_state* st, int keep_low, int k, int batch_idx, double2** d_out);
+// sampler levels: leaf sums of this device's amplitudes into s1_local[0 .. 2^nl/4096), and the descent over the full
+// level-1 array (n1 leaves of the WHOLE register); a shot whose leaf is not in [leaf_lo, leaf_lo + 2^nl/4096) yields 0
+int qm_sample_leaves(qm_state* st, int batch_idx, double* d_s1_local);
+int qm_sample_descend(qm_state* st, int batch_idx, const double* d_s1, uint64_t n1, uint64_t leaf_lo, uint64_t seed, int nshots,
+                      double* d_levels, uint64_t* d_out);
+int qm_flush(qm_state* st);
