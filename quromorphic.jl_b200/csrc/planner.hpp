@@ -265,6 +265,9 @@ struct Planner {
     size_t first = 0;
     double budget_now = 0.0;         // budget of the passes being built (budget_for_pending)
     bool budget_fixed = false, mode_known = false, short_circuit = false;
+    std::vector<int> last_taken;     // gate indices of the pass next_pass built last
+    std::vector<std::pair<PlanPass, std::vector<int>>> replay;   // the chosen plan of a short stretch, handed out by next_pass
+    size_t replay_at = 0;
 
     int total_bits() const { return opt.n_local + opt.n_global; }
 
@@ -376,13 +379,22 @@ struct Planner {
         }
         uint64_t tmask = ~0ull;
         if (!budget_fixed) budget_now = budget_for_pending();
+        if (replay_at < replay.size()) {            // the stretch was already planned while choosing its budget
+            P = replay[replay_at].first;
+            last_taken = replay[replay_at].second;
+            for (int i : last_taken) done[i] = 1;
+            ++replay_at;
+            return true;
+        }
+        if (!replay.empty()) { replay.clear(); replay_at = 0; budget_fixed = false; return false; }
         choose_tile(m, L, hb, best, tmask);
         if (best <= 0) { budget_fixed = false; return false; }     // end of a stretch (a remap follows): choose again
         std::vector<int> taken;
         build_pass(m, L, hb, P, taken, tmask);
         for (int i : taken) done[i] = 1;
         if (opt.retile && !taken.empty()) retile(P);
-        return !taken.empty();
+        last_taken.swap(taken);
+        return !last_taken.empty();
     }
 
     // Once the gates of a pass are known, only the non-diagonal targets have to be tile bits (controls and
@@ -469,18 +481,29 @@ struct Planner {
         }
         budget_fixed = true;
         if (!short_circuit) return opt.max_cost;
-        static const double mults[] = {1.0, 1.35, 1.8, 2.5, 4.0, 1e9};
+        static const double mults[] = {1.0, 1.8, 3.0, 1e9};
         double best_t = 1e300, best_b = opt.max_cost;
+        std::vector<int> prev_sig;
         for (double mu : mults) {
             if (mu > opt.short_mult) mu = opt.short_mult;
             Planner trial = *this;
+            trial.replay.clear(); trial.replay_at = 0;
             trial.budget_now = std::min(mu * opt.max_cost, 1e30);
             double t = 0.0, work = 0.0; PlanPass P;
-            while (trial.next_pass(P)) { t += predicted_units(P); work += P.cost; }
+            std::vector<std::pair<PlanPass, std::vector<int>>> passes;
+            while (trial.next_pass(P)) {
+                t += predicted_units(P); work += P.cost;
+                passes.emplace_back(P, trial.last_taken);
+            }
             if (work <= 0.0) break;
-            if (t / work < 0.99 * best_t) { best_t = t / work; best_b = trial.budget_now; }
-            if (mu >= opt.short_mult) break;
+            std::vector<int> sig;                // the larger budget changed nothing: neither will the next
+            for (const auto& pr : passes) { sig.push_back(pr.first.ngates); sig.push_back((int)pr.first.groups.size()); }
+            const bool same = sig == prev_sig;
+            prev_sig.swap(sig);
+            if (t / work < 0.99 * best_t) { best_t = t / work; best_b = trial.budget_now; replay.swap(passes); }
+            if (mu >= opt.short_mult || same) break;
         }
+        replay_at = 0;
         return best_b;
     }
 

@@ -444,14 +444,45 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         if (smap) pl.opt.max_subs = (kV4MaxRecs - kV4MaxGroups) / 2;      // every per-state gate takes two records
     }
     pl.done.assign(pl.gates.size(), 0);
+    // plan cache (unsharded, fused, TMA kernel): same structure as a recent circuit -> reuse its passes with this
+    // circuit's matrices
+    const bool cacheable = tma && st->g == 0 && st->fuse && pl.gates.size() <= 4096;
+    std::vector<int64_t> key;
+    qm_state::CachedPlan* hit = nullptr;
+    std::vector<std::pair<PlanPass, std::vector<int>>> fresh;
+    if (cacheable) {
+        key.reserve(pl.gates.size() + 8);
+        key.push_back(st->nl); key.push_back(tile_bits); key.push_back(st->low_bits); key.push_back((int64_t)(pl.opt.max_cost * 16));
+        key.push_back((int64_t)(pl.opt.short_mult > 1e8 ? -1 : pl.opt.short_mult * 100)); key.push_back(pl.opt.max_subs);
+        for (const LGate& x : pl.gates)
+            key.push_back((int64_t)x.target | ((int64_t)(x.ctrl + 1) << 8) | ((int64_t)x.diag << 16) | ((int64_t)(x.slot >= 0) << 17) |
+                          ((int64_t)(gate_cost(x) * 16.0) << 20));
+        for (auto& c : st->plan_cache) if (c.key == key) { hit = &c; break; }
+    }
+    size_t replay_i = 0;
     while (true) {
         passes.clear(); blob.clear(); offs.clear(); v4progs.clear();
         PlanPass P;
         std::vector<int> v4_of;                 // pass -> index into v4progs, or -1 (general kernel, program in the blob)
-        while (pl.next_pass(P)) {
+        auto next = [&](PlanPass& out) -> bool {
+            if (!hit) {
+                if (!pl.next_pass(out)) return false;
+                if (tma) choose_tile_layout(out);
+                if (cacheable) fresh.emplace_back(out, pl.last_taken);
+                return true;
+            }
+            if (replay_i >= hit->passes.size()) return false;
+            out = hit->passes[replay_i].first;
+            const std::vector<int>& idx = hit->passes[replay_i].second;
+            size_t j = 0;
+            for (PlanGroup& G : out.groups) for (LGate& x : G.subs) x = pl.gates[idx[j++]];
+            for (int i : idx) pl.done[i] = 1;
+            ++replay_i;
+            return true;
+        };
+        while (next(P)) {
             offs.push_back(blob.size());
             bool v3 = false;
-            if (tma) choose_tile_layout(P);
             if (tma && v4_eligible(st, P)) {
                 v4progs.emplace_back();
                 if (encode_v4(P, v4progs.back())) v3 = true; else v4progs.pop_back();
@@ -510,6 +541,11 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         // global qubits with the top local ones (all-to-all over NVLink) and relabel the pending gates.
         if (passes.empty() && !pl.pending_global_target()) return set_err(QM_ERR_STATE, "planner stalled (internal error)");
         QM_TRY(dist_remap(st, &pl.gates, &pl.done));
+    }
+    if (cacheable && !hit) {
+        qm_state::CachedPlan c; c.key.swap(key); c.passes.swap(fresh);
+        st->plan_cache.insert(st->plan_cache.begin(), std::move(c));
+        if (st->plan_cache.size() > 8) st->plan_cache.pop_back();
     }
     if (!first_event) { CU(cudaEventRecord(st->ev1, st->stream)); st->ev_pending = true; }
     st->ctr.gates += ngates;
