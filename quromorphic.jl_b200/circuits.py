@@ -53,8 +53,19 @@ class GateList:
     def ry(self, t, th): self.u2(t, Q.ry_gate(th))
     def rz(self, t, th): self.u2(t, Q.rz_gate(th))
     def h(self, t): self.u2(t, Q.H)
+    def x(self, t): self.u2(t, Q.X)
+    def y(self, t): self.u2(t, Q.Y)
+    def z(self, t): self.u2(t, Q.Z)
     def cnot(self, c, t): self.controlled(c, t, Q.X)
+    def crx(self, c, t, th): self.controlled(c, t, Q.rx_gate(th))
+    def cry(self, c, t, th): self.controlled(c, t, Q.ry_gate(th))
     def crz(self, c, t, th): self.controlled(c, t, Q.rz_gate(th))
+
+    def swap(self, q1, q2):
+        """swap!, QSim.jl:262-275: no-op on equal qubits, else three cnot! (each under the reference's index map)"""
+        assert 1 <= q1 <= self.n and 1 <= q2 <= self.n
+        if q1 != q2:
+            self.cnot(q1, q2); self.cnot(q2, q1); self.cnot(q1, q2)
 
     def array(self):
         a = np.zeros(len(self.rows), dtype=L.GATE_DTYPE)

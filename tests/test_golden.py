@@ -1,0 +1,109 @@
+"""Committed golden vectors (tests/golden/qsim_golden.json, written by tests/golden/make_golden.py from the literal
+kron transcription of QSim.jl / QInfo.jl) replayed through (CPU) the C oracle and the host emulator of the encoded pass
+programs and (GPU) the CUDA path behind the reference-named Python mirror.  1e-12 relative for amplitudes and readouts;
+the permutation-only case (x!, cnot!, swap!) bit for bit."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import literal as LIT
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "qsim_golden.json")) as f:
+    GOLDEN = json.load(f)
+CASES = GOLDEN["cases"]
+RTOL = 1e-12
+
+
+def unhex(v):
+    return np.array([float.fromhex(x) for x in v], dtype=np.float64)
+
+
+def unhexc(v):
+    a = unhex(v).reshape(-1, 2)
+    return a[:, 0] + 1j * a[:, 1]
+
+
+def replay(B, s, ops):
+    for op in ops:
+        name = op[0]
+        if isinstance(op[-1], str):
+            getattr(B, name)(s, *op[1:-1], float.fromhex(op[-1]))
+        else:
+            getattr(B, name)(s, *op[1:])
+    return s
+
+
+def check_case(case, amps, mp, mz, mx, my, reduced, entropy):
+    n = case["n"]
+    want = unhexc(case["amps"])
+    if case["name"].endswith("permutations_only"):
+        assert np.array_equal(amps, want)
+    assert np.max(np.abs(amps - want)) <= RTOL * np.max(np.abs(want))
+    assert np.max(np.abs(mp - unhex(case["mp"]))) <= RTOL
+    for t in range(1, n + 1):
+        for got, key in ((mz, "measure_z"), (mx, "measure_x"), (my, "measure_y")):
+            assert np.max(np.abs(np.array(got(t)) - unhex(case[key][t - 1]))) <= RTOL, (case["name"], key, t)
+    for r in case["reduced"]:
+        k = r["k"]
+        rB, rA = reduced(True, k), reduced(False, k)
+        assert np.max(np.abs(rB.ravel() - unhexc(r["rho_B_low"]))) <= RTOL
+        assert np.max(np.abs(rA.ravel() - unhexc(r["rho_A_high"]))) <= RTOL
+        assert entropy(rB) == pytest.approx(float.fromhex(r["S_B"]), abs=1e-9)
+        assert entropy(rA) == pytest.approx(float.fromhex(r["S_A"]), abs=1e-9)
+
+
+def test_golden_file_matches_its_generator():
+    """the committed file is what tests/golden/make_golden.py writes today (the literal restatement has not drifted)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    assert len(CASES) == len(mg.CASES) >= 9
+    for case in CASES[:3]:
+        s = LIT.statevector(case["n"], case["m"])
+        for op in case["ops"]:
+            mg.apply_op(s, op)
+        assert mg.hxc(s) == case["amps"]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_c_oracle_reproduces_golden_vectors(case):
+    n = case["n"]
+    s = replay(O, O.statevector(n, case["m"]), case["ops"])
+    check_case(case, s, O.mp(s),
+               lambda t: O.measure_z(s, t, 1e-10, True), lambda t: O.measure_x(s, t, 1e-10, True),
+               lambda t: O.measure_y(s, t, 1e-10, True),
+               lambda keep_low, k: O.reduced_density(np.ascontiguousarray(s), keep_low, k), LIT.von_neumann_entropy)
+
+
+def test_encoded_tma_programs_reproduce_the_12_qubit_golden_case(pkg):
+    """planner + encoder of the fused TMA kernel against the literal algorithm, without a GPU: the 12-qubit golden
+    case as a wire-format gate list, walked by the host emulator of the encoded pass programs (csrc/emulate.hpp)"""
+    case = next(c for c in CASES if c["n"] == 12)
+    gl = pkg.circuits.GateList(12, "reference")
+    replay_gl = lambda op: getattr(gl, op[0])(*op[1:-1], float.fromhex(op[-1])) if isinstance(op[-1], str) else getattr(gl, op[0])(*op[1:])
+    for op in case["ops"]:
+        replay_gl(op)
+    got, npass = pkg._lib.plan_emulate(12, gl.array(), O.statevector(12, case["m"]), max_cost=75.0)
+    want = unhexc(case["amps"])
+    assert npass >= 1 and np.max(np.abs(got - want)) <= RTOL * np.max(np.abs(want))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_cuda_path_reproduces_golden_vectors(pkg, case):
+    """the reference-named mirror over the C ABI (gates queue and fuse; readouts flush)"""
+    Q, QI = pkg.qsim, pkg.qinfo
+    n = case["n"]
+    s = replay(Q, Q.statevector(n, case["m"]), case["ops"])
+
+    def reduced(keep_low, k):
+        if keep_low:
+            return QI.partial_trace(s, 1 << (n - k), 1 << k, 1)
+        return QI.partial_trace(s, 1 << k, 1 << (n - k), 2)
+    check_case(case, s.to_numpy(), Q.mp(s), lambda t: Q.measure_z(s, t), lambda t: Q.measure_x(s, t),
+               lambda t: Q.measure_y(s, t), reduced, QI.von_neumann_entropy)
