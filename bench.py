@@ -342,6 +342,22 @@ def main():
     del st
     torch.cuda.empty_cache()
 
+    # ---- the weak-scaling base of the N > 1 lines (config C4 on ONE GPU: 2^33 amplitudes, same reservoir step, no
+    # exchange), so that the 2/4/8-GPU values have their own-workload reference in the N = 1 line ----
+    if not args.no_alt and n == C3_QUBITS and args.depth == C3_DEPTH:
+        import copy
+        a4 = copy.copy(args)
+        a4.qubits, a4.max_cost, a4.tile_bits, a4.short_pct = 0, -1, 0, -1
+        try:
+            from bench_dist import run_dist
+            b = run_dist(a4, pkg, 0, 1, 0, emit=False)
+            line["c4_base"] = {"workload": b["config"]["workload"], "n_qubits": b["n_qubits"], "value": b["value"], "unit": unit,
+                               "ms_per_step": b["ms_per_step"], "gates_per_step": b["gates_per_step"],
+                               "passes_per_step": b["passes_per_step"], "fused_pass_gbs": b["roofline"]["achieved"],
+                               "note": "weak-scaling efficiency of the N-GPU C4 lines = (ms_per_step / gates_per_step here) / (theirs)"}
+        except Exception as e:            # the base is informational: never lose the headline line over it
+            line["c4_base"] = {"error": str(e)[:200]}
+
     if not args.no_cpu:
         n_cpu = pick_cpu_qubits(n)
         cg = gates if n_cpu == n else pkg.circuits.c3_circuit(n=n_cpu, depth=2, seed=C3_SEED)

@@ -12,7 +12,7 @@ import json
 import time
 
 
-def run_dist(args, pkg, rank, world, local_rank):
+def run_dist(args, pkg, rank, world, local_rank, emit=True):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -101,7 +101,9 @@ def run_dist(args, pkg, rank, world, local_rank):
         }
         if n != SHARD_QUBITS + g:
             line["config"]["workload"] += " [NON-DEFAULT size: %d qubits]" % n
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     st.close()
     if not single:
         dist.destroy_process_group()
+    return line if rank == 0 else None
