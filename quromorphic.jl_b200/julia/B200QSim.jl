@@ -47,6 +47,11 @@ end
 
 check(rc) = rc == 0 ? nothing : error(lasterror())      # ErrorException, like the reference
 
+# qm_set_option keys (include/qm_b200.h).  The defaults are the measured ones; these are tuning / debugging knobs.
+const OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_REMAP, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = 0:8
+set_option!(s, key::Integer, value::Integer) =
+    check(ccall((:qm_set_option, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), s.handle, key, value))
+
 """
     B200State(n, m = 0; batch = 1, device = 0, mode = :reference, threshold = 1e-10)
 

@@ -385,3 +385,30 @@ def test_c5_at_20_qubits_properties(pkg):
         assert np.all(np.abs(f[:n]) <= 1 + 1e-12) and 0 <= f[n] <= k + 1e-9 and 0 <= f[n + 1] <= k + 1e-9
     rho = pkg.qinfo.partial_trace(qr.state, 1 << (n - k), 1 << k, 1)
     assert abs(np.trace(rho).real - 1) < 1e-12 and np.max(np.abs(rho - rho.conj().T)) < 1e-15
+
+
+def test_plan_cache_reuses_structure_not_values(pkg):
+    """run_circuit caches plans by circuit STRUCTURE: the same layer with new angles must reuse the plan and still be
+    exact, and an angle that changes a gate's class (ry(0) = identity, rx(pi) = -iX, rz only: diagonal) must not be
+    served a stale plan.  13 qubits (TMA kernel), eight steps on one register against the oracle."""
+    n, C = 13, pkg.circuits
+    st = pkg.B200State(n, 0)
+    ref = O.statevector(n, 0)
+    g = C.SplitMix64(4242)
+    specials = {3: 0.0, 5: np.pi, 6: 2 * np.pi}
+    for step in range(8):
+        gl = C.GateList(n, "reference")
+        for q in range(1, n + 1):
+            gl.ry(q, specials.get(step, np.pi * g.uniform()) if q % 4 == 1 else np.pi * g.uniform())
+        for q in range(1, n + 1):
+            gl.rx(q, specials.get(step, g.angle()) if q % 5 == 2 else g.angle())
+            gl.rz(q, g.angle())
+        for q in range(1, n):
+            gl.cnot(q, q + 1)
+        gl.crz(n, 1, g.angle())
+        gates = gl.array()
+        st.apply_circuit(gates)
+        O.apply_circuit(ref, gates)
+        assert rel_err(st.to_numpy(), ref) < RTOL, step
+        assert np.max(np.abs(st.expect_z_all() - O.expect_z_all(ref, 1e-10))) < RTOL
+    st.close()
