@@ -457,9 +457,9 @@ struct Planner {
     // the budget.  `taken` receives the indices (into `gates`) of the gates of the pass; nothing is marked done.
     //
     // Budget (opt.max_cost) = sum of gate costs + opt.group_cost per group.  Measured on B200 at 30 qubits
-    // (tools/pass_model.py): a pass costs about 1.2 ms + 1.9 ms per group + 0.05 ms per cost unit against 5.9 ms
-    // of HBM time, i.e. one register-block group is worth ~38 cost units — a pass with ONE well-filled group stays
-    // on the HBM roofline, a second group almost never does.
+    // (tools/pass_model.py, final kernel): a pass costs about 2.04 ms + 0.89 ms per group + 0.05 ms per cost unit
+    // against 5.7 ms of HBM time, i.e. one register-block group is worth 18 cost units — a pass with ONE well-filled
+    // group (13-14 gates) stays on the HBM roofline, a second group does not.
     //
     // Short circuits: the budget keeps a pass at HBM time, which is the right trade when the circuit is deep enough
     // to fill one register block per pass (C3: 13-14 gates).  A reservoir step is not — 2-4 gates per qubit, then a
