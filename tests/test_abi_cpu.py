@@ -246,3 +246,18 @@ def test_short_circuit_is_planned_at_the_budget_that_finishes_first(pkg):
         ref = O.apply_circuit(ref, gates)
         assert npass <= 2
         assert np.max(np.abs(psi - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
+@pytest.mark.parametrize("n,depth,cost", [(14, 52, 75.0), (13, 60, 60.0), (15, 40, 110.0)])
+def test_deep_circuit_programs_emulated_on_cpu(pkg, n, depth, cost):
+    """circuits longer than the planner's look-ahead (768 gates) keep the budget as it is — the C3 headline path:
+    single-block passes filled to the budget.  Encoded programs walked by the host emulator against the oracle."""
+    gates = pkg.circuits.c3_circuit(n=n, depth=depth, seed=3001 + n)
+    assert len(gates) > 768
+    plan = pkg._lib.plan_describe(n, gates, max_cost=cost)
+    assert np.mean([len(p["groups"]) for p in plan]) <= 1.15              # deep mode, decided once for the whole circuit
+    psi0 = O.random_state(n, n)
+    got, npass = pkg._lib.plan_emulate(n, gates, psi0, max_cost=cost)
+    ref = O.apply_circuit(psi0.copy(), gates)
+    assert npass == len(plan)
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12

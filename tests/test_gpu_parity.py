@@ -412,3 +412,19 @@ def test_plan_cache_reuses_structure_not_values(pkg):
         assert rel_err(st.to_numpy(), ref) < RTOL, step
         assert np.max(np.abs(st.expect_z_all() - O.expect_z_all(ref, 1e-10))) < RTOL
     st.close()
+
+
+def test_deep_circuit_default_budget_at_20_qubits(pkg):
+    """the C3 headline path at a size the oracle follows: a circuit longer than the planner's look-ahead (1,200 gates),
+    default budget, single-block HBM-bound passes on the TMA kernel"""
+    n = 20
+    gates = pkg.circuits.c3_circuit(n=n, depth=40, seed=3001)
+    assert len(gates) > 768
+    st = pkg.B200State(n, 0)
+    st.apply_circuit(gates)
+    c = st.counters()
+    assert len(gates) / c["passes"] < 16                 # budget-limited passes, not deep fusion
+    ref = O.apply_circuit(O.statevector(n, 0), gates)
+    assert rel_err(st.to_numpy(), ref) < RTOL
+    assert np.max(np.abs(st.expect_z_all() - O.expect_z_all(ref, 1e-10))) < RTOL
+    st.close()
