@@ -174,6 +174,10 @@ int32_t qm_dm_measure(qm_state* rho, int32_t t0, const double* R, double thresho
  *                    log2(world) index bits equal `rank`; n_qubits is the GLOBAL register size.
  * Gates, readouts and counters then work on the global register; global-qubit gates are
  * remapped by an in-place chunked all-to-all over NVLink.
+ * Collective calls (every rank makes them, in the same order, and gets the same answer):
+ * qm_expect_z_all, qm_norm2, qm_measure*, qm_reduced_density (keep_low = 0 needs k <= n/2),
+ * qm_sample (>= 12 local bits; the shots equal those of an unsharded register bit for bit).
+ * qm_upload / qm_download move this rank's contiguous slice.
  */
 int32_t qm_dist_unique_id(uint8_t id_out[128]);
 int32_t qm_create_dist(int32_t n_qubits, uint64_t basis_index, int32_t device, int32_t rank,
