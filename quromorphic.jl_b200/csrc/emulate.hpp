@@ -137,8 +137,16 @@ inline bool emulate_v4(const V4Program& prog, const PlanPass& P, EmuAmp* amp, in
                         }
                     }
                 }
+                // the END record says where the registers go: the load offsets, unless a tail of x! / cnot! gates on
+                // block bits was folded into the stores (encode_v4)
+                if (R->op != (uint32_t)V4_OP_END) return false;
+                uint64_t packed; memcpy(&packed, &R->c[0], 8);
+                const uint32_t so[kV4BlockBits] = { R->tm, R->cm, R->aux, (uint32_t)packed };
+                uint32_t sb[kV4BlockBits];
+                for (int j = 0; j < NB; ++j) { const uint32_t u = so[j] >> 4; sb[j] = u ^ ((u >> 3) & 7u); }
+                const uint32_t du = (uint32_t)(packed >> 32) >> 4, dm = du ^ ((du >> 3) & 7u);
                 for (int l = 0; l < nl_; ++l)
-                    for (int k = 0; k < NA; ++k) { uint32_t off = 0; for (int j = 0; j < NB; ++j) if ((k >> j) & 1) off |= bm[j]; tile[v[l] | off] = a[l][k]; }
+                    for (int k = 0; k < NA; ++k) { uint32_t off = dm; for (int j = 0; j < NB; ++j) if ((k >> j) & 1) off ^= sb[j]; tile[v[l] ^ off] = a[l][k]; }
             }
         }
         for (uint32_t i = 0; i < (1u << m); ++i) amp[phys(i)] = tile[i];

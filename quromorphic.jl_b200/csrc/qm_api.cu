@@ -291,7 +291,29 @@ static bool encode_v4(const PlanPass& P, V4Program& out) {
             out.warp_tab[gi][w] = (uint16_t)v;
         }
         g.rec_off = (uint32_t)(offsetof(V4Program, recs) + (size_t)nrec * sizeof(V4Rec));
-        for (const LGate& x : G.subs) {
+        // A tail of x! / cnot! gates whose target AND control are register-block bits only permutes the thread's own
+        // sixteen amplitudes: register k ends up at block index A k + c over GF(2).  The swizzled offsets are
+        // xor-linear, so the tail is folded into the offsets the END record hands to the stores (v4_dispatch.inc)
+        // instead of being executed: store offset of block bit j = xor_i A[i][j] s[i], base xor = xor_i c[i] s[i].
+        auto block_index = [&](int phys) { const int tl = tile_local_of(P, phys); if (tl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == tl) return i; return -1; };
+        size_t nexec = G.subs.size();
+        while (nexec > 0) {
+            const LGate& x = G.subs[nexec - 1];
+            LiftCoef Lt;
+            if (x.slot >= 0 || x.diag || lift_classify(x.m, Lt) != LK_PERMX || block_index(x.target) < 0) break;
+            if (x.ctrl >= 0 && block_index(x.ctrl) < 0) break;
+            --nexec;
+        }
+        uint32_t Arow[NB], cvec = 0;                 // Arow[i] = row i of A as a bit mask over k's bits
+        for (int i = 0; i < NB; ++i) Arow[i] = 1u << i;
+        for (size_t q = nexec; q < G.subs.size(); ++q) {
+            const LGate& x = G.subs[q];
+            const int b = block_index(x.target);
+            if (x.ctrl < 0) cvec ^= 1u << b;
+            else { const int a = block_index(x.ctrl); Arow[b] ^= Arow[a]; cvec ^= ((cvec >> a) & 1u) << b; }
+        }
+        for (size_t qi = 0; qi < nexec; ++qi) {
+            const LGate& x = G.subs[qi];
             if (nrec + 4 > kV4MaxRecs) { ok = false; break; }
             int CB = -1; uint32_t cm = 0;
             if (x.ctrl >= 0) {
@@ -341,6 +363,14 @@ static bool encode_v4(const PlanPass& P, V4Program& out) {
         if (!ok) break;
         V4Rec& E = out.recs[nrec++]; memset(&E, 0, sizeof(E));
         E.op = V4_OP_END;
+        uint32_t so[NB] = { 0, 0, 0, 0 }, delta = 0;
+        for (int i = 0; i < NB; ++i) {
+            for (int j = 0; j < NB; ++j) if ((Arow[i] >> j) & 1u) so[j] ^= g.s[i];
+            if ((cvec >> i) & 1u) delta ^= g.s[i];
+        }
+        E.tm = so[0]; E.cm = so[1]; E.aux = so[2];
+        const uint64_t packed = (uint64_t)so[3] | ((uint64_t)delta << 32);
+        memcpy(&E.c[0], &packed, 8);
     }
     out.nrecs = nrec; out.n_outer = n_outer; out.ctx_const = 0;
     return ok;

@@ -25,6 +25,7 @@ Design notes (all measured on B200, see profiles/ and DESIGN.md):
     ~0.2 ms per dispatched record at 30 qubits whatever the record does, tools/pass_model.py.)
 
 A record is 64 bytes:  u32 op, tm, cm, aux;  f64 c0, c3, c1, c4, c2, c5.
+  END record: tm, cm, aux, low word of c0 = store offsets of block bits 0..3, high word of c0 = xor for the thread's base.
   cm   controlled entry: context bits that must all be set          tm   THR: context bit selecting the coefficient set
   aux  SLOT: per-state coefficient slot
 Operands:  %0 shared address of the current record ("+r")   %1 context word   %2 shared address of the per-state coefficient base
@@ -170,14 +171,22 @@ def addresses(tag):
     across the gate loop (sixteen addresses did not fit the register budget and were spilled)."""
     if tag == "setup":
         return ["mov.b32 o0, %4;", "xor.b32 o1, o0, %5;", "xor.b32 o2, o0, %6;", "xor.b32 o3, o1, %6;"]
+    # stores: the END record carries the store offsets of the four block bits and an xor for the thread's base.  They
+    # equal the load offsets unless the group ended in x! / cnot! gates on register-block bits: such a tail only
+    # permutes the thread's own sixteen amplitudes, an affine map over GF(2) of the block bits, and the swizzle is
+    # xor-linear, so the whole tail is folded into WHERE the registers are stored (encode_v4) and costs nothing.
     o = []
+    b2, b3 = ("%7", "%8") if tag == "load" else ("e2", "e3")
+    if tag == "store":
+        o += ["ld.shared.u32 e0, [%0+4];", "ld.shared.v2.u32 {e1, e2}, [%0+8];", "ld.shared.v2.u32 {e3, t}, [%0+16];",
+              "xor.b32 o0, %4, t;", "xor.b32 o1, o0, e0;", "xor.b32 o2, o0, e1;", "xor.b32 o3, o1, e1;"]
     for k in range(NA):
         src = "o%d" % (k & 3)
         if k & 4:
-            o.append("xor.b32 ad, %s, %%7;" % src)
+            o.append("xor.b32 ad, %s, %s;" % (src, b2))
             src = "ad"
         if k & 8:
-            o.append("xor.b32 ad, %s, %%8;" % src)
+            o.append("xor.b32 ad, %s, %s;" % (src, b3))
             src = "ad"
         o.append("add.u32 ad, %s, %%3;" % src)
         if tag == "load":
@@ -209,7 +218,7 @@ def main():
     OP_SLOT, OP_END = 2 * n_gate_ops, 2 * n_gate_ops + 1
     nops = 2 * n_gate_ops + 2
     targets = ["V4L%d" % i for i in range(n_gate_ops)] + ["V4C%d" % i for i in range(n_gate_ops)] + ["V4L%d" % OP_SLOT, "V4L%d" % OP_END]
-    lines = ["{", ".reg .f64 x<%d>, y<%d>, c<6>, ng, n0, n1, n2, tm<2>;" % (NA, NA), ".reg .b32 hop, hcm, htm, hax, t, ad, o<4>;",
+    lines = ["{", ".reg .f64 x<%d>, y<%d>, c<6>, ng, n0, n1, n2, tm<2>;" % (NA, NA), ".reg .b32 hop, hcm, htm, hax, t, ad, o<4>, e<4>;",
              ".reg .pred pact, phi;", ".reg .b64 sa, sb;",
              "V4T: .branchtargets " + ", ".join(targets) + ";"]
     lines += addresses("setup") + addresses("load")
