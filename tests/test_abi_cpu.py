@@ -261,3 +261,36 @@ def test_deep_circuit_programs_emulated_on_cpu(pkg, n, depth, cost):
     ref = O.apply_circuit(psi0.copy(), gates)
     assert npass == len(plan)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
+@pytest.mark.parametrize("n,seed,perm_only", [(12, 1, True), (13, 2, True), (14, 3, False), (12, 4, False), (15, 5, False),
+                                              (13, 6, True), (16, 7, False)])
+def test_permutation_tails_folded_into_the_stores_are_exact(pkg, n, seed, perm_only):
+    """x!/cnot!/swap!-heavy circuits: groups end in permutation tails that encode_v4 folds into the END record's store
+    offsets instead of executing them.  Pure permutation circuits must stay bit for bit (np.array_equal), mixed ones
+    within 1e-12; short chunks applied one after the other so that many groups END in such a tail."""
+    rng = np.random.default_rng(9000 + seed)
+    Q = pkg.qsim
+    psi = O.random_state(n, seed)
+    ref = psi.copy()
+    for chunk in range(6):
+        gl = pkg.circuits.GateList(n, "reference" if seed % 2 else "corrected")
+        for _ in range(int(rng.integers(8, 60))):
+            k = int(rng.integers(0, 10 if not perm_only else 6))
+            t, c = int(rng.integers(1, n + 1)), int(rng.integers(1, n + 1))
+            if k <= 1: gl.x(t)
+            elif k <= 4 and c != t: gl.cnot(c, t)
+            elif k == 5 and c != t: gl.swap(c, t)
+            elif k == 6: gl.ry(t, float(rng.uniform(-3, 3)))
+            elif k == 7: gl.rz(t, float(rng.uniform(-3, 3)))
+            elif k == 8 and c != t: gl.crz(c, t, float(rng.uniform(-3, 3)))
+            elif k == 9: gl.h(t)
+        gates = gl.array()
+        if len(gates) == 0:
+            continue
+        psi, npass = pkg._lib.plan_emulate(n, gates, psi, max_cost=75.0)
+        ref = O.apply_circuit(ref, gates)
+        if perm_only:
+            assert np.array_equal(psi, ref), (chunk, npass)
+        else:
+            assert np.max(np.abs(psi - ref)) / np.max(np.abs(ref)) < 1e-12

@@ -428,3 +428,39 @@ def test_deep_circuit_default_budget_at_20_qubits(pkg):
     assert rel_err(st.to_numpy(), ref) < RTOL
     assert np.max(np.abs(st.expect_z_all() - O.expect_z_all(ref, 1e-10))) < RTOL
     st.close()
+
+
+@pytest.mark.parametrize("n,seed", [(12, 1), (14, 2), (17, 3)])
+def test_permutation_circuits_bit_exact_on_the_tma_kernel(pkg, n, seed):
+    """x!/cnot!/swap! through the fused TMA kernel (>= 12 qubits), where tails of such gates on register-block bits
+    are folded into the store offsets instead of being executed: pure moves, so bit for bit; then a mixed circuit
+    (rotations between the permutations) within 1e-12."""
+    rng = np.random.default_rng(7700 + seed)
+    psi0 = O.random_state(n, 100 + seed)
+    st = pkg.B200State.from_numpy(psi0) if hasattr(pkg.B200State, "from_numpy") else None
+    if st is None:
+        st = pkg.B200State(n, 0); st.upload(psi0)
+    ref = psi0.copy()
+    for chunk in range(5):
+        gl = pkg.circuits.GateList(n, "reference")
+        for _ in range(int(rng.integers(10, 70))):
+            k = int(rng.integers(0, 6))
+            t, c = int(rng.integers(1, n + 1)), int(rng.integers(1, n + 1))
+            if k <= 1: gl.x(t)
+            elif k <= 4 and c != t: gl.cnot(c, t)
+            elif c != t: gl.swap(c, t)
+        gates = gl.array()
+        st.apply_circuit(gates)
+        ref = O.apply_circuit(ref, gates)
+        assert np.array_equal(st.to_numpy(), ref), chunk
+    gl = pkg.circuits.GateList(n, "reference")
+    for q in range(1, n + 1):
+        gl.ry(q, float(rng.uniform(-3, 3)))
+    for q in range(1, n):
+        gl.cnot(q, q + 1)
+    gl.x(1); gl.cnot(n, 1)
+    gates = gl.array()
+    st.apply_circuit(gates)
+    ref = O.apply_circuit(ref, gates)
+    assert rel_err(st.to_numpy(), ref) < RTOL
+    st.close()
