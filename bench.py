@@ -168,11 +168,11 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-ALT_MAX_COST = 250         # planner budget of the secondary "deep fusion" measurement (engine default: 75)
+ALT_MAX_COST = 250         # planner budget of the secondary "deep fusion" measurement (engine default: 80)
 
 
 def st_max_cost(args):
-    return int(args.max_cost) if args.max_cost >= 0 else 75
+    return int(args.max_cost) if args.max_cost >= 0 else 80
 
 
 def workload_config(ngpus, n, c4=False):

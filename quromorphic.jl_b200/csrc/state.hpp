@@ -39,7 +39,7 @@ struct qm_state {
     std::vector<float> pass_desc;              // per timed pass: groups, records, planner cost
     int tile_bits = 0, low_bits = 5;     // tile_bits 0 = automatic (12)
     double short_mult = 1e9;    // QM_OPT_SHORT_PCT / 100 (planner.hpp budget_for_pending); 1e9 = no limit
-    double max_cost = 75.0;  // per-pass budget of the planner cost model (gate costs + 18 per register-block group, planner.hpp); 0 = unlimited
+    double max_cost = 80.0;  // per-pass budget of the planner cost model (gate costs + 18 per register-block group, planner.hpp); 0 = unlimited
     // plans of recent circuits keyed by STRUCTURE (targets, controls, diagonal / slot flags, cost classes — everything
     // the planner looks at; not the matrix values): a reservoir loop applies the same layer with new angles every
     // step, and planning a 50-gate step costs ~1 ms on the host against ~0.1 ms of kernels at 20 qubits
