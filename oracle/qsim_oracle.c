@@ -13,7 +13,12 @@
  *       this path, and
  *   (2) oracle/literal.py — a numpy transcription of the reference's literal algorithm
  *       (kron(id(r), kron(U, id(l))) then a dense matrix-vector product), for every gate kind
- *       and every (c, t) pair on small registers.
+ *       and every (c, t) pair on small registers, and
+ *   (3) the committed golden vectors tests/golden/qsim_golden.json (written by tests/golden/make_golden.py
+ *       from that literal transcription; tests/test_golden.py).
+ * What no reference test or literal counterpart pins ("parity unpinned"): the all-qubit
+ * expectation call, fused/batched application, psi -> reduced rho without forming rho, and the sampler — there
+ * this file is the definition.
  *
  * Conventions: qubit arguments are the reference's own 1-BASED indices (qubit t <-> bit t-1 of
  * the 0-based amplitude index, QSim.jl:56-58, :304).  States are interleaved (re, im) doubles.
