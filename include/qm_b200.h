@@ -220,6 +220,17 @@ int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, 
 int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
                         const qm_gate* gates, int32_t ngates, double* state_interleaved, int32_t* n_passes);
 
+/* TEST INFRASTRUCTURE, host only: the same for a register sharded over 2^global_bits ranks, all ranks emulated in
+ * this one process.  `state` is the WHOLE register in canonical order (rank r's shard = amplitudes
+ * [r << n_local, (r + 1) << n_local)).  Every rank's shard is walked with the encoded programs (rank predicates for
+ * controls and rank-dependent phases for diagonal targets on global qubits come from the rank's index bits, as in the
+ * kernel); when the planner runs out of local work the shards trade chunks on the host exactly as the in-place
+ * exchange does (chunk j of rank r <-> chunk r of rank j), the pending gates are relabelled, and at the end the
+ * canonical layout is restored.  n_local = n_qubits - global_bits must be in [11, 22]. */
+int32_t qm_plan_emulate_sharded(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits, double max_cost,
+                                const qm_gate* gates, int32_t ngates, double* state_interleaved, int32_t* n_passes,
+                                int32_t* n_remaps);
+
 /* host-only introspection: record counts of the encoded pass programs by family:
  * hist[0..8] = ROT, ROTX, PHASE, PERMX, THR, SLOT, CTRL records, register-block groups, passes */
 int32_t qm_plan_ophist(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,

@@ -78,6 +78,8 @@ SIGNATURES = {
     "qm_plan_gates": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _vp,
                                   C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "qm_plan_emulate": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _dp, C.POINTER(C.c_int32)]),
+    "qm_plan_emulate_sharded": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _dp,
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "qm_pass_times": (C.c_int32, [_vp, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
     "qm_plan_ophist": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, C.POINTER(C.c_int64)]),
     "qm_sync": (C.c_int32, [_vp]),
@@ -177,6 +179,16 @@ def plan_emulate(n, gates, psi, tile_bits=12, low_bits=5, max_cost=0.0):
     npass = C.c_int32()
     check(lib().qm_plan_emulate(n, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates), dptr(out), C.byref(npass)))
     return out, npass.value
+
+
+def plan_emulate_sharded(n, global_bits, gates, psi, tile_bits=12, low_bits=5, max_cost=0.0):
+    """host-only test helper: plan_emulate for a register sharded over 2^global_bits ranks, all emulated in this
+    process on the whole state vector; returns (state, passes, remaps)"""
+    out = np.ascontiguousarray(psi, dtype=np.complex128).copy()
+    npass, nrem = C.c_int32(), C.c_int32()
+    check(lib().qm_plan_emulate_sharded(n, global_bits, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates), dptr(out),
+                                        C.byref(npass), C.byref(nrem)))
+    return out, npass.value, nrem.value
 
 
 def plan_ophist(n, gates, tile_bits=12, low_bits=5, max_cost=0.0):

@@ -31,3 +31,47 @@ def test_sharded_planner_with_gloo_ranks(world, n, tile, low, seed):
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "DIST_OK" in outs[0], outs[0]
     assert "remaps=0" not in outs[0], "the test circuit must exercise at least one remap: " + outs[0]
+
+
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("n,g,kind,seed", [(14, 1, "random", 1), (15, 2, "random", 2), (16, 3, "random", 3), (14, 2, "c4", 4),
+                                           (15, 1, "c4", 5), (16, 2, "c3deep", 6), (15, 3, "perm", 7)])
+def test_sharded_encoded_programs_emulated_on_cpu(pkg, n, g, kind, seed):
+    """every rank's ENCODED pass programs (the bytes the TMA kernel is launched with) walked on the host over the
+    rank's shard — rank predicates for controls on global qubits, rank-dependent phases for diagonal targets on them,
+    permutation tails folded into the stores, the short-circuit planner across exchanges — with the chunk exchange
+    and the relabelling done as the engine does them; the whole register must equal the oracle's."""
+    from oracle import oracle as O
+    from test_abi_cpu import random_circuit
+    C = pkg.circuits
+    if kind == "random":
+        chunks = [random_circuit(pkg, n, 260, 5200 + seed)]
+    elif kind == "c4":
+        chunks = [C.c4_step(n, s) for s in range(3)]              # short circuits, consecutive steps on one register
+    elif kind == "c3deep":
+        chunks = [C.c3_circuit(n=n, depth=36, seed=77)]           # > 768 gates: budget-limited passes
+    else:
+        rng = np.random.default_rng(seed)
+        gl = C.GateList(n, "corrected")
+        for _ in range(200):
+            t, c = int(rng.integers(1, n + 1)), int(rng.integers(1, n + 1))
+            if c == t: gl.x(t)
+            elif rng.uniform() < 0.7: gl.cnot(c, t)
+            else: gl.swap(c, t)
+        chunks = [gl.array()]
+    psi = O.random_state(n, 40 + seed)
+    ref = psi.copy()
+    remaps = 0
+    for gates in chunks:
+        psi, npass, nrem = pkg._lib.plan_emulate_sharded(n, g, gates, psi, max_cost=80.0)
+        ref = O.apply_circuit(ref, gates)
+        remaps += nrem
+        assert npass > 0
+    assert remaps > 0                                             # the global qubits did get non-diagonal gates
+    if kind == "perm":
+        assert np.array_equal(psi, ref)
+    else:
+        assert np.max(np.abs(psi - ref)) / np.max(np.abs(ref)) < 1e-12
