@@ -61,7 +61,7 @@ enum {
     QM_OPT_TILE_BITS  = 1,  /* fused pass tile size m: 11 or 12 for the TMA kernel; default 0 = automatic (12) */
     QM_OPT_LOW_BITS   = 2,  /* contiguous low bits every tile keeps (default 5: 512-byte rows)                    */
     QM_OPT_FUSE       = 3,  /* 0: planner emits one pass per gate (debug), 1: fuse (default)                      */
-    QM_OPT_REMAP      = 4,  /* 1: planner may relabel qubits inside a pass (logical->physical permutation)        */
+    QM_OPT_TRACE      = 4,  /* 1: CTA 0 of every fused pass records SM-clock stamps per tile (qm_trace_read; diagnostics) */
     QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel                     */
     QM_OPT_MAX_COST   = 6,  /* planner: budget of a pass = gate costs (FP64 FMAs per amplitude + 1) + 18 per register-block group (planner.hpp gate_cost); default 80, 0 = no cap */
     QM_OPT_TIME_PASSES = 7, /* 1: CUDA events around every fused pass, read back with qm_pass_times (diagnostics) */
@@ -195,12 +195,7 @@ int32_t qm_dist_ipc_import(qm_state* st, const uint8_t* handles);
  * top qubits sharded; writes a flat int32 description of the passes into `out` (layout in
  * DESIGN.md §planner) and the number of int32 written into *out_len.  Returns QM_ERR_ARG
  * if cap is too small (then *out_len = needed). */
-int32_t qm_plan_describe(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
-                         int32_t allow_remap, const qm_gate* gates, int32_t ngates,
-                         int32_t* out, int64_t cap, int64_t* out_len);
-
-/* qm_plan_describe with the engine's own planner settings: a cap on a pass's arithmetic (0 = none) and
- * the limits of the persistent TMA kernel (pipeline != 0). */
+/* max_cost: cap on a pass's arithmetic (0 = none); pipeline != 0: the limits of the persistent TMA kernel. */
 int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
                             double max_cost, int32_t pipeline, const qm_gate* gates, int32_t ngates,
                             int32_t* out, int64_t cap, int64_t* out_len);
@@ -211,25 +206,6 @@ int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, int32_t tile_
 int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
                       double max_cost, const qm_gate* gates, int32_t ngates, qm_gate* out,
                       int32_t* pass_of, int32_t cap, int32_t* out_len);
-
-/* TEST INFRASTRUCTURE, host only: plans `gates` as the engine does for its TMA kernel, encodes every pass
- * into the kernel's program format and walks the encoded programs over the host vector `state`
- * (2^n_qubits interleaved amplitudes, 11 <= n_qubits <= 24) with a scalar restatement of the kernel's
- * interpreter.  Lets the CPU tests check planner + encoder against the oracle without a GPU.  Not a
- * fallback: no other entry point calls it. */
-int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
-                        const qm_gate* gates, int32_t ngates, double* state_interleaved, int32_t* n_passes);
-
-/* TEST INFRASTRUCTURE, host only: the same for a register sharded over 2^global_bits ranks, all ranks emulated in
- * this one process.  `state` is the WHOLE register in canonical order (rank r's shard = amplitudes
- * [r << n_local, (r + 1) << n_local)).  Every rank's shard is walked with the encoded programs (rank predicates for
- * controls and rank-dependent phases for diagonal targets on global qubits come from the rank's index bits, as in the
- * kernel); when the planner runs out of local work the shards trade chunks on the host exactly as the in-place
- * exchange does (chunk j of rank r <-> chunk r of rank j), the pending gates are relabelled, and at the end the
- * canonical layout is restored.  n_local = n_qubits - global_bits must be in [11, 22]. */
-int32_t qm_plan_emulate_sharded(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits, double max_cost,
-                                const qm_gate* gates, int32_t ngates, double* state_interleaved, int32_t* n_passes,
-                                int32_t* n_remaps);
 
 /* host-only introspection: record counts of the encoded pass programs by family:
  * hist[0..8] = ROT, ROTX, PHASE, PERMX, THR, SLOT, CTRL records, register-block groups, passes */
@@ -246,6 +222,9 @@ int32_t qm_abi_version(void);
  * records with full FP64 cost, with a control in the register block (half cost), xor exchanges, thread-constant phases};
  * *n_passes receives the number of passes timed, at most cap_passes are written */
 int32_t qm_pass_times(qm_state* st, float* out, int32_t cap_passes, int32_t* n_passes);
+/* diagnostics (QM_OPT_TRACE): 8 SM-clock stamps per tile of CTA 0 of the last fused pass: the compute team's wait
+ * start, tile landed, after register-block group 0, 1, 2, arrival; the producer's "computed" seen and next load issued */
+int32_t qm_trace_read(qm_state* st, uint64_t* out, int64_t cap_u64);
 /* device-side view for harnesses that time on the library's stream (no ownership transfer) */
 int32_t qm_device_ptr(qm_state* st, void** amps, void** cuda_stream);
 

@@ -17,7 +17,7 @@ SO_PATH = os.environ.get("QM_B200_LIB") or os.path.join(HERE, "libqm_b200.so")
 QM_OK, QM_ERR_ARG, QM_ERR_CUDA, QM_ERR_NOMEM, QM_ERR_NO_DEVICE, QM_ERR_STATE, QM_ERR_COMM = range(7)
 GATE_U2, GATE_CU2, GATE_SWAP, GATE_U2_SLOT = 0, 1, 2, 3
 BASIS_Z, BASIS_X, BASIS_Y = 0, 1, 2
-OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_REMAP, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = range(9)
+OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_TRACE, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = range(9)
 
 GATE_DTYPE = np.dtype([("kind", np.int32), ("q0", np.int32), ("q1", np.int32), ("flags", np.int32),
                        ("m", np.float64, (8,))])
@@ -71,16 +71,12 @@ SIGNATURES = {
                                    C.POINTER(C.c_uint8), C.POINTER(_vp)]),
     "qm_dist_ipc_export": (C.c_int32, [_vp, C.POINTER(C.c_uint8)]),
     "qm_dist_ipc_import": (C.c_int32, [_vp, C.POINTER(C.c_uint8)]),
-    "qm_plan_describe": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_int32,
-                                     C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
     "qm_plan_describe_ex": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, _vp,
                                         C.c_int32, C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
     "qm_plan_gates": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _vp,
                                   C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
-    "qm_plan_emulate": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _dp, C.POINTER(C.c_int32)]),
-    "qm_plan_emulate_sharded": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, _dp,
-                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "qm_pass_times": (C.c_int32, [_vp, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
+    "qm_trace_read": (C.c_int32, [_vp, C.POINTER(C.c_uint64), C.c_int64]),
     "qm_plan_ophist": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, C.POINTER(C.c_int64)]),
     "qm_sync": (C.c_int32, [_vp]),
     "qm_last_error": (C.c_int32, [C.c_char_p, C.c_int32]),
@@ -171,24 +167,6 @@ def plan_describe(n, gates, global_bits=0, tile_bits=12, low_bits=5, max_cost=0.
             i += 2 + nrb
         steps.append({"ngates": ng, "m": m, "L": L, "hb": hb, "groups": groups})
     return steps
-
-
-def plan_emulate(n, gates, psi, tile_bits=12, low_bits=5, max_cost=0.0):
-    """host-only test helper: the planned + encoded pass programs walked over psi (complex128, length 2^n)"""
-    out = np.ascontiguousarray(psi, dtype=np.complex128).copy()
-    npass = C.c_int32()
-    check(lib().qm_plan_emulate(n, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates), dptr(out), C.byref(npass)))
-    return out, npass.value
-
-
-def plan_emulate_sharded(n, global_bits, gates, psi, tile_bits=12, low_bits=5, max_cost=0.0):
-    """host-only test helper: plan_emulate for a register sharded over 2^global_bits ranks, all emulated in this
-    process on the whole state vector; returns (state, passes, remaps)"""
-    out = np.ascontiguousarray(psi, dtype=np.complex128).copy()
-    npass, nrem = C.c_int32(), C.c_int32()
-    check(lib().qm_plan_emulate_sharded(n, global_bits, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates), dptr(out),
-                                        C.byref(npass), C.byref(nrem)))
-    return out, npass.value, nrem.value
 
 
 def plan_ophist(n, gates, tile_bits=12, low_bits=5, max_cost=0.0):

@@ -199,6 +199,9 @@ int dist_remap(qm_state* st, std::vector<LGate>* gates, std::vector<char>* done)
     return QM_OK;
 }
 
+// qm_reset rewrites the basis state in the canonical layout and sets perm to the identity: the layout flag follows
+void dist_reset(qm_state* st) { if (st->dist) st->dist->swapped = false; }
+
 int dist_canonicalize(qm_state* st) {
     if (!st->dist || !st->dist->swapped) return QM_OK;
     return dist_remap(st, nullptr, nullptr);

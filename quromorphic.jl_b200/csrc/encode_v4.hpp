@@ -1,0 +1,192 @@
+// encode_v4.hpp — host only: PlanPass -> V4Program, the byte image the fused TMA kernel interprets (layout in
+// fused_tma.cuh, opcodes in v4_ops.inc / tools/gen_v4_dispatch.py).  Shared by the engine (qm_api.cu) and by the
+// host emulator of the test suite (tests/native/emu_api.cu), so both see the same bytes.
+#pragma once
+#include <stddef.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "fused_tma.cuh"
+#include "lifting.hpp"
+#include "planner.hpp"
+
+namespace qm {
+
+// the planner limits of the TMA kernel, in one place (engine, introspection and emulator must agree)
+inline void v4_planner_options(PlanOptions& o, double max_cost) {
+    o.max_runs = 3; o.max_run_len = 8; o.max_subs = kV4MaxSubs; o.max_groups = kV4MaxGroups;
+    o.max_outer = kV4MaxOuter; o.warp_uniform_ctrl = true; o.block_bits = kV4BlockBits;
+    o.group_cost = kV4GroupCost; o.retile = true;
+    if (max_cost > 0 && o.max_cost < kV4GroupCost + 5.0) o.max_cost = kV4GroupCost + 5.0;
+}
+
+// decode op -> family (0 ROT, 1 ROTX, 2 PHASE, 3 PERMX, 4 THR), variant, B, CB
+inline bool v4_decode_op(uint32_t op, int& fam, int& var, int& B, int& CB) {
+    auto bc = [&](int idx) {
+        int i = 0;
+        for (int b = 0; b < kV4BlockBits; ++b) for (int c = -1; c < kV4BlockBits; ++c) { if (c == b) continue; if (i == idx) { B = b; CB = c; return; } ++i; }
+    };
+    if (op < (uint32_t)V4_OP_ROTX) { fam = 0; var = op / V4_NBC; bc(op % V4_NBC); return true; }
+    if (op < (uint32_t)V4_OP_PHASE) { fam = 1; var = (op - V4_OP_ROTX) / V4_NBC; bc((op - V4_OP_ROTX) % V4_NBC); return true; }
+    if (op < (uint32_t)V4_OP_PERMX) { fam = 2; var = (op - V4_OP_PHASE) / V4_NBC; bc((op - V4_OP_PHASE) % V4_NBC); return true; }
+    if (op < (uint32_t)V4_OP_THR) { fam = 3; var = 0; bc(op - V4_OP_PERMX); return true; }
+    if (op < (uint32_t)V4_NUM_GATE_OPS) { fam = 4; var = (op - V4_OP_THR) / (kV4BlockBits + 1); B = -1; CB = (int)((op - V4_OP_THR) % (kV4BlockBits + 1)) - 1; return true; }
+    return false;
+}
+
+// runs of consecutive bits in hb (ascending), cut after 8 bits: one TMA box dimension holds at most 256 elements
+inline int hb_runs(const std::vector<int>& hb, int start[8], int len[8]) {
+    int nr = 0;
+    for (size_t i = 0; i < hb.size(); ++i) {
+        if (nr > 0 && hb[i] == start[nr - 1] + len[nr - 1] && len[nr - 1] < 8) { len[nr - 1]++; continue; }
+        if (nr == 8) return 99;
+        start[nr] = hb[i]; len[nr] = 1; ++nr;
+    }
+    return nr;
+}
+
+// PlanPass -> V4Program (layout in fused_tma.cuh).  Returns false when the pass breaks a limit of the
+// kernel that the planner is supposed to respect (context bits, warp-uniform controls); the caller then
+// falls back to the general kernel.
+inline bool encode_v4(const PlanPass& P, V4Program& out) {
+    memset(&out, 0, offsetof(V4Program, recs));
+    out.ngroups = (int)P.groups.size();
+    int outer_of[64]; for (int i = 0; i < 64; ++i) outer_of[i] = -1;
+    int n_outer = 0, nrec = 0;
+    bool ok = true;
+    // context bit of a physical index bit that is not a register-block bit of the current group
+    auto ctx_bit = [&](int phys) -> uint32_t {
+        const int tl = tile_local_of(P, phys);
+        if (tl >= 0) return 1u << tl;
+        if (outer_of[phys] < 0) {
+            if (n_outer >= kV4MaxOuter) { ok = false; return 0u; }
+            outer_of[phys] = n_outer;
+            out.outer_pack[n_outer / 10] |= (uint64_t)phys << (6 * (n_outer % 10));
+            ++n_outer;
+        }
+        return 1u << (kV4CtxOuter + outer_of[phys]);
+    };
+    const int NB = kV4BlockBits;
+    const int nwarp_bits = P.m - NB - 5;
+    for (size_t gi = 0; gi < P.groups.size(); ++gi) {
+        const PlanGroup& G = P.groups[gi];
+        V4Group& g = out.groups[gi];
+        int rbl[NB]; for (int i = 0; i < NB; ++i) rbl[i] = -1;
+        uint32_t blockmask = 0; int nrb = 0;
+        for (size_t i = 0; i < G.rb.size() && nrb < NB; ++i) { rbl[nrb] = tile_local_of(P, G.rb[i]); blockmask |= 1u << rbl[nrb]; ++nrb; }
+        // always four block bits: pad with tile bits no gate of this group targets (highest first)
+        for (int b = P.m - 1; b >= 0 && nrb < NB; --b) if (!((blockmask >> b) & 1)) { rbl[nrb++] = b; blockmask |= 1u << b; }
+        std::sort(rbl, rbl + NB);
+        for (int i = 0; i < NB; ++i) { const uint32_t mk = 1u << rbl[i]; g.s[i] = (mk ^ ((mk >> 3) & 7u)) << 4; }
+        // Thread-index bit order.  The three lowest thread bits must give distinct 16-byte bank groups under
+        // slot = i ^ ((i >> 3) & 7): bit k of the slot's low 3 bits is i_k ^ i_{k+3}, so pick a free bit from
+        // {k, k+3} for k = 0, 1, 2.  Bits the planner pinned to the warp index (controls that are not block
+        // bits) go last.
+        uint32_t wmask = 0;
+        for (int b : G.wb) { const int tl = tile_local_of(P, b); if (tl >= 0 && !((blockmask >> tl) & 1)) wmask |= 1u << tl; }
+        std::vector<int> order; uint32_t used = blockmask | wmask;
+        for (int k = 0; k < 3; ++k) {
+            int pick = -1;
+            if (!((used >> k) & 1)) pick = k; else if (!((used >> (k + 3)) & 1)) pick = k + 3;
+            if (pick >= 0) { order.push_back(pick); used |= 1u << pick; }
+        }
+        for (int b = 0; b < P.m; ++b) if (!((used >> b) & 1)) { order.push_back(b); used |= 1u << b; }
+        for (int b = 0; b < P.m; ++b) if ((wmask >> b) & 1) order.push_back(b);
+        if ((int)order.size() != P.m - NB || __builtin_popcount(wmask) > nwarp_bits) { ok = false; break; }
+        for (int lane = 0; lane < 32; ++lane) {
+            uint32_t v = 0; for (int j = 0; j < 5; ++j) if ((lane >> j) & 1) v |= 1u << order[j];
+            out.lane_tab[gi][lane] = (uint16_t)v;
+        }
+        for (int w = 0; w < (1 << nwarp_bits); ++w) {
+            uint32_t v = 0; for (int j = 0; j < nwarp_bits; ++j) if ((w >> j) & 1) v |= 1u << order[5 + j];
+            out.warp_tab[gi][w] = (uint16_t)v;
+        }
+        g.rec_off = (uint32_t)(offsetof(V4Program, recs) + (size_t)nrec * sizeof(V4Rec));
+        // A tail of x! / cnot! gates whose target AND control are register-block bits only permutes the thread's own
+        // sixteen amplitudes: register k ends up at block index A k + c over GF(2).  The swizzled offsets are
+        // xor-linear, so the tail is folded into the offsets the END record hands to the stores (v4_dispatch.inc)
+        // instead of being executed: store offset of block bit j = xor_i A[i][j] s[i], base xor = xor_i c[i] s[i].
+        auto block_index = [&](int phys) { const int tl = tile_local_of(P, phys); if (tl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == tl) return i; return -1; };
+        size_t nexec = G.subs.size();
+        while (nexec > 0) {
+            const LGate& x = G.subs[nexec - 1];
+            LiftCoef Lt;
+            if (x.slot >= 0 || x.diag || lift_classify(x.m, Lt) != LK_PERMX || block_index(x.target) < 0) break;
+            if (x.ctrl >= 0 && block_index(x.ctrl) < 0) break;
+            --nexec;
+        }
+        uint32_t Arow[NB], cvec = 0;                 // Arow[i] = row i of A as a bit mask over k's bits
+        for (int i = 0; i < NB; ++i) Arow[i] = 1u << i;
+        for (size_t q = nexec; q < G.subs.size(); ++q) {
+            const LGate& x = G.subs[q];
+            const int b = block_index(x.target);
+            if (x.ctrl < 0) cvec ^= 1u << b;
+            else { const int a = block_index(x.ctrl); Arow[b] ^= Arow[a]; cvec ^= ((cvec >> a) & 1u) << b; }
+        }
+        for (size_t qi = 0; qi < nexec; ++qi) {
+            const LGate& x = G.subs[qi];
+            if (nrec + 4 > kV4MaxRecs) { ok = false; break; }
+            int CB = -1; uint32_t cm = 0;
+            if (x.ctrl >= 0) {
+                const int cl = tile_local_of(P, x.ctrl);
+                int bi = -1; if (cl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == cl) bi = i;
+                if (bi >= 0) CB = bi;
+                else {
+                    cm = ctx_bit(x.ctrl);
+                    if (cl >= 0 && !((wmask >> cl) & 1)) ok = false;      // the control predicate must be warp-uniform
+                }
+            }
+            if (x.slot >= 0) {                 // per-state coefficients: a SLOT record in front of the gate
+                V4Rec& R = out.recs[nrec++]; memset(&R, 0, sizeof(R));
+                R.op = V4_OP_SLOT; R.aux = (uint32_t)x.slot;
+            }
+            V4Rec& S = out.recs[nrec++]; memset(&S, 0, sizeof(S));
+            const int tl = tile_local_of(P, x.target);
+            int bi = -1; if (tl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == tl) bi = i;
+            if (!x.diag && bi < 0) ok = false;
+            LiftCoef Lc; memset(&Lc, 0, sizeof(Lc));
+            const int kind = x.slot >= 0 ? x.skind : lift_classify(x.m, Lc);   // liftable was checked by v4_eligible
+            double cc[6]; memcpy(cc, Lc.c, sizeof(cc));
+            // static sign variants: sg = (mk[0] ? 1 : 0) | (mk[1] ? 2 : 0); per-state slots are built for sg 0
+            const int sgA = (Lc.mk[0] ? 1 : 0) | (Lc.mk[1] ? 2 : 0), sgB = (Lc.mk[2] ? 1 : 0) | (Lc.mk[3] ? 2 : 0);
+            if (kind == LK_PHASE && bi < 0) {
+                // the target bit is constant for the thread: pick one of two coefficient sets
+                S.tm = ctx_bit(x.target);
+                int variant;
+                if (sgA == sgB && (sgA == 0 || sgA == 3)) variant = sgA == 3 ? 1 : 0;
+                else {                          // halves with different signs (z!): plain complex multiply by d0 / d1
+                    variant = 2;
+                    cc[0] = x.m[0]; cc[1] = x.m[1]; cc[2] = 0; cc[3] = x.m[6]; cc[4] = x.m[7]; cc[5] = 0;
+                }
+                S.op = (uint32_t)(V4_OP_THR + variant * (NB + 1) + (CB + 1));
+            } else {
+                const int bc = v4_bc_index(bi, CB);
+                int base;
+                if (kind == LK_ROT) base = sgA * V4_NBC;
+                else if (kind == LK_ROTX) base = V4_OP_ROTX + (sgA == 3 ? V4_NBC : 0);
+                else if (kind == LK_PHASE) base = V4_OP_PHASE + ((sgA == 3 ? 2 : 0) + (sgB == 3 ? 1 : 0)) * V4_NBC;
+                else base = V4_OP_PERMX;
+                S.op = (uint32_t)(base + bc);
+            }
+            if (cm) { S.op += V4_NUM_GATE_OPS; S.cm = cm; }      // a control outside the register block: the body's controlled entry
+            for (int q = 0; q < 3; ++q) { S.c[2 * q] = cc[q]; S.c[2 * q + 1] = cc[3 + q]; }     // pairwise {set 0, set 1}
+        }
+        if (!ok) break;
+        V4Rec& E = out.recs[nrec++]; memset(&E, 0, sizeof(E));
+        E.op = V4_OP_END;
+        uint32_t so[NB] = { 0, 0, 0, 0 }, delta = 0;
+        for (int i = 0; i < NB; ++i) {
+            for (int j = 0; j < NB; ++j) if ((Arow[i] >> j) & 1u) so[j] ^= g.s[i];
+            if ((cvec >> i) & 1u) delta ^= g.s[i];
+        }
+        E.tm = so[0]; E.cm = so[1]; E.aux = so[2];
+        const uint64_t packed = (uint64_t)so[3] | ((uint64_t)delta << 32);
+        memcpy(&E.c[0], &packed, 8);
+    }
+    out.nrecs = nrec; out.n_outer = n_outer; out.ctx_const = 0;
+    return ok;
+}
+
+
+}  // namespace qm

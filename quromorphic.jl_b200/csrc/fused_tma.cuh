@@ -99,15 +99,24 @@ __host__ __device__ inline int v4_bc_index(int B, int CB) {     // position of (
     return 0;
 }
 
+static const int kV4Gaps = 6;          // <= 3 runs of high tile bits + <= 3 pinned slab bits, merged in ascending order
+static const int kV4TraceStride = 8;   // phase trace: 8 clock stamps per tile of CTA 0 (diagnostics)
+
 struct V4Launch {
-    uint64_t ntiles;        // over the whole batch
+    uint64_t ntiles;        // tiles this launch covers (the whole batch, or one slab of it)
     int32_t  reg_bits;      // index bits of one register
     int32_t  L;             // low bits
-    int32_t  run_start[3];  // the high tile bits as <= 3 runs of consecutive index bits (ascending)
-    int32_t  run_len[3];
+    // The tile index enumerates the index bits that are NOT tile bits and not pinned; gaps are opened for the runs
+    // of high tile bits (they stay zero: the TMA box spans them) and for pinned bits (fixed_or supplies their value).
+    int32_t  gap_start[kV4Gaps];
+    int32_t  gap_len[kV4Gaps];
+    uint64_t fixed_or;      // slab launches (sharded registers, exchange overlapped with passes): index bits pinned to a value
     uint64_t rank_or;
     int32_t  nslots;
     int32_t  rowdim;        // which TMA dimension (1..4) takes the tile's base row as its coordinate
+    int32_t  sm_cap;        // 0 = all SMs; otherwise the persistent grid leaves the other SMs to a concurrent exchange kernel
+    int32_t  nfixed;        // number of pinned bits (they are not enumerated by the tile index)
+    unsigned long long* trace;   // nullptr, or device buffer of kV4TraceStride stamps per tile of CTA 0
 };
 
 static const int kV4ProducerThreads = 128;     // a whole warpgroup, so that setmaxnreg can hand its registers over

@@ -77,13 +77,17 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     constexpr uint32_t TILE_BYTES = 16u << M;
     static_assert(TEAMS <= STAGES && NCOMP % 128 == 0 && TEAM % 32 == 0, "team shape");
     extern __shared__ unsigned char smem_dyn[];
-    // [stages][TILE_BYTES] | lane_tab, warp_tab | gate records | per-team slot bases | barriers ; SWIZZLE_128B needs the stages 1024-byte aligned
+    // [stages][TILE_BYTES] | lane_tab, warp_tab | gate records | per-stage tile descriptors | barriers ; SWIZZLE_128B needs the stages 1024-byte aligned
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* stage_base = smem;
     unsigned char* tabs = smem + (size_t)STAGES * TILE_BYTES;
     unsigned char* recs = tabs + kV4TabBytes;
-    uint64_t* slot_bases = reinterpret_cast<uint64_t*>(recs + sizeof(V4Rec) * kV4MaxRecs);     // two per team (tile parity)
-    uint64_t* full = slot_bases + 8;
+    // One 16-byte descriptor per stage, written by the producer lane together with the TMA load of the tile that goes
+    // into the stage: {per-state coefficient base of the tile's register, outer context word}.  Everything a compute
+    // thread needs to know about WHICH tile it holds — so the 512 compute threads never decode a tile index (the
+    // first version did: 145 of ~1270 instructions per thread per tile, ncu r1m).
+    uint64_t* tdesc = reinterpret_cast<uint64_t*>(recs + sizeof(V4Rec) * kV4MaxRecs);          // [STAGES][2], room for 8 stages
+    uint64_t* full = tdesc + 16;
     uint64_t* computed = full + 2 * STAGES;
     // full[] holds TWO barriers per stage, used alternately (use k = i / STAGES of a stage takes barrier
     // s + STAGES * (k & 1), parity (k >> 1) & 1).  With one barrier a parity wait cannot tell "use k has
@@ -113,53 +117,77 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     }
     __syncthreads();
 
-    const int tbits = lp.reg_bits - M;
+    const int tbits = lp.reg_bits - M - lp.nfixed;      // tile-index bits per register
     const uint64_t first = blockIdx.x, step = gridDim.x;
     const uint64_t ntiles = lp.ntiles;
     const uint64_t my_tiles = first < ntiles ? (ntiles - first + step - 1) / step : 0;
+    // optional phase trace (diagnostics, tools/tile_timeline.py): CTA 0 writes SM-clock stamps per tile
+    unsigned long long* const trace = blockIdx.x == 0 ? lp.trace : nullptr;
 
-    auto tile_base = [&](uint64_t tile_id, uint64_t& gbase_out, uint64_t& breg_out) -> uint64_t {
-        const uint64_t breg = tile_id >> tbits;
-        uint64_t base = (tile_id & ((1ull << tbits) - 1ull)) << lp.L;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {           // open a gap of run_len zero bits at run_start
-            const uint64_t lo = base & ((1ull << lp.run_start[j]) - 1ull);
-            base = ((base >> lp.run_start[j]) << (lp.run_start[j] + lp.run_len[j])) | lo;
-        }
-        gbase_out = base | lp.rank_or; breg_out = breg;
-        return (breg << lp.reg_bits) + base;      // amplitude index of the tile's first element in the whole array
-    };
-
-    // the tile's base row goes into TMA coordinate lp.rowdim, the other coordinates are 0
-#define TMA_COORDS(b) const int tr_ = (int)((b) >> 3), tc1 = lp.rowdim == 1 ? tr_ : 0, tc2 = lp.rowdim == 2 ? tr_ : 0, \
-                      tc3 = lp.rowdim == 3 ? tr_ : 0, tc4 = lp.rowdim == 4 ? tr_ : 0
     if (tid >= NCOMP) {
         // ===================== producer warpgroup: one elected lane drives TMA =====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (tid == NCOMP) {
-            uint64_t gb, br;
+            const int n_outer = P.n_outer;
+            const uint32_t ctx_const = P.ctx_const | kV4CtxAlways;
+            const uint64_t opk0 = P.outer_pack[0], opk1 = P.outer_pack[1];
+            // tile index -> amplitude index of its first element in the whole array (TMA row coordinate), plus the
+            // stage descriptor {slot base, outer context word}
+            auto tile_base = [&](uint64_t tile_id, uint64_t& d0, uint64_t& d1) -> uint64_t {
+                const uint64_t breg = tile_id >> tbits;
+                uint64_t base = (tile_id & ((1ull << tbits) - 1ull)) << lp.L;
+#pragma unroll
+                for (int j = 0; j < kV4Gaps; ++j) {     // open a gap of gap_len zero bits at gap_start (ascending)
+                    const uint64_t lo = base & ((1ull << lp.gap_start[j]) - 1ull);
+                    base = ((base >> lp.gap_start[j]) << (lp.gap_start[j] + lp.gap_len[j])) | lo;
+                }
+                base |= lp.fixed_or;                    // slab launches: some index bits pinned to a value
+                const uint64_t gbase = base | lp.rank_or;
+                // outer part of the context word: the index bits outside the tile that some gate of this pass
+                // uses as a control or as the target of a diagonal gate
+                uint32_t octx = ctx_const;
+                uint64_t pk = opk0;
+                for (int j = 0; j < n_outer; ++j) {
+                    octx |= (uint32_t)((gbase >> (pk & 63ull)) & 1ull) << (kV4CtxOuter + j);
+                    pk >>= 6;
+                    if (j == 9) pk = opk1;
+                }
+                d0 = slots ? (uint64_t)(slots + (size_t)breg * lp.nslots * 8) : 0ull;
+                d1 = octx;
+                return (breg << lp.reg_bits) + base;
+            };
+            // the tile's base row goes into TMA coordinate lp.rowdim, the other coordinates are 0
+#define TMA_COORDS(b) const int tr_ = (int)((b) >> 3), tc1 = lp.rowdim == 1 ? tr_ : 0, tc2 = lp.rowdim == 2 ? tr_ : 0, \
+                      tc3 = lp.rowdim == 3 ? tr_ : 0, tc4 = lp.rowdim == 4 ? tr_ : 0
+            uint64_t d0, d1;
             const uint64_t pro = my_tiles < (uint64_t)STAGES ? my_tiles : (uint64_t)STAGES;
             for (uint64_t i = 0; i < pro; ++i) {
-                const uint64_t base = tile_base(first + i * step, gb, br);
-                mbar_arrive_expect_tx(&full[i], TILE_BYTES);
+                const uint64_t base = tile_base(first + i * step, d0, d1);
+                tdesc[2 * i] = d0; tdesc[2 * i + 1] = d1;
+                mbar_arrive_expect_tx(&full[i], TILE_BYTES);        // release: the descriptor is visible to whoever sees the phase
                 TMA_COORDS(base);
                 tma_load_5d(stage_base + i * TILE_BYTES, &tmap, &full[i], 0, tc1, tc2, tc3, tc4);
             }
             for (uint64_t i = 0; i < my_tiles; ++i) {
                 const int s = (int)(i % STAGES);
                 const uint32_t ph = (uint32_t)((i / STAGES) & 1);
+                const uint64_t nxt = i + STAGES;
+                // everything that does not depend on the wait is done before it
+                uint64_t n0 = 0, n1 = 0, nbase = 0, dd0, dd1;
+                const uint64_t base = tile_base(first + i * step, dd0, dd1);
+                if (nxt < my_tiles) nbase = tile_base(first + nxt * step, n0, n1);
                 mbar_wait_sleep(&computed[s], ph);
-                const uint64_t base = tile_base(first + i * step, gb, br);
+                if (trace) trace[kV4TraceStride * i + 6] = clock64();
                 { TMA_COORDS(base); tma_store_5d(&tmap, stage_base + (size_t)s * TILE_BYTES, 0, tc1, tc2, tc3, tc4); }
                 tma_commit();
-                const uint64_t nxt = i + STAGES;
                 if (nxt < my_tiles) {
                     tma_wait_read0();            // the store has read the buffer: safe to overwrite
-                    const uint64_t nbase = tile_base(first + nxt * step, gb, br);
                     uint64_t* fb = &full[s + STAGES * (int)((nxt / STAGES) & 1)];
+                    tdesc[2 * s] = n0; tdesc[2 * s + 1] = n1;
                     mbar_arrive_expect_tx(fb, TILE_BYTES);
                     TMA_COORDS(nbase);
                     tma_load_5d(stage_base + (size_t)s * TILE_BYTES, &tmap, fb, 0, tc1, tc2, tc3, tc4);
+                    if (trace) trace[kV4TraceStride * i + 7] = clock64();
                 }
             }
             tma_wait_all0();
@@ -171,38 +199,21 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int team = tid / TEAM, ttid = tid % TEAM;
     const int lane = ttid & 31, warp = ttid >> 5;
-    const int ngroups = P.ngroups, n_outer = P.n_outer;
-    const uint32_t ctx_const = P.ctx_const | kV4CtxAlways;
-    const uint64_t opk0 = P.outer_pack[0], opk1 = P.outer_pack[1];
+    const int ngroups = P.ngroups;
     const uint32_t stage_s = smem_u32(stage_base);
-    uint32_t slot_s = smem_u32(slot_bases) + 16u * team;
+    const uint32_t desc_s = smem_u32(tdesc);
     const uint32_t lane_s = smem_u32(tabs) + 2u * lane, warp_s = smem_u32(tabs) + 2u * (kV4MaxGroups * 32 + warp);
     int s = team % STAGES; uint32_t k = 0;        // stage and use count of the stage (tile i: s = i % STAGES, k = i / STAGES)
 #pragma unroll 1
     for (uint32_t i = team; i < (uint32_t)my_tiles; i += TEAMS) {
-        uint64_t gbase, breg;
-        tile_base((uint64_t)blockIdx.x + (uint64_t)i * gridDim.x, gbase, breg);
-        // outer part of the context word: the index bits outside the tile that some gate of this pass
-        // uses as a control or as the target of a diagonal gate
-        uint32_t octx = ctx_const;
-        {
-            uint64_t pk = opk0;
-            for (int j = 0; j < n_outer; ++j) {
-                octx |= (uint32_t)((gbase >> (pk & 63ull)) & 1ull) << (kV4CtxOuter + j);
-                pk >>= 6;
-                if (j == 9) pk = opk1;
-            }
-        }
-        // per-state coefficient base of this tile's register, double-buffered by tile parity: the first thread of
-        // the team may already be here while slower warps still read the previous tile's entry
-        slot_s ^= 8u;
-        if (slots && ttid == 0) {
-            const uint64_t sb = (uint64_t)(slots + (size_t)breg * lp.nslots * 8);
-            asm volatile("st.shared.u64 [%0], %1;" ::"r"(slot_s), "l"(sb) : "memory");
-        }
         const uint32_t tile_s = stage_s + (uint32_t)s * TILE_BYTES;
+        const uint32_t slot_s = desc_s + 16u * (uint32_t)s;        // the SLOT record reads the coefficient base from here
+        const bool tr = trace && ttid == 0;
+        if (tr) trace[kV4TraceStride * i + 0] = clock64();
         mbar_wait(&full[s + STAGES * (int)(k & 1u)], (k >> 1) & 1u);
-        if (slots) bar_sync_named(1 + team, TEAM);       // the team sees its slot base
+        if (tr) trace[kV4TraceStride * i + 1] = clock64();
+        uint32_t octx;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(octx) : "r"(slot_s + 8u));
 #pragma unroll 1
         for (int gi = 0; gi < ngroups; ++gi) {
             const uint64_t ga = pa + offsetof(V4Program, groups) + 32u * gi;
@@ -222,11 +233,13 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
                          : "r"(ctx), "r"(slot_s), "r"(tile_s), "r"(b0), "r"((uint32_t)g01), "r"((uint32_t)(g01 >> 32)),
                            "r"((uint32_t)g23), "r"((uint32_t)(g23 >> 32))
                          : "memory");
+            if (tr && gi < 3) trace[kV4TraceStride * i + 2 + gi] = clock64();
             if (gi + 1 < ngroups) bar_sync_named(1 + team, TEAM);
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&computed[s]);
+        if (tr) trace[kV4TraceStride * i + 5] = clock64();
         s += TEAMS; if (s >= STAGES) { s -= STAGES; ++k; }
     }
 }
@@ -235,10 +248,15 @@ template <int M, int TEAMS, int STAGES>
 static int launch_v4_t(cudaStream_t stream, int sms, const CUtensorMap& tm, const V4Program& prog, const double* d_slots,
                        const V4Launch& lp) {
     constexpr int threads = TEAMS * (1 << (M - kV4BlockBits)) + kV4ProducerThreads;
-    constexpr size_t smem = (size_t)STAGES * (16u << M) + kV4TabBytes + sizeof(V4Rec) * kV4MaxRecs + 64 + 3 * STAGES * 8 + 1024;
-    static bool attr = false;
-    if (!attr) { CU(cudaFuncSetAttribute(k_fused_tma<M, TEAMS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    const uint64_t cap = (uint64_t)sms;
+    constexpr size_t smem = (size_t)STAGES * (16u << M) + kV4TabBytes + sizeof(V4Rec) * kV4MaxRecs + 128 + 3 * STAGES * 8 + 1024;
+    // the attribute belongs to the device, not to the process: one flag per device (qm_create takes `device`)
+    static bool attr[64] = { false };
+    int dev = 0; CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
+        CU(cudaFuncSetAttribute(k_fused_tma<M, TEAMS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) attr[dev] = true;
+    }
+    const uint64_t cap = (uint64_t)(lp.sm_cap > 0 && lp.sm_cap < sms ? lp.sm_cap : sms);
     const int grid = (int)(lp.ntiles < cap ? lp.ntiles : cap);
     k_fused_tma<M, TEAMS, STAGES><<<grid, threads, smem, stream>>>(tm, prog, d_slots, lp);
     CU(cudaGetLastError());

@@ -11,7 +11,7 @@
 
 #include "../../include/qm_b200.h"
 #include "dist.hpp"
-#include "emulate.hpp"
+#include "encode_v4.hpp"
 #include "fused_tma.cuh"
 #include "kernels.cuh"
 #include "lifting.hpp"
@@ -43,6 +43,8 @@ int ensure_pinned(void** p, size_t* cap, size_t need) {
     return QM_OK;
 }
 
+
+static const size_t kTraceBytes = 8u << 20;      // QM_OPT_TRACE buffer: 8 stamps x 8 bytes x up to 131072 tiles of CTA 0
 
 static int grid_for(uint64_t work_items, int threads, int sms, int per_sm) {
     uint64_t blocks = (work_items + threads - 1) / threads;
@@ -94,6 +96,7 @@ extern "C" int32_t qm_destroy(qm_state* st) {
     cudaSetDevice(st->device);
     if (st->stream) cudaStreamSynchronize(st->stream);
     if (st->dist) { dist_destroy(st->dist); st->dist = nullptr; }
+    cudaFree(st->trace_buf);
     cudaFree(st->amp); cudaFree(st->d_blob); cudaFree(st->d_scratch); cudaFree(st->d_slots);
     cudaFreeHost(st->h_blob); cudaFreeHost(st->h_scratch);
     if (st->ev0) cudaEventDestroy(st->ev0);
@@ -110,6 +113,7 @@ extern "C" int32_t qm_reset(qm_state* st, uint64_t basis) {
     CU(cudaSetDevice(st->device));
     st->queue.clear();
     for (int i = 0; i < st->n; ++i) st->perm[i] = i;
+    dist_reset(st);
     CU(cudaMemsetAsync(st->amp, 0, (size_t)total_amps(st) * 16, st->stream));
     uint64_t owner = st->g ? (basis >> st->nl) : 0;
     if ((int)owner == st->rank) {
@@ -132,7 +136,11 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
         if (value < 0 || value > 8) return set_err(QM_ERR_ARG, "low bits must be in [0, 8]");
         st->low_bits = (int)value; break;
     case QM_OPT_FUSE: st->fuse = value != 0; break;
-    case QM_OPT_REMAP: st->remap = value != 0; break;
+    case QM_OPT_TRACE:
+        CU(cudaSetDevice(st->device));
+        if (value && !st->trace_buf) { CU(cudaMalloc((void**)&st->trace_buf, kTraceBytes)); CU(cudaMemset(st->trace_buf, 0, kTraceBytes)); }
+        if (!value && st->trace_buf) { CU(cudaStreamSynchronize(st->stream)); cudaFree(st->trace_buf); st->trace_buf = nullptr; }
+        break;
     case QM_OPT_PIPELINE: st->pipeline = value != 0; break;
     case QM_OPT_MAX_COST: st->max_cost = (double)value; break;
     case QM_OPT_TIME_PASSES: st->time_passes = value != 0; break;
@@ -205,17 +213,6 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// runs of consecutive bits in hb (ascending), cut after 8 bits: one TMA box dimension holds at most 256 elements
-static int hb_runs(const std::vector<int>& hb, int start[8], int len[8]) {
-    int nr = 0;
-    for (size_t i = 0; i < hb.size(); ++i) {
-        if (nr > 0 && hb[i] == start[nr - 1] + len[nr - 1] && len[nr - 1] < 8) { len[nr - 1]++; continue; }
-        if (nr == 8) return 99;
-        start[nr] = hb[i]; len[nr] = 1; ++nr;
-    }
-    return nr;
-}
-
 // can this pass go through the TMA kernel?
 static bool v4_eligible(const qm_state* st, const PlanPass& P) {
     if (!st->pipeline || !get_encode()) return false;
@@ -234,149 +231,11 @@ static bool v4_eligible(const qm_state* st, const PlanPass& P) {
     return true;
 }
 
-// PlanPass -> V4Program (layout in fused_tma.cuh).  Returns false when the pass breaks a limit of the
-// kernel that the planner is supposed to respect (context bits, warp-uniform controls); the caller then
-// falls back to the general kernel.
-static bool encode_v4(const PlanPass& P, V4Program& out) {
-    memset(&out, 0, offsetof(V4Program, recs));
-    out.ngroups = (int)P.groups.size();
-    int outer_of[64]; for (int i = 0; i < 64; ++i) outer_of[i] = -1;
-    int n_outer = 0, nrec = 0;
-    bool ok = true;
-    // context bit of a physical index bit that is not a register-block bit of the current group
-    auto ctx_bit = [&](int phys) -> uint32_t {
-        const int tl = tile_local_of(P, phys);
-        if (tl >= 0) return 1u << tl;
-        if (outer_of[phys] < 0) {
-            if (n_outer >= kV4MaxOuter) { ok = false; return 0u; }
-            outer_of[phys] = n_outer;
-            out.outer_pack[n_outer / 10] |= (uint64_t)phys << (6 * (n_outer % 10));
-            ++n_outer;
-        }
-        return 1u << (kV4CtxOuter + outer_of[phys]);
-    };
-    const int NB = kV4BlockBits;
-    const int nwarp_bits = P.m - NB - 5;
-    for (size_t gi = 0; gi < P.groups.size(); ++gi) {
-        const PlanGroup& G = P.groups[gi];
-        V4Group& g = out.groups[gi];
-        int rbl[NB]; for (int i = 0; i < NB; ++i) rbl[i] = -1;
-        uint32_t blockmask = 0; int nrb = 0;
-        for (size_t i = 0; i < G.rb.size() && nrb < NB; ++i) { rbl[nrb] = tile_local_of(P, G.rb[i]); blockmask |= 1u << rbl[nrb]; ++nrb; }
-        // always four block bits: pad with tile bits no gate of this group targets (highest first)
-        for (int b = P.m - 1; b >= 0 && nrb < NB; --b) if (!((blockmask >> b) & 1)) { rbl[nrb++] = b; blockmask |= 1u << b; }
-        std::sort(rbl, rbl + NB);
-        for (int i = 0; i < NB; ++i) { const uint32_t mk = 1u << rbl[i]; g.s[i] = (mk ^ ((mk >> 3) & 7u)) << 4; }
-        // Thread-index bit order.  The three lowest thread bits must give distinct 16-byte bank groups under
-        // slot = i ^ ((i >> 3) & 7): bit k of the slot's low 3 bits is i_k ^ i_{k+3}, so pick a free bit from
-        // {k, k+3} for k = 0, 1, 2.  Bits the planner pinned to the warp index (controls that are not block
-        // bits) go last.
-        uint32_t wmask = 0;
-        for (int b : G.wb) { const int tl = tile_local_of(P, b); if (tl >= 0 && !((blockmask >> tl) & 1)) wmask |= 1u << tl; }
-        std::vector<int> order; uint32_t used = blockmask | wmask;
-        for (int k = 0; k < 3; ++k) {
-            int pick = -1;
-            if (!((used >> k) & 1)) pick = k; else if (!((used >> (k + 3)) & 1)) pick = k + 3;
-            if (pick >= 0) { order.push_back(pick); used |= 1u << pick; }
-        }
-        for (int b = 0; b < P.m; ++b) if (!((used >> b) & 1)) { order.push_back(b); used |= 1u << b; }
-        for (int b = 0; b < P.m; ++b) if ((wmask >> b) & 1) order.push_back(b);
-        if ((int)order.size() != P.m - NB || __builtin_popcount(wmask) > nwarp_bits) { ok = false; break; }
-        for (int lane = 0; lane < 32; ++lane) {
-            uint32_t v = 0; for (int j = 0; j < 5; ++j) if ((lane >> j) & 1) v |= 1u << order[j];
-            out.lane_tab[gi][lane] = (uint16_t)v;
-        }
-        for (int w = 0; w < (1 << nwarp_bits); ++w) {
-            uint32_t v = 0; for (int j = 0; j < nwarp_bits; ++j) if ((w >> j) & 1) v |= 1u << order[5 + j];
-            out.warp_tab[gi][w] = (uint16_t)v;
-        }
-        g.rec_off = (uint32_t)(offsetof(V4Program, recs) + (size_t)nrec * sizeof(V4Rec));
-        // A tail of x! / cnot! gates whose target AND control are register-block bits only permutes the thread's own
-        // sixteen amplitudes: register k ends up at block index A k + c over GF(2).  The swizzled offsets are
-        // xor-linear, so the tail is folded into the offsets the END record hands to the stores (v4_dispatch.inc)
-        // instead of being executed: store offset of block bit j = xor_i A[i][j] s[i], base xor = xor_i c[i] s[i].
-        auto block_index = [&](int phys) { const int tl = tile_local_of(P, phys); if (tl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == tl) return i; return -1; };
-        size_t nexec = G.subs.size();
-        while (nexec > 0) {
-            const LGate& x = G.subs[nexec - 1];
-            LiftCoef Lt;
-            if (x.slot >= 0 || x.diag || lift_classify(x.m, Lt) != LK_PERMX || block_index(x.target) < 0) break;
-            if (x.ctrl >= 0 && block_index(x.ctrl) < 0) break;
-            --nexec;
-        }
-        uint32_t Arow[NB], cvec = 0;                 // Arow[i] = row i of A as a bit mask over k's bits
-        for (int i = 0; i < NB; ++i) Arow[i] = 1u << i;
-        for (size_t q = nexec; q < G.subs.size(); ++q) {
-            const LGate& x = G.subs[q];
-            const int b = block_index(x.target);
-            if (x.ctrl < 0) cvec ^= 1u << b;
-            else { const int a = block_index(x.ctrl); Arow[b] ^= Arow[a]; cvec ^= ((cvec >> a) & 1u) << b; }
-        }
-        for (size_t qi = 0; qi < nexec; ++qi) {
-            const LGate& x = G.subs[qi];
-            if (nrec + 4 > kV4MaxRecs) { ok = false; break; }
-            int CB = -1; uint32_t cm = 0;
-            if (x.ctrl >= 0) {
-                const int cl = tile_local_of(P, x.ctrl);
-                int bi = -1; if (cl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == cl) bi = i;
-                if (bi >= 0) CB = bi;
-                else {
-                    cm = ctx_bit(x.ctrl);
-                    if (cl >= 0 && !((wmask >> cl) & 1)) ok = false;      // the control predicate must be warp-uniform
-                }
-            }
-            if (x.slot >= 0) {                 // per-state coefficients: a SLOT record in front of the gate
-                V4Rec& R = out.recs[nrec++]; memset(&R, 0, sizeof(R));
-                R.op = V4_OP_SLOT; R.aux = (uint32_t)x.slot;
-            }
-            V4Rec& S = out.recs[nrec++]; memset(&S, 0, sizeof(S));
-            const int tl = tile_local_of(P, x.target);
-            int bi = -1; if (tl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == tl) bi = i;
-            if (!x.diag && bi < 0) ok = false;
-            LiftCoef Lc; memset(&Lc, 0, sizeof(Lc));
-            const int kind = x.slot >= 0 ? x.skind : lift_classify(x.m, Lc);   // liftable was checked by v4_eligible
-            double cc[6]; memcpy(cc, Lc.c, sizeof(cc));
-            // static sign variants: sg = (mk[0] ? 1 : 0) | (mk[1] ? 2 : 0); per-state slots are built for sg 0
-            const int sgA = (Lc.mk[0] ? 1 : 0) | (Lc.mk[1] ? 2 : 0), sgB = (Lc.mk[2] ? 1 : 0) | (Lc.mk[3] ? 2 : 0);
-            if (kind == LK_PHASE && bi < 0) {
-                // the target bit is constant for the thread: pick one of two coefficient sets
-                S.tm = ctx_bit(x.target);
-                int variant;
-                if (sgA == sgB && (sgA == 0 || sgA == 3)) variant = sgA == 3 ? 1 : 0;
-                else {                          // halves with different signs (z!): plain complex multiply by d0 / d1
-                    variant = 2;
-                    cc[0] = x.m[0]; cc[1] = x.m[1]; cc[2] = 0; cc[3] = x.m[6]; cc[4] = x.m[7]; cc[5] = 0;
-                }
-                S.op = (uint32_t)(V4_OP_THR + variant * (NB + 1) + (CB + 1));
-            } else {
-                const int bc = v4_bc_index(bi, CB);
-                int base;
-                if (kind == LK_ROT) base = sgA * V4_NBC;
-                else if (kind == LK_ROTX) base = V4_OP_ROTX + (sgA == 3 ? V4_NBC : 0);
-                else if (kind == LK_PHASE) base = V4_OP_PHASE + ((sgA == 3 ? 2 : 0) + (sgB == 3 ? 1 : 0)) * V4_NBC;
-                else base = V4_OP_PERMX;
-                S.op = (uint32_t)(base + bc);
-            }
-            if (cm) { S.op += V4_NUM_GATE_OPS; S.cm = cm; }      // a control outside the register block: the body's controlled entry
-            for (int q = 0; q < 3; ++q) { S.c[2 * q] = cc[q]; S.c[2 * q + 1] = cc[3 + q]; }     // pairwise {set 0, set 1}
-        }
-        if (!ok) break;
-        V4Rec& E = out.recs[nrec++]; memset(&E, 0, sizeof(E));
-        E.op = V4_OP_END;
-        uint32_t so[NB] = { 0, 0, 0, 0 }, delta = 0;
-        for (int i = 0; i < NB; ++i) {
-            for (int j = 0; j < NB; ++j) if ((Arow[i] >> j) & 1u) so[j] ^= g.s[i];
-            if ((cvec >> i) & 1u) delta ^= g.s[i];
-        }
-        E.tm = so[0]; E.cm = so[1]; E.aux = so[2];
-        const uint64_t packed = (uint64_t)so[3] | ((uint64_t)delta << 32);
-        memcpy(&E.c[0], &packed, 8);
-    }
-    out.nrecs = nrec; out.n_outer = n_outer; out.ctx_const = 0;
-    return ok;
-}
-
-static int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const double* d_slots, int nslots) {
+// slab: nullptr for a pass over the whole register; otherwise the pass covers only the amplitudes whose index bits
+// slab->bit[] have the values in slab->value_or (sharded registers: the exchange of one slab runs beside the passes
+// of its neighbours, dist.cu), on a grid of slab->sm_cap CTAs.
+int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const double* d_slots, int nslots,
+                   const PassSlab* slab, cudaStream_t stream) {
     // tensor map: dim0 = one 128-byte row (8 amplitudes = 16 doubles); dim1 = row index over the whole
     // array (the box takes 2^(L-3) consecutive rows at the tile's base); dims 2..4 = the runs of high
     // tile bits (size 2^len, stride 16 * 2^start bytes), unused dims have size 1.
@@ -407,14 +266,30 @@ static int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P
     const int nr = hb_runs(P.hb, rs, rl);
     V4Launch lp; memset(&lp, 0, sizeof(lp));
     lp.ntiles = amps >> P.m; lp.reg_bits = st->nl; lp.L = P.L; lp.rowdim = rowdim;
-    for (int i = 0; i < 3; ++i) { lp.run_start[i] = i < nr ? rs[i] : 0; lp.run_len[i] = i < nr ? rl[i] : 0; }
+    // gaps of the tile index, ascending: the runs of high tile bits and the pinned slab bits
+    std::vector<std::pair<int, int>> gaps;
+    for (int i = 0; i < nr; ++i) gaps.push_back({ rs[i], rl[i] });
+    if (slab) {
+        if (st->batch != 1 || slab->nbits > 3) return set_err(QM_ERR_STATE, "slab launch: bad shape (internal error)");
+        for (int i = 0; i < slab->nbits; ++i) {
+            if (tile_local_of(P, slab->bit[i]) >= 0 || slab->bit[i] >= st->nl) return set_err(QM_ERR_STATE, "slab bit %d is a tile bit (internal error)", slab->bit[i]);
+            gaps.push_back({ slab->bit[i], 1 });
+        }
+        lp.nfixed = slab->nbits; lp.fixed_or = slab->value_or; lp.sm_cap = slab->sm_cap;
+        lp.ntiles >>= slab->nbits;
+    }
+    std::sort(gaps.begin(), gaps.end());
+    if ((int)gaps.size() > kV4Gaps) return set_err(QM_ERR_STATE, "tile layout needs more than %d index gaps (internal error)", kV4Gaps);
+    for (int i = 0; i < kV4Gaps; ++i) { lp.gap_start[i] = i < (int)gaps.size() ? gaps[i].first : 0; lp.gap_len[i] = i < (int)gaps.size() ? gaps[i].second : 0; }
     lp.rank_or = st->g ? ((uint64_t)st->rank << st->nl) : 0; lp.nslots = nslots;
-    if (P.m == 11) QM_TRY(launch_v4_m11(st->stream, st->sms, tm, prog, d_slots, lp));
-    else QM_TRY(launch_v4_m12(st->stream, st->sms, tm, prog, d_slots, lp));
+    lp.trace = st->trace_buf;
+    if (P.m == 11) QM_TRY(launch_v4_m11(stream, st->sms, tm, prog, d_slots, lp));
+    else QM_TRY(launch_v4_m12(stream, st->sms, tm, prog, d_slots, lp));
     // the program crosses the host link with the launch: counted as host->device bytes
     st->ctr.bytes_h2d += offsetof(V4Program, recs) + (size_t)prog.nrecs * sizeof(V4Rec);
-    st->ctr.launches++; st->ctr.passes++;
-    st->ctr.bytes_hbm += 32ull * amps;
+    st->ctr.launches++;
+    if (!slab || slab->index == 0) st->ctr.passes++;
+    st->ctr.bytes_hbm += (32ull * amps) >> (slab ? slab->nbits : 0);
     return QM_OK;
 }
 
@@ -467,10 +342,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         if (tma) pl.gates.swap(lifted);
     }
     if (tma) {
-        pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
-        pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
-        pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
-        if (st->max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 5.0) pl.opt.max_cost = kV4GroupCost + 5.0;
+        v4_planner_options(pl.opt, st->max_cost);
         if (smap) pl.opt.max_subs = (kV4MaxRecs - kV4MaxGroups) / 2;      // every per-state gate takes two records
     }
     pl.done.assign(pl.gates.size(), 0);
@@ -541,7 +413,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             for (size_t i = 0; i < passes.size(); ++i) {
                 cudaEvent_t ea = nullptr, eb = nullptr;
                 if (st->time_passes) { CU(cudaEventCreate(&ea)); CU(cudaEventCreate(&eb)); CU(cudaEventRecord(ea, st->stream)); }
-                if (v4_of[i] >= 0) QM_TRY(launch_pass_v4(st, v4progs[v4_of[i]], passes[i], d_slots_lift, nslots));
+                if (v4_of[i] >= 0) QM_TRY(launch_pass_v4(st, v4progs[v4_of[i]], passes[i], d_slots_lift, nslots, nullptr, st->stream));
                 else QM_TRY(launch_pass(st, st->d_blob + offs[i], passes[i], d_slots, nslots));
                 if (st->time_passes) {
                     CU(cudaEventRecord(eb, st->stream));
@@ -558,7 +430,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
                             uint32_t op = pr.recs[r].op;
                             if (op >= (uint32_t)V4_NUM_GATE_OPS) { if (op >= (uint32_t)V4_OP_SLOT) continue; op -= V4_NUM_GATE_OPS; }
                             int fam, var, B, CB;
-                            if (!emu_decode(op, fam, var, B, CB)) continue;
+                            if (!v4_decode_op(op, fam, var, B, CB)) continue;
                             if (fam == 3) kinds[2] += 1; else if (fam == 4) kinds[3] += 1; else if (CB >= 0) kinds[1] += 1; else kinds[0] += 1;
                         }
                     }
@@ -1106,13 +978,6 @@ extern "C" int32_t qm_device_ptr(qm_state* st, void** amps, void** stream) {
 
 // Planner introspection (host only).  Flat int32 layout, per step:
 //   [kind(0 pass | 1 remap), ngates, m, L, nhigh, hb[0..nhigh), ngroups, {nrb, rb[0..nrb), nsub}*ngroups]
-extern "C" int32_t qm_plan_describe(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
-                                    int32_t allow_remap, const qm_gate* gates, int32_t ngates, int32_t* out,
-                                    int64_t cap, int64_t* out_len) {
-    (void)allow_remap;
-    return qm_plan_describe_ex(n_qubits, global_bits, tile_bits, low_bits, 0.0, 0, gates, ngates, out, cap, out_len);
-}
-
 extern "C" int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits,
                                        double max_cost, int32_t pipeline, const qm_gate* gates, int32_t ngates,
                                        int32_t* out, int64_t cap, int64_t* out_len) {
@@ -1122,10 +987,7 @@ extern "C" int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, in
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
     if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
     if (pipeline) {
-        pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
-        pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
-        pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
-        if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 5.0) pl.opt.max_cost = kV4GroupCost + 5.0;
+        v4_planner_options(pl.opt, max_cost);
     }
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
@@ -1200,98 +1062,6 @@ extern "C" int32_t qm_plan_gates(int32_t n_qubits, int32_t global_bits, int32_t 
     return QM_OK;
 }
 
-// TEST INFRASTRUCTURE (host only, see emulate.hpp): plan `gates` exactly as the engine would for the TMA
-// kernel, encode every pass and walk the encoded programs over a host state vector.
-extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
-                                   const qm_gate* gates, int32_t ngates, double* state, int32_t* n_passes) {
-    if (!gates || !state || n_qubits < 11 || n_qubits > 24 || (tile_bits != 11 && tile_bits != 12) || tile_bits > n_qubits ||
-        low_bits < 3 || low_bits > 8)
-        return set_err(QM_ERR_ARG, "bad argument");
-    Planner pl;
-    pl.opt.n_local = n_qubits; pl.opt.n_global = 0;
-    pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
-    if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
-    pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
-    pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
-    pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
-    if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 5.0) pl.opt.max_cost = kV4GroupCost + 5.0;
-    int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
-    if (rc) return set_err(rc, "bad gate");
-    prepare_for_lifting(pl.gates);
-    for (const LGate& x : pl.gates) if (!x.liftable) return set_err(QM_ERR_STATE, "a gate has no lifting form");
-    pl.done.assign(pl.gates.size(), 0);
-    std::vector<V4Program> prog(1);
-    PlanPass P; int np = 0;
-    while (pl.next_pass(P)) {
-        choose_tile_layout(P);
-        if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
-        if (!emulate_v4(prog[0], P, reinterpret_cast<EmuAmp*>(state), n_qubits, 0, nullptr))
-            return set_err(QM_ERR_STATE, "pass %d: malformed program (opcode / non-uniform control predicate)", np);
-        ++np;
-    }
-    for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) return set_err(QM_ERR_STATE, "planner left a gate behind");
-    if (n_passes) *n_passes = np;
-    return QM_OK;
-}
-
-// TEST INFRASTRUCTURE (host only): qm_plan_emulate for a sharded register, every rank emulated in this process.
-extern "C" int32_t qm_plan_emulate_sharded(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits, double max_cost,
-                                           const qm_gate* gates, int32_t ngates, double* state, int32_t* n_passes, int32_t* n_remaps) {
-    const int g = global_bits, nl = n_qubits - global_bits;
-    if (!gates || !state || g < 1 || g > 4 || nl < 11 || nl > 22 || 2 * g > nl || (tile_bits != 11 && tile_bits != 12) || tile_bits > nl ||
-        low_bits < 3 || low_bits > 8)
-        return set_err(QM_ERR_ARG, "bad argument");
-    Planner pl;
-    pl.opt.n_local = nl; pl.opt.n_global = g;
-    pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
-    if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
-    pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
-    pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
-    pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
-    if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 5.0) pl.opt.max_cost = kV4GroupCost + 5.0;
-    int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
-    if (rc) return set_err(rc, "bad gate");
-    prepare_for_lifting(pl.gates);
-    for (const LGate& x : pl.gates) if (!x.liftable) return set_err(QM_ERR_STATE, "a gate has no lifting form");
-    pl.done.assign(pl.gates.size(), 0);
-    EmuAmp* amp = reinterpret_cast<EmuAmp*>(state);
-    const int W = 1 << g;
-    const uint64_t shard = 1ull << nl, chunk = 1ull << (nl - g);
-    auto exchange = [&]() {                          // what k_remap_swap does, on the host
-        for (int r = 0; r < W; ++r)
-            for (int j = r + 1; j < W; ++j)
-                for (uint64_t i = 0; i < chunk; ++i)
-                    std::swap(amp[(uint64_t)r * shard + (uint64_t)j * chunk + i], amp[(uint64_t)j * shard + (uint64_t)r * chunk + i]);
-    };
-    std::vector<V4Program> prog(1);
-    PlanPass P; int np = 0, nr = 0; bool swapped = false;
-    for (int guard = 0; guard < 4 * ngates + 8; ++guard) {
-        while (pl.next_pass(P)) {
-            choose_tile_layout(P);
-            if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
-            for (int r = 0; r < W; ++r)
-                if (!emulate_v4(prog[0], P, amp + (uint64_t)r * shard, nl, (uint64_t)r << nl, nullptr))
-                    return set_err(QM_ERR_STATE, "pass %d, rank %d: malformed program (opcode / non-uniform control predicate)", np, r);
-            ++np;
-        }
-        bool left = false;
-        for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) { left = true; break; }
-        if (!left) break;
-        if (!pl.pending_global_target()) return set_err(QM_ERR_STATE, "planner stalled");
-        exchange(); swapped = !swapped; ++nr;
-        for (size_t i = 0; i < pl.gates.size(); ++i) {
-            if (pl.done[i]) continue;
-            pl.gates[i].target = dist_swap_bit(pl.gates[i].target, nl, g);
-            if (pl.gates[i].ctrl >= 0) pl.gates[i].ctrl = dist_swap_bit(pl.gates[i].ctrl, nl, g);
-        }
-    }
-    for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) return set_err(QM_ERR_STATE, "planner left a gate behind");
-    if (swapped) exchange();                         // back to the canonical layout (dist_canonicalize)
-    if (n_passes) *n_passes = np;
-    if (n_remaps) *n_remaps = nr;
-    return QM_OK;
-}
-
 // Diagnostics (QM_OPT_TIME_PASSES): per fused pass since the last call {ms, groups, gates, planner cost, records: full, half, xor, thr}.
 extern "C" int32_t qm_pass_times(qm_state* st, float* out, int32_t cap_passes, int32_t* n_passes) {
     if (!st || !n_passes) return set_err(QM_ERR_ARG, "null argument");
@@ -1308,6 +1078,17 @@ extern "C" int32_t qm_pass_times(qm_state* st, float* out, int32_t cap_passes, i
     return QM_OK;
 }
 
+// Diagnostics (QM_OPT_TRACE): SM-clock stamps of CTA 0 for the LAST fused pass launched, 8 per tile:
+// {team: wait start, tile landed, after group 0, 1, 2, arrived | producer: computed seen, next load issued}
+extern "C" int32_t qm_trace_read(qm_state* st, uint64_t* out, int64_t cap_u64) {
+    if (!st || !out || cap_u64 <= 0) return set_err(QM_ERR_ARG, "null argument");
+    if (!st->trace_buf) return set_err(QM_ERR_STATE, "QM_OPT_TRACE is off");
+    QM_TRY(qm_sync(st));
+    size_t bytes = (size_t)cap_u64 * 8; if (bytes > kTraceBytes) bytes = kTraceBytes;
+    CU(cudaMemcpy(out, st->trace_buf, bytes, cudaMemcpyDeviceToHost));
+    return QM_OK;
+}
+
 // Host-only introspection: plans and encodes `gates` as for the TMA kernel and counts the records by family:
 // hist[0..7] = ROT, ROTX, PHASE, PERMX, THR, SLOT, gates entered through the controlled entry, groups; hist[8] = passes.
 extern "C" int32_t qm_plan_ophist(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
@@ -1317,10 +1098,7 @@ extern "C" int32_t qm_plan_ophist(int32_t n_qubits, int32_t tile_bits, int32_t l
     pl.opt.n_local = n_qubits; pl.opt.n_global = 0;
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
     if (max_cost > 0) pl.opt.max_cost = max_cost;
-    pl.opt.max_runs = 3; pl.opt.max_run_len = 8; pl.opt.max_subs = kV4MaxSubs; pl.opt.max_groups = kV4MaxGroups;
-    pl.opt.max_outer = kV4MaxOuter; pl.opt.warp_uniform_ctrl = true; pl.opt.block_bits = kV4BlockBits;
-    pl.opt.group_cost = kV4GroupCost; pl.opt.retile = true;
-    if (max_cost > 0 && pl.opt.max_cost < kV4GroupCost + 5.0) pl.opt.max_cost = kV4GroupCost + 5.0;
+    v4_planner_options(pl.opt, max_cost);
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
     prepare_for_lifting(pl.gates);

@@ -33,7 +33,7 @@ struct qm_state {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
     bool ev_pending = false;
     // options
-    bool eager = false, fuse = true, remap = false, pipeline = true;
+    bool eager = false, fuse = true, pipeline = true;
     bool time_passes = false;   // QM_OPT_TIME_PASSES: CUDA events around every fused pass (diagnostics, tools/pass_model.py)
     std::vector<cudaEvent_t> pass_events;      // 2 per timed pass, resolved by qm_pass_times
     std::vector<float> pass_desc;              // per timed pass: groups, records, planner cost
@@ -61,6 +61,16 @@ struct qm_state {
     qm_counters_t ctr{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> remap_events;   // resolved into ctr.ms_remap at the next sync
     DistCtx* dist = nullptr;
+    unsigned long long* trace_buf = nullptr;     // QM_OPT_TRACE: phase trace of CTA 0 of the next fused pass (diagnostics)
+};
+
+// one slab of a sharded register: the amplitudes whose index bits bit[0..nbits) have the values in value_or
+struct PassSlab {
+    int nbits = 0;
+    int bit[3] = { 0, 0, 0 };
+    uint64_t value_or = 0;
+    int index = 0;          // which slab (counters: a pass is counted once, with its slab 0)
+    int sm_cap = 0;         // CTAs of the persistent grid (0 = all SMs)
 };
 
 int ensure_dev(void** p, size_t* cap, size_t need);

@@ -1,0 +1,54 @@
+"""TEST INFRASTRUCTURE: ctypes binding of tests/native/libqm_emu.so — the host emulator of the fused-pass programs
+(the engine's planner + encoder, then a scalar walk over the encoded bytes).  A library of its own: the shipped
+libqm_b200.so neither contains nor calls it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "native", "libqm_emu.so")
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            subprocess.check_call(["make", "-C", os.path.join(HERE, "native")])
+        l = C.CDLL(SO)
+        l.qm_plan_emulate.restype = C.c_int32
+        l.qm_plan_emulate.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32, _dp, C.POINTER(C.c_int32)]
+        l.qm_plan_emulate_sharded.restype = C.c_int32
+        l.qm_plan_emulate_sharded.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32, _dp,
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        _lib = l
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        buf = C.create_string_buffer(512)
+        lib().qm_emu_last_error(buf, 512)
+        raise RuntimeError("qm_emu error %d: %s" % (rc, buf.value.decode("utf-8", "replace")))
+
+
+def plan_emulate(n, gates, psi, tile_bits=12, low_bits=5, max_cost=0.0):
+    """the planned + encoded pass programs walked over psi (complex128, length 2^n): (state, passes)"""
+    out = np.ascontiguousarray(psi, dtype=np.complex128).copy()
+    npass = C.c_int32()
+    _check(lib().qm_plan_emulate(n, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates),
+                                 out.ctypes.data_as(_dp), C.byref(npass)))
+    return out, npass.value
+
+
+def plan_emulate_sharded(n, global_bits, gates, psi, tile_bits=12, low_bits=5, max_cost=0.0):
+    """plan_emulate for a register sharded over 2^global_bits ranks, all emulated in this process on the whole
+    state vector: (state, passes, remaps)"""
+    out = np.ascontiguousarray(psi, dtype=np.complex128).copy()
+    npass, nrem = C.c_int32(), C.c_int32()
+    _check(lib().qm_plan_emulate_sharded(n, global_bits, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates),
+                                         out.ctypes.data_as(_dp), C.byref(npass), C.byref(nrem)))
+    return out, npass.value, nrem.value

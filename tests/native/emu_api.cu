@@ -1,0 +1,111 @@
+// emu_api.cu — TEST INFRASTRUCTURE, host only, built into tests/native/libqm_emu.so (NOT into libqm_b200.so):
+// plans a gate list exactly as the engine does for its TMA kernel, encodes every pass with the engine's own encoder
+// (csrc/encode_v4.hpp) and walks the encoded programs over a host vector with the scalar restatement of the
+// kernel's interpreter in emulate.hpp.  Lets the CPU suite check planner + encoder against the oracle without a GPU.
+#include <stdarg.h>
+#include <stdio.h>
+#include <vector>
+
+#include "../../include/qm_b200.h"
+#include "emulate.hpp"
+#include "../../quromorphic.jl_b200/csrc/dist_bits.hpp"
+
+using namespace qm;
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+extern "C" int32_t qm_emu_last_error(char* buf, int32_t cap) {
+    if (!buf || cap <= 0) return QM_ERR_ARG;
+    snprintf(buf, (size_t)cap, "%s", g_err);
+    return QM_OK;
+}
+
+// TEST INFRASTRUCTURE (host only, see emulate.hpp): plan `gates` exactly as the engine would for the TMA
+// kernel, encode every pass and walk the encoded programs over a host state vector.
+extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t low_bits, double max_cost,
+                                   const qm_gate* gates, int32_t ngates, double* state, int32_t* n_passes) {
+    if (!gates || !state || n_qubits < 11 || n_qubits > 24 || (tile_bits != 11 && tile_bits != 12) || tile_bits > n_qubits ||
+        low_bits < 3 || low_bits > 8)
+        return set_err(QM_ERR_ARG, "bad argument");
+    Planner pl;
+    pl.opt.n_local = n_qubits; pl.opt.n_global = 0;
+    pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
+    if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
+    v4_planner_options(pl.opt, max_cost);
+    int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
+    if (rc) return set_err(rc, "bad gate");
+    prepare_for_lifting(pl.gates);
+    for (const LGate& x : pl.gates) if (!x.liftable) return set_err(QM_ERR_STATE, "a gate has no lifting form");
+    pl.done.assign(pl.gates.size(), 0);
+    std::vector<V4Program> prog(1);
+    PlanPass P; int np = 0;
+    while (pl.next_pass(P)) {
+        choose_tile_layout(P);
+        if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
+        if (!emulate_v4(prog[0], P, reinterpret_cast<EmuAmp*>(state), n_qubits, 0, nullptr))
+            return set_err(QM_ERR_STATE, "pass %d: malformed program (opcode / non-uniform control predicate)", np);
+        ++np;
+    }
+    for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) return set_err(QM_ERR_STATE, "planner left a gate behind");
+    if (n_passes) *n_passes = np;
+    return QM_OK;
+}
+
+// TEST INFRASTRUCTURE (host only): qm_plan_emulate for a sharded register, every rank emulated in this process.
+extern "C" int32_t qm_plan_emulate_sharded(int32_t n_qubits, int32_t global_bits, int32_t tile_bits, int32_t low_bits, double max_cost,
+                                           const qm_gate* gates, int32_t ngates, double* state, int32_t* n_passes, int32_t* n_remaps) {
+    const int g = global_bits, nl = n_qubits - global_bits;
+    if (!gates || !state || g < 1 || g > 4 || nl < 11 || nl > 22 || 2 * g > nl || (tile_bits != 11 && tile_bits != 12) || tile_bits > nl ||
+        low_bits < 3 || low_bits > 8)
+        return set_err(QM_ERR_ARG, "bad argument");
+    Planner pl;
+    pl.opt.n_local = nl; pl.opt.n_global = g;
+    pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
+    if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
+    v4_planner_options(pl.opt, max_cost);
+    int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
+    if (rc) return set_err(rc, "bad gate");
+    prepare_for_lifting(pl.gates);
+    for (const LGate& x : pl.gates) if (!x.liftable) return set_err(QM_ERR_STATE, "a gate has no lifting form");
+    pl.done.assign(pl.gates.size(), 0);
+    EmuAmp* amp = reinterpret_cast<EmuAmp*>(state);
+    const int W = 1 << g;
+    const uint64_t shard = 1ull << nl, chunk = 1ull << (nl - g);
+    auto exchange = [&]() {                          // what k_remap_swap does, on the host
+        for (int r = 0; r < W; ++r)
+            for (int j = r + 1; j < W; ++j)
+                for (uint64_t i = 0; i < chunk; ++i)
+                    std::swap(amp[(uint64_t)r * shard + (uint64_t)j * chunk + i], amp[(uint64_t)j * shard + (uint64_t)r * chunk + i]);
+    };
+    std::vector<V4Program> prog(1);
+    PlanPass P; int np = 0, nr = 0; bool swapped = false;
+    for (int guard = 0; guard < 4 * ngates + 8; ++guard) {
+        while (pl.next_pass(P)) {
+            choose_tile_layout(P);
+            if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
+            for (int r = 0; r < W; ++r)
+                if (!emulate_v4(prog[0], P, amp + (uint64_t)r * shard, nl, (uint64_t)r << nl, nullptr))
+                    return set_err(QM_ERR_STATE, "pass %d, rank %d: malformed program (opcode / non-uniform control predicate)", np, r);
+            ++np;
+        }
+        bool left = false;
+        for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) { left = true; break; }
+        if (!left) break;
+        if (!pl.pending_global_target()) return set_err(QM_ERR_STATE, "planner stalled");
+        exchange(); swapped = !swapped; ++nr;
+        for (size_t i = 0; i < pl.gates.size(); ++i) {
+            if (pl.done[i]) continue;
+            pl.gates[i].target = dist_swap_bit(pl.gates[i].target, nl, g);
+            if (pl.gates[i].ctrl >= 0) pl.gates[i].ctrl = dist_swap_bit(pl.gates[i].ctrl, nl, g);
+        }
+    }
+    for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) return set_err(QM_ERR_STATE, "planner left a gate behind");
+    if (swapped) exchange();                         // back to the canonical layout (dist_canonicalize)
+    if (n_passes) *n_passes = np;
+    if (n_remaps) *n_remaps = nr;
+    return QM_OK;
+}
+

@@ -4,7 +4,8 @@
 // form with the same operation order as tools/gen_v4_dispatch.py emits).
 //
 // It exists so that the CPU test suite (no GPU in CI) can check planner + encoder against the oracle for
-// the programs the GPU will be handed: tests/test_abi_cpu.py calls qm_plan_emulate on small registers.
+// the programs the GPU will be handed: tests/test_abi_cpu.py calls qm_plan_emulate (tests/native/libqm_emu.so,
+// a library of its own — the shipped libqm_b200.so does not contain it) on small registers.
 // It is NOT a fallback: nothing in the product path calls it, and state-creating entry points still fail
 // with QM_ERR_NO_DEVICE when there is no GPU.
 #pragma once
@@ -12,8 +13,7 @@
 #include <stdint.h>
 #include <vector>
 
-#include "fused_tma.cuh"
-#include "planner.hpp"
+#include "../../quromorphic.jl_b200/csrc/encode_v4.hpp"
 
 namespace qm {
 
@@ -23,20 +23,6 @@ inline void emu_lift(double& x, double& y, double t1, double s1, double t2, int 
     x = fma(t1, y, x);
     y = (sg & 1) ? fma(s1, x, -y) : fma(s1, x, y);
     x = (sg & 2) ? fma(t2, y, -x) : fma(t2, y, x);
-}
-
-// decode op -> family (0 ROT, 1 ROTX, 2 PHASE, 3 PERMX, 4 THR), variant, B, CB
-inline bool emu_decode(uint32_t op, int& fam, int& var, int& B, int& CB) {
-    auto bc = [&](int idx) {
-        int i = 0;
-        for (int b = 0; b < kV4BlockBits; ++b) for (int c = -1; c < kV4BlockBits; ++c) { if (c == b) continue; if (i == idx) { B = b; CB = c; return; } ++i; }
-    };
-    if (op < (uint32_t)V4_OP_ROTX) { fam = 0; var = op / V4_NBC; bc(op % V4_NBC); return true; }
-    if (op < (uint32_t)V4_OP_PHASE) { fam = 1; var = (op - V4_OP_ROTX) / V4_NBC; bc((op - V4_OP_ROTX) % V4_NBC); return true; }
-    if (op < (uint32_t)V4_OP_PERMX) { fam = 2; var = (op - V4_OP_PHASE) / V4_NBC; bc((op - V4_OP_PHASE) % V4_NBC); return true; }
-    if (op < (uint32_t)V4_OP_THR) { fam = 3; var = 0; bc(op - V4_OP_PERMX); return true; }
-    if (op < (uint32_t)V4_NUM_GATE_OPS) { fam = 4; var = (op - V4_OP_THR) / (kV4BlockBits + 1); B = -1; CB = (int)((op - V4_OP_THR) % (kV4BlockBits + 1)) - 1; return true; }
-    return false;
 }
 
 // Runs one pass program over a host register of nl index bits (rank_or: the sharded bits of this rank).
@@ -100,7 +86,7 @@ inline bool emulate_v4(const V4Program& prog, const PlanPass& P, EmuAmp* amp, in
                         active = (ctx[0] & R->cm) == R->cm;
                         for (int l = 0; l < nl_; ++l) if (((ctx[l] & R->cm) == R->cm) != active) return false;   // must be warp-uniform
                     } else if (R->cm) return false;
-                    if (!emu_decode(op, fam, var, B, CB)) return false;
+                    if (!v4_decode_op(op, fam, var, B, CB)) return false;
                     if (!active) continue;
                     for (int l = 0; l < nl_; ++l) {
                         EmuAmp* x = a[l]; double* cc = c[l];

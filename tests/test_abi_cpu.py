@@ -6,6 +6,8 @@ import os
 import re
 
 import numpy as np
+
+import emu  # noqa: E402  (tests/emu.py: the host emulator library)
 import pytest
 
 from oracle import oracle as O
@@ -115,8 +117,8 @@ def test_planner_leaves_global_targets_for_remap(pkg):
     gl.rx(3, 0.4); gl.rz(10, 0.3); gl.cnot(10, 2); gl.rx(9, 0.2); gl.h(1)
     out = np.zeros(4096, dtype=np.int32); ln = C.c_int64()
     a = gl.array()
-    pkg._lib.check(pkg._lib.lib().qm_plan_describe(n, g, 6, 3, 0, a.ctypes.data, len(a),
-                                                   out.ctypes.data_as(C.POINTER(C.c_int32)), len(out), C.byref(ln)))
+    pkg._lib.check(pkg._lib.lib().qm_plan_describe_ex(n, g, 6, 3, 0.0, 0, a.ctypes.data, len(a),
+                                                      out.ctypes.data_as(C.POINTER(C.c_int32)), len(out), C.byref(ln)))
     v = out[:ln.value]
     # the diagonal rz on global qubit 10 and the cnot controlled by it run locally; only rx(9) is left
     assert v[-2] == 1 and v[-1] == 1
@@ -133,7 +135,7 @@ def test_encoded_pass_programs_emulated_on_cpu(pkg, n, tile, low, cost, seed):
     or a pass the kernel could not take is an error"""
     gates = random_circuit(pkg, n, 300, 4000 + 17 * seed)
     psi0 = O.random_state(n, seed)
-    got, npass = pkg._lib.plan_emulate(n, gates, psi0, tile_bits=tile, low_bits=low, max_cost=cost)
+    got, npass = emu.plan_emulate(n, gates, psi0, tile_bits=tile, low_bits=low, max_cost=cost)
     ref = O.apply_circuit(psi0.copy(), gates)
     assert npass > 0
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
@@ -143,7 +145,7 @@ def test_encoded_c3_programs_emulated_on_cpu(pkg):
     n = 16
     gates = pkg.circuits.c3_circuit(n=n, depth=8)
     for tile, cost in ((12, 0.0), (11, 24.0), (12, 48.0), (12, 86.0), (11, 86.0), (12, 130.0), (11, 250.0)):
-        got, npass = pkg._lib.plan_emulate(n, gates, O.statevector(n, 0), tile_bits=tile, max_cost=cost)
+        got, npass = emu.plan_emulate(n, gates, O.statevector(n, 0), tile_bits=tile, max_cost=cost)
         ref = O.apply_circuit(O.statevector(n, 0), gates)
         assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
 
@@ -242,7 +244,7 @@ def test_short_circuit_is_planned_at_the_budget_that_finishes_first(pkg):
     ref = psi.copy()
     for s in range(3):
         gates = pkg.circuits.c4_step(n, s)
-        psi, npass = L.plan_emulate(n, gates, psi, max_cost=75.0)
+        psi, npass = emu.plan_emulate(n, gates, psi, max_cost=75.0)
         ref = O.apply_circuit(ref, gates)
         assert npass <= 2
         assert np.max(np.abs(psi - ref)) / np.max(np.abs(ref)) < 1e-12
@@ -257,7 +259,7 @@ def test_deep_circuit_programs_emulated_on_cpu(pkg, n, depth, cost):
     plan = pkg._lib.plan_describe(n, gates, max_cost=cost)
     assert np.mean([len(p["groups"]) for p in plan]) <= 1.15              # deep mode, decided once for the whole circuit
     psi0 = O.random_state(n, n)
-    got, npass = pkg._lib.plan_emulate(n, gates, psi0, max_cost=cost)
+    got, npass = emu.plan_emulate(n, gates, psi0, max_cost=cost)
     ref = O.apply_circuit(psi0.copy(), gates)
     assert npass == len(plan)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
@@ -288,7 +290,7 @@ def test_permutation_tails_folded_into_the_stores_are_exact(pkg, n, seed, perm_o
         gates = gl.array()
         if len(gates) == 0:
             continue
-        psi, npass = pkg._lib.plan_emulate(n, gates, psi, max_cost=75.0)
+        psi, npass = emu.plan_emulate(n, gates, psi, max_cost=75.0)
         ref = O.apply_circuit(ref, gates)
         if perm_only:
             assert np.array_equal(psi, ref), (chunk, npass)

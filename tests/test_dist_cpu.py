@@ -34,6 +34,8 @@ def test_sharded_planner_with_gloo_ranks(world, n, tile, low, seed):
 
 
 import numpy as np
+
+import emu  # noqa: E402  (tests/emu.py: the host emulator library)
 import pytest
 
 
@@ -66,7 +68,7 @@ def test_sharded_encoded_programs_emulated_on_cpu(pkg, n, g, kind, seed):
     ref = psi.copy()
     remaps = 0
     for gates in chunks:
-        psi, npass, nrem = pkg._lib.plan_emulate_sharded(n, g, gates, psi, max_cost=80.0)
+        psi, npass, nrem = emu.plan_emulate_sharded(n, g, gates, psi, max_cost=80.0)
         ref = O.apply_circuit(ref, gates)
         remaps += nrem
         assert npass > 0

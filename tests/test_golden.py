@@ -6,6 +6,8 @@ import json
 import os
 
 import numpy as np
+
+import emu  # noqa: E402  (tests/emu.py: the host emulator library)
 import pytest
 
 from oracle import literal as LIT
@@ -88,7 +90,7 @@ def test_encoded_tma_programs_reproduce_the_12_qubit_golden_case(pkg):
     replay_gl = lambda op: getattr(gl, op[0])(*op[1:-1], float.fromhex(op[-1])) if isinstance(op[-1], str) else getattr(gl, op[0])(*op[1:])
     for op in case["ops"]:
         replay_gl(op)
-    got, npass = pkg._lib.plan_emulate(12, gl.array(), O.statevector(12, case["m"]), max_cost=75.0)
+    got, npass = emu.plan_emulate(12, gl.array(), O.statevector(12, case["m"]), max_cost=75.0)
     want = unhexc(case["amps"])
     assert npass >= 1 and np.max(np.abs(got - want)) <= RTOL * np.max(np.abs(want))
 
