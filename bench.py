@@ -46,6 +46,33 @@ def peaks():
         return 6650.0, "fallback"
 
 
+KERNEL_SOURCES = ("fused_tma_kernel.cuh", "fused_tma.cuh", "v4_dispatch.inc")
+
+
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "quromorphic.jl_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def static_traffic(n):
+    """DRAM bytes of one k_fused_tma launch.  It cannot be measured inside a plain run (it needs the profiler's
+    counters), so it is a STATIC figure: the dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    capture committed under profiles/, accepted only when that capture was taken from the kernel sources this run was
+    built from (hash of KERNEL_SOURCES) and at this register size; otherwise null."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            t = json.load(f)["k_fused_tma"]
+        if t["n_qubits"] == n and t["kernel_source_hash"] == kernel_source_hash():
+            return t["dram_bytes_per_launch"], "static: %s (ncu --set full, one launch; same kernel sources)" % t["capture"]
+    except Exception:
+        pass
+    return None, "not captured for this binary"
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -96,12 +123,19 @@ class ClockSampler:
                 "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_sample(n, gates, budget_s, threads=None):
-    """time the oracle on a prefix of `gates` at n qubits: returns (gates/s, ngates, threads, seconds)"""
+def host_threads():
+    """every host core this process may use (torchrun exports OMP_NUM_THREADS=1: the oracle is told explicitly)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample(n, gates, budget_s, threads=None, keep_state=False):
+    """time the oracle on a prefix of `gates` at n qubits: returns (gates/s, ngates, threads, seconds[, state])"""
     import numpy as np
     from oracle import oracle as O
-    if threads:
-        O.set_threads(threads)
+    O.set_threads(threads or host_threads())
     s = O.statevector(n, 0)
     O.apply_circuit(s, gates[:1].copy())            # touch pages / warm up
     s = O.statevector(n, 0)
@@ -114,7 +148,33 @@ def cpu_sample(n, gates, budget_s, threads=None):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
+    if keep_state:
+        return done / dt, done, O.num_threads(), dt, s
     return done / dt, done, O.num_threads(), dt
+
+
+def parity_block(pkg, n, gates, ref_state, tol=1e-12):
+    """the GPU path on the very gate prefix the CPU leg just ran (same size, same circuit), compared with the
+    oracle's state: all-qubit <Z> with the reference's 1e-10 threshold and without one, the norm, both 4-qubit
+    reduced density matrices (every amplitude enters them) and 64 seeded shots (bit for bit)."""
+    import numpy as np
+    from oracle import oracle as O
+    st = pkg.B200State(n, 0)
+    st.apply_circuit(np.ascontiguousarray(gates))
+    errs = {}
+    for name, thr in (("z_thr1e-10", 1e-10), ("z_nothr", -1.0)):
+        errs[name] = float(np.max(np.abs(st.expect_z_all(threshold=thr) - O.expect_z_all(ref_state, thr))))
+    errs["norm2"] = abs(st.norm2() - O.norm2(ref_state))
+    k = min(4, n - 1)
+    errs["rho_low%d" % k] = float(np.max(np.abs(st.reduced_density(True, k) - O.reduced_density(ref_state, True, k))))
+    errs["rho_high%d" % k] = float(np.max(np.abs(st.reduced_density(False, k) - O.reduced_density(ref_state, False, k))))
+    shots_equal = bool(np.array_equal(st.sample(20261020, 64), O.sample(ref_state, 20261020, 64)))
+    norm2 = st.norm2()
+    st.close()
+    worst = max(errs.values())
+    return {"n_qubits": n, "gates": int(len(gates)), "against": "oracle/qsim_oracle.c on the same gates from |0..0>",
+            "max_abs_err": worst, "tol": tol, "errors": errs, "sampler_bit_exact": shots_equal, "norm2": norm2,
+            "ok": bool(worst < tol and shots_equal)}
 
 
 def pick_cpu_qubits(n):
@@ -130,18 +190,22 @@ def pick_cpu_qubits(n):
 
 
 def run_reference(args, rank):
-    """--impl reference: the CPU restatement of the reference's own arithmetic on the host cores."""
+    """--impl reference: the CPU restatement of the reference's own arithmetic on ALL host cores (set explicitly:
+    torchrun exports OMP_NUM_THREADS=1).  N = 1: the C3 circuit itself.  N > 1: the C4 reservoir step, timed at the
+    largest register that fits host memory and converted per amplitude (one gate over 2^30 amplitudes = one unit) —
+    the config says which size was timed."""
     if rank != 0:
         return
-    import numpy as np
     import __graft_entry__ as ge
     pkg = ge.load_package()
     n_full = C3_QUBITS if args.gpus == 1 else SHARD_QUBITS + (args.gpus.bit_length() - 1)
-    gates = pkg.circuits.c3_circuit(n=n_full, depth=2, seed=C3_SEED) if args.gpus == 1 else \
-        pkg.circuits.c4_step(n_full, 0)
     n_cpu = pick_cpu_qubits(min(n_full, 30))
-    if n_cpu != n_full:   # same gate sequence restricted to the qubits that fit in host memory
-        gates = pkg.circuits.c3_circuit(n=n_cpu, depth=2, seed=C3_SEED)
+    if args.gpus == 1:
+        gates = pkg.circuits.c3_circuit(n=n_cpu, depth=2 if n_cpu != n_full else C3_DEPTH, seed=C3_SEED)
+        what = "C3 circuit"
+    else:
+        gates = pkg.circuits.c4_step(n_cpu, 0)
+        what = "C4 reservoir step (encoding layer + C3-style layer)"
     budget = 6.0
     vals = []
     t_all = time.perf_counter()
@@ -152,13 +216,20 @@ def run_reference(args, rank):
     gps = sum(v[1] for v in vals) / sum(v[2] for v in vals)
     scale = 2.0 ** (n_cpu - 30)                    # convert to units of one gate over 2^30 amplitudes
     value = gps * scale
-    sample = "first %d gates of the %d-qubit circuit per step (state 16*2^%d B), %d threads" % (vals[0][1], n_cpu, n_cpu, thr)
+    sample = "first %d gates of the %s at %d qubits per step (state 16*2^%d B), %d OpenMP threads" % (
+        vals[0][1], what, n_cpu, n_cpu, thr)
+    cfg = workload_config(args.gpus, n_full, c4=args.gpus > 1)
+    cfg["cpu_timed_qubits"] = n_cpu
+    if n_cpu != n_full:
+        cfg["cpu_extrapolation"] = ("a %d-qubit state does not fit host memory: the same gate sequence is timed at %d qubits and "
+                                    "counted per amplitude (one gate over 2^30 amplitudes = one unit), i.e. the CPU cost per "
+                                    "amplitude is assumed flat up to 2^%d" % (n_full, n_cpu, n_full))
     line = {
         "impl": "reference", "metric": "gates_per_sec", "value": value, "unit": "gates/s (one gate over 2^30 amplitudes)",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(v[2] for v in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, n_full),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "gates/s (one gate over 2^30 amplitudes)", "cores": thr,
                          "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "gates/s (one gate over 2^30 amplitudes)", "h2d_bytes_per_step": 0,
@@ -282,19 +353,12 @@ def main():
     e2e = args.steps * ngates / wall * scale
 
     hbm_peak, peak_kind = peaks()
-    traffic = None
-    try:    # dram__bytes_read.sum + dram__bytes_write.sum of one k_fused_tma launch (ncu --set full capture)
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            t = json.load(f)["k_fused_tma"]
-            if t["n_qubits"] == n:
-                traffic = t["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    traffic, traffic_from = static_traffic(n)
     bytes_per_launch = 32.0 * (1 << n)
     avg_pass_ms = pass_ms / max(npasses, 1)
     achieved = bytes_per_launch / (avg_pass_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "k_fused_tma", "achieved": achieved, "peak": hbm_peak, "peak_kind": peak_kind,
-            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_from": traffic_from,
             "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_pass_ms, "launches": npasses,
             "gates_per_pass": args.steps * ngates / max(npasses, 1),
             "frac_of_nominal_8TBs": achieved / 8000.0}
@@ -358,14 +422,38 @@ def main():
         except Exception as e:            # the base is informational: never lose the headline line over it
             line["c4_base"] = {"error": str(e)[:200]}
 
+    parity_ok = True
     if not args.no_cpu:
         n_cpu = pick_cpu_qubits(n)
         cg = gates if n_cpu == n else pkg.circuits.c3_circuit(n=n_cpu, depth=2, seed=C3_SEED)
-        gps, ng, thr, dt = cpu_sample(n_cpu, cg, 15.0)
+        gps, ng, thr, dt, ref_state = cpu_sample(n_cpu, cg, 15.0, keep_state=True)
         line["cpu_baseline"] = {"value": gps * 2.0 ** (n_cpu - 30), "unit": unit, "cores": thr, "kind": "port",
                                 "sample": "first %d gates of the same circuit at %d qubits from |0..0> "
                                           "(%.1f s of oracle/qsim_oracle.c, OpenMP)" % (ng, n_cpu, dt)}
+        # parity at the headline size: the GPU path on the same gate prefix against the state the CPU leg just made
+        try:
+            line["parity"] = parity_block(pkg, n_cpu, cg[:ng], ref_state)
+        except Exception as e:
+            line["parity"] = {"ok": False, "error": str(e)[:300]}
+        parity_ok = bool(line["parity"].get("ok"))
+        del ref_state
+
+    # ---- the other BASELINE.json configurations, so that the driver's record carries a number for each ----
+    if not args.no_alt and n == C3_QUBITS and args.depth == C3_DEPTH:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        try:
+            import bench_batched
+            import bench_pipeline
+            cpu_steps = 0 if args.no_cpu else 1
+            line["c2_batched"] = bench_batched.run_c2(pkg, steps=8)
+            line["c1"] = bench_pipeline.run_c1(pkg, 12, 100, 25 * cpu_steps)
+            line["c5"] = bench_pipeline.run_c5(pkg, 20, 100, 4, 10 * cpu_steps)
+        except Exception as e:
+            line["other_configs_error"] = str(e)[:300]
     print(json.dumps(line), flush=True)
+    if not parity_ok:
+        sys.stderr.write("bench.py: PARITY FAILED against the oracle: %s\n" % json.dumps(line.get("parity")))
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -131,7 +131,9 @@ int32_t qm_apply_batched(qm_state* st, const qm_gate* gates, int32_t ngates,
  *                   threshold < 0 disables the test).  batch_idx selects the register.
  * qm_expect_z_all   all-qubit measure_z in ONE pass: out[2q] = p0, out[2q+1] = p1 for q = 0..n-1,
  *                   for every register of the batch (out: batch * 2n doubles, host)
- * qm_expect_all     same for basis X or Y (one pass per qubit)
+ * qm_expect_all     same for basis X or Y (measure_x / measure_y of every qubit, QSim.jl:320-330): the state is read
+ *                   once per 12 (then 9) qubits, every pair rotated in registers; qm_expect_all_with takes the
+ *                   caller's own rotation matrix like qm_measure_with (R == NULL: the Z basis)
  * qm_reduced_density  statevector_to_density_matrix + partial_trace, QSim.jl:39-41 and
  *                   QInfo.jl:381-405, without ever forming rho: keep_low=1 keeps B = the low k
  *                   qubits (partial_trace(..., 1)), keep_low=0 keeps A = the high k qubits
@@ -149,6 +151,7 @@ int32_t qm_measure_with(qm_state* st, int32_t t0, const double* R, double thresh
                         double out[2]);
 int32_t qm_expect_z_all(qm_state* st, double threshold, double* out_host);
 int32_t qm_expect_all(qm_state* st, int32_t basis, double threshold, double* out_host);
+int32_t qm_expect_all_with(qm_state* st, const double* R, double threshold, double* out_host);
 int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k, int32_t batch_idx,
                            double* out_colmajor);
 int32_t qm_sample(qm_state* st, uint64_t seed, int32_t nshots, int32_t batch_idx, uint64_t* out);

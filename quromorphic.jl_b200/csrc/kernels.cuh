@@ -322,6 +322,90 @@ k_zfinal(const double* __restrict__ partial, int reg_bits, int cb, int hbits, in
         for (int q = 0; q < nq; ++q) out[((size_t)r * nq + q) * 2] = out_tot[r] - out[((size_t)r * nq + q) * 2 + 1];
 }
 
+// K5  all-qubit measure_x / measure_y (QSim.jl:320-330 for every t): a tile of 2^m amplitudes (the L lowest index
+// bits + m - L bits starting at hs) is staged in shared memory ONCE and every index bit of the tile selected by
+// `tmask` is measured from it — the pair (a[i0], a[i0 | bit]) is rotated by R in registers exactly as k_measure_rot
+// does, the threshold applies to the ROTATED probabilities.  The reference makes a copy of the state, multiplies a
+// dense 2^n x 2^n operator into it and scans it, per qubit; here a 30-qubit register is read 3 times for all 30.
+// CTA c of a register sweeps tiles c, c + ctas_per_reg, ... in order and emits partial[cta][12][2]; k_pauli_final
+// adds the CTAs of a register in order and scatters to out[reg][index bit][2].
+// ---------------------------------------------------------------------------------------------
+static const int kPauliM = 12;
+static const int kPauliThreads = 256;
+__global__ void __launch_bounds__(kPauliThreads)
+k_pauli_tile(const double2* __restrict__ amp, int reg_bits, int m, int L, int hs, uint32_t tmask, Mat2 R, double thr,
+             uint32_t ctas_per_reg, double* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* tile = reinterpret_cast<double2*>(smem_raw);
+    const double2 u11 = make_double2(R.v[0], R.v[1]), u21 = make_double2(R.v[2], R.v[3]);
+    const double2 u12 = make_double2(R.v[4], R.v[5]), u22 = make_double2(R.v[6], R.v[7]);
+    const uint32_t reg = blockIdx.x / ctas_per_reg, c = blockIdx.x % ctas_per_reg;
+    const double2* __restrict__ base_reg = amp + ((uint64_t)reg << reg_bits);
+    const uint32_t tsize = 1u << m, lmask = (1u << L) - 1u;
+    const int nh = m - L;
+    const uint64_t ntiles = 1ull << (reg_bits - m);
+    double p0[kPauliM], p1[kPauliM];
+#pragma unroll
+    for (int b = 0; b < kPauliM; ++b) { p0[b] = 0.0; p1[b] = 0.0; }
+    for (uint64_t t = c; t < ntiles; t += ctas_per_reg) {
+        // tile index -> base: the bits below hs above the L low ones, then the bits above the high run
+        uint64_t base;
+        if (nh == 0) base = t << m;
+        else {
+            const uint64_t midbits = (uint64_t)(hs - L);
+            const uint64_t mid = t & ((1ull << midbits) - 1ull), top = t >> midbits;
+            base = (mid << L) | (top << (hs + nh));
+        }
+        for (uint32_t idx = threadIdx.x; idx < tsize; idx += kPauliThreads)
+            tile[idx] = base_reg[base | (idx & lmask) | ((uint64_t)(idx >> L) << hs)];
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < kPauliM; ++b) {
+            if (!((tmask >> b) & 1u)) continue;
+            double a0s = 0.0, a1s = 0.0;
+            for (uint32_t j = threadIdx.x; j < (tsize >> 1); j += kPauliThreads) {
+                const uint32_t i0 = (uint32_t)insert0(j, b);
+                const double2 a0 = tile[i0], a1 = tile[i0 | (1u << b)];
+                const double2 b0 = cfma(u12, a1, cmul(u11, a0)), b1 = cfma(u22, a1, cmul(u21, a0));
+                const double q0 = abs2_exact(b0), q1 = abs2_exact(b1);
+                a0s += q0 > thr ? q0 : 0.0;
+                a1s += q1 > thr ? q1 : 0.0;
+            }
+            p0[b] += a0s; p1[b] += a1s;
+        }
+        __syncthreads();
+    }
+    __shared__ double red[kPauliThreads / 32][2 * kPauliM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int b = 0; b < kPauliM; ++b) {
+        double v0 = p0[b], v1 = p1[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+        if (lane == 0) { red[warp][2 * b] = v0; red[warp][2 * b + 1] = v1; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kPauliM) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kPauliThreads / 32; ++w) v += red[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * 2 * kPauliM + threadIdx.x] = v;
+    }
+}
+// one thread per (register, tile-local bit, 0/1): out[reg][phys bit][2], only the bits in tmask are written
+__global__ void __launch_bounds__(128)
+k_pauli_final(const double* __restrict__ partial, int nreg, int nq, int m, int L, int hs, uint32_t tmask, uint32_t ctas_per_reg,
+              double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nreg * 2 * kPauliM) return;
+    const int reg = e / (2 * kPauliM), r = e % (2 * kPauliM), b = r >> 1;
+    if (b >= m || !((tmask >> b) & 1u)) return;
+    double v = 0.0;
+    for (uint32_t c = 0; c < ctas_per_reg; ++c) v += partial[((size_t)reg * ctas_per_reg + c) * 2 * kPauliM + r];
+    const int phys = b < L ? b : hs + (b - L);
+    out[((size_t)reg * nq + phys) * 2 + (r & 1)] = v;
+}
+
 // K5  (p0, p1) of bit tbit after rotating it by R: measure_x / measure_y (QSim.jl:320-330); with
 // R = identity it is measure_z of a single qubit.  Fixed grid -> fixed summation tree.
 static const int kMeasBlocks = 1184;    // 148 SMs x 8

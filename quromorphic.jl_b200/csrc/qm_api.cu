@@ -785,13 +785,68 @@ extern "C" int32_t qm_measure_with(qm_state* st, int32_t t0, const double* R, do
     return qm_measure_phys(st, st->perm[t0], threshold, batch_idx, R, out);
 }
 
+// all-qubit marginals in the X or Y basis (or any caller-supplied rotation R): ceil((n - 12) / 9) + 1 reads of the state
+static int expect_all_rot(qm_state* st, const double* Rm, double thr, double* out_host) {
+    const int nl = st->nl, B = st->batch;
+    Mat2 R; memcpy(R.v, Rm, sizeof(R.v));
+    const int m = nl < kPauliM ? nl : kPauliM;
+    const uint64_t tiles_per_reg = 1ull << (nl - m);
+    uint64_t cpr = (uint64_t)st->sms * 4 / (uint64_t)B; if (cpr < 1) cpr = 1; if (cpr > tiles_per_reg) cpr = tiles_per_reg;
+    const uint64_t nctas = cpr * (uint64_t)B;
+    if (nctas > 0x7fffffffull) return set_err(QM_ERR_ARG, "batch too large for the readout grid");
+    const size_t part_doubles = (size_t)nctas * 2 * kPauliM, out_doubles = (size_t)B * nl * 2;
+    QM_TRY(ENSURE_DEV(st, d_scratch, (part_doubles + out_doubles) * 8));
+    QM_TRY(ENSURE_PIN(st, h_scratch, out_doubles * 8));
+    double* d_part = st->d_scratch; double* d_out = d_part + part_doubles;
+    static bool attr[64] = { false };
+    if (st->device < 0 || st->device >= 64 || !attr[st->device]) {
+        CU(cudaFuncSetAttribute(k_pauli_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << kPauliM));
+        if (st->device >= 0 && st->device < 64) attr[st->device] = true;
+    }
+    // pass 0: the m lowest bits (contiguous tiles); then windows of m - 3 high bits on 128-byte rows, the last one
+    // pulled back so that it ends at the top bit (bits measured twice are masked out)
+    int done = 0;
+    for (int pass = 0; done < nl; ++pass) {
+        int L, hs; uint32_t tmask;
+        if (pass == 0) { L = m; hs = m; tmask = (1u << m) - 1u; done = m; }
+        else {
+            L = 3; const int nh = m - L;
+            hs = done; if (hs + nh > nl) hs = nl - nh;
+            tmask = 0; for (int j = 0; j < nh; ++j) if (hs + j >= done) tmask |= 1u << (L + j);
+            done = hs + nh;
+        }
+        k_pauli_tile<<<(unsigned)nctas, kPauliThreads, (size_t)16 << m, st->stream>>>(st->amp, nl, m, L, hs, tmask, R, thr, (uint32_t)cpr, d_part);
+        CU(cudaGetLastError());
+        k_pauli_final<<<(unsigned)((B * 2 * kPauliM + 127) / 128), 128, 0, st->stream>>>(d_part, B, nl, m, L, hs, tmask, (uint32_t)cpr, d_out);
+        CU(cudaGetLastError());
+        st->ctr.launches += 2; st->ctr.bytes_hbm += 16ull * total_amps(st);
+    }
+    CU(cudaMemcpyAsync(st->h_scratch, d_out, out_doubles * 8, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += out_doubles * 8;
+    QM_TRY(qm_sync(st));
+    memcpy(out_host, st->h_scratch, out_doubles * 8);
+    return QM_OK;
+}
+
+extern "C" int32_t qm_expect_all_with(qm_state* st, const double* R, double threshold, double* out_host) {
+    if (!st || !out_host) return set_err(QM_ERR_ARG, "null argument");
+    if (!R) return qm_expect_z_all(st, threshold, out_host);
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    if (st->dist) {         // sharded: qubit by qubit (a rotated basis on a global qubit brings it home first, dist_measure)
+        for (int q = 0; q < st->n; ++q) QM_TRY(dist_measure(st, q, threshold, R, out_host + 2 * (size_t)q));
+        return QM_OK;
+    }
+    return expect_all_rot(st, R, threshold, out_host);
+}
+
 extern "C" int32_t qm_expect_all(qm_state* st, int32_t basis, double threshold, double* out_host) {
     if (!st || !out_host) return set_err(QM_ERR_ARG, "null argument");
+    if (basis < QM_BASIS_Z || basis > QM_BASIS_Y) return set_err(QM_ERR_ARG, "unknown basis %d", basis);
     if (basis == QM_BASIS_Z) return qm_expect_z_all(st, threshold, out_host);
-    for (int b = 0; b < st->batch; ++b)
-        for (int q = 0; q < st->n; ++q)
-            QM_TRY(qm_measure(st, basis, q, threshold, b, out_host + ((size_t)b * st->n + q) * 2));
-    return QM_OK;
+    double R[8];
+    if (basis == QM_BASIS_X) memcpy(R, kHmat, sizeof(R)); else y_rotation(R);
+    return qm_expect_all_with(st, R, threshold, out_host);
 }
 
 int qm_reduced_local(qm_state* st, int keep_low, int k, int batch_idx, double2** d_out_p) {

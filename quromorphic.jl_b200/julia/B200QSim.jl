@@ -15,10 +15,11 @@ module B200QSim
 
 using Quromorphic.QSim: H, X, Y, Z, I2, rx_gate, ry_gate, rz_gate
 import Quromorphic.QSim: nb, u2!, h!, x!, y!, z!, rx!, ry!, rz!, controlled!, cnot!, crx!, cry!, crz!,
-                          swap!, mp, measure_z, measure_x, measure_y, prstate
+                          swap!, mp, measure_z, measure_x, measure_y, prstate,
+                          density_matrix, statevector_to_density_matrix      # new METHODS of the reference's functions
 import Quromorphic.QInfo: partial_trace, entanglement_entropy, von_neumann_entropy
 
-export B200State, expect_z_all, reduced_density, sample, apply_circuit!, QMGate
+export B200State, B200Density, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, QMGate
 
 const LIB = get(ENV, "QM_B200_LIB", joinpath(@__DIR__, "..", "libqm_b200.so"))
 
@@ -37,6 +38,7 @@ mutable struct B200State
     batch::Int
     mode::Symbol          # :reference reproduces controlled!'s index map (QSim.jl:181-197); :corrected does not
     threshold::Float64    # measure_z's probability cut (QSim.jl:308)
+    world::Int            # ranks the register is sharded over (1: the whole register is on this GPU)
 end
 
 function lasterror()
@@ -48,7 +50,7 @@ end
 check(rc) = rc == 0 ? nothing : error(lasterror())      # ErrorException, like the reference
 
 # qm_set_option keys (include/qm_b200.h).  The defaults are the measured ones; these are tuning / debugging knobs.
-const OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_REMAP, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = 0:8
+const OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_TRACE, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = 0:8
 set_option!(s, key::Integer, value::Integer) =
     check(ccall((:qm_set_option, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), s.handle, key, value))
 
@@ -62,7 +64,7 @@ function B200State(n::Int, m::Int = 0; batch::Int = 1, device::Int = 0, mode::Sy
     0 <= m < (1 << n) || throw(BoundsError())            # statevector(n, m) indexes s[m+1]
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:qm_create, LIB), Int32, (Int32, UInt64, Int32, Int32, Ptr{Ptr{Cvoid}}), n, m, batch, device, h))
-    st = B200State(h[], n, batch, mode, threshold)
+    st = B200State(h[], n, batch, mode, threshold, 1)
     finalizer(s -> (s.handle != C_NULL && ccall((:qm_destroy, LIB), Int32, (Ptr{Cvoid},), s.handle); s.handle = C_NULL), st)
     st
 end
@@ -140,8 +142,8 @@ function load_gates(path::AbstractString)
 end
 
 # ---- readouts -----------------------------------------------------------------------------------
-function mp(s::B200State; batch_idx::Int = 0)             # QSim.jl:293
-    p = Vector{Float64}(undef, 1 << s.n)
+function mp(s::B200State; batch_idx::Int = 0)             # QSim.jl:293 (a sharded register: this rank's slice)
+    p = Vector{Float64}(undef, (1 << s.n) ÷ s.world)
     check(ccall((:qm_probs, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), s.handle, p, batch_idx))
     p
 end
@@ -162,6 +164,22 @@ measure_y(s::B200State, t::Int; batch_idx::Int = 0) = _measure(s, t, rx_gate(π 
 function expect_z_all(s::B200State; threshold::Float64 = s.threshold)
     out = Array{Float64}(undef, 2, s.n, s.batch)
     check(ccall((:qm_expect_z_all, LIB), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}), s.handle, threshold, out))
+    out
+end
+
+"""
+    expect_all(s, basis)   basis = :z, :x, :y or a 2x2 rotation matrix
+
+measure_z / measure_x / measure_y (QSim.jl:297-330) of EVERY qubit: 2 x n x batch array of (p0, p1).  X and Y read the
+state once per window of 12 (then 9) qubits and rotate every pair in registers; the matrices are the host's own H and
+rx_gate(pi/2), so the engine sees the same bits measure_x / measure_y pass.
+"""
+function expect_all(s::B200State, basis; threshold::Float64 = s.threshold)
+    R = basis === :z ? nothing : basis === :x ? H : basis === :y ? rx_gate(π / 2) : basis
+    out = Array{Float64}(undef, 2, s.n, s.batch)
+    Rp = R === nothing ? Ptr{ComplexF64}(C_NULL) : pointer(R)
+    GC.@preserve R check(ccall((:qm_expect_all_with, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Float64, Ptr{Float64}),
+                               s.handle, Rp, threshold, out))
     out
 end
 

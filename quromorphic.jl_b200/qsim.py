@@ -178,6 +178,21 @@ class B200State:
         L.check(L.lib().qm_expect_z_all(self._h, thr, L.dptr(out)))
         return out if self.batch > 1 else out[0]
 
+    def expect_all(self, basis, threshold=None):
+        """[batch, n, 2] array of (p0, p1): measure_z / measure_x / measure_y of EVERY qubit (QSim.jl:297-330).
+        basis: "z", "x", "y" or a 2x2 rotation matrix R (the marginals of R applied to each qubit in turn).  The
+        X/Y matrices are the host's own H and rx_gate(pi/2), as in measure_x / measure_y below."""
+        out = np.empty((self.batch, self.n, 2), dtype=np.float64)
+        thr = self.threshold if threshold is None else threshold
+        if isinstance(basis, str):
+            b = basis.lower()
+            R = None if b == "z" else (H if b == "x" else rx_gate(np.pi / 2))
+        else:
+            R = np.asarray(basis, dtype=np.complex128)
+        Rp = L.dptr(L.mat8(R)) if R is not None else None
+        L.check(L.lib().qm_expect_all_with(self._h, Rp, thr, L.dptr(out)))
+        return out if self.batch > 1 else out[0]
+
     def reduced_density(self, keep_low, k, batch_idx=0):
         d = 1 << k
         out = np.empty(d * d, dtype=np.complex128)
@@ -351,7 +366,7 @@ def mp(s, batch_idx=0):
         out = np.empty(1 << s.q, dtype=np.float64)
         L.check(L.lib().qm_dm_diag(s.vec._h, L.dptr(out)))
         return out
-    out = np.empty(1 << s.n, dtype=np.float64)
+    out = np.empty(s.local_len, dtype=np.float64)      # a sharded register returns this rank's contiguous slice
     L.check(L.lib().qm_probs(s._h, L.dptr(out), batch_idx))
     return out
 
@@ -382,6 +397,11 @@ def measure_x(s, t, batch_idx=0):
 def measure_y(s, t, batch_idx=0):
     """measure_y(s, t) = measure_z(rx!(copy(s), t, pi/2), t), QSim.jl:326-330"""
     return _measure(s, t, rx_gate(np.pi / 2), batch_idx)
+
+
+def measure_all(s, basis="z"):
+    """measure_z / measure_x / measure_y for every qubit t = 1..n in one call: array [n, 2] (or [batch, n, 2])"""
+    return s.expect_all(basis)
 
 
 def prstate(s, batch_idx=0, file=None):

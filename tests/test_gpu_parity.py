@@ -464,3 +464,60 @@ def test_permutation_circuits_bit_exact_on_the_tma_kernel(pkg, n, seed):
     ref = O.apply_circuit(ref, gates)
     assert rel_err(st.to_numpy(), ref) < RTOL
     st.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 11, 12, 13, 16, 21, 22])
+def test_all_qubit_x_and_y_marginals_match_oracle(pkg, n):
+    """qm_expect_all_with: measure_x / measure_y (QSim.jl:320-330) of EVERY qubit from ceil((n-12)/9)+1 reads of the
+    state, against the oracle's copy-rotate-scan per qubit; the threshold applies to the rotated probabilities."""
+    psi0 = O.random_state(n, 900 + n)
+    st = pkg.B200State.from_numpy(psi0)
+    st.apply_circuit(random_circuit(pkg, n, 40, 31 + n))
+    ref = O.apply_circuit(psi0.copy(), random_circuit(pkg, n, 40, 31 + n))
+    before = st.counters()["launches"]
+    for basis, fo in (("x", O.measure_x), ("y", O.measure_y), ("z", O.measure_z)):
+        got = st.expect_all(basis)
+        want = np.array([fo(ref, t) for t in range(1, n + 1)])
+        assert got.shape == (n, 2)
+        assert np.max(np.abs(got - want)) < RTOL, basis
+        # no threshold at all (the literal sums)
+        got0 = st.expect_all(basis, threshold=-1.0)
+        want0 = np.array([fo(ref, t, -1.0) for t in range(1, n + 1)])
+        assert np.max(np.abs(got0 - want0)) < RTOL, basis
+    # X and Y: one kernel pair per window of qubits, not one per qubit
+    windows = 1 if n <= 12 else 1 + -(-(n - 12) // 9)
+    assert st.counters()["launches"] - before == 2 * (2 * 2 * windows) + 2 * 2
+    # the module-level mirror
+    assert np.array_equal(pkg.qsim.measure_all(st, "x"), st.expect_all("x"))
+
+
+def test_all_qubit_x_marginals_apply_the_threshold_to_rotated_probabilities(pkg):
+    """amplitudes chosen so that |a|^2 is above 1e-10 but the H-rotated probability of one branch is below it"""
+    n = 13
+    v = np.zeros(1 << n, dtype=np.complex128)
+    v[0] = 1.0
+    eps = 3e-6                                   # (eps / sqrt 2)^2 = 4.5e-12 < 1e-10 < eps^2 ... both dropped / kept differently
+    v[5] = eps; v[5 | (1 << 12)] = -eps * (1 - 1e-3)
+    v[77] = 2e-5; v[77 ^ 1] = 2e-5               # |a|^2 = 4e-10 kept in Z; X-rotated: 8e-10 and exactly 0
+    st = pkg.B200State.from_numpy(v)
+    for basis, fo in (("x", O.measure_x), ("y", O.measure_y)):
+        got = st.expect_all(basis)
+        want = np.array([fo(v, t) for t in range(1, n + 1)])
+        assert np.max(np.abs(got - want)) < 1e-14, basis
+        one = np.array([getattr(pkg.qsim, "measure_" + basis)(st, t) for t in range(1, n + 1)])
+        assert np.max(np.abs(got - one)) < 1e-14
+
+
+def test_all_qubit_x_marginals_batched(pkg):
+    B, n = 5, 14
+    st = pkg.B200State(n, 0, batch=B)
+    refs = []
+    for b in range(B):
+        psi = O.random_state(n, 60 + b)
+        st.upload(psi, b)
+        refs.append(psi)
+    got = st.expect_all("y")
+    assert got.shape == (B, n, 2)
+    for b in range(B):
+        want = np.array([O.measure_y(refs[b], t) for t in range(1, n + 1)])
+        assert np.max(np.abs(got[b] - want)) < RTOL

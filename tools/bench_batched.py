@@ -15,6 +15,39 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 
+def run_c2(pkg, steps=8, batch=4096, n=16, max_cost=-1):
+    C, L = pkg.circuits, pkg._lib
+    B = batch
+    gates = C.c2_step_gates(n, seed=1603)
+    w = [C.SplitMix64(7).uniform() for _ in range(n)]
+    st = pkg.B200State(n, 0, batch=B)
+    if max_cost >= 0:
+        st.set_option(L.OPT_MAX_COST, max_cost)
+    encs = [C.c2_encoding(B, n, t, w) for t in range(3)]
+    for t in range(2):
+        st.apply_batched(gates, encs[t]); st.expect_z_all()
+    st.sync(); st.counters_reset()
+    dev_ms, t0 = 0.0, time.perf_counter()
+    for t in range(steps):
+        st.apply_batched(gates, encs[t % 3])
+        st.expect_z_all()
+        dev_ms += st.counters()["ms_device"]
+    wall = time.perf_counter() - t0
+    c = st.counters()
+    per_pass = dev_ms / max(c["passes"], 1)
+    gbs = 32.0 * B * (1 << n) / (per_pass * 1e-3) / 1e9
+    out = {"workload": "C2: %d independent %d-qubit registers in lockstep, per-state ry encodings + shared reservoir layer + "
+                       "CNOT chain, all-qubit <Z> per register per step" % (B, n),
+           "batch": B, "n_qubits": n, "steps": steps, "gates_per_step_per_register": len(gates),
+           "passes_per_step": c["passes"] / steps, "ms_circuit_per_step_device": dev_ms / steps, "ms_per_pass": per_pass,
+           "fused_pass_gbs": gbs, "ms_per_step_wall_incl_readout_and_encoding_upload": 1e3 * wall / steps,
+           "gate_applications_per_s_device": B * len(gates) * steps / (dev_ms * 1e-3),
+           "gate_applications_per_s_wall": B * len(gates) * steps / wall,
+           "h2d_bytes_per_step": c["bytes_h2d"] / steps, "d2h_bytes_per_step": c["bytes_d2h"] / steps}
+    st.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4096)
@@ -22,33 +55,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--max-cost", type=int, default=-1)
     a = ap.parse_args()
-    pkg = ge.load_package()
-    C, L = pkg.circuits, pkg._lib
-    n, B = a.qubits, a.batch
-    gates = C.c2_step_gates(n, seed=1603)
-    w = [C.SplitMix64(7).uniform() for _ in range(n)]
-    st = pkg.B200State(n, 0, batch=B)
-    if a.max_cost >= 0:
-        st.set_option(L.OPT_MAX_COST, a.max_cost)
-    encs = [C.c2_encoding(B, n, t, w) for t in range(3)]
-    for t in range(2):
-        st.apply_batched(gates, encs[t]); st.expect_z_all()
-    st.sync(); st.counters_reset()
-    dev_ms, t0 = 0.0, time.perf_counter()
-    for t in range(a.steps):
-        st.apply_batched(gates, encs[t % 3])
-        z = st.expect_z_all()
-        dev_ms += st.counters()["ms_device"]
-    wall = time.perf_counter() - t0
-    c = st.counters()
-    per_pass = dev_ms / max(c["passes"], 1)
-    gbs = 32.0 * B * (1 << n) / (per_pass * 1e-3) / 1e9
-    print(json.dumps({"workload": "C2 batched", "batch": B, "n_qubits": n, "steps": a.steps, "gates_per_step_per_register": len(gates),
-                      "passes_per_step": c["passes"] / a.steps, "ms_circuit_per_step_device": dev_ms / a.steps, "ms_per_pass": per_pass,
-                      "fused_pass_gbs": gbs, "ms_per_step_wall_incl_readout_and_encoding_upload": 1e3 * wall / a.steps,
-                      "gate_applications_per_s_device": B * len(gates) * a.steps / (dev_ms * 1e-3),
-                      "h2d_bytes_per_step": c["bytes_h2d"] / a.steps}))
-    st.close()
+    print(json.dumps(run_c2(ge.load_package(), a.steps, a.batch, a.qubits, a.max_cost)))
 
 
 if __name__ == "__main__":

@@ -18,7 +18,10 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 
-def run_c5(pkg, O, LIT, n, T, k, cpu_steps):
+def run_c5(pkg, n, T, k, cpu_steps):
+    if cpu_steps:
+        from oracle import literal as LIT
+        from oracle import oracle as O
     R = pkg.reservoir
     rng = np.random.default_rng(2001)
     lsm = R.LSMNet(rng.uniform(-1, 1, size=(50, 3)), 0.05 * rng.normal(size=(50, 50)), leak_rate=0.3)
@@ -30,8 +33,8 @@ def run_c5(pkg, O, LIT, n, T, k, cpu_steps):
     feats = qr.collect_states(drive)
     wall = time.perf_counter() - t0
     c = qr.state.counters()
-    # CPU port on a prefix of the same steps
-    ref = O.statevector(n, 0)
+    # CPU port on a prefix of the same steps (cpu_steps = 0: GPU side only)
+    ref = O.statevector(n, 0) if cpu_steps else None
     t1 = time.perf_counter()
     err = 0.0
     for t in range(cpu_steps):
@@ -44,11 +47,14 @@ def run_c5(pkg, O, LIT, n, T, k, cpu_steps):
     return {"workload": "C5: LSM (50 units) -> %d-qubit reservoir, <Z> all qubits + entropies of rho_B / rho_A (k = %d) per step" % (n, k),
             "steps": T, "gates_per_step": len(qr.step_gates(drive[:, 0])), "steps_per_s": T / wall, "ms_per_step": 1e3 * wall / T,
             "launches_per_step": c["launches"] / T, "passes_per_step": c["passes"] / T,
-            "cpu_port_steps_per_s": cpu_steps / cpu, "cpu_steps_timed": cpu_steps, "cpu_threads": os.cpu_count(),
-            "max_abs_diff_vs_cpu_port": err}
+            "cpu_port_steps_per_s": (cpu_steps / cpu) if cpu_steps else None, "cpu_steps_timed": cpu_steps,
+            "cpu_threads": O.num_threads() if cpu_steps else None,
+            "max_abs_diff_vs_cpu_port": err if cpu_steps else None}
 
 
-def run_c1(pkg, O, n, T, cpu_steps):
+def run_c1(pkg, n, T, cpu_steps):
+    if cpu_steps:
+        from oracle import oracle as O
     Q, C = pkg.qsim, pkg.circuits
     u, w, layer, gamma = C.c1_inputs(n, T)
 
@@ -75,7 +81,7 @@ def run_c1(pkg, O, n, T, cpu_steps):
         out[:, t] = z[:, 0] - z[:, 1]
     wall = time.perf_counter() - t0
     c = st.counters()
-    ref = O.statevector(n, 0)
+    ref = O.statevector(n, 0) if cpu_steps else None
     t1 = time.perf_counter()
     err = 0.0
     for t in range(cpu_steps):
@@ -86,8 +92,9 @@ def run_c1(pkg, O, n, T, cpu_steps):
     st.close()
     return {"workload": "C1: %d-qubit reservoir, %d gates per step (incl. the non-adjacent crz!), <Z> of every qubit per step" % (n, len(step_gates(0))),
             "steps": T, "steps_per_s": T / wall, "ms_per_step": 1e3 * wall / T, "launches_per_step": c["launches"] / T,
-            "cpu_port_steps_per_s": cpu_steps / cpu, "cpu_steps_timed": cpu_steps, "cpu_threads": os.cpu_count(),
-            "max_abs_diff_vs_cpu_port": err}
+            "cpu_port_steps_per_s": (cpu_steps / cpu) if cpu_steps else None, "cpu_steps_timed": cpu_steps,
+            "cpu_threads": O.num_threads() if cpu_steps else None,
+            "max_abs_diff_vs_cpu_port": err if cpu_steps else None}
 
 
 def main():
@@ -97,10 +104,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=20)
     a = ap.parse_args()
     pkg = ge.load_package()
-    from oracle import literal as LIT
-    from oracle import oracle as O
-    print(json.dumps(run_c1(pkg, O, 12, a.steps, min(a.cpu_steps * 5, a.steps))), flush=True)
-    print(json.dumps(run_c5(pkg, O, LIT, a.c5_qubits, a.steps, 4, min(a.cpu_steps, a.steps))), flush=True)
+    print(json.dumps(run_c1(pkg, 12, a.steps, min(a.cpu_steps * 5, a.steps))), flush=True)
+    print(json.dumps(run_c5(pkg, a.c5_qubits, a.steps, 4, min(a.cpu_steps, a.steps))), flush=True)
 
 
 if __name__ == "__main__":
