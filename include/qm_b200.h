@@ -58,11 +58,12 @@ enum { QM_BASIS_Z = 0, QM_BASIS_X = 1, QM_BASIS_Y = 2 };
 /* qm_set_option keys */
 enum {
     QM_OPT_EAGER      = 0,  /* 1: run every gate call at once with the unfused kernels (default 0: queue + fuse) */
-    QM_OPT_TILE_BITS  = 1,  /* fused pass tile size m: 11 or 12 for the TMA kernel; default 0 = automatic (12) */
+    QM_OPT_TILE_BITS  = 1,  /* fused pass tile size m: 11 or 12 for the TMA kernels; default 0 = automatic (11) */
     QM_OPT_LOW_BITS   = 2,  /* contiguous low bits every tile keeps (default 5: 512-byte rows)                    */
     QM_OPT_FUSE       = 3,  /* 0: planner emits one pass per gate (debug), 1: fuse (default)                      */
     QM_OPT_TRACE      = 4,  /* 1: CTA 0 of every fused pass records SM-clock stamps per tile (qm_trace_read; diagnostics) */
-    QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel                     */
+    QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel; 1 (default): persistent TMA kernels — split inbound/outbound buffers at
+                               2^11-amplitude tiles, in-place ring at 2^12; 2: the in-place ring kernel at both sizes */
     QM_OPT_MAX_COST   = 6,  /* planner: budget of a pass = gate costs (FP64 FMAs per amplitude + 1) + 18 per register-block group (planner.hpp gate_cost); default 80, 0 = no cap */
     QM_OPT_TIME_PASSES = 7, /* 1: CUDA events around every fused pass, read back with qm_pass_times (diagnostics) */
     QM_OPT_SHORT_PCT = 8    /* planner: a circuit shorter than the look-ahead window (a reservoir step before a readout) is planned at the multiple of the budget, up to this many per cent, that the pass model says finishes first; default 0 = no limit, 100 = off */

@@ -257,14 +257,18 @@ void orc_reduced_density(const double* s, int n, int keep_low, int k, double* ou
 #pragma omp parallel for schedule(static) collapse(2) if (n >= 12)
     for (uint64_t j = 0; j < d; ++j)
         for (uint64_t i = 0; i < d; ++i) {
-            double sr = 0.0, si = 0.0;
+            /* The reference adds these terms left to right in Float64 (QInfo.jl:387-389, :398-400); with 2^26 terms per
+             * entry (30 qubits, k = 4) that order alone carries ~1e-11 of rounding, more than the 1e-12 the parity bar
+             * asks of the engine.  The checker therefore accumulates in x87 extended precision (64-bit mantissa): the
+             * products are still IEEE doubles, the SUM is the exact one to ~1e-19 per term. */
+            long double sr = 0.0L, si = 0.0L;
             for (uint64_t x = 0; x < rest; ++x) {
                 cplx p = keep_low ? psi[x * d + i] : psi[i * rest + x];
                 cplx q = keep_low ? psi[x * d + j] : psi[j * rest + x];
-                sr += p.re * q.re + p.im * q.im;       /* p * conj(q) */
-                si += p.im * q.re - p.re * q.im;
+                sr += (long double)(p.re * q.re) + (long double)(p.im * q.im);       /* p * conj(q) */
+                si += (long double)(p.im * q.re) - (long double)(p.re * q.im);
             }
-            r[j * d + i].re = sr; r[j * d + i].im = si;
+            r[j * d + i].re = (double)sr; r[j * d + i].im = (double)si;
         }
     cplx* o = (cplx*)out;
     for (uint64_t j = 0; j < d; ++j)

@@ -141,7 +141,9 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
         if (value && !st->trace_buf) { CU(cudaMalloc((void**)&st->trace_buf, kTraceBytes)); CU(cudaMemset(st->trace_buf, 0, kTraceBytes)); }
         if (!value && st->trace_buf) { CU(cudaStreamSynchronize(st->stream)); cudaFree(st->trace_buf); st->trace_buf = nullptr; }
         break;
-    case QM_OPT_PIPELINE: st->pipeline = value != 0; break;
+    case QM_OPT_PIPELINE:
+        if (value < 0 || value > 2) return set_err(QM_ERR_ARG, "pipeline must be 0, 1 or 2");
+        st->pipeline = (int)value; break;
     case QM_OPT_MAX_COST: st->max_cost = (double)value; break;
     case QM_OPT_TIME_PASSES: st->time_passes = value != 0; break;
     case QM_OPT_SHORT_PCT:
@@ -283,7 +285,8 @@ int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const
     for (int i = 0; i < kV4Gaps; ++i) { lp.gap_start[i] = i < (int)gaps.size() ? gaps[i].first : 0; lp.gap_len[i] = i < (int)gaps.size() ? gaps[i].second : 0; }
     lp.rank_or = st->g ? ((uint64_t)st->rank << st->nl) : 0; lp.nslots = nslots;
     lp.trace = st->trace_buf;
-    if (P.m == 11) QM_TRY(launch_v4_m11(stream, st->sms, tm, prog, d_slots, lp));
+    if (P.m == 11 && st->pipeline != 2) QM_TRY(launch_v4_s11(stream, st->sms, tm, prog, d_slots, lp));
+    else if (P.m == 11) QM_TRY(launch_v4_m11(stream, st->sms, tm, prog, d_slots, lp));
     else QM_TRY(launch_v4_m12(stream, st->sms, tm, prog, d_slots, lp));
     // the program crosses the host link with the launch: counted as host->device bytes
     st->ctr.bytes_h2d += offsetof(V4Program, recs) + (size_t)prog.nrecs * sizeof(V4Rec);
@@ -315,9 +318,9 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         st->ctr.gates += ngates;
         return QM_OK;
     }
-    // tile size: 2^12 amplitudes unless the caller asks for 2^11 (four teams of 128 threads, six stages): the two are
-    // within 1 % of each other for single-group passes, 2^12 holds more qubits per pass for deep fusion
-    const int tile_bits = st->tile_bits ? st->tile_bits : 12;
+    // tile size: 2^11 amplitudes on the split-buffer kernel (three teams of 128 threads, an inbound and an outbound
+    // buffer each) unless the caller asks for 2^12 (the in-place ring kernel: two teams of 256 threads, three stages)
+    const int tile_bits = st->tile_bits ? st->tile_bits : (st->nl >= 11 ? 11 : 12);
     Planner pl;
     pl.opt.n_local = st->nl; pl.opt.n_global = st->g;
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = st->low_bits; pl.opt.fuse = st->fuse;
@@ -603,8 +606,8 @@ extern "C" int32_t qm_apply_batched(qm_state* st, const qm_gate* gates, int32_t 
     CU(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(st->d_slots) + bytes, lifts.data(), bytes, cudaMemcpyHostToDevice, st->stream));
     CU(cudaStreamSynchronize(st->stream));
     st->ctr.bytes_h2d += 2 * bytes;
-    const bool saved = st->pipeline;
-    if (!all_liftable) st->pipeline = false;
+    const int saved = st->pipeline;
+    if (!all_liftable) st->pipeline = 0;
     int rc = run_circuit(st, gates, ngates, st->d_slots, nsub, &sm, st->d_slots + mats.size());
     st->pipeline = saved;
     return rc;

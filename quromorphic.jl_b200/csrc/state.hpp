@@ -33,7 +33,10 @@ struct qm_state {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
     bool ev_pending = false;
     // options
-    bool eager = false, fuse = true, pipeline = true;
+    bool eager = false, fuse = true;
+    int pipeline = 1;           // QM_OPT_PIPELINE: 0 general kernel, 1 TMA kernels (split buffers at 2^11 tiles), 2 in-place ring kernel at every tile size
+    bool overlap = true;        // sharded: run the exchange beside the passes when the plan allows (QM_OPT_OVERLAP)
+    int xsm = 16, xun = 8;      // sharded, overlapped exchange: SMs the exchange kernel claims, loads in flight per thread
     bool time_passes = false;   // QM_OPT_TIME_PASSES: CUDA events around every fused pass (diagnostics, tools/pass_model.py)
     std::vector<cudaEvent_t> pass_events;      // 2 per timed pass, resolved by qm_pass_times
     std::vector<float> pass_desc;              // per timed pass: groups, records, planner cost

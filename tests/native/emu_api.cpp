@@ -1,4 +1,4 @@
-// emu_api.cu — TEST INFRASTRUCTURE, host only, built into tests/native/libqm_emu.so (NOT into libqm_b200.so):
+// emu_api.cpp — TEST INFRASTRUCTURE, host only, built into tests/native/libqm_emu.so (NOT into libqm_b200.so):
 // plans a gate list exactly as the engine does for its TMA kernel, encodes every pass with the engine's own encoder
 // (csrc/encode_v4.hpp) and walks the encoded programs over a host vector with the scalar restatement of the
 // kernel's interpreter in emulate.hpp.  Lets the CPU suite check planner + encoder against the oracle without a GPU.
