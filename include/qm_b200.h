@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define QM_ABI_VERSION 1
+#define QM_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -58,14 +58,17 @@ enum { QM_BASIS_Z = 0, QM_BASIS_X = 1, QM_BASIS_Y = 2 };
 /* qm_set_option keys */
 enum {
     QM_OPT_EAGER      = 0,  /* 1: run every gate call at once with the unfused kernels (default 0: queue + fuse) */
-    QM_OPT_TILE_BITS  = 1,  /* fused pass tile size m: 11 or 12 for the TMA kernels; default 0 = automatic (11) */
+    QM_OPT_TILE_BITS  = 1,  /* fused pass tile size m: 11 or 12 for the TMA kernels; default 0 = automatic (12) */
     QM_OPT_LOW_BITS   = 2,  /* contiguous low bits every tile keeps (default 5: 512-byte rows)                    */
     QM_OPT_FUSE       = 3,  /* 0: planner emits one pass per gate (debug), 1: fuse (default)                      */
     QM_OPT_TRACE      = 4,  /* 1: CTA 0 of every fused pass records SM-clock stamps per tile (qm_trace_read; diagnostics) */
-    QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel; 1 (default): persistent TMA kernels — split inbound/outbound buffers at
-                               2^11-amplitude tiles, in-place ring at 2^12; 2: the in-place ring kernel at both sizes */
+    QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel                     */
     QM_OPT_MAX_COST   = 6,  /* planner: budget of a pass = gate costs (FP64 FMAs per amplitude + 1) + 18 per register-block group (planner.hpp gate_cost); default 80, 0 = no cap */
     QM_OPT_TIME_PASSES = 7, /* 1: CUDA events around every fused pass, read back with qm_pass_times (diagnostics) */
+    QM_OPT_OVERLAP   = 9,   /* sharded registers: 1 (default) run the global<->local exchange slab by slab beside the passes before and after it, 0: exchange between passes */
+    QM_OPT_XSM       = 10,  /* ... SMs the overlapped exchange kernel claims (default 16; the passes beside it use the rest) */
+    QM_OPT_XUN       = 11,  /* ... amplitude pairs in flight per exchange thread: 4 (1024 threads per SM) or 8 (512, default) */
+    QM_OPT_SLAB_BITS = 12,  /* ... log2 of the number of slabs (1..3, default 2) */
     QM_OPT_SHORT_PCT = 8    /* planner: a circuit shorter than the look-ahead window (a reservoir step before a readout) is planned at the multiple of the budget, up to this many per cent, that the pass model says finishes first; default 0 = no limit, 100 = off */
 };
 
@@ -92,6 +95,7 @@ typedef struct qm_counters_t {
     double   ms_device;      /* CUDA-event time of the last flushed circuit     */
     double   ms_plan;        /* host planning time of the last flushed circuit  */
     double   ms_remap;       /* CUDA-event time spent in global-qubit remaps (all-to-all) since reset */
+    uint64_t overlapped_remaps; /* remaps that ran slab by slab beside the fused passes before and after them */
 } qm_counters_t;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -187,12 +191,22 @@ int32_t qm_dist_unique_id(uint8_t id_out[128]);
 int32_t qm_create_dist(int32_t n_qubits, uint64_t basis_index, int32_t device, int32_t rank,
                        int32_t world, const uint8_t nccl_id[128], qm_state** out);
 
-/* Optional, after qm_create_dist: map the other ranks' shards into this process (CUDA IPC) so that the
- * global<->local exchange is ONE kernel doing loads/stores over NVLink peer memory instead of NCCL
- * send/recv through a staging ring.  Every rank exports 64 bytes, the host all-gathers them
- * (world x 64 bytes, rank-major) and every rank imports.  If the import fails the engine keeps NCCL. */
+/* Optional, after qm_create_dist: map the other ranks' shards into this process (CUDA IPC).  With peer memory the
+ * global<->local exchange is a kernel of loads/stores over NVLink (no staging), ranks are ordered by flags in each
+ * other's memory that the consumer's STREAM waits on (no NCCL kernel, no SM), the exchange runs slab by slab beside the
+ * fused passes before and after it, and the readouts' small collectives go through mailboxes in rank order.  Every rank
+ * exports 64 bytes, the host all-gathers them (world x 64 bytes, rank-major) and every rank imports.  If the import
+ * fails the engine keeps NCCL (grouped send/recv through a staging ring, ncclAllReduce for the readouts). */
 int32_t qm_dist_ipc_export(qm_state* st, uint8_t handle_out[64]);
 int32_t qm_dist_ipc_import(qm_state* st, const uint8_t* handles);
+
+/* All ranks of a sharded register inside ONE process (one host thread per rank, one device or several with peer
+ * access): no NCCL, no IPC — the ranks see each other through plain pointers.  `key` names the world; every rank calls
+ * qm_create_dist_local with the same key, and once all of them have returned (the caller's own barrier) every rank
+ * calls qm_dist_local_connect.  This is how the sharded kernels, fences and collectives are tested on a 1-GPU box. */
+int32_t qm_create_dist_local(int32_t n_qubits, uint64_t basis_index, int32_t device, int32_t rank,
+                             int32_t world, uint64_t key, qm_state** out);
+int32_t qm_dist_local_connect(qm_state* st);
 
 /* ---- host-only planner introspection (works without a GPU; used by the CPU tests) ------
  * Plans `gates` for an n-qubit register with the given tile/low-bit sizes and `global_bits`

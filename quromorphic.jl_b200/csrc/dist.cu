@@ -3,14 +3,30 @@
 // control or a diagonal target on a global qubit is a rank predicate / rank-dependent phase inside
 // the ordinary kernels).  When the planner runs out of local work, the g global qubits are exchanged
 // with the top g local ones: viewed as [2^g chunks][2^(n-2g)], chunk j of rank r trades places with
-// chunk r of rank j — an all-to-all done IN PLACE through a small staging ring, because a 2^33
-// amplitude shard (128 GiB) leaves no room for an out-of-place copy on a 180 GB part.
-// NCCL (grouped ncclSend/ncclRecv over NVLink 5 / NVSwitch) is dlopen'ed on first use.
+// chunk r of rank j — an all-to-all done IN PLACE, because a 2^33-amplitude shard (128 GiB) leaves no
+// room for an out-of-place copy on a 180 GB part.
+//
+// Two transports:
+//  * PEER MEMORY (preferred; CUDA IPC between processes, or plain pointers between the ranks of one process):
+//    every rank sees the others' shards and a small WINDOW (flags + mailboxes) that sits right behind each shard
+//    in the same allocation.  The exchange is one kernel of loads/stores over NVLink (k_remap_swap); ranks are
+//    ordered by FLAGS — a one-warp kernel stores an epoch number into every rank's window after
+//    __threadfence_system(), the consumer's STREAM waits on its own window with cuStreamWaitValue32 — so no
+//    fence costs an SM or a NCCL kernel, and no kernel ever spins on another GPU.  With that the exchange is cut
+//    into SLABS (a few index bits pinned) and runs on a second stream BESIDE the fused passes of the neighbouring
+//    slabs (run_circuit in qm_api.cu): the pass before the exchange and the pass after it hide most of it.
+//    The small collectives of the readouts (sums of a few doubles, the sampler's level-1 all-gather) go through
+//    the mailboxes and are folded in rank order, so every rank computes bit-identical results.
+//  * NCCL (fallback when peer mapping is refused): grouped ncclSend/ncclRecv through a staging ring and
+//    ncclAllReduce / ncclAllGather for the readouts.  NCCL is dlopen'ed on first use.
 #include "dist.hpp"
 
+#include <cuda.h>
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
 
 using namespace qm;
 
@@ -49,62 +65,149 @@ static int nccl_load() {
 }
 #define NC(x) do { int r_ = (x); if (r_ != 0) return set_err(QM_ERR_COMM, "%s failed: %s", #x, g_nccl.GetErrorString(r_)); } while (0)
 
+// ---- stream memory operations (driver API, resolved at run time) ---------------------------------------------
+typedef CUresult (*PFN_waitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static PFN_waitValue32 get_wait_value() {
+    static PFN_waitValue32 fn = nullptr; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_waitValue32)p;
+    }
+    return fn;
+}
+
 // ---------------------------------------------------------------------------------------------
-// K7  global<->local qubit exchange over peer memory.  Chunk j of rank r trades places with chunk r
-// of rank j.  Every rank runs ONE kernel: for each peer it owns half of the chunk pair (the lower
-// rank the first half, the higher rank the second), loads its own 16 bytes and the peer's 16 bytes
-// (a load over NVLink), and stores them crosswise (a store over NVLink).  In place, no staging, both
-// link directions busy; each amplitude pair is touched by exactly one thread of one rank.
-// Ranks are fenced before and after by a one-element NCCL all-reduce on the same stream (the kernel
-// itself never waits on another GPU).
+// The window behind every shard:  flags[1024] (uint32)  |  mailboxes [2 parities][16 sources][kMboxBytes]
+// flag index = kind * 256 + source rank * 16 + slab
 // ---------------------------------------------------------------------------------------------
+enum { FK_PASS = 0, FK_EXCH = 1, FK_MBOX = 2, FK_FENCE = 3 };
+static const size_t kFlagBytes = 4096;
+static const size_t kMboxBytes = 128u << 10;
+static const size_t kWinBytes = kFlagBytes + 2 * 16 * kMboxBytes;
+size_t dist_window_bytes() { return kWinBytes; }
+
+struct PeerWins { unsigned char* p[16]; };
 struct PeerPtrs { double2* p[16]; };
 
-// Work is cut into 64 KiB segments that are dealt round-robin over the peers, and every rank starts
-// its round at a different peer ((rank + 1 + k) mod world), so at any moment each GPU's NVLink ingress
-// is fed by all the others evenly instead of everyone hammering the same peer.
-__global__ void __launch_bounds__(512)
-k_remap_swap(double2* __restrict__ mine, PeerPtrs peers, int rank, int world, unsigned long long chunk) {
+// after everything earlier in the stream: make it visible system-wide, then post `epoch` in every rank's window
+__global__ void k_signal(const __grid_constant__ PeerWins pw, int world, int flag_index, uint32_t epoch) {
+    const int j = threadIdx.x;
+    __threadfence_system();
+    if (j < world) {
+        volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(pw.p[j]) + flag_index;
+        *f = epoch;
+    }
+}
+
+// block j copies n16 16-byte words from src into mailbox [parity][me] of rank j, then posts the epoch there
+__global__ void __launch_bounds__(256)
+k_mbox_put(const __grid_constant__ PeerWins pw, int me, int parity, const uint4* __restrict__ src, uint32_t n16, uint32_t epoch) {
+    const int j = blockIdx.x;
+    uint4* dst = reinterpret_cast<uint4*>(pw.p[j] + kFlagBytes + ((size_t)parity * 16 + me) * kMboxBytes);
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(pw.p[j]) + (FK_MBOX * 256 + me * 16);
+        *f = epoch;
+    }
+}
+// out[i] = sum over ranks in rank order of mailbox[parity][r][i]: the same bits on every rank
+template <typename T>
+__global__ void k_mbox_sum(const unsigned char* win, int world, int parity, uint32_t count, T* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    T acc = 0;
+    for (int r = 0; r < world; ++r)
+        acc += reinterpret_cast<const volatile T*>(win + kFlagBytes + ((size_t)parity * 16 + r) * kMboxBytes)[i];
+    out[i] = acc;
+}
+// out[r * stride + i] = mailbox[parity][r][i]
+__global__ void k_mbox_gather(const unsigned char* win, int world, int parity, uint32_t count, size_t stride, double* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    for (int r = 0; r < world; ++r)
+        out[(size_t)r * stride + i] = reinterpret_cast<const volatile double*>(win + kFlagBytes + ((size_t)parity * 16 + r) * kMboxBytes)[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7  global<->local qubit exchange over peer memory.  Chunk j of rank r trades places with chunk r of rank j.
+// For each peer a rank owns half of the chunk pair (the lower rank the first half, the higher rank the second),
+// loads its own 16 bytes and the peer's 16 bytes (a load over NVLink) and stores them crosswise (a store over
+// NVLink).  In place, no staging, both link directions busy; each amplitude pair is touched by exactly one thread
+// of one rank.  Work is cut into 64 KiB segments dealt round-robin over the peers, and every rank starts its round at
+// a different peer ((rank + 1 + k) mod world), so every GPU's NVLink ingress is fed by all the others evenly.
+// A SLAB launch covers only the offsets whose pinned bits (positions >= 12 inside the half-chunk offset, so whole
+// segments) have the given values; UN = loads in flight per thread.
+// ---------------------------------------------------------------------------------------------
+struct SwapSlab { int nbits; int bit[3]; unsigned long long value_or; };
+
+template <int UN, int THREADS>
+__global__ void __launch_bounds__(THREADS, (UN == 4 && THREADS == 512) ? 2 : 1)
+k_remap_swap(double2* __restrict__ mine, const __grid_constant__ PeerPtrs peers, int rank, int world, unsigned long long chunk,
+             const __grid_constant__ SwapSlab slab) {
     const unsigned long long half = chunk >> 1;
-    const unsigned long long SEG = half < 4096ull ? half : 4096ull;       // amplitudes per segment (64 KiB)
-    const unsigned long long segs_per_peer = half / SEG;
-    const unsigned long long total = half * (unsigned long long)(world - 1);
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 4 * stride) {
-        double2 a[4], b[4]; unsigned long long mo[4], po[4]; double2* pp[4]; bool ok[4];
+    const int seg_log2 = half < 4096ull ? (63 - __clzll((long long)half)) : 12;    // amplitudes per segment: 2^12 (64 KiB) or the whole half
+    const unsigned long long seg_mask = (1ull << seg_log2) - 1ull;
+    const unsigned long long half_c = half >> slab.nbits;                  // compressed offsets this launch covers
+    const unsigned long long total = half_c * (unsigned long long)(world - 1);
+    const unsigned long long stride = (unsigned long long)gridDim.x * THREADS;
+    const uint32_t wm1 = (uint32_t)(world - 1);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * THREADS + threadIdx.x; i < total; i += UN * stride) {
+        double2 a[UN], b[UN]; double2 *mp[UN], *pp[UN]; bool ok[UN];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UN; ++u) {
             const unsigned long long ii = i + (unsigned long long)u * stride;
             ok[u] = ii < total;
             const unsigned long long q = ok[u] ? ii : 0;
-            const unsigned long long sg = q / SEG, within = q % SEG;
-            const int k = (int)(sg % (unsigned long long)(world - 1));             // which peer, round-robin
-            const unsigned long long o = (sg / (unsigned long long)(world - 1)) * SEG + within;
-            int j = rank + 1 + k; if (j >= world) j -= world;                      // rank-rotated peer order
+            const uint32_t sg = (uint32_t)(q >> seg_log2);                          // < 2^32: a shard has < 2^44 amplitudes
+            const uint32_t sgq = sg / wm1, k = sg - sgq * wm1;                      // which peer, round-robin
+            unsigned long long o = ((unsigned long long)sgq << seg_log2) | (q & seg_mask);
+            for (int s = 0; s < slab.nbits; ++s) {                                  // open the pinned bits (ascending)
+                const unsigned long long lo = o & ((1ull << slab.bit[s]) - 1ull);
+                o = ((o >> slab.bit[s]) << (slab.bit[s] + 1)) | lo;
+            }
+            o |= slab.value_or;
+            int j = rank + 1 + (int)k; if (j >= world) j -= world;                  // rank-rotated peer order
             const unsigned long long off = (rank < j ? 0ull : half) + o;
-            mo[u] = (unsigned long long)j * chunk + off; po[u] = (unsigned long long)rank * chunk + off; pp[u] = peers.p[j];
-            if (ok[u]) { a[u] = mine[mo[u]]; b[u] = pp[u][po[u]]; }
+            mp[u] = mine + ((unsigned long long)j * chunk + off); pp[u] = peers.p[j] + ((unsigned long long)rank * chunk + off);
+            if (ok[u]) { a[u] = *mp[u]; b[u] = *pp[u]; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (ok[u]) { mine[mo[u]] = b[u]; pp[u][po[u]] = a[u]; }
+        for (int u = 0; u < UN; ++u) if (ok[u]) { *mp[u] = b[u]; *pp[u] = a[u]; }
     }
-    (void)segs_per_peer;
 }
 
 struct DistCtx {
-    double2* peer[16] = { nullptr };                    // IPC-mapped shards of the other ranks (null: NCCL path)
-    bool have_peers = false;
+    double2* peer[16] = { nullptr };                    // the other ranks' shards (IPC-mapped or same-process pointers); null: NCCL path
+    unsigned char* win[16] = { nullptr };               // every rank's window, own included
+    bool have_peers = false, ipc_mapped = false;
     ncclComm_t comm = nullptr;
-    double2* stage = nullptr; size_t stage_amps = 0;     // (world - 1) x sub-chunk
-    double* d_small = nullptr;                           // all-reduce scratch
+    double2* stage = nullptr; size_t stage_amps = 0;     // NCCL path: (world - 1) x sub-chunk
+    double* d_small = nullptr;                           // collective scratch (4096 doubles)
     bool swapped = false;                                // layout B: global qubits currently sit on the top local bits
+    cudaStream_t xstream = nullptr;                      // the exchange runs here when it is overlapped with passes
+    uint32_t ep[4] = { 0, 0, 0, 0 };                     // epochs per flag kind; every rank advances them alike (SPMD calls)
+    int mbox_parity = 0;
+    unsigned long long local_key = 0; bool local_world = false;
 };
+
+// ---- same-process worlds (all ranks in one process: the 1-GPU test of the sharded path) ------------------------
+static std::mutex g_local_mu;
+static std::map<unsigned long long, std::vector<qm_state*>> g_local_worlds;
 
 int dist_destroy(DistCtx* d) {
     if (!d) return QM_OK;
-    for (int j = 0; j < 16; ++j) if (d->peer[j]) cudaIpcCloseMemHandle(d->peer[j]);
+    if (d->ipc_mapped) for (int j = 0; j < 16; ++j) if (d->peer[j]) cudaIpcCloseMemHandle(d->peer[j]);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    if (d->xstream) cudaStreamDestroy(d->xstream);
     cudaFree(d->stage); cudaFree(d->d_small);
+    if (d->local_world) {
+        std::lock_guard<std::mutex> lk(g_local_mu);
+        g_local_worlds.erase(d->local_key);
+    }
     delete d;
     return QM_OK;
 }
@@ -118,75 +221,200 @@ extern "C" int32_t qm_dist_unique_id(uint8_t id_out[128]) {
     return QM_OK;
 }
 
-extern "C" int32_t qm_create_dist(int32_t n, uint64_t basis, int32_t device, int32_t rank, int32_t world,
-                                  const uint8_t nccl_id[128], qm_state** out) {
-    if (!nccl_id || !out) return set_err(QM_ERR_ARG, "null argument");
-    if (world < 2) return set_err(QM_ERR_ARG, "world must be >= 2 (use qm_create for one GPU)");
-    QM_TRY(nccl_load());
-    QM_TRY(qm_create_common(n, basis, 1, device, rank, world, out));
-    qm_state* st = *out;
-    if (2 * st->g > st->n) { qm_destroy(st); *out = nullptr; return set_err(QM_ERR_ARG, "register too small for %d ranks", world); }
-    DistCtx* d = new DistCtx();
-    ncclUniqueId id; memcpy(id.internal, nccl_id, 128);
-    int r = g_nccl.CommInitRank(&d->comm, world, id, rank);
-    if (r != 0) { delete d; qm_destroy(st); *out = nullptr; return set_err(QM_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
-    // staging ring: (world - 1) sub-chunks of at most 2^24 amplitudes (256 MiB) each
-    const uint64_t chunk = 1ull << (st->nl - st->g);
-    uint64_t sub = chunk < (1ull << 24) ? chunk : (1ull << 24);
-    d->stage_amps = sub;
-    CU(cudaMalloc((void**)&d->stage, (size_t)(world - 1) * sub * 16));
+static unsigned char* own_window(const qm_state* st) {
+    return reinterpret_cast<unsigned char*>(st->amp) + (size_t)local_amps(st) * 16;
+}
+
+static int dist_common_init(qm_state* st, DistCtx* d) {
     CU(cudaMalloc((void**)&d->d_small, 4096 * sizeof(double)));
-    st->dist = d;
+    CU(cudaMemset(d->d_small, 0, 4096 * sizeof(double)));
+    CU(cudaMemset(own_window(st), 0, kWinBytes));
+    CU(cudaStreamCreateWithFlags(&d->xstream, cudaStreamNonBlocking));
+    CU(cudaDeviceSynchronize());
+    d->win[st->rank] = own_window(st);
     return QM_OK;
 }
 
-int dist_remap(qm_state* st, std::vector<LGate>* gates, std::vector<char>* done) {
+extern "C" int32_t qm_create_dist(int32_t n, uint64_t basis, int32_t device, int32_t rank, int32_t world,
+                                  const uint8_t nccl_id[128], qm_state** out) {
+    if (!nccl_id || !out) return set_err(QM_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (world < 2 || world > 16) return set_err(QM_ERR_ARG, "world must be in [2, 16] (use qm_create for one GPU)");
+    QM_TRY(nccl_load());
+    qm_state* st = nullptr;
+    QM_TRY(qm_create_common(n, basis, 1, device, rank, world, &st));
+    if (2 * st->g > st->n) { qm_destroy(st); return set_err(QM_ERR_ARG, "register too small for %d ranks", world); }
+    DistCtx* d = new DistCtx();
+    st->dist = d;                                       // from here on qm_destroy releases everything
+    ncclUniqueId id; memcpy(id.internal, nccl_id, 128);
+    int r = g_nccl.CommInitRank(&d->comm, world, id, rank);
+    if (r != 0) { d->comm = nullptr; qm_destroy(st); return set_err(QM_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
+    // NCCL path staging ring: (world - 1) sub-chunks of at most 2^24 amplitudes (256 MiB) each, allocated on first use
+    const uint64_t chunk = 1ull << (st->nl - st->g);
+    d->stage_amps = chunk < (1ull << 24) ? chunk : (1ull << 24);
+    int rc = dist_common_init(st, d);
+    if (rc != QM_OK) { qm_destroy(st); return rc; }
+    *out = st;
+    return QM_OK;
+}
+
+// All ranks of a register inside ONE process (one host thread per rank; one device, or several that can reach each
+// other): no NCCL, peers are plain pointers.  `key` names the world; every rank calls qm_create_dist_local with the
+// same key, then — after all of them have returned (the caller's own barrier) — qm_dist_local_connect.
+extern "C" int32_t qm_create_dist_local(int32_t n, uint64_t basis, int32_t device, int32_t rank, int32_t world,
+                                        uint64_t key, qm_state** out) {
+    if (!out) return set_err(QM_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (world < 2 || world > 16) return set_err(QM_ERR_ARG, "world must be in [2, 16]");
+    qm_state* st = nullptr;
+    QM_TRY(qm_create_common(n, basis, 1, device, rank, world, &st));
+    if (!get_wait_value()) { qm_destroy(st); return set_err(QM_ERR_COMM, "cuStreamWaitValue32 is not available: a same-process world needs stream memory operations"); }
+    if (2 * st->g > st->n) { qm_destroy(st); return set_err(QM_ERR_ARG, "register too small for %d ranks", world); }
+    DistCtx* d = new DistCtx();
+    st->dist = d;
+    d->local_world = true; d->local_key = key;
+    int rc = dist_common_init(st, d);
+    if (rc != QM_OK) { qm_destroy(st); return rc; }
+    {
+        std::lock_guard<std::mutex> lk(g_local_mu);
+        std::vector<qm_state*>& v = g_local_worlds[key];
+        if (v.size() < (size_t)world) v.resize(world, nullptr);
+        v[rank] = st;
+    }
+    *out = st;
+    return QM_OK;
+}
+
+extern "C" int32_t qm_dist_local_connect(qm_state* st) {
+    if (!st || !st->dist || !st->dist->local_world) return set_err(QM_ERR_ARG, "not a rank of a same-process world");
     DistCtx* d = st->dist;
-    if (!d) return set_err(QM_ERR_STATE, "not a sharded register");
     CU(cudaSetDevice(st->device));
-    const int g = st->g, nl = st->nl, W = st->world, r = st->rank;
-    const uint64_t chunk = 1ull << (nl - g), sub = d->stage_amps;
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    if (d->have_peers && chunk >= 2) {
-        // fence, one exchange kernel over peer memory, fence
-        NC(g_nccl.AllReduce(d->d_small, d->d_small, 1, kNcclFloat64, kNcclSum, d->comm, st->stream));
-        CU(cudaEventRecord(e0, st->stream));
-        PeerPtrs pp; for (int j = 0; j < 16; ++j) pp.p[j] = d->peer[j];
-        const uint64_t total = (chunk >> 1) * (uint64_t)(W - 1);
-        uint64_t blocks = (total + 512ull * 4 - 1) / (512ull * 4);
-        const uint64_t cap = (uint64_t)st->sms * 4; if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
-        k_remap_swap<<<(unsigned)blocks, 512, 0, st->stream>>>(st->amp, pp, r, W, chunk);
+    std::lock_guard<std::mutex> lk(g_local_mu);
+    const std::vector<qm_state*>& v = g_local_worlds[d->local_key];
+    for (int j = 0; j < st->world; ++j) {
+        if ((size_t)j >= v.size() || !v[j]) return set_err(QM_ERR_STATE, "rank %d of the world has not been created yet", j);
+        if (v[j]->n != st->n || v[j]->world != st->world) return set_err(QM_ERR_ARG, "rank %d has a different shape", j);
+        if (j == st->rank) continue;
+        if (v[j]->device != st->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(v[j]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return set_err(QM_ERR_COMM, "cannot enable peer access to device %d", v[j]->device); }
+            cudaGetLastError();
+        }
+        d->peer[j] = v[j]->amp;
+        d->win[j] = own_window(v[j]);
+    }
+    d->have_peers = true;
+    return QM_OK;
+}
+
+// ---- flag fences and mailbox collectives (peer-memory transport) ----------------------------------------------
+static PeerWins wins_of(const DistCtx* d) { PeerWins pw; for (int j = 0; j < 16; ++j) pw.p[j] = d->win[j]; return pw; }
+
+static int signal_all(qm_state* st, cudaStream_t stream, int kind, int slab, uint32_t epoch) {
+    k_signal<<<1, 32, 0, stream>>>(wins_of(st->dist), st->world, kind * 256 + st->rank * 16 + slab, epoch);
+    CU(cudaGetLastError());
+    st->ctr.launches++;
+    return QM_OK;
+}
+// the stream waits until every rank (this one included) has posted `epoch` for (kind, slab)
+static int wait_all(qm_state* st, cudaStream_t stream, int kind, int slab, uint32_t epoch) {
+    PFN_waitValue32 wv = get_wait_value();
+    if (!wv) return set_err(QM_ERR_COMM, "cuStreamWaitValue32 is not available");
+    unsigned char* w = st->dist->win[st->rank];
+    for (int j = 0; j < st->world; ++j) {
+        CUresult r = wv((CUstream)stream, (CUdeviceptr)(w + 4u * (kind * 256 + j * 16 + slab)), epoch, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r != CUDA_SUCCESS) return set_err(QM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)r);
+    }
+    return QM_OK;
+}
+static int fence_all(qm_state* st, cudaStream_t stream) {
+    const uint32_t e = ++st->dist->ep[FK_FENCE];
+    QM_TRY(signal_all(st, stream, FK_FENCE, 0, e));
+    return wait_all(st, stream, FK_FENCE, 0, e);
+}
+// every rank's `bytes` (<= kMboxBytes, multiple of 16, device memory) land in every rank's mailboxes [parity][rank].
+// Two parities suffice: a rank can only start exchange c + 2 after it has seen every rank's post for c + 1, which every
+// rank issues (in stream order) after its kernel that read the mailboxes of c.
+static int mbox_exchange(qm_state* st, const void* d_src, size_t bytes, int* parity_out) {
+    DistCtx* d = st->dist;
+    if (bytes > kMboxBytes || (bytes & 15)) return set_err(QM_ERR_ARG, "mailbox payload %zu", bytes);
+    const uint32_t e = ++d->ep[FK_MBOX];
+    const int parity = d->mbox_parity; d->mbox_parity ^= 1;
+    k_mbox_put<<<st->world, 256, 0, st->stream>>>(wins_of(d), st->rank, parity, reinterpret_cast<const uint4*>(d_src), (uint32_t)(bytes / 16), e);
+    CU(cudaGetLastError());
+    st->ctr.launches++;
+    QM_TRY(wait_all(st, st->stream, FK_MBOX, 0, e));
+    *parity_out = parity;
+    return QM_OK;
+}
+// in place over d_buf (room for the count rounded up to 16 bytes)
+template <typename T>
+static int win_allreduce(qm_state* st, T* d_buf, size_t count) {
+    const size_t per = kMboxBytes / sizeof(T);
+    for (size_t off = 0; off < count; off += per) {
+        const size_t c = count - off < per ? count - off : per;
+        int parity = 0;
+        QM_TRY(mbox_exchange(st, d_buf + off, (c * sizeof(T) + 15) & ~(size_t)15, &parity));
+        k_mbox_sum<T><<<(unsigned)((c + 255) / 256), 256, 0, st->stream>>>(st->dist->win[st->rank], st->world, parity, (uint32_t)c, d_buf + off);
         CU(cudaGetLastError());
-        CU(cudaEventRecord(e1, st->stream));
-        NC(g_nccl.AllReduce(d->d_small, d->d_small, 1, kNcclFloat64, kNcclSum, d->comm, st->stream));
-        st->ctr.launches += 1;
-    } else {
-    CU(cudaEventRecord(e0, st->stream));
-    for (uint64_t off = 0; off < chunk; off += sub) {
-        NC(g_nccl.GroupStart());
-        int slot = 0;
-        for (int j = 0; j < W; ++j) {
-            if (j == r) continue;
-            NC(g_nccl.Send(st->amp + (uint64_t)j * chunk + off, (size_t)sub * 2, kNcclFloat64, j, d->comm, st->stream));
-            NC(g_nccl.Recv(d->stage + (uint64_t)slot * sub, (size_t)sub * 2, kNcclFloat64, j, d->comm, st->stream));
-            ++slot;
-        }
-        NC(g_nccl.GroupEnd());
-        slot = 0;
-        for (int j = 0; j < W; ++j) {
-            if (j == r) continue;
-            CU(cudaMemcpyAsync(st->amp + (uint64_t)j * chunk + off, d->stage + (uint64_t)slot * sub, (size_t)sub * 16,
-                               cudaMemcpyDeviceToDevice, st->stream));
-            ++slot;
-        }
+        st->ctr.launches++;
     }
-    CU(cudaEventRecord(e1, st->stream));
-    st->ctr.launches += (uint64_t)((chunk + sub - 1) / sub);
+    return QM_OK;
+}
+// d_src: this rank's `count` doubles (readable up to the next multiple of 2); d_out: [world][count]
+static int win_allgather(qm_state* st, const double* d_src, double* d_out, size_t count) {
+    const size_t per = kMboxBytes / sizeof(double);
+    for (size_t off = 0; off < count; off += per) {
+        const size_t c = count - off < per ? count - off : per;
+        int parity = 0;
+        QM_TRY(mbox_exchange(st, d_src + off, (c * 8 + 15) & ~(size_t)15, &parity));
+        k_mbox_gather<<<(unsigned)((c + 255) / 256), 256, 0, st->stream>>>(st->dist->win[st->rank], st->world, parity, (uint32_t)c, count, d_out + off);
+        CU(cudaGetLastError());
+        st->ctr.launches++;
     }
-    st->remap_events.push_back(std::make_pair(e0, e1));
+    return QM_OK;
+}
+
+static int allreduce_dev_f64(qm_state* st, double* d_buf, size_t count) {
+    DistCtx* d = st->dist;
+    if (d->have_peers) return win_allreduce<double>(st, d_buf, count);
+    NC(g_nccl.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, d->comm, st->stream));
+    return QM_OK;
+}
+static int allreduce_dev_u64(qm_state* st, unsigned long long* d_buf, size_t count) {
+    DistCtx* d = st->dist;
+    if (d->have_peers) return win_allreduce<unsigned long long>(st, d_buf, count);
+    NC(g_nccl.AllReduce(d_buf, d_buf, count, kNcclUint64, kNcclSum, d->comm, st->stream));
+    return QM_OK;
+}
+
+// ---- the exchange -------------------------------------------------------------------------------------------------
+static const int kSwapSmem = 120 * 1024;     // an overlapped exchange CTA claims an SM for itself: it can share one
+                                             // neither with a fused-pass CTA (> 210 KB) nor with a second exchange CTA
+
+template <int UN, int THREADS>
+static int launch_swap(qm_state* st, cudaStream_t stream, int ctas, bool exclusive, const SwapSlab& slab) {
+    DistCtx* d = st->dist;
+    PeerPtrs pp; for (int j = 0; j < 16; ++j) pp.p[j] = d->peer[j];
+    const uint64_t chunk = 1ull << (st->nl - st->g);
+    static bool attr[64] = { false };
+    if (st->device < 0 || st->device >= 64 || !attr[st->device]) {
+        CU(cudaFuncSetAttribute(k_remap_swap<UN, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSmem));
+        if (st->device >= 0 && st->device < 64) attr[st->device] = true;
+    }
+    k_remap_swap<UN, THREADS><<<ctas, THREADS, exclusive ? kSwapSmem : 0, stream>>>(st->amp, pp, st->rank, st->world, chunk, slab);
+    CU(cudaGetLastError());
+    st->ctr.launches++;
+    return QM_OK;
+}
+
+// relabel after an exchange: perm, the pending lowered gates, the layout flag, the traffic counters
+void dist_relabel(qm_state* st, std::vector<LGate>* gates, std::vector<char>* done) {
+    DistCtx* d = st->dist;
+    const int g = st->g, nl = st->nl, W = st->world;
+    const uint64_t chunk = 1ull << (nl - g);
     st->ctr.bytes_link += (uint64_t)(W - 1) * chunk * 16;
-    st->ctr.bytes_hbm += 2ull * (uint64_t)(W - 1) * chunk * 16 * 2;      // send read + stage write, stage read + place write
+    st->ctr.bytes_hbm += 2ull * (uint64_t)(W - 1) * chunk * 16 * 2;
     d->swapped = !d->swapped;
     for (int q = 0; q < st->n; ++q) st->perm[q] = dist_swap_bit(st->perm[q], nl, g);
     if (gates)
@@ -196,6 +424,100 @@ int dist_remap(qm_state* st, std::vector<LGate>* gates, std::vector<char>* done)
             x.target = dist_swap_bit(x.target, nl, g);
             if (x.ctrl >= 0) x.ctrl = dist_swap_bit(x.ctrl, nl, g);
         }
+}
+
+// can the exchange run beside the passes?  (peer memory, stream waits, and enough offset bits for whole-segment slabs)
+bool dist_can_overlap(const qm_state* st) {
+    const DistCtx* d = st->dist;
+    return d && d->have_peers && get_wait_value() && st->overlap && (st->nl - st->g - 1) >= 14;
+}
+void dist_next_epochs(qm_state* st, uint32_t* ep_pass, uint32_t* ep_exch) {
+    *ep_pass = ++st->dist->ep[FK_PASS]; *ep_exch = ++st->dist->ep[FK_EXCH];
+}
+// Overlapped exchange of one slab, three calls.  (1) after the slab's last pass before the exchange has been enqueued on
+// the pass stream: post "pass done" to every rank.
+int dist_slab_pass_done(qm_state* st, const PassSlab& slab, uint32_t ep_pass) {
+    return signal_all(st, st->stream, FK_PASS, slab.index, ep_pass);
+}
+// (2) on the exchange stream: wait for every rank's post, exchange the slab (a grid of st->xsm CTAs that each claim an
+// SM), post "exchange done" to every rank.  slab.bit[] are positions in the shard's index; they lie below the half-chunk bit.
+int dist_slab_exchange(qm_state* st, const PassSlab& slab, uint32_t ep_pass, uint32_t ep_exch, bool first, bool last) {
+    DistCtx* d = st->dist;
+    QM_TRY(wait_all(st, d->xstream, FK_PASS, slab.index, ep_pass));
+    if (first) {
+        cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        st->remap_events.push_back(std::make_pair(e0, e1));
+        CU(cudaEventRecord(e0, d->xstream));
+    }
+    SwapSlab ss; ss.nbits = slab.nbits; ss.value_or = slab.value_or;
+    for (int i = 0; i < 3; ++i) ss.bit[i] = i < slab.nbits ? slab.bit[i] : 0;
+    const int ctas = st->xsm > 0 ? st->xsm : 16;
+    // one CTA per claimed SM: 512 threads with 8 (or 1024 with 4) amplitude pairs in flight each
+    if (st->xun == 4) QM_TRY((launch_swap<4, 1024>(st, d->xstream, ctas, true, ss)));
+    else QM_TRY((launch_swap<8, 512>(st, d->xstream, ctas, true, ss)));
+    if (last) CU(cudaEventRecord(st->remap_events.back().second, d->xstream));
+    return signal_all(st, d->xstream, FK_EXCH, slab.index, ep_exch);
+}
+// (3) before the slab's first pass after the exchange is enqueued on the pass stream: wait for every rank's "exchange done"
+int dist_slab_wait_exchanged(qm_state* st, const PassSlab& slab, uint32_t ep_exch) {
+    return wait_all(st, st->stream, FK_EXCH, slab.index, ep_exch);
+}
+
+// the exchange itself, whole shard at once on the pass stream (no relabelling)
+int dist_exchange_now(qm_state* st) {
+    DistCtx* d = st->dist;
+    if (!d) return set_err(QM_ERR_STATE, "not a sharded register");
+    CU(cudaSetDevice(st->device));
+    const int g = st->g, nl = st->nl, W = st->world, r = st->rank;
+    const uint64_t chunk = 1ull << (nl - g);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (d->have_peers && chunk >= 2) {
+        // fence (flags), one exchange kernel over peer memory on the whole grid, fence
+        QM_TRY(fence_all(st, st->stream));
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        st->remap_events.push_back(std::make_pair(e0, e1));      // owned by the state from here on (qm_sync / qm_destroy)
+        CU(cudaEventRecord(e0, st->stream));
+        const uint64_t total = (chunk >> 1) * (uint64_t)(W - 1);
+        uint64_t blocks = (total + 512ull * 4 - 1) / (512ull * 4);
+        const uint64_t cap = (uint64_t)st->sms * 4; if (blocks > cap) blocks = cap; if (blocks < 1) blocks = 1;
+        SwapSlab none; memset(&none, 0, sizeof(none));
+        QM_TRY((launch_swap<4, 512>(st, st->stream, (int)blocks, false, none)));
+        CU(cudaEventRecord(e1, st->stream));
+        QM_TRY(fence_all(st, st->stream));
+    } else {
+        if (!d->comm) return set_err(QM_ERR_COMM, "no transport: peers are not mapped and there is no NCCL communicator");
+        const uint64_t sub = d->stage_amps;
+        if (!d->stage) CU(cudaMalloc((void**)&d->stage, (size_t)(W - 1) * sub * 16));
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        st->remap_events.push_back(std::make_pair(e0, e1));
+        CU(cudaEventRecord(e0, st->stream));
+        for (uint64_t off = 0; off < chunk; off += sub) {
+            NC(g_nccl.GroupStart());
+            int slot = 0;
+            for (int j = 0; j < W; ++j) {
+                if (j == r) continue;
+                NC(g_nccl.Send(st->amp + (uint64_t)j * chunk + off, (size_t)sub * 2, kNcclFloat64, j, d->comm, st->stream));
+                NC(g_nccl.Recv(d->stage + (uint64_t)slot * sub, (size_t)sub * 2, kNcclFloat64, j, d->comm, st->stream));
+                ++slot;
+            }
+            NC(g_nccl.GroupEnd());
+            slot = 0;
+            for (int j = 0; j < W; ++j) {
+                if (j == r) continue;
+                CU(cudaMemcpyAsync(st->amp + (uint64_t)j * chunk + off, d->stage + (uint64_t)slot * sub, (size_t)sub * 16,
+                                   cudaMemcpyDeviceToDevice, st->stream));
+                ++slot;
+            }
+        }
+        CU(cudaEventRecord(e1, st->stream));
+        st->ctr.launches += (uint64_t)((chunk + sub - 1) / sub);
+    }
+    return QM_OK;
+}
+
+int dist_remap(qm_state* st, std::vector<LGate>* gates, std::vector<char>* done) {
+    QM_TRY(dist_exchange_now(st));
+    dist_relabel(st, gates, done);
     return QM_OK;
 }
 
@@ -212,7 +534,7 @@ static int allreduce_host(qm_state* st, double* v, int count) {
     DistCtx* d = st->dist;
     if (count > 4096) return set_err(QM_ERR_ARG, "allreduce too large");
     CU(cudaMemcpyAsync(d->d_small, v, count * sizeof(double), cudaMemcpyHostToDevice, st->stream));
-    NC(g_nccl.AllReduce(d->d_small, d->d_small, (size_t)count, kNcclFloat64, kNcclSum, d->comm, st->stream));
+    QM_TRY(allreduce_dev_f64(st, d->d_small, (size_t)count));
     CU(cudaMemcpyAsync(v, d->d_small, count * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
     CU(cudaStreamSynchronize(st->stream));
     return QM_OK;
@@ -266,7 +588,6 @@ int dist_measure(qm_state* st, int t0, double thr, const double* R, double out[2
 // the kept qubits are first swapped with the low ones (bit-exact exchanges through the ordinary circuit path,
 // remaps included), which turns the request into the case above with the same index order, and swapped back.
 int dist_reduced_density(qm_state* st, int keep_low, int k, double* out) {
-    DistCtx* d = st->dist;
     if (k > st->nl) return set_err(QM_ERR_ARG, "Dimension mismatch: k = %d exceeds the %d local bits of a sharded register", k, st->nl);
     if (!keep_low) {
         if (2 * k > st->n) return set_err(QM_ERR_ARG, "sharded register: keeping the high k qubits needs k <= n/2 (k = %d, n = %d)", k, st->n);
@@ -285,7 +606,7 @@ int dist_reduced_density(qm_state* st, int keep_low, int k, double* out) {
     double2* d_out = nullptr;
     QM_TRY(qm_reduced_local(st, 1, k, 0, &d_out));
     const size_t entries = (size_t)1 << (2 * k);
-    NC(g_nccl.AllReduce(d_out, d_out, entries * 2, kNcclFloat64, kNcclSum, d->comm, st->stream));
+    QM_TRY(allreduce_dev_f64(st, reinterpret_cast<double*>(d_out), entries * 2));
     CU(cudaMemcpyAsync(st->h_scratch, d_out, entries * 16, cudaMemcpyDeviceToHost, st->stream));
     st->ctr.bytes_d2h += entries * 16;
     QM_TRY(qm_sync(st));
@@ -306,14 +627,22 @@ int dist_sample(qm_state* st, uint64_t seed, int nshots, uint64_t* out) {
     QM_TRY(dist_canonicalize(st));
     const uint64_t n1l = local_amps(st) >> 12, n1 = n1l * (uint64_t)st->world;
     const uint64_t n2 = (n1 + 4095) >> 12, n3 = (n2 + 4095) >> 12;
-    QM_TRY(ENSURE_DEV(st, d_scratch, (n1 + n2 + n3) * 8 + (size_t)nshots * 8 + 64));
+    // [level 1, all ranks][levels 2, 3 (+ pad to an even count)][this rank's level 1: the mailbox source][shots]
+    const uint64_t lev = (n1 + n2 + n3 + 1) & ~1ull, minepad = (n1l + 1) & ~1ull;
+    QM_TRY(ENSURE_DEV(st, d_scratch, (lev + minepad) * 8 + (((size_t)nshots + 1) & ~(size_t)1) * 8 + 64));
     QM_TRY(ENSURE_PIN(st, h_scratch, (size_t)nshots * 8));
     double* s1 = st->d_scratch;
-    uint64_t* d_out = reinterpret_cast<uint64_t*>(s1 + n1 + n2 + n3);
-    QM_TRY(qm_sample_leaves(st, 0, s1 + (uint64_t)st->rank * n1l));
-    NC(g_nccl.AllGather(s1 + (uint64_t)st->rank * n1l, s1, (size_t)n1l, kNcclFloat64, d->comm, st->stream));
+    double* mine = s1 + lev;
+    uint64_t* d_out = reinterpret_cast<uint64_t*>(mine + minepad);
+    if (d->have_peers) {
+        QM_TRY(qm_sample_leaves(st, 0, mine));
+        QM_TRY(win_allgather(st, mine, s1, (size_t)n1l));
+    } else {
+        QM_TRY(qm_sample_leaves(st, 0, s1 + (uint64_t)st->rank * n1l));
+        NC(g_nccl.AllGather(s1 + (uint64_t)st->rank * n1l, s1, (size_t)n1l, kNcclFloat64, d->comm, st->stream));
+    }
     QM_TRY(qm_sample_descend(st, 0, s1, n1, (uint64_t)st->rank * n1l, seed, nshots, s1 + n1, d_out));
-    NC(g_nccl.AllReduce(d_out, d_out, (size_t)nshots, kNcclUint64, kNcclSum, d->comm, st->stream));
+    QM_TRY(allreduce_dev_u64(st, reinterpret_cast<unsigned long long*>(d_out), (size_t)nshots));
     CU(cudaMemcpyAsync(st->h_scratch, d_out, (size_t)nshots * 8, cudaMemcpyDeviceToHost, st->stream));
     st->ctr.bytes_d2h += (size_t)nshots * 8;
     QM_TRY(qm_sync(st));
@@ -321,8 +650,8 @@ int dist_sample(qm_state* st, uint64_t seed, int nshots, uint64_t* out) {
     return QM_OK;
 }
 
-// ---- peer-memory mapping (CUDA IPC): every rank exports its shard, the host all-gathers the 64-byte
-// handles, every rank imports the others'.  Optional: without it the remap goes through NCCL.
+// ---- peer-memory mapping (CUDA IPC): every rank exports its allocation (shard + window), the host all-gathers the
+// 64-byte handles, every rank imports the others'.  Optional: without it everything goes through NCCL.
 extern "C" int32_t qm_dist_ipc_export(qm_state* st, uint8_t handle_out[64]) {
     if (!st || !st->dist || !handle_out) return set_err(QM_ERR_ARG, "not a sharded register");
     CU(cudaSetDevice(st->device));
@@ -338,6 +667,7 @@ extern "C" int32_t qm_dist_ipc_import(qm_state* st, const uint8_t* handles /* [w
     if (st->world > 16) return set_err(QM_ERR_ARG, "at most 16 ranks");
     CU(cudaSetDevice(st->device));
     DistCtx* d = st->dist;
+    if (!get_wait_value()) return set_err(QM_ERR_COMM, "cuStreamWaitValue32 is not available — exchanges stay on NCCL");
     for (int j = 0; j < st->world; ++j) {
         if (j == st->rank) continue;
         cudaIpcMemHandle_t h; memcpy(&h, handles + 64 * j, 64);
@@ -345,11 +675,16 @@ extern "C" int32_t qm_dist_ipc_import(qm_state* st, const uint8_t* handles /* [w
         cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            for (int k = 0; k < 16; ++k) if (d->peer[k]) { cudaIpcCloseMemHandle(d->peer[k]); d->peer[k] = nullptr; }
-            d->have_peers = false;
-            return set_err(QM_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s — remaps stay on NCCL", j, cudaGetErrorString(e));
+            for (int k = 0; k < 16; ++k) {
+                if (d->peer[k]) { cudaIpcCloseMemHandle(d->peer[k]); d->peer[k] = nullptr; }
+                if (k != st->rank) d->win[k] = nullptr;
+            }
+            d->have_peers = false; d->ipc_mapped = false;
+            return set_err(QM_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s — exchanges stay on NCCL", j, cudaGetErrorString(e));
         }
         d->peer[j] = reinterpret_cast<double2*>(p);
+        d->win[j] = reinterpret_cast<unsigned char*>(p) + (size_t)local_amps(st) * 16;
+        d->ipc_mapped = true;
     }
     d->have_peers = true;
     return QM_OK;

@@ -126,7 +126,6 @@ static const int kV4ProducerThreads = 128;     // a whole warpgroup, so that set
 //   M = 12: 2 teams x 256 threads, 3 stages of 64 KiB        M = 11: 4 teams x 128 threads, 6 stages of 32 KiB
 int launch_v4_m12(cudaStream_t stream, int sms, const CUtensorMap& tm, const V4Program& prog, const double* d_slots, const V4Launch& lp);
 int launch_v4_m11(cudaStream_t stream, int sms, const CUtensorMap& tm, const V4Program& prog, const double* d_slots, const V4Launch& lp);
-//   split buffers, M = 11: 3 teams x 128 threads, inbound + outbound 32 KiB buffer per team (the default)
-int launch_v4_s11(cudaStream_t stream, int sms, const CUtensorMap& tm, const V4Program& prog, const double* d_slots, const V4Launch& lp);
+
 
 }  // namespace qm

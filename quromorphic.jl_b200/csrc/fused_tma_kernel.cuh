@@ -233,7 +233,7 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
             asm volatile(V4_GROUP_PTX
                          : "+r"(rp)
                          : "r"(ctx), "r"(slot_s), "r"(tile_s), "r"(b0), "r"((uint32_t)g01), "r"((uint32_t)(g01 >> 32)),
-                           "r"((uint32_t)g23), "r"((uint32_t)(g23 >> 32)), "r"(tile_s), "r"(0u), "r"(0u), "r"(0u)
+                           "r"((uint32_t)g23), "r"((uint32_t)(g23 >> 32))
                          : "memory");
             if (tr && gi < 3) trace[kV4TraceStride * i + 2 + gi] = clock64();
             if (gi + 1 < ngroups) bar_sync_named(1 + team, TEAM);
@@ -244,212 +244,6 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
         if (tr) trace[kV4TraceStride * i + 5] = clock64();
         s += TEAMS; if (s >= STAGES) { s -= STAGES; ++k; }
     }
-}
-
-// =====================================================================================================================
-// k_fused_split — the fused pass with SPLIT buffers (the default kernel since round 2).
-//
-// What the phase trace of k_fused_tma showed (tools/tile_timeline.py, 30 qubits, HBM-bound pass of 13 gates): a stage
-// buffer is held ~12,000 cycles by its compute team (load 16 amplitudes per thread, run the gates FROM REGISTERS, store
-// them back) and only then goes through store-drain (2,700 cycles: the TMA store reads the buffer at the rate HBM
-// accepts it) and reload (~4,700 cycles of HBM latency under load) — with three 64 KiB stages and two teams, two
-// thirds of the shared memory sits under tiles that are not being touched while their gates run, only ~0.7 tile per SM
-// is in flight to or from HBM, and every extra gate lengthens exactly that.  Gates never touch shared memory, so:
-//
-//   * every team owns an INBOUND and an OUTBOUND buffer (2^11 amplitudes = 32 KiB each; three teams of 128 threads).
-//   * tile k of a team: wait full -> 16 loads per thread from the inbound buffer -> ARRIVE in_free (the loader lane
-//     refills the buffer with the team's next tile at once: the whole HBM read latency now hides behind this tile's
-//     gates) -> gates on registers -> wait out_free (the previous tile's store has drained: long done) -> 16 stores
-//     per thread into the outbound buffer -> arrive out_full (the storer lane issues the TMA store).
-//     Further register-block groups of the same tile work in place on the outbound buffer.
-//   * two producer lanes in two warps: the LOADER follows in_free in tile order, the STORER follows out_full in tile
-//     order and hands a buffer back when its store has been read (cp.async.bulk.wait_group.read 1: one store may stay
-//     in flight behind it).
-// HBM traffic per pass is unchanged (one read + one write of the state); what changes is that the memory pipeline's
-// depth no longer depends on how many gates a pass carries.
-// =====================================================================================================================
-template <int M, int TEAMS>
-__global__ void __launch_bounds__(TEAMS * (1 << (M - 4)) + kV4ProducerThreads, 1)
-k_fused_split(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4Program P, const double* __restrict__ slots,
-              const V4Launch lp) {
-    constexpr int TEAM = 1 << (M - kV4BlockBits);
-    constexpr int NCOMP = TEAMS * TEAM;
-    constexpr uint32_t TILE_BYTES = 16u << M;
-    static_assert(NCOMP % 128 == 0 && TEAM % 32 == 0 && TEAMS <= 4, "team shape");
-    extern __shared__ unsigned char smem_dyn[];
-    // [TEAMS inbound][TEAMS outbound] | lane_tab, warp_tab | gate records | tile descriptors [TEAMS][2] | barriers
-    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    unsigned char* in_base = smem;
-    unsigned char* out_base = smem + (size_t)TEAMS * TILE_BYTES;
-    unsigned char* tabs = smem + (size_t)2 * TEAMS * TILE_BYTES;
-    unsigned char* recs = tabs + kV4TabBytes;
-    uint64_t* tdesc = reinterpret_cast<uint64_t*>(recs + sizeof(V4Rec) * kV4MaxRecs);          // [TEAMS][2 (tile parity)][2]
-    uint64_t* full = tdesc + 16;            // [TEAMS] tile landed in the inbound buffer
-    uint64_t* in_free = full + 4;           // [TEAMS] every warp of the team has issued its loads
-    uint64_t* out_full = in_free + 4;       // [TEAMS] every warp of the team has stored its results
-    uint64_t* out_free = out_full + 4;      // [TEAMS] the TMA store has read the outbound buffer
-
-    const int tid = threadIdx.x;
-    uint64_t pa;
-    asm("cvta.to.param.u64 %0, %1;" : "=l"(pa) : "l"(&P));
-    {
-        uint32_t* dst = reinterpret_cast<uint32_t*>(tabs);
-        const int nl = P.ngroups * 16, nw = P.ngroups * 4;
-        for (int i = tid; i < nl; i += NCOMP + kV4ProducerThreads) dst[i] = ldp32(pa + offsetof(V4Program, lane_tab) + 4u * i);
-        for (int i = tid; i < nw; i += NCOMP + kV4ProducerThreads) dst[kV4MaxGroups * 16 + i] = ldp32(pa + offsetof(V4Program, warp_tab) + 4u * i);
-    }
-    {
-        uint64_t* dst = reinterpret_cast<uint64_t*>(recs);
-        const int n8 = P.nrecs * 8;
-        for (int i = tid; i < n8; i += NCOMP + kV4ProducerThreads) dst[i] = ldp64(pa + offsetof(V4Program, recs) + 8u * i);
-    }
-    if (tid == 0) {
-        for (int t = 0; t < TEAMS; ++t) {
-            mbar_init(&full[t], 1); mbar_init(&in_free[t], TEAM / 32); mbar_init(&out_full[t], TEAM / 32); mbar_init(&out_free[t], 1);
-        }
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    const int tbits = lp.reg_bits - M - lp.nfixed;
-    const uint64_t first = blockIdx.x, step = gridDim.x;
-    const uint64_t ntiles = lp.ntiles;
-    const uint64_t my_tiles = first < ntiles ? (ntiles - first + step - 1) / step : 0;
-    unsigned long long* const trace = blockIdx.x == 0 ? lp.trace : nullptr;
-
-    if (tid >= NCOMP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        const int pw = (tid - NCOMP) >> 5;
-        if ((tid & 31) != 0 || pw > 1) return;
-        const int n_outer = P.n_outer;
-        const uint32_t ctx_const = P.ctx_const | kV4CtxAlways;
-        const uint64_t opk0 = P.outer_pack[0], opk1 = P.outer_pack[1];
-        auto tile_base = [&](uint64_t tile_id, uint64_t& d0, uint64_t& d1) -> uint64_t {
-            const uint64_t breg = tile_id >> tbits;
-            uint64_t base = (tile_id & ((1ull << tbits) - 1ull)) << lp.L;
-#pragma unroll
-            for (int j = 0; j < kV4Gaps; ++j) {
-                const uint64_t lo = base & ((1ull << lp.gap_start[j]) - 1ull);
-                base = ((base >> lp.gap_start[j]) << (lp.gap_start[j] + lp.gap_len[j])) | lo;
-            }
-            base |= lp.fixed_or;
-            const uint64_t gbase = base | lp.rank_or;
-            uint32_t octx = ctx_const;
-            uint64_t pk = opk0;
-            for (int j = 0; j < n_outer; ++j) {
-                octx |= (uint32_t)((gbase >> (pk & 63ull)) & 1ull) << (kV4CtxOuter + j);
-                pk >>= 6;
-                if (j == 9) pk = opk1;
-            }
-            d0 = slots ? (uint64_t)(slots + (size_t)breg * lp.nslots * 8) : 0ull;
-            d1 = octx;
-            return (breg << lp.reg_bits) + base;
-        };
-        uint64_t d0, d1;
-        if (pw == 0) {
-            // ===================== loader lane =====================
-            for (uint64_t i = 0; i < my_tiles; ++i) {
-                const int t = (int)(i % TEAMS);
-                const uint32_t k = (uint32_t)(i / TEAMS);
-                const uint64_t base = tile_base(first + i * step, d0, d1);
-                if (k >= 1) mbar_wait_sleep(&in_free[t], (k - 1) & 1u);      // the team has taken tile k-1 out of the buffer
-                uint64_t* td = tdesc + 4 * t + 2 * (k & 1u);
-                td[0] = d0; td[1] = d1;
-                mbar_arrive_expect_tx(&full[t], TILE_BYTES);                  // release: the descriptor is visible with the phase
-                TMA_COORDS(base);
-                tma_load_5d(in_base + (size_t)t * TILE_BYTES, &tmap, &full[t], 0, tc1, tc2, tc3, tc4);
-                if (trace) trace[kV4TraceStride * i + 7] = clock64();
-            }
-        } else {
-            // ===================== storer lane =====================
-            for (uint64_t i = 0; i < my_tiles; ++i) {
-                const int t = (int)(i % TEAMS);
-                const uint32_t k = (uint32_t)(i / TEAMS);
-                const uint64_t base = tile_base(first + i * step, d0, d1);
-                mbar_wait_sleep(&out_full[t], k & 1u);
-                if (trace) trace[kV4TraceStride * i + 6] = clock64();
-                { TMA_COORDS(base); tma_store_5d(&tmap, out_base + (size_t)t * TILE_BYTES, 0, tc1, tc2, tc3, tc4); }
-                tma_commit();
-                if (i >= 1) {               // the store before this one has been read: its buffer goes back to its team
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    mbar_arrive(&out_free[(int)((i - 1) % TEAMS)]);
-                }
-            }
-            tma_wait_read0();
-            if (my_tiles >= 1) mbar_arrive(&out_free[(int)((my_tiles - 1) % TEAMS)]);
-            tma_wait_all0();
-        }
-        return;
-    }
-
-    // ================================ compute teams ================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-    const int team = tid / TEAM, ttid = tid % TEAM;
-    const int lane = ttid & 31, warp = ttid >> 5;
-    const int ngroups = P.ngroups;
-    const uint32_t in_s = smem_u32(in_base) + (uint32_t)team * TILE_BYTES, out_s = smem_u32(out_base) + (uint32_t)team * TILE_BYTES;
-    const uint32_t desc_s = smem_u32(tdesc) + 32u * (uint32_t)team;
-    const uint32_t lane_s = smem_u32(tabs) + 2u * lane, warp_s = smem_u32(tabs) + 2u * (kV4MaxGroups * 32 + warp);
-    const uint32_t infree_s = lane == 0 ? smem_u32(&in_free[team]) : 0u;
-    const uint32_t outfree_s = smem_u32(&out_free[team]);
-    uint32_t k = 0;
-#pragma unroll 1
-    for (uint32_t i = team; i < (uint32_t)my_tiles; i += TEAMS, ++k) {
-        const uint32_t slot_s = desc_s + 16u * (k & 1u);
-        const bool tr = trace && ttid == 0;
-        if (tr) trace[kV4TraceStride * i + 0] = clock64();
-        mbar_wait(&full[team], k & 1u);
-        if (tr) trace[kV4TraceStride * i + 1] = clock64();
-        uint32_t octx;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(octx) : "r"(slot_s + 8u));
-#pragma unroll 1
-        for (int gi = 0; gi < ngroups; ++gi) {
-            const uint64_t ga = pa + offsetof(V4Program, groups) + 32u * gi;
-            const uint64_t g01 = ldp64(ga), g23 = ldp64(ga + 8);
-            const uint32_t gw = ldp32(ga + 16);
-            uint32_t v, vw;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(lane_s + 64u * gi));
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(vw) : "r"(warp_s + 16u * gi));
-            v |= vw;
-            const uint32_t b0 = (v ^ ((v >> 3) & 7u)) << 4;
-            const uint32_t ctx = v | octx;
-            uint32_t rp = smem_u32(recs) + (gw - (uint32_t)offsetof(V4Program, recs));
-            // group 0 reads the inbound buffer and hands it back; every group writes the outbound buffer, the first
-            // one after the previous tile's store has drained it
-            const uint32_t ld_s = gi == 0 ? in_s : out_s;
-            const uint32_t fr_s = gi == 0 ? infree_s : 0u;
-            const uint32_t wt_s = (gi == 0 && k >= 1u) ? outfree_s : 0u;
-            asm volatile(V4_GROUP_PTX
-                         : "+r"(rp)
-                         : "r"(ctx), "r"(slot_s), "r"(ld_s), "r"(b0), "r"((uint32_t)g01), "r"((uint32_t)(g01 >> 32)),
-                           "r"((uint32_t)g23), "r"((uint32_t)(g23 >> 32)), "r"(out_s), "r"(fr_s), "r"(wt_s), "r"((k - 1u) & 1u)
-                         : "memory");
-            if (tr && gi < 3) trace[kV4TraceStride * i + 2 + gi] = clock64();
-            if (gi + 1 < ngroups) bar_sync_named(1 + team, TEAM);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&out_full[team]);
-        if (tr) trace[kV4TraceStride * i + 5] = clock64();
-    }
-}
-
-template <int M, int TEAMS>
-static int launch_split_t(cudaStream_t stream, int sms, const CUtensorMap& tm, const V4Program& prog, const double* d_slots,
-                          const V4Launch& lp) {
-    constexpr int threads = TEAMS * (1 << (M - kV4BlockBits)) + kV4ProducerThreads;
-    constexpr size_t smem = (size_t)2 * TEAMS * (16u << M) + kV4TabBytes + sizeof(V4Rec) * kV4MaxRecs + 128 + 16 * 8 + 1024;
-    static bool attr[64] = { false };
-    int dev = 0; CU(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr[dev]) {
-        CU(cudaFuncSetAttribute(k_fused_split<M, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev >= 0 && dev < 64) attr[dev] = true;
-    }
-    const uint64_t cap = (uint64_t)(lp.sm_cap > 0 && lp.sm_cap < sms ? lp.sm_cap : sms);
-    const int grid = (int)(lp.ntiles < cap ? lp.ntiles : cap);
-    k_fused_split<M, TEAMS><<<grid, threads, smem, stream>>>(tm, prog, d_slots, lp);
-    CU(cudaGetLastError());
-    return QM_OK;
 }
 
 template <int M, int TEAMS, int STAGES>

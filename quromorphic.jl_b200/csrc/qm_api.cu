@@ -26,23 +26,25 @@ int set_err(int code, const char* fmt, ...) {
     return code;
 }
 
-int ensure_dev(void** p, size_t* cap, size_t need) {
+// Scratch buffers only grow.  The outgrown buffer is NOT freed here: cudaFree / cudaFreeHost wait for the whole device,
+// and when several ranks of a sharded register share a device (same-process worlds) another rank's stream may be parked
+// on a flag this very call is about to post.  Outgrown buffers are released by qm_destroy.
+int ensure_dev(void** p, size_t* cap, size_t need, std::vector<void*>* retired) {
     if (*cap >= need) return QM_OK;
-    if (*p) CU(cudaFree(*p));
+    if (*p) retired->push_back(*p);
     *p = nullptr; *cap = 0;
     size_t c = need < 4096 ? 4096 : need;
     CU(cudaMalloc(p, c)); *cap = c;
     return QM_OK;
 }
-int ensure_pinned(void** p, size_t* cap, size_t need) {
+int ensure_pinned(void** p, size_t* cap, size_t need, std::vector<void*>* retired) {
     if (*cap >= need) return QM_OK;
-    if (*p) CU(cudaFreeHost(*p));
+    if (*p) retired->push_back(*p);
     *p = nullptr; *cap = 0;
     size_t c = need < 4096 ? 4096 : need;
     CU(cudaMallocHost(p, c)); *cap = c;
     return QM_OK;
 }
-
 
 static const size_t kTraceBytes = 8u << 20;      // QM_OPT_TRACE buffer: 8 stamps x 8 bytes x up to 131072 tiles of CTA 0
 
@@ -72,19 +74,25 @@ int qm_create_common(int n, uint64_t basis, int batch, int device, int rank, int
     if (ndev == 0) return set_err(QM_ERR_NO_DEVICE, "no CUDA device");
     if (device < 0 || device >= ndev) return set_err(QM_ERR_ARG, "device %d of %d", device, ndev);
     CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
     qm_state* st = new qm_state();
     st->n = n; st->g = g; st->nl = n - g; st->rank = rank; st->world = world; st->batch = batch; st->device = device;
-    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
     st->sms = prop.multiProcessorCount;
     st->perm.resize(n); for (int i = 0; i < n; ++i) st->perm[i] = i;
-    size_t bytes = (size_t)total_amps(st) * 16;
+    // a sharded register carries its peer window (flags + mailboxes, dist.cu) right behind the shard, in the same
+    // allocation: one IPC handle maps both into the other ranks
+    const size_t bytes = (size_t)total_amps(st) * 16 + (world > 1 ? dist_window_bytes() : 0);
     cudaError_t e = cudaMalloc((void**)&st->amp, bytes);
-    if (e != cudaSuccess) { delete st; return set_err(QM_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
-    CU(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&st->ev0)); CU(cudaEventCreate(&st->ev1));
-    CU(cudaEventCreateWithFlags(&st->ev_stage, cudaEventDisableTiming));
+    if (e != cudaSuccess) { cudaGetLastError(); delete st; return set_err(QM_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    int rc = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&st->ev0)); CU(cudaEventCreate(&st->ev1));
+        CU(cudaEventCreateWithFlags(&st->ev_stage, cudaEventDisableTiming));
+        return qm_reset(st, basis);
+    }();
+    if (rc != QM_OK) { qm_destroy(st); return rc; }
     *out = st;
-    return qm_reset(st, basis);
+    return QM_OK;
 }
 
 extern "C" int32_t qm_create(int32_t n, uint64_t basis, int32_t batch, int32_t device, qm_state** out) {
@@ -96,9 +104,14 @@ extern "C" int32_t qm_destroy(qm_state* st) {
     cudaSetDevice(st->device);
     if (st->stream) cudaStreamSynchronize(st->stream);
     if (st->dist) { dist_destroy(st->dist); st->dist = nullptr; }
+    for (auto& pr : st->remap_events) { if (pr.first) cudaEventDestroy(pr.first); if (pr.second) cudaEventDestroy(pr.second); }
+    for (cudaEvent_t ev : st->pass_events) cudaEventDestroy(ev);
+    st->remap_events.clear(); st->pass_events.clear();
     cudaFree(st->trace_buf);
     cudaFree(st->amp); cudaFree(st->d_blob); cudaFree(st->d_scratch); cudaFree(st->d_slots);
     cudaFreeHost(st->h_blob); cudaFreeHost(st->h_scratch);
+    for (void* q : st->retired_dev) cudaFree(q);
+    for (void* q : st->retired_pinned) cudaFreeHost(q);
     if (st->ev0) cudaEventDestroy(st->ev0);
     if (st->ev1) cudaEventDestroy(st->ev1);
     if (st->ev_stage) cudaEventDestroy(st->ev_stage);
@@ -141,11 +154,19 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
         if (value && !st->trace_buf) { CU(cudaMalloc((void**)&st->trace_buf, kTraceBytes)); CU(cudaMemset(st->trace_buf, 0, kTraceBytes)); }
         if (!value && st->trace_buf) { CU(cudaStreamSynchronize(st->stream)); cudaFree(st->trace_buf); st->trace_buf = nullptr; }
         break;
-    case QM_OPT_PIPELINE:
-        if (value < 0 || value > 2) return set_err(QM_ERR_ARG, "pipeline must be 0, 1 or 2");
-        st->pipeline = (int)value; break;
+    case QM_OPT_PIPELINE: st->pipeline = value != 0 ? 1 : 0; break;
     case QM_OPT_MAX_COST: st->max_cost = (double)value; break;
     case QM_OPT_TIME_PASSES: st->time_passes = value != 0; break;
+    case QM_OPT_OVERLAP: st->overlap = value != 0; break;
+    case QM_OPT_XSM:
+        if (value < 1 || value > 64) return set_err(QM_ERR_ARG, "exchange SMs must be in [1, 64]");
+        st->xsm = (int)value; break;
+    case QM_OPT_XUN:
+        if (value != 4 && value != 8) return set_err(QM_ERR_ARG, "pairs in flight per exchange thread: 4 or 8");
+        st->xun = (int)value; break;
+    case QM_OPT_SLAB_BITS:
+        if (value < 1 || value > 3) return set_err(QM_ERR_ARG, "slab bits must be in [1, 3]");
+        st->slab_bits = (int)value; break;
     case QM_OPT_SHORT_PCT:
         if (value != 0 && value < 100) return set_err(QM_ERR_ARG, "short-circuit per cent must be 0 (no limit) or >= 100");
         st->short_mult = value == 0 ? 1e9 : (double)value / 100.0; break;
@@ -164,6 +185,9 @@ extern "C" int32_t qm_num_qubits(const qm_state* st, int32_t* n, int32_t* batch)
 // ---------------------------------------------------------------------------------------------
 // gate execution
 // ---------------------------------------------------------------------------------------------
+int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const double* d_slots, int nslots,
+                   const PassSlab* slab, cudaStream_t stream);
+
 static int launch_1q(qm_state* st, int tbit, int cbit, const double* m) {
     // physical bits; control on a sharded bit is a rank predicate, target must be local
     uint64_t cmask = 0;
@@ -285,8 +309,7 @@ int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const
     for (int i = 0; i < kV4Gaps; ++i) { lp.gap_start[i] = i < (int)gaps.size() ? gaps[i].first : 0; lp.gap_len[i] = i < (int)gaps.size() ? gaps[i].second : 0; }
     lp.rank_or = st->g ? ((uint64_t)st->rank << st->nl) : 0; lp.nslots = nslots;
     lp.trace = st->trace_buf;
-    if (P.m == 11 && st->pipeline != 2) QM_TRY(launch_v4_s11(stream, st->sms, tm, prog, d_slots, lp));
-    else if (P.m == 11) QM_TRY(launch_v4_m11(stream, st->sms, tm, prog, d_slots, lp));
+    if (P.m == 11) QM_TRY(launch_v4_m11(stream, st->sms, tm, prog, d_slots, lp));
     else QM_TRY(launch_v4_m12(stream, st->sms, tm, prog, d_slots, lp));
     // the program crosses the host link with the launch: counted as host->device bytes
     st->ctr.bytes_h2d += offsetof(V4Program, recs) + (size_t)prog.nrecs * sizeof(V4Rec);
@@ -318,18 +341,14 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         st->ctr.gates += ngates;
         return QM_OK;
     }
-    // tile size: 2^11 amplitudes on the split-buffer kernel (three teams of 128 threads, an inbound and an outbound
-    // buffer each) unless the caller asks for 2^12 (the in-place ring kernel: two teams of 256 threads, three stages)
-    const int tile_bits = st->tile_bits ? st->tile_bits : (st->nl >= 11 ? 11 : 12);
+    // tile size: 2^12 amplitudes unless the caller asks for 2^11 (four teams of 128 threads, six stages): the two are
+    // within 2 % of each other for single-group passes, 2^12 holds more qubits per pass for deep fusion
+    const int tile_bits = st->tile_bits ? st->tile_bits : 12;
     Planner pl;
     pl.opt.n_local = st->nl; pl.opt.n_global = st->g;
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = st->low_bits; pl.opt.fuse = st->fuse;
     if (st->max_cost > 0) pl.opt.max_cost = st->max_cost < 9.0 ? 9.0 : st->max_cost;
     pl.opt.short_mult = st->short_mult;
-    std::vector<PlanPass> passes;          // of the current segment (between remaps)
-    std::vector<unsigned char> blob;
-    std::vector<size_t> offs;
-    std::vector<V4Program> v4progs;
     bool first_event = true;
     // lower once under the current logical->physical map; a remap later relabels what is left
     int rc = lower_gates(gates, ngates, st->n, st->perm.data(), st->fuse, pl.gates, smap);
@@ -346,109 +365,193 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     }
     if (tma) {
         v4_planner_options(pl.opt, st->max_cost);
-        if (smap) pl.opt.max_subs = (kV4MaxRecs - kV4MaxGroups) / 2;      // every per-state gate takes two records
+        // every per-state gate takes two records (SLOT + gate); two records of slack for the encoder's END records
+        if (smap) pl.opt.max_subs = (kV4MaxRecs - kV4MaxGroups) / 2 - 2;
     }
     pl.done.assign(pl.gates.size(), 0);
-    // plan cache (unsharded, fused, TMA kernel): same structure as a recent circuit -> reuse its passes with this
-    // circuit's matrices
-    const bool cacheable = tma && st->g == 0 && st->fuse && pl.gates.size() <= 4096;
-    std::vector<int64_t> key;
+    // Plan cache (unsharded, fused, TMA kernel): same STRUCTURE as a recent circuit -> reuse its passes with this
+    // circuit's matrices.  The key is everything the planner reads — the options and, per lowered gate, target, control,
+    // diagonal / per-state-slot flag and cost class — folded into two independent 64-bit hashes (a deep circuit has
+    // thousands of gates; the gate count is compared too).
+    const bool cacheable = tma && st->g == 0 && st->fuse;
+    uint64_t key[3] = { 0, 0, 0 };
     qm_state::CachedPlan* hit = nullptr;
     std::vector<std::pair<PlanPass, std::vector<int>>> fresh;
     if (cacheable) {
-        key.reserve(pl.gates.size() + 8);
-        key.push_back(st->nl); key.push_back(tile_bits); key.push_back(st->low_bits); key.push_back((int64_t)(pl.opt.max_cost * 16));
-        key.push_back((int64_t)(pl.opt.short_mult > 1e8 ? -1 : pl.opt.short_mult * 100)); key.push_back(pl.opt.max_subs);
+        uint64_t h1 = 0xcbf29ce484222325ull, h2 = 0x9e3779b97f4a7c15ull;
+        auto mix = [&](uint64_t v) {
+            h1 = (h1 ^ v) * 0x100000001b3ull;
+            h2 ^= v + 0x9e3779b97f4a7c15ull + (h2 << 6) + (h2 >> 2); h2 *= 0xff51afd7ed558ccdull; h2 ^= h2 >> 33;
+        };
+        mix((uint64_t)st->nl); mix((uint64_t)tile_bits); mix((uint64_t)st->low_bits); mix((uint64_t)(pl.opt.max_cost * 16));
+        mix((uint64_t)(pl.opt.short_mult > 1e8 ? -1 : pl.opt.short_mult * 100)); mix((uint64_t)pl.opt.max_subs);
         for (const LGate& x : pl.gates)
-            key.push_back((int64_t)x.target | ((int64_t)(x.ctrl + 1) << 8) | ((int64_t)x.diag << 16) | ((int64_t)(x.slot >= 0) << 17) |
-                          ((int64_t)(gate_cost(x) * 16.0) << 20));
-        for (auto& c : st->plan_cache) if (c.key == key) { hit = &c; break; }
+            mix((uint64_t)x.target | ((uint64_t)(x.ctrl + 1) << 8) | ((uint64_t)x.diag << 16) | ((uint64_t)(x.slot >= 0) << 17) |
+                ((uint64_t)(gate_cost(x) * 16.0) << 20));
+        key[0] = h1; key[1] = h2; key[2] = pl.gates.size();
+        for (auto& c : st->plan_cache) if (c.key[0] == key[0] && c.key[1] == key[1] && c.key[2] == key[2]) { hit = &c; break; }
     }
     size_t replay_i = 0;
-    while (true) {
-        passes.clear(); blob.clear(); offs.clear(); v4progs.clear();
-        PlanPass P;
-        std::vector<int> v4_of;                 // pass -> index into v4progs, or -1 (general kernel, program in the blob)
-        auto next = [&](PlanPass& out) -> bool {
-            if (!hit) {
-                if (!pl.next_pass(out)) return false;
-                if (tma) choose_tile_layout(out);
-                if (cacheable) fresh.emplace_back(out, pl.last_taken);
-                return true;
-            }
-            if (replay_i >= hit->passes.size()) return false;
-            out = hit->passes[replay_i].first;
-            const std::vector<int>& idx = hit->passes[replay_i].second;
-            size_t j = 0;
-            for (PlanGroup& G : out.groups) for (LGate& x : G.subs) x = pl.gates[idx[j++]];
-            for (int i : idx) pl.done[i] = 1;
-            ++replay_i;
+    // the next pass: planned now, or replayed from the cache with this circuit's matrices
+    auto plan_one = [&](PlanPass& out) -> bool {
+        if (!hit) {
+            if (!pl.next_pass(out)) return false;
+            if (tma) choose_tile_layout(out);
+            if (cacheable) fresh.emplace_back(out, pl.last_taken);
             return true;
-        };
-        while (next(P)) {
-            offs.push_back(blob.size());
-            bool v3 = false;
-            if (tma && v4_eligible(st, P)) {
-                v4progs.emplace_back();
-                if (encode_v4(P, v4progs.back())) v3 = true; else v4progs.pop_back();
+        }
+        if (replay_i >= hit->passes.size()) return false;
+        out = hit->passes[replay_i].first;
+        const std::vector<int>& idx = hit->passes[replay_i].second;
+        size_t j = 0;
+        for (PlanGroup& G : out.groups) for (LGate& x : G.subs) x = pl.gates[idx[j++]];
+        for (int i : idx) pl.done[i] = 1;
+        ++replay_i;
+        return true;
+    };
+    // A planned pass ready to launch: the TMA kernel's program (a launch parameter), the general kernel's blob, or —
+    // when the encoder refuses a pass the planner built for the TMA kernel — its gates one by one (kind 2)
+    struct Item { PlanPass P; int kind = 0; V4Program prog; std::vector<unsigned char> blob; };
+    auto prepare = [&](Item& it) -> int {
+        it.kind = 1; it.blob.clear();
+        if (tma) {
+            if (v4_eligible(st, it.P) && encode_v4(it.P, it.prog)) { it.kind = 0; return QM_OK; }
+            // The planner is supposed to respect the kernel's limits; if a pass slips through, it is still applied
+            // (one unfused launch per gate) rather than dropped with the queue already swapped out.
+            for (const PlanGroup& G : it.P.groups)
+                for (const LGate& x : G.subs)
+                    if (x.slot >= 0 || x.target >= st->nl || (x.ctrl >= st->nl && x.diag))
+                        return set_err(QM_ERR_STATE, "planner produced a pass the TMA kernel cannot run (internal error)");
+            it.kind = 2;
+            return QM_OK;
+        }
+        encode_pass(it.P, it.blob);
+        return QM_OK;
+    };
+    auto launch_full = [&](Item& it) -> int {
+        if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
+        cudaEvent_t ea = nullptr, eb = nullptr;
+        if (st->time_passes) { CU(cudaEventCreate(&ea)); CU(cudaEventCreate(&eb)); CU(cudaEventRecord(ea, st->stream)); }
+        if (it.kind == 0) QM_TRY(launch_pass_v4(st, it.prog, it.P, d_slots_lift, nslots, nullptr, st->stream));
+        else if (it.kind == 2) {
+            for (const PlanGroup& G : it.P.groups) for (const LGate& x : G.subs) QM_TRY(launch_1q(st, x.target, x.ctrl, x.m));
+            st->ctr.passes++;
+        } else {
+            QM_TRY(ENSURE_DEV(st, d_blob, it.blob.size()));
+            CU(cudaEventSynchronize(st->ev_stage));      // pinned staging buffer free again?
+            QM_TRY(ENSURE_PIN(st, h_blob, it.blob.size()));
+            memcpy(st->h_blob, it.blob.data(), it.blob.size());
+            CU(cudaMemcpyAsync(st->d_blob, st->h_blob, it.blob.size(), cudaMemcpyHostToDevice, st->stream));
+            st->ctr.bytes_h2d += it.blob.size();
+            CU(cudaEventRecord(st->ev_stage, st->stream));
+            QM_TRY(launch_pass(st, st->d_blob, it.P, d_slots, nslots));
+        }
+        if (st->time_passes) {
+            CU(cudaEventRecord(eb, st->stream));
+            st->pass_events.push_back(ea); st->pass_events.push_back(eb);
+            st->pass_desc.push_back((float)it.P.groups.size());
+            st->pass_desc.push_back((float)it.P.ngates);
+            st->pass_desc.push_back((float)it.P.cost);
+            // records by kind: full-cost FP64 (uncontrolled or context-controlled), half-cost (control in the
+            // register block), xor exchanges, thread-constant phases
+            float kinds[4] = { 0, 0, 0, 0 };
+            if (it.kind == 0) {
+                const V4Program& pr = it.prog;
+                for (int r = 0; r < pr.nrecs; ++r) {
+                    uint32_t op = pr.recs[r].op;
+                    if (op >= (uint32_t)V4_NUM_GATE_OPS) { if (op >= (uint32_t)V4_OP_SLOT) continue; op -= V4_NUM_GATE_OPS; }
+                    int fam, var, B, CB;
+                    if (!v4_decode_op(op, fam, var, B, CB)) continue;
+                    if (fam == 3) kinds[2] += 1; else if (fam == 4) kinds[3] += 1; else if (CB >= 0) kinds[1] += 1; else kinds[0] += 1;
+                }
             }
-            if (v3) v4_of.push_back((int)v4progs.size() - 1);
-            else if (tma) return set_err(QM_ERR_STATE, "planner produced a pass the TMA kernel cannot run (internal error)");
-            else { encode_pass(P, blob); v4_of.push_back(-1); }
-            while (blob.size() % 16) blob.push_back(0);
-            passes.push_back(P);
+            for (int q = 0; q < 4; ++q) st->pass_desc.push_back(kinds[q]);
+        }
+        return QM_OK;
+    };
+    // Sharded registers: index bits that pin a slab — below the half-chunk bit of the exchange (so that the kernel's
+    // lower-rank / higher-rank halves and the exchanged bits stay whole), at or above bit 12 (whole 64 KiB segments),
+    // and outside the tiles of the pass before and the pass after the exchange.  Highest first: long contiguous runs.
+    auto tile_has = [](const PlanPass& P, int b) { return b < P.L || std::find(P.hb.begin(), P.hb.end(), b) != P.hb.end(); };
+    auto choose_slab_bits = [&](const PlanPass& A, const PlanPass& B, std::vector<int>& bits) -> bool {
+        bits.clear();
+        const int want = st->slab_bits < 1 ? 1 : (st->slab_bits > 3 ? 3 : st->slab_bits);
+        for (int b = st->nl - st->g - 2; b >= 12 && (int)bits.size() < want; --b)
+            if (!tile_has(A, b) && !tile_has(B, b)) bits.push_back(b);
+        std::sort(bits.begin(), bits.end());
+        return !bits.empty();
+    };
+
+    // Passes are launched as they are planned, ONE pass behind the planner: while the GPU runs pass i the host plans
+    // pass i + 1 (a 30-qubit depth-200 circuit takes ~70 ms to plan against ~3.6 s of kernels — but all of it used to
+    // sit in front of the first launch).  The look-ahead also tells a sharded register which pass is the last before
+    // an exchange: that pass and the first one after it are cut into slabs and run beside the exchange of the
+    // neighbouring slabs (dist.cu).
+    Item held, nxt;
+    bool have_held = false, seg_had_pass = false;
+    for (int guard = 0; guard < 8 * ngates + 64; ++guard) {
+        PlanPass P;
+        if (plan_one(P)) {
+            nxt.P = P;
+            QM_TRY(prepare(nxt));
+            if (have_held) QM_TRY(launch_full(held));
+            std::swap(held, nxt); have_held = true; seg_had_pass = true;
+            continue;
         }
         bool leftover = false;
         for (size_t i = pl.first; i < pl.gates.size(); ++i) if (!pl.done[i]) { leftover = true; break; }
-        if (leftover && st->g == 0) return set_err(QM_ERR_STATE, "planner could not place a gate (internal error)");
-        // upload (general-kernel programs only; the TMA kernel takes its program as a launch parameter) + launch
-        if (!passes.empty()) {
-            if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
-            if (!blob.empty()) {
-                QM_TRY(ENSURE_DEV(st, d_blob, blob.size()));
-                CU(cudaEventSynchronize(st->ev_stage));      // pinned staging buffer free again?
-                QM_TRY(ENSURE_PIN(st, h_blob, blob.size()));
-                memcpy(st->h_blob, blob.data(), blob.size());
-                CU(cudaMemcpyAsync(st->d_blob, st->h_blob, blob.size(), cudaMemcpyHostToDevice, st->stream));
-                st->ctr.bytes_h2d += blob.size();
-                CU(cudaEventRecord(st->ev_stage, st->stream));
-            }
-            for (size_t i = 0; i < passes.size(); ++i) {
-                cudaEvent_t ea = nullptr, eb = nullptr;
-                if (st->time_passes) { CU(cudaEventCreate(&ea)); CU(cudaEventCreate(&eb)); CU(cudaEventRecord(ea, st->stream)); }
-                if (v4_of[i] >= 0) QM_TRY(launch_pass_v4(st, v4progs[v4_of[i]], passes[i], d_slots_lift, nslots, nullptr, st->stream));
-                else QM_TRY(launch_pass(st, st->d_blob + offs[i], passes[i], d_slots, nslots));
-                if (st->time_passes) {
-                    CU(cudaEventRecord(eb, st->stream));
-                    st->pass_events.push_back(ea); st->pass_events.push_back(eb);
-                    st->pass_desc.push_back((float)passes[i].groups.size());
-                    st->pass_desc.push_back((float)passes[i].ngates);
-                    st->pass_desc.push_back((float)passes[i].cost);
-                    // records by kind: full-cost FP64 (uncontrolled or context-controlled), half-cost (control in the
-                    // register block), xor exchanges, thread-constant phases
-                    float kinds[4] = { 0, 0, 0, 0 };
-                    if (v4_of[i] >= 0) {
-                        const V4Program& pr = v4progs[v4_of[i]];
-                        for (int r = 0; r < pr.nrecs; ++r) {
-                            uint32_t op = pr.recs[r].op;
-                            if (op >= (uint32_t)V4_NUM_GATE_OPS) { if (op >= (uint32_t)V4_OP_SLOT) continue; op -= V4_NUM_GATE_OPS; }
-                            int fam, var, B, CB;
-                            if (!v4_decode_op(op, fam, var, B, CB)) continue;
-                            if (fam == 3) kinds[2] += 1; else if (fam == 4) kinds[3] += 1; else if (CB >= 0) kinds[1] += 1; else kinds[0] += 1;
-                        }
-                    }
-                    for (int q = 0; q < 4; ++q) st->pass_desc.push_back(kinds[q]);
-                }
-            }
-        }
-        if (!leftover) break;
+        if (!leftover) { if (have_held) QM_TRY(launch_full(held)); have_held = false; break; }
+        if (st->g == 0) return set_err(QM_ERR_STATE, "planner could not place a gate (internal error)");
         // sharded register: what is left needs a non-diagonal target on a global qubit.  Exchange the
         // global qubits with the top local ones (all-to-all over NVLink) and relabel the pending gates.
-        if (passes.empty() && !pl.pending_global_target()) return set_err(QM_ERR_STATE, "planner stalled (internal error)");
-        QM_TRY(dist_remap(st, &pl.gates, &pl.done));
+        if (!seg_had_pass && !pl.pending_global_target()) return set_err(QM_ERR_STATE, "planner stalled (internal error)");
+        seg_had_pass = false;
+        const bool ov = have_held && held.kind == 0 && tma && dist_can_overlap(st);
+        if (!ov) {
+            if (have_held) QM_TRY(launch_full(held));
+            have_held = false;
+            QM_TRY(dist_remap(st, &pl.gates, &pl.done));
+            continue;
+        }
+        // overlapped exchange: relabel first (host only), plan the first pass of the new layout, pick the slab bits
+        dist_relabel(st, &pl.gates, &pl.done);
+        PlanPass P2;
+        const bool got2 = plan_one(P2);
+        if (got2) { nxt.P = P2; QM_TRY(prepare(nxt)); seg_had_pass = true; }
+        std::vector<int> sb;
+        if (!got2 || nxt.kind != 0 || !choose_slab_bits(held.P, nxt.P, sb)) {
+            QM_TRY(launch_full(held));
+            have_held = false;
+            QM_TRY(dist_exchange_now(st));
+            if (got2) { std::swap(held, nxt); have_held = true; }
+            continue;
+        }
+        if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
+        uint32_t ep_pass = 0, ep_exch = 0;
+        dist_next_epochs(st, &ep_pass, &ep_exch);
+        const int ns = 1 << sb.size();
+        std::vector<PassSlab> slabs(ns);
+        for (int h = 0; h < ns; ++h) {
+            PassSlab& S = slabs[h];
+            S.nbits = (int)sb.size(); S.index = h; S.value_or = 0;
+            S.sm_cap = st->sms - st->xsm > 8 ? st->sms - st->xsm : st->sms;
+            for (size_t i = 0; i < sb.size(); ++i) { S.bit[i] = sb[i]; if ((h >> i) & 1) S.value_or |= 1ull << sb[i]; }
+        }
+        for (int h = 0; h < ns; ++h) {
+            QM_TRY(launch_pass_v4(st, held.prog, held.P, d_slots_lift, nslots, &slabs[h], st->stream));
+            QM_TRY(dist_slab_pass_done(st, slabs[h], ep_pass));
+        }
+        for (int h = 0; h < ns; ++h) QM_TRY(dist_slab_exchange(st, slabs[h], ep_pass, ep_exch, h == 0, h == ns - 1));
+        for (int h = 0; h < ns; ++h) {
+            QM_TRY(dist_slab_wait_exchanged(st, slabs[h], ep_exch));
+            QM_TRY(launch_pass_v4(st, nxt.prog, nxt.P, d_slots_lift, nslots, &slabs[h], st->stream));
+        }
+        st->ctr.overlapped_remaps++;
+        have_held = false;
     }
+    if (have_held) return set_err(QM_ERR_STATE, "planner did not terminate (internal error)");
     if (cacheable && !hit) {
-        qm_state::CachedPlan c; c.key.swap(key); c.passes.swap(fresh);
+        qm_state::CachedPlan c; c.key[0] = key[0]; c.key[1] = key[1]; c.key[2] = key[2]; c.passes.swap(fresh);
         st->plan_cache.insert(st->plan_cache.begin(), std::move(c));
         if (st->plan_cache.size() > 8) st->plan_cache.pop_back();
     }
@@ -626,8 +729,8 @@ extern "C" int32_t qm_sync(qm_state* st) {
         st->ctr.ms_device = ms; st->ev_pending = false;
     }
     for (auto& pr : st->remap_events) {
-        float ms = 0.f; CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
-        st->ctr.ms_remap += ms;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) st->ctr.ms_remap += ms; else cudaGetLastError();
         cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
     }
     st->remap_events.clear();

@@ -34,9 +34,10 @@ struct qm_state {
     bool ev_pending = false;
     // options
     bool eager = false, fuse = true;
-    int pipeline = 1;           // QM_OPT_PIPELINE: 0 general kernel, 1 TMA kernels (split buffers at 2^11 tiles), 2 in-place ring kernel at every tile size
+    int pipeline = 1;           // QM_OPT_PIPELINE: 0 general kernel, 1 persistent TMA kernel
     bool overlap = true;        // sharded: run the exchange beside the passes when the plan allows (QM_OPT_OVERLAP)
     int xsm = 16, xun = 8;      // sharded, overlapped exchange: SMs the exchange kernel claims, loads in flight per thread
+    int slab_bits = 2;          // ... and log2 of the number of slabs
     bool time_passes = false;   // QM_OPT_TIME_PASSES: CUDA events around every fused pass (diagnostics, tools/pass_model.py)
     std::vector<cudaEvent_t> pass_events;      // 2 per timed pass, resolved by qm_pass_times
     std::vector<float> pass_desc;              // per timed pass: groups, records, planner cost
@@ -47,7 +48,7 @@ struct qm_state {
     // the planner looks at; not the matrix values): a reservoir loop applies the same layer with new angles every
     // step, and planning a 50-gate step costs ~1 ms on the host against ~0.1 ms of kernels at 20 qubits
     struct CachedPlan {
-        std::vector<int64_t> key;
+        uint64_t key[3] = { 0, 0, 0 };    // two independent hashes of everything the planner reads + the gate count
         std::vector<std::pair<qm::PlanPass, std::vector<int>>> passes;     // pass (stale matrices) + gate indices in group order
     };
     std::vector<CachedPlan> plan_cache;       // most recent first, <= 8 entries
@@ -61,6 +62,7 @@ struct qm_state {
     double* d_scratch = nullptr; size_t d_scratch_cap = 0;   // partial sums
     double* h_scratch = nullptr; size_t h_scratch_cap = 0;   // pinned
     double* d_slots = nullptr; size_t d_slots_cap = 0;
+    std::vector<void*> retired_dev, retired_pinned;          // outgrown scratch buffers, released by qm_destroy (ensure_dev)
     qm_counters_t ctr{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> remap_events;   // resolved into ctr.ms_remap at the next sync
     DistCtx* dist = nullptr;
@@ -76,10 +78,10 @@ struct PassSlab {
     int sm_cap = 0;         // CTAs of the persistent grid (0 = all SMs)
 };
 
-int ensure_dev(void** p, size_t* cap, size_t need);
-int ensure_pinned(void** p, size_t* cap, size_t need);
-#define ENSURE_DEV(st, field, need) ensure_dev((void**)&(st)->field, &(st)->field##_cap, (need))
-#define ENSURE_PIN(st, field, need) ensure_pinned((void**)&(st)->field, &(st)->field##_cap, (need))
+int ensure_dev(void** p, size_t* cap, size_t need, std::vector<void*>* retired);
+int ensure_pinned(void** p, size_t* cap, size_t need, std::vector<void*>* retired);
+#define ENSURE_DEV(st, field, need) ensure_dev((void**)&(st)->field, &(st)->field##_cap, (need), &(st)->retired_dev)
+#define ENSURE_PIN(st, field, need) ensure_pinned((void**)&(st)->field, &(st)->field##_cap, (need), &(st)->retired_pinned)
 
 static inline uint64_t local_amps(const qm_state* st) { return 1ull << st->nl; }
 static inline uint64_t total_amps(const qm_state* st) { return (uint64_t)st->batch << st->nl; }

@@ -100,6 +100,20 @@ class B200State:
         st.world, st.rank = world, rank
         return st
 
+    @classmethod
+    def create_dist_local(cls, n, rank, world, key, m=0, device=0, mode="reference", threshold=1e-10):
+        """this rank's shard when ALL ranks live in this process (one host thread per rank; one device or several):
+        every rank calls this with the same `key`, then — after all have returned — .connect_local()."""
+        h = L._vp()
+        L.check(L.lib().qm_create_dist_local(int(n), int(m), int(device), int(rank), int(world), int(key), C.byref(h)))
+        st = cls(n, m, 1, device, mode, threshold, _handle=h)
+        st.world, st.rank = world, rank
+        return st
+
+    def connect_local(self):
+        L.check(L.lib().qm_dist_local_connect(self._h))
+        self.p2p = True
+
     @staticmethod
     def unique_id():
         buf = (C.c_uint8 * 128)()

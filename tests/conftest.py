@@ -9,6 +9,11 @@ if ROOT not in sys.path:
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+# several ranks of a sharded register may live in this process (tests of the sharded path on one GPU): give every
+# stream its own hardware queue so that one rank's stream wait can never sit in front of another rank's kernels
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

@@ -294,6 +294,30 @@ def test_sharded_two_gpus(pkg, n):
     assert all("GPU_DIST_OK" in o for o in outs), "\n".join(outs)
 
 
+@pytest.mark.timeout(300, method="thread")
+@pytest.mark.parametrize("n,world,overlap", [(14, 2, 1), (23, 2, 1), (23, 2, 0), (21, 4, 1), (16, 4, 1)])
+def test_sharded_same_process_world(pkg, n, world, overlap):
+    """The sharded path on ONE GPU: every rank is a host thread of this process with its own shard allocation, streams
+    and peer window on device 0 (qm_create_dist_local).  The rank kernels are the product's own — fused passes with rank
+    predicates, the in-place exchange kernel over "peer" pointers, the flag fences (stream waits: no kernel ever waits
+    for another rank's kernel) and the mailbox collectives.  At 23 / 21 qubits the exchange runs slab by slab beside the
+    passes (QM_OPT_OVERLAP), which is asserted.  Everything is compared with the oracle: amplitudes, <Z> with and without
+    the threshold, X/Y/Z marginals incl. global qubits, both reduced densities, the sampler bit for bit, and a reset
+    after an odd number of layout changes."""
+    import gpu_dist_worker as W
+    R = W.reference(pkg, n)
+    L = pkg._lib
+    res = pkg.dist.run_local_world(n, world, lambda r, st: W.check_sharded(pkg, st, r, world, R), m=R["m"],
+                                   options={L.OPT_OVERLAP: overlap}, timeout=240.0)
+    for r, out in enumerate(res):
+        assert out["ok"], (r, out)
+    g = world.bit_length() - 1
+    if overlap and n >= 23:
+        assert all(out["overlapped_remaps"] > 0 for out in res), res
+    if not overlap:
+        assert all(out["overlapped_remaps"] == 0 for out in res), res
+
+
 def test_c2_batched_full_size_4096_registers_of_16_qubits(pkg):
     """config C2 at BASELINE.json's size: 4096 independent 16-qubit registers (4 GiB) evolved in lockstep with
     per-state encodings.  A sample of registers is checked against the per-state oracle, all of them through

@@ -29,13 +29,8 @@ A record is 64 bytes:  u32 op, tm, cm, aux;  f64 c0, c3, c1, c4, c2, c5.
   cm   controlled entry: context bits that must all be set          tm   THR: context bit selecting the coefficient set
   aux  SLOT: per-state coefficient slot
 Operands:  %0 shared address of the current record ("+r")   %1 context word   %2 shared address of the per-state coefficient base
-           %3 shared address of the tile buffer the amplitudes are LOADED from      %4 the thread's swizzled byte offset in the tile
+           %3 shared address of the tile buffer      %4 the thread's swizzled byte offset in the tile
            %5..%8 swizzled byte offsets of the four block bits
-           %9 shared address of the tile buffer the amplitudes are STORED to (the split-buffer kernel loads a tile from its
-              inbound buffer and stores it to its outbound buffer; the in-place kernel passes %3 again)
-           %10 mbarrier to arrive on once the sixteen loads have been issued ("inbound buffer may be refilled"), 0 = none
-               (non-zero in one lane per warp only)
-           %11 mbarrier to wait on before the sixteen stores ("outbound buffer has been drained"), 0 = none;  %12 its parity
 Opcodes (must match encode_v4 in qm_api.cu), NBC = 16 legal (B, CB) pairs:
    ROT   sign variant 0..3 x NBC      ROTX  sign variant 0, 3 x NBC      PHASE (sg set 0, sg set 1) in 00 03 30 33 x NBC
    PERMX x NBC       THR (lift sg 0, lift sg 3, complex multiply) x 5 (CB = -1, 0..3);   + V4_NUM_GATE_OPS: controlled entry
@@ -183,9 +178,6 @@ def addresses(tag):
     o = []
     b2, b3 = ("%7", "%8") if tag == "load" else ("e2", "e3")
     if tag == "store":
-        # split-buffer kernel: the outbound buffer must have been read by the previous tile's TMA store
-        o += ["setp.eq.u32 pact, %11, 0;", "@pact bra.uni V4NOWAIT;", "V4WAIT:",
-              "mbarrier.try_wait.parity.shared::cta.b64 phi, [%11], %12;", "@!phi bra V4WAIT;", "V4NOWAIT:"]
         o += ["ld.shared.u32 e0, [%0+4];", "ld.shared.v2.u32 {e1, e2}, [%0+8];", "ld.shared.v2.u32 {e3, t}, [%0+16];",
               "xor.b32 o0, %4, t;", "xor.b32 o1, o0, e0;", "xor.b32 o2, o0, e1;", "xor.b32 o3, o1, e1;"]
     for k in range(NA):
@@ -196,7 +188,7 @@ def addresses(tag):
         if k & 8:
             o.append("xor.b32 ad, %s, %s;" % (src, b3))
             src = "ad"
-        o.append("add.u32 ad, %s, %s;" % (src, "%3" if tag == "load" else "%9"))
+        o.append("add.u32 ad, %s, %%3;" % src)
         if tag == "load":
             o.append("ld.shared.v2.f64 {x%d, y%d}, [ad];" % (k, k))
         else:
@@ -230,9 +222,6 @@ def main():
              ".reg .pred pact, phi;", ".reg .b64 sa, sb;",
              "V4T: .branchtargets " + ", ".join(targets) + ";"]
     lines += addresses("setup") + addresses("load")
-    # split-buffer kernel: the loads are in flight, the inbound buffer belongs to the producer again (release semantics of
-    # the arrive order the loads before it)
-    lines += ["setp.ne.u32 pact, %10, 0;", "@pact mbarrier.arrive.shared::cta.b64 _, [%10];"]
     lines += ["ld.shared.v2.u32 {hop, htm}, [%0];"] + LOAD_PAIR
     lines += ["V4DISP:", "brx.idx.uni hop, V4T;"] if SHARED_DISPATCH else DISPATCH
     for i, (pre, b) in enumerate(bodies):

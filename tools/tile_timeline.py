@@ -21,8 +21,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--costs", default="80,110,150,250")
-    ap.add_argument("--tile", type=int, default=11)
-    ap.add_argument("--pipe", type=int, default=1, help="1: split-buffer kernel at tile 11 (ring kernel at 12), 2: ring kernel")
+    ap.add_argument("--tile", type=int, default=12)
     a = ap.parse_args()
     pkg = ge.load_package()
     L = pkg._lib
@@ -32,7 +31,6 @@ def main():
         st = pkg.B200State(n, 0)
         st.set_option(L.OPT_MAX_COST, cost)
         st.set_option(L.OPT_TILE_BITS, a.tile)
-        st.set_option(L.OPT_PIPELINE, a.pipe)
         st.apply_circuit(gates); st.sync()                 # dense state, warm
         st.set_option(L.OPT_TRACE, 1)
         st.set_option(L.OPT_TIME_PASSES, 1)
@@ -44,14 +42,14 @@ def main():
         t = buf.reshape(-1, 8).astype(np.int64)
         last = pt[-1]
         ngroups = int(last[1])
-        teams = 2 if a.tile == 12 else (3 if a.pipe == 1 else 4)
+        teams = 2 if a.tile == 12 else 4
         t = t[8:-8]                                            # steady state
         end_body = t[:, 2 + min(ngroups, 3) - 1]
-        out = {"tile": a.tile, "pipe": a.pipe, "budget": cost, "last_pass_ms": float(last[0]), "groups": ngroups, "gates": int(last[2]),
+        out = {"tile": a.tile, "budget": cost, "last_pass_ms": float(last[0]), "groups": ngroups, "gates": int(last[2]),
                "wait_full": float(np.mean(t[:, 1] - t[:, 0])), "groups_total": float(np.mean(end_body - t[:, 1])),
                "arrive": float(np.mean(t[:, 5] - end_body)),
                "tile_period_per_team": float(np.mean(np.diff(t[::teams, 0]))),
-               "producer_store_to_load": float(np.mean((t[:, 7] - t[:, 6])[t[:, 7] > 0])) if a.tile == 12 or a.pipe == 2 else None,
+               "producer_store_to_load": float(np.mean((t[:, 7] - t[:, 6])[t[:, 7] > 0])),
                "computed_seen_after_arrive": float(np.mean(t[:, 6] - t[:, 5]))}
         # overlap of body intervals [landed, end_body] between consecutive tiles (which belong to different teams)
         a0, a1 = t[:-1, 1], end_body[:-1]
