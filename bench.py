@@ -275,6 +275,10 @@ def main():
     ap.add_argument("--short-pct", type=int, default=-1, help="QM_OPT_SHORT_PCT (default 180; 100 = off)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-alt", action="store_true", help="skip the deep-fusion secondary measurement")
+    ap.add_argument("--overlap", type=int, default=-1, help="sharded: QM_OPT_OVERLAP (default: engine default, 1)")
+    ap.add_argument("--xsm", type=int, default=-1, help="sharded: SMs of the overlapped exchange kernel")
+    ap.add_argument("--xun", type=int, default=-1, help="sharded: pairs in flight per exchange thread (4 or 8)")
+    ap.add_argument("--slab-bits", type=int, default=-1, help="sharded: log2 of the number of slabs")
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c4"],
                     help="auto: C3 at N = 1, C4 at N > 1; c4 at N = 1 runs the 33-qubit weak-scaling base")
     args = ap.parse_args()

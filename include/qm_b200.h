@@ -162,6 +162,21 @@ int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k, int32_t ba
 int32_t qm_sample(qm_state* st, uint64_t seed, int32_t nshots, int32_t batch_idx, uint64_t* out);
 int32_t qm_norm2(qm_state* st, int32_t batch_idx, double* out);
 
+/* ---- QInfo measures for MANY small matrices, on the device ---------------------------
+ * The reference evaluates every measure from a host eigen-decomposition of one 2^k x 2^k matrix (QInfo.jl:24-28);
+ * a batched reservoir has thousands per step.  One warp diagonalises one matrix (cyclic complex Jacobi, d <= 16).
+ * qm_reduced_density_batch  qm_reduced_density for every register of the batch: out [batch][4^k] ComplexF64, column-major
+ * qm_entropy_batch          entropy of the reduced matrix of every register (k <= 4): kind 0 von_neumann_entropy
+ *                           (QInfo.jl:47-50, eigenvalues clamped at 1e-10 inside the log as :26), 1 renyi_entropy(alpha)
+ *                           (:199-204), 2 min_entropy (:353-357), 3 max_entropy (:332-337); out [batch] doubles
+ * qm_herm_measure_batch     the same measures for `count` host matrices (d x d, column-major), plus 4 trace_distance of
+ *                           (A, B) (:311-316), 5 fidelity(A, B) (:289-294), 6 ascending eigenvalues (out [count][d])
+ */
+int32_t qm_reduced_density_batch(qm_state* st, int32_t keep_low, int32_t k, double* out_colmajor);
+int32_t qm_entropy_batch(qm_state* st, int32_t keep_low, int32_t k, int32_t kind, double alpha, double* out_host);
+int32_t qm_herm_measure_batch(int32_t device, int32_t kind, double alpha, const double* A, const double* B,
+                              int32_t d, int32_t count, double* out_host);
+
 /* ---- density matrices (the Matrix{ComplexF64} methods of QSim.jl) ----------------------------
  * rho on q qubits is a register of 2q qubits holding vec(rho) in Julia's column-major Matrix memory:
  * amplitude r + c 2^q = rho[r, c].  rho <- op rho op' (u2!  QSim.jl:67-79, controlled!  :209-232) is then

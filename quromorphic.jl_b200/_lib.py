@@ -63,6 +63,9 @@ SIGNATURES = {
     "qm_expect_all": (C.c_int32, [_vp, C.c_int32, C.c_double, _dp]),
     "qm_expect_all_with": (C.c_int32, [_vp, _dp, C.c_double, _dp]),
     "qm_reduced_density": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp]),
+    "qm_reduced_density_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, _dp]),
+    "qm_entropy_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_double, _dp]),
+    "qm_herm_measure_batch": (C.c_int32, [C.c_int32, C.c_int32, C.c_double, _dp, _dp, C.c_int32, C.c_int32, _dp]),
     "qm_sample": (C.c_int32, [_vp, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
     "qm_norm2": (C.c_int32, [_vp, C.c_int32, _dp]),
     "qm_dm_from_state": (C.c_int32, [_vp, _vp]),

@@ -524,8 +524,11 @@ k_probs(const double2* __restrict__ amp, uint64_t n, double* __restrict__ out) {
 // ---------------------------------------------------------------------------------------------
 static const int kRedXC = 64;
 __global__ void __launch_bounds__(256)
-k_reduced_partial(const double2* __restrict__ psi, int nbits, int k, int keep_low, uint64_t x_per_cta,
-                  double2* __restrict__ partial) {
+k_reduced_partial(const double2* __restrict__ psi_all, int nbits, int k, int keep_low, uint64_t x_per_cta,
+                  double2* __restrict__ partial_all) {
+    // blockIdx.z = register of a batch (its amplitudes and its partial tiles follow those of register z - 1)
+    const double2* __restrict__ psi = psi_all + ((uint64_t)blockIdx.z << nbits);
+    double2* __restrict__ partial = partial_all + (size_t)blockIdx.z * gridDim.x * ((size_t)1 << (2 * k));
     const uint32_t d = 1u << k, T = d < 16 ? d : 16, tiles = d / T;
     const uint64_t R = 1ull << (nbits - k);
     const uint32_t ti0 = (blockIdx.y % tiles) * T, tj0 = (blockIdx.y / tiles) * T;
@@ -561,7 +564,9 @@ k_reduced_partial(const double2* __restrict__ psi, int nbits, int k, int keep_lo
     if (active) partial[((size_t)blockIdx.x * d + (tj0 + tj)) * d + (ti0 + ti)] = acc;   // column-major [j][i]
 }
 __global__ void __launch_bounds__(256)
-k_reduced_final(const double2* __restrict__ partial, uint32_t nchunks, uint32_t entries, double2* __restrict__ out) {
+k_reduced_final(const double2* __restrict__ partial_all, uint32_t nchunks, uint32_t entries, double2* __restrict__ out_all) {
+    const double2* __restrict__ partial = partial_all + (size_t)blockIdx.y * nchunks * entries;      // blockIdx.y = register
+    double2* __restrict__ out = out_all + (size_t)blockIdx.y * entries;
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= entries) return;
     double2 acc = make_double2(0.0, 0.0);

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "lifting.hpp"
 #include "planner.hpp"
+#include "qinfo_kernels.cuh"
 #include "state.hpp"
 
 using namespace qm;
@@ -991,6 +992,108 @@ extern "C" int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k,
     QM_TRY(qm_sync(st));
     memcpy(out, st->h_scratch, entries * 16);
     return QM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reduced matrices and QInfo measures for a whole batch of registers, on the device
+// ---------------------------------------------------------------------------------------------
+// reduced density of EVERY register of the batch: d_out [batch][4^k] double2 on the device
+static int reduced_batch_local(qm_state* st, int keep_low, int k, double2** d_out_p) {
+    const uint32_t d = 1u << k, T = d < 16 ? d : 16, tiles = d / T;
+    const uint64_t R = 1ull << (st->nl - k);
+    const int B = st->batch;
+    if (B > 65535) return set_err(QM_ERR_ARG, "batch too large for the readout grid");
+    uint64_t xchunks = R / kRedXC; if (xchunks < 1) xchunks = 1;
+    uint64_t cap = (uint64_t)st->sms * 8 / (uint64_t)B; if (cap < 1) cap = 1; if (cap > 512) cap = 512;
+    if (xchunks > cap) xchunks = cap;
+    while (R % xchunks) --xchunks;
+    const uint64_t x_per = R / xchunks;
+    const size_t entries = (size_t)d * d;
+    QM_TRY(ENSURE_DEV(st, d_scratch, ((size_t)B * (xchunks + 1) * entries) * 16 + (size_t)B * 8 * (kHermMaxD + 1)));
+    double2* d_part = reinterpret_cast<double2*>(st->d_scratch);
+    double2* d_out = d_part + (size_t)B * xchunks * entries;
+    dim3 grid((unsigned)xchunks, tiles * tiles, (unsigned)B);
+    k_reduced_partial<<<grid, 256, 0, st->stream>>>(st->amp, st->nl, k, keep_low ? 1 : 0, x_per, d_part);
+    CU(cudaGetLastError());
+    dim3 g2((unsigned)((entries + 255) / 256), (unsigned)B);
+    k_reduced_final<<<g2, 256, 0, st->stream>>>(d_part, (uint32_t)xchunks, (uint32_t)entries, d_out);
+    CU(cudaGetLastError());
+    st->ctr.launches += 2; st->ctr.bytes_hbm += 16ull * total_amps(st);
+    *d_out_p = d_out;
+    return QM_OK;
+}
+
+extern "C" int32_t qm_reduced_density_batch(qm_state* st, int32_t keep_low, int32_t k, double* out) {
+    if (!st || !out) return set_err(QM_ERR_ARG, "null argument");
+    if (st->dist) return set_err(QM_ERR_STATE, "sharded registers are not batched");
+    if (k < 1 || k >= st->n || k > 10) return set_err(QM_ERR_ARG, "Dimension mismatch: k = %d of n = %d (1 <= k < n, k <= 10)", k, st->n);
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    double2* d_out = nullptr;
+    QM_TRY(reduced_batch_local(st, keep_low, k, &d_out));
+    const size_t bytes = ((size_t)st->batch << (2 * k)) * 16;
+    CU(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += bytes;
+    return qm_sync(st);
+}
+
+// von Neumann / Renyi / min / max entropy of the reduced matrix of every register of the batch: one read of the states,
+// one warp-per-matrix Jacobi launch, `batch` doubles back (QInfo.jl:178-182 entanglement_entropy for a whole batch)
+extern "C" int32_t qm_entropy_batch(qm_state* st, int32_t keep_low, int32_t k, int32_t kind, double alpha, double* out_host) {
+    if (!st || !out_host) return set_err(QM_ERR_ARG, "null argument");
+    if (st->dist) return set_err(QM_ERR_STATE, "sharded registers are not batched");
+    if (k < 1 || k >= st->n || k > 4) return set_err(QM_ERR_ARG, "Dimension mismatch: k = %d of n = %d (1 <= k < n, k <= 4 on the device)", k, st->n);
+    if (kind < HM_VON_NEUMANN || kind > HM_MAX_ENTROPY) return set_err(QM_ERR_ARG, "unknown entropy kind %d", kind);
+    if (kind == HM_RENYI && alpha == 1.0) return set_err(QM_ERR_ARG, "Renyi entropy undefined for alpha = 1; use von Neumann entropy");
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    double2* d_rho = nullptr;
+    QM_TRY(reduced_batch_local(st, keep_low, k, &d_rho));
+    double* d_ent = reinterpret_cast<double*>(d_rho + ((size_t)st->batch << (2 * k)));
+    QM_TRY(ENSURE_PIN(st, h_scratch, (size_t)st->batch * 8));
+    k_herm_measure<<<st->batch, 32, 0, st->stream>>>(d_rho, nullptr, 1 << k, st->batch, kind, alpha, d_ent);
+    CU(cudaGetLastError());
+    st->ctr.launches++;
+    CU(cudaMemcpyAsync(st->h_scratch, d_ent, (size_t)st->batch * 8, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += (size_t)st->batch * 8;
+    QM_TRY(qm_sync(st));
+    memcpy(out_host, st->h_scratch, (size_t)st->batch * 8);
+    return QM_OK;
+}
+
+// QInfo measures of `count` host matrices (d x d complex, d <= 16, column-major), computed on `device`.
+// kind: 0 von Neumann, 1 Renyi(alpha), 2 min-entropy, 3 max-entropy, 4 trace distance of (A - B), 5 fidelity(A, B),
+// 6 eigenvalues (out: [count][d] ascending).  B may be NULL for the one-matrix kinds.
+extern "C" int32_t qm_herm_measure_batch(int32_t device, int32_t kind, double alpha, const double* A, const double* B,
+                                         int32_t d, int32_t count, double* out_host) {
+    if (!A || !out_host || count < 0) return set_err(QM_ERR_ARG, "null argument");
+    if (d < 1 || d > kHermMaxD) return set_err(QM_ERR_ARG, "matrix dimension %d (1 <= d <= %d)", d, kHermMaxD);
+    if (kind < HM_VON_NEUMANN || kind > HM_EIGVALS) return set_err(QM_ERR_ARG, "unknown measure %d", kind);
+    if ((kind == HM_FIDELITY || kind == HM_TRACE_DISTANCE) && !B) return set_err(QM_ERR_ARG, "this measure takes two matrices");
+    if (kind == HM_RENYI && alpha == 1.0) return set_err(QM_ERR_ARG, "Renyi entropy undefined for alpha = 1");
+    if (count == 0) return QM_OK;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return set_err(QM_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return set_err(QM_ERR_ARG, "device %d of %d", device, ndev);
+    CU(cudaSetDevice(device));
+    const size_t mbytes = (size_t)count * d * d * 16, obytes = (size_t)count * (kind == HM_EIGVALS ? d : 1) * 8;
+    double2 *dA = nullptr, *dB = nullptr; double* dO = nullptr;
+    int rc = [&]() -> int {
+        CU(cudaMalloc((void**)&dA, mbytes)); CU(cudaMalloc((void**)&dO, obytes));
+        if (kind == HM_TRACE_DISTANCE) {            // eigenvalues of A - B: subtract on the host
+            std::vector<double> D((size_t)count * d * d * 2);
+            for (size_t i = 0; i < D.size(); ++i) D[i] = A[i] - B[i];
+            CU(cudaMemcpy(dA, D.data(), mbytes, cudaMemcpyHostToDevice));
+        } else CU(cudaMemcpy(dA, A, mbytes, cudaMemcpyHostToDevice));
+        if (kind == HM_FIDELITY) { CU(cudaMalloc((void**)&dB, mbytes)); CU(cudaMemcpy(dB, B, mbytes, cudaMemcpyHostToDevice)); }
+        k_herm_measure<<<count, 32>>>(dA, dB, d, count, kind, alpha, dO);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(out_host, dO, obytes, cudaMemcpyDeviceToHost));
+        return QM_OK;
+    }();
+    cudaFree(dA); cudaFree(dB); cudaFree(dO);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------

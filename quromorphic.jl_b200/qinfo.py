@@ -1,4 +1,4 @@
-"""qinfo.py — host-side mirror of the QInfo readouts a quantum reservoir uses.
+"""qinfo.py — host-side mirror of the QInfo readouts a quantum reservoir uses, and their batched device versions.
 
 partial_trace / entanglement_entropy take the device state directly (the reference needs the full
 density matrix rho = psi psi', 16 * 4^n bytes — QSim.jl:39-41, QInfo.jl:381-405; the engine
@@ -161,3 +161,58 @@ def trace_distance(rho, sigma):
     """QInfo.jl:311-316: half the sum of |eigenvalues| of rho - sigma"""
     d = _herm(_joint(rho)) - _herm(_joint(sigma))
     return float(0.5 * np.sum(np.abs(np.linalg.eigvalsh(d))))
+
+
+# ---- batched measures on the device (SURVEY.md §8f N4) -------------------------------------------------------------
+# One warp of k_herm_measure diagonalises one matrix (cyclic complex Jacobi); thousands of matrices are one launch.
+# rhos / sigmas: arrays [count, d, d] (numpy [i, j]), d <= 16.
+
+_KINDS = {"von_neumann": 0, "renyi": 1, "min": 2, "max": 3, "trace_distance": 4, "fidelity": 5, "eigvals": 6}
+
+
+def _colmajor(ms):
+    ms = np.asarray(ms, dtype=np.complex128)
+    if ms.ndim == 2:
+        ms = ms[None]
+    assert ms.ndim == 3 and ms.shape[1] == ms.shape[2] and ms.shape[1] <= 16
+    return np.ascontiguousarray(ms.transpose(0, 2, 1)), ms.shape[0], ms.shape[1]
+
+
+def measure_batch(kind, rhos, sigmas=None, alpha=2.0, device=0):
+    from . import _lib as L
+    A, count, d = _colmajor(rhos)
+    B = None
+    if sigmas is not None:
+        B, cb, db = _colmajor(sigmas)
+        assert (cb, db) == (count, d)
+    out = np.empty((count, d) if kind == "eigvals" else count, dtype=np.float64)
+    L.check(L.lib().qm_herm_measure_batch(int(device), _KINDS[kind], float(alpha), L.dptr(A.view(np.float64)),
+                                          L.dptr(B.view(np.float64)) if B is not None else None, d, count, L.dptr(out)))
+    return out
+
+
+def von_neumann_entropy_batch(rhos, device=0): return measure_batch("von_neumann", rhos, device=device)
+def renyi_entropy_batch(rhos, alpha, device=0): return measure_batch("renyi", rhos, alpha=alpha, device=device)
+def min_entropy_batch(rhos, device=0): return measure_batch("min", rhos, device=device)
+def max_entropy_batch(rhos, device=0): return measure_batch("max", rhos, device=device)
+def trace_distance_batch(rhos, sigmas, device=0): return measure_batch("trace_distance", rhos, sigmas, device=device)
+def fidelity_batch(rhos, sigmas, device=0): return measure_batch("fidelity", rhos, sigmas, device=device)
+def eigvalsh_batch(rhos, device=0): return measure_batch("eigvals", rhos, device=device)
+
+
+def quantum_mutual_information_batch(rhos_AB, dim_A, dim_B, device=0):
+    """QInfo.jl:68-73 for a batch of joint matrices [count, dA dB, dA dB] (dA dB <= 16): S(A) + S(B) - S(AB); the partial
+    traces are reshapes on the host, the three eigen-decompositions per item run on the device"""
+    r = np.asarray(rhos_AB, dtype=np.complex128)
+    r = (r + r.conj().transpose(0, 2, 1)) / 2
+    t = r.reshape(-1, dim_A, dim_B, dim_A, dim_B)
+    rA, rB = np.einsum("niljl->nij", t), np.einsum("nkikj->nij", t)
+    return (von_neumann_entropy_batch(rA, device) + von_neumann_entropy_batch(rB, device) - von_neumann_entropy_batch(r, device))
+
+
+def entanglement_entropy_batch(s, dim_A, dim_B):
+    """entanglement_entropy (QInfo.jl:178-182) of EVERY register of a batched B200State, on the device"""
+    kA = int(round(np.log2(dim_A)))
+    if dim_A * dim_B != (1 << s.n) or (1 << kA) != dim_A:
+        raise AssertionError("Dimension mismatch")
+    return s.entropy_batch(False, kA, "von_neumann")

@@ -213,6 +213,21 @@ class B200State:
         L.check(L.lib().qm_reduced_density(self._h, 1 if keep_low else 0, k, batch_idx, L.dptr(out)))
         return out.reshape(d, d).T.copy()          # column-major -> numpy [i, j]
 
+    def reduced_density_batch(self, keep_low, k):
+        """reduced density matrix of EVERY register of the batch: array [batch, 2^k, 2^k] (numpy [i, j])"""
+        d = 1 << k
+        out = np.empty((self.batch, d * d), dtype=np.complex128)
+        L.check(L.lib().qm_reduced_density_batch(self._h, 1 if keep_low else 0, k, L.dptr(out)))
+        return out.reshape(self.batch, d, d).transpose(0, 2, 1).copy()
+
+    def entropy_batch(self, keep_low, k, kind="von_neumann", alpha=2.0):
+        """entropy of the reduced matrix of every register of the batch, computed on the device (one Jacobi warp per
+        register): kind in von_neumann, renyi, min, max — QInfo.jl:47-50, :199-204, :353-357, :332-337"""
+        kinds = {"von_neumann": 0, "renyi": 1, "min": 2, "max": 3}
+        out = np.empty(self.batch, dtype=np.float64)
+        L.check(L.lib().qm_entropy_batch(self._h, 1 if keep_low else 0, k, kinds[kind], float(alpha), L.dptr(out)))
+        return out
+
     def sample(self, seed, nshots, batch_idx=0):
         out = np.empty(nshots, dtype=np.uint64)
         L.check(L.lib().qm_sample(self._h, int(seed), nshots, batch_idx, out.ctypes.data_as(C.POINTER(C.c_uint64))))
