@@ -145,6 +145,8 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
             line["config"]["workload"] += " [NON-DEFAULT size: %d qubits]" % n
         if emit:
             print(json.dumps(line), flush=True)
+    if not single:
+        dist.barrier()
     st.close()
     if not single:
         dist.destroy_process_group()
@@ -175,6 +177,7 @@ def dist_parity(pkg, rank, world, g):
     R = W.reference(pkg, n)
     st = pkg.dist.sharded_state(n, R["m"])
     out = W.check_sharded(pkg, st, rank, world, R)
+    dist.barrier()                       # nobody frees a shard another rank may still be writing flags into
     st.close()
     worst = max(out[k] for k in ("err", "zerr", "z0err", "nerr", "merr", "rerr", "err_after_reset"))
     t = torch.tensor([worst, 0.0 if out["ok"] else 1.0, 0.0 if out["sample_bitexact"] else 1.0, float(out["overlapped_remaps"])],

@@ -25,8 +25,12 @@
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <chrono>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
 
 using namespace qm;
 
@@ -180,7 +184,24 @@ k_remap_swap(double2* __restrict__ mine, const __grid_constant__ PeerPtrs peers,
     }
 }
 
+// A same-process world whose ranks all sit on ONE device runs every rank on one shared, in-order stream.  Flags and
+// stream waits between streams of the same device are ordering the CUDA scheduler cannot see (it may park the kernel that
+// posts a flag behind the stream that waits for it), so there the ordering is made of what it does see: stream order,
+// with a host-side handshake (a rank enqueues work that depends on another rank's only after that rank has ENQUEUED its
+// part).  The kernels, the exchange, the mailboxes and the slab bookkeeping are the ones every other transport runs.
+struct LocalWorld {
+    std::vector<qm_state*> ranks;
+    cudaStream_t shared = nullptr;
+    int refs = 0;
+    std::atomic<uint32_t> issued[4][16][16];      // [kind][rank][slab]: last epoch whose signal has been enqueued
+    LocalWorld() { for (auto& a : issued) for (auto& b : a) for (auto& c : b) c.store(0); }
+};
+
 struct DistCtx {
+    std::shared_ptr<LocalWorld> lw;                     // same-process worlds only
+    bool shared_stream = false;                         // ... with every rank on one device
+    cudaEvent_t ev_sig[4][16] = { { nullptr } };        // this rank's own signals as CUDA events: dependencies between its own
+                                                        // two streams must be visible to the scheduler
     double2* peer[16] = { nullptr };                    // the other ranks' shards (IPC-mapped or same-process pointers); null: NCCL path
     unsigned char* win[16] = { nullptr };               // every rank's window, own included
     bool have_peers = false, ipc_mapped = false;
@@ -196,21 +217,25 @@ struct DistCtx {
 
 // ---- same-process worlds (all ranks in one process: the 1-GPU test of the sharded path) ------------------------
 static std::mutex g_local_mu;
-static std::map<unsigned long long, std::vector<qm_state*>> g_local_worlds;
+static std::map<unsigned long long, std::shared_ptr<LocalWorld>> g_local_worlds;
 
 int dist_destroy(DistCtx* d) {
     if (!d) return QM_OK;
     if (d->ipc_mapped) for (int j = 0; j < 16; ++j) if (d->peer[j]) cudaIpcCloseMemHandle(d->peer[j]);
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
-    if (d->xstream) cudaStreamDestroy(d->xstream);
+    if (d->xstream && !d->shared_stream) cudaStreamDestroy(d->xstream);
+    for (auto& a : d->ev_sig) for (cudaEvent_t e : a) if (e) cudaEventDestroy(e);
     cudaFree(d->stage); cudaFree(d->d_small);
     if (d->local_world) {
         std::lock_guard<std::mutex> lk(g_local_mu);
+        if (d->lw && d->shared_stream && --d->lw->refs == 0 && d->lw->shared) { cudaStreamDestroy(d->lw->shared); d->lw->shared = nullptr; }
         g_local_worlds.erase(d->local_key);
     }
     delete d;
     return QM_OK;
 }
+// the state's stream belongs to the world, not to the state
+bool dist_owns_stream(const qm_state* st) { return st->dist && st->dist->shared_stream; }
 
 extern "C" int32_t qm_dist_unique_id(uint8_t id_out[128]) {
     if (!id_out) return set_err(QM_ERR_ARG, "null argument");
@@ -230,6 +255,12 @@ static int dist_common_init(qm_state* st, DistCtx* d) {
     CU(cudaMemset(d->d_small, 0, 4096 * sizeof(double)));
     CU(cudaMemset(own_window(st), 0, kWinBytes));
     CU(cudaStreamCreateWithFlags(&d->xstream, cudaStreamNonBlocking));
+    // Readout scratch is allocated NOW, large enough for every collective readout of a moderate register (all-qubit
+    // marginals, single-qubit measurements, reduced densities up to k = 6, the sampler up to 2^30 amplitudes):
+    // cudaMalloc / cudaMallocHost synchronise with the other streams of the device, and when several ranks share a
+    // device (same-process worlds) another rank's stream may be parked on a flag this rank has yet to post.
+    QM_TRY(ENSURE_DEV(st, d_scratch, (size_t)48 << 20));
+    QM_TRY(ENSURE_PIN(st, h_scratch, (size_t)1 << 20));
     CU(cudaDeviceSynchronize());
     d->win[st->rank] = own_window(st);
     return QM_OK;
@@ -277,9 +308,11 @@ extern "C" int32_t qm_create_dist_local(int32_t n, uint64_t basis, int32_t devic
     if (rc != QM_OK) { qm_destroy(st); return rc; }
     {
         std::lock_guard<std::mutex> lk(g_local_mu);
-        std::vector<qm_state*>& v = g_local_worlds[key];
-        if (v.size() < (size_t)world) v.resize(world, nullptr);
-        v[rank] = st;
+        std::shared_ptr<LocalWorld>& w = g_local_worlds[key];
+        if (!w) w = std::make_shared<LocalWorld>();
+        if (w->ranks.size() < (size_t)world) w->ranks.resize(world, nullptr);
+        w->ranks[rank] = st;
+        d->lw = w;
     }
     *out = st;
     return QM_OK;
@@ -290,7 +323,10 @@ extern "C" int32_t qm_dist_local_connect(qm_state* st) {
     DistCtx* d = st->dist;
     CU(cudaSetDevice(st->device));
     std::lock_guard<std::mutex> lk(g_local_mu);
-    const std::vector<qm_state*>& v = g_local_worlds[d->local_key];
+    if (!d->lw) return set_err(QM_ERR_STATE, "world not registered");
+    const std::vector<qm_state*>& v = d->lw->ranks;
+    bool one_device = true;
+    for (int j = 0; j < st->world; ++j) one_device = one_device && (size_t)j < v.size() && v[j] && v[j]->device == st->device;
     for (int j = 0; j < st->world; ++j) {
         if ((size_t)j >= v.size() || !v[j]) return set_err(QM_ERR_STATE, "rank %d of the world has not been created yet", j);
         if (v[j]->n != st->n || v[j]->world != st->world) return set_err(QM_ERR_ARG, "rank %d has a different shape", j);
@@ -303,6 +339,13 @@ extern "C" int32_t qm_dist_local_connect(qm_state* st) {
         d->peer[j] = v[j]->amp;
         d->win[j] = own_window(v[j]);
     }
+    if (one_device) {           // every rank on one device: one shared in-order stream for all of them (see LocalWorld)
+        if (!d->lw->shared) CU(cudaStreamCreateWithFlags(&d->lw->shared, cudaStreamNonBlocking));
+        CU(cudaStreamSynchronize(st->stream)); CU(cudaStreamSynchronize(d->xstream));
+        cudaStreamDestroy(st->stream); cudaStreamDestroy(d->xstream);
+        st->stream = d->lw->shared; d->xstream = d->lw->shared;
+        d->shared_stream = true; d->lw->refs++;
+    }
     d->have_peers = true;
     return QM_OK;
 }
@@ -311,17 +354,42 @@ extern "C" int32_t qm_dist_local_connect(qm_state* st) {
 static PeerWins wins_of(const DistCtx* d) { PeerWins pw; for (int j = 0; j < 16; ++j) pw.p[j] = d->win[j]; return pw; }
 
 static int signal_all(qm_state* st, cudaStream_t stream, int kind, int slab, uint32_t epoch) {
-    k_signal<<<1, 32, 0, stream>>>(wins_of(st->dist), st->world, kind * 256 + st->rank * 16 + slab, epoch);
+    DistCtx* d = st->dist;
+    if (d->shared_stream) {         // stream order is the ordering: publish that this rank's part has been enqueued
+        d->lw->issued[kind][st->rank][slab].store(epoch, std::memory_order_release);
+        return QM_OK;
+    }
+    k_signal<<<1, 32, 0, stream>>>(wins_of(d), st->world, kind * 256 + st->rank * 16 + slab, epoch);
     CU(cudaGetLastError());
     st->ctr.launches++;
+    // this rank's own streams see the signal as an event (a dependency the scheduler knows about)
+    if (!d->ev_sig[kind][slab]) CU(cudaEventCreateWithFlags(&d->ev_sig[kind][slab], cudaEventDisableTiming));
+    CU(cudaEventRecord(d->ev_sig[kind][slab], stream));
     return QM_OK;
 }
 // the stream waits until every rank (this one included) has posted `epoch` for (kind, slab)
 static int wait_all(qm_state* st, cudaStream_t stream, int kind, int slab, uint32_t epoch) {
+    DistCtx* d = st->dist;
+    if (d->shared_stream) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int j = 0; j < st->world; ++j) {
+            int spins = 0;
+            while ((int32_t)(d->lw->issued[kind][j][slab].load(std::memory_order_acquire) - epoch) < 0) {
+                if (++spins < 200) std::this_thread::yield(); else std::this_thread::sleep_for(std::chrono::microseconds(50));
+                if ((spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
+                    return set_err(QM_ERR_COMM, "rank %d of the same-process world did not reach this collective (kind %d, slab %d)", j, kind, slab);
+            }
+        }
+        return QM_OK;
+    }
     PFN_waitValue32 wv = get_wait_value();
     if (!wv) return set_err(QM_ERR_COMM, "cuStreamWaitValue32 is not available");
-    unsigned char* w = st->dist->win[st->rank];
+    unsigned char* w = d->win[st->rank];
     for (int j = 0; j < st->world; ++j) {
+        if (j == st->rank) {
+            if (d->ev_sig[kind][slab]) CU(cudaStreamWaitEvent(stream, d->ev_sig[kind][slab], 0));
+            continue;
+        }
         CUresult r = wv((CUstream)stream, (CUdeviceptr)(w + 4u * (kind * 256 + j * 16 + slab)), epoch, CU_STREAM_WAIT_VALUE_GEQ);
         if (r != CUDA_SUCCESS) return set_err(QM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)r);
     }
@@ -343,6 +411,7 @@ static int mbox_exchange(qm_state* st, const void* d_src, size_t bytes, int* par
     k_mbox_put<<<st->world, 256, 0, st->stream>>>(wins_of(d), st->rank, parity, reinterpret_cast<const uint4*>(d_src), (uint32_t)(bytes / 16), e);
     CU(cudaGetLastError());
     st->ctr.launches++;
+    if (d->shared_stream) d->lw->issued[FK_MBOX][st->rank][0].store(e, std::memory_order_release);
     QM_TRY(wait_all(st, st->stream, FK_MBOX, 0, e));
     *parity_out = parity;
     return QM_OK;

@@ -6,6 +6,7 @@
 #include "state.hpp"
 
 int  dist_destroy(DistCtx* d);
+bool dist_owns_stream(const qm_state* st);      // the state's stream belongs to a same-process world
 // exchange the g global index bits with the top g local ones (in-place chunked all-to-all over NVLink),
 // update st->perm, and relabel the not-yet-executed lowered gates (may be null)
 int  dist_remap(qm_state* st, std::vector<qm::LGate>* gates, std::vector<char>* done);

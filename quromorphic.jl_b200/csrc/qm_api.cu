@@ -6,7 +6,9 @@
 #include <math.h>
 #include <stdio.h>
 #include <chrono>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/qm_b200.h"
@@ -104,13 +106,15 @@ extern "C" int32_t qm_destroy(qm_state* st) {
     if (!st) return QM_OK;
     cudaSetDevice(st->device);
     if (st->stream) cudaStreamSynchronize(st->stream);
+    if (dist_owns_stream(st)) st->stream = nullptr;
     if (st->dist) { dist_destroy(st->dist); st->dist = nullptr; }
     for (auto& pr : st->remap_events) { if (pr.first) cudaEventDestroy(pr.first); if (pr.second) cudaEventDestroy(pr.second); }
     for (cudaEvent_t ev : st->pass_events) cudaEventDestroy(ev);
     st->remap_events.clear(); st->pass_events.clear();
     cudaFree(st->trace_buf);
     cudaFree(st->amp); cudaFree(st->d_blob); cudaFree(st->d_scratch); cudaFree(st->d_slots);
-    cudaFreeHost(st->h_blob); cudaFreeHost(st->h_scratch);
+    cudaFreeHost(st->h_blob); cudaFreeHost(st->h_scratch); cudaFreeHost(st->h_slots);
+    for (int i = 0; i < 2; ++i) if (st->ev_slots[i]) cudaEventDestroy(st->ev_slots[i]);
     for (void* q : st->retired_dev) cudaFree(q);
     for (void* q : st->retired_pinned) cudaFreeHost(q);
     if (st->ev0) cudaEventDestroy(st->ev0);
@@ -647,7 +651,6 @@ extern "C" int32_t qm_apply_batched(qm_state* st, const qm_gate* gates, int32_t 
     // matrices for the v1 kernel, lifting coefficients for v2.
     const int B = st->batch;
     SlotMap sm; sm.first.resize(nslots); sm.count.resize(nslots);
-    bool all_liftable = true;
     std::vector<int> kinds(nslots);
     auto plain_kind = [](const double* m) {
         LiftCoef L; int k = lift_classify(m, L);
@@ -655,64 +658,117 @@ extern "C" int32_t qm_apply_batched(qm_state* st, const qm_gate* gates, int32_t 
         if (k != LK_NONE && (L.mk[0] | L.mk[1] | L.mk[2] | L.mk[3])) return (int)LK_NONE;
         return k;
     };
-    for (int s = 0; s < nslots; ++s) {
-        int k0 = plain_kind(per_state_mats + (size_t)s * 8);
-        for (int b = 1; b < B && k0 != LK_NONE; ++b)
-            if (plain_kind(per_state_mats + ((size_t)b * nslots + s) * 8) != k0) k0 = LK_NONE;
-        kinds[s] = k0;
-        sm.first[s] = (int)sm.kind.size(); sm.count[s] = (k0 == LK_NONE) ? 5 : 1;
-        if (k0 == LK_NONE) { const int ks[5] = { LK_PHASE, LK_PHASE, LK_ROT, LK_PHASE, LK_PHASE }; sm.kind.insert(sm.kind.end(), ks, ks + 5); }
-        else sm.kind.push_back(k0);
+    // The host side of a batched step is B x nslots small classifications (65,536 at 4096 x 16): spread over host
+    // threads, states in contiguous blocks.  It used to be a single loop and, with the synchronous pageable upload
+    // after it, 46 % of a C2 step.
+    int nthreads = (int)std::thread::hardware_concurrency(); if (nthreads < 1) nthreads = 1; if (nthreads > 16) nthreads = 16;
+    if ((long long)B * nslots < 4096) nthreads = 1;
+    auto parallel_states = [&](const std::function<void(int, int, int)>& fn) {        // fn(thread, b0, b1)
+        if (nthreads == 1) { fn(0, 0, B); return; }
+        std::vector<std::thread> th;
+        const int per = (B + nthreads - 1) / nthreads;
+        for (int t = 0; t < nthreads; ++t) {
+            const int b0 = t * per, b1 = b0 + per < B ? b0 + per : B;
+            if (b0 >= b1) break;
+            th.emplace_back(fn, t, b0, b1);
+        }
+        for (auto& x : th) x.join();
+    };
+    {   // slot kinds: one lifting kind with plain signs for every state, or the general five-piece form
+        std::vector<std::vector<int>> part(nthreads, std::vector<int>(nslots, -2));       // -2 = no state seen
+        parallel_states([&](int t, int b0, int b1) {
+            std::vector<int>& k = part[t];
+            for (int b = b0; b < b1; ++b)
+                for (int s = 0; s < nslots; ++s) {
+                    if (k[s] == LK_NONE) continue;
+                    const int kk = plain_kind(per_state_mats + ((size_t)b * nslots + s) * 8);
+                    k[s] = (k[s] == -2 || k[s] == kk) ? kk : (int)LK_NONE;
+                }
+        });
+        for (int s = 0; s < nslots; ++s) {
+            int k0 = -2;
+            for (int t = 0; t < nthreads; ++t) { const int k = part[t][s]; if (k == -2) continue; k0 = (k0 == -2 || k0 == k) ? k : (int)LK_NONE; }
+            if (k0 == -2) k0 = LK_NONE;
+            kinds[s] = k0;
+            sm.first[s] = (int)sm.kind.size(); sm.count[s] = (k0 == LK_NONE) ? 5 : 1;
+            if (k0 == LK_NONE) { const int ks[5] = { LK_PHASE, LK_PHASE, LK_ROT, LK_PHASE, LK_PHASE }; sm.kind.insert(sm.kind.end(), ks, ks + 5); }
+            else sm.kind.push_back(k0);
+        }
     }
     const int nsub = (int)sm.kind.size();
-    std::vector<double> mats((size_t)B * nsub * 8), lifts((size_t)B * nsub * 8, 0.0);
+    const size_t ndoubles = (size_t)B * nsub * 8, bytes = ndoubles * sizeof(double);
+    // pinned staging, two halves used alternately (a half is reused once its upload has finished): [mats | lifts] each
+    // (an outgrown staging buffer is only retired, never freed under a copy in flight: ensure_pinned).
+    // No stream synchronisation: the call returns as soon as the step is enqueued, so the caller's preparation of the
+    // next step overlaps this step's kernels.
+    const int half = st->slots_half; st->slots_half ^= 1;
+    if (!st->ev_slots[0]) { CU(cudaEventCreateWithFlags(&st->ev_slots[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&st->ev_slots[1], cudaEventDisableTiming)); }
+    QM_TRY(ENSURE_PIN(st, h_slots, 4 * bytes));
+    CU(cudaEventSynchronize(st->ev_slots[half]));
+    double* mats = st->h_slots + (size_t)half * 2 * ndoubles;
+    double* lifts = mats + ndoubles;
+    memset(lifts, 0, bytes);
     static const double I8[8] = { 1, 0, 0, 0, 0, 0, 1, 0 };
-    for (int b = 0; b < B; ++b)
-        for (int s = 0; s < nslots; ++s) {
-            const double* m = per_state_mats + ((size_t)b * nslots + s) * 8;
-            double* mo = &mats[((size_t)b * nsub + sm.first[s]) * 8];
-            double* lo = &lifts[((size_t)b * nsub + sm.first[s]) * 8];
-            if (kinds[s] != LK_NONE) {
-                memcpy(mo, m, 64);
-                LiftCoef L; lift_classify(m, L); memcpy(lo, &L, 64);
-                continue;
-            }
-            double f[3][8];
-            if (!decompose_unitary(m, f)) {
-                all_liftable = false;      // v1 only: the first subslot carries the matrix, the rest are identities
-                memcpy(mo, m, 64); for (int i = 1; i < 5; ++i) memcpy(mo + 8 * i, I8, 64);
-                continue;
-            }
-            double piece[5][8];
-            for (int side = 0; side < 2; ++side) {          // f[0] = right phase, f[2] = left phase
-                const double* d = f[side == 0 ? 0 : 2];
-                double h[8] = { 1, 0, 0, 0, 0, 0, 1, 0 };
-                unit_sqrt(d[0], d[1], h[0], h[1]); unit_sqrt(d[6], d[7], h[6], h[7]);
-                memcpy(piece[side == 0 ? 0 : 3], h, 64); memcpy(piece[side == 0 ? 1 : 4], h, 64);
-            }
-            memcpy(piece[2], f[1], 64);
-            for (int i = 0; i < 5; ++i) {
-                memcpy(mo + 8 * i, piece[i], 64);
-                LiftCoef L; const int k = lift_classify(piece[i], L);
-                // an identity piece classifies as PHASE with zero shears; a rotation by exactly 0 is diagonal -> PHASE too
-                if (k != sm.kind[sm.first[s] + i] || (L.mk[0] | L.mk[1] | L.mk[2] | L.mk[3])) {
-                    if (i == 2 && k == LK_PHASE && !(L.mk[0] | L.mk[1] | L.mk[2] | L.mk[3])) { memset(&L, 0, sizeof(L)); }  // identity rotation: zero shears
-                    else all_liftable = false;
+    std::vector<char> thread_ok(nthreads, 1);
+    parallel_states([&](int t, int b0, int b1) {
+        bool ok = true;
+        for (int b = b0; b < b1; ++b)
+            for (int s = 0; s < nslots; ++s) {
+                const double* m = per_state_mats + ((size_t)b * nslots + s) * 8;
+                double* mo = &mats[((size_t)b * nsub + sm.first[s]) * 8];
+                double* lo = &lifts[((size_t)b * nsub + sm.first[s]) * 8];
+                if (kinds[s] != LK_NONE) {
+                    memcpy(mo, m, 64);
+                    LiftCoef L; lift_classify(m, L); memcpy(lo, &L, 64);
+                    continue;
                 }
-                memcpy(lo + 8 * i, &L, 64);
+                double f[3][8];
+                if (!decompose_unitary(m, f)) {
+                    ok = false;      // v1 only: the first subslot carries the matrix, the rest are identities
+                    memcpy(mo, m, 64); for (int i = 1; i < 5; ++i) memcpy(mo + 8 * i, I8, 64);
+                    continue;
+                }
+                double piece[5][8];
+                for (int side = 0; side < 2; ++side) {          // f[0] = right phase, f[2] = left phase
+                    const double* d = f[side == 0 ? 0 : 2];
+                    double h[8] = { 1, 0, 0, 0, 0, 0, 1, 0 };
+                    unit_sqrt(d[0], d[1], h[0], h[1]); unit_sqrt(d[6], d[7], h[6], h[7]);
+                    memcpy(piece[side == 0 ? 0 : 3], h, 64); memcpy(piece[side == 0 ? 1 : 4], h, 64);
+                }
+                memcpy(piece[2], f[1], 64);
+                for (int i = 0; i < 5; ++i) {
+                    memcpy(mo + 8 * i, piece[i], 64);
+                    LiftCoef L; const int k = lift_classify(piece[i], L);
+                    // an identity piece classifies as PHASE with zero shears; a rotation by exactly 0 is diagonal -> PHASE too
+                    if (k != sm.kind[sm.first[s] + i] || (L.mk[0] | L.mk[1] | L.mk[2] | L.mk[3])) {
+                        if (i == 2 && k == LK_PHASE && !(L.mk[0] | L.mk[1] | L.mk[2] | L.mk[3])) { memset(&L, 0, sizeof(L)); }  // identity rotation: zero shears
+                        else ok = false;
+                    }
+                    memcpy(lo + 8 * i, &L, 64);
+                }
             }
-        }
+        thread_ok[t] = ok ? 1 : 0;
+    });
+    bool all_liftable = true;
+    for (char c : thread_ok) all_liftable = all_liftable && c;
     if (!all_liftable) for (size_t i = 0; i < sm.kind.size(); ++i) sm.kind[i] = LK_NONE;
-    const size_t bytes = mats.size() * sizeof(double);
     QM_TRY(ENSURE_DEV(st, d_slots, 2 * bytes));
-    // pageable host vectors: these copies return when the bytes have left the host buffers
-    CU(cudaMemcpyAsync(st->d_slots, mats.data(), bytes, cudaMemcpyHostToDevice, st->stream));
-    CU(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(st->d_slots) + bytes, lifts.data(), bytes, cudaMemcpyHostToDevice, st->stream));
-    CU(cudaStreamSynchronize(st->stream));
-    st->ctr.bytes_h2d += 2 * bytes;
+    // the TMA kernel reads only the lifting coefficients, the general kernel only the matrices: upload what will be read
+    const int tb = st->tile_bits ? st->tile_bits : 12;
+    const bool tma_path = all_liftable && st->pipeline && get_encode() && (tb == 11 || tb == 12) && st->nl >= tb && st->low_bits >= 3 &&
+                          st->fuse && (total_amps(st) >> 3) <= 0x7fffffffull;
+    if (!tma_path) {
+        CU(cudaMemcpyAsync(st->d_slots, mats, bytes, cudaMemcpyHostToDevice, st->stream));
+        st->ctr.bytes_h2d += bytes;
+    }
+    if (all_liftable) {
+        CU(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(st->d_slots) + bytes, lifts, bytes, cudaMemcpyHostToDevice, st->stream));
+        st->ctr.bytes_h2d += bytes;
+    }
+    CU(cudaEventRecord(st->ev_slots[half], st->stream));
     const int saved = st->pipeline;
     if (!all_liftable) st->pipeline = 0;
-    int rc = run_circuit(st, gates, ngates, st->d_slots, nsub, &sm, st->d_slots + mats.size());
+    int rc = run_circuit(st, gates, ngates, st->d_slots, nsub, &sm, st->d_slots + ndoubles);
     st->pipeline = saved;
     return rc;
 }

@@ -294,7 +294,7 @@ def test_sharded_two_gpus(pkg, n):
     assert all("GPU_DIST_OK" in o for o in outs), "\n".join(outs)
 
 
-@pytest.mark.timeout(300, method="thread")
+@pytest.mark.timeout(150, method="thread")
 @pytest.mark.parametrize("n,world,overlap", [(14, 2, 1), (23, 2, 1), (23, 2, 0), (21, 4, 1), (16, 4, 1)])
 def test_sharded_same_process_world(pkg, n, world, overlap):
     """The sharded path on ONE GPU: every rank is a host thread of this process with its own shard allocation, streams
@@ -308,7 +308,7 @@ def test_sharded_same_process_world(pkg, n, world, overlap):
     R = W.reference(pkg, n)
     L = pkg._lib
     res = pkg.dist.run_local_world(n, world, lambda r, st: W.check_sharded(pkg, st, r, world, R), m=R["m"],
-                                   options={L.OPT_OVERLAP: overlap}, timeout=240.0)
+                                   options={L.OPT_OVERLAP: overlap}, timeout=120.0)
     for r, out in enumerate(res):
         assert out["ok"], (r, out)
     g = world.bit_length() - 1
