@@ -66,9 +66,9 @@ enum {
     QM_OPT_MAX_COST   = 6,  /* planner: budget of a pass = gate costs (FP64 FMAs per amplitude + 1) + 18 per register-block group (planner.hpp gate_cost); default 80, 0 = no cap */
     QM_OPT_TIME_PASSES = 7, /* 1: CUDA events around every fused pass, read back with qm_pass_times (diagnostics) */
     QM_OPT_OVERLAP   = 9,   /* sharded registers: 1 (default) run the global<->local exchange slab by slab beside the passes before and after it, 0: exchange between passes */
-    QM_OPT_XSM       = 10,  /* ... SMs the overlapped exchange kernel claims (default 16; the passes beside it use the rest) */
+    QM_OPT_XSM       = 10,  /* ... SMs the overlapped exchange kernel claims (default 40: ~17 GB/s per SM per direction, the passes beside it use the rest) */
     QM_OPT_XUN       = 11,  /* ... amplitude pairs in flight per exchange thread: 4 (1024 threads per SM) or 8 (512, default) */
-    QM_OPT_SLAB_BITS = 12,  /* ... log2 of the number of slabs (1..3, default 2) */
+    QM_OPT_SLAB_BITS = 12,  /* ... log2 of the number of slabs (1..3, default 3) */
     QM_OPT_SHORT_PCT = 8    /* planner: a circuit shorter than the look-ahead window (a reservoir step before a readout) is planned at the multiple of the budget, up to this many per cent, that the pass model says finishes first; default 0 = no limit, 100 = off */
 };
 

@@ -520,7 +520,7 @@ int dist_slab_exchange(qm_state* st, const PassSlab& slab, uint32_t ep_pass, uin
     }
     SwapSlab ss; ss.nbits = slab.nbits; ss.value_or = slab.value_or;
     for (int i = 0; i < 3; ++i) ss.bit[i] = i < slab.nbits ? slab.bit[i] : 0;
-    const int ctas = st->xsm > 0 ? st->xsm : 16;
+    const int ctas = st->xsm > 0 ? st->xsm : 40;
     // one CTA per claimed SM: 512 threads with 8 (or 1024 with 4) amplitude pairs in flight each
     if (st->xun == 4) QM_TRY((launch_swap<4, 1024>(st, d->xstream, ctas, true, ss)));
     else QM_TRY((launch_swap<8, 512>(st, d->xstream, ctas, true, ss)));
