@@ -279,6 +279,7 @@ def main():
     ap.add_argument("--xsm", type=int, default=-1, help="sharded: SMs of the overlapped exchange kernel")
     ap.add_argument("--xun", type=int, default=-1, help="sharded: pairs in flight per exchange thread (4 or 8)")
     ap.add_argument("--slab-bits", type=int, default=-1, help="sharded: log2 of the number of slabs")
+    ap.add_argument("--overlap-depth", type=int, default=-1, help="sharded: passes in front of an exchange that run slab by slab beside it")
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c4"],
                     help="auto: C3 at N = 1, C4 at N > 1; c4 at N = 1 runs the 33-qubit weak-scaling base")
     args = ap.parse_args()

@@ -43,7 +43,8 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
                 torch.cuda.empty_cache()
             dist.barrier()
     st = pkg.B200State(n, 0) if single else pkg.dist.sharded_state(n, 0)
-    for key, name in ((L.OPT_OVERLAP, "overlap"), (L.OPT_XSM, "xsm"), (L.OPT_XUN, "xun"), (L.OPT_SLAB_BITS, "slab_bits")):
+    for key, name in ((L.OPT_OVERLAP, "overlap"), (L.OPT_XSM, "xsm"), (L.OPT_XUN, "xun"), (L.OPT_SLAB_BITS, "slab_bits"),
+                      (L.OPT_OVERLAP_DEPTH, "overlap_depth")):
         v = getattr(args, name, -1)
         if not single and v is not None and v >= 0:
             st.set_option(key, v)
@@ -134,6 +135,7 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
             "norm2": norm2, "norm2_ok": bool(abs(norm2 - 1.0) < 1e-12),
             "passes_per_step": npasses / args.steps,
             "overlapped_remaps_per_step": c.get("overlapped_remaps", 0) / args.steps,
+            "overlapped_passes_per_step": c.get("overlapped_passes", 0) / args.steps,
         }
         if parity is not None:
             line["parity"] = parity

@@ -68,6 +68,7 @@ enum {
     QM_OPT_OVERLAP   = 9,   /* sharded registers: 1 (default) run the global<->local exchange slab by slab beside the passes before and after it, 0: exchange between passes */
     QM_OPT_XSM       = 10,  /* ... SMs the overlapped exchange kernel claims (default 40: ~17 GB/s per SM per direction, the passes beside it use the rest) */
     QM_OPT_XUN       = 11,  /* ... amplitude pairs in flight per exchange thread: 4 (1024 threads per SM) or 8 (512, default) */
+    QM_OPT_OVERLAP_DEPTH = 13, /* ... how many of the last passes before an exchange run slab by slab in front of it (1..4, default 2) */
     QM_OPT_SLAB_BITS = 12,  /* ... log2 of the number of slabs (1..3, default 3) */
     QM_OPT_SHORT_PCT = 8    /* planner: a circuit shorter than the look-ahead window (a reservoir step before a readout) is planned at the multiple of the budget, up to this many per cent, that the pass model says finishes first; default 0 = no limit, 100 = off */
 };
@@ -96,6 +97,7 @@ typedef struct qm_counters_t {
     double   ms_plan;        /* host planning time of the last flushed circuit  */
     double   ms_remap;       /* CUDA-event time spent in global-qubit remaps (all-to-all) since reset */
     uint64_t overlapped_remaps; /* remaps that ran slab by slab beside the fused passes before and after them */
+    uint64_t overlapped_passes; /* fused passes that were cut into slabs to run beside an exchange */
 } qm_counters_t;
 
 /* ---- lifetime -------------------------------------------------------------------- */

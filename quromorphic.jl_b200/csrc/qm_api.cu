@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <chrono>
+#include <deque>
 #include <functional>
 #include <string>
 #include <thread>
@@ -169,6 +170,9 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
     case QM_OPT_XUN:
         if (value != 4 && value != 8) return set_err(QM_ERR_ARG, "pairs in flight per exchange thread: 4 or 8");
         st->xun = (int)value; break;
+    case QM_OPT_OVERLAP_DEPTH:
+        if (value < 1 || value > 4) return set_err(QM_ERR_ARG, "overlap depth must be in [1, 4]");
+        st->overlap_depth = (int)value; break;
     case QM_OPT_SLAB_BITS:
         if (value < 1 || value > 3) return set_err(QM_ERR_ARG, "slab bits must be in [1, 3]");
         st->slab_bits = (int)value; break;
@@ -478,13 +482,17 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     // lower-rank / higher-rank halves and the exchanged bits stay whole), at or above bit 12 (whole 64 KiB segments),
     // and outside the tiles of the pass before and the pass after the exchange.  Highest first: long contiguous runs.
     auto tile_has = [](const PlanPass& P, int b) { return b < P.L || std::find(P.hb.begin(), P.hb.end(), b) != P.hb.end(); };
-    auto choose_slab_bits = [&](const PlanPass& A, const PlanPass& B, std::vector<int>& bits) -> bool {
+    auto choose_slab_bits = [&](const std::vector<const PlanPass*>& tiles, std::vector<int>& bits) -> bool {
         bits.clear();
         const int want = st->slab_bits < 1 ? 1 : (st->slab_bits > 3 ? 3 : st->slab_bits);
-        for (int b = st->nl - st->g - 2; b >= 12 && (int)bits.size() < want; --b)
-            if (!tile_has(A, b) && !tile_has(B, b)) bits.push_back(b);
+        for (int b = st->nl - st->g - 2; b >= 12 && (int)bits.size() < want; --b) {
+            bool free_ = true;
+            for (const PlanPass* T : tiles) free_ = free_ && !tile_has(*T, b);
+            if (free_) bits.push_back(b);
+        }
         std::sort(bits.begin(), bits.end());
-        return !bits.empty();
+        // a pass over a slab must still find enough tiles for its grid; one slab bit less than asked for is accepted
+        return (int)bits.size() >= (want > 1 ? want - 1 : 1);
     };
 
     // Passes are launched as they are planned, ONE pass behind the planner: while the GPU runs pass i the host plans
@@ -492,43 +500,63 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     // sit in front of the first launch).  The look-ahead also tells a sharded register which pass is the last before
     // an exchange: that pass and the first one after it are cut into slabs and run beside the exchange of the
     // neighbouring slabs (dist.cu).
-    Item held, nxt;
-    bool have_held = false, seg_had_pass = false;
+    // `held`: the planned passes not launched yet, oldest first.  One for an ordinary register; a sharded register that can
+    // overlap keeps the last st->overlap_depth passes back, because ALL of them — not only the very last — can run slab by
+    // slab in front of the exchange (pass p + 1 on a slab only needs pass p on the same slab when the slab bits lie outside
+    // both tiles), which lets the exchange of slab 0 start one or two passes earlier.
+    const size_t hold_max = (st->g > 0 && tma && dist_can_overlap(st)) ? (size_t)(st->overlap_depth < 1 ? 1 : st->overlap_depth) : 1;
+    std::deque<Item> held;
+    Item nxt;
+    bool seg_had_pass = false;
+    auto launch_all_held = [&]() -> int {
+        while (!held.empty()) { QM_TRY(launch_full(held.front())); held.pop_front(); }
+        return QM_OK;
+    };
+    bool finished = false;
     for (int guard = 0; guard < 8 * ngates + 64; ++guard) {
         PlanPass P;
         if (plan_one(P)) {
             nxt.P = P;
             QM_TRY(prepare(nxt));
-            if (have_held) QM_TRY(launch_full(held));
-            std::swap(held, nxt); have_held = true; seg_had_pass = true;
+            held.push_back(nxt); seg_had_pass = true;
+            if (held.size() > hold_max) { QM_TRY(launch_full(held.front())); held.pop_front(); }
             continue;
         }
         bool leftover = false;
         for (size_t i = pl.first; i < pl.gates.size(); ++i) if (!pl.done[i]) { leftover = true; break; }
-        if (!leftover) { if (have_held) QM_TRY(launch_full(held)); have_held = false; break; }
+        if (!leftover) { QM_TRY(launch_all_held()); finished = true; break; }
         if (st->g == 0) return set_err(QM_ERR_STATE, "planner could not place a gate (internal error)");
         // sharded register: what is left needs a non-diagonal target on a global qubit.  Exchange the
         // global qubits with the top local ones (all-to-all over NVLink) and relabel the pending gates.
         if (!seg_had_pass && !pl.pending_global_target()) return set_err(QM_ERR_STATE, "planner stalled (internal error)");
         seg_had_pass = false;
-        const bool ov = have_held && held.kind == 0 && tma && dist_can_overlap(st);
+        bool ov = !held.empty() && tma && dist_can_overlap(st);
+        for (const Item& it : held) ov = ov && it.kind == 0;
         if (!ov) {
-            if (have_held) QM_TRY(launch_full(held));
-            have_held = false;
+            QM_TRY(launch_all_held());
             QM_TRY(dist_remap(st, &pl.gates, &pl.done));
             continue;
         }
-        // overlapped exchange: relabel first (host only), plan the first pass of the new layout, pick the slab bits
+        // overlapped exchange: relabel first (host only), plan the first pass of the new layout, pick the slab bits —
+        // outside the tiles of every held pass and of the new one; if there are too few such bits, the oldest held pass
+        // is launched whole and the choice is made again with one pass less
         dist_relabel(st, &pl.gates, &pl.done);
         PlanPass P2;
         const bool got2 = plan_one(P2);
         if (got2) { nxt.P = P2; QM_TRY(prepare(nxt)); seg_had_pass = true; }
         std::vector<int> sb;
-        if (!got2 || nxt.kind != 0 || !choose_slab_bits(held.P, nxt.P, sb)) {
-            QM_TRY(launch_full(held));
-            have_held = false;
+        bool ok = got2 && nxt.kind == 0;
+        while (ok) {
+            std::vector<const PlanPass*> tiles; for (const Item& it : held) tiles.push_back(&it.P);
+            tiles.push_back(&nxt.P);
+            if (choose_slab_bits(tiles, sb)) break;
+            if (held.size() <= 1) { ok = false; break; }
+            QM_TRY(launch_full(held.front())); held.pop_front();
+        }
+        if (!ok) {
+            QM_TRY(launch_all_held());
             QM_TRY(dist_exchange_now(st));
-            if (got2) { std::swap(held, nxt); have_held = true; }
+            if (got2) held.push_back(nxt);
             continue;
         }
         if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
@@ -543,7 +571,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             for (size_t i = 0; i < sb.size(); ++i) { S.bit[i] = sb[i]; if ((h >> i) & 1) S.value_or |= 1ull << sb[i]; }
         }
         for (int h = 0; h < ns; ++h) {
-            QM_TRY(launch_pass_v4(st, held.prog, held.P, d_slots_lift, nslots, &slabs[h], st->stream));
+            for (Item& it : held) QM_TRY(launch_pass_v4(st, it.prog, it.P, d_slots_lift, nslots, &slabs[h], st->stream));
             QM_TRY(dist_slab_pass_done(st, slabs[h], ep_pass));
         }
         for (int h = 0; h < ns; ++h) QM_TRY(dist_slab_exchange(st, slabs[h], ep_pass, ep_exch, h == 0, h == ns - 1));
@@ -552,9 +580,10 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             QM_TRY(launch_pass_v4(st, nxt.prog, nxt.P, d_slots_lift, nslots, &slabs[h], st->stream));
         }
         st->ctr.overlapped_remaps++;
-        have_held = false;
+        st->ctr.overlapped_passes += held.size() + 1;
+        held.clear();
     }
-    if (have_held) return set_err(QM_ERR_STATE, "planner did not terminate (internal error)");
+    if (!finished) return set_err(QM_ERR_STATE, "planner did not terminate (internal error)");
     if (cacheable && !hit) {
         qm_state::CachedPlan c; c.key[0] = key[0]; c.key[1] = key[1]; c.key[2] = key[2]; c.passes.swap(fresh);
         st->plan_cache.insert(st->plan_cache.begin(), std::move(c));
