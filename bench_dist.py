@@ -26,7 +26,7 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
     n = args.qubits or (SHARD_QUBITS + g)
     parity, base = None, None
     if not single:
-        parity = dist_parity(pkg, rank, world, g)
+        parity = dist_parity(pkg, rank, world, g, args)
         # the weak-scaling base of this line: the same reservoir step on ONE GPU (2^33 amplitudes, no exchange), timed
         # by rank 0 on its own GPU right here, in the same run, while the other ranks wait
         if n == SHARD_QUBITS + g and not getattr(args, "no_alt", False):
@@ -159,7 +159,7 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
     return line if rank == 0 else None
 
 
-def dist_parity(pkg, rank, world, g):
+def dist_parity(pkg, rank, world, g, args=None):
     """Before anything is timed: a (21+g)-qubit register sharded over the same ranks runs a 260-gate random circuit
     (several global<->local exchanges, the overlapped path included) and every collective readout — amplitudes, <Z>
     with and without the threshold, X/Y/Z marginals of local and global qubits, both reduced densities, the seeded
@@ -178,6 +178,12 @@ def dist_parity(pkg, rank, world, g):
     n = 21 + g
     R = W.reference(pkg, n)
     st = pkg.dist.sharded_state(n, R["m"])
+    L = pkg._lib
+    for key, name in ((L.OPT_OVERLAP, "overlap"), (L.OPT_XSM, "xsm"), (L.OPT_XUN, "xun"), (L.OPT_SLAB_BITS, "slab_bits"),
+                      (L.OPT_OVERLAP_DEPTH, "overlap_depth")):        # the exchange settings under test are the ones checked
+        v = getattr(args, name, -1) if args is not None else -1
+        if v is not None and v >= 0:
+            st.set_option(key, v)
     out = W.check_sharded(pkg, st, rank, world, R)
     dist.barrier()                       # nobody frees a shard another rank may still be writing flags into
     st.close()
