@@ -184,62 +184,6 @@ k_remap_swap(double2* __restrict__ mine, const __grid_constant__ PeerPtrs peers,
     }
 }
 
-// The same exchange with twice the remote bytes in flight per thread: the kernel above holds its own and the peer's 16 bytes
-// of UN pairs in registers while the remote loads (~3.6 us over NVSwitch) are out, so half of the register file waits for
-// local loads that take a fraction of that.  Here a thread first issues UN = 16 REMOTE loads (256 bytes in flight, 64
-// registers), and only when they are back loads its own amplitudes four at a time and stores crosswise; addresses are
-// recomputed instead of kept.  128 KB of remote loads in flight per SM instead of 64 KB.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-k_remap_swap_deep(double2* __restrict__ mine, const __grid_constant__ PeerPtrs peers, int rank, int world, unsigned long long chunk,
-                  const __grid_constant__ SwapSlab slab) {
-    constexpr int UN = 16;
-    const unsigned long long half = chunk >> 1;
-    const int seg_log2 = half < 4096ull ? (63 - __clzll((long long)half)) : 12;
-    const unsigned long long seg_mask = (1ull << seg_log2) - 1ull;
-    const unsigned long long total = (half >> slab.nbits) * (unsigned long long)(world - 1);
-    const unsigned long long stride = (unsigned long long)gridDim.x * THREADS;
-    const uint32_t wm1 = (uint32_t)(world - 1);
-    auto locate = [&](unsigned long long q, double2*& mp, double2*& pp) {
-        const uint32_t sg = (uint32_t)(q >> seg_log2);
-        const uint32_t sgq = sg / wm1, k = sg - sgq * wm1;
-        unsigned long long o = ((unsigned long long)sgq << seg_log2) | (q & seg_mask);
-        for (int s = 0; s < slab.nbits; ++s) {
-            const unsigned long long lo = o & ((1ull << slab.bit[s]) - 1ull);
-            o = ((o >> slab.bit[s]) << (slab.bit[s] + 1)) | lo;
-        }
-        o |= slab.value_or;
-        int j = rank + 1 + (int)k; if (j >= world) j -= world;
-        const unsigned long long off = (rank < j ? 0ull : half) + o;
-        mp = mine + ((unsigned long long)j * chunk + off); pp = peers.p[j] + ((unsigned long long)rank * chunk + off);
-    };
-    for (unsigned long long i = (unsigned long long)blockIdx.x * THREADS + threadIdx.x; i < total; i += UN * stride) {
-        double2 b[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const unsigned long long ii = i + (unsigned long long)u * stride;
-            double2 *mp, *pp;
-            locate(ii < total ? ii : 0, mp, pp);
-            if (ii < total) b[u] = *pp;
-        }
-#pragma unroll
-        for (int u0 = 0; u0 < UN; u0 += 4) {
-            double2 a[4]; double2 *mp[4], *pp[4];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const unsigned long long ii = i + (unsigned long long)(u0 + v) * stride;
-                locate(ii < total ? ii : 0, mp[v], pp[v]);
-                if (ii < total) a[v] = *mp[v];
-            }
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const unsigned long long ii = i + (unsigned long long)(u0 + v) * stride;
-                if (ii < total) { *mp[v] = b[u0 + v]; *pp[v] = a[v]; }
-            }
-        }
-    }
-}
-
 // A same-process world whose ranks all sit on ONE device runs every rank on one shared, in-order stream.  Flags and
 // stream waits between streams of the same device are ordering the CUDA scheduler cannot see (it may park the kernel that
 // posts a flag behind the stream that waits for it), so there the ordering is made of what it does see: stream order,
@@ -577,19 +521,10 @@ int dist_slab_exchange(qm_state* st, const PassSlab& slab, uint32_t ep_pass, uin
     SwapSlab ss; ss.nbits = slab.nbits; ss.value_or = slab.value_or;
     for (int i = 0; i < 3; ++i) ss.bit[i] = i < slab.nbits ? slab.bit[i] : 0;
     const int ctas = st->xsm > 0 ? st->xsm : 40;
-    // one CTA per claimed SM: 512 threads with 8 (or 1024 with 4) amplitude pairs in flight each, or the deep variant
-    if (st->xun == 16) {
-        PeerPtrs pp; for (int j = 0; j < 16; ++j) pp.p[j] = d->peer[j];
-        static bool attr16[64] = { false };
-        if (st->device < 0 || st->device >= 64 || !attr16[st->device]) {
-            CU(cudaFuncSetAttribute(k_remap_swap_deep<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwapSmem));
-            if (st->device >= 0 && st->device < 64) attr16[st->device] = true;
-        }
-        k_remap_swap_deep<384><<<ctas, 384, kSwapSmem, d->xstream>>>(st->amp, pp, st->rank, st->world, 1ull << (st->nl - st->g), ss);
-        CU(cudaGetLastError());
-        st->ctr.launches++;
-    }
-    else if (st->xun == 4) QM_TRY((launch_swap<4, 1024>(st, d->xstream, ctas, true, ss)));
+    // one CTA per claimed SM: 512 threads with 8 (or 1024 with 4) amplitude pairs in flight each.  (A variant that first
+    // issues 16 remote loads per thread and fetches its own amplitudes only when they are back — 96 KB instead of 64 KB of
+    // remote loads in flight per SM — was measured and dropped: 372 against 478 GB/s at 40 SMs, profiles/r2k_*.)
+    if (st->xun == 4) QM_TRY((launch_swap<4, 1024>(st, d->xstream, ctas, true, ss)));
     else QM_TRY((launch_swap<8, 512>(st, d->xstream, ctas, true, ss)));
     if (last) CU(cudaEventRecord(st->remap_events.back().second, d->xstream));
     return signal_all(st, d->xstream, FK_EXCH, slab.index, ep_exch);

@@ -168,7 +168,7 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
         if (value < 1 || value > 64) return set_err(QM_ERR_ARG, "exchange SMs must be in [1, 64]");
         st->xsm = (int)value; break;
     case QM_OPT_XUN:
-        if (value != 4 && value != 8 && value != 16) return set_err(QM_ERR_ARG, "pairs in flight per exchange thread: 4, 8 or 16");
+        if (value != 4 && value != 8) return set_err(QM_ERR_ARG, "pairs in flight per exchange thread: 4 or 8");
         st->xun = (int)value; break;
     case QM_OPT_OVERLAP_DEPTH:
         if (value < 1 || value > 4) return set_err(QM_ERR_ARG, "overlap depth must be in [1, 4]");

@@ -318,6 +318,22 @@ def test_sharded_same_process_world(pkg, n, world, overlap):
         assert all(out["overlapped_remaps"] == 0 for out in res), res
 
 
+@pytest.mark.timeout(150, method="thread")
+@pytest.mark.parametrize("xun,slab_bits,depth", [(4, 1, 1), (8, 3, 3), (8, 2, 4), (4, 3, 2)])
+def test_sharded_exchange_kernel_variants(pkg, xun, slab_bits, depth):
+    """every variant of the overlapped exchange (pairs in flight per thread 4 / 8, 2 / 4 / 8 slabs, 1-4 passes in front of the exchange) on a same-process world, against the oracle"""
+    import gpu_dist_worker as W
+    n, world = 23, 2
+    R = W.reference(pkg, n, seed_base=4300)
+    L = pkg._lib
+    res = pkg.dist.run_local_world(n, world, lambda r, st: W.check_sharded(pkg, st, r, world, R), m=R["m"],
+                                   options={L.OPT_XUN: xun, L.OPT_SLAB_BITS: slab_bits, L.OPT_OVERLAP_DEPTH: depth, L.OPT_XSM: 24},
+                                   timeout=120.0)
+    for r, out in enumerate(res):
+        assert out["ok"], (r, out)
+    assert all(out["overlapped_remaps"] > 0 for out in res), res
+
+
 def test_c2_batched_full_size_4096_registers_of_16_qubits(pkg):
     """config C2 at BASELINE.json's size: 4096 independent 16-qubit registers (4 GiB) evolved in lockstep with
     per-state encodings.  A sample of registers is checked against the per-state oracle, all of them through
