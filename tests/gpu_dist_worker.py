@@ -1,6 +1,6 @@
 """GPU check of the sharded engine: gates, remaps (overlapped with the passes when the plan allows) and every collective
 readout must match the single-process oracle.  check_sharded() is the body; it runs
-  * one process per GPU (spawned by tests/test_gpu_parity.py::test_sharded_two_gpus, torchrun-style environment), and
+  * one process per GPU (spawned by tests/test_gpu_parity.py::test_sharded_two_ranks, torchrun-style environment), and
   * all ranks as threads of one process on ONE GPU (tests/test_gpu_parity.py::test_sharded_same_process_world), and
   * as the parity block of bench_dist.py at every N."""
 import os

@@ -21,23 +21,32 @@ def test_measures_of_many_matrices_match_host_qinfo(pkg, d):
     QI = pkg.qinfo
     rng = np.random.default_rng(100 + d)
     count = 257
-    rhos = np.array([random_density(rng, d, rank=(None if i % 3 else max(1, d // 2))) for i in range(count)])
+    full = np.array([random_density(rng, d) for _ in range(count)])
+    defic = np.array([random_density(rng, d, rank=max(1, d // 2)) for _ in range(count)])       # rank-deficient: zero eigenvalues
     sigmas = np.array([random_density(rng, d) for _ in range(count)])
-    ev = QI.eigvalsh_batch(rhos)
-    assert np.max(np.abs(ev - np.array([np.linalg.eigvalsh(r) for r in rhos]))) < 1e-12
-    for name, dev, host in (("von_neumann", QI.von_neumann_entropy_batch(rhos), [QI.von_neumann_entropy(r) for r in rhos]),
-                            ("renyi 2", QI.renyi_entropy_batch(rhos, 2.0), [QI.renyi_entropy(r, 2.0) for r in rhos]),
-                            ("renyi 0.5", QI.renyi_entropy_batch(rhos, 0.5), [QI.renyi_entropy(r, 0.5) for r in rhos]),
-                            ("renyi 3", QI.renyi_entropy_batch(rhos, 3.0), [QI.renyi_entropy(r, 3.0) for r in rhos]),
-                            ("min", QI.min_entropy_batch(rhos), [QI.min_entropy(r) for r in rhos]),
-                            ("trace_distance", QI.trace_distance_batch(rhos, sigmas), [QI.trace_distance(r, s) for r, s in zip(rhos, sigmas)]),
-                            ("fidelity", QI.fidelity_batch(rhos, sigmas), [QI.fidelity(r, s) for r, s in zip(rhos, sigmas)])):
-        assert np.max(np.abs(dev - np.array(host))) < 1e-9, name
-    # max_entropy counts eigenvalues above 1e-10: compare on the full-rank and clearly rank-deficient cases
-    assert np.array_equal(QI.max_entropy_batch(rhos), np.array([QI.max_entropy(r) for r in rhos]))
+    for rhos in (full, defic):
+        ev = QI.eigvalsh_batch(rhos)
+        assert np.max(np.abs(ev - np.array([np.linalg.eigvalsh(r) for r in rhos]))) < 1e-12
+
+    def check(name, dev, host, tol=1e-9):
+        assert np.max(np.abs(dev - np.array(host))) < tol, name
+    for tag, rhos in (("full rank", full), ("rank-deficient", defic)):
+        check(tag + " von_neumann", QI.von_neumann_entropy_batch(rhos), [QI.von_neumann_entropy(r) for r in rhos])
+        check(tag + " renyi 2", QI.renyi_entropy_batch(rhos, 2.0), [QI.renyi_entropy(r, 2.0) for r in rhos])
+        check(tag + " renyi 3", QI.renyi_entropy_batch(rhos, 3.0), [QI.renyi_entropy(r, 3.0) for r in rhos])
+        check(tag + " min", QI.min_entropy_batch(rhos), [QI.min_entropy(r) for r in rhos])
+        check(tag + " trace_distance", QI.trace_distance_batch(rhos, sigmas), [QI.trace_distance(r, s) for r, s in zip(rhos, sigmas)])
+    # measures that take a root of the eigenvalues are only conditioned to ~sqrt(eps) = 1e-8 where eigenvalues vanish (a zero
+    # eigenvalue comes out as +-1e-17 from any solver, and its square root is 3e-9): 1e-9 on full-rank matrices, 1e-6 otherwise
+    for tag, rhos, tol in (("full rank", full, 1e-9), ("rank-deficient", defic, 1e-6)):
+        check(tag + " renyi 0.5", QI.renyi_entropy_batch(rhos, 0.5), [QI.renyi_entropy(r, 0.5) for r in rhos], tol)
+        check(tag + " fidelity", QI.fidelity_batch(rhos, sigmas), [QI.fidelity(r, s) for r, s in zip(rhos, sigmas)], tol)
+    # max_entropy counts eigenvalues above 1e-10: exact on full-rank matrices; on rank-deficient ones the count must be the rank
+    assert np.array_equal(QI.max_entropy_batch(full), np.array([QI.max_entropy(r) for r in full]))
+    assert np.array_equal(QI.max_entropy_batch(defic), np.full(count, np.log2(max(1, d // 2))))
     # fidelity of a state with itself, trace distance to itself
-    assert np.max(np.abs(QI.fidelity_batch(rhos, rhos) - 1.0)) < 1e-9
-    assert np.max(np.abs(QI.trace_distance_batch(rhos, rhos))) < 1e-12
+    assert np.max(np.abs(QI.fidelity_batch(full, full) - 1.0)) < 1e-9
+    assert np.max(np.abs(QI.trace_distance_batch(full, full))) < 1e-12
 
 
 def test_quantum_mutual_information_batch(pkg):
