@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define QM_ABI_VERSION 2
+#define QM_ABI_VERSION 3
 
 /* status codes */
 enum {
@@ -70,6 +70,7 @@ enum {
     QM_OPT_XUN       = 11,  /* ... amplitude pairs in flight per exchange thread: 4 (1024 threads per SM) or 8 (512, default) */
     QM_OPT_OVERLAP_DEPTH = 13, /* ... how many of the last passes before an exchange run slab by slab in front of it (1..4, default 2) */
     QM_OPT_SLAB_BITS = 12,  /* ... log2 of the number of slabs (1..3, default 3) */
+    QM_OPT_JIT       = 14,  /* compiled pass kernels: a fused pass whose opcode sequence (gate kinds, sign variants, register-block positions) has been seen this many times is compiled into straight-line code and launched instead of the interpreter; default 2 (the second time a circuit of the same structure runs), 1 = at first sight, 0 = never */
     QM_OPT_SHORT_PCT = 8    /* planner: a circuit shorter than the look-ahead window (a reservoir step before a readout) is planned at the multiple of the budget, up to this many per cent, that the pass model says finishes first; default 0 = no limit, 100 = off */
 };
 
@@ -98,6 +99,7 @@ typedef struct qm_counters_t {
     double   ms_remap;       /* CUDA-event time spent in global-qubit remaps (all-to-all) since reset */
     uint64_t overlapped_remaps; /* remaps that ran slab by slab beside the fused passes before and after them */
     uint64_t overlapped_passes; /* fused passes that were cut into slabs to run beside an exchange */
+    uint64_t compiled_passes;   /* fused passes that ran as compiled straight-line kernels (QM_OPT_JIT) instead of the interpreter */
 } qm_counters_t;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -253,6 +255,14 @@ int32_t qm_last_error(char* buf, int32_t cap);
 int32_t qm_counters(qm_state* st, qm_counters_t* out);
 int32_t qm_counters_reset(qm_state* st);
 int32_t qm_abi_version(void);
+/* compiled pass kernels, process-wide: out = {compiled, failed, kernels in the cache, backend (1 nvJitLink, 2 driver PTX
+ * compiler, 0 none yet)}; *compile_ms = wall time spent compiling so far */
+int32_t qm_jit_stats(uint64_t out[4], double* compile_ms);
+/* host-only check of the compiled pass kernels (no GPU needed): every 2^12-tile pass of the planned circuit is turned into PTX
+ * text and, with compile != 0 and libnvJitLink present, assembled for sm_100a.  out = {passes, passes with PTX text, passes
+ * assembled, distinct opcode sequences, bytes of the largest cubin}; ptx_out (optional) receives the text of the first pass */
+int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_cost, const qm_gate* gates, int32_t ngates,
+                     int32_t compile, int64_t out[5], char* ptx_out, int64_t ptx_cap);
 /* diagnostics (QM_OPT_TIME_PASSES): per fused pass since the last call, 8 floats {ms, groups, gates, planner cost,
  * records with full FP64 cost, with a control in the register block (half cost), xor exchanges, thread-constant phases};
  * *n_passes receives the number of passes timed, at most cap_passes are written */

@@ -18,7 +18,7 @@ QM_OK, QM_ERR_ARG, QM_ERR_CUDA, QM_ERR_NOMEM, QM_ERR_NO_DEVICE, QM_ERR_STATE, QM
 GATE_U2, GATE_CU2, GATE_SWAP, GATE_U2_SLOT = 0, 1, 2, 3
 BASIS_Z, BASIS_X, BASIS_Y = 0, 1, 2
 OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_TRACE, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = range(9)
-OPT_OVERLAP, OPT_XSM, OPT_XUN, OPT_SLAB_BITS, OPT_OVERLAP_DEPTH = 9, 10, 11, 12, 13
+OPT_OVERLAP, OPT_XSM, OPT_XUN, OPT_SLAB_BITS, OPT_OVERLAP_DEPTH, OPT_JIT = 9, 10, 11, 12, 13, 14
 
 GATE_DTYPE = np.dtype([("kind", np.int32), ("q0", np.int32), ("q1", np.int32), ("flags", np.int32),
                        ("m", np.float64, (8,))])
@@ -29,7 +29,8 @@ class Counters(C.Structure):
     _fields_ = [("gates", C.c_uint64), ("passes", C.c_uint64), ("launches", C.c_uint64),
                 ("bytes_hbm", C.c_uint64), ("bytes_link", C.c_uint64), ("bytes_h2d", C.c_uint64),
                 ("bytes_d2h", C.c_uint64), ("ms_device", C.c_double),
-                ("ms_plan", C.c_double), ("ms_remap", C.c_double), ("overlapped_remaps", C.c_uint64), ("overlapped_passes", C.c_uint64)]
+                ("ms_plan", C.c_double), ("ms_remap", C.c_double), ("overlapped_remaps", C.c_uint64), ("overlapped_passes", C.c_uint64),
+                ("compiled_passes", C.c_uint64)]
 
 
 class QMError(RuntimeError):
@@ -89,6 +90,8 @@ SIGNATURES = {
     "qm_last_error": (C.c_int32, [C.c_char_p, C.c_int32]),
     "qm_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),
     "qm_counters_reset": (C.c_int32, [_vp]),
+    "qm_jit_stats": (C.c_int32, [C.POINTER(C.c_uint64), _dp]),
+    "qm_jit_check": (C.c_int32, [C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_char_p, C.c_int64]),
     "qm_abi_version": (C.c_int32, []),
     "qm_device_ptr": (C.c_int32, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
 }
@@ -174,6 +177,26 @@ def plan_describe(n, gates, global_bits=0, tile_bits=12, low_bits=5, max_cost=0.
             i += 2 + nrb
         steps.append({"ngates": ng, "m": m, "L": L, "hb": hb, "groups": groups})
     return steps
+
+
+def jit_check(n, gates, low_bits=5, max_cost=0.0, compile=True, want_ptx=False):
+    """host-only: {passes, with_ptx, assembled, distinct, max_cubin_bytes} (+ the PTX text of the first pass) for the compiled
+    pass kernels of this circuit"""
+    out = (C.c_int64 * 5)()
+    buf = C.create_string_buffer(4 << 20) if want_ptx else None
+    check(lib().qm_jit_check(n, low_bits, max_cost, gates.ctypes.data, len(gates), 1 if compile else 0, out, buf, (4 << 20) if want_ptx else 0))
+    d = dict(zip(("passes", "with_ptx", "assembled", "distinct", "max_cubin_bytes"), list(out)))
+    if want_ptx:
+        d["ptx"] = buf.value.decode()
+    return d
+
+
+def jit_stats():
+    out = (C.c_uint64 * 4)()
+    ms = C.c_double()
+    check(lib().qm_jit_stats(out, C.byref(ms)))
+    return {"compiled": out[0], "failed": out[1], "cached": out[2], "backend": {0: "none", 1: "nvJitLink", 2: "driver"}[int(out[3])],
+            "compile_ms": ms.value}
 
 
 def plan_ophist(n, gates, tile_bits=12, low_bits=5, max_cost=0.0):

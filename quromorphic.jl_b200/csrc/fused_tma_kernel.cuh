@@ -73,7 +73,12 @@ __device__ __forceinline__ uint32_t ldp32(uint64_t pa) {
 #define TMA_COORDS(b) const int tr_ = (int)((b) >> 3), tc1 = lp.rowdim == 1 ? tr_ : 0, tc2 = lp.rowdim == 2 ? tr_ : 0, \
                       tc3 = lp.rowdim == 3 ? tr_ : 0, tc4 = lp.rowdim == 4 ? tr_ : 0
 
-template <int M, int TEAMS, int STAGES>
+// JIT = true: the same kernel with the interpreter cut out.  The register-block group is an EMPTY inline-PTX block between two
+// marker comments; the build turns this instantiation into PTX text (fused_jit.cu -> jit_template_m*.inc) and at run time the
+// engine splices straight-line code generated for one pass program between the markers (jit.cpp) and hands the text to the
+// driver's PTX compiler.  The records never go to shared memory: the generated code reads its coefficients from the
+// kernel-parameter bank at fixed offsets.
+template <int M, int TEAMS, int STAGES, bool JIT = false>
 __global__ void __launch_bounds__(TEAMS * (1 << (M - 4)) + kV4ProducerThreads, 1)
 k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4Program P, const double* __restrict__ slots,
             const V4Launch lp) {
@@ -111,7 +116,7 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
         for (int i = tid; i < nl; i += NCOMP + kV4ProducerThreads) dst[i] = ldp32(pa + offsetof(V4Program, lane_tab) + 4u * i);
         for (int i = tid; i < nw; i += NCOMP + kV4ProducerThreads) dst[kV4MaxGroups * 16 + i] = ldp32(pa + offsetof(V4Program, warp_tab) + 4u * i);
     }
-    {   // gate records -> shared memory (the interpreter reads them with 16-byte broadcasts)
+    if (!JIT) {   // gate records -> shared memory (the interpreter reads them with 16-byte broadcasts)
         uint64_t* dst = reinterpret_cast<uint64_t*>(recs);
         const int n8 = P.nrecs * 8;
         for (int i = tid; i < n8; i += NCOMP + kV4ProducerThreads) dst[i] = ldp64(pa + offsetof(V4Program, recs) + 8u * i);
@@ -230,6 +235,13 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
             const uint32_t b0 = (v ^ ((v >> 3) & 7u)) << 4;
             const uint32_t ctx = v | octx;
             uint32_t rp = smem_u32(recs) + (gw - (uint32_t)offsetof(V4Program, recs));
+            if (JIT)
+                asm volatile("// QMJIT_BEGIN %0 %1 %2 %3 %4 %5 %6 %7 %8 %9\n\t// QMJIT_END\n\t"
+                             : "+r"(rp)
+                             : "r"(ctx), "r"(slot_s), "r"(tile_s), "r"(b0), "r"((uint32_t)g01), "r"((uint32_t)(g01 >> 32)),
+                               "r"((uint32_t)g23), "r"((uint32_t)(g23 >> 32)), "r"(gi)
+                             : "memory");
+            else
             asm volatile(V4_GROUP_PTX
                          : "+r"(rp)
                          : "r"(ctx), "r"(slot_s), "r"(tile_s), "r"(b0), "r"((uint32_t)g01), "r"((uint32_t)(g01 >> 32)),

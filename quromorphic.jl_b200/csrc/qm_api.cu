@@ -15,6 +15,8 @@
 #include "../../include/qm_b200.h"
 #include "dist.hpp"
 #include "encode_v4.hpp"
+#include "jit.hpp"
+#include "jit_codegen.hpp"
 #include "fused_tma.cuh"
 #include "kernels.cuh"
 #include "lifting.hpp"
@@ -179,8 +181,19 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
     case QM_OPT_SHORT_PCT:
         if (value != 0 && value < 100) return set_err(QM_ERR_ARG, "short-circuit per cent must be 0 (no limit) or >= 100");
         st->short_mult = value == 0 ? 1e9 : (double)value / 100.0; break;
+    case QM_OPT_JIT:
+        if (value < 0 || value > 1000000) return set_err(QM_ERR_ARG, "jit threshold must be >= 0");
+        st->jit = (int)value; break;
     default: return set_err(QM_ERR_ARG, "unknown option %d", key);
     }
+    return QM_OK;
+}
+
+extern "C" int32_t qm_jit_stats(uint64_t out[4], double* compile_ms) {
+    if (!out) return set_err(QM_ERR_ARG, "null argument");
+    const JitStats s = jit_stats();
+    out[0] = s.compiled; out[1] = s.failed; out[2] = s.cached; out[3] = (uint64_t)s.backend;
+    if (compile_ms) *compile_ms = s.compile_ms;
     return QM_OK;
 }
 
@@ -195,7 +208,7 @@ extern "C" int32_t qm_num_qubits(const qm_state* st, int32_t* n, int32_t* batch)
 // gate execution
 // ---------------------------------------------------------------------------------------------
 int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const double* d_slots, int nslots,
-                   const PassSlab* slab, cudaStream_t stream);
+                   const PassSlab* slab, cudaStream_t stream, JitKernel* jk = nullptr);
 
 static int launch_1q(qm_state* st, int tbit, int cbit, const double* m) {
     // physical bits; control on a sharded bit is a rank predicate, target must be local
@@ -270,7 +283,7 @@ static bool v4_eligible(const qm_state* st, const PlanPass& P) {
 // slab->bit[] have the values in slab->value_or (sharded registers: the exchange of one slab runs beside the passes
 // of its neighbours, dist.cu), on a grid of slab->sm_cap CTAs.
 int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const double* d_slots, int nslots,
-                   const PassSlab* slab, cudaStream_t stream) {
+                   const PassSlab* slab, cudaStream_t stream, JitKernel* jk) {
     // tensor map: dim0 = one 128-byte row (8 amplitudes = 16 doubles); dim1 = row index over the whole
     // array (the box takes 2^(L-3) consecutive rows at the tile's base); dims 2..4 = the runs of high
     // tile bits (size 2^len, stride 16 * 2^start bytes), unused dims have size 1.
@@ -318,7 +331,9 @@ int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const
     for (int i = 0; i < kV4Gaps; ++i) { lp.gap_start[i] = i < (int)gaps.size() ? gaps[i].first : 0; lp.gap_len[i] = i < (int)gaps.size() ? gaps[i].second : 0; }
     lp.rank_or = st->g ? ((uint64_t)st->rank << st->nl) : 0; lp.nslots = nslots;
     lp.trace = st->trace_buf;
-    if (P.m == 11) QM_TRY(launch_v4_m11(stream, st->sms, tm, prog, d_slots, lp));
+    // a pass program whose opcode sequence has been compiled (jit.hpp) runs as straight-line code; otherwise the interpreter
+    if (jk) { QM_TRY(jit_launch(jk, stream, st->sms, P.m, tm, prog, d_slots, lp)); st->ctr.compiled_passes += (!slab || slab->index == 0); }
+    else if (P.m == 11) QM_TRY(launch_v4_m11(stream, st->sms, tm, prog, d_slots, lp));
     else QM_TRY(launch_v4_m12(stream, st->sms, tm, prog, d_slots, lp));
     // the program crosses the host link with the launch: counted as host->device bytes
     st->ctr.bytes_h2d += offsetof(V4Program, recs) + (size_t)prog.nrecs * sizeof(V4Rec);
@@ -420,11 +435,37 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     };
     // A planned pass ready to launch: the TMA kernel's program (a launch parameter), the general kernel's blob, or —
     // when the encoder refuses a pass the planner built for the TMA kernel — its gates one by one (kind 2)
-    struct Item { PlanPass P; int kind = 0; V4Program prog; std::vector<unsigned char> blob; };
+    struct Item { PlanPass P; int kind = 0; V4Program prog; std::vector<unsigned char> blob; JitKernel* jk = nullptr; };
+    // Compiled pass kernels (jit.hpp).  A replayed plan knows all its passes in advance: they are encoded once up front and the
+    // opcode sequences that have been seen often enough are compiled together on several host threads (a deep circuit has
+    // hundreds of passes, ~0.25 s of PTX compilation each); otherwise a pass asks for its kernel when it is prepared.
+    std::vector<JitKernel*> pre_jit;
+    if (hit && tma && st->jit > 0) {
+        std::vector<V4Program> progs(hit->passes.size());
+        std::vector<const V4Program*> ptrs; std::vector<size_t> which;
+        for (size_t r = 0; r < hit->passes.size(); ++r) {
+            PlanPass P = hit->passes[r].first;
+            const std::vector<int>& idx = hit->passes[r].second;
+            size_t j = 0;
+            for (PlanGroup& G : P.groups) for (LGate& x : G.subs) x = pl.gates[idx[j++]];
+            if (v4_eligible(st, P) && encode_v4(P, progs[r]) && P.m == 12) { ptrs.push_back(&progs[r]); which.push_back(r); }
+        }
+        std::vector<JitKernel*> got;
+        jit_get_many(st->device, 12, ptrs, st->jit, got);
+        pre_jit.assign(hit->passes.size(), nullptr);
+        for (size_t i = 0; i < which.size(); ++i) pre_jit[which[i]] = got[i];
+    }
     auto prepare = [&](Item& it) -> int {
-        it.kind = 1; it.blob.clear();
+        it.kind = 1; it.blob.clear(); it.jk = nullptr;
         if (tma) {
-            if (v4_eligible(st, it.P) && encode_v4(it.P, it.prog)) { it.kind = 0; return QM_OK; }
+            if (v4_eligible(st, it.P) && encode_v4(it.P, it.prog)) {
+                it.kind = 0;
+                if (st->jit > 0) {
+                    if (!pre_jit.empty()) it.jk = replay_i >= 1 && replay_i <= pre_jit.size() ? pre_jit[replay_i - 1] : nullptr;
+                    else it.jk = jit_get(st->device, it.P.m, it.prog, st->jit);
+                }
+                return QM_OK;
+            }
             // The planner is supposed to respect the kernel's limits; if a pass slips through, it is still applied
             // (one unfused launch per gate) rather than dropped with the queue already swapped out.
             for (const PlanGroup& G : it.P.groups)
@@ -441,7 +482,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
         cudaEvent_t ea = nullptr, eb = nullptr;
         if (st->time_passes) { CU(cudaEventCreate(&ea)); CU(cudaEventCreate(&eb)); CU(cudaEventRecord(ea, st->stream)); }
-        if (it.kind == 0) QM_TRY(launch_pass_v4(st, it.prog, it.P, d_slots_lift, nslots, nullptr, st->stream));
+        if (it.kind == 0) QM_TRY(launch_pass_v4(st, it.prog, it.P, d_slots_lift, nslots, nullptr, st->stream, it.jk));
         else if (it.kind == 2) {
             for (const PlanGroup& G : it.P.groups) for (const LGate& x : G.subs) QM_TRY(launch_1q(st, x.target, x.ctrl, x.m));
             st->ctr.passes++;
@@ -571,13 +612,13 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             for (size_t i = 0; i < sb.size(); ++i) { S.bit[i] = sb[i]; if ((h >> i) & 1) S.value_or |= 1ull << sb[i]; }
         }
         for (int h = 0; h < ns; ++h) {
-            for (Item& it : held) QM_TRY(launch_pass_v4(st, it.prog, it.P, d_slots_lift, nslots, &slabs[h], st->stream));
+            for (Item& it : held) QM_TRY(launch_pass_v4(st, it.prog, it.P, d_slots_lift, nslots, &slabs[h], st->stream, it.jk));
             QM_TRY(dist_slab_pass_done(st, slabs[h], ep_pass));
         }
         for (int h = 0; h < ns; ++h) QM_TRY(dist_slab_exchange(st, slabs[h], ep_pass, ep_exch, h == 0, h == ns - 1));
         for (int h = 0; h < ns; ++h) {
             QM_TRY(dist_slab_wait_exchanged(st, slabs[h], ep_exch));
-            QM_TRY(launch_pass_v4(st, nxt.prog, nxt.P, d_slots_lift, nslots, &slabs[h], st->stream));
+            QM_TRY(launch_pass_v4(st, nxt.prog, nxt.P, d_slots_lift, nslots, &slabs[h], st->stream, nxt.jk));
         }
         st->ctr.overlapped_remaps++;
         st->ctr.overlapped_passes += held.size() + 1;
@@ -1468,6 +1509,46 @@ extern "C" int32_t qm_plan_ophist(int32_t n_qubits, int32_t tile_bits, int32_t l
             else if (op < (uint32_t)V4_OP_THR) hist[3]++;
             else if (op < (uint32_t)V4_NUM_GATE_OPS) hist[4]++;
             else if (op == (uint32_t)V4_OP_SLOT) hist[5]++;
+        }
+    }
+    return QM_OK;
+}
+
+// Host-only introspection of the compiled pass kernels (no GPU needed: the PTX text is generated and, when libnvJitLink is
+// present, assembled into a cubin for sm_100a): plans and encodes `gates` as for the TMA kernel and puts every pass of tile
+// size 2^12 through jit_ptx_for / jit_compile_cubin.  out = {passes, passes with PTX text, passes compiled to a cubin,
+// distinct opcode sequences, bytes of the largest cubin}; ptx_out (optional) receives the text of the first pass.
+extern "C" int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_cost, const qm_gate* gates, int32_t ngates,
+                                int32_t compile, int64_t out[5], char* ptx_out, int64_t ptx_cap) {
+    if (!gates || !out || n_qubits < 12) return set_err(QM_ERR_ARG, "bad argument");
+    Planner pl;
+    pl.opt.n_local = n_qubits; pl.opt.n_global = 0;
+    pl.opt.tile_bits = 12; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
+    if (max_cost > 0) pl.opt.max_cost = max_cost;
+    v4_planner_options(pl.opt, max_cost);
+    int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
+    if (rc) return set_err(rc, "bad gate");
+    prepare_for_lifting(pl.gates);
+    pl.done.assign(pl.gates.size(), 0);
+    for (int i = 0; i < 5; ++i) out[i] = 0;
+    std::vector<V4Program> prog(1);
+    std::vector<std::vector<uint32_t>> seen;
+    PlanPass P;
+    while (pl.next_pass(P)) {
+        choose_tile_layout(P);
+        if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass cannot be encoded");
+        out[0]++;
+        std::string ptx;
+        if (!jit_ptx_for(P.m, prog[0], ptx)) continue;
+        if (out[1] == 0 && ptx_out && ptx_cap > 0) snprintf(ptx_out, (size_t)ptx_cap, "%s", ptx.c_str());
+        out[1]++;
+        std::vector<uint32_t> sig; jit_structure_bytes(prog[0], P.m, sig);
+        if (std::find(seen.begin(), seen.end(), sig) == seen.end()) { seen.push_back(sig); out[3]++; }
+        if (compile) {
+            std::vector<char> cubin; std::string log;
+            if (!jit_compile_cubin(ptx, cubin, log)) return set_err(QM_ERR_STATE, "pass %lld does not assemble: %s", (long long)out[0] - 1, log.c_str());
+            out[2]++;
+            if ((int64_t)cubin.size() > out[4]) out[4] = (int64_t)cubin.size();
         }
     }
     return QM_OK;

@@ -23,3 +23,14 @@ def pkg():
     """the product package (directory `quromorphic.jl_b200/`, importable name quromorphic_jl_b200)"""
     import __graft_entry__ as ge
     return ge.load_package()
+
+
+@pytest.fixture(params=["records", "compiled_ptx"])
+def emu_mode(request):
+    """the host emulation of the fused-pass programs runs twice: over the encoded records (what the interpreter kernel reads)
+    and over the straight-line PTX text generated for the compiled pass kernels (csrc/jit_codegen.hpp, executed by the
+    PTX-subset interpreter of tests/native/ptx_interp.hpp)"""
+    import emu
+    emu.set_jit(request.param == "compiled_ptx")
+    yield request.param
+    emu.set_jit(0)

@@ -24,6 +24,8 @@ def lib():
         l.qm_plan_emulate_sharded.restype = C.c_int32
         l.qm_plan_emulate_sharded.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32, _dp,
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        l.qm_emu_set_jit.restype = C.c_int32
+        l.qm_emu_set_jit.argtypes = [C.c_int32]
         _lib = l
     return _lib
 
@@ -52,3 +54,9 @@ def plan_emulate_sharded(n, global_bits, gates, psi, tile_bits=12, low_bits=5, m
     _check(lib().qm_plan_emulate_sharded(n, global_bits, tile_bits, low_bits, max_cost, gates.ctypes.data, len(gates),
                                          out.ctypes.data_as(_dp), C.byref(npass), C.byref(nrem)))
     return out, npass.value, nrem.value
+
+
+def set_jit(on):
+    """0: walk the encoded records (the interpreter kernel's view); 1: execute the straight-line PTX text generated for the
+    compiled pass kernels (csrc/jit_codegen.hpp) with the PTX-subset interpreter of tests/native/ptx_interp.hpp"""
+    _check(lib().qm_emu_set_jit(1 if on else 0))

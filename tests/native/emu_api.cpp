@@ -8,9 +8,20 @@
 
 #include "../../include/qm_b200.h"
 #include "emulate.hpp"
+#include "ptx_interp.hpp"
 #include "../../quromorphic.jl_b200/csrc/dist_bits.hpp"
 
 using namespace qm;
+
+// 0: walk the encoded records (what the interpreter kernel does); 1: generate the straight-line PTX text of the compiled pass
+// kernels (csrc/jit_codegen.hpp) and execute THAT with the PTX-subset interpreter of ptx_interp.hpp
+static int g_jit_mode = 0;
+extern "C" int32_t qm_emu_set_jit(int32_t on) { g_jit_mode = on ? 1 : 0; return QM_OK; }
+static bool run_program(const V4Program& prog, const PlanPass& P, EmuAmp* amp, int nl, uint64_t rank_or, std::string& why) {
+    why.clear();
+    if (!g_jit_mode) { if (!emulate_v4(prog, P, amp, nl, rank_or, nullptr)) { why = "malformed program (opcode / non-uniform control predicate)"; return false; } return true; }
+    return emulate_v4_jit(prog, P, amp, nl, rank_or, nullptr, &why);
+}
 
 static thread_local char g_err[512] = "";
 static int set_err(int code, const char* fmt, ...) {
@@ -45,8 +56,9 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     while (pl.next_pass(P)) {
         choose_tile_layout(P);
         if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
-        if (!emulate_v4(prog[0], P, reinterpret_cast<EmuAmp*>(state), n_qubits, 0, nullptr))
-            return set_err(QM_ERR_STATE, "pass %d: malformed program (opcode / non-uniform control predicate)", np);
+        std::string why;
+        if (!run_program(prog[0], P, reinterpret_cast<EmuAmp*>(state), n_qubits, 0, why))
+            return set_err(QM_ERR_STATE, "pass %d: %s", np, why.c_str());
         ++np;
     }
     for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) return set_err(QM_ERR_STATE, "planner left a gate behind");
@@ -86,9 +98,11 @@ extern "C" int32_t qm_plan_emulate_sharded(int32_t n_qubits, int32_t global_bits
         while (pl.next_pass(P)) {
             choose_tile_layout(P);
             if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
-            for (int r = 0; r < W; ++r)
-                if (!emulate_v4(prog[0], P, amp + (uint64_t)r * shard, nl, (uint64_t)r << nl, nullptr))
-                    return set_err(QM_ERR_STATE, "pass %d, rank %d: malformed program (opcode / non-uniform control predicate)", np, r);
+            for (int r = 0; r < W; ++r) {
+                std::string why;
+                if (!run_program(prog[0], P, amp + (uint64_t)r * shard, nl, (uint64_t)r << nl, why))
+                    return set_err(QM_ERR_STATE, "pass %d, rank %d: %s", np, r, why.c_str());
+            }
             ++np;
         }
         bool left = false;

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for s in syms:
         assert hasattr(lib, s), s
         assert s in pkg._lib.SIGNATURES, "ctypes signature missing for " + s
-    assert lib.qm_abi_version() == 2
+    assert lib.qm_abi_version() == 3
 
 
 def test_gate_struct_layout(pkg):
@@ -128,7 +128,7 @@ def test_planner_leaves_global_targets_for_remap(pkg):
                                                   (14, 12, 8, 32.0, 5), (15, 11, 4, 40.0, 6), (16, 12, 6, 96.0, 7),
                                                   (16, 12, 5, 86.0, 8), (16, 11, 5, 86.0, 9), (15, 12, 5, 120.0, 10),
                                                   (16, 11, 5, 250.0, 11), (14, 11, 3, 60.0, 12), (16, 12, 7, 180.0, 13)])
-def test_encoded_pass_programs_emulated_on_cpu(pkg, n, tile, low, cost, seed):
+def test_encoded_pass_programs_emulated_on_cpu(pkg, emu_mode, n, tile, low, cost, seed):
     """planner + encoder of the TMA kernel, checked without a GPU: the encoded pass programs (the bytes the kernel
     is launched with) are walked over a host vector by the scalar emulation in csrc/emulate.hpp (test
     infrastructure) and must reproduce the oracle; a control predicate that is not warp-uniform, an unknown opcode
@@ -141,7 +141,7 @@ def test_encoded_pass_programs_emulated_on_cpu(pkg, n, tile, low, cost, seed):
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
 
 
-def test_encoded_c3_programs_emulated_on_cpu(pkg):
+def test_encoded_c3_programs_emulated_on_cpu(pkg, emu_mode):
     n = 16
     gates = pkg.circuits.c3_circuit(n=n, depth=8)
     for tile, cost in ((12, 0.0), (11, 24.0), (12, 48.0), (12, 86.0), (11, 86.0), (12, 130.0), (11, 250.0)):
@@ -227,7 +227,7 @@ def test_default_budget_packs_one_full_group_per_pass_on_c3(pkg):
     assert len(deep) < len(plan) / 3
 
 
-def test_short_circuit_is_planned_at_the_budget_that_finishes_first(pkg):
+def test_short_circuit_is_planned_at_the_budget_that_finishes_first(pkg, emu_mode):
     """A reservoir step (C4: 2-3 gates per qubit, then a readout) cannot fill one register block per pass; a circuit
     shorter than the look-ahead window is planned at the multiple of the budget the pass model says finishes first
     (planner.hpp budget_for_pending): the 33-qubit step must come out in <= 5 passes instead of 10-11 and the batched
@@ -251,7 +251,7 @@ def test_short_circuit_is_planned_at_the_budget_that_finishes_first(pkg):
 
 
 @pytest.mark.parametrize("n,depth,cost", [(14, 52, 80.0), (13, 60, 60.0), (15, 40, 110.0), (14, 56, 75.0)])
-def test_deep_circuit_programs_emulated_on_cpu(pkg, n, depth, cost):
+def test_deep_circuit_programs_emulated_on_cpu(pkg, emu_mode, n, depth, cost):
     """circuits longer than the planner's look-ahead (768 gates) keep the budget as it is — the C3 headline path:
     single-block passes filled to the budget.  Encoded programs walked by the host emulator against the oracle."""
     gates = pkg.circuits.c3_circuit(n=n, depth=depth, seed=3001 + n)
@@ -267,7 +267,7 @@ def test_deep_circuit_programs_emulated_on_cpu(pkg, n, depth, cost):
 
 @pytest.mark.parametrize("n,seed,perm_only", [(12, 1, True), (13, 2, True), (14, 3, False), (12, 4, False), (15, 5, False),
                                               (13, 6, True), (16, 7, False)])
-def test_permutation_tails_folded_into_the_stores_are_exact(pkg, n, seed, perm_only):
+def test_permutation_tails_folded_into_the_stores_are_exact(pkg, emu_mode, n, seed, perm_only):
     """x!/cnot!/swap!-heavy circuits: groups end in permutation tails that encode_v4 folds into the END record's store
     offsets instead of executing them.  Pure permutation circuits must stay bit for bit (np.array_equal), mixed ones
     within 1e-12; short chunks applied one after the other so that many groups END in such a tail."""
@@ -296,3 +296,27 @@ def test_permutation_tails_folded_into_the_stores_are_exact(pkg, n, seed, perm_o
             assert np.array_equal(psi, ref), (chunk, npass)
         else:
             assert np.max(np.abs(psi - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
+def test_compiled_pass_kernels_generate_and_assemble_for_sm_100a(pkg):
+    """the compiled pass kernels (QM_OPT_JIT) without a GPU: every pass of a planned circuit becomes PTX text (the JIT
+    template embedded in the library + the straight-line register-block groups of csrc/jit_codegen.hpp) and, where
+    libnvJitLink is installed, assembles into an sm_100a cubin.  (What the text COMPUTES is checked by the
+    `compiled_ptx` mode of the emulator tests above.)"""
+    L = pkg._lib
+    for n, cost, seed in ((14, 80.0, 1), (16, 0.0, 2), (13, 24.0, 3)):
+        gates = random_circuit(pkg, n, 200, 600 + seed)
+        d = L.jit_check(n, gates, max_cost=cost, compile=False, want_ptx=True)
+        assert d["passes"] == d["with_ptx"] > 0 and d["distinct"] > 0
+        ptx = d["ptx"]
+        assert "// QMJIT_BEGIN" in ptx and "// QMJIT_END" in ptx and ".target sm_100a" in ptx
+        body = ptx[ptx.index("// QMJIT_BEGIN"):ptx.index("// QMJIT_END")]
+        assert body.count("ld.shared.v2.f64") % 16 == 0 and body.count("st.shared.v2.f64") == body.count("ld.shared.v2.f64")
+        assert "brx.idx" not in body                       # no dispatch: that is the point
+        try:
+            d2 = L.jit_check(n, gates, max_cost=cost, compile=True)
+        except L.QMError as e:
+            if "libnvJitLink not found" in str(e):
+                pytest.skip("libnvJitLink is not installed here")
+            raise
+        assert d2["assembled"] == d2["passes"] and 10000 < d2["max_cubin_bytes"] < 400000

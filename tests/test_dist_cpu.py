@@ -41,7 +41,7 @@ import pytest
 
 @pytest.mark.parametrize("n,g,kind,seed", [(14, 1, "random", 1), (15, 2, "random", 2), (16, 3, "random", 3), (14, 2, "c4", 4),
                                            (15, 1, "c4", 5), (16, 2, "c3deep", 6), (15, 3, "perm", 7)])
-def test_sharded_encoded_programs_emulated_on_cpu(pkg, n, g, kind, seed):
+def test_sharded_encoded_programs_emulated_on_cpu(pkg, emu_mode, n, g, kind, seed):
     """every rank's ENCODED pass programs (the bytes the TMA kernel is launched with) walked on the host over the
     rank's shard — rank predicates for controls on global qubits, rank-dependent phases for diagonal targets on them,
     permutation tails folded into the stores, the short-circuit planner across exchanges — with the chunk exchange

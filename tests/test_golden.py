@@ -82,7 +82,7 @@ def test_c_oracle_reproduces_golden_vectors(case):
                lambda keep_low, k: O.reduced_density(np.ascontiguousarray(s), keep_low, k), LIT.von_neumann_entropy)
 
 
-def test_encoded_tma_programs_reproduce_the_12_qubit_golden_case(pkg):
+def test_encoded_tma_programs_reproduce_the_12_qubit_golden_case(pkg, emu_mode):
     """planner + encoder of the fused TMA kernel against the literal algorithm, without a GPU: the 12-qubit golden
     case as a wire-format gate list, walked by the host emulator of the encoded pass programs (csrc/emulate.hpp)"""
     case = next(c for c in CASES if c["n"] == 12)

@@ -1,0 +1,143 @@
+"""GPU parity tests of the COMPILED pass kernels (QM_OPT_JIT, csrc/jit.cu + jit_codegen.hpp): a fused pass whose opcode
+sequence repeats is compiled into straight-line code and launched instead of the interpreter.  Same bar as the interpreter:
+1e-12 against the CPU oracle, permutation circuits bit for bit; every test asserts that compiled kernels really ran
+(counters()["compiled_passes"]) and, where both exist, that the two paths agree to the last bit (same operation order)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from test_abi_cpu import random_circuit
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("n,cost,seed", [(12, 0, 1), (13, 80, 2), (14, 24, 3), (17, 80, 4), (20, 120, 5), (16, 250, 6), (22, 80, 7)])
+def test_compiled_passes_match_oracle_and_interpreter(pkg, n, cost, seed):
+    L = pkg._lib
+    gates = random_circuit(pkg, n, 300, 9100 + seed)
+    psi0 = O.random_state(n, 40 + seed)
+    ref = O.apply_circuit(psi0.copy(), gates)
+    out = {}
+    for jit in (0, 1):
+        st = pkg.B200State.from_numpy(psi0)
+        st.set_option(L.OPT_JIT, jit)
+        st.set_option(L.OPT_MAX_COST, cost)
+        st.apply_circuit(gates)
+        out[jit] = st.to_numpy()
+        c = st.counters()
+        assert (c["compiled_passes"] > 0) == (jit == 1), c
+        if jit:
+            assert c["compiled_passes"] == c["passes"], c
+        st.close()
+    assert rel_err(out[1], ref) < RTOL
+    assert np.array_equal(out[0], out[1])          # same shears in the same order: identical bits
+    s = L.jit_stats()
+    assert s["compiled"] > 0 and s["failed"] == 0, s
+
+
+def test_default_threshold_compiles_on_the_second_run_of_a_structure(pkg):
+    """QM_OPT_JIT default (2): the first circuit of a structure runs through the interpreter, the second one — same
+    structure, NEW angles — through compiled kernels (all its passes compiled together from the cached plan)"""
+    L = pkg._lib
+    n = 16
+    st = pkg.B200State(n, 0)
+    ref = O.statevector(n, 0)
+    rng = np.random.default_rng(3)
+    seen = []
+    for rep in range(3):
+        gl = pkg.circuits.GateList(n)
+        for q in range(1, n + 1):
+            gl.ry(q, float(rng.uniform(0, np.pi)))          # plain signs for every angle: one opcode sequence
+            gl.rx(q, 0.3 + 0.1 * q); gl.rz(q, 0.2 + 0.05 * q)
+        for q in range(1, n):
+            gl.cnot(q, q + 1)
+        g = gl.array()
+        st.apply_circuit(g)
+        ref = O.apply_circuit(ref, g)
+        seen.append(st.counters()["compiled_passes"])
+    assert seen[0] == 0 and seen[1] > 0 and seen[2] > seen[1], seen
+    assert rel_err(st.to_numpy(), ref) < RTOL
+
+
+@pytest.mark.parametrize("n,seed", [(12, 1), (14, 2), (17, 3)])
+def test_compiled_permutation_circuits_are_bit_exact(pkg, n, seed):
+    """x!/cnot!/swap! inside the register block are register renames in the compiled code, tails are folded into the stores"""
+    L = pkg._lib
+    rng = np.random.default_rng(700 + seed)
+    psi = O.random_state(n, seed)
+    st = pkg.B200State.from_numpy(psi)
+    st.set_option(L.OPT_JIT, 1)
+    ref = psi.copy()
+    for chunk in range(5):
+        gl = pkg.circuits.GateList(n)
+        for _ in range(int(rng.integers(10, 70))):
+            k = int(rng.integers(0, 6))
+            t, c = int(rng.integers(1, n + 1)), int(rng.integers(1, n + 1))
+            if k <= 1: gl.x(t)
+            elif k <= 4 and c != t: gl.cnot(c, t)
+            elif c != t: gl.swap(c, t)
+        g = gl.array()
+        if len(g) == 0:
+            continue
+        st.apply_circuit(g)
+        ref = O.apply_circuit(ref, g)
+    assert np.array_equal(st.to_numpy(), ref)
+    assert st.counters()["compiled_passes"] > 0
+
+
+def test_compiled_c3_layers_at_24_qubits(pkg):
+    L = pkg._lib
+    n = 24
+    gates = pkg.circuits.c3_circuit(n=n, depth=12)
+    st = pkg.B200State(n, 0)
+    st.set_option(L.OPT_JIT, 1)
+    st.apply_circuit(gates)
+    ref = O.apply_circuit(O.statevector(n, 0), gates)
+    assert rel_err(st.to_numpy(), ref) < RTOL
+    c = st.counters()
+    assert c["compiled_passes"] == c["passes"] > 0, c
+    z = st.expect_z_all()
+    assert np.max(np.abs(z - O.expect_z_all(ref, 1e-10))) < RTOL
+
+
+def test_compiled_batched_registers_with_per_state_slots(pkg):
+    """C2-shaped batched step (SLOT records: the coefficients of a gate come from the per-state table): three steps, the
+    second and third through compiled kernels (default threshold)"""
+    n, B, T = 12, 37, 3
+    C = pkg.circuits
+    gates = C.c2_step_gates(n, seed=1603)
+    w = [C.SplitMix64(5).uniform() for _ in range(n)]
+    st = pkg.B200State(n, 0, batch=B)
+    refs = [O.statevector(n, 0) for _ in range(B)]
+    for t in range(T):
+        enc = C.c2_encoding(B, n, t, w)
+        st.apply_batched(gates, enc)
+        for b in range(B):
+            g = gates.copy()
+            for i in range(len(g)):
+                if g[i]["kind"] == pkg._lib.GATE_U2_SLOT:
+                    g[i]["m"] = enc[b, g[i]["q1"]]; g[i]["kind"] = pkg._lib.GATE_U2; g[i]["q1"] = 0
+            O.apply_circuit(refs[b], g)
+    for b in (0, 17, B - 1):
+        assert rel_err(st.to_numpy(b), refs[b]) < RTOL
+    assert st.counters()["compiled_passes"] > 0
+
+
+@pytest.mark.timeout(150, method="thread")
+@pytest.mark.parametrize("n,world", [(23, 2), (21, 4)])
+def test_compiled_passes_on_a_sharded_register(pkg, n, world):
+    """sharded registers (same-process world on one GPU): rank predicates and rank-dependent phases are data of the launch,
+    slab launches beside the exchange use the same compiled kernel"""
+    import gpu_dist_worker as W
+    R = W.reference(pkg, n)
+    L = pkg._lib
+    res = pkg.dist.run_local_world(n, world, lambda r, st: W.check_sharded(pkg, st, r, world, R), m=R["m"],
+                                   options={L.OPT_JIT: 1}, timeout=120.0)
+    for r, out in enumerate(res):
+        assert out["ok"], (r, out)
+    assert L.jit_stats()["failed"] == 0

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--costs", default="0,32,64,128")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--pipes", default="1")
+    ap.add_argument("--jits", default="0", help="QM_OPT_JIT values: 0 interpreter, 1 compiled pass kernels (compiled in the first repetition)")
     ap.add_argument("--clocks", action="store_true", help="sample nvidia-smi clocks / power while a configuration runs")
     ap.add_argument("--reset", action="store_true", help="reset to |0..0> before every repetition")
     args = ap.parse_args()
@@ -29,10 +30,11 @@ def main():
     n = args.qubits
     gates = pkg.circuits.c3_circuit(n=n, depth=args.depth)
     st = pkg.B200State(n, 0)
-    for pipe, tile, low, cost in itertools.product([int(x) for x in args.pipes.split(",")],
+    for jit, pipe, tile, low, cost in itertools.product([int(x) for x in args.jits.split(",")], [int(x) for x in args.pipes.split(",")],
                                                    [int(x) for x in args.tiles.split(",")],
                                                    [int(x) for x in args.lows.split(",")],
                                                    [int(x) for x in args.costs.split(",")]):
+        st.set_option(L.OPT_JIT, jit)
         st.set_option(L.OPT_PIPELINE, pipe)
         st.set_option(L.OPT_TILE_BITS, tile)
         st.set_option(L.OPT_LOW_BITS, low)
@@ -55,7 +57,8 @@ def main():
         ms = best["ms_device"]
         per = ms / best["passes"]
         gbs = 32.0 * (1 << n) / (per * 1e-3) / 1e9
-        print(json.dumps({"pipe": pipe, "tile": tile, "low": low, "max_cost": cost, "passes": best["passes"], "ms_total": round(ms, 2),
+        js = L.jit_stats()
+        print(json.dumps({"jit": jit, "compiled_passes": best["compiled_passes"], "jit_compile_ms": round(js["compile_ms"], 1), "jit_backend": js["backend"], "pipe": pipe, "tile": tile, "low": low, "max_cost": cost, "passes": best["passes"], "ms_total": round(ms, 2),
                           "ms_per_pass": round(per, 3), "hbm_gbs": round(gbs, 1), "gates_per_s": round(len(gates) / ms * 1e3, 1),
                           "plan_ms": round(best["ms_plan"], 2), "sm_mhz": clk.get("sm_mhz"), "power_w": clk.get("power_w"),
                           "reasons": clk.get("reasons")}), flush=True)
