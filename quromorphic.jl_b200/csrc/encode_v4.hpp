@@ -14,11 +14,13 @@
 namespace qm {
 
 // the planner limits of the TMA kernel, in one place (engine, introspection and emulator must agree)
-inline void v4_planner_options(PlanOptions& o, double max_cost) {
+inline void v4_planner_options(PlanOptions& o, double max_cost, int cost_model = 0) {
     o.max_runs = 3; o.max_run_len = 8; o.max_subs = kV4MaxSubs; o.max_groups = kV4MaxGroups;
     o.max_outer = kV4MaxOuter; o.warp_uniform_ctrl = true; o.block_bits = kV4BlockBits;
-    o.group_cost = kV4GroupCost; o.retile = true;
-    if (max_cost > 0 && o.max_cost < kV4GroupCost + 5.0) o.max_cost = kV4GroupCost + 5.0;
+    o.cost_model = cost_model;
+    o.group_cost = cost_model == 1 ? kV4GroupCostCompiled : kV4GroupCost; o.retile = true;
+    if (cost_model == 1) { o.fixed_units = 24.0; o.hbm_units = 112.0; }
+    if (max_cost > 0 && o.max_cost < o.group_cost + 5.0) o.max_cost = o.group_cost + 5.0;
 }
 
 // decode op -> family (0 ROT, 1 ROTX, 2 PHASE, 3 PERMX, 4 THR), variant, B, CB

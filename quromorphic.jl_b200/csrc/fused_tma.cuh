@@ -61,6 +61,7 @@ static const int kV4MaxSubs = 96;
 // planner budget units (0.05 ms at 30 qubits) one register-block group costs on top of its gates, and the fixed cost
 // of a pass; see planner.hpp gate_cost for the fit
 static const double kV4GroupCost = 18.0;
+static const double kV4GroupCostCompiled = 29.0;     // the compiled pass kernels (jit.hpp): 1.45 ms per group against 0.11 ms per record
 
 struct V4Rec {              // 64 bytes, read by the PTX interpreter with shared-memory broadcasts
     uint32_t op;            // opcode

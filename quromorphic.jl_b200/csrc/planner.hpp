@@ -120,6 +120,7 @@ struct PlanOptions {
     double short_mult = 1e9;         // circuits shorter than the window may use up to short_mult x the budget (Planner::budget_for_pending)
     double hbm_units = 114.0;        // fitted pass model in budget units (0.05 ms at 30 qubits): HBM time of a pass,
     double fixed_units = 41.0;       // compute-side time = fixed_units + group_cost per group + gate costs
+    int cost_model = 0;              // gate_cost: 0 the interpreter kernel, 1 the compiled pass kernels
     bool warp_uniform_ctrl = false;  // controls inside the tile must be block bits or one of the (m - block_bits - 5) warp-index bits
 };
 
@@ -218,12 +219,18 @@ inline int lower_gates(const qm_gate* gates, int ng, int nbits, const int* perm,
 //     phase: 0.194 ms is the FP64 pipe at peak) + 0.091 per record whose control is a register-block bit
 //     + 0.136 per xor exchange (x!, cnot!) + 0.246 per thread-constant phase
 // against ~5.6 ms of HBM time.  A matrix that needs phase * rotation * phase is three records.
-inline double gate_cost(const LGate& g) {
+//
+// cost_model 1 — the COMPILED pass kernels (jit.hpp): no dispatch, no record fetch, x!/cnot! on register-block bits are register
+// renames.  Same fit on the compiled kernels (profiles/r3b_*: 192 passes at 30 qubits): pass ms = 1.2 + 1.45 per group + 0.037
+// per FP64 operation per amplitude — a full-cost record is 0.11 ms (2.3 units), a single group carries 22-24 of them inside the
+// 5.5 ms of HBM time, a second group costs as much as 13 records.
+inline double gate_cost(const LGate& g, int cost_model = 0) {
     const bool is_x = !g.diag && g.m[0] == 0 && g.m[1] == 0 && g.m[6] == 0 && g.m[7] == 0 && g.m[2] == 1 && g.m[3] == 0 &&
                       g.m[4] == 1 && g.m[5] == 0;
     const bool real_or_rx = (g.m[1] == 0 && g.m[7] == 0) && ((g.m[3] == 0 && g.m[5] == 0) || (g.m[2] == 0 && g.m[4] == 0));
-    if (is_x) return 2.7;
     const double records = (g.diag || real_or_rx || g.slot >= 0) ? 1.0 : 3.0;
+    if (cost_model == 1) return is_x ? 0.4 : records * (g.ctrl >= 0 ? 1.2 : 2.3);
+    if (is_x) return 2.7;
     return records * (g.ctrl >= 0 ? 2.5 : 4.6);
 }
 
@@ -235,7 +242,7 @@ inline double gate_cost(const LGate& g) {
 template <class Allowed>
 inline void pull(const std::vector<LGate>& g, const std::vector<char>& done, size_t first, int window,
                  uint64_t all_bits, double max_cost, int max_take, Allowed&& allowed, std::vector<int>& taken,
-                 uint64_t tile_mask = ~0ull, int max_outer = 64) {
+                 uint64_t tile_mask = ~0ull, int max_outer = 64, int cost_model = 0) {
     uint64_t blockedN = 0, blockedD = 0, outer_used = 0;
     int scanned = 0; double cost = 0;
     for (size_t i = first; i < g.size() && scanned < window; ++i) {
@@ -247,10 +254,10 @@ inline void pull(const std::vector<LGate>& g, const std::vector<char>& done, siz
         bool free_ = !((actsN | actsD) & blockedN) && !(actsN & blockedD);
         bool take = false;
         const uint64_t ob = (cm | (x.diag ? tm : 0ull)) & ~tile_mask;
-        if (free_ && (int)taken.size() < max_take && (taken.empty() || cost + gate_cost(x) <= max_cost) &&
+        if (free_ && (int)taken.size() < max_take && (taken.empty() || cost + gate_cost(x, cost_model) <= max_cost) &&
             __builtin_popcountll(outer_used | ob) <= max_outer)
             take = allowed(x);
-        if (take) { taken.push_back((int)i); cost += gate_cost(x); outer_used |= ob; }
+        if (take) { taken.push_back((int)i); cost += gate_cost(x, cost_model); outer_used |= ob; }
         else {
             blockedN |= actsN; blockedD |= actsD;
             if ((blockedN & all_bits) == all_bits) break;
@@ -286,7 +293,7 @@ struct Planner {
     int count_with(uint64_t tilemask) const {
         std::vector<int> taken;
         pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, opt.max_cost, opt.max_subs,
-             [&](const LGate& x) { return x.diag || ((tilemask >> x.target) & 1); }, taken, tilemask, opt.max_outer);
+             [&](const LGate& x) { return x.diag || ((tilemask >> x.target) & 1); }, taken, tilemask, opt.max_outer, opt.cost_model);
         return (int)taken.size();
     }
 
@@ -373,7 +380,7 @@ struct Planner {
             PlanGroup G; if (!x.diag) G.rb.push_back(x.target);
             if (opt.warp_uniform_ctrl && x.ctrl >= 0 && (x.ctrl < L || std::find(hb.begin(), hb.end(), x.ctrl) != hb.end()))
                 G.rb.push_back(x.ctrl);
-            G.subs.push_back(x); P.groups.push_back(G); P.ngates = 1; P.cost = gate_cost(x);
+            G.subs.push_back(x); P.groups.push_back(G); P.ngates = 1; P.cost = gate_cost(x, opt.cost_model);
             done[first] = 1;
             return true;
         }
@@ -522,7 +529,7 @@ struct Planner {
         while (true) {
             std::vector<int> taken;
             pull(gates, done, first, opt.window, (1ull << total_bits()) - 1, gate_budget, max_take,
-                 [&](const LGate& x) { return x.diag || ((tgt >> x.target) & 1); }, taken, tilemask, opt.max_outer);
+                 [&](const LGate& x) { return x.diag || ((tgt >> x.target) & 1); }, taken, tilemask, opt.max_outer, opt.cost_model);
             P = PlanPass(); P.m = m; P.L = L; P.hb = hb;
             std::vector<LGate> pg; pg.reserve(taken.size());
             for (int i : taken) pg.push_back(gates[i]);
@@ -570,12 +577,12 @@ struct Planner {
             double est = 0.0; size_t keep = 0;
             for (size_t g = 0; g < P.groups.size(); ++g) {
                 double gc = opt.group_cost;
-                for (const LGate& x : P.groups[g].subs) gc += gate_cost(x);
+                for (const LGate& x : P.groups[g].subs) gc += gate_cost(x, opt.cost_model);
                 if (g > 0 && est + gc > max_cost) break;
                 bool cut = false;
                 if (g == 0 && gc > max_cost) {
                     double c = opt.group_cost; size_t nk = 0;
-                    for (const LGate& x : P.groups[0].subs) { if (nk > 0 && c + gate_cost(x) > max_cost) break; c += gate_cost(x); ++nk; }
+                    for (const LGate& x : P.groups[0].subs) { if (nk > 0 && c + gate_cost(x, opt.cost_model) > max_cost) break; c += gate_cost(x, opt.cost_model); ++nk; }
                     P.groups[0].subs.resize(nk); gidx[0].resize(nk);
                     gc = c; cut = true;
                 }
@@ -585,7 +592,7 @@ struct Planner {
             P.groups.resize(keep); gidx.resize(keep);
             P.cost = 0.0; P.ngates = 0;
             for (size_t g = 0; g < keep; ++g)
-                for (size_t j = 0; j < gidx[g].size(); ++j) { taken_out.push_back(taken[gidx[g][j]]); P.cost += gate_cost(pg[gidx[g][j]]); ++P.ngates; }
+                for (size_t j = 0; j < gidx[g].size(); ++j) { taken_out.push_back(taken[gidx[g][j]]); P.cost += gate_cost(pg[gidx[g][j]], opt.cost_model); ++P.ngates; }
             break;
         }
     }

@@ -261,6 +261,15 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
+// Compiled pass kernels for this register?  QM_OPT_JIT 0: never; 1: every pass program, at first sight (tests, tools);
+// >= 2: an opcode sequence seen that many times — but only on registers whose pass is long enough for a compilation
+// (~0.25 s of one host core, 16 at a time) to pay for itself within a few hundred launches: 2^26 amplitudes and more
+// (a 1 GiB pass takes 0.36 ms; a 20-qubit reservoir step takes microseconds and would never earn it back).
+static int jit_threshold(const qm_state* st) {
+    if (st->jit <= 1) return st->jit;
+    return total_amps(st) >= (1ull << 26) ? st->jit : 0;
+}
+
 // can this pass go through the TMA kernel?
 static bool v4_eligible(const qm_state* st, const PlanPass& P) {
     if (!st->pipeline || !get_encode()) return false;
@@ -388,7 +397,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         if (tma) pl.gates.swap(lifted);
     }
     if (tma) {
-        v4_planner_options(pl.opt, st->max_cost);
+        v4_planner_options(pl.opt, st->max_cost, jit_threshold(st) > 0 ? 1 : 0);     // the planner prices gates for the kernel that will run them
         // every per-state gate takes two records (SLOT + gate); two records of slack for the encoder's END records
         if (smap) pl.opt.max_subs = (kV4MaxRecs - kV4MaxGroups) / 2 - 2;
     }
@@ -408,10 +417,10 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             h2 ^= v + 0x9e3779b97f4a7c15ull + (h2 << 6) + (h2 >> 2); h2 *= 0xff51afd7ed558ccdull; h2 ^= h2 >> 33;
         };
         mix((uint64_t)st->nl); mix((uint64_t)tile_bits); mix((uint64_t)st->low_bits); mix((uint64_t)(pl.opt.max_cost * 16));
-        mix((uint64_t)(pl.opt.short_mult > 1e8 ? -1 : pl.opt.short_mult * 100)); mix((uint64_t)pl.opt.max_subs);
+        mix((uint64_t)(pl.opt.short_mult > 1e8 ? -1 : pl.opt.short_mult * 100)); mix((uint64_t)pl.opt.max_subs); mix((uint64_t)pl.opt.cost_model);
         for (const LGate& x : pl.gates)
             mix((uint64_t)x.target | ((uint64_t)(x.ctrl + 1) << 8) | ((uint64_t)x.diag << 16) | ((uint64_t)(x.slot >= 0) << 17) |
-                ((uint64_t)(gate_cost(x) * 16.0) << 20));
+                ((uint64_t)(gate_cost(x, pl.opt.cost_model) * 16.0) << 20));
         key[0] = h1; key[1] = h2; key[2] = pl.gates.size();
         for (auto& c : st->plan_cache) if (c.key[0] == key[0] && c.key[1] == key[1] && c.key[2] == key[2]) { hit = &c; break; }
     }
@@ -440,7 +449,8 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     // opcode sequences that have been seen often enough are compiled together on several host threads (a deep circuit has
     // hundreds of passes, ~0.25 s of PTX compilation each); otherwise a pass asks for its kernel when it is prepared.
     std::vector<JitKernel*> pre_jit;
-    if (hit && tma && st->jit > 0) {
+    const int jit_thr = jit_threshold(st);
+    if (hit && tma && jit_thr > 0) {
         std::vector<V4Program> progs(hit->passes.size());
         std::vector<const V4Program*> ptrs; std::vector<size_t> which;
         for (size_t r = 0; r < hit->passes.size(); ++r) {
@@ -451,7 +461,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             if (v4_eligible(st, P) && encode_v4(P, progs[r]) && P.m == 12) { ptrs.push_back(&progs[r]); which.push_back(r); }
         }
         std::vector<JitKernel*> got;
-        jit_get_many(st->device, 12, ptrs, st->jit, got);
+        jit_get_many(st->device, 12, ptrs, jit_thr, got);
         pre_jit.assign(hit->passes.size(), nullptr);
         for (size_t i = 0; i < which.size(); ++i) pre_jit[which[i]] = got[i];
     }
@@ -460,9 +470,9 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         if (tma) {
             if (v4_eligible(st, it.P) && encode_v4(it.P, it.prog)) {
                 it.kind = 0;
-                if (st->jit > 0) {
+                if (jit_thr > 0) {
                     if (!pre_jit.empty()) it.jk = replay_i >= 1 && replay_i <= pre_jit.size() ? pre_jit[replay_i - 1] : nullptr;
-                    else it.jk = jit_get(st->device, it.P.m, it.prog, st->jit);
+                    else it.jk = jit_get(st->device, it.P.m, it.prog, jit_thr);
                 }
                 return QM_OK;
             }
@@ -1525,7 +1535,7 @@ extern "C" int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_c
     pl.opt.n_local = n_qubits; pl.opt.n_global = 0;
     pl.opt.tile_bits = 12; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
     if (max_cost > 0) pl.opt.max_cost = max_cost;
-    v4_planner_options(pl.opt, max_cost);
+    v4_planner_options(pl.opt, max_cost, 1);
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
     prepare_for_lifting(pl.gates);

@@ -16,6 +16,7 @@ using namespace qm;
 // 0: walk the encoded records (what the interpreter kernel does); 1: generate the straight-line PTX text of the compiled pass
 // kernels (csrc/jit_codegen.hpp) and execute THAT with the PTX-subset interpreter of ptx_interp.hpp
 static int g_jit_mode = 0;
+// in mode 1 the planner also prices gates as the engine does when the compiled kernels will run them (planner.hpp cost_model 1)
 extern "C" int32_t qm_emu_set_jit(int32_t on) { g_jit_mode = on ? 1 : 0; return QM_OK; }
 static bool run_program(const V4Program& prog, const PlanPass& P, EmuAmp* amp, int nl, uint64_t rank_or, std::string& why) {
     why.clear();
@@ -45,7 +46,7 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     pl.opt.n_local = n_qubits; pl.opt.n_global = 0;
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
     if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
-    v4_planner_options(pl.opt, max_cost);
+    v4_planner_options(pl.opt, max_cost, g_jit_mode);
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
     prepare_for_lifting(pl.gates);
@@ -77,7 +78,7 @@ extern "C" int32_t qm_plan_emulate_sharded(int32_t n_qubits, int32_t global_bits
     pl.opt.n_local = nl; pl.opt.n_global = g;
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
     if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
-    v4_planner_options(pl.opt, max_cost);
+    v4_planner_options(pl.opt, max_cost, g_jit_mode);
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");
     prepare_for_lifting(pl.gates);

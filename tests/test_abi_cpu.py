@@ -261,7 +261,10 @@ def test_deep_circuit_programs_emulated_on_cpu(pkg, emu_mode, n, depth, cost):
     psi0 = O.random_state(n, n)
     got, npass = emu.plan_emulate(n, gates, psi0, max_cost=cost)
     ref = O.apply_circuit(psi0.copy(), gates)
-    assert npass == len(plan)
+    if emu_mode == "records":
+        assert npass == len(plan)
+    else:                                 # the compiled kernels' cost model (planner.hpp cost_model 1): fewer, fuller passes
+        assert npass <= len(plan)
     assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
 
 

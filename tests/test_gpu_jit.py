@@ -42,10 +42,12 @@ def test_compiled_passes_match_oracle_and_interpreter(pkg, n, cost, seed):
 
 def test_default_threshold_compiles_on_the_second_run_of_a_structure(pkg):
     """QM_OPT_JIT default (2): the first circuit of a structure runs through the interpreter, the second one — same
-    structure, NEW angles — through compiled kernels (all its passes compiled together from the cached plan)"""
+    structure, NEW angles — through compiled kernels (all its passes compiled together from the cached plan).  The default
+    only applies to registers of 2^26 amplitudes and more (here 1024 registers of 16 qubits); a small register never compiles."""
     L = pkg._lib
     n = 16
-    st = pkg.B200State(n, 0)
+    small = pkg.B200State(n, 0)
+    st = pkg.B200State(n, 0, batch=1024)
     ref = O.statevector(n, 0)
     rng = np.random.default_rng(3)
     seen = []
@@ -53,15 +55,21 @@ def test_default_threshold_compiles_on_the_second_run_of_a_structure(pkg):
         gl = pkg.circuits.GateList(n)
         for q in range(1, n + 1):
             gl.ry(q, float(rng.uniform(0, np.pi)))          # plain signs for every angle: one opcode sequence
-            gl.rx(q, 0.3 + 0.1 * q); gl.rz(q, 0.2 + 0.05 * q)
+        for q in range(1, n):
+            gl.cnot(q, q + 1)
+        for q in range(1, n + 1):
+            gl.rx(q, 0.3 + 0.1 * q)                         # (not merged with the ry: the cnot chain sits between them)
         for q in range(1, n):
             gl.cnot(q, q + 1)
         g = gl.array()
         st.apply_circuit(g)
+        small.apply_circuit(g)
         ref = O.apply_circuit(ref, g)
         seen.append(st.counters()["compiled_passes"])
     assert seen[0] == 0 and seen[1] > 0 and seen[2] > seen[1], seen
-    assert rel_err(st.to_numpy(), ref) < RTOL
+    for b in (0, 513, 1023):
+        assert rel_err(st.to_numpy(b), ref) < RTOL
+    assert rel_err(small.to_numpy(), ref) < RTOL and small.counters()["compiled_passes"] == 0
 
 
 @pytest.mark.parametrize("n,seed", [(12, 1), (14, 2), (17, 3)])
@@ -107,12 +115,13 @@ def test_compiled_c3_layers_at_24_qubits(pkg):
 
 def test_compiled_batched_registers_with_per_state_slots(pkg):
     """C2-shaped batched step (SLOT records: the coefficients of a gate come from the per-state table): three steps, the
-    second and third through compiled kernels (default threshold)"""
+    all through compiled kernels"""
     n, B, T = 12, 37, 3
     C = pkg.circuits
     gates = C.c2_step_gates(n, seed=1603)
     w = [C.SplitMix64(5).uniform() for _ in range(n)]
     st = pkg.B200State(n, 0, batch=B)
+    st.set_option(pkg._lib.OPT_JIT, 1)
     refs = [O.statevector(n, 0) for _ in range(B)]
     for t in range(T):
         enc = C.c2_encoding(B, n, t, w)

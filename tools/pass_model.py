@@ -18,11 +18,14 @@ def main():
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--depth", type=int, default=30)
     ap.add_argument("--costs", default="32,48,64")
+    ap.add_argument("--jit", type=int, default=0, help="QM_OPT_JIT (1: compiled pass kernels)")
+    ap.add_argument("--dump", default="", help="write the raw rows [budget, ms, groups, gates, planner cost, full, half, xor, thr] here (.npy)")
     a = ap.parse_args()
     pkg = ge.load_package()
     L = pkg._lib
     gates = pkg.circuits.c3_circuit(n=a.qubits, depth=a.depth)
     st = pkg.B200State(a.qubits, 0)
+    st.set_option(L.OPT_JIT, a.jit)
     st.apply_circuit(gates); st.sync()                # dense state
     st.set_option(L.OPT_TIME_PASSES, 1)
     allrows = []
@@ -32,6 +35,9 @@ def main():
         st.apply_circuit(gates)
         t = st.pass_times()
         allrows.append(t.astype(np.float64))
+        if a.dump:
+            np.save(a.dump, np.concatenate([np.concatenate([np.full((len(r), 1), float(c)), r], axis=1)
+                                            for c, r in zip([int(x) for x in a.costs.split(",")], allrows)]))
         ms, groups, ng, pc = t[:, 0], t[:, 1], t[:, 2], t[:, 3]
         A = np.stack([np.ones_like(ms), groups, pc - ng], axis=1)      # ms ~ c0 + c1 groups + c2 (FP64 ops per amplitude)
         coef, *_ = np.linalg.lstsq(A, ms, rcond=None)
