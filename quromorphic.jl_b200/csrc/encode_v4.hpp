@@ -51,7 +51,17 @@ inline int hb_runs(const std::vector<int>& hb, int start[8], int len[8]) {
 // PlanPass -> V4Program (layout in fused_tma.cuh).  Returns false when the pass breaks a limit of the
 // kernel that the planner is supposed to respect (context bits, warp-uniform controls); the caller then
 // falls back to the general kernel.
-inline bool encode_v4(const PlanPass& P, V4Program& out) {
+//
+// gph (optional, {re, im}, multiplied in place): DIAGONAL GATES IN "D1" FORM.  An uncontrolled diagonal gate diag(d0, d1)
+// (rz, z, the phase factors of a general unitary) equals d0 * diag(1, d1 / d0): the scalar d0 is a GLOBAL phase of the
+// register — it is multiplied into *gph and never touches an amplitude (the engine applies the accumulated phase when
+// somebody reads amplitudes, qm_api.cu materialize_phase; probabilities, expectations, reduced densities and samples do not
+// depend on it) — and diag(1, r) only rotates the amplitudes whose target bit is set: HALF the FP64 work of the gate
+// (1.5 operations per amplitude instead of 3; rz is a third of the one-qubit gates of config C3 and of every reservoir
+// layer).  The form is used when the target is a register-block bit (a PHASE record "controlled" by the target bit itself)
+// or a bit that is uniform over a warp (outside the tile or on the warp index: the thread-constant phase entered through
+// its controlled entry, so half of the warps skip the record); on a lane bit the gate keeps both coefficient sets.
+inline bool encode_v4(const PlanPass& P, V4Program& out, double* gph = nullptr) {
     memset(&out, 0, offsetof(V4Program, recs));
     out.ngroups = (int)P.groups.size();
     int outer_of[64]; for (int i = 0; i < 64; ++i) outer_of[i] = -1;
@@ -96,6 +106,8 @@ inline bool encode_v4(const PlanPass& P, V4Program& out) {
         for (int b = 0; b < P.m; ++b) if (!((used >> b) & 1)) { order.push_back(b); used |= 1u << b; }
         for (int b = 0; b < P.m; ++b) if ((wmask >> b) & 1) order.push_back(b);
         if ((int)order.size() != P.m - NB || __builtin_popcount(wmask) > nwarp_bits) { ok = false; break; }
+        uint32_t warp_uniform = 0;                    // tile-local bits that sit on the warp index in this group
+        for (size_t j = 5; j < order.size(); ++j) warp_uniform |= 1u << order[j];
         for (int lane = 0; lane < 32; ++lane) {
             uint32_t v = 0; for (int j = 0; j < 5; ++j) if ((lane >> j) & 1) v |= 1u << order[j];
             out.lane_tab[gi][lane] = (uint16_t)v;
@@ -148,7 +160,25 @@ inline bool encode_v4(const PlanPass& P, V4Program& out) {
             int bi = -1; if (tl >= 0) for (int i = 0; i < NB; ++i) if (rbl[i] == tl) bi = i;
             if (!x.diag && bi < 0) ok = false;
             LiftCoef Lc; memset(&Lc, 0, sizeof(Lc));
-            const int kind = x.slot >= 0 ? x.skind : lift_classify(x.m, Lc);   // liftable was checked by v4_eligible
+            // D1 form of an uncontrolled diagonal gate (see the comment above encode_v4)
+            bool d1_block = false, d1_ctx = false;
+            double md1[8];
+            if (gph && x.diag && x.ctrl < 0 && x.slot < 0 && (bi >= 0 || tl < 0 || ((warp_uniform >> tl) & 1u))) {
+                const double d0r = x.m[0], d0i = x.m[1], d1r = x.m[6], d1i = x.m[7];
+                double rr = d1r * d0r + d1i * d0i, ri = d1i * d0r - d1r * d0i;       // d1 * conj(d0)
+                const double h = hypot(rr, ri);
+                if (h > 0) { rr /= h; ri /= h; }
+                const double md[8] = { rr, ri, 0, 0, 0, 0, rr, ri };
+                LiftCoef Lt;
+                if (lift_classify(md, Lt) == LK_PHASE) {
+                    memcpy(md1, md, sizeof(md1));
+                    const double gr = gph[0] * d0r - gph[1] * d0i, gi = gph[0] * d0i + gph[1] * d0r;
+                    gph[0] = gr; gph[1] = gi;
+                    if (bi >= 0) d1_block = true; else d1_ctx = true;
+                }
+            }
+            const double* xm = (d1_block || d1_ctx) ? md1 : x.m;
+            const int kind = x.slot >= 0 ? x.skind : lift_classify(xm, Lc);   // liftable was checked by v4_eligible
             double cc[6]; memcpy(cc, Lc.c, sizeof(cc));
             // static sign variants: sg = (mk[0] ? 1 : 0) | (mk[1] ? 2 : 0); per-state slots are built for sg 0
             const int sgA = (Lc.mk[0] ? 1 : 0) | (Lc.mk[1] ? 2 : 0), sgB = (Lc.mk[2] ? 1 : 0) | (Lc.mk[3] ? 2 : 0);
@@ -162,8 +192,10 @@ inline bool encode_v4(const PlanPass& P, V4Program& out) {
                     cc[0] = x.m[0]; cc[1] = x.m[1]; cc[2] = 0; cc[3] = x.m[6]; cc[4] = x.m[7]; cc[5] = 0;
                 }
                 S.op = (uint32_t)(V4_OP_THR + variant * (NB + 1) + (CB + 1));
+                if (d1_ctx) cm |= S.tm;        // D1: only the threads (whole warps) that have the target bit run the record
             } else {
-                const int bc = v4_bc_index(bi, CB);
+                // D1 on a register-block bit: the PHASE body "controlled" by the target bit itself (both sets hold the same phase)
+                const int bc = d1_block ? v4_bc_index((bi + 1) % NB, bi) : v4_bc_index(bi, CB);
                 int base;
                 if (kind == LK_ROT) base = sgA * V4_NBC;
                 else if (kind == LK_ROTX) base = V4_OP_ROTX + (sgA == 3 ? V4_NBC : 0);

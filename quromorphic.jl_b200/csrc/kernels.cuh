@@ -60,6 +60,14 @@ k_apply_1q(double2* __restrict__ amp, uint64_t npairs, int tbit, uint64_t cmask,
     }
 }
 
+// amplitudes *= (pr + i pi): the global phase the fused passes left pending (state.hpp gphase)
+__global__ void k_scale_phase(double2* __restrict__ amp, uint64_t n, double pr, double pi) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double2 a = amp[i];
+        amp[i] = make_double2(a.x * pr - a.y * pi, a.x * pi + a.y * pr);
+    }
+}
+
 __global__ void k_set_basis(double2* __restrict__ amp, uint64_t reg_stride, int nreg, uint64_t index) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < nreg) amp[(uint64_t)r * reg_stride + index] = make_double2(1.0, 0.0);

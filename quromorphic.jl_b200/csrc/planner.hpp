@@ -229,9 +229,12 @@ inline double gate_cost(const LGate& g, int cost_model = 0) {
                       g.m[4] == 1 && g.m[5] == 0;
     const bool real_or_rx = (g.m[1] == 0 && g.m[7] == 0) && ((g.m[3] == 0 && g.m[5] == 0) || (g.m[2] == 0 && g.m[4] == 0));
     const double records = (g.diag || real_or_rx || g.slot >= 0) ? 1.0 : 3.0;
-    if (cost_model == 1) return is_x ? 0.4 : records * (g.ctrl >= 0 ? 1.2 : 2.3);
+    // an uncontrolled diagonal gate runs in D1 form (encode_v4): only the amplitudes that have the target bit are touched
+    const bool d1 = g.diag && g.ctrl < 0 && g.slot < 0;
+    if (cost_model == 1) return is_x ? 0.4 : d1 ? 1.3 : records == 3.0 ? (g.ctrl >= 0 ? 3.6 : 4.9) : (g.ctrl >= 0 ? 1.2 : 2.3);
     if (is_x) return 2.7;
-    return records * (g.ctrl >= 0 ? 2.5 : 4.6);
+    if (d1) return 3.0;
+    return records == 3.0 ? (g.ctrl >= 0 ? 7.5 : 10.7) : (g.ctrl >= 0 ? 2.5 : 4.6);
 }
 
 // Commutation-aware pull: walk the not-yet-done gates in order; take a gate when no earlier

@@ -133,6 +133,7 @@ extern "C" int32_t qm_reset(qm_state* st, uint64_t basis) {
     if (basis >> st->n) return set_err(QM_ERR_ARG, "basis index out of range");
     CU(cudaSetDevice(st->device));
     st->queue.clear();
+    st->gphase[0] = 1.0; st->gphase[1] = 0.0;
     for (int i = 0; i < st->n; ++i) st->perm[i] = i;
     dist_reset(st);
     CU(cudaMemsetAsync(st->amp, 0, (size_t)total_amps(st) * 16, st->stream));
@@ -458,7 +459,8 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             const std::vector<int>& idx = hit->passes[r].second;
             size_t j = 0;
             for (PlanGroup& G : P.groups) for (LGate& x : G.subs) x = pl.gates[idx[j++]];
-            if (v4_eligible(st, P) && encode_v4(P, progs[r]) && P.m == 12) { ptrs.push_back(&progs[r]); which.push_back(r); }
+            double scratch_phase[2] = { 1.0, 0.0 };        // this encoding only names the kernels; the phase is counted in prepare()
+            if (v4_eligible(st, P) && encode_v4(P, progs[r], scratch_phase) && P.m == 12) { ptrs.push_back(&progs[r]); which.push_back(r); }
         }
         std::vector<JitKernel*> got;
         jit_get_many(st->device, 12, ptrs, jit_thr, got);
@@ -468,8 +470,10 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     auto prepare = [&](Item& it) -> int {
         it.kind = 1; it.blob.clear(); it.jk = nullptr;
         if (tma) {
-            if (v4_eligible(st, it.P) && encode_v4(it.P, it.prog)) {
+            double gph[2] = { st->gphase[0], st->gphase[1] };
+            if (v4_eligible(st, it.P) && encode_v4(it.P, it.prog, gph)) {
                 it.kind = 0;
+                st->gphase[0] = gph[0]; st->gphase[1] = gph[1];       // global phase of the pass's diagonal gates (D1 form)
                 if (jit_thr > 0) {
                     if (!pre_jit.empty()) it.jk = replay_i >= 1 && replay_i <= pre_jit.size() ? pre_jit[replay_i - 1] : nullptr;
                     else it.jk = jit_get(st->device, it.P.m, it.prog, jit_thr);
@@ -856,6 +860,20 @@ extern "C" int32_t qm_apply_batched(qm_state* st, const qm_gate* gates, int32_t 
 // ---------------------------------------------------------------------------------------------
 // state transfer
 // ---------------------------------------------------------------------------------------------
+int materialize_phase(qm_state* st) {
+    if (st->gphase[0] == 1.0 && st->gphase[1] == 0.0) return QM_OK;
+    CU(cudaSetDevice(st->device));
+    double pr = st->gphase[0], pi = st->gphase[1];
+    const double h = hypot(pr, pi);            // a product of unit-modulus factors: keep it on the unit circle
+    if (h > 0) { pr /= h; pi /= h; }
+    const uint64_t N = total_amps(st);
+    k_scale_phase<<<grid_for(N, 256, st->sms, 16), 256, 0, st->stream>>>(st->amp, N, pr, pi);
+    CU(cudaGetLastError());
+    st->ctr.launches++; st->ctr.bytes_hbm += 32ull * N;
+    st->gphase[0] = 1.0; st->gphase[1] = 0.0;
+    return QM_OK;
+}
+
 extern "C" int32_t qm_sync(qm_state* st) {
     if (!st) return set_err(QM_ERR_ARG, "null state");
     QM_TRY(flush(st));
@@ -881,6 +899,7 @@ extern "C" int32_t qm_upload(qm_state* st, const double* host, uint64_t n_amps, 
     QM_TRY(flush(st));
     CU(cudaSetDevice(st->device));
     if (st->dist) QM_TRY(dist_canonicalize(st));
+    QM_TRY(materialize_phase(st));          // the other registers of the batch keep their phase; this one is overwritten
     CU(cudaMemcpyAsync(st->amp + ((uint64_t)batch_idx << st->nl), host, (size_t)n_amps * 16, cudaMemcpyHostToDevice, st->stream));
     st->ctr.bytes_h2d += n_amps * 16;
     CU(cudaStreamSynchronize(st->stream));
@@ -894,6 +913,7 @@ extern "C" int32_t qm_download(qm_state* st, double* host, uint64_t n_amps, int3
     QM_TRY(flush(st));
     CU(cudaSetDevice(st->device));
     if (st->dist) QM_TRY(dist_canonicalize(st));
+    QM_TRY(materialize_phase(st));
     CU(cudaMemcpyAsync(host, st->amp + ((uint64_t)batch_idx << st->nl), (size_t)n_amps * 16, cudaMemcpyDeviceToHost, st->stream));
     st->ctr.bytes_d2h += n_amps * 16;
     QM_TRY(qm_sync(st));
@@ -1252,6 +1272,7 @@ extern "C" int32_t qm_dm_from_state(qm_state* sv, qm_state* rho) {
     CU(cudaSetDevice(rho->device));
     CU(cudaStreamSynchronize(sv->stream));
     for (int i = 0; i < rho->n; ++i) rho->perm[i] = i;
+    rho->gphase[0] = 1.0; rho->gphase[1] = 0.0;          // overwritten whole; psi psi' does not see psi's pending phase
     k_dm_outer<<<grid_for(total_amps(rho), 256, rho->sms, 16), 256, 0, rho->stream>>>(sv->amp, q, rho->amp);
     CU(cudaGetLastError());
     rho->ctr.launches++; rho->ctr.bytes_hbm += 16ull * total_amps(rho);
@@ -1264,6 +1285,7 @@ extern "C" int32_t qm_dm_diag(qm_state* rho, double* out_host) {
     if (!out_host) return set_err(QM_ERR_ARG, "null argument");
     QM_TRY(flush(rho));
     CU(cudaSetDevice(rho->device));
+    QM_TRY(materialize_phase(rho));          // the diagonal of rho is linear in the stored amplitudes
     const uint64_t d = 1ull << q;
     QM_TRY(ENSURE_DEV(rho, d_scratch, (size_t)d * 8));
     k_dm_diag<<<grid_for(d, 256, rho->sms, 16), 256, 0, rho->stream>>>(rho->amp, q, rho->d_scratch);
@@ -1281,6 +1303,7 @@ extern "C" int32_t qm_dm_measure(qm_state* rho, int32_t t0, const double* R, dou
     if (t0 < 0 || t0 >= q) return set_err(QM_ERR_ARG, "Qubit index out of range (target bit %d, q = %d)", t0, q);
     QM_TRY(flush(rho));
     CU(cudaSetDevice(rho->device));
+    QM_TRY(materialize_phase(rho));
     Mat2 U; const int identity = (R == nullptr);
     if (R) memcpy(U.v, R, sizeof(U.v)); else memset(&U, 0, sizeof(U));
     const uint64_t npairs = (1ull << q) >> 1;
@@ -1371,7 +1394,7 @@ extern "C" int32_t qm_counters_reset(qm_state* st) {
 extern "C" int32_t qm_abi_version(void) { return QM_ABI_VERSION; }
 extern "C" int32_t qm_device_ptr(qm_state* st, void** amps, void** stream) {
     if (!st) return set_err(QM_ERR_ARG, "null state");
-    if (amps) *amps = st->amp;
+    if (amps) { QM_TRY(flush(st)); QM_TRY(materialize_phase(st)); *amps = st->amp; }     // the caller will read amplitudes
     if (stream) *stream = st->stream;
     return QM_OK;
 }
@@ -1508,7 +1531,8 @@ extern "C" int32_t qm_plan_ophist(int32_t n_qubits, int32_t tile_bits, int32_t l
     PlanPass P;
     while (pl.next_pass(P)) {
         choose_tile_layout(P);
-        if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass cannot be encoded");
+        double gph[2] = { 1.0, 0.0 };
+        if (!encode_v4(P, prog[0], gph)) return set_err(QM_ERR_STATE, "pass cannot be encoded");
         hist[8]++; hist[7] += prog[0].ngroups;
         for (int i = 0; i < prog[0].nrecs; ++i) {
             uint32_t op = prog[0].recs[i].op;
@@ -1546,7 +1570,8 @@ extern "C" int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_c
     PlanPass P;
     while (pl.next_pass(P)) {
         choose_tile_layout(P);
-        if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass cannot be encoded");
+        double gph[2] = { 1.0, 0.0 };
+        if (!encode_v4(P, prog[0], gph)) return set_err(QM_ERR_STATE, "pass cannot be encoded");
         out[0]++;
         std::string ptx;
         if (!jit_ptx_for(P.m, prog[0], ptx)) continue;

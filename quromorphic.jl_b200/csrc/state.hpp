@@ -54,6 +54,11 @@ struct qm_state {
         std::vector<std::pair<qm::PlanPass, std::vector<int>>> passes;     // pass (stale matrices) + gate indices in group order
     };
     std::vector<CachedPlan> plan_cache;       // most recent first, <= 8 entries
+    // Global phase of the register that the fused passes have NOT applied to the amplitudes (encode_v4: uncontrolled diagonal
+    // gates run in D1 form, diag(d0, d1) = d0 * diag(1, d1 / d0), and d0 lands here): true amplitudes = gphase * stored ones.
+    // Probabilities, expectations, reduced densities and samples do not depend on it; whoever reads amplitudes linearly
+    // (download, the density-matrix readouts, qm_device_ptr) calls materialize_phase first.
+    double gphase[2] = { 1.0, 0.0 };
     // queue
     std::vector<qm_gate> queue;
     // logical -> physical qubit map (identity unless a sharded remap happened)
@@ -102,3 +107,4 @@ int qm_sample_leaves(qm_state* st, int batch_idx, double* d_s1_local);
 int qm_sample_descend(qm_state* st, int batch_idx, const double* d_s1, uint64_t n1, uint64_t leaf_lo, uint64_t seed, int nshots,
                       double* d_levels, uint64_t* d_out);
 int qm_flush(qm_state* st);
+int materialize_phase(qm_state* st);       // multiplies the pending global phase into the amplitudes (one pass; no-op when it is 1)

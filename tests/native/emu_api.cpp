@@ -18,6 +18,11 @@ using namespace qm;
 static int g_jit_mode = 0;
 // in mode 1 the planner also prices gates as the engine does when the compiled kernels will run them (planner.hpp cost_model 1)
 extern "C" int32_t qm_emu_set_jit(int32_t on) { g_jit_mode = on ? 1 : 0; return QM_OK; }
+static void apply_phase(EmuAmp* a, uint64_t n, const double g[2]) {
+    if (g[0] == 1.0 && g[1] == 0.0) return;
+    double pr = g[0], pi = g[1]; const double h = hypot(pr, pi); if (h > 0) { pr /= h; pi /= h; }
+    for (uint64_t i = 0; i < n; ++i) { const double x = a[i].x, y = a[i].y; a[i].x = x * pr - y * pi; a[i].y = x * pi + y * pr; }
+}
 static bool run_program(const V4Program& prog, const PlanPass& P, EmuAmp* amp, int nl, uint64_t rank_or, std::string& why) {
     why.clear();
     if (!g_jit_mode) { if (!emulate_v4(prog, P, amp, nl, rank_or, nullptr)) { why = "malformed program (opcode / non-uniform control predicate)"; return false; } return true; }
@@ -54,15 +59,17 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     pl.done.assign(pl.gates.size(), 0);
     std::vector<V4Program> prog(1);
     PlanPass P; int np = 0;
+    double gph[2] = { 1.0, 0.0 };        // the global phase the D1 form of the diagonal gates leaves pending (encode_v4)
     while (pl.next_pass(P)) {
         choose_tile_layout(P);
-        if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
+        if (!encode_v4(P, prog[0], gph)) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
         std::string why;
         if (!run_program(prog[0], P, reinterpret_cast<EmuAmp*>(state), n_qubits, 0, why))
             return set_err(QM_ERR_STATE, "pass %d: %s", np, why.c_str());
         ++np;
     }
     for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) return set_err(QM_ERR_STATE, "planner left a gate behind");
+    apply_phase(reinterpret_cast<EmuAmp*>(state), 1ull << n_qubits, gph);       // what the engine's materialize_phase does
     if (n_passes) *n_passes = np;
     return QM_OK;
 }
@@ -95,10 +102,11 @@ extern "C" int32_t qm_plan_emulate_sharded(int32_t n_qubits, int32_t global_bits
     };
     std::vector<V4Program> prog(1);
     PlanPass P; int np = 0, nr = 0; bool swapped = false;
+    double gph[2] = { 1.0, 0.0 };
     for (int guard = 0; guard < 4 * ngates + 8; ++guard) {
         while (pl.next_pass(P)) {
             choose_tile_layout(P);
-            if (!encode_v4(P, prog[0])) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
+            if (!encode_v4(P, prog[0], gph)) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
             for (int r = 0; r < W; ++r) {
                 std::string why;
                 if (!run_program(prog[0], P, amp + (uint64_t)r * shard, nl, (uint64_t)r << nl, why))
@@ -119,6 +127,7 @@ extern "C" int32_t qm_plan_emulate_sharded(int32_t n_qubits, int32_t global_bits
     }
     for (size_t i = 0; i < pl.gates.size(); ++i) if (!pl.done[i]) return set_err(QM_ERR_STATE, "planner left a gate behind");
     if (swapped) exchange();                         // back to the canonical layout (dist_canonicalize)
+    apply_phase(amp, 1ull << n_qubits, gph);
     if (n_passes) *n_passes = np;
     if (n_remaps) *n_remaps = nr;
     return QM_OK;

@@ -34,8 +34,11 @@ def test_compiled_passes_match_oracle_and_interpreter(pkg, n, cost, seed):
         if jit:
             assert c["compiled_passes"] == c["passes"], c
         st.close()
-    assert rel_err(out[1], ref) < RTOL
-    assert np.array_equal(out[0], out[1])          # same shears in the same order: identical bits
+    assert rel_err(out[1], ref) < RTOL and rel_err(out[0], ref) < RTOL
+    if cost == 0:
+        # without a budget the planner does not look at gate prices, both kernels get the same passes — and then the same
+        # shears in the same order: identical bits
+        assert np.array_equal(out[0], out[1])
     s = L.jit_stats()
     assert s["compiled"] > 0 and s["failed"] == 0, s
 

@@ -43,6 +43,7 @@ def run_c2(pkg, steps=8, batch=4096, n=16, max_cost=-1):
            "fused_pass_gbs": gbs, "ms_per_step_wall_incl_readout_and_encoding_upload": 1e3 * wall / steps,
            "gate_applications_per_s_device": B * len(gates) * steps / (dev_ms * 1e-3),
            "gate_applications_per_s_wall": B * len(gates) * steps / wall,
+           "compiled_passes_per_step": c["compiled_passes"] / steps,
            "h2d_bytes_per_step": c["bytes_h2d"] / steps, "d2h_bytes_per_step": c["bytes_d2h"] / steps}
     st.close()
     return out
