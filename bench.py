@@ -289,6 +289,9 @@ def main():
     ap.add_argument("--low-bits", type=int, default=-1)
     ap.add_argument("--max-cost", type=float, default=-1)
     ap.add_argument("--short-pct", type=int, default=-1, help="QM_OPT_SHORT_PCT (default 180; 100 = off)")
+    ap.add_argument("--jit", type=int, default=-1, help="QM_OPT_JIT (compiled pass kernels): -1 = default (C3: engine default 2; C4: 1, with --structure-warmup)")
+    ap.add_argument("--structure-warmup", type=int, default=12,
+                    help="C4: extra untimed reservoir steps in front of the W warm-up steps (the pass programs of a step repeat with period 6; 12 = every structure twice)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-alt", action="store_true", help="skip the deep-fusion secondary measurement")
     ap.add_argument("--overlap", type=int, default=-1, help="sharded: QM_OPT_OVERLAP (default: engine default, 1)")
@@ -333,6 +336,8 @@ def main():
         st.set_option(L.OPT_MAX_COST, int(args.max_cost))
     if args.short_pct >= 0:
         st.set_option(L.OPT_SHORT_PCT, args.short_pct)
+    if args.jit >= 0:
+        st.set_option(L.OPT_JIT, args.jit)
     import ctypes as C
     amps, stream = C.c_void_p(), C.c_void_p()
     L.check(L.lib().qm_device_ptr(st._h, C.byref(amps), C.byref(stream)))

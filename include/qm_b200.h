@@ -260,9 +260,10 @@ int32_t qm_abi_version(void);
 int32_t qm_jit_stats(uint64_t out[4], double* compile_ms);
 /* host-only check of the compiled pass kernels (no GPU needed): every 2^12-tile pass of the planned circuit is turned into PTX
  * text and, with compile != 0 and libnvJitLink present, assembled for sm_100a.  out = {passes, passes with PTX text, passes
- * assembled, distinct opcode sequences, bytes of the largest cubin}; ptx_out (optional) receives the text of the first pass */
+ * assembled, distinct opcode sequences, bytes of the largest cubin, hash over all passes' opcode sequences (canonical signs: it
+ * depends on the structure of the circuit, not on its angles)}; ptx_out (optional) receives the text of the first pass */
 int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_cost, const qm_gate* gates, int32_t ngates,
-                     int32_t compile, int64_t out[5], char* ptx_out, int64_t ptx_cap);
+                     int32_t compile, int64_t out[6], char* ptx_out, int64_t ptx_cap);
 /* diagnostics (QM_OPT_TIME_PASSES): per fused pass since the last call, 8 floats {ms, groups, gates, planner cost,
  * records with full FP64 cost, with a control in the register block (half cost), xor exchanges, thread-constant phases};
  * *n_passes receives the number of passes timed, at most cap_passes are written */

@@ -182,10 +182,10 @@ def plan_describe(n, gates, global_bits=0, tile_bits=12, low_bits=5, max_cost=0.
 def jit_check(n, gates, low_bits=5, max_cost=0.0, compile=True, want_ptx=False):
     """host-only: {passes, with_ptx, assembled, distinct, max_cubin_bytes} (+ the PTX text of the first pass) for the compiled
     pass kernels of this circuit"""
-    out = (C.c_int64 * 5)()
+    out = (C.c_int64 * 6)()
     buf = C.create_string_buffer(4 << 20) if want_ptx else None
     check(lib().qm_jit_check(n, low_bits, max_cost, gates.ctypes.data, len(gates), 1 if compile else 0, out, buf, (4 << 20) if want_ptx else 0))
-    d = dict(zip(("passes", "with_ptx", "assembled", "distinct", "max_cubin_bytes"), list(out)))
+    d = dict(zip(("passes", "with_ptx", "assembled", "distinct", "max_cubin_bytes", "structure_hash"), list(out)))
     if want_ptx:
         d["ptx"] = buf.value.decode()
     return d

@@ -61,7 +61,16 @@ inline int hb_runs(const std::vector<int>& hb, int start[8], int len[8]) {
 // layer).  The form is used when the target is a register-block bit (a PHASE record "controlled" by the target bit itself)
 // or a bit that is uniform over a warp (outside the tile or on the warp index: the thread-constant phase entered through
 // its controlled entry, so half of the warps skip the record); on a lane bit the gate keeps both coefficient sets.
-inline bool encode_v4(const PlanPass& P, V4Program& out, double* gph = nullptr) {
+//
+// canon (needs gph; COMPILED pass kernels only — the interpreter ignores a record's aux): CANONICAL SIGNS.  The lifting form of
+// a rotation whose cosine is negative uses negated addends (the "sign variants" of the opcode table), so the opcode of a gate
+// would depend on its ANGLE and a reservoir step with new angles would never find its compiled kernel again.  In canonical
+// form the matrix is negated first (-M has the plain form) and the -1 is put where it is cheapest: into the global phase
+// for an uncontrolled rotation, else into aux bit 0 / 1 = "negate the amplitudes that took coefficient set 0 / 1" — one
+// integer xor per value in the generated code (jit_codegen.hpp), data of the launch.  What is left in the opcodes is the
+// structure of the circuit only: gate family, rotation or reflection, register-block positions, controlled or not.
+inline bool encode_v4(const PlanPass& P, V4Program& out, double* gph = nullptr, bool canon = false) {
+    if (canon && !gph) return false;
     memset(&out, 0, offsetof(V4Program, recs));
     out.ngroups = (int)P.groups.size();
     int outer_of[64]; for (int i = 0; i < 64; ++i) outer_of[i] = -1;
@@ -179,6 +188,23 @@ inline bool encode_v4(const PlanPass& P, V4Program& out, double* gph = nullptr) 
             }
             const double* xm = (d1_block || d1_ctx) ? md1 : x.m;
             const int kind = x.slot >= 0 ? x.skind : lift_classify(xm, Lc);   // liftable was checked by v4_eligible
+            uint32_t negflags = 0;
+            if (canon && x.slot < 0 && (kind == LK_ROT || kind == LK_ROTX || kind == LK_PHASE)) {
+                double mm[8]; memcpy(mm, xm, sizeof(mm));
+                if (kind == LK_PHASE) {
+                    if (Lc.mk[0] && Lc.mk[1]) { mm[0] = -mm[0]; mm[1] = -mm[1]; negflags |= 1u; }
+                    if (Lc.mk[2] && Lc.mk[3]) { mm[6] = -mm[6]; mm[7] = -mm[7]; negflags |= 2u; }
+                } else if (Lc.mk[1]) { for (int i = 0; i < 8; ++i) mm[i] = -mm[i]; negflags = 1u; }
+                if (negflags) {
+                    LiftCoef L2;
+                    if (lift_classify(mm, L2) != kind) { ok = false; break; }
+                    Lc = L2;
+                    if (kind != LK_PHASE && x.ctrl < 0) {       // -1 on every amplitude: a global phase
+                        gph[0] = -gph[0]; gph[1] = -gph[1]; negflags = 0;
+                    }
+                }
+            }
+            S.aux = negflags;
             double cc[6]; memcpy(cc, Lc.c, sizeof(cc));
             // static sign variants: sg = (mk[0] ? 1 : 0) | (mk[1] ? 2 : 0); per-state slots are built for sg 0
             const int sgA = (Lc.mk[0] ? 1 : 0) | (Lc.mk[1] ? 2 : 0), sgB = (Lc.mk[2] ? 1 : 0) | (Lc.mk[3] ? 2 : 0);
@@ -218,7 +244,7 @@ inline bool encode_v4(const PlanPass& P, V4Program& out, double* gph = nullptr) 
         const uint64_t packed = (uint64_t)so[3] | ((uint64_t)delta << 32);
         memcpy(&E.c[0], &packed, 8);
     }
-    out.nrecs = nrec; out.n_outer = n_outer; out.ctx_const = 0;
+    out.nrecs = nrec; out.n_outer = n_outer; out.ctx_const = 0; out.flags = canon ? 1u : 0u;
     return ok;
 }
 

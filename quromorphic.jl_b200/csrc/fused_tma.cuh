@@ -85,6 +85,8 @@ struct V4Program {
     int32_t  ngroups, nrecs, n_outer;
     uint32_t ctx_const;
     uint64_t outer_pack[2]; // 6-bit fields: global index bit behind context bit kV4CtxOuter + j (10 per word)
+    uint32_t flags;         // bit 0: canonical signs (compiled pass kernels only, encode_v4 `canon`): no sign-variant opcodes, a record's aux bits 0 / 1 = negate the amplitudes that took coefficient set 0 / 1
+    uint32_t pad_[3];
     V4Group  groups[kV4MaxGroups];
     uint16_t lane_tab[kV4MaxGroups][32];    // tile-local index bits contributed by the lane
     uint16_t warp_tab[kV4MaxGroups][8];     // ... by the warp within its team

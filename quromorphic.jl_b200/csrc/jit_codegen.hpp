@@ -36,7 +36,7 @@ struct JitOperands {
 // what the code depends on: the opcode sequence, group by group
 inline void jit_structure_bytes(const V4Program& p, int m, std::vector<uint32_t>& out) {
     out.clear();
-    out.push_back(0x4a495431u); out.push_back((uint32_t)m); out.push_back((uint32_t)p.ngroups);
+    out.push_back(0x4a495431u); out.push_back((uint32_t)m); out.push_back((uint32_t)p.ngroups); out.push_back(p.flags);
     for (int g = 0; g < p.ngroups; ++g) {
         const V4Rec* R = reinterpret_cast<const V4Rec*>(reinterpret_cast<const unsigned char*>(&p) + p.groups[g].rec_off);
         for (int guard = 0; guard < kV4MaxRecs + 1; ++guard, ++R) { out.push_back(R->op); if (R->op == (uint32_t)V4_OP_END) break; }
@@ -68,7 +68,7 @@ public:
         std::string head = "{\n";
         char buf[256];
         snprintf(buf, sizeof(buf), "\t.reg .f64 x<16>, y<16>, ng, tq<2>, sw, c<%d>;\n", ncoef + 1); head += buf;
-        head += "\t.reg .b32 t, ad, o<4>, e<4>, hcm;\n\t.reg .pred pact, phi, pg;\n\t.reg .b64 sa, sb;\n";
+        head += "\t.reg .b32 t, ad, o<4>, e<4>, hcm, ng0, ng1, ngs, wlo, whi;\n\t.reg .pred pact, phi, pg;\n\t.reg .b64 sa, sb;\n";
         if (ng > 1) {       // which group: a warp-uniform branch per group (the C++ loop around the block passes gi)
             for (int g = 1; g < ng; ++g) {
                 snprintf(buf, sizeof(buf), "\tsetp.eq.u32 pg, %s, %d;\n\t@pg bra.uni QJ_G%d;\n", O.gi.c_str(), g, g); head += buf;
@@ -109,6 +109,21 @@ private:
             if (c.sg & 2) { line("neg.f64 ng, %s;", c.x.c_str()); line("fma.rn.f64 %s, %s, %s, ng;", c.x.c_str(), c.t2.c_str(), c.y.c_str()); }
             else line("fma.rn.f64 %s, %s, %s, %s;", c.x.c_str(), c.t2.c_str(), c.y.c_str(), c.x.c_str());
         }
+    }
+
+    // canonical signs (V4Program::flags bit 0): the record's aux bit 0 / 1 = negate the values that took coefficient set 0 / 1.
+    // ng0 / ng1 become 0 or 0x80000000 and are xor-ed into the high word of every value of the set: an integer operation per
+    // value beside the FP64 pipe, data of the launch — so the code does not depend on the signs of the angles.
+    void neg_masks(size_t rec_off) {
+        line("ld.param.u32 t, [%s+%zu];", O.prog.c_str(), rec_off + 12);
+        line("shl.b32 ng0, t, 31;");
+        line("and.b32 ng1, t, 2;");
+        line("shl.b32 ng1, ng1, 30;");
+    }
+    void neg_value(const std::string& v, const char* mask) {
+        line("mov.b64 {wlo, whi}, %s;", v.c_str());
+        line("xor.b32 whi, whi, %s;", mask);
+        line("mov.b64 %s, {wlo, whi};", v.c_str());
     }
 
     bool group(int g) {
@@ -169,6 +184,8 @@ private:
                 line("setp.ne.u32 pact, t, hcm;");
                 line("@pact bra.uni QJ_S%d;", skip);
             }
+            const bool canon = (P.flags & 1u) != 0;
+            if (canon && ((fam == 0 && var > 1) || (fam == 1 && var != 0) || (fam == 2 && var != 0) || (fam == 4 && var != 0))) return false;
             std::vector<Chain> ch;
             if (fam == 0) {
                 for (int k = 0; k < 16; ++k) {
@@ -178,6 +195,10 @@ private:
                     ch.push_back({ Y(k), Y(k1), C(0), C(1), C(2), var });
                 }
                 lift_all(ch);
+                if (canon && (CB >= 0 || controlled)) {
+                    neg_masks(off);
+                    for (int k = 0; k < 16; ++k) if (ctrl_ok(k, CB)) { neg_value(X(k), "ng0"); neg_value(Y(k), "ng0"); }
+                }
             } else if (fam == 1) {
                 const int sg = var ? 3 : 0;
                 line("neg.f64 tq0, %s;", C(0).c_str());      // mirrored pair: coefficients negated
@@ -190,6 +211,10 @@ private:
                     ch.push_back({ Y(k), X(k1), "tq0", "tq1", "sw", sg });
                 }
                 lift_all(ch);
+                if (canon && (CB >= 0 || controlled)) {
+                    neg_masks(off);
+                    for (int k = 0; k < 16; ++k) if (ctrl_ok(k, CB)) { neg_value(X(k), "ng0"); neg_value(Y(k), "ng0"); }
+                }
             } else if (fam == 2) {
                 static const int sgs[4][2] = { { 0, 0 }, { 0, 3 }, { 3, 0 }, { 3, 3 } };
                 for (int k = 0; k < 16; ++k) {
@@ -198,6 +223,14 @@ private:
                     else ch.push_back({ X(k), Y(k), C(0), C(1), C(2), sgs[var][0] });
                 }
                 lift_all(ch);
+                if (canon) {
+                    neg_masks(off);
+                    for (int k = 0; k < 16; ++k) {
+                        if (!ctrl_ok(k, CB)) continue;
+                        const char* mk = ((k >> B) & 1) ? "ng1" : "ng0";
+                        neg_value(X(k), mk); neg_value(Y(k), mk);
+                    }
+                }
             } else if (fam == 3) {
                 for (int k = 0; k < 16; ++k) {
                     if (!ctrl_ok(k, CB) || ((k >> B) & 1)) continue;
@@ -230,6 +263,11 @@ private:
                 } else {
                     for (int k = 0; k < 16; ++k) if (ctrl_ok(k, CB)) ch.push_back({ X(k), Y(k), C(0), C(1), C(2), var == 1 ? 3 : 0 });
                     lift_all(ch);
+                    if (canon) {
+                        neg_masks(off);
+                        line("selp.b32 ngs, ng1, ng0, phi;");
+                        for (int k = 0; k < 16; ++k) if (ctrl_ok(k, CB)) { neg_value(X(k), "ngs"); neg_value(Y(k), "ngs"); }
+                    }
                 }
             }
             if (controlled) line("QJ_S%d:", skip);

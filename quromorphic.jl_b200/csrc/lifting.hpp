@@ -105,6 +105,14 @@ inline bool decompose_unitary(const double* m, double out[3][8]) {
 // After lower_gates: make every (non-slot) gate a single in-place sub where possible.  General
 // unitaries are replaced by their three factors; `liftable` is cleared on gates that have no
 // lifting form at all (non-unitary), which sends their pass to the v1 kernel.
+// A factor of the decomposition that is the identity up to rounding (the right phase of rz * ry is exactly 1 in exact
+// arithmetic and 1 +- a few 1e-17 in floating point) is dropped.  The test has a tolerance on purpose: whether a record
+// exists must depend on the STRUCTURE of the circuit, not on how an angle happened to round — the compiled pass kernels are
+// keyed by the record sequence (jit_codegen.hpp).  1e-14 is 100x inside the 1e-12 parity bound.
+inline bool mat_near_identity(const double* m) {
+    return mat_is_diag(m) && fabs(m[0] - 1.0) <= 1e-14 && fabs(m[1]) <= 1e-14 && fabs(m[6] - 1.0) <= 1e-14 && fabs(m[7]) <= 1e-14;
+}
+
 inline void prepare_for_lifting(std::vector<LGate>& gates) {
     std::vector<LGate> out; out.reserve(gates.size() + 16);
     for (const LGate& g : gates) {
@@ -114,10 +122,10 @@ inline void prepare_for_lifting(std::vector<LGate>& gates) {
         double f[3][8];
         if (decompose_unitary(g.m, f)) {
             bool ok = true; LiftCoef t;
-            for (int i = 0; i < 3; ++i) if (!mat_is_identity(f[i]) && lift_classify(f[i], t) == LK_NONE) ok = false;
+            for (int i = 0; i < 3; ++i) if (!mat_near_identity(f[i]) && lift_classify(f[i], t) == LK_NONE) ok = false;
             if (ok) {
                 for (int i = 0; i < 3; ++i) {
-                    if (mat_is_identity(f[i])) continue;
+                    if (mat_near_identity(f[i])) continue;
                     LGate h = g; memcpy(h.m, f[i], sizeof(h.m)); h.diag = mat_is_diag(h.m); h.liftable = true;
                     out.push_back(h);
                 }

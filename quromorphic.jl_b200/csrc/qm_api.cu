@@ -460,7 +460,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             size_t j = 0;
             for (PlanGroup& G : P.groups) for (LGate& x : G.subs) x = pl.gates[idx[j++]];
             double scratch_phase[2] = { 1.0, 0.0 };        // this encoding only names the kernels; the phase is counted in prepare()
-            if (v4_eligible(st, P) && encode_v4(P, progs[r], scratch_phase) && P.m == 12) { ptrs.push_back(&progs[r]); which.push_back(r); }
+            if (v4_eligible(st, P) && P.m == 12 && encode_v4(P, progs[r], scratch_phase, true)) { ptrs.push_back(&progs[r]); which.push_back(r); }
         }
         std::vector<JitKernel*> got;
         jit_get_many(st->device, 12, ptrs, jit_thr, got);
@@ -470,14 +470,21 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     auto prepare = [&](Item& it) -> int {
         it.kind = 1; it.blob.clear(); it.jk = nullptr;
         if (tma) {
-            double gph[2] = { st->gphase[0], st->gphase[1] };
-            if (v4_eligible(st, it.P) && encode_v4(it.P, it.prog, gph)) {
-                it.kind = 0;
-                st->gphase[0] = gph[0]; st->gphase[1] = gph[1];       // global phase of the pass's diagonal gates (D1 form)
-                if (jit_thr > 0) {
+            const bool eligible = v4_eligible(st, it.P);
+            // compiled kernel first: the program in canonical-sign form (what the kernel's opcode sequence is keyed by);
+            // only when there is no kernel (yet) is the pass encoded for the interpreter
+            if (eligible && jit_thr > 0 && it.P.m == 12) {
+                double gph[2] = { st->gphase[0], st->gphase[1] };
+                if (encode_v4(it.P, it.prog, gph, true)) {
                     if (!pre_jit.empty()) it.jk = replay_i >= 1 && replay_i <= pre_jit.size() ? pre_jit[replay_i - 1] : nullptr;
                     else it.jk = jit_get(st->device, it.P.m, it.prog, jit_thr);
+                    if (it.jk) { it.kind = 0; st->gphase[0] = gph[0]; st->gphase[1] = gph[1]; return QM_OK; }
                 }
+            }
+            double gph[2] = { st->gphase[0], st->gphase[1] };
+            if (eligible && encode_v4(it.P, it.prog, gph)) {
+                it.kind = 0;
+                st->gphase[0] = gph[0]; st->gphase[1] = gph[1];       // global phase of the pass's diagonal gates (D1 form)
                 return QM_OK;
             }
             // The planner is supposed to respect the kernel's limits; if a pass slips through, it is still applied
@@ -1551,9 +1558,11 @@ extern "C" int32_t qm_plan_ophist(int32_t n_qubits, int32_t tile_bits, int32_t l
 // Host-only introspection of the compiled pass kernels (no GPU needed: the PTX text is generated and, when libnvJitLink is
 // present, assembled into a cubin for sm_100a): plans and encodes `gates` as for the TMA kernel and puts every pass of tile
 // size 2^12 through jit_ptx_for / jit_compile_cubin.  out = {passes, passes with PTX text, passes compiled to a cubin,
-// distinct opcode sequences, bytes of the largest cubin}; ptx_out (optional) receives the text of the first pass.
+// distinct opcode sequences, bytes of the largest cubin, a hash over the opcode sequences of all passes in order}; ptx_out
+// (optional) receives the text of the first pass.  Programs are encoded as the engine encodes them for a compiled kernel
+// (canonical signs): two circuits of the same structure with different angles give the same hash.
 extern "C" int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_cost, const qm_gate* gates, int32_t ngates,
-                                int32_t compile, int64_t out[5], char* ptx_out, int64_t ptx_cap) {
+                                int32_t compile, int64_t out[6], char* ptx_out, int64_t ptx_cap) {
     if (!gates || !out || n_qubits < 12) return set_err(QM_ERR_ARG, "bad argument");
     Planner pl;
     pl.opt.n_local = n_qubits; pl.opt.n_global = 0;
@@ -1564,14 +1573,14 @@ extern "C" int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_c
     if (rc) return set_err(rc, "bad gate");
     prepare_for_lifting(pl.gates);
     pl.done.assign(pl.gates.size(), 0);
-    for (int i = 0; i < 5; ++i) out[i] = 0;
+    for (int i = 0; i < 6; ++i) out[i] = 0;
     std::vector<V4Program> prog(1);
     std::vector<std::vector<uint32_t>> seen;
     PlanPass P;
     while (pl.next_pass(P)) {
         choose_tile_layout(P);
         double gph[2] = { 1.0, 0.0 };
-        if (!encode_v4(P, prog[0], gph)) return set_err(QM_ERR_STATE, "pass cannot be encoded");
+        if (!encode_v4(P, prog[0], gph, true)) return set_err(QM_ERR_STATE, "pass cannot be encoded");
         out[0]++;
         std::string ptx;
         if (!jit_ptx_for(P.m, prog[0], ptx)) continue;
@@ -1579,6 +1588,7 @@ extern "C" int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_c
         out[1]++;
         std::vector<uint32_t> sig; jit_structure_bytes(prog[0], P.m, sig);
         if (std::find(seen.begin(), seen.end(), sig) == seen.end()) { seen.push_back(sig); out[3]++; }
+        { uint64_t k[2]; jit_hash(sig, k); out[5] = (int64_t)(((uint64_t)out[5] * 0x100000001b3ull) ^ k[0] ^ (k[1] << 1)); }
         if (compile) {
             std::vector<char> cubin; std::string log;
             if (!jit_compile_cubin(ptx, cubin, log)) return set_err(QM_ERR_STATE, "pass %lld does not assemble: %s", (long long)out[0] - 1, log.c_str());

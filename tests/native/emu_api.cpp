@@ -62,7 +62,7 @@ extern "C" int32_t qm_plan_emulate(int32_t n_qubits, int32_t tile_bits, int32_t 
     double gph[2] = { 1.0, 0.0 };        // the global phase the D1 form of the diagonal gates leaves pending (encode_v4)
     while (pl.next_pass(P)) {
         choose_tile_layout(P);
-        if (!encode_v4(P, prog[0], gph)) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
+        if (!encode_v4(P, prog[0], gph, g_jit_mode != 0)) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
         std::string why;
         if (!run_program(prog[0], P, reinterpret_cast<EmuAmp*>(state), n_qubits, 0, why))
             return set_err(QM_ERR_STATE, "pass %d: %s", np, why.c_str());
@@ -106,7 +106,7 @@ extern "C" int32_t qm_plan_emulate_sharded(int32_t n_qubits, int32_t global_bits
     for (int guard = 0; guard < 4 * ngates + 8; ++guard) {
         while (pl.next_pass(P)) {
             choose_tile_layout(P);
-            if (!encode_v4(P, prog[0], gph)) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
+            if (!encode_v4(P, prog[0], gph, g_jit_mode != 0)) return set_err(QM_ERR_STATE, "pass %d cannot be encoded for the TMA kernel", np);
             for (int r = 0; r < W; ++r) {
                 std::string why;
                 if (!run_program(prog[0], P, amp + (uint64_t)r * shard, nl, (uint64_t)r << nl, why))

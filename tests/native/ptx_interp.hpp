@@ -17,7 +17,7 @@ namespace qm {
 
 struct PtxIns {
     enum Op { MOV32, MOVF, XOR, AND, ADD32, ADD64, MULWIDE, SETP_EQ, SETP_NE, SELP, NEG, MUL, FMA, LDP32, LDPF, LDS_V2, LDS_U64, LDG_V2,
-              STS_V2, BRA, LABEL } op;
+              STS_V2, BRA, LABEL, SHL, UNPACK, PACK } op;
     int pred = -1; bool pneg = false;      // guard predicate register
     int d = -1, d2 = -1, a = -1, b = -1, c = -1;     // register indices (-1: unused)
     bool a_imm = false, b_imm = false; int64_t imm_a = 0, imm_b = 0, off = 0;
@@ -94,9 +94,12 @@ inline bool ptx_parse(const std::string& text, PtxProgram& P) {
             I.op = opc == "xor.b32" ? PtxIns::XOR : opc == "and.b32" ? PtxIns::AND : opc == "add.u32" ? PtxIns::ADD32 : PtxIns::ADD64;
             I.d = P.R(o[0]); src(o[1], I.a, dummy, dimm); src(o[2], I.b, I.b_imm, I.imm_b);
         }
+        else if (opc == "shl.b32") { I.op = PtxIns::SHL; I.d = P.R(o[0]); I.a = P.R(o[1]); src(o[2], I.b, I.b_imm, I.imm_b); }
+        else if (opc == "mov.b64" && o[0][0] == '{') { I.op = PtxIns::UNPACK; pair(o[0], I.d, I.d2); I.a = P.R(o[1]); }
+        else if (opc == "mov.b64" && o[1][0] == '{') { I.op = PtxIns::PACK; I.d = P.R(o[0]); pair(o[1], I.a, I.b); }
         else if (opc == "mul.wide.u32") { I.op = PtxIns::MULWIDE; I.d = P.R(o[0]); I.a = P.R(o[1]); src(o[2], I.b, I.b_imm, I.imm_b); }
         else if (opc == "setp.eq.u32" || opc == "setp.ne.u32") { I.op = opc == "setp.eq.u32" ? PtxIns::SETP_EQ : PtxIns::SETP_NE; I.d = P.R(o[0]); I.a = P.R(o[1]); src(o[2], I.b, I.b_imm, I.imm_b); }
-        else if (opc == "selp.f64") { I.op = PtxIns::SELP; I.d = P.R(o[0]); I.a = P.R(o[1]); I.b = P.R(o[2]); I.c = P.R(o[3]); }
+        else if (opc == "selp.f64" || opc == "selp.b32") { I.op = PtxIns::SELP; I.d = P.R(o[0]); I.a = P.R(o[1]); I.b = P.R(o[2]); I.c = P.R(o[3]); }
         else if (opc == "neg.f64") { I.op = PtxIns::NEG; I.d = P.R(o[0]); I.a = P.R(o[1]); }
         else if (opc == "mul.f64") { I.op = PtxIns::MUL; I.d = P.R(o[0]); I.a = P.R(o[1]); I.b = P.R(o[2]); }
         else if (opc == "fma.rn.f64") { I.op = PtxIns::FMA; I.d = P.R(o[0]); I.a = P.R(o[1]); I.b = P.R(o[2]); I.c = P.R(o[3]); }
@@ -138,6 +141,9 @@ inline bool ptx_run(const PtxProgram& P, std::vector<uint64_t>& regs, const unsi
         case PtxIns::AND: regs[I.d] = (uint32_t)(regs[I.a] & bv); break;
         case PtxIns::ADD32: regs[I.d] = (uint32_t)(regs[I.a] + bv); break;
         case PtxIns::ADD64: regs[I.d] = regs[I.a] + bv; break;
+        case PtxIns::SHL: regs[I.d] = (uint32_t)((uint32_t)regs[I.a] << (bv & 31)); break;
+        case PtxIns::UNPACK: { const uint64_t v = regs[I.a]; regs[I.d] = (uint32_t)v; regs[I.d2] = (uint32_t)(v >> 32); break; }
+        case PtxIns::PACK: regs[I.d] = (uint64_t)(uint32_t)regs[I.a] | ((uint64_t)(uint32_t)regs[I.b] << 32); break;
         case PtxIns::MULWIDE: regs[I.d] = (uint64_t)(uint32_t)regs[I.a] * (uint64_t)(uint32_t)bv; break;
         case PtxIns::SETP_EQ: regs[I.d] = (uint32_t)regs[I.a] == (uint32_t)bv; break;
         case PtxIns::SETP_NE: regs[I.d] = (uint32_t)regs[I.a] != (uint32_t)bv; break;
@@ -171,6 +177,7 @@ inline bool ptx_run(const PtxProgram& P, std::vector<uint64_t>& regs, const unsi
 }
 
 // emulate_v4 with the register-block groups executed from the generated PTX text
+// (the caller encodes with canonical signs when it wants the text the engine compiles: encode_v4(..., canon = true))
 inline bool emulate_v4_jit(const V4Program& prog, const PlanPass& Pp, EmuAmp* amp, int nl, uint64_t rank_or, const double* slot_lifts,
                            std::string* err = nullptr) {
     JitOperands O;

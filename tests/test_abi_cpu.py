@@ -323,3 +323,30 @@ def test_compiled_pass_kernels_generate_and_assemble_for_sm_100a(pkg):
                 pytest.skip("libnvJitLink is not installed here")
             raise
         assert d2["assembled"] == d2["passes"] and 10000 < d2["max_cubin_bytes"] < 400000
+
+
+def test_compiled_kernels_are_keyed_by_structure_not_by_angles(pkg):
+    """canonical signs (encode_v4 canon): the opcode sequence of a pass program — the key of a compiled kernel — must not
+    depend on the angles.  C4 reservoir steps have a structure period of 6 (gate kind (q + l) mod 3, brickwork l mod 2) and
+    fresh random angles every step, incl. merged general unitaries whose lifting forms take every sign variant."""
+    L = pkg._lib
+    for n in (16, 21):
+        h = [L.jit_check(n, pkg.circuits.c4_step(n, s), max_cost=80.0, compile=False)["structure_hash"] for s in range(18)]
+        for s in range(12):
+            assert h[s] == h[s + 6], (n, s)
+        assert len(set(h[:6])) >= 4                      # ... and it does tell different structures apart
+    # same circuit shape, random angles in [-2 pi, 2 pi]: rx / ry / rz / crz / crx with every sign of cos and sin
+    rng = np.random.default_rng(11)
+    hs = set()
+    for rep in range(6):
+        gl = pkg.circuits.GateList(14, "corrected")
+        for q in range(1, 15):
+            gl.rx(q, float(rng.uniform(-6.3, 6.3))); gl.rz(q, float(rng.uniform(-6.3, 6.3)))
+        for q in range(1, 14):
+            gl.crz(q, q + 1, float(rng.uniform(-6.3, 6.3)))
+        for q in range(1, 15):
+            gl.ry(q, float(rng.uniform(-6.3, 6.3)))
+        for q in range(2, 14, 2):
+            gl.crx(q + 1, q, float(rng.uniform(-6.3, 6.3)))
+        hs.add(L.jit_check(14, gl.array(), max_cost=80.0, compile=False)["structure_hash"])
+    assert len(hs) == 1

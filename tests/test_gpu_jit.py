@@ -57,13 +57,13 @@ def test_default_threshold_compiles_on_the_second_run_of_a_structure(pkg):
     for rep in range(3):
         gl = pkg.circuits.GateList(n)
         for q in range(1, n + 1):
-            gl.ry(q, float(rng.uniform(0, np.pi)))          # plain signs for every angle: one opcode sequence
+            gl.ry(q, float(rng.uniform(-6.3, 6.3)))         # merged with the rx and rz into one general unitary per qubit:
+            gl.rx(q, float(rng.uniform(-6.3, 6.3)))         # every sign variant of the lifting forms turns up, and the
+            gl.rz(q, float(rng.uniform(-6.3, 6.3)))         # canonical-sign encoding keeps the opcode sequence the same
         for q in range(1, n):
             gl.cnot(q, q + 1)
-        for q in range(1, n + 1):
-            gl.rx(q, 0.3 + 0.1 * q)                         # (not merged with the ry: the cnot chain sits between them)
-        for q in range(1, n):
-            gl.cnot(q, q + 1)
+        for q in range(1, n, 2):
+            gl.crz(q, q + 1, float(rng.uniform(-6.3, 6.3)))
         g = gl.array()
         st.apply_circuit(g)
         small.apply_circuit(g)

@@ -470,7 +470,7 @@ def test_deep_circuit_default_budget_at_20_qubits(pkg):
     st = pkg.B200State(n, 0)
     st.apply_circuit(gates)
     c = st.counters()
-    assert len(gates) / c["passes"] < 16                 # budget-limited passes, not deep fusion
+    assert len(gates) / c["passes"] < 20                 # budget-limited passes (interpreter kernel at this size), not deep fusion
     ref = O.apply_circuit(O.statevector(n, 0), gates)
     assert rel_err(st.to_numpy(), ref) < RTOL
     assert np.max(np.abs(st.expect_z_all() - O.expect_z_all(ref, 1e-10))) < RTOL
