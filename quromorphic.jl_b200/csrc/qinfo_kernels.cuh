@@ -178,7 +178,12 @@ k_herm_measure(const double2* __restrict__ mats, const double2* __restrict__ mat
     v = warp_sum(v);
     if (lane == 0) {
         if (kind == HM_RENYI) v = log2(v) / (1.0 - alpha);
-        else if (kind == HM_MAX_ENTROPY) v = log2(v);
+        else if (kind == HM_MAX_ENTROPY) {
+            // log2 of a COUNT: CUDA's log2 is a 1-ulp function (log2(8.0) comes out as 2.9999999999999996), the host's is exact
+            // on powers of two — and so is the reference's log2(rank) (QInfo.jl:336)
+            const double cnt = v, l = log2(cnt), r = rint(l);
+            v = (exp2(r) == cnt) ? r : l;
+        }
         out[item] = v;
     }
 }

@@ -35,10 +35,9 @@ def test_compiled_passes_match_oracle_and_interpreter(pkg, n, cost, seed):
             assert c["compiled_passes"] == c["passes"], c
         st.close()
     assert rel_err(out[1], ref) < RTOL and rel_err(out[0], ref) < RTOL
-    if cost == 0:
-        # without a budget the planner does not look at gate prices, both kernels get the same passes — and then the same
-        # shears in the same order: identical bits
-        assert np.array_equal(out[0], out[1])
+    # the two kernels agree far inside the parity bound (not to the last bit: the planner prices gates differently for the two,
+    # and the canonical-sign form replaces the complex-multiply variant of a thread-constant phase by a lift)
+    assert rel_err(out[0], out[1]) < 1e-13
     s = L.jit_stats()
     assert s["compiled"] > 0 and s["failed"] == 0, s
 
