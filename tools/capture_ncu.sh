@@ -5,10 +5,10 @@ P=$1
 CMD="python bench.py --steps 1 --warmup 3 --depth 40 --no-cpu --no-alt"
 $CMD > gpurun_out/${P}_plain_depth40.json 2> gpurun_out/${P}_plain_depth40.err || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/${P}_launches_bench_depth40.csv $CMD > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_fused_tma -s 300 -c 3 -f -o gpurun_out/${P}_fused $CMD > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_fused_tma -s 150 -c 3 -f -o gpurun_out/${P}_fused $CMD > /dev/null 2>&1
 python tools/ncu_summary.py gpurun_out/${P}_fused.ncu-rep > gpurun_out/${P}_ncu_k_fused_tma_default_budget80.txt 2>&1
 ncu -i gpurun_out/${P}_fused.ncu-rep --page source --csv > gpurun_out/${P}_fused_source.csv 2>/dev/null
-python tools/ncu_regions.py gpurun_out/${P}_fused_source.csv >> gpurun_out/${P}_ncu_k_fused_tma_default_budget80.txt 2>&1
+(python tools/ncu_regions_jit.py gpurun_out/${P}_fused_source.csv || python tools/ncu_regions.py gpurun_out/${P}_fused_source.csv) >> gpurun_out/${P}_ncu_k_fused_tma_default_budget80.txt 2>&1
 rm -f gpurun_out/${P}_fused_source.csv
 python - <<PY
 import csv, collections
