@@ -51,6 +51,7 @@ check(rc) = rc == 0 ? nothing : error(lasterror())      # ErrorException, like t
 
 # qm_set_option keys (include/qm_b200.h).  The defaults are the measured ones; these are tuning / debugging knobs.
 const OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_TRACE, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = 0:8
+const OPT_OVERLAP, OPT_XSM, OPT_XUN, OPT_SLAB_BITS, OPT_OVERLAP_DEPTH, OPT_JIT = 9:14      # OPT_JIT: compiled pass kernels (0 never, 1 at first sight, default 2)
 set_option!(s, key::Integer, value::Integer) =
     check(ccall((:qm_set_option, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), s.handle, key, value))
 
