@@ -70,6 +70,7 @@ enum {
     QM_OPT_XUN       = 11,  /* ... amplitude pairs in flight per exchange thread: 4 (1024 threads per SM) or 8 (512, default) */
     QM_OPT_OVERLAP_DEPTH = 13, /* ... how many of the last passes before an exchange run slab by slab in front of it (1..4, default 2) */
     QM_OPT_SLAB_BITS = 12,  /* ... log2 of the number of slabs (1..3, default 3) */
+    QM_OPT_DEFER_PASS = 15, /* sharded registers: 1 (default) the last fused pass planned before an exchange is postponed to after it when it does not target an outgoing qubit and the passes after the exchange do not become more (a reservoir layer: 4 passes per step instead of 5), 0: never */
     QM_OPT_JIT       = 14,  /* compiled pass kernels: a fused pass whose opcode sequence (gate kinds, sign variants, register-block positions) has been seen this many times is compiled into straight-line code and launched instead of the interpreter; default 2 (the second time a circuit of the same structure runs; only on registers of 2^26 amplitudes and more, batch included — below that a pass takes microseconds and a 0.25 s compilation never pays), 1 = every pass at first sight whatever the size, 0 = never.  The planner prices gates for the kernel that will run them. */
     QM_OPT_SHORT_PCT = 8    /* planner: a circuit shorter than the look-ahead window (a reservoir step before a readout) is planned at the multiple of the budget, up to this many per cent, that the pass model says finishes first; default 0 = no limit, 100 = off */
 };
@@ -100,6 +101,7 @@ typedef struct qm_counters_t {
     uint64_t overlapped_remaps; /* remaps that ran slab by slab beside the fused passes before and after them */
     uint64_t overlapped_passes; /* fused passes that were cut into slabs to run beside an exchange */
     uint64_t compiled_passes;   /* fused passes that ran as compiled straight-line kernels (QM_OPT_JIT) instead of the interpreter */
+    uint64_t deferred_passes;   /* sharded: passes postponed from before an exchange to after it (QM_OPT_DEFER_PASS) */
 } qm_counters_t;
 
 /* ---- lifetime -------------------------------------------------------------------- */

@@ -18,7 +18,7 @@ QM_OK, QM_ERR_ARG, QM_ERR_CUDA, QM_ERR_NOMEM, QM_ERR_NO_DEVICE, QM_ERR_STATE, QM
 GATE_U2, GATE_CU2, GATE_SWAP, GATE_U2_SLOT = 0, 1, 2, 3
 BASIS_Z, BASIS_X, BASIS_Y = 0, 1, 2
 OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_TRACE, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = range(9)
-OPT_OVERLAP, OPT_XSM, OPT_XUN, OPT_SLAB_BITS, OPT_OVERLAP_DEPTH, OPT_JIT = 9, 10, 11, 12, 13, 14
+OPT_OVERLAP, OPT_XSM, OPT_XUN, OPT_SLAB_BITS, OPT_OVERLAP_DEPTH, OPT_JIT, OPT_DEFER_PASS = 9, 10, 11, 12, 13, 14, 15
 
 GATE_DTYPE = np.dtype([("kind", np.int32), ("q0", np.int32), ("q1", np.int32), ("flags", np.int32),
                        ("m", np.float64, (8,))])
@@ -30,7 +30,7 @@ class Counters(C.Structure):
                 ("bytes_hbm", C.c_uint64), ("bytes_link", C.c_uint64), ("bytes_h2d", C.c_uint64),
                 ("bytes_d2h", C.c_uint64), ("ms_device", C.c_double),
                 ("ms_plan", C.c_double), ("ms_remap", C.c_double), ("overlapped_remaps", C.c_uint64), ("overlapped_passes", C.c_uint64),
-                ("compiled_passes", C.c_uint64)]
+                ("compiled_passes", C.c_uint64), ("deferred_passes", C.c_uint64)]
 
 
 class QMError(RuntimeError):

@@ -120,6 +120,7 @@ struct PlanOptions {
     double short_mult = 1e9;         // circuits shorter than the window may use up to short_mult x the budget (Planner::budget_for_pending)
     double hbm_units = 114.0;        // fitted pass model in budget units (0.05 ms at 30 qubits): HBM time of a pass,
     double fixed_units = 41.0;       // compute-side time = fixed_units + group_cost per group + gate costs
+    bool defer_bias = true;          // sharded: schedule the passes on the outgoing qubits first (choose_tile, try_defer_last_pass)
     int cost_model = 0;              // gate_cost: 0 the interpreter kernel, 1 the compiled pass kernels
     bool warp_uniform_ctrl = false;  // controls inside the tile must be block bits or one of the (m - block_bits - 5) warp-index bits
 };
@@ -305,6 +306,8 @@ struct Planner {
     void choose_tile(int m, int L, std::vector<int>& hb_best, int& best, uint64_t& tmask_best) const {
         const int nl = opt.n_local, nh = m - L;
         hb_best.clear(); best = -1; tmask_best = ~0ull;
+        double best_score = -1.0;
+        const bool outgoing_first = opt.n_global > 0 && opt.defer_bias && pending_global_target();
         if (nh <= 0) { best = count_with((1ull << L) - 1); return; }
         uint64_t low = (1ull << L) - 1;
         auto try_set = [&](const std::vector<int>& hb, uint64_t tmask = ~0ull) {
@@ -316,13 +319,21 @@ struct Planner {
             }
             if (runs > opt.max_runs) return;
             uint64_t mask = low; for (int b : hb) mask |= 1ull << b;
-            int c;
+            int c; double score;
             if (opt.group_cost > 0) {       // what the pass built on this tile would really take
                 PlanPass tmp; std::vector<int> tk;
                 build_pass(m, L, hb, tmp, tk, tmask);
-                c = (int)tk.size();
-            } else c = count_with(mask);
-            if (c > best) { best = c; hb_best = hb; tmask_best = tmask; }
+                c = (int)tk.size(); score = c;
+                // Sharded register with an exchange ahead: passes that work on the OUTGOING qubits (the top n_global local
+                // bits) go first, so that the last pass before the exchange does not need them and can be postponed to
+                // after it (try_defer_last_pass) — worth a few gates of difference between otherwise similar tiles.
+                if (outgoing_first && c > 0) {
+                    uint64_t out_q = 0;
+                    for (int i : tk) if (!gates[i].diag && gates[i].target >= nl - opt.n_global) out_q |= 1ull << gates[i].target;
+                    score += 4.0 * __builtin_popcountll(out_q);          // per outgoing qubit the pass finishes
+                }
+            } else { c = count_with(mask); score = c; }
+            if (score > best_score) { best_score = score; best = c; hb_best = hb; tmask_best = tmask; }
         };
         // (1) greedy: the first nh distinct non-diagonal high local targets in dependency order
         {
@@ -600,6 +611,36 @@ struct Planner {
         }
     }
 };
+
+// Sharded registers: should the LAST pass planned before an exchange be postponed to after it?  A pass brings at most
+// 12 - low_bits new qubits into its tile, so a reservoir layer over 33 local qubits takes 4 passes and the few gates on the
+// ex-global qubits a 5th.  When the last of the 4 does not target an outgoing qubit (the top g local bits become global), it
+// and the ex-global gates often fit ONE tile after the exchange: 4 passes per step instead of 5.  Both orders are planned on
+// copies of the planner; the postponement is kept only if the stretch after the exchange does not grow.  On true the gates
+// of the pass are pending again (the caller drops the pass and takes its global-phase factor back).
+inline bool try_defer_last_pass(Planner& pl, const std::vector<int>& taken, int nl, int g) {
+    if (g <= 0 || taken.empty()) return false;
+    for (int i : taken) { const LGate& x = pl.gates[i]; if (!x.diag && x.target >= nl - g) return false; }
+    auto swap_bit = [&](int b) { return b >= nl ? b - g : (b >= nl - g ? b + g : b); };      // dist_bits.hpp dist_swap_bit
+    auto passes_after = [&](bool defer) -> int {
+        Planner t = pl;
+        t.replay.clear(); t.replay_at = 0; t.budget_fixed = false; t.first = 0;
+        if (defer) for (int i : taken) t.done[i] = 0;
+        for (size_t i = 0; i < t.gates.size(); ++i) {
+            if (t.done[i]) continue;
+            t.gates[i].target = swap_bit(t.gates[i].target);
+            if (t.gates[i].ctrl >= 0) t.gates[i].ctrl = swap_bit(t.gates[i].ctrl);
+        }
+        int np = 0; PlanPass Pt;
+        while (np < 64 && t.next_pass(Pt)) ++np;
+        return np;
+    };
+    const int keep = passes_after(false), moved = passes_after(true);
+    if (moved > keep) return false;
+    for (int i : taken) pl.done[i] = 0;
+    pl.first = 0; pl.replay.clear(); pl.replay_at = 0; pl.budget_fixed = false;
+    return true;
+}
 
 // physical bit -> tile-local bit (or -1)
 inline int tile_local_of(const PlanPass& P, int phys) {

@@ -17,6 +17,7 @@
 #include "encode_v4.hpp"
 #include "jit.hpp"
 #include "jit_codegen.hpp"
+#include "dist_bits.hpp"
 #include "fused_tma.cuh"
 #include "kernels.cuh"
 #include "lifting.hpp"
@@ -182,6 +183,8 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
     case QM_OPT_SHORT_PCT:
         if (value != 0 && value < 100) return set_err(QM_ERR_ARG, "short-circuit per cent must be 0 (no limit) or >= 100");
         st->short_mult = value == 0 ? 1e9 : (double)value / 100.0; break;
+    case QM_OPT_DEFER_PASS:
+        st->defer_pass = value != 0; break;
     case QM_OPT_JIT:
         if (value < 0 || value > 1000000) return set_err(QM_ERR_ARG, "jit threshold must be >= 0");
         st->jit = (int)value; break;
@@ -445,7 +448,11 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     };
     // A planned pass ready to launch: the TMA kernel's program (a launch parameter), the general kernel's blob, or —
     // when the encoder refuses a pass the planner built for the TMA kernel — its gates one by one (kind 2)
-    struct Item { PlanPass P; int kind = 0; V4Program prog; std::vector<unsigned char> blob; JitKernel* jk = nullptr; };
+    struct Item {
+        PlanPass P; int kind = 0; V4Program prog; std::vector<unsigned char> blob; JitKernel* jk = nullptr;
+        std::vector<int> taken;                  // indices (into pl.gates) of the pass's gates, when it was planned here (not replayed)
+        double gf[2] = { 1.0, 0.0 };             // the global-phase factor the pass contributed (D1 form), so that a cancelled pass can take it back
+    };
     // Compiled pass kernels (jit.hpp).  A replayed plan knows all its passes in advance: they are encoded once up front and the
     // opcode sequences that have been seen often enough are compiled together on several host threads (a deep circuit has
     // hundreds of passes, ~0.25 s of PTX compilation each); otherwise a pass asks for its kernel when it is prepared.
@@ -473,18 +480,24 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
             const bool eligible = v4_eligible(st, it.P);
             // compiled kernel first: the program in canonical-sign form (what the kernel's opcode sequence is keyed by);
             // only when there is no kernel (yet) is the pass encoded for the interpreter
+            auto commit_phase = [&](const double f[2]) {          // global phase of the pass's diagonal gates (D1 form)
+                it.gf[0] = f[0]; it.gf[1] = f[1];
+                const double r = st->gphase[0] * f[0] - st->gphase[1] * f[1], i = st->gphase[0] * f[1] + st->gphase[1] * f[0];
+                st->gphase[0] = r; st->gphase[1] = i;
+            };
+            it.gf[0] = 1.0; it.gf[1] = 0.0;
             if (eligible && jit_thr > 0 && it.P.m == 12) {
-                double gph[2] = { st->gphase[0], st->gphase[1] };
-                if (encode_v4(it.P, it.prog, gph, true)) {
+                double f[2] = { 1.0, 0.0 };
+                if (encode_v4(it.P, it.prog, f, true)) {
                     if (!pre_jit.empty()) it.jk = replay_i >= 1 && replay_i <= pre_jit.size() ? pre_jit[replay_i - 1] : nullptr;
                     else it.jk = jit_get(st->device, it.P.m, it.prog, jit_thr);
-                    if (it.jk) { it.kind = 0; st->gphase[0] = gph[0]; st->gphase[1] = gph[1]; return QM_OK; }
+                    if (it.jk) { it.kind = 0; commit_phase(f); return QM_OK; }
                 }
             }
-            double gph[2] = { st->gphase[0], st->gphase[1] };
-            if (eligible && encode_v4(it.P, it.prog, gph)) {
+            double f[2] = { 1.0, 0.0 };
+            if (eligible && encode_v4(it.P, it.prog, f)) {
                 it.kind = 0;
-                st->gphase[0] = gph[0]; st->gphase[1] = gph[1];       // global phase of the pass's diagonal gates (D1 form)
+                commit_phase(f);
                 return QM_OK;
             }
             // The planner is supposed to respect the kernel's limits; if a pass slips through, it is still applied
@@ -579,6 +592,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         PlanPass P;
         if (plan_one(P)) {
             nxt.P = P;
+            nxt.taken.clear(); if (!hit) nxt.taken = pl.last_taken;
             QM_TRY(prepare(nxt));
             held.push_back(nxt); seg_had_pass = true;
             if (held.size() > hold_max) { QM_TRY(launch_full(held.front())); held.pop_front(); }
@@ -592,6 +606,15 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         // global qubits with the top local ones (all-to-all over NVLink) and relabel the pending gates.
         if (!seg_had_pass && !pl.pending_global_target()) return set_err(QM_ERR_STATE, "planner stalled (internal error)");
         seg_had_pass = false;
+        // the last pass planned before the exchange is postponed to after it when that saves a pass (planner.hpp try_defer_last_pass)
+        if (st->g > 0 && st->defer_pass && !held.empty() && try_defer_last_pass(pl, held.back().taken, st->nl, st->g)) {
+            // the pass had already put its global phase in: take it back (unit modulus: divide = multiply by the conjugate)
+            const Item& last = held.back();
+            const double r = st->gphase[0] * last.gf[0] + st->gphase[1] * last.gf[1], im = st->gphase[1] * last.gf[0] - st->gphase[0] * last.gf[1];
+            st->gphase[0] = r; st->gphase[1] = im;
+            held.pop_back();
+            st->ctr.deferred_passes++;
+        }
         bool ov = !held.empty() && tma && dist_can_overlap(st);
         for (const Item& it : held) ov = ov && it.kind == 0;
         if (!ov) {
@@ -605,7 +628,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         dist_relabel(st, &pl.gates, &pl.done);
         PlanPass P2;
         const bool got2 = plan_one(P2);
-        if (got2) { nxt.P = P2; QM_TRY(prepare(nxt)); seg_had_pass = true; }
+        if (got2) { nxt.P = P2; nxt.taken = pl.last_taken; QM_TRY(prepare(nxt)); seg_had_pass = true; }
         std::vector<int> sb;
         bool ok = got2 && nxt.kind == 0;
         while (ok) {
@@ -1417,7 +1440,7 @@ extern "C" int32_t qm_plan_describe_ex(int32_t n_qubits, int32_t global_bits, in
     pl.opt.tile_bits = tile_bits; pl.opt.low_bits = low_bits; pl.opt.fuse = true;
     if (max_cost > 0) pl.opt.max_cost = max_cost < 9.0 ? 9.0 : max_cost;
     if (pipeline) {
-        v4_planner_options(pl.opt, max_cost);
+        v4_planner_options(pl.opt, max_cost, pipeline == 2 ? 1 : 0);      // pipeline 2: priced for the compiled pass kernels
     }
     int rc = lower_gates(gates, ngates, n_qubits, nullptr, true, pl.gates);
     if (rc) return set_err(rc, "bad gate");

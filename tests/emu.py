@@ -24,6 +24,9 @@ def lib():
         l.qm_plan_emulate_sharded.restype = C.c_int32
         l.qm_plan_emulate_sharded.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32, _dp,
                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        l.qm_emu_set_defer.restype = C.c_int32
+        l.qm_emu_set_defer.argtypes = [C.c_int32]
+        l.qm_emu_last_deferred.restype = C.c_int32
         l.qm_emu_set_jit.restype = C.c_int32
         l.qm_emu_set_jit.argtypes = [C.c_int32]
         _lib = l
@@ -60,3 +63,26 @@ def set_jit(on):
     """0: walk the encoded records (the interpreter kernel's view); 1: execute the straight-line PTX text generated for the
     compiled pass kernels (csrc/jit_codegen.hpp) with the PTX-subset interpreter of tests/native/ptx_interp.hpp"""
     _check(lib().qm_emu_set_jit(1 if on else 0))
+
+
+def set_defer(on):
+    """sharded emulation: allow (default) or forbid postponing the last pass before an exchange (planner.hpp try_defer_last_pass)"""
+    _check(lib().qm_emu_set_defer(1 if on else 0))
+
+
+def last_deferred():
+    """passes postponed across an exchange by the last plan_emulate_sharded call"""
+    return int(lib().qm_emu_last_deferred())
+
+
+def plan_count_sharded(n, global_bits, gates, low_bits=5, max_cost=80.0, cost_model=1):
+    """planning only, any size: (passes, exchanges, postponed passes, [gates per pass, -1 = exchange])"""
+    l = lib()
+    l.qm_emu_plan_count_sharded.restype = C.c_int32
+    l.qm_emu_plan_count_sharded.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_int32,
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]
+    a, b, d = C.c_int32(), C.c_int32(), C.c_int32()
+    seq = (C.c_int32 * 64)()
+    _check(l.qm_emu_plan_count_sharded(n, global_bits, low_bits, max_cost, cost_model, gates.ctypes.data, len(gates),
+                                       C.byref(a), C.byref(b), C.byref(d), seq, 64))
+    return a.value, b.value, d.value, list(seq[:a.value + b.value])

@@ -77,3 +77,32 @@ def test_sharded_encoded_programs_emulated_on_cpu(pkg, emu_mode, n, g, kind, see
         assert np.array_equal(psi, ref)
     else:
         assert np.max(np.abs(psi - ref)) / np.max(np.abs(ref)) < 1e-12
+
+
+@pytest.mark.parametrize("n,g", [(19, 1), (20, 2), (21, 3)])
+def test_last_pass_before_an_exchange_is_postponed_when_that_saves_a_pass(pkg, emu_mode, n, g):
+    """a reservoir layer on a sharded register: the last pass before the exchange does not target an outgoing qubit, and
+    after the exchange it fits one tile together with the gates of the ex-global qubits (planner.hpp try_defer_last_pass):
+    one pass per step less, same amplitudes"""
+    from oracle import oracle as O
+    C = pkg.circuits
+    res = {}
+    for defer in (0, 1):
+        emu.set_defer(defer)
+        try:
+            psi = O.random_state(n, 90 + n)
+            ref = psi.copy()
+            passes = deferred = 0
+            for s in range(4):
+                gates = C.c4_step(n, s)
+                psi, npass, nrem = emu.plan_emulate_sharded(n, g, gates, psi, max_cost=80.0)
+                ref = O.apply_circuit(ref, gates)
+                passes += npass
+                deferred += emu.last_deferred()
+                assert nrem >= 1
+            assert np.max(np.abs(psi - ref)) / np.max(np.abs(ref)) < 1e-12
+            res[defer] = (passes, deferred)
+        finally:
+            emu.set_defer(1)
+    assert res[0][1] == 0 and res[1][1] > 0, res
+    assert res[1][0] < res[0][0], res
