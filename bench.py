@@ -292,6 +292,7 @@ def main():
     ap.add_argument("--jit", type=int, default=-1, help="QM_OPT_JIT (compiled pass kernels): -1 = default (C3: engine default 2; C4: 1, with --structure-warmup)")
     ap.add_argument("--structure-warmup", type=int, default=12,
                     help="C4: extra untimed reservoir steps in front of the W warm-up steps (the pass programs of a step repeat with period 6; 12 = every structure twice)")
+    ap.add_argument("--defer-pass", type=int, default=-1, help="sharded: QM_OPT_DEFER_PASS (default: engine default, 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-alt", action="store_true", help="skip the deep-fusion secondary measurement")
     ap.add_argument("--overlap", type=int, default=-1, help="sharded: QM_OPT_OVERLAP (default: engine default, 1)")

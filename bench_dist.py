@@ -50,6 +50,10 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
             st.set_option(key, v)
     if args.tile_bits:
         st.set_option(L.OPT_TILE_BITS, args.tile_bits)
+    if getattr(args, "low_bits", -1) >= 0:
+        st.set_option(L.OPT_LOW_BITS, args.low_bits)
+    if getattr(args, "defer_pass", -1) >= 0:
+        st.set_option(L.OPT_DEFER_PASS, args.defer_pass)
     if args.max_cost >= 0:
         st.set_option(L.OPT_MAX_COST, int(args.max_cost))
     if args.short_pct >= 0:
@@ -148,6 +152,7 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
             "overlapped_remaps_per_step": c.get("overlapped_remaps", 0) / args.steps,
             "overlapped_passes_per_step": c.get("overlapped_passes", 0) / args.steps,
             "compiled_passes_per_step": c.get("compiled_passes", 0) / args.steps,
+            "deferred_passes_per_step": c.get("deferred_passes", 0) / args.steps,
             "structure_warmup_steps": sw,
             "compiled_pass_kernels": dict(L.jit_stats(), note="rank 0's process; compiled during the untimed structure warm-up"),
         }

@@ -59,7 +59,7 @@ enum { QM_BASIS_Z = 0, QM_BASIS_X = 1, QM_BASIS_Y = 2 };
 enum {
     QM_OPT_EAGER      = 0,  /* 1: run every gate call at once with the unfused kernels (default 0: queue + fuse) */
     QM_OPT_TILE_BITS  = 1,  /* fused pass tile size m: 11 or 12 for the TMA kernels; default 0 = automatic (12) */
-    QM_OPT_LOW_BITS   = 2,  /* contiguous low bits every tile keeps (default 5: 512-byte rows)                    */
+    QM_OPT_LOW_BITS   = 2,  /* contiguous low bits every tile keeps (default 5: 512-byte rows; sharded registers 4)    */
     QM_OPT_FUSE       = 3,  /* 0: planner emits one pass per gate (debug), 1: fuse (default)                      */
     QM_OPT_TRACE      = 4,  /* 1: CTA 0 of every fused pass records SM-clock stamps per tile (qm_trace_read; diagnostics) */
     QM_OPT_PIPELINE   = 5,  /* 0: one CTA per tile kernel, 1: persistent TMA-pipelined kernel                     */

@@ -84,6 +84,10 @@ int qm_create_common(int n, uint64_t basis, int batch, int device, int rank, int
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
     qm_state* st = new qm_state();
     st->n = n; st->g = g; st->nl = n - g; st->rank = rank; st->world = world; st->batch = batch; st->device = device;
+    // sharded registers keep 4 low bits per tile by default (8 new qubits per pass instead of 7): with the last pass before an
+    // exchange postponed across it (try_defer_last_pass) a reservoir step then takes 4.0-4.5 passes instead of 5
+    // (profiles/r3l_*: 34 qubits on 2 GPUs 330 -> 295 ms per step; 3 low bits: 303 ms, the 128-byte rows cost more than they save)
+    if (g > 0) st->low_bits = 4;
     st->sms = prop.multiProcessorCount;
     st->perm.resize(n); for (int i = 0; i < n; ++i) st->perm[i] = i;
     // a sharded register carries its peer window (flags + mailboxes, dist.cu) right behind the shard, in the same
