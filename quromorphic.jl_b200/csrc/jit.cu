@@ -44,6 +44,8 @@ static const JitLinkApi& jitlink() {
         // minor version) under the same soname, and a bare soname would resolve to that one
         const char* names[] = { "/usr/local/cuda/lib64/libnvJitLink.so.12", "libnvJitLink.so.12", "/usr/local/cuda/lib64/libnvJitLink.so.13",
                                 "libnvJitLink.so.13", "libnvJitLink.so" };
+        const char* be = getenv("QM_JIT_BACKEND");            // "driver": skip nvJitLink, hand the PTX text to the driver's compiler
+        if (be && strcmp(be, "driver") == 0) return;
         const char* env = getenv("QM_NVJITLINK");
         if (env && *env) A.lib = dlopen(env, RTLD_NOW | RTLD_LOCAL);
         for (size_t i = 0; !A.lib && i < sizeof(names) / sizeof(names[0]); ++i) A.lib = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);

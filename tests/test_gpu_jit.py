@@ -152,3 +152,28 @@ def test_compiled_passes_on_a_sharded_register(pkg, n, world):
     for r, out in enumerate(res):
         assert out["ok"], (r, out)
     assert L.jit_stats()["failed"] == 0
+
+
+def test_driver_ptx_compiler_when_nvjitlink_is_not_used(pkg):
+    """without libnvJitLink the generated text goes to the driver's own PTX compiler (cuModuleLoadDataEx): same results.
+    The choice is made once per process, so this runs in a fresh interpreter with QM_JIT_BACKEND=driver."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import __graft_entry__ as ge\n"
+        "from oracle import oracle as O\n"
+        "from test_abi_cpu import random_circuit\n"
+        "pkg = ge.load_package(); L = pkg._lib\n"
+        "n = 15; gates = random_circuit(pkg, n, 200, 4242); psi0 = O.random_state(n, 9)\n"
+        "st = pkg.B200State.from_numpy(psi0); st.set_option(L.OPT_JIT, 1); st.apply_circuit(gates)\n"
+        "err = float(np.max(np.abs(st.to_numpy() - O.apply_circuit(psi0.copy(), gates))))\n"
+        "c = st.counters(); s = L.jit_stats()\n"
+        "assert err < 1e-12 and c['compiled_passes'] == c['passes'] > 0 and s['backend'] == 'driver' and s['failed'] == 0, (err, c, s)\n"
+        "print('DRIVER_JIT_OK', err, s)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QM_JIT_BACKEND="driver")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "DRIVER_JIT_OK" in out.stdout, out.stdout + out.stderr
