@@ -162,6 +162,9 @@ void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs,
     std::vector<JitKey> keys(progs.size());
     {
         std::lock_guard<std::mutex> lk(g_mu);
+        // sequences that were seen but never came back (one-shot circuits) must not pile up in a long-running process
+        if (g_cache.size() > 65536)
+            for (auto it = g_cache.begin(); it != g_cache.end();) { if (it->second.state == 0) it = g_cache.erase(it); else ++it; }
         std::vector<uint32_t> sig;
         for (size_t i = 0; i < progs.size(); ++i) {
             keys[i] = make_key(device, m, *progs[i], sig);
