@@ -161,6 +161,11 @@ int32_t qm_measure(qm_state* st, int32_t basis, int32_t t0, double threshold, in
 int32_t qm_measure_with(qm_state* st, int32_t t0, const double* R, double threshold, int32_t batch_idx,
                         double out[2]);
 int32_t qm_expect_z_all(qm_state* st, double threshold, double* out_host);
+/* the same readout in two halves, for loops whose host side prepares the next step while the device still runs this one:
+ * _begin enqueues the readout of the state as it is at this point of the stream and returns at once (gate calls may
+ * follow immediately), _end waits for the oldest pending one and copies it out.  At most two pending; unsharded registers. */
+int32_t qm_expect_z_all_begin(qm_state* st, double threshold);
+int32_t qm_expect_z_all_end(qm_state* st, double* out_host);
 int32_t qm_expect_all(qm_state* st, int32_t basis, double threshold, double* out_host);
 int32_t qm_expect_all_with(qm_state* st, const double* R, double threshold, double* out_host);
 int32_t qm_reduced_density(qm_state* st, int32_t keep_low, int32_t k, int32_t batch_idx,

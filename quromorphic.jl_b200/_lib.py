@@ -61,6 +61,8 @@ SIGNATURES = {
     "qm_measure": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, _dp]),
     "qm_measure_with": (C.c_int32, [_vp, C.c_int32, _dp, C.c_double, C.c_int32, _dp]),
     "qm_expect_z_all": (C.c_int32, [_vp, C.c_double, _dp]),
+    "qm_expect_z_all_begin": (C.c_int32, [_vp, C.c_double]),
+    "qm_expect_z_all_end": (C.c_int32, [_vp, _dp]),
     "qm_expect_all": (C.c_int32, [_vp, C.c_int32, C.c_double, _dp]),
     "qm_expect_all_with": (C.c_int32, [_vp, _dp, C.c_double, _dp]),
     "qm_reduced_density": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _dp]),

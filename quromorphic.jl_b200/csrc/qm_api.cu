@@ -123,6 +123,7 @@ extern "C" int32_t qm_destroy(qm_state* st) {
     cudaFree(st->amp); cudaFree(st->d_blob); cudaFree(st->d_scratch); cudaFree(st->d_slots);
     cudaFreeHost(st->h_blob); cudaFreeHost(st->h_scratch); cudaFreeHost(st->h_slots);
     for (int i = 0; i < 2; ++i) if (st->ev_slots[i]) cudaEventDestroy(st->ev_slots[i]);
+    for (int i = 0; i < 2; ++i) { if (st->ev_zq[i]) cudaEventDestroy(st->ev_zq[i]); cudaFreeHost(st->h_zq[i]); }
     for (void* q : st->retired_dev) cudaFree(q);
     for (void* q : st->retired_pinned) cudaFreeHost(q);
     if (st->ev0) cudaEventDestroy(st->ev0);
@@ -974,7 +975,19 @@ extern "C" int32_t qm_probs(qm_state* st, double* out_host, int32_t batch_idx) {
 }
 
 // all-qubit z marginals of every register into st->h_scratch: [batch][nl][2] then [batch] totals
+// enqueue the all-qubit Z statistics and their copy into h_dst (pinned, out_doubles doubles); no synchronisation
+static int zstats_enqueue(qm_state* st, double thr, double* h_dst, size_t* out_doubles_p);
+
 int qm_zstats(qm_state* st, double thr, double** h_pairs, double** h_tot) {
+    size_t out_doubles = (size_t)st->batch * st->nl * 2 + st->batch;
+    QM_TRY(ENSURE_PIN(st, h_scratch, out_doubles * 8));
+    QM_TRY(zstats_enqueue(st, thr, st->h_scratch, nullptr));
+    QM_TRY(qm_sync(st));
+    *h_pairs = st->h_scratch; *h_tot = st->h_scratch + (size_t)st->batch * st->nl * 2;
+    return QM_OK;
+}
+
+static int zstats_enqueue(qm_state* st, double thr, double* h_dst, size_t* out_doubles_p) {
     const int nl = st->nl;
     int cb = nl < kZMaxChunkBits ? nl : kZMaxChunkBits;
     int rest = nl - cb;                                    // chunk-index bits per register
@@ -986,7 +999,7 @@ int qm_zstats(qm_state* st, double thr, double** h_pairs, double** h_tot) {
     size_t part_bytes = (size_t)nctas * kZVals * 8;
     size_t out_doubles = (size_t)st->batch * nl * 2 + st->batch;
     QM_TRY(ENSURE_DEV(st, d_scratch, part_bytes + out_doubles * 8));
-    QM_TRY(ENSURE_PIN(st, h_scratch, out_doubles * 8));
+    if (out_doubles_p) *out_doubles_p = out_doubles;
     double* d_part = st->d_scratch;
     double* d_out = st->d_scratch + (size_t)nctas * kZVals;
     double* d_tot = d_out + (size_t)st->batch * nl * 2;
@@ -996,10 +1009,38 @@ int qm_zstats(qm_state* st, double thr, double** h_pairs, double** h_tot) {
     k_zfinal<<<st->batch, 256, 0, st->stream>>>(d_part, nl, cb, hbits, ctas_log2, d_out, d_tot);
     CU(cudaGetLastError());
     st->ctr.launches += 2; st->ctr.bytes_hbm += 16ull * total_amps(st);
-    CU(cudaMemcpyAsync(st->h_scratch, d_out, out_doubles * 8, cudaMemcpyDeviceToHost, st->stream));
+    CU(cudaMemcpyAsync(h_dst, d_out, out_doubles * 8, cudaMemcpyDeviceToHost, st->stream));
     st->ctr.bytes_d2h += out_doubles * 8;
-    QM_TRY(qm_sync(st));
-    *h_pairs = st->h_scratch; *h_tot = st->h_scratch + (size_t)st->batch * nl * 2;
+    return QM_OK;
+}
+
+// Split readout for pipelines (a reservoir loop whose host side prepares step t + 1 while the device still runs step t):
+// _begin enqueues the all-qubit <Z> of the state AS IT IS AT THIS POINT OF THE STREAM and returns at once, later gate calls
+// may follow immediately; _end hands out the oldest pending result (at most two may be pending).  Unsharded registers.
+extern "C" int32_t qm_expect_z_all_begin(qm_state* st, double threshold) {
+    if (!st) return set_err(QM_ERR_ARG, "null state");
+    if (st->dist) return set_err(QM_ERR_STATE, "split readout is for unsharded registers");
+    if (st->zq_count >= 2) return set_err(QM_ERR_STATE, "two readouts are already pending: call qm_expect_z_all_end first");
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    const int slot = (st->zq_head + st->zq_count) & 1;
+    const size_t out_doubles = (size_t)st->batch * st->nl * 2 + st->batch;
+    QM_TRY(ensure_pinned((void**)&st->h_zq[slot], &st->h_zq_cap[slot], out_doubles * 8, &st->retired_pinned));
+    if (!st->ev_zq[slot]) CU(cudaEventCreateWithFlags(&st->ev_zq[slot], cudaEventDisableTiming));
+    QM_TRY(zstats_enqueue(st, threshold, st->h_zq[slot], nullptr));
+    CU(cudaEventRecord(st->ev_zq[slot], st->stream));
+    st->zq_count++;
+    return QM_OK;
+}
+
+extern "C" int32_t qm_expect_z_all_end(qm_state* st, double* out_host) {
+    if (!st || !out_host) return set_err(QM_ERR_ARG, "null argument");
+    if (st->zq_count <= 0) return set_err(QM_ERR_STATE, "no readout is pending");
+    CU(cudaSetDevice(st->device));
+    const int slot = st->zq_head;
+    CU(cudaEventSynchronize(st->ev_zq[slot]));
+    memcpy(out_host, st->h_zq[slot], (size_t)st->batch * st->nl * 2 * sizeof(double));
+    st->zq_head ^= 1; st->zq_count--;
     return QM_OK;
 }
 

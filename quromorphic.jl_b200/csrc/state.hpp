@@ -72,6 +72,9 @@ struct qm_state {
     double* d_slots = nullptr; size_t d_slots_cap = 0;
     double* h_slots = nullptr; size_t h_slots_cap = 0;       // pinned staging of the per-state coefficients, two halves used alternately
     cudaEvent_t ev_slots[2] = { nullptr, nullptr }; int slots_half = 0;
+    // split readout (qm_expect_z_all_begin / _end): two pinned result buffers used as a FIFO
+    double* h_zq[2] = { nullptr, nullptr }; size_t h_zq_cap[2] = { 0, 0 }; cudaEvent_t ev_zq[2] = { nullptr, nullptr };
+    int zq_head = 0, zq_count = 0;
     std::vector<void*> retired_dev, retired_pinned;          // outgrown scratch buffers, released by qm_destroy (ensure_dev)
     qm_counters_t ctr{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> remap_events;   // resolved into ctr.ms_remap at the next sync

@@ -192,6 +192,18 @@ class B200State:
         L.check(L.lib().qm_expect_z_all(self._h, thr, L.dptr(out)))
         return out if self.batch > 1 else out[0]
 
+    def expect_z_all_begin(self, threshold=None):
+        """first half of a split readout: enqueue the all-qubit <Z> of the state as it is now and return at once (gate calls
+        may follow immediately; at most two readouts pending)"""
+        thr = self.threshold if threshold is None else threshold
+        L.check(L.lib().qm_expect_z_all_begin(self._h, thr))
+
+    def expect_z_all_end(self):
+        """second half: the oldest pending readout, [batch, n, 2]"""
+        out = np.empty((self.batch, self.n, 2), dtype=np.float64)
+        L.check(L.lib().qm_expect_z_all_end(self._h, L.dptr(out)))
+        return out if self.batch > 1 else out[0]
+
     def expect_all(self, basis, threshold=None):
         """[batch, n, 2] array of (p0, p1): measure_z / measure_x / measure_y of EVERY qubit (QSim.jl:297-330).
         basis: "z", "x", "y" or a 2x2 rotation matrix R (the marginals of R applied to each qubit in turn).  The

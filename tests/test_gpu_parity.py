@@ -568,3 +568,34 @@ def test_all_qubit_x_marginals_batched(pkg):
     for b in range(B):
         want = np.array([O.measure_y(refs[b], t) for t in range(1, n + 1)])
         assert np.max(np.abs(got[b] - want)) < RTOL
+
+
+def test_split_readout_matches_the_synchronous_one(pkg):
+    """qm_expect_z_all_begin / _end: the readout of step t is taken from the stream position of _begin even though the gates
+    of step t + 1 are enqueued before _end; two may be pending, a third _begin is refused"""
+    n, B = 12, 16
+    C = pkg.circuits
+    gates = C.c2_step_gates(n, seed=1603)
+    w = [C.SplitMix64(5).uniform() for _ in range(n)]
+    encs = [C.c2_encoding(B, n, t, w) for t in range(4)]
+    ref_state = pkg.B200State(n, 0, batch=B)
+    want = []
+    for t in range(4):
+        ref_state.apply_batched(gates, encs[t])
+        want.append(ref_state.expect_z_all())
+    st = pkg.B200State(n, 0, batch=B)
+    got = []
+    for t in range(4):
+        st.apply_batched(gates, encs[t])
+        st.expect_z_all_begin()
+        if t > 0:
+            got.append(st.expect_z_all_end())
+    got.append(st.expect_z_all_end())
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    st.expect_z_all_begin(); st.expect_z_all_begin()
+    with pytest.raises(pkg._lib.QMError):
+        st.expect_z_all_begin()
+    st.expect_z_all_end(); st.expect_z_all_end()
+    with pytest.raises(pkg._lib.QMError):
+        st.expect_z_all_end()
