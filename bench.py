@@ -410,7 +410,9 @@ def main():
         line["config"]["workload"] += " [NON-DEFAULT size: depth %d, %d qubits]" % (args.depth, n)
     line["config"]["planner_max_cost"] = st_max_cost(args)
 
-    # ---- same workload with deeper fusion (fewer, FP64-heavier passes): the other end of the trade-off ----
+    # ---- same workload with deeper fusion (two register-block groups per pass: fewer, FP64-heavier passes).  With the compiled
+    # kernels this no longer pays (a second group costs as much as 13 gates and the FP64 pipe is already ~60 % busy): the
+    # block is kept as the measured other end of the trade-off ----
     if not args.no_alt:
         st.set_option(L.OPT_MAX_COST, ALT_MAX_COST)
         step(); st.sync()
