@@ -120,6 +120,8 @@ struct PlanOptions {
     double short_mult = 1e9;         // circuits shorter than the window may use up to short_mult x the budget (Planner::budget_for_pending)
     double hbm_units = 114.0;        // fitted pass model in budget units (0.05 ms at 30 qubits): HBM time of a pass,
     double fixed_units = 41.0;       // compute-side time = fixed_units + group_cost per group + gate costs
+    int low_bits_short = 4;          // low tile bits of a circuit shorter than the look-ahead window (0: opt.low_bits)
+    bool defer_low3 = true;          // ... and let the stretch after a postponement keep 3 low bits when that is what makes the tile fit
     bool defer_bias = true;          // sharded: schedule the passes on the outgoing qubits first (choose_tile, try_defer_last_pass)
     int cost_model = 0;              // gate_cost: 0 the interpreter kernel, 1 the compiled pass kernels
     bool warp_uniform_ctrl = false;  // controls inside the tile must be block bits or one of the (m - block_bits - 5) warp-index bits
@@ -279,6 +281,7 @@ struct Planner {
     std::vector<int> last_taken;     // gate indices of the pass next_pass built last
     std::vector<std::pair<PlanPass, std::vector<int>>> replay;   // the chosen plan of a short stretch, handed out by next_pass
     size_t replay_at = 0;
+    int saved_low_bits = -1;         // try_defer_last_pass lowered opt.low_bits for one stretch: restored when the stretch ends
 
     int total_bits() const { return opt.n_local + opt.n_global; }
 
@@ -348,6 +351,16 @@ struct Planner {
                      if ((int)hb.size() < nh) { hb.push_back(t); have |= 1ull << t; return true; }
                      return false;
                  }, taken);
+            // filler bits: first the ones that lengthen an existing run of high bits (a tile may have at most max_runs runs:
+            // a lone filler at bit L next to targets at 12-15, 24-25 and 32 would be a fourth), then the lowest free ones
+            for (bool grown = true; grown && (int)hb.size() < nh;) {
+                grown = false;
+                for (int b = L; b < nl && (int)hb.size() < nh; ++b) {
+                    if ((have >> b) & 1) continue;
+                    const bool below = b > L && ((have >> (b - 1)) & 1), above = b + 1 < nl && ((have >> (b + 1)) & 1);
+                    if ((below || above) && !hb.empty()) { hb.push_back(b); have |= 1ull << b; grown = true; }
+                }
+            }
             for (int b = L; b < nl && (int)hb.size() < nh; ++b) if (!((have >> b) & 1)) { hb.push_back(b); have |= 1ull << b; }
             std::sort(hb.begin(), hb.end());
             try_set(hb);
@@ -400,6 +413,10 @@ struct Planner {
         }
         uint64_t tmask = ~0ull;
         if (!budget_fixed) budget_now = budget_for_pending();
+        // a short circuit (a reservoir step) wants as many NEW qubits per pass as it can get — its passes are few and every one
+        // of them costs at least the HBM time — so its tiles keep 4 low bits instead of 5 (8 new qubits per pass: a 33-qubit
+        // layer is 12 + 8 + 8 + 5 and never leaves a lone gate for a fifth pass); deep circuits keep opt.low_bits
+        if (mode_known && short_circuit && opt.low_bits_short > 0 && L > opt.low_bits_short && m - opt.low_bits_short >= 1) L = opt.low_bits_short;
         if (replay_at < replay.size()) {            // the stretch was already planned while choosing its budget
             P = replay[replay_at].first;
             last_taken = replay[replay_at].second;
@@ -409,7 +426,11 @@ struct Planner {
         }
         if (!replay.empty()) { replay.clear(); replay_at = 0; budget_fixed = false; return false; }
         choose_tile(m, L, hb, best, tmask);
-        if (best <= 0) { budget_fixed = false; return false; }     // end of a stretch (a remap follows): choose again
+        if (best <= 0) {                                            // end of a stretch (a remap follows): choose again
+            budget_fixed = false;
+            if (saved_low_bits >= 0) { opt.low_bits = saved_low_bits; saved_low_bits = -1; }
+            return false;
+        }
         std::vector<int> taken;
         build_pass(m, L, hb, P, taken, tmask);
         for (int i : taken) done[i] = 1;
@@ -622,9 +643,10 @@ inline bool try_defer_last_pass(Planner& pl, const std::vector<int>& taken, int 
     if (g <= 0 || taken.empty()) return false;
     for (int i : taken) { const LGate& x = pl.gates[i]; if (!x.diag && x.target >= nl - g) return false; }
     auto swap_bit = [&](int b) { return b >= nl ? b - g : (b >= nl - g ? b + g : b); };      // dist_bits.hpp dist_swap_bit
-    auto passes_after = [&](bool defer) -> int {
+    auto passes_after = [&](bool defer, int low_bits) -> int {
         Planner t = pl;
         t.replay.clear(); t.replay_at = 0; t.budget_fixed = false; t.first = 0;
+        t.opt.low_bits = low_bits;
         if (defer) for (int i : taken) t.done[i] = 0;
         for (size_t i = 0; i < t.gates.size(); ++i) {
             if (t.done[i]) continue;
@@ -635,10 +657,20 @@ inline bool try_defer_last_pass(Planner& pl, const std::vector<int>& taken, int 
         while (np < 64 && t.next_pass(Pt)) ++np;
         return np;
     };
-    const int keep = passes_after(false), moved = passes_after(true);
+    const int keep = passes_after(false, pl.opt.low_bits);
+    int moved = passes_after(true, pl.opt.low_bits);
+    // One qubit too many for the tile?  The stretch after the exchange may keep 3 low bits instead of 4 (9 new qubits per
+    // pass): its 128-byte rows make that pass ~10 % slower, a whole pass is saved.  pl.stretch_low_bits lasts until the next
+    // exchange (Planner::end_stretch).
+    int low = pl.opt.low_bits;
+    if (moved > keep && pl.opt.low_bits > 3 && pl.opt.defer_low3) {
+        const int m3 = passes_after(true, 3);
+        if (m3 <= keep) { moved = m3; low = 3; }
+    }
     if (moved > keep) return false;
     for (int i : taken) pl.done[i] = 0;
     pl.first = 0; pl.replay.clear(); pl.replay_at = 0; pl.budget_fixed = false;
+    if (low != pl.opt.low_bits) { pl.saved_low_bits = pl.opt.low_bits; pl.opt.low_bits = low; }
     return true;
 }
 
