@@ -279,6 +279,15 @@ static int jit_threshold(const qm_state* st) {
     return total_amps(st) >= (1ull << 26) ? st->jit : 0;
 }
 
+// L2 promotion of the tile loads: 256 B unless QM_TMA_L2PROMO says otherwise (0 none, 1 64 B, 2 128 B, 3 256 B; a tuning knob of
+// the measurement tools, read once)
+static CUtensorMapL2promotion tma_l2_promotion() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("QM_TMA_L2PROMO"); v = (e && *e >= '0' && *e <= '3') ? (*e - '0') : 3; }
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 // can this pass go through the TMA kernel?
 static bool v4_eligible(const qm_state* st, const PlanPass& P) {
     if (!st->pipeline || !get_encode()) return false;
@@ -325,7 +334,7 @@ int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const
     }
     CUtensorMap tm;
     CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, st->amp, gdim, gstr, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, tma_l2_promotion(),
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(QM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     int rs[8], rl[8];
