@@ -128,6 +128,10 @@ int32_t qm_download(qm_state* st, double* host_interleaved, uint64_t n_amps, int
  * qm_apply_batched     a gate list applied to every register of the batch; QM_GATE_U2_SLOT
  *                      gates take their matrix from per_state_mats[b][slot][8] (host, doubles)
  */
+/* compiled pass kernels ahead of time: plans `gates` as qm_apply_circuit would, compiles the kernels of its passes (QM_OPT_JIT)
+ * and keeps the plan, without touching the register — the first application then already runs compiled.  *n_compiled
+ * (optional) = kernels compiled by this call.  No-op when compiled kernels are not in use for this register. */
+int32_t qm_precompile_circuit(qm_state* st, const qm_gate* gates, int32_t ngates, int32_t* n_compiled);
 int32_t qm_apply_u2(qm_state* st, int32_t t0, const double U[8]);
 int32_t qm_apply_controlled(qm_state* st, int32_t c0, int32_t t0, const double V[8]);
 int32_t qm_apply_swap(qm_state* st, int32_t a0, int32_t b0);
@@ -265,6 +269,14 @@ int32_t qm_abi_version(void);
 /* compiled pass kernels, process-wide: out = {compiled, failed, kernels in the cache, backend (1 nvJitLink, 2 driver PTX
  * compiler, 0 none yet)}; *compile_ms = wall time spent compiling so far */
 int32_t qm_jit_stats(uint64_t out[4], double* compile_ms);
+/* optional disk cache of the compiled pass kernels, process-wide: a directory (created if missing; NULL or "" = none, the
+ * default unless the environment variable QM_JIT_CACHE_DIR names one) that keeps every assembled kernel as a file keyed by a
+ * hash of the complete PTX text and of the assembler's version, so that a later process running a circuit of the same
+ * structure loads its kernels instead of assembling them again.  Processes may share the directory (files are renamed into
+ * place); a file that does not verify is ignored.  qm_jit_cache_stats: out = {kernels read from the directory, kernels
+ * written to it} since the process started. */
+int32_t qm_jit_cache_dir(const char* path);
+int32_t qm_jit_cache_stats(uint64_t out[2]);
 /* host-only check of the compiled pass kernels (no GPU needed): every 2^12-tile pass of the planned circuit is turned into PTX
  * text and, with compile != 0 and libnvJitLink present, assembled for sm_100a.  out = {passes, passes with PTX text, passes
  * assembled, distinct opcode sequences, bytes of the largest cubin, hash over all passes' opcode sequences (canonical signs: it

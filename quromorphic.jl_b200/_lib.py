@@ -56,6 +56,7 @@ SIGNATURES = {
     "qm_apply_controlled": (C.c_int32, [_vp, C.c_int32, C.c_int32, _dp]),
     "qm_apply_swap": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
     "qm_apply_circuit": (C.c_int32, [_vp, _vp, C.c_int32]),
+    "qm_precompile_circuit": (C.c_int32, [_vp, _vp, C.c_int32, C.POINTER(C.c_int32)]),
     "qm_apply_batched": (C.c_int32, [_vp, _vp, C.c_int32, _dp, C.c_int32]),
     "qm_probs": (C.c_int32, [_vp, _dp, C.c_int32]),
     "qm_measure": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, _dp]),
@@ -93,6 +94,8 @@ SIGNATURES = {
     "qm_counters": (C.c_int32, [_vp, C.POINTER(Counters)]),
     "qm_counters_reset": (C.c_int32, [_vp]),
     "qm_jit_stats": (C.c_int32, [C.POINTER(C.c_uint64), _dp]),
+    "qm_jit_cache_dir": (C.c_int32, [C.c_char_p]),
+    "qm_jit_cache_stats": (C.c_int32, [C.POINTER(C.c_uint64)]),
     "qm_jit_check": (C.c_int32, [C.c_int32, C.c_int32, C.c_double, _vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_char_p, C.c_int64]),
     "qm_abi_version": (C.c_int32, []),
     "qm_device_ptr": (C.c_int32, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
@@ -199,6 +202,17 @@ def jit_stats():
     check(lib().qm_jit_stats(out, C.byref(ms)))
     return {"compiled": out[0], "failed": out[1], "cached": out[2], "backend": {0: "none", 1: "nvJitLink", 2: "driver"}[int(out[3])],
             "compile_ms": ms.value}
+
+
+def jit_cache_dir(path):
+    """keep compiled pass kernels as files under `path` (None = no disk cache); process-wide, see include/qm_b200.h"""
+    check(lib().qm_jit_cache_dir(None if path is None else str(path).encode()))
+
+
+def jit_cache_stats():
+    out = (C.c_uint64 * 2)()
+    check(lib().qm_jit_cache_stats(out))
+    return {"disk_hits": out[0], "disk_stores": out[1]}
 
 
 def plan_ophist(n, gates, tile_bits=12, low_bits=5, max_cost=0.0):

@@ -2,7 +2,11 @@
 #include "jit.hpp"
 
 #include <dlfcn.h>
+#include <stdio.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -35,6 +39,7 @@ struct JitLinkApi {
     void* lib = nullptr;
     PFN_jlCreate create = nullptr; PFN_jlDestroy destroy = nullptr; PFN_jlAddData add = nullptr; PFN_jlComplete complete = nullptr;
     PFN_jlGetSize cubin_size = nullptr, log_size = nullptr; PFN_jlGet cubin = nullptr, log = nullptr;
+    unsigned ver[2] = { 0, 0 };                 // nvJitLinkVersion (part of the disk-cache key: another assembler, another cubin)
     bool ok = false;
 };
 static const JitLinkApi& jitlink() {
@@ -55,6 +60,8 @@ static const JitLinkApi& jitlink() {
         A.cubin_size = (PFN_jlGetSize)dlsym(A.lib, "nvJitLinkGetLinkedCubinSize"); A.cubin = (PFN_jlGet)dlsym(A.lib, "nvJitLinkGetLinkedCubin");
         A.log_size = (PFN_jlGetSize)dlsym(A.lib, "nvJitLinkGetErrorLogSize"); A.log = (PFN_jlGet)dlsym(A.lib, "nvJitLinkGetErrorLog");
         A.ok = A.create && A.destroy && A.add && A.complete && A.cubin_size && A.cubin;
+        typedef int (*PFN_jlVersion)(unsigned*, unsigned*);
+        if (PFN_jlVersion v = (PFN_jlVersion)dlsym(A.lib, "nvJitLinkVersion")) v(&A.ver[0], &A.ver[1]);
     });
     return A;
 }
@@ -83,6 +90,95 @@ bool jit_compile_cubin(const std::string& ptx, std::vector<char>& cubin, std::st
     }
     A.destroy(&h);
     return ok;
+}
+
+// ---- disk cache of assembled kernels (optional) ---------------------------------------------------
+// QM_JIT_CACHE_DIR / qm_jit_cache_dir(): cubins are kept as files keyed by a 128-bit hash of the COMPLETE PTX text handed to
+// the assembler (template + generated groups: a rebuilt library or a changed generator can never meet a stale file) and of
+// the assembler's version.  A later process that plans the same circuit structure loads them instead of assembling again
+// (~0.25 s of one core per kernel; C3 has 110).  Files are written under a temporary name and renamed, so concurrent
+// processes (one per GPU) can share a directory; a file that does not verify (size, hashes, checksum) is ignored.
+static std::mutex g_dir_mu;
+static std::string g_dir; static bool g_dir_set = false;
+static std::atomic<uint64_t> g_disk_hits{0}, g_disk_stores{0};
+
+static std::string disk_dir() {
+    std::lock_guard<std::mutex> lk(g_dir_mu);
+    if (!g_dir_set) { const char* e = getenv("QM_JIT_CACHE_DIR"); g_dir = e ? e : ""; g_dir_set = true; }
+    return g_dir;
+}
+void jit_set_cache_dir(const char* path) {
+    std::lock_guard<std::mutex> lk(g_dir_mu);
+    g_dir = path ? path : ""; g_dir_set = true;
+}
+void jit_disk_stats(uint64_t out[2]) { out[0] = g_disk_hits.load(); out[1] = g_disk_stores.load(); }
+
+static void hash128(const void* data, size_t n, uint64_t h[2]) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    uint64_t h1 = 0xcbf29ce484222325ull, h2 = 0x9e3779b97f4a7c15ull;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w; memcpy(&w, p + i, 8);
+        h1 = (h1 ^ w) * 0x100000001b3ull; h1 ^= h1 >> 29;
+        h2 ^= w + 0x9e3779b97f4a7c15ull + (h2 << 6) + (h2 >> 2); h2 *= 0xff51afd7ed558ccdull; h2 ^= h2 >> 33;
+    }
+    for (; i < n; ++i) { h1 = (h1 ^ p[i]) * 0x100000001b3ull; h2 = (h2 ^ p[i]) * 0xc4ceb9fe1a85ec53ull; h2 ^= h2 >> 31; }
+    h[0] = h1; h[1] = h2 ^ ((uint64_t)n << 40);
+}
+
+struct DiskHeader { uint64_t magic, ptx_h[2], ptx_len, ver, cubin_len, cubin_h[2]; };
+static const uint64_t kDiskMagic = 0x31434a4d51ull;      // "QMJC1"
+
+static std::string disk_path(const std::string& dir, const uint64_t h[2], uint64_t ver) {
+    char name[96];
+    snprintf(name, sizeof(name), "/qmjit-%016llx%016llx-%llx.cubin", (unsigned long long)h[0], (unsigned long long)h[1], (unsigned long long)ver);
+    return dir + name;
+}
+
+static bool disk_load(const std::string& ptx, std::vector<char>& cubin) {
+    const std::string dir = disk_dir();
+    if (dir.empty()) return false;
+    uint64_t h[2]; hash128(ptx.data(), ptx.size(), h);
+    const JitLinkApi& A = jitlink();
+    const uint64_t ver = ((uint64_t)A.ver[0] << 32) | A.ver[1];
+    FILE* f = fopen(disk_path(dir, h, ver).c_str(), "rb");
+    if (!f) return false;
+    DiskHeader H; bool ok = fread(&H, sizeof(H), 1, f) == 1 && H.magic == kDiskMagic && H.ptx_h[0] == h[0] && H.ptx_h[1] == h[1] &&
+                            H.ptx_len == ptx.size() && H.ver == ver && H.cubin_len > 0 && H.cubin_len < (64u << 20);
+    if (ok) { cubin.resize((size_t)H.cubin_len); ok = fread(cubin.data(), 1, cubin.size(), f) == cubin.size() && fgetc(f) == EOF; }
+    fclose(f);
+    if (ok) { uint64_t c[2]; hash128(cubin.data(), cubin.size(), c); ok = c[0] == H.cubin_h[0] && c[1] == H.cubin_h[1]; }
+    if (!ok) cubin.clear(); else g_disk_hits++;
+    return ok;
+}
+
+static void disk_store(const std::string& ptx, const std::vector<char>& cubin) {
+    const std::string dir = disk_dir();
+    if (dir.empty() || cubin.empty()) return;
+    mkdir(dir.c_str(), 0777);                              // one level; an existing directory is fine
+    DiskHeader H; memset(&H, 0, sizeof(H));
+    H.magic = kDiskMagic; hash128(ptx.data(), ptx.size(), H.ptx_h); H.ptx_len = ptx.size();
+    const JitLinkApi& A = jitlink();
+    H.ver = ((uint64_t)A.ver[0] << 32) | A.ver[1];
+    H.cubin_len = cubin.size(); hash128(cubin.data(), cubin.size(), H.cubin_h);
+    const std::string path = disk_path(dir, H.ptx_h, H.ver);
+    static std::atomic<uint64_t> serial{0};
+    char suffix[64]; snprintf(suffix, sizeof(suffix), ".tmp.%ld.%llu", (long)getpid(), (unsigned long long)serial++);
+    const std::string tmp = path + suffix;
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;                                         // a directory that cannot be written is not an error: no cache
+    const bool ok = fwrite(&H, sizeof(H), 1, f) == 1 && fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    if (fclose(f) != 0 || !ok || rename(tmp.c_str(), path.c_str()) != 0) { remove(tmp.c_str()); return; }
+    g_disk_stores++;
+}
+
+bool jit_cubin_for(const std::string& ptx, std::vector<char>& cubin, std::string& log, bool* from_disk) {
+    if (from_disk) *from_disk = false;
+    if (!jitlink().ok) { cubin.clear(); log = "libnvJitLink not found"; return false; }
+    if (disk_load(ptx, cubin)) { if (from_disk) *from_disk = true; log.clear(); return true; }
+    if (!jit_compile_cubin(ptx, cubin, log)) return false;
+    disk_store(ptx, cubin);
+    return true;
 }
 
 // ---- driver API (entry points through the runtime: the library never links libcuda) --------------
@@ -157,7 +253,7 @@ void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs,
     out.assign(progs.size(), nullptr);
     if (threshold <= 0 || template_for(m).empty() || !driver().ok) return;
     // which programs need compiling now (one compile per distinct opcode sequence)
-    struct Job { JitKey key; const V4Program* prog; std::vector<char> image; bool is_ptx = false, ok = false; };
+    struct Job { JitKey key; const V4Program* prog; std::vector<char> image; std::string ptx; bool is_ptx = false, ok = false, from_disk = false; };
     std::vector<Job> jobs;
     std::vector<JitKey> keys(progs.size());
     {
@@ -187,9 +283,9 @@ void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs,
         auto work = [&](int t) {
             for (size_t i = (size_t)t; i < jobs.size(); i += (size_t)nth) {
                 Job& j = jobs[i];
-                std::string ptx, log;
+                std::string& ptx = j.ptx; std::string log;
                 if (!jit_build_ptx(template_for(m), *j.prog, ptx)) continue;
-                if (have_jl) j.ok = jit_compile_cubin(ptx, j.image, log);
+                if (have_jl) j.ok = jit_cubin_for(ptx, j.image, log, &j.from_disk);
                 else { j.image.assign(ptx.begin(), ptx.end()); j.image.push_back('\0'); j.is_ptx = true; j.ok = true; }
             }
         };
@@ -197,7 +293,11 @@ void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs,
         else { std::vector<std::thread> th; for (int t = 0; t < nth; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
         // modules are loaded on this thread (the context of the caller's device is current here)
         for (Job& j : jobs) {
-            JitKernel k; const bool ok = j.ok && load_kernel(j.image, j.is_ptx, m, k);
+            JitKernel k; bool ok = j.ok && load_kernel(j.image, j.is_ptx, m, k);
+            if (!ok && j.ok && j.from_disk) {        // a file that verified but does not load (another driver?): assemble it here
+                std::string log;
+                ok = jit_compile_cubin(j.ptx, j.image, log) && load_kernel(j.image, false, m, k);
+            }
             std::lock_guard<std::mutex> lk(g_mu);
             JitEntry& e = g_cache[j.key];
             if (ok) { e.k = k; e.state = 1; g_stats.compiled++; } else { e.state = 2; g_stats.failed++; }

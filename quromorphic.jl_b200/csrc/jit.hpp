@@ -43,4 +43,10 @@ JitStats jit_stats();
 bool jit_ptx_for(int m, const V4Program& prog, std::string& ptx);
 bool jit_compile_cubin(const std::string& ptx, std::vector<char>& cubin, std::string& log);
 
+// The same through the optional disk cache (QM_JIT_CACHE_DIR or jit_set_cache_dir; empty = none): cubins are files keyed by a
+// hash of the complete PTX text and the assembler's version.  *from_disk (optional) says whether the file was there.
+bool jit_cubin_for(const std::string& ptx, std::vector<char>& cubin, std::string& log, bool* from_disk);
+void jit_set_cache_dir(const char* path);
+void jit_disk_stats(uint64_t out[2]);            // {cubins read from the directory, cubins written to it} since the process started
+
 }  // namespace qm

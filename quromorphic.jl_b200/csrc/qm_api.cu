@@ -198,6 +198,12 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
     return QM_OK;
 }
 
+extern "C" int32_t qm_jit_cache_dir(const char* path) { jit_set_cache_dir(path); return QM_OK; }
+extern "C" int32_t qm_jit_cache_stats(uint64_t out[2]) {
+    if (!out) return set_err(QM_ERR_ARG, "null argument");
+    jit_disk_stats(out);
+    return QM_OK;
+}
 extern "C" int32_t qm_jit_stats(uint64_t out[4], double* compile_ms) {
     if (!out) return set_err(QM_ERR_ARG, "null argument");
     const JitStats s = jit_stats();
@@ -239,10 +245,12 @@ static int launch_pass(qm_state* st, const unsigned char* d_pass, const PlanPass
     uint64_t ntiles = total_amps(st) >> m;
     size_t smem = ((size_t)16 << m) + ((size_t)8 << P.hb.size());
     const int threads = 256;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute belongs to the device, not to the process (qm_create takes `device`)
+    static bool attr[64] = { false };
+    const int dev = st->device;
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
         CU(cudaFuncSetAttribute(k_fused_pass<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
     }
     int per_sm = (int)((220 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 8) per_sm = 8;
     uint64_t cap = (uint64_t)st->sms * per_sm;
@@ -275,6 +283,7 @@ static PFN_encodeTiled get_encode() {
 // (~0.25 s of one host core, 16 at a time) to pay for itself within a few hundred launches: 2^26 amplitudes and more
 // (a 1 GiB pass takes 0.36 ms; a 20-qubit reservoir step takes microseconds and would never earn it back).
 static int jit_threshold(const qm_state* st) {
+    if (st->dry_run) return 1;                 // qm_precompile_circuit: plan for the compiled kernels and compile at first sight
     if (st->jit <= 1) return st->jit;
     return total_amps(st) >= (1ull << 26) ? st->jit : 0;
 }
@@ -471,7 +480,9 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
     // opcode sequences that have been seen often enough are compiled together on several host threads (a deep circuit has
     // hundreds of passes, ~0.25 s of PTX compilation each); otherwise a pass asks for its kernel when it is prepared.
     std::vector<JitKernel*> pre_jit;
-    const int jit_thr = jit_threshold(st);
+    // qm_precompile_circuit, first walk (dry_run 1): only the plan is wanted — it goes into the plan cache and the second walk
+    // (dry_run 2) finds it there and compiles all its kernels together on several host threads, not one pass at a time
+    const int jit_thr = st->dry_run == 1 ? 0 : jit_threshold(st);
     if (hit && tma && jit_thr > 0) {
         std::vector<V4Program> progs(hit->passes.size());
         std::vector<const V4Program*> ptrs; std::vector<size_t> which;
@@ -527,6 +538,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         return QM_OK;
     };
     auto launch_full = [&](Item& it) -> int {
+        if (st->dry_run) return QM_OK;            // qm_precompile_circuit: plan, encode, compile — launch nothing
         if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
         cudaEvent_t ea = nullptr, eb = nullptr;
         if (st->time_passes) { CU(cudaEventCreate(&ea)); CU(cudaEventCreate(&eb)); CU(cudaEventRecord(ea, st->stream)); }
@@ -689,7 +701,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         if (st->plan_cache.size() > 8) st->plan_cache.pop_back();
     }
     if (!first_event) { CU(cudaEventRecord(st->ev1, st->stream)); st->ev_pending = true; }
-    st->ctr.gates += ngates;
+    if (!st->dry_run) st->ctr.gates += ngates;
     st->ctr.ms_plan = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return QM_OK;
 }
@@ -752,6 +764,29 @@ static int validate_gates(const qm_state* st, const qm_gate* gates, int ng, int 
         }
     }
     return QM_OK;
+}
+
+// Plans `gates` exactly as qm_apply_circuit would, compiles the pass kernels it will need and keeps the plan — without touching
+// the register.  A caller that knows its circuit ahead of time (a reservoir loop, a benchmark) calls this once, e.g. while data
+// is still loading, and the FIRST application already runs compiled instead of going through the interpreter kernel.
+// Does nothing when compiled kernels are not in use for this register (QM_OPT_JIT 0, or the default on a small register).
+extern "C" int32_t qm_precompile_circuit(qm_state* st, const qm_gate* gates, int32_t ngates, int32_t* n_compiled) {
+    if (!st || (!gates && ngates > 0) || ngates < 0) return set_err(QM_ERR_ARG, "null argument");
+    if (n_compiled) *n_compiled = 0;
+    if (st->dist || st->eager) return set_err(QM_ERR_STATE, "precompilation is for unsharded registers on the fused path");
+    QM_TRY(validate_gates(st, gates, ngates, 0));
+    QM_TRY(flush(st));
+    if (jit_threshold(st) == 0) return QM_OK;
+    const uint64_t before = jit_stats().compiled;
+    const double g0 = st->gphase[0], g1 = st->gphase[1];
+    st->dry_run = 1;
+    int rc = run_circuit(st, gates, ngates, nullptr, 0);                 // plan -> plan cache
+    st->dry_run = 2;
+    if (rc == QM_OK) rc = run_circuit(st, gates, ngates, nullptr, 0);    // replay the cached plan: compile what is missing
+    st->dry_run = 0;
+    st->gphase[0] = g0; st->gphase[1] = g1;          // nothing was applied: the encodings' global-phase factors are not owed
+    if (n_compiled) *n_compiled = (int32_t)(jit_stats().compiled - before);
+    return rc;
 }
 
 extern "C" int32_t qm_apply_circuit(qm_state* st, const qm_gate* gates, int32_t ngates) {
@@ -1668,7 +1703,7 @@ extern "C" int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_c
         { uint64_t k[2]; jit_hash(sig, k); out[5] = (int64_t)(((uint64_t)out[5] * 0x100000001b3ull) ^ k[0] ^ (k[1] << 1)); }
         if (compile) {
             std::vector<char> cubin; std::string log;
-            if (!jit_compile_cubin(ptx, cubin, log)) return set_err(QM_ERR_STATE, "pass %lld does not assemble: %s", (long long)out[0] - 1, log.c_str());
+            if (!jit_cubin_for(ptx, cubin, log, nullptr)) return set_err(QM_ERR_STATE, "pass %lld does not assemble: %s", (long long)out[0] - 1, log.c_str());
             out[2]++;
             if ((int64_t)cubin.size() > out[4]) out[4] = (int64_t)cubin.size();
         }

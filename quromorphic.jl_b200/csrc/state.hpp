@@ -40,6 +40,7 @@ struct qm_state {
     int overlap_depth = 2;      // ... passes in front of an exchange that run slab by slab beside it (1..4)
     int slab_bits = 3;          // ... and log2 of the number of slabs (measured: profiles/r2f_*, r2g_*)
     bool defer_pass = true;     // QM_OPT_DEFER_PASS: sharded registers may postpone the last pass before an exchange to after it (qm_api.cu run_circuit)
+    int dry_run = 0;            // inside qm_precompile_circuit: run_circuit launches nothing; 1 = plan only (into the plan cache), 2 = replay the plan and compile its kernels
     int jit = 2;                // QM_OPT_JIT: a pass program whose opcode sequence has been seen this many times is compiled (0 = never)
     bool time_passes = false;   // QM_OPT_TIME_PASSES: CUDA events around every fused pass (diagnostics, tools/pass_model.py)
     std::vector<cudaEvent_t> pass_events;      // 2 per timed pass, resolved by qm_pass_times

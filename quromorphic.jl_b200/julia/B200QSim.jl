@@ -19,7 +19,7 @@ import Quromorphic.QSim: nb, u2!, h!, x!, y!, z!, rx!, ry!, rz!, controlled!, cn
                           density_matrix, statevector_to_density_matrix      # new METHODS of the reference's functions
 import Quromorphic.QInfo: partial_trace, entanglement_entropy, von_neumann_entropy
 
-export B200State, B200Density, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, QMGate
+export B200State, B200Density, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, precompile_circuit!, jit_cache_dir, QMGate
 
 const LIB = get(ENV, "QM_B200_LIB", joinpath(@__DIR__, "..", "libqm_b200.so"))
 
@@ -126,6 +126,20 @@ function swap!(s::B200State, q1::Int, q2::Int)            # QSim.jl:262-275
 end
 
 "apply a whole gate list (0-based textbook bits, the wire format) in as few HBM passes as possible"
+"""
+    precompile_circuit!(s, gates) -> Int
+
+Compile the pass kernels `gates` will need (QM_OPT_JIT) ahead of its first application; the register is not touched.
+Only the structure of `gates` matters (gate kinds and qubits), not the angles.  `jit_cache_dir(path)` keeps the kernels
+as files for later processes.
+"""
+function precompile_circuit!(s::B200State, gates::Vector{QMGate})
+    k = Ref{Int32}(0)
+    check(ccall((:qm_precompile_circuit, LIB), Int32, (Ptr{Cvoid}, Ptr{QMGate}, Int32, Ptr{Int32}), s.handle, gates, length(gates), k))
+    return Int(k[])
+end
+jit_cache_dir(path::AbstractString) = check(ccall((:qm_jit_cache_dir, LIB), Int32, (Cstring,), path))
+
 function apply_circuit!(s::B200State, gates::Vector{QMGate})
     check(ccall((:qm_apply_circuit, LIB), Int32, (Ptr{Cvoid}, Ptr{QMGate}, Int32), s.handle, gates, length(gates)))
     s

@@ -171,6 +171,13 @@ class B200State:
     def counters_reset(self):
         L.check(L.lib().qm_counters_reset(self._h))
 
+    def precompile_circuit(self, gates):
+        """compile the pass kernels `gates` will need (QM_OPT_JIT) without touching the register; returns how many were compiled"""
+        assert gates.dtype == L.GATE_DTYPE and gates.flags["C_CONTIGUOUS"]
+        n = C.c_int32()
+        L.check(L.lib().qm_precompile_circuit(self._h, gates.ctypes.data, len(gates), C.byref(n)))
+        return n.value
+
     def apply_circuit(self, gates):
         """gates: numpy structured array of _lib.GATE_DTYPE, 0-based textbook bits (wire format)."""
         assert gates.dtype == L.GATE_DTYPE and gates.flags["C_CONTIGUOUS"]

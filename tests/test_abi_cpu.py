@@ -325,6 +325,56 @@ def test_compiled_pass_kernels_generate_and_assemble_for_sm_100a(pkg):
         assert d2["assembled"] == d2["passes"] and 10000 < d2["max_cubin_bytes"] < 400000
 
 
+def test_compiled_kernel_disk_cache(pkg, tmp_path):
+    """qm_jit_cache_dir: assembled kernels are kept as files keyed by the complete PTX text; a second walk over the same circuit
+    reads them instead of assembling again, a damaged file is ignored and replaced, and without a directory nothing is written."""
+    import os
+    import time
+    L = pkg._lib
+    gates = random_circuit(pkg, 13, 60, 4242)
+    try:
+        L.jit_check(13, gates, max_cost=24.0, compile=True)
+    except L.QMError as e:
+        if "libnvJitLink not found" in str(e):
+            pytest.skip("libnvJitLink is not installed here")
+        raise
+    d = tmp_path / "jitcache"
+    try:
+        L.jit_cache_dir(d)
+        s0 = L.jit_cache_stats()
+        t0 = time.perf_counter()
+        a = L.jit_check(13, gates, max_cost=24.0, compile=True)
+        t_cold = time.perf_counter() - t0
+        s1 = L.jit_cache_stats()
+        files = sorted(os.listdir(d))
+        # one file per distinct PTX text (coefficient offsets can differ between passes of one opcode sequence: >= distinct)
+        assert a["distinct"] <= len(files) <= a["passes"] and all(f.startswith("qmjit-") and f.endswith(".cubin") for f in files)
+        assert s1["disk_stores"] - s0["disk_stores"] == len(files)
+        assert s1["disk_hits"] - s0["disk_hits"] == a["passes"] - len(files)
+        t0 = time.perf_counter()
+        b = L.jit_check(13, gates, max_cost=24.0, compile=True)
+        t_warm = time.perf_counter() - t0
+        s2 = L.jit_cache_stats()
+        assert b == a
+        assert s2["disk_hits"] - s1["disk_hits"] == a["passes"] and s2["disk_stores"] == s1["disk_stores"]
+        assert t_warm < t_cold
+        # a truncated file and a file with a flipped byte do not verify: assembled again and written again
+        f0, f1 = d / files[0], d / files[-1]
+        raw = f0.read_bytes(); f0.write_bytes(raw[:len(raw) // 2])
+        if f1 != f0:
+            raw1 = bytearray(f1.read_bytes()); raw1[-5] ^= 0x40; f1.write_bytes(bytes(raw1))
+        c = L.jit_check(13, gates, max_cost=24.0, compile=True)
+        s3 = L.jit_cache_stats()
+        assert c == a and s3["disk_stores"] - s2["disk_stores"] == (1 if f1 == f0 else 2)
+        assert f0.read_bytes() == raw
+        assert not [f for f in os.listdir(d) if ".tmp." in f]
+    finally:
+        L.jit_cache_dir(None)
+    s4 = L.jit_cache_stats()
+    L.jit_check(13, gates, max_cost=24.0, compile=True)
+    assert L.jit_cache_stats() == s4
+
+
 def test_compiled_kernels_are_keyed_by_structure_not_by_angles(pkg):
     """canonical signs (encode_v4 canon): the opcode sequence of a pass program — the key of a compiled kernel — must not
     depend on the angles.  C4 reservoir steps have a structure period of 6 (gate kind (q + l) mod 3, brickwork l mod 2) and

@@ -177,3 +177,82 @@ def test_driver_ptx_compiler_when_nvjitlink_is_not_used(pkg):
     env = dict(os.environ, QM_JIT_BACKEND="driver")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "DRIVER_JIT_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_precompile_circuit_compiles_ahead_and_leaves_the_register_alone(pkg):
+    """qm_precompile_circuit: the kernels of a circuit's passes are compiled before its first application (all together, from the
+    plan it leaves in the plan cache), the register — amplitudes and pending global phase — is not touched, and the FIRST
+    application already runs compiled.  On a register below the default size gate it is a no-op."""
+    L = pkg._lib
+    n = 16
+    gl = pkg.circuits.GateList(n)
+    rng = np.random.default_rng(77)
+    for q in range(1, n + 1):
+        gl.rz(q, float(rng.uniform(-6.3, 6.3))); gl.ry(q, float(rng.uniform(-6.3, 6.3)))
+    for q in range(1, n - 2):
+        gl.crx(q, q + 2, float(rng.uniform(-6.3, 6.3)))
+    for q in range(n, 1, -1):
+        gl.cnot(q, q - 1)
+    for q in range(1, n + 1):
+        gl.rz(q, float(rng.uniform(-6.3, 6.3))); gl.rx(q, float(rng.uniform(-6.3, 6.3)))
+    gates = gl.array()
+    small = pkg.B200State(n, 5)
+    assert small.precompile_circuit(gates) == 0
+    small.apply_circuit(gates)
+    assert small.counters()["compiled_passes"] == 0
+    st = pkg.B200State(n, 5, batch=1024)                    # 2^26 amplitudes: the default (QM_OPT_JIT 2) applies
+    st.counters_reset()
+    before = L.jit_stats()
+    k = st.precompile_circuit(gates)
+    after = L.jit_stats()
+    assert k > 0 and after["compiled"] - before["compiled"] == k and after["failed"] == 0, (k, before, after)
+    c = st.counters()
+    assert c["passes"] == 0 and c["launches"] == 0 and c["gates"] == 0, c
+    e5 = np.zeros(1 << n, dtype=np.complex128); e5[5] = 1.0
+    for b in (0, 1023):
+        assert np.array_equal(st.to_numpy(b), e5)           # untouched, and no global phase owed
+    assert st.precompile_circuit(gates) == 0                # everything is there already
+    st.apply_circuit(gates)
+    c = st.counters()
+    assert c["passes"] > 0 and c["compiled_passes"] == c["passes"], c
+    ref = O.apply_circuit(O.statevector(n, 5), gates)
+    for b in (0, 700, 1023):
+        assert rel_err(st.to_numpy(b), ref) < RTOL
+    assert rel_err(small.to_numpy(), ref) < RTOL
+    st.close(); small.close()
+
+
+def test_disk_cache_of_compiled_kernels_across_processes(pkg, tmp_path):
+    """QM_JIT_CACHE_DIR: the second PROCESS that runs a circuit of the same structure loads its kernels from the directory
+    (nothing assembled, same results to the last bit)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import __graft_entry__ as ge\n"
+        "from oracle import oracle as O\n"
+        "from test_abi_cpu import random_circuit\n"
+        "pkg = ge.load_package(); L = pkg._lib\n"
+        "n = 15; gates = random_circuit(pkg, n, 200, 777); psi0 = O.random_state(n, 9)\n"
+        "st = pkg.B200State.from_numpy(psi0); st.set_option(L.OPT_JIT, 1); st.apply_circuit(gates)\n"
+        "got = st.to_numpy(); err = float(np.max(np.abs(got - O.apply_circuit(psi0.copy(), gates))))\n"
+        "c = st.counters(); s = L.jit_stats(); d = L.jit_cache_stats()\n"
+        "assert err < 1e-12 and c['compiled_passes'] == c['passes'] > 0 and s['failed'] == 0, (err, c, s)\n"
+        "import hashlib\n"
+        "print('DISK_CACHE', s['backend'], s['compiled'], d['disk_hits'], d['disk_stores'], hashlib.sha1(got.tobytes()).hexdigest())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QM_JIT_CACHE_DIR=str(tmp_path / "kernels"))
+    env.pop("QM_JIT_BACKEND", None)
+    runs = []
+    for rep in range(2):
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "DISK_CACHE" in out.stdout, out.stdout + out.stderr
+        runs.append(out.stdout[out.stdout.index("DISK_CACHE"):].split())
+    (_, be0, comp0, hits0, stores0, sha0), (_, be1, comp1, hits1, stores1, sha1) = runs
+    if be0 != "nvJitLink":
+        pytest.skip("libnvJitLink is not installed here: the driver compiler takes PTX text, there is no cubin to keep")
+    assert int(stores0) > 0 and int(hits1) == int(comp1) == int(comp0) and int(stores1) == 0, runs
+    assert sha0 == sha1
+    assert len(os.listdir(tmp_path / "kernels")) == int(stores0)
