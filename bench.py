@@ -46,12 +46,22 @@ def peaks():
         return 6650.0, "fallback"
 
 
-KERNEL_SOURCES = ("fused_tma_kernel.cuh", "fused_tma.cuh", "v4_dispatch.inc", "jit_codegen.hpp", "encode_v4.hpp")
+KERNEL_SOURCES = ("jit_codegen.hpp", "encode_v4.hpp")
 
 
 def kernel_source_hash():
+    """Identifies the code of the dominant kernel (the compiled fused pass): the complete PTX text the library hands to the
+    assembler for a fixed reference pass — the kernel template embedded in the library with generated groups spliced in,
+    mangled entry name normalised — plus the sources of the generator and the encoder.  Taken from the loaded library, so it
+    describes the binary that runs, not the files next to it."""
     import hashlib
-    h = hashlib.sha256()
+    import re
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    gates = pkg.circuits.c3_circuit(n=14, depth=3, seed=3001)
+    ptx = pkg._lib.jit_check(14, gates, max_cost=80.0, compile=False, want_ptx=True)["ptx"]
+    ptx = re.sub(r"k_fused_tmaI(?:Li\d+E)+(?:Lb[01]E)+EEv", "k_fused_tmaI_EEv", ptx)     # template arguments: a defaulted one may be appended
+    h = hashlib.sha256(ptx.encode())
     for f in KERNEL_SOURCES:
         with open(os.path.join(ROOT, "quromorphic.jl_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
@@ -61,8 +71,8 @@ def kernel_source_hash():
 def static_traffic(n):
     """DRAM bytes of one k_fused_tma launch.  It cannot be measured inside a plain run (it needs the profiler's
     counters), so it is a STATIC figure: the dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
-    capture committed under profiles/, accepted only when that capture was taken from the kernel sources this run was
-    built from (hash of KERNEL_SOURCES) and at this register size; otherwise null."""
+    capture committed under profiles/, accepted only when that capture was taken from the very kernel text this run's
+    library assembles (kernel_source_hash) and at this register size; otherwise null."""
     try:
         with open(os.path.join(ROOT, "profiles", "r3_traffic.json")) as f:
             t = json.load(f)["k_fused_tma"]
@@ -300,6 +310,7 @@ def main():
     ap.add_argument("--xun", type=int, default=-1, help="sharded: pairs in flight per exchange thread (4 or 8)")
     ap.add_argument("--slab-bits", type=int, default=-1, help="sharded: log2 of the number of slabs")
     ap.add_argument("--overlap-depth", type=int, default=-1, help="sharded: passes in front of an exchange that run slab by slab beside it")
+    ap.add_argument("--zfold", type=int, default=1, help="C4: 1 = one call per step (qm_apply_circuit_expect_z, <Z> sums inside the last pass), 0 = circuit then readout")
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c4"],
                     help="auto: C3 at N = 1, C4 at N > 1; c4 at N = 1 runs the 33-qubit weak-scaling base")
     args = ap.parse_args()
@@ -471,6 +482,7 @@ def main():
             line["c4_base"] = {"workload": b["config"]["workload"], "n_qubits": b["n_qubits"], "value": b["value"], "unit": unit,
                                "ms_per_step": b["ms_per_step"], "gates_per_step": b["gates_per_step"],
                                "passes_per_step": b["passes_per_step"], "fused_pass_gbs": b["roofline"]["achieved"],
+                               "step_call": b.get("step_call"), "folded_readouts_per_step": b.get("folded_readouts_per_step"),
                                "note": "weak-scaling efficiency of the N-GPU C4 lines = (ms_per_step / gates_per_step here) / (theirs)"}
         except Exception as e:            # the base is informational: never lose the headline line over it
             line["c4_base"] = {"error": str(e)[:200]}

@@ -72,13 +72,22 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
     steps = [pkg.circuits.c4_step(n, sw + s) for s in range(args.warmup + args.steps)]
     ngates = sum(len(x) for x in steps[args.warmup:])
 
-    def step(i):
-        st.apply_circuit(steps[i])
+    # one reservoir step = circuit + all-qubit <Z>.  Default: ONE call (qm_apply_circuit_expect_z), which takes the <Z> sums inside
+    # the last fused pass when that pass is a compiled kernel over the whole register (QM_OPT_ZFOLD) — the separate 16 * 2^n
+    # byte read of the readout kernels disappears; --zfold 0 makes the two calls one after the other as before.
+    zfold = getattr(args, "zfold", 1) != 0
+
+    def run_step(g):
+        if zfold:
+            return st.apply_circuit_expect_z(g)
+        st.apply_circuit(g)
         return st.expect_z_all()
 
+    def step(i):
+        return run_step(steps[i])
+
     for gates_pre in pre:
-        st.apply_circuit(gates_pre)
-        st.expect_z_all()
+        run_step(gates_pre)
     for i in range(args.warmup):
         step(i)
     st.sync()
@@ -153,6 +162,8 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
             "overlapped_passes_per_step": c.get("overlapped_passes", 0) / args.steps,
             "compiled_passes_per_step": c.get("compiled_passes", 0) / args.steps,
             "deferred_passes_per_step": c.get("deferred_passes", 0) / args.steps,
+            "folded_readouts_per_step": c.get("folded_readouts", 0) / args.steps,
+            "step_call": "qm_apply_circuit_expect_z" if zfold else "qm_apply_circuit + qm_expect_z_all",
             "structure_warmup_steps": sw,
             "compiled_pass_kernels": dict(L.jit_stats(), note="rank 0's process; compiled during the untimed structure warm-up"),
         }

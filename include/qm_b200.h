@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define QM_ABI_VERSION 3
+#define QM_ABI_VERSION 4
 
 /* status codes */
 enum {
@@ -71,6 +71,7 @@ enum {
     QM_OPT_OVERLAP_DEPTH = 13, /* ... how many of the last passes before an exchange run slab by slab in front of it (1..4, default 2) */
     QM_OPT_SLAB_BITS = 12,  /* ... log2 of the number of slabs (1..3, default 3) */
     QM_OPT_DEFER_PASS = 15, /* sharded registers: 1 (default) the last fused pass planned before an exchange is postponed to after it when it does not target an outgoing qubit and the passes after the exchange do not become more (a reservoir layer: 4 passes per step instead of 5), 0: never */
+    QM_OPT_ZFOLD     = 16,  /* 1 (default): qm_apply_circuit_expect_z folds the all-qubit <Z> sums into the last fused pass of the circuit when that pass runs as a compiled kernel over one whole register (the state is not read again by the readout kernels); 0: the circuit, then the ordinary readout */
     QM_OPT_JIT       = 14,  /* compiled pass kernels: a fused pass whose opcode sequence (gate kinds, sign variants, register-block positions) has been seen this many times is compiled into straight-line code and launched instead of the interpreter; default 2 (the second time a circuit of the same structure runs; only on registers of 2^26 amplitudes and more, batch included — below that a pass takes microseconds and a 0.25 s compilation never pays), 1 = every pass at first sight whatever the size, 0 = never.  The planner prices gates for the kernel that will run them. */
     QM_OPT_SHORT_PCT = 8    /* planner: a circuit shorter than the look-ahead window (a reservoir step before a readout) is planned at the multiple of the budget, up to this many per cent, that the pass model says finishes first; default 0 = no limit, 100 = off */
 };
@@ -102,6 +103,7 @@ typedef struct qm_counters_t {
     uint64_t overlapped_passes; /* fused passes that were cut into slabs to run beside an exchange */
     uint64_t compiled_passes;   /* fused passes that ran as compiled straight-line kernels (QM_OPT_JIT) instead of the interpreter */
     uint64_t deferred_passes;   /* sharded: passes postponed from before an exchange to after it (QM_OPT_DEFER_PASS) */
+    uint64_t folded_readouts;   /* qm_apply_circuit_expect_z calls whose <Z> sums were taken inside the last pass (QM_OPT_ZFOLD); ABI 4 */
 } qm_counters_t;
 
 /* ---- lifetime -------------------------------------------------------------------- */
@@ -132,6 +134,12 @@ int32_t qm_download(qm_state* st, double* host_interleaved, uint64_t n_amps, int
  * and keeps the plan, without touching the register — the first application then already runs compiled.  *n_compiled
  * (optional) = kernels compiled by this call.  No-op when compiled kernels are not in use for this register. */
 int32_t qm_precompile_circuit(qm_state* st, const qm_gate* gates, int32_t ngates, int32_t* n_compiled);
+/* a reservoir step in one call: qm_apply_circuit(gates) followed by qm_expect_z_all(threshold, out) — same results, same
+ * layout of `out` ([n][2] doubles; batch x n x 2 for a batch).  When the last fused pass of the circuit runs as a compiled
+ * kernel over one whole register (QM_OPT_JIT, batch 1), the thresholded |a|^2 sums of measure_z (QSim.jl:297-318, every qubit)
+ * are taken from the tiles of that pass while they are still in shared memory, so the 16 * 2^n byte read of the readout kernels
+ * disappears (QM_OPT_ZFOLD, counters.folded_readouts); otherwise the two calls are made one after the other. */
+int32_t qm_apply_circuit_expect_z(qm_state* st, const qm_gate* gates, int32_t ngates, double threshold, double* out);
 int32_t qm_apply_u2(qm_state* st, int32_t t0, const double U[8]);
 int32_t qm_apply_controlled(qm_state* st, int32_t c0, int32_t t0, const double V[8]);
 int32_t qm_apply_swap(qm_state* st, int32_t a0, int32_t b0);
@@ -278,7 +286,8 @@ int32_t qm_jit_stats(uint64_t out[4], double* compile_ms);
 int32_t qm_jit_cache_dir(const char* path);
 int32_t qm_jit_cache_stats(uint64_t out[2]);
 /* host-only check of the compiled pass kernels (no GPU needed): every 2^12-tile pass of the planned circuit is turned into PTX
- * text and, with compile != 0 and libnvJitLink present, assembled for sm_100a.  out = {passes, passes with PTX text, passes
+ * text and, with bit 0 of `compile` set and libnvJitLink present, assembled for sm_100a (bit 1: the ZFOLD flavour of the kernels,
+ * qm_apply_circuit_expect_z).  out = {passes, passes with PTX text, passes
  * assembled, distinct opcode sequences, bytes of the largest cubin, hash over all passes' opcode sequences (canonical signs: it
  * depends on the structure of the circuit, not on its angles)}; ptx_out (optional) receives the text of the first pass */
 int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_cost, const qm_gate* gates, int32_t ngates,

@@ -18,7 +18,7 @@ QM_OK, QM_ERR_ARG, QM_ERR_CUDA, QM_ERR_NOMEM, QM_ERR_NO_DEVICE, QM_ERR_STATE, QM
 GATE_U2, GATE_CU2, GATE_SWAP, GATE_U2_SLOT = 0, 1, 2, 3
 BASIS_Z, BASIS_X, BASIS_Y = 0, 1, 2
 OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_TRACE, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = range(9)
-OPT_OVERLAP, OPT_XSM, OPT_XUN, OPT_SLAB_BITS, OPT_OVERLAP_DEPTH, OPT_JIT, OPT_DEFER_PASS = 9, 10, 11, 12, 13, 14, 15
+OPT_OVERLAP, OPT_XSM, OPT_XUN, OPT_SLAB_BITS, OPT_OVERLAP_DEPTH, OPT_JIT, OPT_DEFER_PASS, OPT_ZFOLD = 9, 10, 11, 12, 13, 14, 15, 16
 
 GATE_DTYPE = np.dtype([("kind", np.int32), ("q0", np.int32), ("q1", np.int32), ("flags", np.int32),
                        ("m", np.float64, (8,))])
@@ -30,7 +30,7 @@ class Counters(C.Structure):
                 ("bytes_hbm", C.c_uint64), ("bytes_link", C.c_uint64), ("bytes_h2d", C.c_uint64),
                 ("bytes_d2h", C.c_uint64), ("ms_device", C.c_double),
                 ("ms_plan", C.c_double), ("ms_remap", C.c_double), ("overlapped_remaps", C.c_uint64), ("overlapped_passes", C.c_uint64),
-                ("compiled_passes", C.c_uint64), ("deferred_passes", C.c_uint64)]
+                ("compiled_passes", C.c_uint64), ("deferred_passes", C.c_uint64), ("folded_readouts", C.c_uint64)]
 
 
 class QMError(RuntimeError):
@@ -56,6 +56,7 @@ SIGNATURES = {
     "qm_apply_controlled": (C.c_int32, [_vp, C.c_int32, C.c_int32, _dp]),
     "qm_apply_swap": (C.c_int32, [_vp, C.c_int32, C.c_int32]),
     "qm_apply_circuit": (C.c_int32, [_vp, _vp, C.c_int32]),
+    "qm_apply_circuit_expect_z": (C.c_int32, [_vp, _vp, C.c_int32, C.c_double, _dp]),
     "qm_precompile_circuit": (C.c_int32, [_vp, _vp, C.c_int32, C.POINTER(C.c_int32)]),
     "qm_apply_batched": (C.c_int32, [_vp, _vp, C.c_int32, _dp, C.c_int32]),
     "qm_probs": (C.c_int32, [_vp, _dp, C.c_int32]),
@@ -184,12 +185,12 @@ def plan_describe(n, gates, global_bits=0, tile_bits=12, low_bits=5, max_cost=0.
     return steps
 
 
-def jit_check(n, gates, low_bits=5, max_cost=0.0, compile=True, want_ptx=False):
+def jit_check(n, gates, low_bits=5, max_cost=0.0, compile=True, want_ptx=False, zfold=False):
     """host-only: {passes, with_ptx, assembled, distinct, max_cubin_bytes} (+ the PTX text of the first pass) for the compiled
     pass kernels of this circuit"""
     out = (C.c_int64 * 6)()
     buf = C.create_string_buffer(4 << 20) if want_ptx else None
-    check(lib().qm_jit_check(n, low_bits, max_cost, gates.ctypes.data, len(gates), 1 if compile else 0, out, buf, (4 << 20) if want_ptx else 0))
+    check(lib().qm_jit_check(n, low_bits, max_cost, gates.ctypes.data, len(gates), (1 if compile else 0) | (2 if zfold else 0), out, buf, (4 << 20) if want_ptx else 0))
     d = dict(zip(("passes", "with_ptx", "assembled", "distinct", "max_cubin_bytes", "structure_hash"), list(out)))
     if want_ptx:
         d["ptx"] = buf.value.decode()

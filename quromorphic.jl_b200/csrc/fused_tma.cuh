@@ -119,7 +119,20 @@ struct V4Launch {
     int32_t  rowdim;        // which TMA dimension (1..4) takes the tile's base row as its coordinate
     int32_t  sm_cap;        // 0 = all SMs; otherwise the persistent grid leaves the other SMs to a concurrent exchange kernel
     int32_t  nfixed;        // number of pinned bits (they are not enumerated by the tile index)
-    unsigned long long* trace;   // nullptr, or device buffer of kV4TraceStride stamps per tile of CTA 0
+    union {                      // same size and offset either way: the parameter layout of every kernel is unchanged
+        unsigned long long* trace;   // nullptr, or device buffer of kV4TraceStride stamps per tile of CTA 0
+        const struct V4Fold* fold;   // ZFOLD instantiations (a pass that also sums the all-qubit <Z> statistics): never null there
+    };
+};
+
+// Device-side parameters of a ZFOLD pass.  The pass is the LAST one of a circuit whose caller wants measure_z of every qubit
+// (QSim.jl:297-318) right after it: each team sums the thresholded |a|^2 of the tile it has just finished from shared memory,
+// per index bit, so the state is not read from HBM again by the readout kernels.
+static const int kV4FoldVals = 64;     // [b] = kept probability with physical index bit b set (b < 63), [63] = kept total
+struct V4Fold {
+    double   thr;                      // probabilities not above thr are dropped (strict >, QSim.jl:308); negative: keep all
+    double*  part;                     // [gridDim.x][kV4FoldVals], written by every CTA of the launch
+    uint32_t tl[16];                   // physical index bit of tile-local position k (PlanPass::tl)
 };
 
 static const int kV4ProducerThreads = 128;     // a whole warpgroup, so that setmaxnreg can hand its registers over

@@ -78,7 +78,15 @@ __device__ __forceinline__ uint32_t ldp32(uint64_t pa) {
 // engine splices straight-line code generated for one pass program between the markers (jit.cpp) and hands the text to the
 // driver's PTX compiler.  The records never go to shared memory: the generated code reads its coefficients from the
 // kernel-parameter bank at fixed offsets.
-template <int M, int TEAMS, int STAGES, bool JIT = false>
+//
+// ZFOLD = true: the pass also sums the all-qubit <Z> statistics of what it stores (V4Fold, fused_tma.cuh).  After the last
+// group of a tile the team reads the finished tile back from shared memory — element j * TEAM + ttid, conflict-free under the
+// swizzle — so tile-local bits 0..M-5 are bits of the thread index and bits M-4..M-1 bits of j; the kept probability of
+// the whole tile goes to the index bits outside the tile that are set in the tile's base (lane l of every warp keeps bits l
+// and l + 32).  Everything is accumulated in registers over the CTA's tiles and folded ONCE per CTA in a fixed order
+// (shuffles inside a warp, then warp by warp), so the result does not depend on timing.  A separate instantiation: the
+// kernels without the fold are byte for byte what they were.
+template <int M, int TEAMS, int STAGES, bool JIT = false, bool ZFOLD = false>
 __global__ void __launch_bounds__(TEAMS * (1 << (M - 4)) + kV4ProducerThreads, 1)
 k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4Program P, const double* __restrict__ slots,
             const V4Launch lp) {
@@ -86,6 +94,8 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     constexpr int NCOMP = TEAMS * TEAM;
     constexpr uint32_t TILE_BYTES = 16u << M;
     static_assert(TEAMS <= STAGES && NCOMP % 128 == 0 && TEAM % 32 == 0, "team shape");
+    static_assert(!ZFOLD || (3 * STAGES <= 16 && JIT && (NCOMP / 32) * kV4FoldVals * 8 <= (int)(sizeof(V4Rec) * kV4MaxRecs) && M - 4 >= 5 && M <= 16),
+                  "ZFOLD: a third descriptor word per stage, and the record area (unused by compiled kernels) as reduction scratch");
     extern __shared__ unsigned char smem_dyn[];
     // [stages][TILE_BYTES] | lane_tab, warp_tab | gate records | per-stage tile descriptors | barriers ; SWIZZLE_128B needs the stages 1024-byte aligned
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -132,7 +142,7 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     const uint64_t ntiles = lp.ntiles;
     const uint64_t my_tiles = first < ntiles ? (ntiles - first + step - 1) / step : 0;
     // optional phase trace (diagnostics, tools/tile_timeline.py): CTA 0 writes SM-clock stamps per tile
-    unsigned long long* const trace = blockIdx.x == 0 ? lp.trace : nullptr;
+    unsigned long long* const trace = (!ZFOLD && blockIdx.x == 0) ? lp.trace : nullptr;
 
     if (tid >= NCOMP) {
         // ===================== producer warpgroup: one elected lane drives TMA =====================
@@ -171,6 +181,7 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
             for (uint64_t i = 0; i < pro; ++i) {
                 const uint64_t base = tile_base(first + i * step, d0, d1);
                 tdesc[2 * i] = d0; tdesc[2 * i + 1] = d1;
+                if (ZFOLD) tdesc[2 * STAGES + i] = base;            // the tile's index bits outside the tile (one register: base == index)
                 mbar_arrive_expect_tx(&full[i], TILE_BYTES);        // release: the descriptor is visible to whoever sees the phase
                 TMA_COORDS(base);
                 tma_load_5d(stage_base + i * TILE_BYTES, &tmap, &full[i], 0, tc1, tc2, tc3, tc4);
@@ -191,6 +202,7 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
                     tma_wait_read0();            // the store has read the buffer: safe to overwrite
                     uint64_t* fb = &full[s + STAGES * (int)((nxt / STAGES) & 1)];
                     tdesc[2 * s] = n0; tdesc[2 * s + 1] = n1;
+                    if (ZFOLD) tdesc[2 * STAGES + s] = nbase;
                     mbar_arrive_expect_tx(fb, TILE_BYTES);
                     TMA_COORDS(nbase);
                     tma_load_5d(stage_base + (size_t)s * TILE_BYTES, &tmap, fb, 0, tc1, tc2, tc3, tc4);
@@ -210,6 +222,11 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
     const uint32_t stage_s = smem_u32(stage_base);
     const uint32_t desc_s = smem_u32(tdesc);
     const uint32_t lane_s = smem_u32(tabs) + 2u * lane, warp_s = smem_u32(tabs) + 2u * (kV4MaxGroups * 32 + warp);
+    // ZFOLD accumulators of this thread over the CTA's tiles: kept probability of its 16 elements per tile, the same split by
+    // the four bits of j, and — per lane — the tile totals of the tiles whose base has index bit lane / lane + 32 set
+    double zT = 0.0, zB0 = 0.0, zB1 = 0.0, zB2 = 0.0, zB3 = 0.0, zO = 0.0, zO2 = 0.0;
+    double zthr = 0.0;
+    if (ZFOLD) zthr = lp.fold->thr;
     int s = team % STAGES; uint32_t k = 0;        // stage and use count of the stage (tile i: s = i % STAGES, k = i / STAGES)
 #pragma unroll 1
     for (uint32_t i = team; i < (uint32_t)my_tiles; i += TEAMS) {
@@ -250,11 +267,82 @@ k_fused_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ V4
             if (tr && gi < 3) trace[kV4TraceStride * i + 2 + gi] = clock64();
             if (gi + 1 < ngroups) bar_sync_named(1 + team, TEAM);
         }
+        if (ZFOLD) {
+            bar_sync_named(1 + team, TEAM);          // the last group's stores of the whole team are in the tile
+            uint64_t tbase;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(tbase) : "r"(desc_s + 8u * (uint32_t)(2 * STAGES + s)));
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t e = (uint32_t)j * TEAM + (uint32_t)ttid;
+                const uint32_t slot = e ^ ((e >> 3) & 7u);
+                double re, im;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(re), "=d"(im) : "r"(tile_s + 16u * slot));
+                const double pr = __dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im));      // abs2_exact (kernels.cuh): the oracle's abs2, no contraction
+                v[j] = pr > zthr ? pr : 0.0;
+            }
+            {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j & 1) a0 += v[j];
+                    if (j & 2) a1 += v[j];
+                    if (j & 4) a2 += v[j];
+                    if (j & 8) a3 += v[j];
+                }
+                zB0 += a0; zB1 += a1; zB2 += a2; zB3 += a3;
+            }
+#pragma unroll
+            for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+                for (int j = 0; j < w; ++j) v[j] += v[j + w];
+            double tw = v[0];
+            zT += tw;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tw += __shfl_xor_sync(0xffffffffu, tw, o);      // the warp's share of the tile
+            zO += ((tbase >> lane) & 1ull) ? tw : 0.0;
+            zO2 += ((tbase >> (lane + 32)) & 1ull) ? tw : 0.0;
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&computed[s]);
         if (tr) trace[kV4TraceStride * i + 5] = clock64();
         s += TEAMS; if (s >= STAGES) { s -= STAGES; ++k; }
+    }
+    if (ZFOLD) {
+        // one fold per CTA, fixed order.  Row w of zred (the record area: compiled kernels keep no records in shared memory)
+        // belongs to compute warp w: the lanes write their outer-bit sums — exactly zero at tile-bit positions and at 63,
+        // because a tile's base has no such bit — then lane 0 writes the tile-bit sums and the total over them.
+        const V4Fold* const zf = lp.fold;
+        double* const zred = reinterpret_cast<double*>(recs);
+        const int cw = tid >> 5;                                    // compute warp of the CTA
+        double* const row = zred + cw * kV4FoldVals;
+        auto wsum = [](double x) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            return x;
+        };
+        row[lane] = zO; row[lane + 32] = zO2;
+        __syncwarp();
+        const double wt = wsum(zT);
+        double tb[M];                                               // kept probability with tile-local bit k set, this warp
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk) tb[kk] = wsum(((lane >> kk) & 1) ? zT : 0.0);
+#pragma unroll
+        for (int kk = 5; kk < M - 4; ++kk) tb[kk] = ((warp >> (kk - 5)) & 1) ? wt : 0.0;
+        tb[M - 4] = wsum(zB0); tb[M - 3] = wsum(zB1); tb[M - 2] = wsum(zB2); tb[M - 1] = wsum(zB3);
+        if (lane == 0) {
+#pragma unroll
+            for (int kk = 0; kk < M; ++kk) row[zf->tl[kk] & 63u] = tb[kk];
+            row[kV4FoldVals - 1] = wt;
+        }
+        bar_sync_named(8, NCOMP);                                   // the compute warps only: the producer warpgroup is not here
+        if (tid < kV4FoldVals) {
+            double acc = 0.0;
+#pragma unroll 1
+            for (int w = 0; w < NCOMP / 32; ++w) acc += zred[w * kV4FoldVals + tid];
+            zf->part[(size_t)blockIdx.x * kV4FoldVals + tid] = acc;
+        }
     }
 }
 

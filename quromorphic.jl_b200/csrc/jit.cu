@@ -23,9 +23,13 @@ static const char kTemplateM12[] =
 #include "build/jit_template_m12.inc"
     ;
 
-static const std::string& template_for(int m) {
-    static const std::string t12(kTemplateM12), none;
-    return m == 12 ? t12 : none;
+static const char kTemplateM12Z[] =              // ... and its ZFOLD instantiation (the pass also takes the all-qubit <Z> sums)
+#include "build/jit_template_m12z.inc"
+    ;
+
+static const std::string& template_for(int m, bool zfold = false) {
+    static const std::string t12(kTemplateM12), t12z(kTemplateM12Z), none;
+    return m != 12 ? none : (zfold ? t12z : t12);
 }
 
 // ---- nvJitLink (optional, dlopen) --------------------------------------------------------------
@@ -66,8 +70,8 @@ static const JitLinkApi& jitlink() {
     return A;
 }
 
-bool jit_ptx_for(int m, const V4Program& prog, std::string& ptx) {
-    const std::string& t = template_for(m);
+bool jit_ptx_for(int m, const V4Program& prog, std::string& ptx, bool zfold) {
+    const std::string& t = template_for(m, zfold);
     ptx.clear();
     if (t.empty()) return false;
     return jit_build_ptx(t, prog, ptx);
@@ -228,20 +232,21 @@ static const size_t kMaxKernels = 4096;
 
 JitStats jit_stats() { std::lock_guard<std::mutex> lk(g_mu); JitStats s = g_stats; s.cached = 0; for (auto& e : g_cache) s.cached += e.second.state == 1; return s; }
 
-static JitKey make_key(int device, int m, const V4Program& prog, std::vector<uint32_t>& sig) {
+static JitKey make_key(int device, int m, const V4Program& prog, std::vector<uint32_t>& sig, bool zfold) {
     jit_structure_bytes(prog, m, sig);
+    if (zfold) sig.push_back(0x5a464f4cu);          // "ZFOL": another kernel for the same opcode sequence
     JitKey k; memset(&k, 0, sizeof(k)); k.device = device; k.m = m; jit_hash(sig, k.h);
     return k;
 }
 
 // cubin (or PTX text when nvJitLink is missing) -> module + function, on the calling thread's current context
-static bool load_kernel(const std::vector<char>& image, bool is_ptx, int m, JitKernel& out) {
+static bool load_kernel(const std::vector<char>& image, bool is_ptx, int m, JitKernel& out, bool zfold) {
     const DriverApi& D = driver();
     if (!D.ok) return false;
     CUmodule mod = nullptr;
     CUresult r = is_ptx ? D.load_ex(&mod, image.data(), 0, nullptr, nullptr) : D.load(&mod, image.data());
     if (r != CUDA_SUCCESS || !mod) return false;
-    const std::string entry = jit_entry_name(template_for(m));
+    const std::string entry = jit_entry_name(template_for(m, zfold));
     CUfunction fn = nullptr;
     if (D.get_fn(&fn, mod, entry.c_str()) != CUDA_SUCCESS || !fn) return false;
     if (D.set_attr(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_for(m)) != CUDA_SUCCESS) return false;
@@ -249,9 +254,9 @@ static bool load_kernel(const std::vector<char>& image, bool is_ptx, int m, JitK
     return true;
 }
 
-void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs, int threshold, std::vector<JitKernel*>& out) {
+void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs, int threshold, std::vector<JitKernel*>& out, bool zfold) {
     out.assign(progs.size(), nullptr);
-    if (threshold <= 0 || template_for(m).empty() || !driver().ok) return;
+    if (threshold <= 0 || template_for(m, zfold).empty() || !driver().ok) return;
     // which programs need compiling now (one compile per distinct opcode sequence)
     struct Job { JitKey key; const V4Program* prog; std::vector<char> image; std::string ptx; bool is_ptx = false, ok = false, from_disk = false; };
     std::vector<Job> jobs;
@@ -263,7 +268,7 @@ void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs,
             for (auto it = g_cache.begin(); it != g_cache.end();) { if (it->second.state == 0) it = g_cache.erase(it); else ++it; }
         std::vector<uint32_t> sig;
         for (size_t i = 0; i < progs.size(); ++i) {
-            keys[i] = make_key(device, m, *progs[i], sig);
+            keys[i] = make_key(device, m, *progs[i], sig, zfold);
             JitEntry& e = g_cache[keys[i]];
             if (e.sig.empty()) e.sig = sig;
             else if (e.sig != sig) { keys[i].m = -1; continue; }        // hash collision: leave this program to the interpreter
@@ -284,7 +289,7 @@ void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs,
             for (size_t i = (size_t)t; i < jobs.size(); i += (size_t)nth) {
                 Job& j = jobs[i];
                 std::string& ptx = j.ptx; std::string log;
-                if (!jit_build_ptx(template_for(m), *j.prog, ptx)) continue;
+                if (!jit_build_ptx(template_for(m, zfold), *j.prog, ptx)) continue;
                 if (have_jl) j.ok = jit_cubin_for(ptx, j.image, log, &j.from_disk);
                 else { j.image.assign(ptx.begin(), ptx.end()); j.image.push_back('\0'); j.is_ptx = true; j.ok = true; }
             }
@@ -293,10 +298,10 @@ void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs,
         else { std::vector<std::thread> th; for (int t = 0; t < nth; ++t) th.emplace_back(work, t); for (auto& x : th) x.join(); }
         // modules are loaded on this thread (the context of the caller's device is current here)
         for (Job& j : jobs) {
-            JitKernel k; bool ok = j.ok && load_kernel(j.image, j.is_ptx, m, k);
+            JitKernel k; bool ok = j.ok && load_kernel(j.image, j.is_ptx, m, k, zfold);
             if (!ok && j.ok && j.from_disk) {        // a file that verified but does not load (another driver?): assemble it here
                 std::string log;
-                ok = jit_compile_cubin(j.ptx, j.image, log) && load_kernel(j.image, false, m, k);
+                ok = jit_compile_cubin(j.ptx, j.image, log) && load_kernel(j.image, false, m, k, zfold);
             }
             std::lock_guard<std::mutex> lk(g_mu);
             JitEntry& e = g_cache[j.key];
@@ -314,10 +319,10 @@ void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs,
     }
 }
 
-JitKernel* jit_get(int device, int m, const V4Program& prog, int threshold) {
+JitKernel* jit_get(int device, int m, const V4Program& prog, int threshold, bool zfold) {
     std::vector<const V4Program*> one(1, &prog);
     std::vector<JitKernel*> out;
-    jit_get_many(device, m, one, threshold, out);
+    jit_get_many(device, m, one, threshold, out, zfold);
     return out[0];
 }
 

@@ -26,11 +26,14 @@ struct JitStats {
 
 // The kernel for this program's opcode sequence, or nullptr.  `threshold`: compile (synchronously, on this thread) when the
 // sequence has been asked for this many times including now (1 = at first sight); below the threshold only the count is kept.
-JitKernel* jit_get(int device, int m, const V4Program& prog, int threshold);
+// zfold: the ZFOLD flavour of the kernel (the pass also takes the all-qubit <Z> sums, fused_tma_kernel.cuh) — a kernel, a count
+// and a cache entry of its own.
+JitKernel* jit_get(int device, int m, const V4Program& prog, int threshold, bool zfold = false);
 
 // The same for many programs at once, compiled on several host threads (a cached plan of a deep circuit: hundreds of passes).
 // out[i] = kernel or nullptr.
-void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs, int threshold, std::vector<JitKernel*>& out);
+void jit_get_many(int device, int m, const std::vector<const V4Program*>& progs, int threshold, std::vector<JitKernel*>& out,
+                  bool zfold = false);
 
 // launch: same geometry and parameters as launch_v4_m12
 int jit_launch(JitKernel* k, cudaStream_t stream, int sms, int m, const CUtensorMap& tm, const V4Program& prog, const double* d_slots,
@@ -40,7 +43,7 @@ JitStats jit_stats();
 
 // host-only pieces, also used by the tests: PTX text of the kernel for this program (empty when there is no template for m
 // or the program cannot be emitted), and the text compiled to a cubin with nvJitLink (false when the library is missing)
-bool jit_ptx_for(int m, const V4Program& prog, std::string& ptx);
+bool jit_ptx_for(int m, const V4Program& prog, std::string& ptx, bool zfold = false);
 bool jit_compile_cubin(const std::string& ptx, std::vector<char>& cubin, std::string& log);
 
 // The same through the optional disk cache (QM_JIT_CACHE_DIR or jit_set_cache_dir; empty = none): cubins are files keyed by a

@@ -330,6 +330,21 @@ k_zfinal(const double* __restrict__ partial, int reg_bits, int cb, int hbits, in
         for (int q = 0; q < nq; ++q) out[((size_t)r * nq + q) * 2] = out_tot[r] - out[((size_t)r * nq + q) * 2 + 1];
 }
 
+// K5, folded flavour: the last fused pass of a circuit has left per-CTA sums partial[cta][64] ([b] = kept probability with
+// index bit b set, [63] = kept total; V4Fold, fused_tma_kernel.cuh ZFOLD).  One CTA adds the CTAs in order and writes the same
+// [reg_bits][2] pairs + total that k_zfinal writes.
+__global__ void __launch_bounds__(64)
+k_zfold_final(const double* __restrict__ partial, int nctas, int reg_bits, double* __restrict__ out, double* __restrict__ out_tot) {
+    __shared__ double sh[64];
+    double acc = 0.0;
+    for (int c = 0; c < nctas; ++c) acc += partial[(size_t)c * 64 + threadIdx.x];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    const double tot = sh[63];
+    if ((int)threadIdx.x < reg_bits) { out[2 * threadIdx.x] = tot - sh[threadIdx.x]; out[2 * threadIdx.x + 1] = sh[threadIdx.x]; }
+    if (threadIdx.x == 0) out_tot[0] = tot;
+}
+
 // K5  all-qubit measure_x / measure_y (QSim.jl:320-330 for every t): a tile of 2^m amplitudes (the L lowest index
 // bits + m - L bits starting at hs) is staged in shared memory ONCE and every index bit of the tile selected by
 // `tmask` is measured from it — the pair (a[i0], a[i0 | bit]) is rotated by R in registers exactly as k_measure_rot

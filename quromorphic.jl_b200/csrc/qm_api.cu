@@ -120,8 +120,8 @@ extern "C" int32_t qm_destroy(qm_state* st) {
     for (cudaEvent_t ev : st->pass_events) cudaEventDestroy(ev);
     st->remap_events.clear(); st->pass_events.clear();
     cudaFree(st->trace_buf);
-    cudaFree(st->amp); cudaFree(st->d_blob); cudaFree(st->d_scratch); cudaFree(st->d_slots);
-    cudaFreeHost(st->h_blob); cudaFreeHost(st->h_scratch); cudaFreeHost(st->h_slots);
+    cudaFree(st->amp); cudaFree(st->d_blob); cudaFree(st->d_scratch); cudaFree(st->d_slots); cudaFree(st->d_zfold);
+    cudaFreeHost(st->h_blob); cudaFreeHost(st->h_scratch); cudaFreeHost(st->h_slots); cudaFreeHost(st->h_zfold);
     for (int i = 0; i < 2; ++i) if (st->ev_slots[i]) cudaEventDestroy(st->ev_slots[i]);
     for (int i = 0; i < 2; ++i) { if (st->ev_zq[i]) cudaEventDestroy(st->ev_zq[i]); cudaFreeHost(st->h_zq[i]); }
     for (void* q : st->retired_dev) cudaFree(q);
@@ -190,6 +190,8 @@ extern "C" int32_t qm_set_option(qm_state* st, int32_t key, int64_t value) {
         st->short_mult = value == 0 ? 1e9 : (double)value / 100.0; break;
     case QM_OPT_DEFER_PASS:
         st->defer_pass = value != 0; break;
+    case QM_OPT_ZFOLD:
+        st->zfold = value != 0; break;
     case QM_OPT_JIT:
         if (value < 0 || value > 1000000) return set_err(QM_ERR_ARG, "jit threshold must be >= 0");
         st->jit = (int)value; break;
@@ -223,7 +225,7 @@ extern "C" int32_t qm_num_qubits(const qm_state* st, int32_t* n, int32_t* batch)
 // gate execution
 // ---------------------------------------------------------------------------------------------
 int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const double* d_slots, int nslots,
-                   const PassSlab* slab, cudaStream_t stream, JitKernel* jk = nullptr);
+                   const PassSlab* slab, cudaStream_t stream, JitKernel* jk = nullptr, const V4Fold* d_fold = nullptr);
 
 static int launch_1q(qm_state* st, int tbit, int cbit, const double* m) {
     // physical bits; control on a sharded bit is a rank predicate, target must be local
@@ -319,7 +321,7 @@ static bool v4_eligible(const qm_state* st, const PlanPass& P) {
 // slab->bit[] have the values in slab->value_or (sharded registers: the exchange of one slab runs beside the passes
 // of its neighbours, dist.cu), on a grid of slab->sm_cap CTAs.
 int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const double* d_slots, int nslots,
-                   const PassSlab* slab, cudaStream_t stream, JitKernel* jk) {
+                   const PassSlab* slab, cudaStream_t stream, JitKernel* jk, const V4Fold* d_fold) {
     // tensor map: dim0 = one 128-byte row (8 amplitudes = 16 doubles); dim1 = row index over the whole
     // array (the box takes 2^(L-3) consecutive rows at the tile's base); dims 2..4 = the runs of high
     // tile bits (size 2^len, stride 16 * 2^start bytes), unused dims have size 1.
@@ -367,6 +369,10 @@ int launch_pass_v4(qm_state* st, const V4Program& prog, const PlanPass& P, const
     for (int i = 0; i < kV4Gaps; ++i) { lp.gap_start[i] = i < (int)gaps.size() ? gaps[i].first : 0; lp.gap_len[i] = i < (int)gaps.size() ? gaps[i].second : 0; }
     lp.rank_or = st->g ? ((uint64_t)st->rank << st->nl) : 0; lp.nslots = nslots;
     lp.trace = st->trace_buf;
+    if (d_fold) {           // jk is a ZFOLD kernel (fused_tma_kernel.cuh): it reads its parameters through this pointer and never traces
+        if (!jk || slab || st->batch != 1) return set_err(QM_ERR_STATE, "folded readout: bad launch (internal error)");
+        lp.fold = d_fold;
+    }
     // a pass program whose opcode sequence has been compiled (jit.hpp) runs as straight-line code; otherwise the interpreter
     if (jk) { QM_TRY(jit_launch(jk, stream, st->sms, P.m, tm, prog, d_slots, lp)); st->ctr.compiled_passes += (!slab || slab->index == 0); }
     else if (P.m == 11) QM_TRY(launch_v4_m11(stream, st->sms, tm, prog, d_slots, lp));
@@ -475,6 +481,7 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         PlanPass P; int kind = 0; V4Program prog; std::vector<unsigned char> blob; JitKernel* jk = nullptr;
         std::vector<int> taken;                  // indices (into pl.gates) of the pass's gates, when it was planned here (not replayed)
         double gf[2] = { 1.0, 0.0 };             // the global-phase factor the pass contributed (D1 form), so that a cancelled pass can take it back
+        bool fold = false;                       // jk is the ZFOLD flavour of the pass's kernel: the launch also takes the all-qubit <Z> sums
     };
     // Compiled pass kernels (jit.hpp).  A replayed plan knows all its passes in advance: they are encoded once up front and the
     // opcode sequences that have been seen often enough are compiled together on several host threads (a deep circuit has
@@ -542,7 +549,30 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         if (first_event) { CU(cudaEventRecord(st->ev0, st->stream)); first_event = false; }
         cudaEvent_t ea = nullptr, eb = nullptr;
         if (st->time_passes) { CU(cudaEventCreate(&ea)); CU(cudaEventCreate(&eb)); CU(cudaEventRecord(ea, st->stream)); }
-        if (it.kind == 0) QM_TRY(launch_pass_v4(st, it.prog, it.P, d_slots_lift, nslots, nullptr, st->stream, it.jk));
+        if (it.kind == 0 && it.fold) {
+            // V4Fold | per-CTA partials | pairs [nl][2] | total — the grid is the one jit_launch will use
+            const uint64_t ntiles = total_amps(st) >> it.P.m;
+            const int grid = (int)(ntiles < (uint64_t)st->sms ? ntiles : (uint64_t)st->sms);
+            const size_t head = 256, part = (size_t)grid * kV4FoldVals * 8, outb = ((size_t)st->nl * 2 + 1) * 8;
+            QM_TRY(ENSURE_DEV(st, d_zfold, head + part + outb));
+            QM_TRY(ENSURE_PIN(st, h_zfold, head));
+            V4Fold hf; memset(&hf, 0, sizeof(hf));
+            hf.thr = st->zfold_thr;
+            hf.part = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(st->d_zfold) + head);
+            for (int k = 0; k < it.P.m && k < 16; ++k) hf.tl[k] = (uint32_t)it.P.tl[k];
+            static_assert(sizeof(V4Fold) <= 256, "V4Fold block");
+            memcpy(st->h_zfold, &hf, sizeof(hf));
+            CU(cudaMemcpyAsync(st->d_zfold, st->h_zfold, sizeof(hf), cudaMemcpyHostToDevice, st->stream));
+            st->ctr.bytes_h2d += sizeof(hf);
+            QM_TRY(launch_pass_v4(st, it.prog, it.P, d_slots_lift, nslots, nullptr, st->stream, it.jk,
+                                  reinterpret_cast<const V4Fold*>(st->d_zfold)));
+            double* d_out = hf.part + (size_t)grid * kV4FoldVals;
+            k_zfold_final<<<1, 64, 0, st->stream>>>(hf.part, grid, st->nl, d_out, d_out + (size_t)st->nl * 2);
+            CU(cudaGetLastError());
+            st->ctr.launches++;
+            st->zfold_done = true;
+        }
+        else if (it.kind == 0) QM_TRY(launch_pass_v4(st, it.prog, it.P, d_slots_lift, nslots, nullptr, st->stream, it.jk));
         else if (it.kind == 2) {
             for (const PlanGroup& G : it.P.groups) for (const LGate& x : G.subs) QM_TRY(launch_1q(st, x.target, x.ctrl, x.m));
             st->ctr.passes++;
@@ -626,7 +656,17 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         }
         bool leftover = false;
         for (size_t i = pl.first; i < pl.gates.size(); ++i) if (!pl.done[i]) { leftover = true; break; }
-        if (!leftover) { QM_TRY(launch_all_held()); finished = true; break; }
+        if (!leftover) {
+            // qm_apply_circuit_expect_z: the very last pass also takes the <Z> sums when it is a compiled kernel over one
+            // whole register and the ZFOLD flavour of that kernel is there (same threshold rule as every compiled kernel)
+            if (st->zfold_want && st->zfold && !st->dry_run && tma && st->batch == 1 && st->nl < 63 && !held.empty()) {
+                Item& last = held.back();
+                if (last.kind == 0 && last.jk && last.P.m == 12 && last.P.tl.size() == 12) {
+                    if (JitKernel* jz = jit_get(st->device, 12, last.prog, jit_thr, true)) { last.jk = jz; last.fold = true; }
+                }
+            }
+            QM_TRY(launch_all_held()); finished = true; break;
+        }
         if (st->g == 0) return set_err(QM_ERR_STATE, "planner could not place a gate (internal error)");
         // sharded register: what is left needs a non-diagonal target on a global qubit.  Exchange the
         // global qubits with the top local ones (all-to-all over NVLink) and relabel the pending gates.
@@ -787,6 +827,38 @@ extern "C" int32_t qm_precompile_circuit(qm_state* st, const qm_gate* gates, int
     st->gphase[0] = g0; st->gphase[1] = g1;          // nothing was applied: the encodings' global-phase factors are not owed
     if (n_compiled) *n_compiled = (int32_t)(jit_stats().compiled - before);
     return rc;
+}
+
+static int zfold_result(qm_state* st, double** h_pairs, double** h_tot) {
+    // the sums the last pass left in d_zfold -> pinned host memory (same layout as qm_zstats: [nl][2] pairs, then the total)
+    const size_t out_doubles = (size_t)st->nl * 2 + 1;
+    const uint64_t ntiles = total_amps(st) >> 12;
+    const int grid = (int)(ntiles < (uint64_t)st->sms ? ntiles : (uint64_t)st->sms);
+    const double* d_out = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(st->d_zfold) + 256) + (size_t)grid * kV4FoldVals;
+    QM_TRY(ENSURE_PIN(st, h_scratch, out_doubles * 8));
+    CU(cudaMemcpyAsync(st->h_scratch, d_out, out_doubles * 8, cudaMemcpyDeviceToHost, st->stream));
+    st->ctr.bytes_d2h += out_doubles * 8;
+    QM_TRY(qm_sync(st));
+    *h_pairs = st->h_scratch; *h_tot = st->h_scratch + (size_t)st->nl * 2;
+    return QM_OK;
+}
+
+// qm_apply_circuit + qm_expect_z_all in one call; the readout is folded into the last pass when it can be (QM_OPT_ZFOLD)
+extern "C" int32_t qm_apply_circuit_expect_z(qm_state* st, const qm_gate* gates, int32_t ngates, double threshold, double* out_host) {
+    if (!st || !out_host || (!gates && ngates > 0) || ngates < 0) return set_err(QM_ERR_ARG, "null argument");
+    QM_TRY(validate_gates(st, gates, ngates, 0));
+    QM_TRY(flush(st));
+    CU(cudaSetDevice(st->device));
+    st->zfold_want = true; st->zfold_done = false; st->zfold_thr = threshold;
+    const int rc = run_circuit(st, gates, ngates, nullptr, 0);
+    st->zfold_want = false;
+    if (rc != QM_OK) { st->zfold_done = false; return rc; }
+    double *pairs, *tot;
+    if (st->zfold_done) { st->zfold_done = false; st->ctr.folded_readouts++; QM_TRY(zfold_result(st, &pairs, &tot)); }
+    else QM_TRY(qm_zstats(st, threshold, &pairs, &tot));
+    if (st->dist) return dist_finish_z(st, pairs, tot, out_host);
+    memcpy(out_host, pairs, (size_t)st->batch * st->nl * 2 * sizeof(double));
+    return QM_OK;
 }
 
 extern "C" int32_t qm_apply_circuit(qm_state* st, const qm_gate* gates, int32_t ngates) {
@@ -1695,13 +1767,13 @@ extern "C" int32_t qm_jit_check(int32_t n_qubits, int32_t low_bits, double max_c
         if (!encode_v4(P, prog[0], gph, true)) return set_err(QM_ERR_STATE, "pass cannot be encoded");
         out[0]++;
         std::string ptx;
-        if (!jit_ptx_for(P.m, prog[0], ptx)) continue;
+        if (!jit_ptx_for(P.m, prog[0], ptx, (compile & 2) != 0)) continue;
         if (out[1] == 0 && ptx_out && ptx_cap > 0) snprintf(ptx_out, (size_t)ptx_cap, "%s", ptx.c_str());
         out[1]++;
         std::vector<uint32_t> sig; jit_structure_bytes(prog[0], P.m, sig);
         if (std::find(seen.begin(), seen.end(), sig) == seen.end()) { seen.push_back(sig); out[3]++; }
         { uint64_t k[2]; jit_hash(sig, k); out[5] = (int64_t)(((uint64_t)out[5] * 0x100000001b3ull) ^ k[0] ^ (k[1] << 1)); }
-        if (compile) {
+        if (compile & 1) {
             std::vector<char> cubin; std::string log;
             if (!jit_cubin_for(ptx, cubin, log, nullptr)) return set_err(QM_ERR_STATE, "pass %lld does not assemble: %s", (long long)out[0] - 1, log.c_str());
             out[2]++;

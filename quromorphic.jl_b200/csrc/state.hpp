@@ -40,6 +40,10 @@ struct qm_state {
     int overlap_depth = 2;      // ... passes in front of an exchange that run slab by slab beside it (1..4)
     int slab_bits = 3;          // ... and log2 of the number of slabs (measured: profiles/r2f_*, r2g_*)
     bool defer_pass = true;     // QM_OPT_DEFER_PASS: sharded registers may postpone the last pass before an exchange to after it (qm_api.cu run_circuit)
+    bool zfold = true;          // QM_OPT_ZFOLD: qm_apply_circuit_expect_z may take the <Z> sums inside the last pass
+    bool zfold_want = false;    // ... inside that call: run_circuit folds the readout into its last pass if it can
+    bool zfold_done = false;    // ... and says here whether it did (the sums are then in d_zfold)
+    double zfold_thr = 0.0;
     int dry_run = 0;            // inside qm_precompile_circuit: run_circuit launches nothing; 1 = plan only (into the plan cache), 2 = replay the plan and compile its kernels
     int jit = 2;                // QM_OPT_JIT: a pass program whose opcode sequence has been seen this many times is compiled (0 = never)
     bool time_passes = false;   // QM_OPT_TIME_PASSES: CUDA events around every fused pass (diagnostics, tools/pass_model.py)
@@ -69,6 +73,8 @@ struct qm_state {
     unsigned char* d_blob = nullptr; size_t d_blob_cap = 0;
     unsigned char* h_blob = nullptr; size_t h_blob_cap = 0;
     double* d_scratch = nullptr; size_t d_scratch_cap = 0;   // partial sums
+    double* d_zfold = nullptr; size_t d_zfold_cap = 0;       // folded readout: V4Fold | per-CTA partials | [nl][2] pairs | total
+    double* h_zfold = nullptr; size_t h_zfold_cap = 0;       // pinned staging of the V4Fold block
     double* h_scratch = nullptr; size_t h_scratch_cap = 0;   // pinned
     double* d_slots = nullptr; size_t d_slots_cap = 0;
     double* h_slots = nullptr; size_t h_slots_cap = 0;       // pinned staging of the per-state coefficients, two halves used alternately

@@ -19,7 +19,7 @@ import Quromorphic.QSim: nb, u2!, h!, x!, y!, z!, rx!, ry!, rz!, controlled!, cn
                           density_matrix, statevector_to_density_matrix      # new METHODS of the reference's functions
 import Quromorphic.QInfo: partial_trace, entanglement_entropy, von_neumann_entropy
 
-export B200State, B200Density, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, precompile_circuit!, jit_cache_dir, QMGate
+export B200State, B200Density, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, apply_circuit_expect_z!, precompile_circuit!, jit_cache_dir, QMGate
 
 const LIB = get(ENV, "QM_B200_LIB", joinpath(@__DIR__, "..", "libqm_b200.so"))
 
@@ -52,6 +52,7 @@ check(rc) = rc == 0 ? nothing : error(lasterror())      # ErrorException, like t
 # qm_set_option keys (include/qm_b200.h).  The defaults are the measured ones; these are tuning / debugging knobs.
 const OPT_EAGER, OPT_TILE_BITS, OPT_LOW_BITS, OPT_FUSE, OPT_TRACE, OPT_PIPELINE, OPT_MAX_COST, OPT_TIME_PASSES, OPT_SHORT_PCT = 0:8
 const OPT_OVERLAP, OPT_XSM, OPT_XUN, OPT_SLAB_BITS, OPT_OVERLAP_DEPTH, OPT_JIT = 9:14      # OPT_JIT: compiled pass kernels (0 never, 1 at first sight, default 2)
+const OPT_DEFER_PASS, OPT_ZFOLD = 15, 16                                                    # OPT_ZFOLD: <Z> sums inside the last pass of apply_circuit_expect_z! (default 1)
 set_option!(s, key::Integer, value::Integer) =
     check(ccall((:qm_set_option, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), s.handle, key, value))
 
@@ -139,6 +140,19 @@ function precompile_circuit!(s::B200State, gates::Vector{QMGate})
     return Int(k[])
 end
 jit_cache_dir(path::AbstractString) = check(ccall((:qm_jit_cache_dir, LIB), Int32, (Cstring,), path))
+
+"""
+    apply_circuit_expect_z!(s, gates; threshold = s.threshold) -> Array{Float64} (2 x n x batch: out[:, q, b] = measure_z of qubit q of register b)
+
+A reservoir step in one call: `apply_circuit!` followed by `expect_z_all`.  On a large register the sums of `measure_z` are
+taken inside the last fused pass (QM_OPT_ZFOLD), so the state is not read again for the readout.
+"""
+function apply_circuit_expect_z!(s::B200State, gates::Vector{QMGate}; threshold::Float64 = s.threshold)
+    out = Array{Float64}(undef, 2, s.n, s.batch)
+    check(ccall((:qm_apply_circuit_expect_z, LIB), Int32, (Ptr{Cvoid}, Ptr{QMGate}, Int32, Float64, Ptr{Float64}),
+                s.handle, gates, length(gates), threshold, out))
+    return out
+end
 
 function apply_circuit!(s::B200State, gates::Vector{QMGate})
     check(ccall((:qm_apply_circuit, LIB), Int32, (Ptr{Cvoid}, Ptr{QMGate}, Int32), s.handle, gates, length(gates)))

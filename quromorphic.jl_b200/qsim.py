@@ -178,6 +178,15 @@ class B200State:
         L.check(L.lib().qm_precompile_circuit(self._h, gates.ctypes.data, len(gates), C.byref(n)))
         return n.value
 
+    def apply_circuit_expect_z(self, gates, threshold=None):
+        """apply_circuit(gates) then expect_z_all(threshold) in one call — a reservoir step.  When the last fused pass runs as
+        a compiled kernel the <Z> sums are taken inside it (QM_OPT_ZFOLD; counters()["folded_readouts"])."""
+        assert gates.dtype == L.GATE_DTYPE and gates.flags["C_CONTIGUOUS"]
+        out = np.empty((self.batch, self.n, 2), dtype=np.float64)
+        thr = self.threshold if threshold is None else threshold
+        L.check(L.lib().qm_apply_circuit_expect_z(self._h, gates.ctypes.data, len(gates), thr, L.dptr(out)))
+        return out if self.batch > 1 else out[0]
+
     def apply_circuit(self, gates):
         """gates: numpy structured array of _lib.GATE_DTYPE, 0-based textbook bits (wire format)."""
         assert gates.dtype == L.GATE_DTYPE and gates.flags["C_CONTIGUOUS"]

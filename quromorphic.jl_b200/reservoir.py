@@ -79,8 +79,8 @@ class QuantumReservoir:
 
     def step(self, x):
         """evolve one step; returns the feature vector z_q = p0 - p1 (and the two entropies if asked)"""
-        self.state.apply_circuit(self.step_gates(x))
-        z = self.state.expect_z_all()
+        # one call per step: circuit + all-qubit <Z>; on a large register the sums are taken inside the last fused pass (QM_OPT_ZFOLD)
+        z = self.state.apply_circuit_expect_z(self.step_gates(x))
         feats = z[:, 0] - z[:, 1]
         if self.entropy_k:
             k, n = self.entropy_k, self.n

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for s in syms:
         assert hasattr(lib, s), s
         assert s in pkg._lib.SIGNATURES, "ctypes signature missing for " + s
-    assert lib.qm_abi_version() == 3
+    assert lib.qm_abi_version() == 4
 
 
 def test_gate_struct_layout(pkg):
