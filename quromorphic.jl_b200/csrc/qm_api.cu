@@ -659,10 +659,12 @@ static int run_circuit(qm_state* st, const qm_gate* gates, int ngates, const dou
         if (!leftover) {
             // qm_apply_circuit_expect_z: the very last pass also takes the <Z> sums when it is a compiled kernel over one
             // whole register and the ZFOLD flavour of that kernel is there (same threshold rule as every compiled kernel)
-            if (st->zfold_want && st->zfold && !st->dry_run && tma && st->batch == 1 && st->nl < 63 && !held.empty()) {
+            // (qm_precompile_circuit compiles that flavour of the last pass as well: the caller may be about to use either call)
+            if ((st->zfold_want || st->dry_run == 2) && st->zfold && tma && st->batch == 1 && st->nl < 63 && !held.empty()) {
                 Item& last = held.back();
                 if (last.kind == 0 && last.jk && last.P.m == 12 && last.P.tl.size() == 12) {
-                    if (JitKernel* jz = jit_get(st->device, 12, last.prog, jit_thr, true)) { last.jk = jz; last.fold = true; }
+                    JitKernel* jz = jit_get(st->device, 12, last.prog, jit_thr, true);
+                    if (jz && !st->dry_run) { last.jk = jz; last.fold = true; }
                 }
             }
             QM_TRY(launch_all_held()); finished = true; break;

@@ -126,3 +126,22 @@ def test_folded_readout_on_a_sharded_register(pkg, n, world):
     for r, out in enumerate(res):
         assert out["err"] < RTOL and out["err_sep"] < 1e-14 and out["err0"] < RTOL, (r, out)
     assert len({out["folded"] for out in res}) == 1, res             # all ranks took the same path
+
+
+def test_precompiled_circuit_folds_at_first_sight(pkg):
+    """qm_precompile_circuit also compiles the fold flavour of the last pass: on a register large enough for the default
+    QM_OPT_JIT (2^26 amplitudes) the FIRST qm_apply_circuit_expect_z already runs compiled and folded"""
+    n = 26
+    gates = pkg.circuits.c4_step(n, 1)
+    st = pkg.B200State(n, 0)
+    k = st.precompile_circuit(gates)
+    assert k >= 2, k                                  # at least one pass kernel and the fold flavour of the last one
+    st.counters_reset()
+    z = st.apply_circuit_expect_z(gates)
+    c = st.counters()
+    assert c["folded_readouts"] == 1 and c["compiled_passes"] == c["passes"] > 0, c
+    assert float(np.max(np.abs(z - st.expect_z_all()))) < 1e-14
+    z0 = st.apply_circuit_expect_z(pkg.circuits.c4_step(n, 7), -1.0)                  # same structure (period 6), new angles, no threshold
+    assert st.counters()["folded_readouts"] == 2
+    assert abs(float(z0[0].sum()) - 1.0) < 1e-12 and abs(st.norm2() - 1.0) < 1e-12
+    st.close()

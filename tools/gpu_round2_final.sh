@@ -22,4 +22,8 @@ except Exception as e:
 PY
   tail -3 gpurun_out/${P}_bench.err
   timeout 200 python tools/bench_first_sight.py --out gpurun_out/${P}_first_sight.json > gpurun_out/${P}_first_sight.log 2>&1; echo "first sight rc=$?"; tail -c 1200 gpurun_out/${P}_first_sight.log
+  # ncu --set full of one reservoir step with the folded readout and one without (30 qubits: passes of ~6 ms), after the plain runs above
+  timeout 150 ncu --set full --clock-control none --kernel-name-base mangled -k regex:k_fused_tma -s 56 -c 16 -f -o gpurun_out/${P}_zfold \
+      python tools/bench_zfold.py --qubits 30 --steps 2 --rounds 1 > gpurun_out/${P}_zfold_ncu.log 2>&1; echo "ncu rc=$?"
+  timeout 60 python tools/ncu_summary.py gpurun_out/${P}_zfold.ncu-rep > gpurun_out/${P}_ncu_k_fused_tma_zfold_30q.txt 2>&1; head -c 1500 gpurun_out/${P}_ncu_k_fused_tma_zfold_30q.txt
 fi
