@@ -483,6 +483,7 @@ def main():
                                "ms_per_step": b["ms_per_step"], "gates_per_step": b["gates_per_step"],
                                "passes_per_step": b["passes_per_step"], "fused_pass_gbs": b["roofline"]["achieved"],
                                "step_call": b.get("step_call"), "folded_readouts_per_step": b.get("folded_readouts_per_step"),
+                               "step_readout_vs_separate_readout": b.get("step_readout_vs_separate_readout"), "norm2": b.get("norm2"),
                                "note": "weak-scaling efficiency of the N-GPU C4 lines = (ms_per_step / gates_per_step here) / (theirs)"}
         except Exception as e:            # the base is informational: never lose the headline line over it
             line["c4_base"] = {"error": str(e)[:200]}

@@ -125,6 +125,9 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
     # reference's 1e-10 threshold drops most of the mass, so the thresholded readout alone proves nothing
     norm2 = st.norm2()
     z_nothr = st.expect_z_all(threshold=-1.0)
+    # ... and the last timed step's readout (taken inside its last pass when the fold applies) against the ordinary readout
+    # kernels on the very same final state, at full size (collective calls: every rank makes them)
+    fold_diff = float(np.max(np.abs(np.asarray(z) - np.asarray(st.expect_z_all())))) if args.steps > 0 else 0.0
     if rank == 0:
         unit = "gates/s (one gate over 2^30 amplitudes)"
         scale = 2.0 ** (n - 30)
@@ -164,6 +167,7 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
             "deferred_passes_per_step": c.get("deferred_passes", 0) / args.steps,
             "folded_readouts_per_step": c.get("folded_readouts", 0) / args.steps,
             "step_call": "qm_apply_circuit_expect_z" if zfold else "qm_apply_circuit + qm_expect_z_all",
+            "step_readout_vs_separate_readout": fold_diff, "step_readout_ok": bool(fold_diff < 1e-12),
             "structure_warmup_steps": sw,
             "compiled_pass_kernels": dict(L.jit_stats(), note="rank 0's process; compiled during the untimed structure warm-up"),
         }
@@ -182,7 +186,7 @@ def run_dist(args, pkg, rank, world, local_rank, emit=True):
     st.close()
     if not single:
         dist.destroy_process_group()
-    if rank == 0 and emit and parity is not None and not (parity.get("ok") and line["norm2_ok"]):
+    if rank == 0 and emit and parity is not None and not (parity.get("ok") and line["norm2_ok"] and line["step_readout_ok"]):
         import sys
         sys.stderr.write("bench_dist.py: PARITY FAILED: %s norm2=%r\n" % (json.dumps(parity), norm2))
         sys.exit(1)
