@@ -325,6 +325,33 @@ def test_compiled_pass_kernels_generate_and_assemble_for_sm_100a(pkg):
         assert d2["assembled"] == d2["passes"] and 10000 < d2["max_cubin_bytes"] < 400000
 
 
+def test_fold_flavour_of_the_compiled_kernels_assembles_and_leaves_the_plain_one_alone(pkg):
+    """QM_OPT_ZFOLD without a GPU: the ZFOLD instantiation of the pass kernel (all-qubit <Z> sums taken inside the last pass) is a
+    second PTX template with the same generated groups spliced in; it assembles for sm_100a, and the plain kernels carry none of it."""
+    import re
+    L = pkg._lib
+    gates = pkg.circuits.c4_step(20, 2)
+    plain = L.jit_check(20, gates, max_cost=80.0, compile=False, want_ptx=True)
+    fold = L.jit_check(20, gates, max_cost=80.0, compile=False, want_ptx=True, zfold=True)
+    assert plain["passes"] == fold["passes"] == fold["with_ptx"] > 0 and plain["structure_hash"] == fold["structure_hash"]
+    entry = lambda t: re.search(r"\.entry\s+(\w+)", t).group(1)
+    assert entry(plain["ptx"]) != entry(fold["ptx"]) and "k_fused_tma" in entry(fold["ptx"])
+    body = lambda t: t[t.index("// QMJIT_BEGIN"):t.index("// QMJIT_END")]
+    # the template's operand register names and the entry's own (mangled) name differ between the two
+    strip = lambda t: re.sub(r"_ZN2qm11k_fused_tma\w+?_param_", "K_param_", re.sub(r"%\w+", "%", t))
+    assert strip(body(plain["ptx"])) == strip(body(fold["ptx"]))          # same generated group code
+    for marker in ("shfl.sync.bfly", "bar.sync \t8", "setp.gt.f64"):
+        assert marker not in plain["ptx"].replace("bar.sync 8", "bar.sync \t8")
+    assert fold["ptx"].count("shfl.sync.bfly") >= 20 and "setp.gt.f64" in fold["ptx"]
+    try:
+        d = L.jit_check(20, gates, max_cost=80.0, compile=True, zfold=True)
+    except L.QMError as e:
+        if "libnvJitLink not found" in str(e):
+            pytest.skip("libnvJitLink is not installed here")
+        raise
+    assert d["assembled"] == d["passes"] and 10000 < d["max_cubin_bytes"] < 400000
+
+
 def test_compiled_kernel_disk_cache(pkg, tmp_path):
     """qm_jit_cache_dir: assembled kernels are kept as files keyed by the complete PTX text; a second walk over the same circuit
     reads them instead of assembling again, a damaged file is ignored and replaced, and without a directory nothing is written."""
