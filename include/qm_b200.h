@@ -281,7 +281,8 @@ int32_t qm_jit_stats(uint64_t out[4], double* compile_ms);
  * default unless the environment variable QM_JIT_CACHE_DIR names one) that keeps every assembled kernel as a file keyed by a
  * hash of the complete PTX text and of the assembler's version, so that a later process running a circuit of the same
  * structure loads its kernels instead of assembling them again.  Processes may share the directory (files are renamed into
- * place); a file that does not verify is ignored.  qm_jit_cache_stats: out = {kernels read from the directory, kernels
+ * place); a file that does not verify is ignored.  The checks guard against truncation and stale files, not against an
+ * adversary: the directory holds code the GPU will run, so give it the permissions of the library itself.  qm_jit_cache_stats: out = {kernels read from the directory, kernels
  * written to it} since the process started. */
 int32_t qm_jit_cache_dir(const char* path);
 int32_t qm_jit_cache_stats(uint64_t out[2]);
