@@ -1,0 +1,1361 @@
+"""oracle/jl_subset.py — TEST INFRASTRUCTURE.  An interpreter for the subset of Julia that the reference's `src/Quantum/*.jl`
+(and the assertions of its `test/test_QSim.jl`, `test/test_QInfo.jl`) are written in, so that golden vectors can be produced by
+EXECUTING THE REFERENCE'S OWN SOURCE TEXT where it lies (/root/reference, read at generation time, never copied) although no Julia
+runtime exists in this image.  It knows nothing about qubits or gates: it implements Julia syntax (modules, constants, generic
+functions with type-annotated methods and dispatch on them, `if` / ternary / short-circuit forms as expressions, `for` over
+ranges incl. `for i in a, j in b`, 1-based indexing with `end`, matrix literals with Julia's whitespace rule, broadcasting dots,
+the adjoint quote, tuples, Dicts, `@assert`, the `Test` macros) over numpy arrays, plus the handful of Base / LinearAlgebra
+functions those files call (kron, Diagonal, mul!, eigen(Hermitian(.)), tr, ...).  Dense algebra is delegated to numpy: results
+agree with a Julia run up to the rounding order inside BLAS/LAPACK (1e-15 relative), which is why fixtures made with it are held
+at 1e-12, like everything else.
+
+Only tests/ and the fixture generator under tests/golden/ use this module.  The product never imports it."""
+import math
+import re
+
+import numpy as np
+
+
+class JuliaError(Exception):
+    """error(...) / failed @assert / MethodError inside interpreted code"""
+
+
+class JType:
+    def __init__(self, name, params=()):
+        self.name, self.params = name, tuple(params)
+
+    def __repr__(self):
+        return self.name + ("{%s}" % ",".join(map(repr, self.params)) if self.params else "")
+
+
+class JRange:
+    def __init__(self, start, stop, step=1):
+        self.start, self.stop, self.step = start, stop, step
+
+    def values(self):
+        if all(isinstance(v, (int, np.integer)) for v in (self.start, self.stop, self.step)):
+            return range(int(self.start), int(self.stop) + (1 if self.step > 0 else -1), int(self.step))
+        n = int(math.floor((self.stop - self.start) / self.step + 1e-12)) + 1
+        return [self.start + i * self.step for i in range(max(n, 0))]
+
+    def __len__(self):
+        return len(self.values())
+
+
+class Hermitian:
+    def __init__(self, a):
+        self.a = np.asarray(a)
+
+
+class ReturnEx(Exception):
+    def __init__(self, v): self.v = v
+
+
+class BreakEx(Exception):
+    pass
+
+
+class ContinueEx(Exception):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------ tokenizer
+OPS = [".==", ".!=", ".<=", ".>=", "...", "===", "!==", "==", "!=", "<=", ">=", "&&", "||", "<<", ">>", "+=", "-=", "*=", "/=", "->", "::", "=>",
+       ".≈", ".+", ".-", ".*", "./", ".^", ".<", ".>", "+", "-", "*", "/", "\\", "^", "%", "÷", "<", ">", "=", "!", "&", "|", "?", ":", ",",
+       ";", "(", ")", "[", "]", "{", "}", ".", "'", "@", "≈", "√", "≤", "≥", "≠", "$"]
+KEYWORDS = {"function", "end", "if", "elseif", "else", "for", "while", "return", "const", "module", "using", "import", "export", "begin", "in",
+            "true", "false", "nothing", "break", "continue", "let", "global", "local", "do", "struct", "mutable", "try", "catch", "finally"}
+
+
+class Tok:
+    __slots__ = ("kind", "val", "sp", "line")
+
+    def __init__(self, kind, val, sp, line):
+        self.kind, self.val, self.sp, self.line = kind, val, sp, line     # sp: whitespace (or start of line) before the token
+
+    def __repr__(self):
+        return "%s(%r)@%d" % (self.kind, self.val, self.line)
+
+
+def _is_ident_start(c):
+    return c == "_" or c.isalpha() or (ord(c) > 0x2000 and c not in "≈√≤≥≠÷⟩" and (c + "a").isidentifier())
+
+
+def tokenize(src):
+    toks, i, n, line, sp = [], 0, len(src), 1, True
+    num_re = re.compile(r"(0x[0-9a-fA-F]+|(\d[\d_]*\.?\d*|\.\d+)([eE][+-]?\d+)?)")
+    while i < n:
+        c = src[i]
+        if c == "\n":
+            toks.append(Tok("nl", "\n", sp, line)); line += 1; i += 1; sp = True; continue
+        if c in " \t\r":
+            i += 1; sp = True; continue
+        if c == "#":
+            if src.startswith("#=", i):
+                j = src.index("=#", i) + 2
+                line += src.count("\n", i, j); i = j
+            else:
+                while i < n and src[i] != "\n": i += 1
+            sp = True; continue
+        if src.startswith('"""', i):
+            j = src.index('"""', i + 3)
+            toks.append(Tok("str", src[i + 3:j], sp, line)); line += src.count("\n", i, j); i = j + 3; sp = False; continue
+        if c == '"':
+            j, buf = i + 1, []
+            while src[j] != '"':
+                if src[j] == "\\":
+                    buf.append({"n": "\n", "t": "\t", '"': '"', "\\": "\\", "$": "$"}.get(src[j + 1], src[j + 1])); j += 2
+                else:
+                    buf.append(src[j]); j += 1
+            toks.append(Tok("str", "".join(buf), sp, line)); i = j + 1; sp = False; continue
+        if c == "'":
+            prev = toks[-1] if toks else None
+            adj = prev is not None and not sp and (prev.kind in ("id", "num") or prev.val in (")", "]", "'", "end"))
+            if not adj:                                   # a character literal
+                j = i + 1
+                ch = src[j + 1] if src[j] == "\\" else src[j]
+                j += 2 if src[j] == "\\" else 1
+                assert src[j] == "'", "bad char literal line %d" % line
+                toks.append(Tok("str", ch, sp, line)); i = j + 1; sp = False; continue
+        m = num_re.match(src, i) if (c.isdigit() or (c == "." and i + 1 < n and src[i + 1].isdigit())) else None
+        if m:
+            txt = m.group(0)
+            # "1:n" must not eat the range colon, "2.field" does not occur; a trailing "." followed by an operator char is a broadcast dot
+            if txt.endswith(".") and i + len(txt) < n and src[i + len(txt)] in "*/^+-=<>≈!":
+                txt = txt[:-1]
+            i += len(txt)
+            val = int(txt.replace("_", ""), 0) if re.fullmatch(r"0x[0-9a-fA-F]+|[\d_]+", txt) else float(txt.replace("_", ""))
+            toks.append(Tok("num", val, sp, line)); sp = False
+            continue
+        if _is_ident_start(c):
+            j = i + 1
+            while j < n and (src[j] == "_" or src[j].isalnum() or src[j] == "!" or (ord(src[j]) > 0x2000 and _is_ident_start(src[j])) or
+                             src[j] in "₀₁₂₃₄₅₆₇₈₉ᵅ′"):
+                if src[j] == "!" and j + 1 < n and src[j + 1] == "=":      # a != b
+                    break
+                j += 1
+            w = src[i:j]
+            toks.append(Tok("kw" if w in KEYWORDS else "id", w, sp, line)); i = j; sp = False; continue
+        for op in OPS:
+            if src.startswith(op, i):
+                toks.append(Tok("op", op, sp, line)); i += len(op); sp = False; break
+        else:
+            raise SyntaxError("jl_subset: cannot tokenize %r at line %d" % (c, line))
+    toks.append(Tok("nl", "\n", True, line)); toks.append(Tok("eof", None, True, line))
+    return toks
+
+
+# ------------------------------------------------------------------------------------------------ parser (AST = tuples)
+BINPREC = {"||": 3, "&&": 4,
+           "==": 5, "!=": 5, "<": 5, "<=": 5, ">": 5, ">=": 5, "≈": 5, "≤": 5, "≥": 5, "≠": 5, "===": 5, "!==": 5, "in": 5,
+           ".==": 5, ".!=": 5, ".<": 5, ".<=": 5, ".>": 5, ".>=": 5, ".≈": 5,
+           ":": 6, "+": 7, "-": 7, "|": 7, ".+": 7, ".-": 7,
+           "*": 8, "/": 8, "%": 8, "&": 8, "÷": 8, "\\": 8, ".*": 8, "./": 8,
+           "<<": 9, ">>": 9}
+UNARY_PREC = 10
+POW_PREC = 11
+
+
+class Parser:
+    def __init__(self, toks):
+        self.t, self.i = toks, 0
+        self.no_nl = 0          # > 0 inside ( ) and [ ]: newlines are not statement ends
+
+    # -- token helpers
+    def peek(self, k=0):
+        j = self.i
+        while True:
+            tok = self.t[j]
+            if tok.kind == "nl" and self.no_nl:
+                j += 1; continue
+            if k == 0: return tok
+            k -= 1; j += 1
+
+    def next(self):
+        while self.t[self.i].kind == "nl" and self.no_nl: self.i += 1
+        tok = self.t[self.i]; self.i += 1
+        return tok
+
+    def at(self, val, kind=None):
+        tok = self.peek()
+        return tok.val == val and tok.kind != "str" and (kind is None or tok.kind == kind)
+
+    def accept(self, val):
+        if self.at(val): return self.next()
+        return None
+
+    def expect(self, val):
+        tok = self.next()
+        if tok.val != val or tok.kind == "str":
+            raise SyntaxError("jl_subset: expected %r, got %r at line %d" % (val, tok.val, tok.line))
+        return tok
+
+    def skip_nl(self):
+        while self.t[self.i].kind == "nl" or (self.t[self.i].kind == "op" and self.t[self.i].val == ";"): self.i += 1
+
+    # -- statements
+    def block(self, enders=("end",)):
+        out = []
+        saved, self.no_nl = self.no_nl, 0
+        while True:
+            self.skip_nl()
+            tok = self.peek()
+            if tok.kind == "eof" or (tok.kind == "kw" and tok.val in enders): break
+            out.append(self.statement())
+        self.no_nl = saved
+        return ("block", out)
+
+    def statement(self):
+        tok = self.peek()
+        if tok.kind == "kw":
+            v = tok.val
+            if v == "module":
+                self.next(); name = self.next().val; body = self.block(); self.expect("end"); return ("module", name, body)
+            if v in ("using", "import", "export"):
+                self.next()
+                while True:                              # names, possibly continued over lines after a comma
+                    while self.peek().kind not in ("nl", "eof") and not self.at(","): self.next()
+                    if self.accept(","):
+                        while self.t[self.i].kind == "nl": self.i += 1
+                        continue
+                    break
+                return ("nop",)
+            if v == "const":
+                self.next(); return self.statement()
+            if v in ("global", "local"):
+                self.next(); return self.statement()
+            if v == "function": return self.function_def()
+            if v == "return":
+                self.next()
+                if self.peek().kind in ("nl", "eof") or self.at("end") or self.at(";"): return ("return", None)
+                return ("return", self.expr_or_tuple())
+            if v == "break": self.next(); return ("break",)
+            if v == "continue": self.next(); return ("continue",)
+            if v == "for": return self.for_stmt()
+            if v == "while":
+                self.next(); cond = self.expr(); body = self.block(); self.expect("end"); return ("while", cond, body)
+        if tok.kind == "op" and tok.val == "@": return self.macro()
+        if tok.kind == "str" and self.t[self.i + 1].kind == "nl":      # a docstring (or a bare string): no effect
+            self.next(); return ("nop",)
+        e = self.expr_or_tuple()
+        tok = self.peek()
+        if tok.kind == "op" and tok.val in ("=", "+=", "-=", "*=", "/="):
+            self.next()
+            while self.t[self.i].kind == "nl": self.i += 1
+            rhs = self.statement_rhs()
+            if tok.val == "=" and e[0] == "call" and not e[3]:         # short-form method definition  f(x::T) = expr
+                return ("function", e[1][1] if e[1][0] == "id" else None, [self.param(a) for a in e[2]], ("block", [("return", rhs)]))
+            return ("assign", tok.val, e, rhs)
+        return ("expr", e)
+
+    def statement_rhs(self):
+        e = self.expr_or_tuple()
+        if self.at("="):                                # a = b = c
+            self.next(); return ("assignx", e, self.statement_rhs())
+        return e
+
+    def param(self, a):
+        if a[0] == "id": return (a[1], None, None)
+        if a[0] == "typed": return (a[1][1] if a[1] and a[1][0] == "id" else "_", a[2], None)
+        if a[0] == "kwarg": nm = self.param(a[1]); return (nm[0], nm[1], a[2])
+        raise SyntaxError("jl_subset: unsupported parameter form %r" % (a,))
+
+    def function_def(self):
+        self.expect("function")
+        name = self.next().val
+        while self.accept("."): name = self.next().val       # function Mod.name(...)
+        self.expect("(")
+        self.no_nl += 1
+        params = []
+        while not self.at(")"):
+            if self.accept(";"): continue
+            a = self.expr()
+            if self.accept("="): a = ("kwarg", a, self.expr())
+            params.append(self.param(a))
+            if not self.accept(","):
+                if self.at(";"): continue
+                break
+        self.no_nl -= 1
+        self.expect(")")
+        if self.accept("::"): self.type_expr()
+        if self.at("where"):
+            while self.peek().kind != "nl": self.next()
+        body = self.block(); self.expect("end")
+        return ("function", name, params, body)
+
+    def for_stmt(self):
+        self.expect("for")
+        iters = []
+        while True:
+            var = self.expr_or_tuple_noin()
+            tok = self.next()
+            if tok.val not in ("in", "=", "∈"): raise SyntaxError("jl_subset: bad for at line %d" % tok.line)
+            iters.append((var, self.expr()))
+            if not self.accept(","): break
+        body = self.block(); self.expect("end")
+        return ("for", iters, body)
+
+    def macro(self):
+        self.expect("@")
+        name = self.next().val
+        if name == "testset":
+            label = None
+            if self.peek().kind == "str": label = self.next().val
+            if self.at("for"):
+                f = self.for_stmt(); return ("testset", label, ("block", [f]))
+            self.expect("begin"); body = self.block(); self.expect("end")
+            return ("testset", label, body)
+        if name == "assert":
+            cond = self.expr(); msg = None
+            if self.peek().kind == "str": msg = self.next().val
+            return ("assert", cond, msg)
+        if name in ("test", "test_nowarn", "test_broken"):
+            e = self.expr(); kw = {}
+            while self.peek().kind == "id" and self.peek(1).val == "=":
+                k = self.next().val; self.next(); kw[k] = self.expr()
+            return ("test", name, e, kw, self.t[self.i - 1].line)
+        if name == "test_throws":
+            exc = self.expr(); e = self.expr()
+            return ("test_throws", exc, e, self.t[self.i - 1].line)
+        if name in ("inbounds", "views", "inline", "simd", "fastmath", "show", "time", "info", "warn"):
+            return self.statement()
+        raise SyntaxError("jl_subset: unsupported macro @%s" % name)
+
+    # -- expressions
+    def expr_or_tuple(self):
+        e = self.expr()
+        if self.at(",") and not self.no_nl:
+            items = [e]
+            while self.accept(","): items.append(self.expr())
+            return ("tuple", items)
+        return e
+
+    def expr_or_tuple_noin(self):
+        self._noin = True
+        try:
+            e = self.expr(6)
+        finally:
+            self._noin = False
+        return e
+
+    _noin = False
+    _inarray = 0
+
+    def expr(self, minprec=0):
+        lhs = self.ternary() if minprec == 0 else self.binary(minprec)
+        return lhs
+
+    def ternary(self):
+        cond = self.binary(3)
+        if self.at("?"):
+            self.next()
+            self._nr_depths.append(self.no_nl)          # a ':' at this nesting depth ends the middle operand (it is not a range)
+            a = self.ternary()
+            self._nr_depths.pop()
+            self.expect(":")
+            b = self.ternary()
+            return ("if", [(cond, ("block", [("expr", a)]))], ("block", [("expr", b)]))
+        if self.at("->"):
+            self.next(); body = self.ternary()
+            params = [self.param(x) for x in (cond[1] if cond[0] == "tuple" else [cond])]
+            return ("lambda", params, ("block", [("return", body)]))
+        return cond
+
+    def binary(self, minprec):
+        lhs = self.unary()
+        while True:
+            tok = self.peek()
+            op = tok.val if tok.kind in ("op", "kw") else None
+            if op == "in" and self._noin: break
+            if op not in BINPREC or tok.kind == "str": break
+            prec = BINPREC[op]
+            if prec < minprec: break
+            if op == ":" and self._nr_depths and self.no_nl == self._nr_depths[-1]: break
+            if self._inarray and tok.sp and op in ("+", "-") and not self.t[self.i + 1].sp:   # [a -b]: two elements
+                break
+            if self._inarray and tok.sp and op == ":" : break
+            self.next()
+            while self.t[self.i].kind == "nl": self.i += 1            # an operator at the end of a line continues the expression
+            if op == ":":
+                rhs = self.binary(prec + 1)
+                if self.at(":") and not (self._nr_depths and self.no_nl == self._nr_depths[-1]) and not (self._inarray and self.peek().sp):
+                    self.next(); third = self.binary(prec + 1)
+                    lhs = ("range", lhs, third, rhs)
+                else:
+                    lhs = ("range", lhs, rhs, None)
+                continue
+            rhs = self.binary(prec + 1)
+            if prec == 5 and lhs[0] == "cmp":
+                lhs = ("cmp", lhs[1] + [op], lhs[2] + [rhs])
+            elif prec == 5:
+                lhs = ("cmp", [op], [lhs, rhs])
+            elif op in ("&&", "||"):
+                lhs = (op, lhs, rhs)
+            else:
+                lhs = ("bin", op, lhs, rhs)
+        return lhs
+
+    _nr_depths = []
+
+    def unary(self):
+        tok = self.peek()
+        if tok.kind == "op" and tok.val in ("-", "+", "!", "√"):
+            self.next()
+            operand = self.unary()
+            if tok.val == "-" and operand[0] == "num": return ("num", -operand[1]) if not self.at("^") else ("un", "-", operand)
+            return ("un", tok.val, operand)
+        if tok.kind == "op" and tok.val == ":" and self.peek(1).kind == "id" and not self.peek(1).sp:     # a Symbol :x
+            self.next(); return ("str", self.next().val)
+        return self.power()
+
+    def power(self):
+        base = self.postfix()
+        tok = self.peek()
+        if tok.kind == "op" and tok.val in ("^", ".^"):
+            self.next()
+            exp = self.unary_for_pow()
+            return ("bin", tok.val, base, exp)
+        return base
+
+    def unary_for_pow(self):
+        tok = self.peek()
+        if tok.kind == "op" and tok.val in ("-", "+"):
+            self.next(); return ("un", tok.val, self.unary_for_pow())
+        return self.power()
+
+    def args(self, closer):
+        """call arguments up to `closer`: (positional, keyword dict)"""
+        self.no_nl += 1
+        saved_arr, self._inarray = self._inarray, 0
+        pos, kw, semi = [], {}, False
+        while not self.at(closer):
+            if self.accept(";"): semi = True; continue
+            e = self.expr()
+            if self.at("=") and e[0] == "id":
+                self.next(); kw[e[1]] = self.expr()
+            elif self.at("..."):
+                self.next(); pos.append(("splat", e))
+            elif self.at("for"):                         # generator  f(x for x in xs)
+                self.next(); var = self.expr_or_tuple_noin(); self.next(); it = self.expr()
+                cond = None
+                if self.at("if"): self.next(); cond = self.expr()
+                pos.append(("gen", e, var, it, cond))
+            else:
+                pos.append(e)
+            if not self.accept(","):
+                if self.at(";"): continue
+                break
+        self._inarray = saved_arr
+        self.no_nl -= 1
+        self.expect(closer)
+        return pos, kw
+
+    def postfix(self):
+        e = self.primary()
+        while True:
+            tok = self.peek()
+            if tok.kind != "op": break
+            v = tok.val
+            if v == "(" and not tok.sp:
+                self.next(); pos, kw = self.args(")"); e = ("call", e, pos, kw)
+            elif v == "[" and not tok.sp:
+                self.next()
+                mark = (self.i, self.no_nl, self._inarray, list(self._nr_depths))
+                try:
+                    pos, _ = self.args("]"); e = ("index", e, pos)
+                except SyntaxError:                          # T[a b; c d]: a typed array literal in matrix syntax
+                    self.i, self.no_nl, self._inarray, self._nr_depths = mark[0], mark[1], mark[2], mark[3]
+                    e = ("typedarray", e, self.array_literal())
+            elif v == "{" and not tok.sp:
+                self.next(); self.no_nl += 1
+                ps = []
+                while not self.at("}"):
+                    ps.append(self.type_expr())
+                    if not self.accept(","): break
+                self.no_nl -= 1; self.expect("}")
+                e = ("curly", e, ps)
+            elif v == "'" and not tok.sp:
+                self.next(); e = ("adjoint", e)
+            elif v == "." and not tok.sp and self.peek(1).val == "(" and self.peek(1).kind == "op" and not self.peek(1).sp:
+                self.next(); self.next(); pos, kw = self.args(")"); e = ("bcall", e, pos, kw)
+            elif v == "." and not tok.sp and self.peek(1).kind in ("id", "kw") and not self.peek(1).sp:
+                self.next(); e = ("field", e, self.next().val)
+            elif v == "::":
+                self.next(); e = ("typed", e, self.type_expr())
+            else:
+                break
+        return e
+
+    def type_expr(self):
+        tok = self.next()
+        name = tok.val
+        while self.at(".") and self.peek(1).kind == "id": self.next(); name = self.next().val
+        params = []
+        if self.at("{") and not self.peek().sp:
+            self.next()
+            while not self.at("}"):
+                params.append(self.type_expr())
+                if not self.accept(","): break
+            self.expect("}")
+        return JType(name, params)
+
+    def primary(self):
+        tok = self.next()
+        if tok.kind == "num":
+            nxt = self.t[self.i]
+            if nxt.kind == "id" and not nxt.sp:          # 0.0im, 2π, 3x: numeric-literal juxtaposition
+                self.i += 1
+                if nxt.val == "im": return ("num", complex(0.0, tok.val))
+                return ("bin", "*", ("num", tok.val), ("id", nxt.val))
+            if nxt.kind == "op" and nxt.val == "(" and not nxt.sp:
+                return ("bin", "*", ("num", tok.val), self.postfix_from_paren())
+            return ("num", tok.val)
+        if tok.kind == "str": return ("str", tok.val)
+        if tok.kind == "id": return ("id", tok.val)
+        if tok.kind == "kw":
+            if tok.val == "true": return ("num", True)
+            if tok.val == "false": return ("num", False)
+            if tok.val == "nothing": return ("num", None)
+            if tok.val == "end": return ("endidx",)
+            if tok.val == "if": return self.if_expr()
+            if tok.val == "begin":
+                b = self.block(); self.expect("end"); return ("blockexpr", b)
+            if tok.val == "function":
+                self.i -= 1; return ("fundef", self.function_def())
+        if tok.kind == "op":
+            if tok.val == "(":
+                self.no_nl += 1
+                saved_arr, self._inarray = self._inarray, 0
+                if self.at(")"):
+                    self.next(); self.no_nl -= 1; self._inarray = saved_arr; return ("tuple", [])
+                e = self.expr()
+                if self.at("=") and e[0] == "id":          # (a = 1, b = 2) named tuple: not needed
+                    raise SyntaxError("jl_subset: named tuples are not supported (line %d)" % tok.line)
+                if self.at(","):
+                    items = [e]
+                    while self.accept(","):
+                        if self.at(")"): break
+                        items.append(self.expr())
+                    e = ("tuple", items)
+                else:
+                    e = ("paren", e)
+                self._inarray = saved_arr
+                self.no_nl -= 1
+                self.expect(")")
+                return e
+            if tok.val == "[": return self.array_literal()
+            if tok.val == ":": return ("colon",)
+        raise SyntaxError("jl_subset: unexpected %r at line %d" % (tok.val, tok.line))
+
+    def postfix_from_paren(self):
+        return self.postfix()
+
+    def if_expr(self):
+        clauses, els = [], None
+        saved, self.no_nl = self.no_nl, 0
+        cond = self.expr()
+        body = self.block(("elseif", "else", "end"))
+        clauses.append((cond, body))
+        while True:
+            if self.accept("elseif"):
+                cond = self.expr(); clauses.append((cond, self.block(("elseif", "else", "end"))))
+            elif self.accept("else"):
+                els = self.block(("end",))
+            else:
+                break
+        self.expect("end")
+        self.no_nl = saved
+        return ("if", clauses, els)
+
+    def array_literal(self):
+        """[a, b, c] | [a b; c d] | [x;;] | [f(x) for x in xs]"""
+        self.no_nl += 1
+        rows, cur, commas = [], [], False
+        if self.at("]"):
+            self.next(); self.no_nl -= 1; return ("vect", [])
+        while True:
+            self._inarray += 1
+            e = self.expr()
+            self._inarray -= 1
+            if self.at("for") and not cur and not rows:
+                self.next(); var = self.expr_or_tuple_noin(); self.next(); it = self.expr()
+                cond = None
+                if self.at("if"): self.next(); cond = self.expr()
+                self.expect("]"); self.no_nl -= 1
+                return ("comprehension", e, var, it, cond)
+            cur.append(e)
+            if self.accept(","):
+                commas = True
+                if self.at("]"): break
+                continue
+            if self.at(";"):
+                nsemi = 0
+                while self.accept(";"): nsemi += 1
+                rows.append(cur); cur = []
+                if nsemi >= 2: rows.append("dim2")
+                if self.at("]"): break
+                continue
+            if self.at("]"): break
+        if cur: rows.append(cur)
+        self.expect("]")
+        self.no_nl -= 1
+        if commas: return ("vect", rows[0])
+        if "dim2" in rows: return ("mat", [r for r in rows if r != "dim2"], True)
+        if len(rows) == 1 and len(rows[0]) == 1: return ("vect", rows[0])
+        return ("mat", rows, False)
+
+
+def parse(src):
+    p = Parser(tokenize(src))
+    b = p.block(())
+    return b
+
+
+# ------------------------------------------------------------------------------------------------ evaluator
+class Method:
+    def __init__(self, params, body, env):
+        self.params, self.body, self.env = params, body, env
+
+
+class GenericFunction:
+    def __init__(self, name):
+        self.name, self.methods = name, []
+
+    def __repr__(self):
+        return "<julia function %s, %d methods>" % (self.name, len(self.methods))
+
+
+def _is_int(v): return isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_))
+def _is_real(v): return isinstance(v, (int, float, np.integer, np.floating)) and not isinstance(v, (bool, np.bool_))
+
+
+def type_match(v, ty):
+    """score >= 0 when value v is an instance of Julia type ty, else -1"""
+    if ty is None: return 0
+    n, ps = ty.name, ty.params
+    if n == "Any": return 0
+    if n in ("Int", "Int64", "Integer"): return 3 if _is_int(v) else -1
+    if n == "Bool": return 3 if isinstance(v, (bool, np.bool_)) else -1
+    if n in ("Float64", "AbstractFloat"): return 3 if isinstance(v, (float, np.floating)) else -1
+    if n == "Real": return 1 if _is_real(v) else -1
+    if n == "Number": return 1 if _is_real(v) or isinstance(v, (complex, np.complexfloating)) else -1
+    if n in ("ComplexF64", "Complex"): return 3 if isinstance(v, (complex, np.complexfloating)) else -1
+    if n in ("String", "AbstractString"): return 3 if isinstance(v, str) else -1
+    if n in ("Vector", "AbstractVector", "Matrix", "AbstractMatrix", "Array", "AbstractArray", "VecOrMat"):
+        if isinstance(v, list):                          # a Vector of non-numbers (e.g. Vector{Matrix{ComplexF64}}) is a Python list here
+            if n not in ("Vector", "AbstractVector", "Array", "AbstractArray"): return -1
+            return 2 if not ps or all(type_match(x, ps[0]) >= 0 for x in v) else -1
+        if not isinstance(v, np.ndarray): return -1
+        if n in ("Vector", "AbstractVector") and v.ndim != 1: return -1
+        if n in ("Matrix", "AbstractMatrix") and v.ndim != 2: return -1
+        if ps:
+            el = ps[0].name
+            ok = {"ComplexF64": np.iscomplexobj(v), "Float64": v.dtype.kind == "f", "Int": v.dtype.kind == "i", "Int64": v.dtype.kind == "i",
+                  "Real": v.dtype.kind in "fi"}.get(el, True)
+            if n.startswith("Abstract") and el in ("T", "Number"): ok = True
+            return 3 if ok else -1
+        return 2
+    if n == "Function": return 2 if isinstance(v, (GenericFunction, Method)) or callable(v) else -1
+    if n == "Tuple": return 2 if isinstance(v, tuple) else -1
+    if n == "Dict": return 2 if isinstance(v, dict) else -1
+    return 0
+
+
+class Env:
+    def __init__(self, parent=None):
+        self.vars, self.parent = {}, parent
+
+    def lookup(self, name):
+        e = self
+        while e is not None:
+            if name in e.vars: return e.vars[name]
+            e = e.parent
+        raise JuliaError("UndefVarError: %s not defined" % name)
+
+    def has(self, name):
+        e = self
+        while e is not None:
+            if name in e.vars: return True
+            e = e.parent
+        return False
+
+    def set(self, name, v):
+        self.vars[name] = v
+
+
+def _adjoint(a):
+    if isinstance(a, Hermitian): return a
+    if isinstance(a, np.ndarray):
+        if a.ndim == 1: return np.conj(a).reshape(1, -1)
+        return np.conj(a).T
+    return np.conj(a) if isinstance(a, (complex, np.complexfloating)) else a
+
+
+def _mul(a, b):
+    if isinstance(a, Hermitian): a = a.a
+    if isinstance(b, Hermitian): b = b.a
+    if isinstance(a, np.ndarray) and isinstance(b, np.ndarray):
+        if a.shape == (2, 2) and b.shape == (2, 2):
+            # Julia multiplies 2x2 matrices with explicit formulas (LinearAlgebra matmul2x2!), not through BLAS: plain products and
+            # sums in this order, so that e.g. U * rho * U' of a diagonal U stays exactly Hermitian (the reference's tests ask
+            # ishermitian of such products)
+            x, y = a.tolist(), b.tolist()
+            out = [[x[0][0] * y[0][0] + x[0][1] * y[1][0], x[0][0] * y[0][1] + x[0][1] * y[1][1]],
+                   [x[1][0] * y[0][0] + x[1][1] * y[1][0], x[1][0] * y[0][1] + x[1][1] * y[1][1]]]
+            return np.array(out, dtype=np.result_type(a, b))
+        if a.ndim == 1 and b.ndim == 2 and b.shape[0] == 1: return a.reshape(-1, 1) @ b          # s * s'
+        if a.ndim == 2 and a.shape[0] == 1 and b.ndim == 1:                                      # s' * t : a scalar
+            return (a @ b)[0]
+        if a.ndim == 1 and b.ndim == 1: raise JuliaError("MethodError: Vector * Vector")
+        return a @ b
+    return a * b
+
+
+def _pow(a, b):
+    if isinstance(a, Hermitian):
+        w, v = np.linalg.eigh(a.a)
+        if np.all(w >= 0) or float(b).is_integer(): d = w.astype(np.complex128 if np.any(w < 0) else w.dtype) ** b
+        else: d = w.astype(np.complex128) ** b
+        return (v * d) @ np.conj(v).T
+    if isinstance(a, np.ndarray) and a.ndim == 2:
+        if _is_int(b): return np.linalg.matrix_power(a, int(b))
+        w, v = np.linalg.eig(a); return (v * (w.astype(np.complex128) ** b)) @ np.linalg.inv(v)
+    if _is_int(a) and _is_int(b):
+        if b < 0: raise JuliaError("DomainError: negative integer power")
+        return int(a) ** int(b)
+    if _is_real(a) and _is_real(b) and a < 0 and not float(b).is_integer(): raise JuliaError("DomainError: %r ^ %r" % (a, b))
+    return a ** b
+
+
+def _div(a, b):
+    if _is_int(a) and _is_int(b): return int(a) / int(b)
+    return a / b
+
+
+def _isapprox(a, b, atol=0.0, rtol=None):
+    a_, b_ = np.asarray(a), np.asarray(b)
+    if rtol is None: rtol = 0.0 if atol > 0 else math.sqrt(np.finfo(np.float64).eps)
+    if a_.ndim == 0 and b_.ndim == 0:
+        return bool(abs(a_ - b_) <= max(atol, rtol * max(abs(a_), abs(b_))))
+    if a_.shape != b_.shape: return False
+    return bool(np.linalg.norm((a_ - b_).ravel()) <= max(atol, rtol * max(np.linalg.norm(a_.ravel()), np.linalg.norm(b_.ravel()))))
+
+
+def _cmp(op, a, b):
+    if op in ("==", "==="):
+        if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+            return isinstance(a, np.ndarray) and isinstance(b, np.ndarray) and a.shape == b.shape and bool(np.all(a == b))
+        return a == b
+    if op in ("!=", "≠", "!=="): return not _cmp("==", a, b)
+    if op == "<": return a < b
+    if op in ("<=", "≤"): return a <= b
+    if op == ">": return a > b
+    if op in (">=", "≥"): return a >= b
+    if op == "≈": return _isapprox(a, b)
+    if op == "in": return a in (b.values() if isinstance(b, JRange) else b)
+    if op.startswith("."):
+        a_, b_ = (np.asarray(x.values()) if isinstance(x, JRange) else x for x in (a, b))
+        if op == ".≈":
+            return np.vectorize(lambda x, y: _isapprox(x, y))(a_, b_)
+        return {".==": np.equal, ".!=": np.not_equal, ".<": np.less, ".<=": np.less_equal, ".>": np.greater, ".>=": np.greater_equal}[op](a_, b_)
+    raise JuliaError("unsupported comparison " + op)
+
+
+class TestLog:
+    def __init__(self): self.passed, self.failed, self.stack = 0, [], []
+
+
+class Interp:
+    def __init__(self):
+        self.globals = Env()
+        self.modules = {}
+        self.tests = TestLog()
+        self.out = []
+        self._install_builtins()
+
+    # ---- builtins -------------------------------------------------------------------------------------------------
+    def _install_builtins(self):
+        G = self.globals.vars
+        for n in ("Int", "Int64", "Float64", "ComplexF64", "Bool", "Real", "Number", "Vector", "Matrix", "Array", "Dict", "String", "Any", "Tuple",
+                  "Integer", "AbstractFloat", "AbstractMatrix", "AbstractVector", "AbstractArray", "Function", "Complex", "Nothing",
+                  "ErrorException", "AssertionError", "BoundsError", "MethodError", "DimensionMismatch", "ArgumentError", "DomainError", "Exception"):
+            G[n] = JType(n)
+        G.update({"π": math.pi, "pi": math.pi, "ℯ": math.e, "im": 1j, "Inf": math.inf, "NaN": math.nan, "nothing": None})
+
+        def arr(x):
+            return np.asarray(x.values()) if isinstance(x, JRange) else x
+
+        def zeros_(*a):
+            if isinstance(a[0], JType): return np.zeros(tuple(int(x) for x in a[1:]), dtype=self._dtype(a[0]))
+            return np.zeros(tuple(int(x) for x in a), dtype=np.float64)
+
+        def ones_(*a):
+            if isinstance(a[0], JType): return np.ones(tuple(int(x) for x in a[1:]), dtype=self._dtype(a[0]))
+            return np.ones(tuple(int(x) for x in a), dtype=np.float64)
+
+        def round_(*a, digits=None):
+            if isinstance(a[0], JType):
+                return int(np.rint(a[1]))
+            if digits is not None: return float(np.round(a[0], int(digits)))
+            return float(np.rint(a[0])) if not isinstance(a[0], np.ndarray) else np.rint(a[0])
+
+        def size_(a, d=None):
+            a = a.a if isinstance(a, Hermitian) else a
+            return tuple(int(x) for x in a.shape) if d is None else int(a.shape[int(d) - 1])
+
+        def mul_(out, a, b):
+            out[...] = _mul(a, b); return out
+
+        def copyto_(dst, src):
+            dst[...] = src; return dst
+
+        def eigen_(a):
+            m = a.a if isinstance(a, Hermitian) else a
+            w, v = np.linalg.eigh(m) if isinstance(a, Hermitian) else np.linalg.eig(m)
+            return (w, v)
+
+        def eigvals_(a):
+            m = a.a if isinstance(a, Hermitian) else a
+            return np.linalg.eigvalsh(m) if isinstance(a, Hermitian) else np.linalg.eigvals(m)
+
+        def error_(*msg):
+            raise JuliaError("".join(str(m) for m in msg))
+
+        def sum_(x, *rest):
+            if isinstance(x, (GenericFunction, Method)) or callable(x) and rest:
+                return sum(self.call(x, [v]) for v in self._iter(rest[0]))
+            x = arr(x)
+            if isinstance(x, np.ndarray):
+                if x.dtype == bool: return int(x.sum())
+                s = x.sum(); return s.item() if hasattr(s, "item") else s
+            return sum(self._iter(x))
+
+        def maxmin(fn, npfn):
+            def f(*a):
+                if len(a) == 1:
+                    v = npfn(arr(a[0])); return v.item() if hasattr(v, "item") else v
+                return fn(a)
+            return f
+
+        def string_(*a, base=10, pad=0):
+            if len(a) == 1 and _is_int(a[0]) and base != 10:
+                return np.base_repr(int(a[0]), int(base)).rjust(int(pad), "0")
+            return "".join(self._show(x) for x in a)
+
+        def println_(*a):
+            self.out.append("".join(self._show(x) for x in a))
+
+        def reshape_(a, *dims):
+            if len(dims) == 1 and isinstance(dims[0], tuple): dims = dims[0]
+            return np.reshape(np.asarray(a), tuple(int(d) for d in dims), order="F")
+
+        def norm_(a, p=2):
+            return float(np.linalg.norm(np.asarray(a).ravel(), p))
+
+        G.update({
+            "kron": lambda a, b: np.kron(a, b),
+            "Diagonal": lambda v: np.diag(np.asarray(v)), "diagm": lambda v: np.diag(np.asarray(v)), "diag": lambda a: np.diag(a).copy(),
+            "zeros": zeros_, "ones": ones_, "similar": lambda a: np.empty_like(a), "copy": lambda a: a.copy() if isinstance(a, np.ndarray) else a,
+            "deepcopy": lambda a: a.copy() if isinstance(a, np.ndarray) else a,
+            "mul!": mul_, "copyto!": copyto_, "length": lambda a: len(a) if not isinstance(a, np.ndarray) else int(a.size), "size": size_,
+            "log2": lambda x: self._math(np.log2, x), "log": lambda x: self._math(np.log, x), "exp": lambda x: self._math(np.exp, x),
+            "cos": lambda x: math.cos(x), "sin": lambda x: math.sin(x), "tan": lambda x: math.tan(x),
+            "sqrt": lambda x: self._sqrt(x), "abs": lambda x: abs(x), "abs2": lambda x: (x.real * x.real + x.imag * x.imag) if isinstance(x, (complex, np.complexfloating)) else x * x,
+            "real": lambda x: np.real(x).copy() if isinstance(x, np.ndarray) else (x.real if isinstance(x, (complex, np.complexfloating)) else x),
+            "imag": lambda x: np.imag(x).copy() if isinstance(x, np.ndarray) else (x.imag if isinstance(x, (complex, np.complexfloating)) else 0),
+            "conj": lambda x: np.conj(x), "adjoint": _adjoint, "transpose": lambda a: a.T, "tr": lambda a: self._scalar(np.trace(a.a if isinstance(a, Hermitian) else a)),
+            "eigen": eigen_, "eigvals": eigvals_, "Hermitian": Hermitian, "Symmetric": Hermitian, "ishermitian": lambda a: bool(np.array_equal(a, np.conj(a).T)),
+            "isposdef": lambda a: bool(np.all(np.linalg.eigvalsh((a + np.conj(a).T) / 2) > 0)),
+            "max": maxmin(max, np.max), "min": maxmin(min, np.min), "maximum": maxmin(max, np.max), "minimum": maxmin(min, np.min),
+            "sum": sum_, "prod": lambda x: self._scalar(np.prod(arr(x))), "all": lambda x, *r: bool(np.all(arr(x))) if not r else all(self.call(x, [v]) for v in self._iter(r[0])),
+            "any": lambda x, *r: bool(np.any(arr(x))) if not r else any(self.call(x, [v]) for v in self._iter(r[0])),
+            "haskey": lambda d, k: k in d, "error": error_, "round": round_, "floor": lambda *a: int(math.floor(a[-1])) if isinstance(a[0], JType) else float(math.floor(a[0])),
+            "ceil": lambda *a: int(math.ceil(a[-1])) if isinstance(a[0], JType) else float(math.ceil(a[0])),
+            "div": lambda a, b: int(a) // int(b), "mod": lambda a, b: a % b, "rem": lambda a, b: int(math.fmod(a, b)) if _is_int(a) else math.fmod(a, b),
+            "isapprox": lambda a, b, atol=0.0, rtol=None: _isapprox(a, b, atol, rtol), "isnan": lambda x: bool(np.isnan(x)), "isinf": lambda x: bool(np.isinf(x)),
+            "isfinite": lambda x: bool(np.isfinite(x)), "isreal": lambda x: bool(np.isreal(x)), "iszero": lambda x: bool(np.all(np.asarray(x) == 0)),
+            "string": string_, "lpad": lambda s, n, c=" ": str(s).rjust(int(n), c), "println": println_, "print": println_,
+            "reshape": reshape_, "vec": lambda a: np.asarray(a).ravel(order="F"), "norm": norm_, "opnorm": lambda a: float(np.linalg.norm(a, 2)),
+            "rank": lambda a: int(np.linalg.matrix_rank(a)), "det": lambda a: self._scalar(np.linalg.det(a)), "inv": lambda a: np.linalg.inv(a),
+            "I": "UniformScaling", "push!": lambda a, v: (a.append(v), a)[1], "collect": lambda x: np.asarray(list(self._iter(x))),
+            "typeof": lambda x: self._typeof(x), "isa": lambda x, t: type_match(x, t) >= 0, "eltype": lambda a: JType("ComplexF64" if np.iscomplexobj(a) else "Float64"),
+            "float": lambda x: float(x) if _is_real(x) else x, "complex": lambda *a: complex(*a), "Complex": lambda *a: complex(*a),
+            "first": lambda x: next(iter(self._iter(x))), "last": lambda x: list(self._iter(x))[-1], "ndims": lambda a: int(np.ndim(a)),
+            "sqrtm": lambda a: self._sqrt(a), "exp2": lambda x: 2.0 ** x, "sign": lambda x: (x > 0) - (x < 0), "hypot": math.hypot, "atan": math.atan2,
+            "identity": lambda x: x, "isempty": lambda x: len(x) == 0, "range": lambda a, b=None, length=None, stop=None: np.linspace(a, b if b is not None else stop, int(length)),
+            "axes": lambda a, d: JRange(1, int(a.shape[int(d) - 1])), "eachindex": lambda a: JRange(1, int(np.size(a))), "enumerate": lambda x: [(i + 1, v) for i, v in enumerate(self._iter(x))],
+            "zip": lambda *xs: list(zip(*[list(self._iter(x)) for x in xs])), "keys": lambda d: list(d.keys()), "values": lambda d: list(d.values()),
+            "dot": lambda a, b: self._scalar(np.vdot(np.asarray(a), np.asarray(b))),
+            "rand": self._no_random, "randn": self._no_random,
+        })
+
+    def _no_random(self, *a, **k):
+        raise JuliaError("rand/randn are not available in the subset interpreter (fixtures must be deterministic)")
+
+    def _dtype(self, ty):
+        return {"ComplexF64": np.complex128, "Float64": np.float64, "Int": np.int64, "Int64": np.int64, "Bool": bool}.get(ty.name, np.float64)
+
+    def _typeof(self, x):
+        if isinstance(x, np.ndarray):
+            el = JType("ComplexF64" if np.iscomplexobj(x) else ("Int64" if x.dtype.kind == "i" else ("Bool" if x.dtype == bool else "Float64")))
+            return JType("Vector" if x.ndim == 1 else "Matrix", [el])
+        if isinstance(x, bool): return JType("Bool")
+        if _is_int(x): return JType("Int64")
+        if isinstance(x, float): return JType("Float64")
+        if isinstance(x, complex): return JType("ComplexF64")
+        return JType(type(x).__name__)
+
+    def _scalar(self, v):
+        return v.item() if hasattr(v, "item") else v
+
+    def _math(self, f, x):
+        if isinstance(x, np.ndarray): return f(x)
+        if isinstance(x, (complex, np.complexfloating)): return complex(f(complex(x)))
+        if _is_real(x) and x < 0 and f in (np.log2, np.log): raise JuliaError("DomainError: log of a negative real")
+        with np.errstate(divide="ignore"):
+            return float(f(float(x)))
+
+    def _sqrt(self, x):
+        if isinstance(x, Hermitian) or (isinstance(x, np.ndarray) and x.ndim == 2):
+            m = x.a if isinstance(x, Hermitian) else x
+            if np.allclose(m, np.conj(m).T):
+                w, v = np.linalg.eigh(m); return (v * np.sqrt(w.astype(np.complex128) if np.any(w < 0) else w)) @ np.conj(v).T
+            w, v = np.linalg.eig(m); return (v * np.sqrt(w.astype(np.complex128))) @ np.linalg.inv(v)
+        if isinstance(x, (complex, np.complexfloating)): return complex(np.sqrt(complex(x)))
+        if x < 0: raise JuliaError("DomainError: sqrt of a negative real")
+        return math.sqrt(x)
+
+    def _show(self, x):
+        if isinstance(x, complex): return "%r %s %rim" % (x.real, "-" if x.imag < 0 or (x.imag == 0 and math.copysign(1, x.imag) < 0) else "+", abs(x.imag))
+        return str(x)
+
+    def _iter(self, x):
+        if isinstance(x, JRange): return x.values()
+        if isinstance(x, np.ndarray): return [self._scalar(v) for v in x.ravel(order="F")]
+        if isinstance(x, dict): return list(x.items())
+        return x
+
+    # ---- running source --------------------------------------------------------------------------------------------
+    def run(self, src, env=None):
+        return self.exec_block(parse(src), env or self.globals)
+
+    def load_file(self, path):
+        with open(path, encoding="utf-8") as f:
+            return self.run(f.read())
+
+    def module(self, name):
+        return self.modules[name]
+
+    def using(self, name):
+        """bring the names a module defines into the global scope (the subset has no export lists: everything comes)"""
+        for k, v in self.modules[name].vars.items():
+            self.globals.vars[k] = v
+
+    # ---- statements -----------------------------------------------------------------------------------------------
+    def exec_block(self, node, env):
+        val = None
+        for st in node[1]:
+            val = self.exec(st, env)
+        return val
+
+    def exec(self, st, env):
+        k = st[0]
+        if k == "expr": return self.eval(st[1], env)
+        if k == "nop": return None
+        if k == "assign": return self.assign(st[1], st[2], st[3], env)
+        if k == "function":
+            return self.define(st, env)
+        if k == "return": raise ReturnEx(self.eval(st[1], env) if st[1] is not None else None)
+        if k == "break": raise BreakEx()
+        if k == "continue": raise ContinueEx()
+        if k == "for":
+            self.run_for(st[1], 0, st[2], env); return None
+        if k == "while":
+            try:
+                while self.eval(st[1], env):
+                    try: self.exec_block(st[2], Env(env))
+                    except ContinueEx: pass
+            except BreakEx: pass
+            return None
+        if k == "module":
+            menv = Env(self.globals)
+            menv.is_module = True
+            self.modules[st[1]] = menv
+            self.exec_block(st[2], menv)
+            return None
+        if k == "assert":
+            if not self.eval(st[1], env): raise JuliaError("AssertionError: " + (st[2] or "assertion failed"))
+            return None
+        if k == "testset":
+            self.tests.stack.append(st[1] or "")
+            try: self.exec_block(st[2], Env(env))
+            except JuliaError as ex:                     # as Test does: an error aborts this testset, is recorded, and the run goes on
+                self.tests.failed.append(" / ".join(self.tests.stack) + ": errored: " + str(ex))
+            finally: self.tests.stack.pop()
+            return None
+        if k == "test":
+            where = " / ".join(self.tests.stack) + " (line %d)" % st[4]
+            try:
+                e = st[2]
+                kw = {a: self.eval(b, env) for a, b in st[3].items()}
+                if kw and e[0] == "cmp" and e[1] == ["≈"]:
+                    ok = _isapprox(self.eval(e[2][0], env), self.eval(e[2][1], env), **kw)
+                else:
+                    ok = self.eval(e, env)
+                if st[1] == "test_nowarn": ok = True
+            except (JuliaError, ReturnEx) as ex:
+                ok = False; where += " raised " + str(ex)
+            if ok is True or (isinstance(ok, np.bool_) and bool(ok)): self.tests.passed += 1
+            else: self.tests.failed.append(where)
+            return None
+        if k == "test_throws":
+            where = " / ".join(self.tests.stack) + " (line %d)" % st[3]
+            try:
+                self.eval(st[2], env)
+                self.tests.failed.append(where + ": nothing was thrown")
+            except JuliaError:
+                self.tests.passed += 1
+            except (IndexError, ValueError, TypeError):
+                self.tests.passed += 1
+            return None
+        raise JuliaError("jl_subset: cannot execute " + k)
+
+    def run_for(self, iters, idx, body, env):
+        var, it = iters[idx]
+        try:
+            for v in self._iter(self.eval(it, env)):
+                inner = Env(env)
+                self.bind(var, v, inner)
+                if idx + 1 < len(iters):
+                    self.run_for(iters, idx + 1, body, inner)
+                else:
+                    try: self.exec_block(body, inner)
+                    except ContinueEx: pass
+        except BreakEx:
+            pass
+
+    def bind(self, target, v, env):
+        if target[0] == "id": env.set(target[1], v)
+        elif target[0] in ("tuple", "paren"):
+            items = target[1] if target[0] == "tuple" else [target[1]]
+            vs = list(self._iter(v))
+            for t_, x in zip(items, vs): self.bind(t_, x, env)
+        else: raise JuliaError("jl_subset: cannot bind to " + target[0])
+
+    def define(self, st, env):
+        _, name, params, body = st
+        # a method is added to the generic function of the scope it is defined in (module or global); a nested `function`
+        # inside a function body makes a local closure
+        if name is None: raise JuliaError("jl_subset: anonymous function statement")
+        gf = env.vars.get(name)
+        if not isinstance(gf, GenericFunction):
+            gf = GenericFunction(name); env.set(name, gf)
+        ps = [(p[0], p[1], p[2]) for p in params]
+        sig = [repr(p[1]) for p in ps]
+        gf.methods = [m for m in gf.methods if [repr(p[1]) for p in m.params] != sig]
+        gf.methods.append(Method(ps, body, env))
+        return gf
+
+    def assign(self, op, target, rhs_node, env):
+        rhs = self.eval(rhs_node, env) if rhs_node[0] != "assignx" else self.assign("=", rhs_node[1], rhs_node[2], env)
+        if op != "=":
+            cur = self.eval(target, env)
+            b = op[0]
+            rhs = {"+": lambda: self.binop("+", cur, rhs), "-": lambda: self.binop("-", cur, rhs), "*": lambda: self.binop("*", cur, rhs),
+                   "/": lambda: self.binop("/", cur, rhs)}[b]()
+        k = target[0]
+        if k == "id":
+            # Julia's rule for functions (hard scope): an assignment updates the binding of the enclosing FUNCTION's locals if the
+            # name exists there (loop bodies are scopes of their own), otherwise it makes a new local — a module's globals are
+            # never rebound from inside a function.  At module / top level the name is (re)defined in that scope.
+            name, e_ = target[1], env
+            while True:
+                if name in e_.vars:
+                    e_.vars[name] = rhs; break
+                if getattr(e_, "is_function_root", False) or getattr(e_, "is_module", False) or e_.parent is None:
+                    env.set(name, rhs); break
+                e_ = e_.parent
+        elif k == "typed":
+            return self.assign("=", target[1], ("lit", rhs), env)
+        elif k == "index":
+            arr = self.eval(target[1], env)
+            if isinstance(arr, dict):
+                arr[self.eval(target[2][0], env)] = rhs
+            else:
+                arr[self.index_key(arr, target[2], env)] = rhs
+        elif k in ("tuple", "paren"):
+            self.bind(target, rhs, env)
+        elif k == "field":
+            raise JuliaError("jl_subset: field assignment is not supported")
+        else:
+            raise JuliaError("jl_subset: cannot assign to " + k)
+        return rhs
+
+    # ---- expressions ----------------------------------------------------------------------------------------------
+    def index_key(self, arr, idx_nodes, env):
+        key = []
+        nd = len(idx_nodes)
+        for d, node in enumerate(idx_nodes):
+            dim_len = int(arr.shape[d]) if nd > 1 else int(arr.size)
+            self._end_stack.append(dim_len)
+            try: v = self.eval(node, env)
+            finally: self._end_stack.pop()
+            if isinstance(v, JRange):
+                vals = v.values(); key.append(np.asarray([int(x) - 1 for x in vals], dtype=np.int64))
+            elif v == "colon": key.append(slice(None))
+            elif isinstance(v, np.ndarray):
+                key.append(v if v.dtype == bool else v.astype(np.int64) - 1)
+            else:
+                if not _is_int(v): raise JuliaError("ArgumentError: invalid index %r" % (v,))
+                if v < 1 or v > dim_len: raise JuliaError("BoundsError: index %d of %d" % (v, dim_len))
+                key.append(int(v) - 1)
+        if nd == 1:
+            if isinstance(arr, np.ndarray) and arr.ndim > 1:            # linear indexing into a matrix: column-major
+                if isinstance(key[0], slice): key[0] = np.arange(arr.size)
+                return tuple(np.unravel_index(key[0], arr.shape, order="F"))
+            return key[0]
+        if sum(isinstance(kk, np.ndarray) for kk in key) > 1:
+            return np.ix_(*[kk if isinstance(kk, np.ndarray) else (np.arange(arr.shape[i]) if isinstance(kk, slice) else np.asarray([kk])) for i, kk in enumerate(key)])
+        return tuple(key)
+
+    _end_stack = []
+
+    def eval(self, e, env):
+        k = e[0]
+        if k == "num": return e[1]
+        if k == "lit": return e[1]
+        if k == "str": return e[1]
+        if k == "id":
+            return env.lookup(e[1])
+        if k == "paren": return self.eval(e[1], env)
+        if k == "bin": return self.binop(e[1], self.eval(e[2], env), self.eval(e[3], env))
+        if k == "un":
+            v = self.eval(e[2], env)
+            if e[1] == "-": return -v
+            if e[1] == "+": return v
+            if e[1] == "!": return not v
+            if e[1] == "√": return self._sqrt(v)
+        if k == "&&":
+            a = self.eval(e[1], env)
+            return self.eval(e[2], env) if a else a
+        if k == "||":
+            a = self.eval(e[1], env)
+            return a if a else self.eval(e[2], env)
+        if k == "cmp":
+            vals = [self.eval(x, env) for x in e[2]]
+            res = True
+            for i, op in enumerate(e[1]):
+                r = _cmp(op, vals[i], vals[i + 1])
+                if isinstance(r, np.ndarray): return r
+                res = res and bool(r)
+            return res
+        if k == "if":
+            for cond, body in e[1]:
+                if self.eval(cond, env): return self.exec_block(body, env)
+            return self.exec_block(e[2], env) if e[2] is not None else None
+        if k == "call": return self.eval_call(e, env)
+        if k == "bcall":
+            f = self.eval(e[1], env)
+            args = [self.eval(a, env) for a in e[2]]
+            kw = {a: self.eval(b, env) for a, b in e[3].items()}
+            return self.broadcast(f, args, kw)
+        if k == "index":
+            a = self.eval(e[1], env)
+            if isinstance(a, dict):
+                key = self.eval(e[2][0], env)
+                if key not in a: raise JuliaError("KeyError: %r" % (key,))
+                return a[key]
+            if isinstance(a, (tuple, list)):
+                self._end_stack.append(len(a))
+                try: i = self.eval(e[2][0], env)
+                finally: self._end_stack.pop()
+                if isinstance(i, JRange): return tuple(a[int(j) - 1] for j in i.values())
+                return a[int(i) - 1]
+            if isinstance(a, JRange):
+                return a.values()[int(self.eval(e[2][0], env)) - 1]
+            if isinstance(a, Hermitian): a = a.a
+            if isinstance(a, JType):                        # T[...] typed array literal
+                return np.asarray([self.eval(x, env) for x in e[2]], dtype=self._dtype(a))
+            v = a[self.index_key(a, e[2], env)]
+            return v.copy() if isinstance(v, np.ndarray) else self._scalar(v)
+        if k == "endidx":
+            if not self._end_stack: raise JuliaError("jl_subset: `end` outside an index")
+            return self._end_stack[-1]
+        if k == "colon": return "colon"
+        if k == "range":
+            a, b = self.eval(e[1], env), self.eval(e[2], env)
+            return JRange(a, b, self.eval(e[3], env) if e[3] is not None else 1)
+        if k == "adjoint": return _adjoint(self.eval(e[1], env))
+        if k == "tuple": return tuple(self.eval(x, env) for x in e[1])
+        if k == "vect":
+            vals = [self.eval(x, env) for x in e[1]]
+            if vals and all(isinstance(v, (bool, int, float, complex, np.number)) for v in vals): return np.asarray(vals)
+            return list(vals)
+        if k == "mat":
+            rows = [[self.eval(x, env) for x in r] for r in e[1]]
+            if any(isinstance(x, np.ndarray) for r in rows for x in r):
+                return np.block([[np.atleast_2d(x) if np.ndim(x) == 2 else np.asarray(x).reshape(-1, 1) if np.ndim(x) == 1 else np.asarray([[x]]) for x in r] for r in rows])
+            m = np.asarray(rows)
+            return m
+        if k == "comprehension":
+            out = []
+            for v in self._iter(self.eval(e[3], env)):
+                inner = Env(env); self.bind(e[2], v, inner)
+                if e[4] is None or self.eval(e[4], inner): out.append(self.eval(e[1], inner))
+            if out and all(not isinstance(v, (np.ndarray, tuple, str)) and v is not None for v in out): return np.asarray(out)
+            return out
+        if k == "typedarray":
+            ty = self.eval(e[1], env)
+            return np.asarray(self.eval(e[2], env), dtype=self._dtype(ty))
+        if k == "curly":
+            base = self.eval(e[1], env)
+            return JType(base.name, e[2]) if isinstance(base, JType) else base
+        if k == "typed": return self.eval(e[1], env)
+        if k == "field":
+            base = e[1]
+            if base[0] == "id" and base[1] in self.modules: return self.modules[base[1]].lookup(e[2])
+            if base[0] == "field":                          # Quromorphic.QSim.f
+                if base[2] in self.modules: return self.modules[base[2]].lookup(e[2])
+            v = self.eval(base, env)
+            if isinstance(v, tuple) and e[2] in ("values", "vectors"): return v[0 if e[2] == "values" else 1]
+            raise JuliaError("jl_subset: no field %s" % e[2])
+        if k == "lambda":
+            return Method(e[1], e[2], env)
+        if k == "blockexpr": return self.exec_block(e[1], env)
+        if k == "fundef": return self.define(e[1], env)
+        if k == "splat": raise JuliaError("jl_subset: splat outside a call")
+        raise JuliaError("jl_subset: cannot evaluate " + k)
+
+    def binop(self, op, a, b):
+        if isinstance(a, JRange) and op in ("+", "-", "*", ".+", ".-", ".*", "./"): a = np.asarray(a.values())
+        if isinstance(b, JRange) and op in ("+", "-", "*", ".+", ".-", ".*", "./"): b = np.asarray(b.values())
+        if a == "UniformScaling" if isinstance(a, str) else False: a = np.eye(b.shape[0]) if isinstance(b, np.ndarray) else 1
+        if b == "UniformScaling" if isinstance(b, str) else False: b = np.eye(a.shape[0]) if isinstance(a, np.ndarray) else 1
+        if op == "+":
+            if isinstance(a, Hermitian): a = a.a
+            if isinstance(b, Hermitian): b = b.a
+            if isinstance(a, np.ndarray) != isinstance(b, np.ndarray): raise JuliaError("MethodError: array + scalar needs a broadcast dot")
+            return a + b
+        if op == "-":
+            if isinstance(a, Hermitian): a = a.a
+            if isinstance(b, Hermitian): b = b.a
+            if isinstance(a, np.ndarray) != isinstance(b, np.ndarray): raise JuliaError("MethodError: array - scalar needs a broadcast dot")
+            return a - b
+        if op == "*":
+            if isinstance(a, str) and isinstance(b, str): return a + b
+            return _mul(a, b)
+        if op == "/":
+            if isinstance(b, np.ndarray):
+                if isinstance(a, np.ndarray): return a @ np.linalg.inv(b)
+                raise JuliaError("MethodError: scalar / array")
+            return _div(a, b)
+        if op == "\\": return np.linalg.solve(a, b)
+        if op == "^": return _pow(a, b)
+        if op == "%": return int(math.fmod(a, b)) if _is_int(a) and _is_int(b) else math.fmod(a, b)
+        if op == "÷": return int(a) // int(b) if (a >= 0) == (b > 0) else -(abs(int(a)) // abs(int(b)))
+        if op == "&": return (a and b) if isinstance(a, bool) and isinstance(b, bool) else int(a) & int(b)
+        if op == "|": return (a or b) if isinstance(a, bool) and isinstance(b, bool) else int(a) | int(b)
+        if op == "<<": return int(a) << int(b)
+        if op == ">>": return int(a) >> int(b)
+        if op in (".+", ".-", ".*", "./", ".^"):
+            a_ = a.a if isinstance(a, Hermitian) else a; b_ = b.a if isinstance(b, Hermitian) else b
+            if op == ".+": return a_ + b_
+            if op == ".-": return a_ - b_
+            if op == ".*": return a_ * b_
+            if op == "./": return a_ / b_
+            return np.power(a_, b_)
+        raise JuliaError("jl_subset: operator %s" % op)
+
+    def broadcast(self, f, args, kw):
+        args = [np.asarray(a.values()) if isinstance(a, JRange) else (a.a if isinstance(a, Hermitian) else a) for a in args]
+        arrs = [a for a in args if isinstance(a, np.ndarray)]
+        if not arrs: return self.call(f, args, kw)
+        shape = np.broadcast(*arrs).shape
+        its = [np.broadcast_to(a, shape) if isinstance(a, np.ndarray) else None for a in args]
+        out = np.empty(shape, dtype=object)
+        for idx in np.ndindex(*shape):
+            out[idx] = self.call(f, [self._scalar(its[i][idx]) if its[i] is not None else args[i] for i in range(len(args))], kw)
+        flat = list(out.ravel())
+        if all(isinstance(v, (bool, np.bool_)) for v in flat): return out.astype(bool)
+        if all(_is_int(v) for v in flat): return out.astype(np.int64)
+        if all(_is_real(v) for v in flat): return out.astype(np.float64)
+        if all(isinstance(v, (int, float, complex, np.number)) for v in flat): return out.astype(np.complex128)
+        return out
+
+    def eval_call(self, e, env):
+        fnode = e[1]
+        pos = []
+        for a in e[2]:
+            if a[0] == "splat": pos.extend(self._iter(self.eval(a[1], env)))
+            elif a[0] == "gen":
+                vals = []
+                for v in self._iter(self.eval(a[3], env)):
+                    inner = Env(env); self.bind(a[2], v, inner)
+                    if a[4] is None or self.eval(a[4], inner): vals.append(self.eval(a[1], inner))
+                pos.append(vals)
+            else: pos.append(self.eval(a, env))
+        kw = {k_: self.eval(v, env) for k_, v in e[3].items()}
+        f = self.eval(fnode, env)
+        return self.call(f, pos, kw)
+
+    def call(self, f, pos, kw=None):
+        kw = kw or {}
+        if isinstance(f, GenericFunction):
+            best, best_score = None, -1
+            for m in f.methods:
+                req = [p for p in m.params if p[2] is None]
+                if len(pos) < len(req) or len(pos) > len(m.params): continue
+                score, ok = 0, True
+                for p, v in zip(m.params, pos):
+                    s = type_match(v, p[1])
+                    if s < 0: ok = False; break
+                    score += s
+                if ok and score > best_score: best, best_score = m, score
+            if best is None:
+                raise JuliaError("MethodError: no method matching %s(%s)" % (f.name, ", ".join(repr(self._typeof(v)) for v in pos)))
+            return self.invoke(best, pos, kw)
+        if isinstance(f, Method): return self.invoke(f, pos, kw)
+        if isinstance(f, JType): return self.construct(f, pos, kw)
+        if callable(f):
+            try:
+                return f(*pos, **kw)
+            except (ValueError, IndexError, np.linalg.LinAlgError) as ex:
+                raise JuliaError("%s: %s" % (type(ex).__name__, ex))
+        raise JuliaError("MethodError: objects of type %s are not callable" % type(f).__name__)
+
+    def invoke(self, m, pos, kw):
+        env = Env(m.env)
+        env.is_function_root = True
+        for i, p in enumerate(m.params):
+            if i < len(pos): env.set(p[0], pos[i])
+            elif p[0] in kw: env.set(p[0], kw[p[0]])
+            else: env.set(p[0], self.eval(p[2], env))
+        for k_, v in kw.items(): env.set(k_, v)
+        try:
+            return self.exec_block(m.body, env)
+        except ReturnEx as r:
+            return r.v
+
+    def construct(self, ty, pos, kw):
+        n = ty.name
+        if n in ("ComplexF64", "Complex"):
+            return complex(*[float(x) if _is_real(x) else x for x in pos]) if len(pos) == 2 else complex(pos[0])
+        if n == "Float64": return float(pos[0])
+        if n in ("Int", "Int64"):
+            if isinstance(pos[0], float) and not pos[0].is_integer(): raise JuliaError("InexactError: Int(%r)" % pos[0])
+            return int(pos[0])
+        if n == "Bool": return bool(pos[0])
+        if n in ("Matrix", "Vector", "Array"):
+            dt = self._dtype(ty.params[0]) if ty.params else None
+            if pos and isinstance(pos[0], (np.ndarray, list)):
+                a = np.array(pos[0].a if isinstance(pos[0], Hermitian) else pos[0], dtype=dt)
+                if n == "Matrix" and a.ndim != 2: raise JuliaError("MethodError: Matrix(::Vector)")
+                return a
+            if pos and isinstance(pos[0], Hermitian): return np.array(pos[0].a, dtype=dt)
+            if pos and (pos[0] == "undef" or pos[0] is None): return np.zeros(tuple(int(x) for x in pos[1:]), dtype=dt)
+            if pos and pos[0] == "UniformScaling": return np.eye(int(pos[1]), dtype=dt)
+            raise JuliaError("jl_subset: unsupported %s constructor call" % n)
+        if n == "Dict": return dict(pos[0]) if pos else {}
+        if n == "String": return str(pos[0])
+        if n in ("ErrorException", "ArgumentError", "DomainError", "AssertionError"): return JuliaError(str(pos[0]) if pos else n)
+        raise JuliaError("jl_subset: cannot construct " + n)

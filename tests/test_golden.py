@@ -1,7 +1,9 @@
-"""Committed golden vectors (tests/golden/qsim_golden.json, written by tests/golden/make_golden.py from the literal
-kron transcription of QSim.jl / QInfo.jl) replayed through (CPU) the C oracle and the host emulator of the encoded pass
-programs and (GPU) the CUDA path behind the reference-named Python mirror.  1e-12 relative for amplitudes and readouts;
-the permutation-only case (x!, cnot!, swap!) bit for bit."""
+"""Committed golden vectors replayed through (CPU) the C oracle and the host emulator of the encoded pass programs and (GPU)
+the CUDA path behind the reference-named Python mirror.  Two files, same cases and call sequences:
+  * tests/golden/ref_exec_golden.json — made by EXECUTING the reference's own src/Quantum/QSim.jl and QInfo.jl with the
+    Julia-subset interpreter oracle/jl_subset.py (tests/golden/make_ref_exec_golden.py; see tests/test_ref_exec.py), and
+  * tests/golden/qsim_golden.json — made from oracle/literal.py, the hand transcription of the same algorithm.
+1e-12 relative for amplitudes and readouts; the permutation-only case (x!, cnot!, swap!) bit for bit."""
 import json
 import os
 
@@ -17,6 +19,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 with open(os.path.join(HERE, "golden", "qsim_golden.json")) as f:
     GOLDEN = json.load(f)
 CASES = GOLDEN["cases"]
+with open(os.path.join(HERE, "golden", "ref_exec_golden.json")) as f:
+    REF_EXEC_CASES = json.load(f)["cases"]
+ALL_CASES = [("refexec", c) for c in REF_EXEC_CASES] + [("literal", c) for c in CASES]
+ALL_IDS = ["%s-%s" % (src, c["name"]) for src, c in ALL_CASES]
 RTOL = 1e-12
 
 
@@ -72,8 +78,9 @@ def test_golden_file_matches_its_generator():
         assert mg.hxc(s) == case["amps"]
 
 
-@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
-def test_c_oracle_reproduces_golden_vectors(case):
+@pytest.mark.parametrize("src_case", ALL_CASES, ids=ALL_IDS)
+def test_c_oracle_reproduces_golden_vectors(src_case):
+    case = src_case[1]
     n = case["n"]
     s = replay(O, O.statevector(n, case["m"]), case["ops"])
     check_case(case, s, O.mp(s),
@@ -85,7 +92,7 @@ def test_c_oracle_reproduces_golden_vectors(case):
 def test_encoded_tma_programs_reproduce_the_12_qubit_golden_case(pkg, emu_mode):
     """planner + encoder of the fused TMA kernel against the literal algorithm, without a GPU: the 12-qubit golden
     case as a wire-format gate list, walked by the host emulator of the encoded pass programs (csrc/emulate.hpp)"""
-    case = next(c for c in CASES if c["n"] == 12)
+    case = next(c for c in REF_EXEC_CASES if c["n"] == 12)
     gl = pkg.circuits.GateList(12, "reference")
     replay_gl = lambda op: getattr(gl, op[0])(*op[1:-1], float.fromhex(op[-1])) if isinstance(op[-1], str) else getattr(gl, op[0])(*op[1:])
     for op in case["ops"]:
@@ -96,9 +103,10 @@ def test_encoded_tma_programs_reproduce_the_12_qubit_golden_case(pkg, emu_mode):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
-def test_cuda_path_reproduces_golden_vectors(pkg, case):
+@pytest.mark.parametrize("src_case", ALL_CASES, ids=ALL_IDS)
+def test_cuda_path_reproduces_golden_vectors(pkg, src_case):
     """the reference-named mirror over the C ABI (gates queue and fuse; readouts flush)"""
+    case = src_case[1]
     Q, QI = pkg.qsim, pkg.qinfo
     n = case["n"]
     s = replay(Q, Q.statevector(n, case["m"]), case["ops"])
