@@ -7,15 +7,19 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this.  The product (quromorphic.jl_b200/csrc) never links or calls it.
  *
- * Parity pinning: Julia is not available in this environment, so the reference itself cannot
- * be executed (no oracle/_ref).  This restatement is pinned (tests/test_oracle.py) against
+ * Parity pinning: Julia is not available in this environment, so the reference cannot be compiled or run by its own
+ * runtime (no oracle/_ref).  Its SOURCE is executed all the same: oracle/jl_subset.py, a generic interpreter for the subset of
+ * Julia that src/Quantum/*.jl and test/*.jl are written in, runs QSim.jl and QInfo.jl where they lie — the reference's own test
+ * files pass on it (126 + 67 assertions, tests/test_ref_exec.py) — and the golden vectors it produces from the reference's
+ * functions (tests/golden/ref_exec_golden.json, tests/golden/make_ref_exec_golden.py) are what this file is held to at 1e-12
+ * (tests/test_golden.py).  Besides, this restatement is pinned (tests/test_oracle.py) against
  *   (1) every known-answer assertion of test/test_QSim.jl and test/test_QInfo.jl that touches
  *       this path, and
  *   (2) oracle/literal.py — a numpy transcription of the reference's literal algorithm
  *       (kron(id(r), kron(U, id(l))) then a dense matrix-vector product), for every gate kind
  *       and every (c, t) pair on small registers, and
  *   (3) the committed golden vectors tests/golden/qsim_golden.json (written by tests/golden/make_golden.py
- *       from that literal transcription; tests/test_golden.py).
+ *       from that literal transcription; tests/test_golden.py), which agree with the executed-source vectors to 2e-15.
  * What no reference test or literal counterpart pins ("parity unpinned"): the all-qubit
  * expectation call, fused/batched application, psi -> reduced rho without forming rho, and the sampler — there
  * this file is the definition.
