@@ -225,3 +225,74 @@ def test_hand_transcription_agrees_with_the_executed_reference_source():
         if a["name"].endswith("permutations_only"):
             assert a["amps"] == b["amps"]
     assert worst < 5e-15, worst
+
+
+# ---- the other transcriptions, against the executed source ---------------------------------------------------------------
+@needs_ref
+def test_density_matrix_transcription_agrees_with_the_executed_reference(ref):
+    """oracle/literal.py's Matrix{ComplexF64} methods (what tests/test_gpu_density.py holds qm_dm_* to) against the reference's own
+    u2!(rho, ..), controlled!(rho, ..), swap!(rho, ..), mp(rho), measure_z/x/y(rho, ..) (QSim.jl:67-79, :209-232, :277-290, :295, :332-365)"""
+    from oracle import literal as L
+    MR, it = ref
+    R = lambda name, *a: MR.ref_call(it, name, *a)
+    rng = np.random.default_rng(2024)
+    for n in (1, 2, 3, 4):
+        rho_ref = R("density_matrix", n, int(rng.integers(0, 1 << n)))
+        rho_lit = rho_ref.copy()
+        for step in range(25):
+            kind = int(rng.integers(0, 6)) if n > 1 else int(rng.integers(0, 3))
+            t = int(rng.integers(1, n + 1))
+            th = float(rng.uniform(-6.3, 6.3))
+            if kind == 0:
+                R("h!", rho_ref, t); rho_lit = L.u2_dm(rho_lit, t, L.H)
+            elif kind == 1:
+                R("rx!", rho_ref, t, th); rho_lit = L.u2_dm(rho_lit, t, L.rx_gate(th))
+            elif kind == 2:
+                R("rz!", rho_ref, t, th); rho_lit = L.u2_dm(rho_lit, t, L.rz_gate(th))
+            else:
+                c = int(rng.integers(1, n)); c = c + 1 if c >= t else c
+                if kind == 3:
+                    R("cnot!", rho_ref, c, t); rho_lit = L.controlled_dm(rho_lit, c, t, L.X)
+                elif kind == 4:
+                    R("cry!", rho_ref, c, t, th); rho_lit = L.controlled_dm(rho_lit, c, t, L.ry_gate(th))
+                else:
+                    R("swap!", rho_ref, c, t); rho_lit = L.swap_dm(rho_lit, c, t)
+            assert np.max(np.abs(rho_ref - rho_lit)) < 1e-14, (n, step, kind)
+        assert np.max(np.abs(R("mp", rho_ref) - L.mp_dm(rho_lit))) < 1e-14
+        for t in range(1, n + 1):
+            for name, f in (("measure_z", L.measure_z_dm), ("measure_x", L.measure_x_dm), ("measure_y", L.measure_y_dm)):
+                assert np.max(np.abs(np.array(R(name, rho_ref, t)) - np.array(f(rho_lit, t)))) < 1e-14, (n, t, name)
+
+
+@needs_ref
+def test_host_qinfo_mirrors_agree_with_the_executed_reference(pkg, ref):
+    """quromorphic.jl_b200/qinfo.py (the host mirrors, and the yardstick of the batched device measures) against the reference's own
+    QInfo.jl functions on random density matrices: full-rank, and pure-state reductions (rank-deficient)"""
+    QI = pkg.qinfo
+    MR, it = ref
+    R = lambda name, *a: MR.ref_call(it, name, *a)
+    rng = np.random.default_rng(77)
+
+    def random_rho(d, rank=None):
+        a = rng.normal(size=(d, rank or d)) + 1j * rng.normal(size=(d, rank or d))
+        m = a @ a.conj().T
+        return np.ascontiguousarray(m / np.trace(m).real)
+
+    for d in (2, 4, 8):
+        rho, sigma = random_rho(d), random_rho(d)
+        for name in ("von_neumann_entropy", "min_entropy", "max_entropy", "l1_norm_coherence"):
+            assert abs(getattr(QI, name)(rho) - R(name, rho)) < 1e-10, (d, name)
+        for alpha in (0.5, 2.0, 3.0):
+            assert abs(QI.renyi_entropy(rho, alpha) - R("renyi_entropy", rho, alpha)) < 1e-10, (d, alpha)
+        assert abs(QI.fidelity(rho, sigma) - R("fidelity", rho, sigma)) < 1e-9
+        assert abs(QI.trace_distance(rho, sigma) - R("trace_distance", rho, sigma)) < 1e-10
+        assert abs(QI.relative_entropy(rho, sigma) - R("relative_entropy", rho, sigma)) < 1e-9
+        low = random_rho(d, rank=1)
+        assert abs(QI.von_neumann_entropy(low) - R("von_neumann_entropy", low)) < 1e-8
+        assert abs(QI.max_entropy(low) - R("max_entropy", low)) < 1e-12
+    for dA, dB in ((2, 2), (2, 4), (4, 2)):
+        rho = random_rho(dA * dB)
+        for name in ("quantum_mutual_information", "conditional_quantum_entropy", "coherent_information"):
+            assert abs(getattr(QI, name)(rho, dA, dB) - R(name, rho, dA, dB)) < 1e-9, (dA, dB, name)
+        for sub in (1, 2):
+            assert np.max(np.abs(QI.partial_trace_matrix(rho, dA, dB, sub) - R("partial_trace", rho, dA, dB, sub))) < 1e-14
