@@ -92,7 +92,33 @@ CASES = [  # (name, n, basis m, number of calls, seed, restrict to kinds)
     ("n2_bell", 2, 0, 0, 109, None),
     # 12 qubits: the smallest register the fused TMA kernel takes (dense 4096 x 4096 operators: ~0.3 s per call here)
     ("n12_mixed_tma_kernel_size", 12, 0, 36, 110, None),
+    # config C1 of BASELINE.json (the reference's own CPU-runnable case): 12-qubit reservoir, three time steps of 48 gates each
+    # (ry encoding, rx/rz layer, CNOT chain, the non-adjacent crz!(12, 1, gamma)) from |0..0>
+    ("c1_reservoir_12q_3_steps", 12, 0, 0, 111, None),
 ]
+
+
+def c1_ops(n=12, steps=3):
+    """the gate calls of config C1 (quromorphic.jl_b200/circuits.py c1_step / c1_inputs) as golden-file ops"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("qm_circuits_for_golden", os.path.join(ROOT, "quromorphic.jl_b200", "circuits.py"))
+    src = open(spec.origin).read()
+    # circuits.py imports the package's ctypes layer for the wire format; only its pure-Python generators are needed here
+    ns = {"__name__": "qm_circuits_for_golden"}
+    exec(compile(src.replace("from . import _lib as L", "L = None").replace("from . import qsim as Q", "Q = None"), spec.origin, "exec"), ns)
+
+    class Rec:
+        def __init__(self): self.ops = []
+        def ry(self, q, th): self.ops.append(["ry", q, float.hex(float(th))])
+        def rx(self, q, th): self.ops.append(["rx", q, float.hex(float(th))])
+        def rz(self, q, th): self.ops.append(["rz", q, float.hex(float(th))])
+        def cnot(self, c, t): self.ops.append(["cnot", c, t])
+        def crz(self, c, t, th): self.ops.append(["crz", c, t, float.hex(float(th))])
+    u, w, layer, gamma = ns["c1_inputs"](n, steps)
+    rec = Rec()
+    for t in range(steps):
+        ns["c1_step"](rec, n, u[t], w, layer, gamma)
+    return rec.ops
 
 
 def main():
@@ -109,6 +135,8 @@ def main():
                         ops.append(["cnot", t, c])
         elif name == "n2_bell":
             ops = [["h", 1], ["cnot", 1, 2]]
+        elif name.startswith("c1_reservoir"):
+            ops = c1_ops(n, 3)
         else:
             ops = make_ops(n, nops, seed, kinds)
         s = L.statevector(n, m)

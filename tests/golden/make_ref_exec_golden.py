@@ -64,6 +64,8 @@ def build_ops(name, n, nops, seed, kinds):
         return ops
     if name == "n2_bell":
         return [["h", 1], ["cnot", 1, 2]]
+    if name.startswith("c1_reservoir"):
+        return MG.c1_ops(n, 3)
     return MG.make_ops(n, nops, seed, kinds)
 
 
