@@ -427,9 +427,9 @@ class Parser:
         """call arguments up to `closer`: (positional, keyword dict)"""
         self.no_nl += 1
         saved_arr, self._inarray = self._inarray, 0
-        pos, kw, semi = [], {}, False
+        pos, kw = [], {}
         while not self.at(closer):
-            if self.accept(";"): semi = True; continue
+            if self.accept(";"): continue                # f(a; k = v): keywords may follow a semicolon
             e = self.expr()
             if self.at("=") and e[0] == "id":
                 self.next(); kw[e[1]] = self.expr()
@@ -508,7 +508,7 @@ class Parser:
                 if nxt.val == "im": return ("num", complex(0.0, tok.val))
                 return ("bin", "*", ("num", tok.val), ("id", nxt.val))
             if nxt.kind == "op" and nxt.val == "(" and not nxt.sp:
-                return ("bin", "*", ("num", tok.val), self.postfix_from_paren())
+                return ("bin", "*", ("num", tok.val), self.postfix())      # 2(x + 1)
             return ("num", tok.val)
         if tok.kind == "str": return ("str", tok.val)
         if tok.kind == "id": return ("id", tok.val)
@@ -546,9 +546,6 @@ class Parser:
             if tok.val == "[": return self.array_literal()
             if tok.val == ":": return ("colon",)
         raise SyntaxError("jl_subset: unexpected %r at line %d" % (tok.val, tok.line))
-
-    def postfix_from_paren(self):
-        return self.postfix()
 
     def if_expr(self):
         clauses, els = [], None
@@ -1229,8 +1226,8 @@ class Interp:
     def binop(self, op, a, b):
         if isinstance(a, JRange) and op in ("+", "-", "*", ".+", ".-", ".*", "./"): a = np.asarray(a.values())
         if isinstance(b, JRange) and op in ("+", "-", "*", ".+", ".-", ".*", "./"): b = np.asarray(b.values())
-        if a == "UniformScaling" if isinstance(a, str) else False: a = np.eye(b.shape[0]) if isinstance(b, np.ndarray) else 1
-        if b == "UniformScaling" if isinstance(b, str) else False: b = np.eye(a.shape[0]) if isinstance(a, np.ndarray) else 1
+        if isinstance(a, str) and a == "UniformScaling": a = np.eye(b.shape[0]) if isinstance(b, np.ndarray) else 1     # LinearAlgebra.I
+        if isinstance(b, str) and b == "UniformScaling": b = np.eye(a.shape[0]) if isinstance(a, np.ndarray) else 1
         if op == "+":
             if isinstance(a, Hermitian): a = a.a
             if isinstance(b, Hermitian): b = b.a
