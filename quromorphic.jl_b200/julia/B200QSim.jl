@@ -126,7 +126,6 @@ function swap!(s::B200State, q1::Int, q2::Int)            # QSim.jl:262-275
     s
 end
 
-"apply a whole gate list (0-based textbook bits, the wire format) in as few HBM passes as possible"
 """
     precompile_circuit!(s, gates) -> Int
 
@@ -154,6 +153,7 @@ function apply_circuit_expect_z!(s::B200State, gates::Vector{QMGate}; threshold:
     return out
 end
 
+"apply a whole gate list (0-based textbook bits, the wire format) in as few HBM passes as possible"
 function apply_circuit!(s::B200State, gates::Vector{QMGate})
     check(ccall((:qm_apply_circuit, LIB), Int32, (Ptr{Cvoid}, Ptr{QMGate}, Int32), s.handle, gates, length(gates)))
     s
