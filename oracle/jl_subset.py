@@ -225,6 +225,22 @@ class Parser:
             if v in ("global", "local"):
                 self.next(); return self.statement()
             if v == "function": return self.function_def()
+            if v in ("struct", "mutable"):
+                self.next()
+                if v == "mutable": self.expect("struct")
+                name = self.next().val
+                if self.at("{"):
+                    while not self.accept("}"): self.next()
+                if self.accept("<"): self.expect(":"); self.type_expr()
+                fields = []
+                self.skip_nl()
+                while not self.at("end"):
+                    fname = self.next().val
+                    fty = self.type_expr() if self.accept("::") else None
+                    fields.append((fname, fty))
+                    self.skip_nl()
+                self.expect("end")
+                return ("struct", name, fields, v == "mutable")
             if v == "return":
                 self.next()
                 if self.peek().kind in ("nl", "eof") or self.at("end") or self.at(";"): return ("return", None)
@@ -235,6 +251,10 @@ class Parser:
             if v == "while":
                 self.next(); cond = self.expr(); body = self.block(); self.expect("end"); return ("while", cond, body)
         if tok.kind == "op" and tok.val == "@": return self.macro()
+        if tok.kind == "id" and tok.val == "GC" and self.peek(1).val == "." and self.peek(2).val == "@":      # GC.@preserve x y stmt
+            self.next(); self.next(); self.next(); self.next()
+            while self.peek().kind == "id" and self.peek(1).kind == "id": self.next()      # the preserved variables
+            return self.statement()
         if tok.kind == "str" and self.t[self.i + 1].kind == "nl":      # a docstring (or a bare string): no effect
             self.next(); return ("nop",)
         e = self.expr_or_tuple()
@@ -243,8 +263,12 @@ class Parser:
             self.next()
             while self.t[self.i].kind == "nl": self.i += 1
             rhs = self.statement_rhs()
-            if tok.val == "=" and e[0] == "call" and not e[3]:         # short-form method definition  f(x::T) = expr
-                return ("function", e[1][1] if e[1][0] == "id" else None, [self.param(a) for a in e[2]], ("block", [("return", rhs)]))
+            if tok.val == "=" and e[0] == "call":                      # short-form method definition  f(x::T; k = v) = expr
+                fname = e[1][1] if e[1][0] == "id" else (e[1][2] if e[1][0] == "field" else None)      # Base.length(x) = ...
+                params = [self.param(a) for a in e[2] if a[0] != "splat"]
+                for k_, v_ in e[3].items():
+                    params.append((k_, v_[1], v_[2]) if v_[0] == "kwtyped" else (k_, None, v_))
+                return ("function", fname, params, ("block", [("return", rhs)]))
             return ("assign", tok.val, e, rhs)
         return ("expr", e)
 
@@ -264,12 +288,22 @@ class Parser:
         self.expect("function")
         name = self.next().val
         while self.accept("."): name = self.next().val       # function Mod.name(...)
+        if self.at("{") and not self.peek().sp:              # function Base.Vector{T}(...): a method of a parametric type's constructor
+            depth = 0
+            while True:
+                t_ = self.next()
+                depth += (t_.val == "{") - (t_.val == "}")
+                if depth == 0: break
         self.expect("(")
         self.no_nl += 1
         params = []
         while not self.at(")"):
             if self.accept(";"): continue
             a = self.expr()
+            if self.accept("..."):                          # kw... / args...: collected, never used by the files this runs
+                params.append((a[1] if a[0] == "id" else "_", None, ("tuple", [])))
+                if not self.accept(","): break
+                continue
             if self.accept("="): a = ("kwarg", a, self.expr())
             params.append(self.param(a))
             if not self.accept(","):
@@ -319,6 +353,8 @@ class Parser:
             return ("test_throws", exc, e, self.t[self.i - 1].line)
         if name in ("inbounds", "views", "inline", "simd", "fastmath", "show", "time", "info", "warn"):
             return self.statement()
+        if name == "eval":                               # @eval $f(x) = ...: parsed (so that a file using it can be checked), not executable
+            return ("evalmacro", self.statement())
         raise SyntaxError("jl_subset: unsupported macro @%s" % name)
 
     # -- expressions
@@ -433,6 +469,8 @@ class Parser:
             e = self.expr()
             if self.at("=") and e[0] == "id":
                 self.next(); kw[e[1]] = self.expr()
+            elif self.at("=") and e[0] == "typed" and e[1][0] == "id":      # f(x; k::T = v) = ...: only meaningful in a definition
+                self.next(); kw[e[1][1]] = ("kwtyped", e[2], self.expr())
             elif self.at("..."):
                 self.next(); pos.append(("splat", e))
             elif self.at("for"):                         # generator  f(x for x in xs)
@@ -454,6 +492,15 @@ class Parser:
         e = self.primary()
         while True:
             tok = self.peek()
+            if tok.kind == "kw" and tok.val == "do" and e[0] == "call":        # f(args) do x ... end: the block is f's first argument
+                self.next()
+                params = []
+                while self.peek().kind != "nl":
+                    params.append(self.param(self.expr()))
+                    if not self.accept(","): break
+                body = self.block(); self.expect("end")
+                e = ("call", e[1], [("lambda", params, body)] + e[2], e[3])
+                continue
             if tok.kind != "op": break
             v = tok.val
             if v == "(" and not tok.sp:
@@ -520,6 +567,9 @@ class Parser:
             if tok.val == "if": return self.if_expr()
             if tok.val == "begin":
                 b = self.block(); self.expect("end"); return ("blockexpr", b)
+            if tok.val == "return":
+                if self.peek().kind in ("nl", "eof") or self.at(")") or self.at("end"): return ("returnx", None)
+                return ("returnx", self.expr())
             if tok.val == "function":
                 self.i -= 1; return ("fundef", self.function_def())
         if tok.kind == "op":
@@ -529,8 +579,21 @@ class Parser:
                 if self.at(")"):
                     self.next(); self.no_nl -= 1; self._inarray = saved_arr; return ("tuple", [])
                 e = self.expr()
-                if self.at("=") and e[0] == "id":          # (a = 1, b = 2) named tuple: not needed
-                    raise SyntaxError("jl_subset: named tuples are not supported (line %d)" % tok.line)
+                if self.at("=") and e[0] in ("id", "field", "index"):        # (b = max(c, t); ...): an assignment inside a block in parentheses
+                    self.next(); e = ("assignexpr", e, self.expr())
+                if self.at(";"):                            # (a; b; c): a block, its value is the last expression
+                    stmts = [("expr", e)]
+                    while self.accept(";"):
+                        if self.at(")"): break
+                        e2 = self.expr()
+                        if self.at("=") and e2[0] in ("id", "field", "index"):
+                            self.next(); e2 = ("assignexpr", e2, self.expr())
+                        stmts.append(("expr", e2))
+                    e = ("blockexpr", ("block", stmts))
+                    self._inarray = saved_arr
+                    self.no_nl -= 1
+                    self.expect(")")
+                    return e
                 if self.at(","):
                     items = [e]
                     while self.accept(","):
@@ -545,6 +608,10 @@ class Parser:
                 return e
             if tok.val == "[": return self.array_literal()
             if tok.val == ":": return ("colon",)
+            if tok.val == "@":                              # @__DIR__ and friends in expression position
+                return ("macrocall", self.next().val)
+            if tok.val == "$":                              # $name inside @eval
+                return ("interp", self.next().val)
         raise SyntaxError("jl_subset: unexpected %r at line %d" % (tok.val, tok.line))
 
     def if_expr(self):
@@ -974,6 +1041,8 @@ class Interp:
                     except ContinueEx: pass
             except BreakEx: pass
             return None
+        if k == "struct":
+            raise JuliaError("jl_subset: struct definitions are parsed but not executable (%s)" % st[1])
         if k == "module":
             menv = Env(self.globals)
             menv.is_module = True
@@ -1219,6 +1288,11 @@ class Interp:
         if k == "lambda":
             return Method(e[1], e[2], env)
         if k == "blockexpr": return self.exec_block(e[1], env)
+        if k == "assignexpr": return self.assign("=", e[1], e[2], env)
+        if k == "returnx": raise ReturnEx(self.eval(e[1], env) if e[1] is not None else None)
+        if k == "macrocall":
+            if e[1] == "__DIR__": return getattr(self, "current_dir", ".")
+            raise JuliaError("jl_subset: macro @%s is not supported in an expression" % e[1])
         if k == "fundef": return self.define(e[1], env)
         if k == "splat": raise JuliaError("jl_subset: splat outside a call")
         raise JuliaError("jl_subset: cannot evaluate " + k)
@@ -1291,7 +1365,7 @@ class Interp:
                     if a[4] is None or self.eval(a[4], inner): vals.append(self.eval(a[1], inner))
                 pos.append(vals)
             else: pos.append(self.eval(a, env))
-        kw = {k_: self.eval(v, env) for k_, v in e[3].items()}
+        kw = {k_: self.eval(v[2] if v[0] == "kwtyped" else v, env) for k_, v in e[3].items()}
         f = self.eval(fnode, env)
         return self.call(f, pos, kw)
 
