@@ -62,10 +62,10 @@ def c_kind(ct):
     raise AssertionError("unmapped ctypes type %r" % (ct,))
 
 
-def test_shim_parses_and_every_ccall_matches_the_c_abi(pkg, shim_ast):
+def check_ccalls(pkg, ast):
+    """every ccall of the tree against the ctypes signature table; returns the set of symbols called"""
     sigs = pkg._lib.SIGNATURES
-    calls = [n for n in walk(shim_ast) if n[0] == "call" and n[1] == ("id", "ccall")]
-    assert len(calls) >= 25
+    calls = [n for n in walk(ast) if n[0] == "call" and n[1] == ("id", "ccall")]
     seen = set()
     for c in calls:
         args = c[2]
@@ -83,6 +83,12 @@ def test_shim_parses_and_every_ccall_matches_the_c_abi(pkg, shim_ast):
             jn = type_name(jt)
             jn = {"Ref": "Ptr", "Cstring": "Ptr", "Cint": "Int32", "Cdouble": "Float64", "Csize_t": "UInt64"}.get(jn, jn)
             assert jn == c_kind(ct), "%s: argument %d is %s in the shim, %s in the C ABI" % (name, i + 1, jn, c_kind(ct))
+    return seen, len(calls)
+
+
+def test_shim_parses_and_every_ccall_matches_the_c_abi(pkg, shim_ast):
+    seen, ncalls = check_ccalls(pkg, shim_ast)
+    assert ncalls >= 25
     # the path of the reference's API is all there
     for must in ("qm_create", "qm_destroy", "qm_upload", "qm_download", "qm_apply_u2", "qm_apply_controlled", "qm_apply_circuit",
                  "qm_apply_circuit_expect_z", "qm_precompile_circuit", "qm_probs", "qm_measure_with", "qm_expect_z_all", "qm_reduced_density",
@@ -114,3 +120,15 @@ def test_shim_methods_extend_real_reference_functions_with_matching_arity(shim_a
         assert mine in ref_arities, "%s: the shim's method takes %d positional arguments, the reference's take %s" % (st[1], mine, sorted(ref_arities))
         checked += 1
     assert checked >= 25
+
+
+def test_integration_md_excerpts_parse_and_agree_with_the_abi(pkg):
+    """the Julia excerpts INTEGRATION.md shows a maintainer are held to the same checks as the shim itself"""
+    with open(os.path.join(ROOT, "INTEGRATION.md"), encoding="utf-8") as f:
+        blocks = re.findall(r"```julia\n(.*?)```", f.read(), flags=re.S)
+    assert len(blocks) >= 2
+    total = 0
+    for blk in blocks:
+        seen, n = check_ccalls(pkg, J.parse(blk))
+        total += n
+    assert total >= 3
