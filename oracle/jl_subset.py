@@ -47,6 +47,20 @@ class Hermitian:
         self.a = np.asarray(a)
 
 
+class JObject:
+    """an instance of a (mutable) struct"""
+    def __init__(self, tname, fields):
+        self.tname, self.fields = tname, fields
+
+    def __repr__(self):
+        return "%s(%s)" % (self.tname, ", ".join("%s=%r" % kv for kv in self.fields.items()))
+
+
+class JRef:
+    """Ref{T}(x): a box; r[] reads it, r[] = v writes it"""
+    def __init__(self, value): self.value = value
+
+
 class ReturnEx(Exception):
     def __init__(self, v): self.v = v
 
@@ -213,13 +227,17 @@ class Parser:
                 self.next(); name = self.next().val; body = self.block(); self.expect("end"); return ("module", name, body)
             if v in ("using", "import", "export"):
                 self.next()
+                toks = []
                 while True:                              # names, possibly continued over lines after a comma
-                    while self.peek().kind not in ("nl", "eof") and not self.at(","): self.next()
+                    while self.peek().kind not in ("nl", "eof") and not self.at(","): toks.append(self.next().val)
                     if self.accept(","):
+                        toks.append(",")
                         while self.t[self.i].kind == "nl": self.i += 1
                         continue
                     break
-                return ("nop",)
+                if v == "export" or ":" not in toks: return ("nop",)
+                k = toks.index(":")                      # using A.B: x, y   /   import A.B: f, g
+                return ("import", [x for x in toks[:k] if x != "."], [x for x in toks[k + 1:] if x != ","])
             if v == "const":
                 self.next(); return self.statement()
             if v in ("global", "local"):
@@ -264,8 +282,13 @@ class Parser:
             while self.t[self.i].kind == "nl": self.i += 1
             rhs = self.statement_rhs()
             if tok.val == "=" and e[0] == "call":                      # short-form method definition  f(x::T; k = v) = expr
-                fname = e[1][1] if e[1][0] == "id" else (e[1][2] if e[1][0] == "field" else None)      # Base.length(x) = ...
-                params = [self.param(a) for a in e[2] if a[0] != "splat"]
+                callee = e[1][1] if e[1][0] == "curly" else e[1]           # Base.Matrix{T}(x) = ...: a constructor method of a parametric type
+                fname = callee[1] if callee[0] == "id" else (callee[2] if callee[0] == "field" else (callee if callee[0] == "interp" else None))   # Base.length(x) = ... / $f(x) = ...
+                params = []
+                for a in e[2]:
+                    if a[0] == "splat": params.append((a[1][1] if a[1][0] == "id" else "_", None, ("varkw",)))
+                    elif a[0] == "eqarg": nm = self.param(a[1]); params.append((nm[0], nm[1], a[2]))
+                    else: params.append(self.param(a))
                 for k_, v_ in e[3].items():
                     params.append((k_, v_[1], v_[2]) if v_[0] == "kwtyped" else (k_, None, v_))
                 return ("function", fname, params, ("block", [("return", rhs)]))
@@ -301,7 +324,7 @@ class Parser:
             if self.accept(";"): continue
             a = self.expr()
             if self.accept("..."):                          # kw... / args...: collected, never used by the files this runs
-                params.append((a[1] if a[0] == "id" else "_", None, ("tuple", [])))
+                params.append((a[1] if a[0] == "id" else "_", None, ("varkw",)))
                 if not self.accept(","): break
                 continue
             if self.accept("="): a = ("kwarg", a, self.expr())
@@ -463,11 +486,15 @@ class Parser:
         """call arguments up to `closer`: (positional, keyword dict)"""
         self.no_nl += 1
         saved_arr, self._inarray = self._inarray, 0
-        pos, kw = [], {}
+        pos, kw, after_semi = [], {}, False
         while not self.at(closer):
-            if self.accept(";"): continue                # f(a; k = v): keywords may follow a semicolon
+            if self.accept(";"): after_semi = True; continue        # f(a; k = v): keywords follow the semicolon
             e = self.expr()
-            if self.at("=") and e[0] == "id":
+            if self.at("=") and not after_semi and (e[0] == "id" or (e[0] == "typed" and e[1][0] == "id")):
+                # before the semicolon `x = v` is a keyword argument in a CALL and an optional positional parameter in a
+                # short-form DEFINITION: kept in place, the consumer decides
+                self.next(); pos.append(("eqarg", e, self.expr()))
+            elif self.at("=") and e[0] == "id":
                 self.next(); kw[e[1]] = self.expr()
             elif self.at("=") and e[0] == "typed" and e[1][0] == "id":      # f(x; k::T = v) = ...: only meaningful in a definition
                 self.next(); kw[e[1][1]] = ("kwtyped", e[2], self.expr())
@@ -682,8 +709,9 @@ class Method:
 
 
 class GenericFunction:
-    def __init__(self, name):
+    def __init__(self, name, base=None):
         self.name, self.methods = name, []
+        self.base = base            # the builtin (Base function or type) this function extends: calls no method takes go there
 
     def __repr__(self):
         return "<julia function %s, %d methods>" % (self.name, len(self.methods))
@@ -719,10 +747,20 @@ def type_match(v, ty):
             if n.startswith("Abstract") and el in ("T", "Number"): ok = True
             return 3 if ok else -1
         return 2
+    if n == "Union":
+        best = max([type_match(v, p) for p in ps] or [-1])
+        return best
+    if n == "Nothing": return 3 if v is None else -1
+    if n == "Symbol": return 3 if isinstance(v, str) else -1
     if n == "Function": return 2 if isinstance(v, (GenericFunction, Method)) or callable(v) else -1
     if n == "Tuple": return 2 if isinstance(v, tuple) else -1
     if n == "Dict": return 2 if isinstance(v, dict) else -1
+    if isinstance(v, JObject): return 3 if v.tname == n else -1
+    if n in STRUCT_NAMES: return -1                     # a value that is not an instance of that struct
     return 0
+
+
+STRUCT_NAMES = set()
 
 
 class Env:
@@ -830,6 +868,8 @@ class TestLog:
 
 
 class Interp:
+    ccall_handler = None
+
     def __init__(self):
         self.globals = Env()
         self.modules = {}
@@ -842,7 +882,8 @@ class Interp:
         G = self.globals.vars
         for n in ("Int", "Int64", "Float64", "ComplexF64", "Bool", "Real", "Number", "Vector", "Matrix", "Array", "Dict", "String", "Any", "Tuple",
                   "Integer", "AbstractFloat", "AbstractMatrix", "AbstractVector", "AbstractArray", "Function", "Complex", "Nothing",
-                  "ErrorException", "AssertionError", "BoundsError", "MethodError", "DimensionMismatch", "ArgumentError", "DomainError", "Exception"):
+                  "ErrorException", "AssertionError", "BoundsError", "MethodError", "DimensionMismatch", "ArgumentError", "DomainError", "Exception",
+                  "Ref", "Ptr", "Cvoid", "Int32", "UInt32", "UInt64", "UInt8", "Symbol", "Union", "NTuple", "Cstring", "AbstractString"):
             G[n] = JType(n)
         G.update({"π": math.pi, "pi": math.pi, "ℯ": math.e, "im": 1j, "Inf": math.inf, "NaN": math.nan, "nothing": None})
 
@@ -950,8 +991,14 @@ class Interp:
             "axes": lambda a, d: JRange(1, int(a.shape[int(d) - 1])), "eachindex": lambda a: JRange(1, int(np.size(a))), "enumerate": lambda x: [(i + 1, v) for i, v in enumerate(self._iter(x))],
             "zip": lambda *xs: list(zip(*[list(self._iter(x)) for x in xs])), "keys": lambda d: list(d.keys()), "values": lambda d: list(d.values()),
             "dot": lambda a, b: self._scalar(np.vdot(np.asarray(a), np.asarray(b))),
+            "finalizer": lambda f, obj: obj, "pointer": lambda a: a, "C_NULL": 0, "undef": "undef", "ENV": dict(__import__("os").environ),
+            "get": lambda d, k, default=None: d.get(k, default), "joinpath": lambda *a: __import__("os").path.join(*a),
+            "throw": self._throw, "isnothing": lambda x: x is None,
             "rand": self._no_random, "randn": self._no_random,
         })
+
+    def _throw(self, ex):
+        raise ex if isinstance(ex, JuliaError) else JuliaError(str(ex))
 
     def _no_random(self, *a, **k):
         raise JuliaError("rand/randn are not available in the subset interpreter (fixtures must be deterministic)")
@@ -1013,6 +1060,7 @@ class Interp:
     def using(self, name):
         """bring the names a module defines into the global scope (the subset has no export lists: everything comes)"""
         for k, v in self.modules[name].vars.items():
+            if isinstance(v, GenericFunction) and v.base is not None: continue      # an extension of a builtin stays reachable through dispatch
             self.globals.vars[k] = v
 
     # ---- statements -----------------------------------------------------------------------------------------------
@@ -1042,7 +1090,30 @@ class Interp:
             except BreakEx: pass
             return None
         if k == "struct":
-            raise JuliaError("jl_subset: struct definitions are parsed but not executable (%s)" % st[1])
+            gf = env.vars.get(st[1])
+            if not isinstance(gf, GenericFunction):
+                gf = GenericFunction(st[1]); env.set(st[1], gf)
+            gf.struct_fields = [f[0] for f in st[2]]
+            STRUCT_NAMES.add(st[1])
+            return None
+        if k == "import":
+            mod = self.modules.get(st[1][-1])
+            if mod is None: raise JuliaError("jl_subset: module %s is not loaded" % ".".join(st[1]))
+            for nm in st[2]: env.set(nm, mod.lookup(nm))      # the same object: a method defined here extends the module's function
+            return None
+        if k == "evalmacro":                            # @eval with $name interpolations: substitute the Symbols' values, then execute
+            def subst(node):
+                if isinstance(node, tuple):
+                    if node and node[0] == "interp": return ("id", str(env.lookup(node[1])))
+                    return tuple(subst(x) for x in node)
+                if isinstance(node, list): return [subst(x) for x in node]
+                if isinstance(node, dict): return {a: subst(b) for a, b in node.items()}
+                return node
+            inner = subst(st[1])
+            if inner[0] == "function" and isinstance(inner[1], tuple): inner = ("function", inner[1][1]) + inner[2:]
+            target = env
+            while not getattr(target, "is_module", False) and target.parent is not None: target = target.parent
+            return self.exec(inner, target)
         if k == "module":
             menv = Env(self.globals)
             menv.is_module = True
@@ -1115,7 +1186,8 @@ class Interp:
         if name is None: raise JuliaError("jl_subset: anonymous function statement")
         gf = env.vars.get(name)
         if not isinstance(gf, GenericFunction):
-            gf = GenericFunction(name); env.set(name, gf)
+            base = self.globals.vars.get(name)
+            gf = GenericFunction(name, base if not isinstance(base, GenericFunction) else None); env.set(name, gf)
         ps = [(p[0], p[1], p[2]) for p in params]
         sig = [repr(p[1]) for p in ps]
         gf.methods = [m for m in gf.methods if [repr(p[1]) for p in m.params] != sig]
@@ -1145,14 +1217,18 @@ class Interp:
             return self.assign("=", target[1], ("lit", rhs), env)
         elif k == "index":
             arr = self.eval(target[1], env)
-            if isinstance(arr, dict):
+            if isinstance(arr, JRef):
+                arr.value = rhs
+            elif isinstance(arr, dict):
                 arr[self.eval(target[2][0], env)] = rhs
             else:
                 arr[self.index_key(arr, target[2], env)] = rhs
         elif k in ("tuple", "paren"):
             self.bind(target, rhs, env)
         elif k == "field":
-            raise JuliaError("jl_subset: field assignment is not supported")
+            obj = self.eval(target[1], env)
+            if not isinstance(obj, JObject) or target[2] not in obj.fields: raise JuliaError("jl_subset: cannot assign field %s" % target[2])
+            obj.fields[target[2]] = rhs
         else:
             raise JuliaError("jl_subset: cannot assign to " + k)
         return rhs
@@ -1227,6 +1303,7 @@ class Interp:
             return self.broadcast(f, args, kw)
         if k == "index":
             a = self.eval(e[1], env)
+            if isinstance(a, JRef): return a.value
             if isinstance(a, dict):
                 key = self.eval(e[2][0], env)
                 if key not in a: raise JuliaError("KeyError: %r" % (key,))
@@ -1275,6 +1352,9 @@ class Interp:
             return np.asarray(self.eval(e[2], env), dtype=self._dtype(ty))
         if k == "curly":
             base = self.eval(e[1], env)
+            if isinstance(base, GenericFunction) and isinstance(base.base, JType):      # Vector{T}(...) where Vector has been extended
+                g2 = GenericFunction(base.name, base.base); g2.methods = base.methods; g2.curly = JType(base.base.name, e[2])
+                return g2
             return JType(base.name, e[2]) if isinstance(base, JType) else base
         if k == "typed": return self.eval(e[1], env)
         if k == "field":
@@ -1283,6 +1363,9 @@ class Interp:
             if base[0] == "field":                          # Quromorphic.QSim.f
                 if base[2] in self.modules: return self.modules[base[2]].lookup(e[2])
             v = self.eval(base, env)
+            if isinstance(v, JObject):
+                if e[2] not in v.fields: raise JuliaError("type %s has no field %s" % (v.tname, e[2]))
+                return v.fields[e[2]]
             if isinstance(v, tuple) and e[2] in ("values", "vectors"): return v[0 if e[2] == "values" else 1]
             raise JuliaError("jl_subset: no field %s" % e[2])
         if k == "lambda":
@@ -1355,9 +1438,21 @@ class Interp:
 
     def eval_call(self, e, env):
         fnode = e[1]
-        pos = []
+        if fnode == ("id", "ccall"):
+            # ccall((:symbol, LIB), Ret, (ArgTypes...), args...): handed to self.ccall_handler(symbol, [argument values]) — a test
+            # installs a recorder there; there is no foreign-function interface in this interpreter
+            target = self.eval(e[2][0], env)
+            args = [self.eval(a, env) for a in e[2][3:]]
+            if self.ccall_handler is None: raise JuliaError("jl_subset: ccall(%s) without a handler" % (target[0],))
+            return self.ccall_handler(target[0], args)
+        pos, kwsplat = [], {}
         for a in e[2]:
-            if a[0] == "splat": pos.extend(self._iter(self.eval(a[1], env)))
+            if a[0] == "eqarg":
+                kwsplat[a[1][1] if a[1][0] == "id" else a[1][1][1]] = self.eval(a[2], env)
+            elif a[0] == "splat":
+                v = self.eval(a[1], env)
+                if isinstance(v, dict): kwsplat.update(v)
+                else: pos.extend(self._iter(v))
             elif a[0] == "gen":
                 vals = []
                 for v in self._iter(self.eval(a[3], env)):
@@ -1365,7 +1460,8 @@ class Interp:
                     if a[4] is None or self.eval(a[4], inner): vals.append(self.eval(a[1], inner))
                 pos.append(vals)
             else: pos.append(self.eval(a, env))
-        kw = {k_: self.eval(v[2] if v[0] == "kwtyped" else v, env) for k_, v in e[3].items()}
+        kw = dict(kwsplat)
+        kw.update({k_: self.eval(v[2] if v[0] == "kwtyped" else v, env) for k_, v in e[3].items()})
         f = self.eval(fnode, env)
         return self.call(f, pos, kw)
 
@@ -1375,7 +1471,7 @@ class Interp:
             best, best_score = None, -1
             for m in f.methods:
                 req = [p for p in m.params if p[2] is None]
-                if len(pos) < len(req) or len(pos) > len(m.params): continue
+                if len(pos) < len(req) or len(pos) > len([p for p in m.params if p[2] != ("varkw",)]): continue
                 score, ok = 0, True
                 for p, v in zip(m.params, pos):
                     s = type_match(v, p[1])
@@ -1383,6 +1479,11 @@ class Interp:
                     score += s
                 if ok and score > best_score: best, best_score = m, score
             if best is None:
+                fields = getattr(f, "struct_fields", None)
+                if fields is not None and len(pos) == len(fields) and not kw:        # the struct's default constructor
+                    return JObject(f.name, dict(zip(fields, pos)))
+                if f.base is not None:                          # Base.length(x::MyType) = ... extends a builtin: other arguments go there
+                    return self.call(getattr(f, "curly", None) or f.base, pos, kw)
                 raise JuliaError("MethodError: no method matching %s(%s)" % (f.name, ", ".join(repr(self._typeof(v)) for v in pos)))
             return self.invoke(best, pos, kw)
         if isinstance(f, Method): return self.invoke(f, pos, kw)
@@ -1397,11 +1498,12 @@ class Interp:
     def invoke(self, m, pos, kw):
         env = Env(m.env)
         env.is_function_root = True
+        named = {p[0] for p in m.params}
         for i, p in enumerate(m.params):
-            if i < len(pos): env.set(p[0], pos[i])
+            if p[2] == ("varkw",): env.set(p[0], {k_: v for k_, v in kw.items() if k_ not in named})      # kw...: the keywords nobody named
+            elif i < len(pos): env.set(p[0], pos[i])
             elif p[0] in kw: env.set(p[0], kw[p[0]])
             else: env.set(p[0], self.eval(p[2], env))
-        for k_, v in kw.items(): env.set(k_, v)
         try:
             return self.exec_block(m.body, env)
         except ReturnEx as r:
@@ -1427,6 +1529,10 @@ class Interp:
             if pos and pos[0] == "UniformScaling": return np.eye(int(pos[1]), dtype=dt)
             raise JuliaError("jl_subset: unsupported %s constructor call" % n)
         if n == "Dict": return dict(pos[0]) if pos else {}
+        if n == "Ref": return JRef(pos[0] if pos else None)
+        if n == "Ptr": return pos[0]
+        if n in ("Int32", "UInt32", "UInt64", "UInt8", "Int8", "Int16", "UInt16"): return int(pos[0])
+        if n == "BoundsError": return JuliaError("BoundsError")
         if n == "String": return str(pos[0])
         if n in ("ErrorException", "ArgumentError", "DomainError", "AssertionError"): return JuliaError(str(pos[0]) if pos else n)
         raise JuliaError("jl_subset: cannot construct " + n)

@@ -6,8 +6,10 @@
 # written against QSim keeps working after `s = statevector(n, m)` is replaced by
 # `s = B200State(n, m)`.
 #
-# STATUS: Julia is not installed in the build image or on the GPU box, so this file has been
-# reviewed against include/qm_b200.h but NEVER EXECUTED.  The same ABI is exercised by the Python
+# STATUS: Julia is not installed in the build image or on the GPU box, so this file has NEVER RUN UNDER A JULIA RUNTIME.
+# It is parsed and its host logic executed by the Julia-subset interpreter oracle/jl_subset.py on top of the reference's own
+# source, with ccall recorded: every ccall is checked against include/qm_b200.h (tests/test_julia_shim_static.py) and the calls
+# it makes are compared one by one with the Python mirror's (tests/test_julia_shim_exec.py).  The same ABI is exercised by the Python
 # mirror quromorphic.jl_b200/qsim.py, which is what tests/ run.  Every conversion below (1-based
 # qubit -> 0-based bit, the reference's control map, argument checks and their order) is the same
 # code as in qsim.py, where it is tested.
@@ -16,7 +18,10 @@ module B200QSim
 using Quromorphic.QSim: H, X, Y, Z, I2, rx_gate, ry_gate, rz_gate
 import Quromorphic.QSim: nb, u2!, h!, x!, y!, z!, rx!, ry!, rz!, controlled!, cnot!, crx!, cry!, crz!,
                           swap!, mp, measure_z, measure_x, measure_y, prstate,
-                          density_matrix, statevector_to_density_matrix      # new METHODS of the reference's functions
+                          statevector_to_density_matrix                      # new METHODS of the reference's functions
+# (not `density_matrix`: its reference method takes (::Int, ::Int) and nothing of ours — a method with that signature would
+#  REPLACE the reference's own, keyword arguments do not take part in dispatch; `B200Density(q, m)` is the constructor instead,
+#  as `B200State(n, m)` stands for `statevector(n, m)`.  Found by executing this file: tests/test_julia_shim_exec.py)
 import Quromorphic.QInfo: partial_trace, entanglement_entropy, von_neumann_entropy
 
 export B200State, B200Density, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, apply_circuit_expect_z!, precompile_circuit!, jit_cache_dir, QMGate
@@ -252,10 +257,10 @@ struct B200Density
     q::Int
     mode::Symbol
 end
-density_matrix(q::Int, m::Int; mode = :reference, kw...) =
-    B200Density(B200State(2q, m * ((1 << q) + 1); mode = :corrected, kw...), q, mode)      # QSim.jl:43-46
+B200Density(q::Int, m::Int = 0; mode::Symbol = :reference, kw...) =
+    B200Density(B200State(2q, m * ((1 << q) + 1); mode = :corrected, kw...), q, mode)      # density_matrix(q, m), QSim.jl:43-46
 function statevector_to_density_matrix(s::B200State)                                          # QSim.jl:39-41
-    rho = density_matrix(s.n, 0; mode = s.mode)
+    rho = B200Density(s.n, 0; mode = s.mode)
     check(ccall((:qm_dm_from_state, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), s.handle, rho.vec.handle))
     rho
 end

@@ -1,0 +1,170 @@
+"""The Julia shim EXECUTED (CPU only): quromorphic.jl_b200/julia/B200QSim.jl cannot run for real here — there is no Julia runtime and,
+in this suite, no GPU — but its host logic can: the Julia-subset interpreter (oracle/jl_subset.py) loads the reference's own
+QSim.jl / QInfo.jl, then the shim on top of them (its `import Quromorphic.QSim: u2!, ...` adds METHODS to the reference's functions,
+as in Julia), with `ccall` handed to a recorder instead of the library.  The same sequence of reference-API calls is then made
+through the tested Python mirror (qsim.py / qinfo.py) with ITS library object replaced by a recorder, and the two call logs must
+be identical: same C symbols in the same order, same 0-based bits after the reference's control/target map, same thresholds and
+batch indices, and bit-identical 2x2 matrices (rx_gate etc. are the reference's own functions on the Julia side, the mirror's on
+the Python side).  What the GPU suite establishes for the mirror therefore carries over to the shim call by call."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from oracle import jl_subset as J  # noqa: E402
+
+REF = os.environ.get("QM_REFERENCE_ROOT", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "src", "Quantum", "QSim.jl")),
+                                reason="the reference sources are not on this machine")
+
+MATRIX_ARGS = {"qm_apply_u2": (2,), "qm_apply_controlled": (3,), "qm_measure_with": (2,), "qm_expect_all_with": (1,), "qm_dm_measure": (2,)}
+HANDLE = 0xBEEF
+
+
+def make_calls(n, count, seed):
+    """a seeded sequence of reference-API calls (1-based qubits): (name, args)"""
+    rng = np.random.default_rng(seed)
+    calls = []
+    for _ in range(count):
+        k = int(rng.integers(0, 15))
+        t = int(rng.integers(1, n + 1))
+        c = int(rng.integers(1, n))
+        c = c + 1 if c >= t else c
+        th = float(rng.uniform(-6.3, 6.3))
+        if k < 4: calls.append((("h", "x", "y", "z")[k], (t,)))
+        elif k < 7: calls.append((("rx", "ry", "rz")[k - 4], (t, th)))
+        elif k == 7: calls.append(("cnot", (c, t)))
+        elif k < 11: calls.append((("crx", "cry", "crz")[k - 8], (c, t, th)))
+        elif k == 11: calls.append(("swap", (c, t)))
+        elif k == 12: calls.append((("measure_z", "measure_x", "measure_y")[int(rng.integers(0, 3))], (t,)))
+        elif k == 13: calls.append(("mp", ()))
+        else: calls.append(("partial_trace", (1 << (n - 2), 4, 1) if rng.random() < 0.5 else (4, 1 << (n - 2), 2)))
+    return calls
+
+
+def julia_log(n, m, calls, density):
+    import make_ref_exec_golden as MR
+    it = MR.load_reference()
+    it.modules["Quromorphic"] = it.globals
+    log = []
+
+    def handler(name, args):
+        rec = [name]
+        for i, a in enumerate(args):
+            if isinstance(a, J.JRef):
+                if name == "qm_create": a.value = HANDLE
+                rec.append("ref")
+            elif isinstance(a, np.ndarray):
+                if i in MATRIX_ARGS.get(name, ()):
+                    rec.append(tuple(np.ascontiguousarray(np.asarray(a, dtype=np.complex128).ravel(order="F")).view(np.float64).tolist()))
+                else:
+                    rec.append("out")
+            elif i in MATRIX_ARGS.get(name, ()) and a == 0: rec.append(None)          # Ptr{ComplexF64}(C_NULL)
+            elif a == HANDLE and i < 2: rec.append("H")
+            else: rec.append(a)
+        log.append(tuple(rec))
+        return 0
+
+    it.ccall_handler = handler
+    it.current_dir = os.path.join(ROOT, "quromorphic.jl_b200", "julia")
+    it.load_file(os.path.join(it.current_dir, "B200QSim.jl"))
+    it.using("B200QSim")
+    lines = ["s = B200Density(%d, %d)" % (n, m) if density else "s = B200State(%d, %d)" % (n, m)]
+    for name, args in calls:
+        a = ", ".join(repr(x) for x in args)
+        bang = "!" if name in ("h", "x", "y", "z", "rx", "ry", "rz", "cnot", "crx", "cry", "crz", "swap") else ""
+        lines.append("%s%s(s%s)" % (name, bang, ", " + a if a else ""))
+    it.run("\n".join(lines))
+    return log
+
+
+class FakeLib:
+    """stands in for the ctypes library object of quromorphic.jl_b200/_lib.py: records every call, returns QM_OK"""
+
+    def __init__(self, log): self._log = log
+
+    def __getattr__(self, name):
+        def call(*args):
+            rec = [name]
+            for i, a in enumerate(args):
+                if isinstance(a, C.c_void_p): rec.append("H")
+                elif i in MATRIX_ARGS.get(name, ()):
+                    rec.append(None if a is None else tuple(float(a[j]) for j in range(8)))
+                elif isinstance(a, (int, np.integer)): rec.append(int(a))
+                elif isinstance(a, float): rec.append(a)
+                elif a is None: rec.append(None)
+                elif type(a).__name__ == "CArgObject": rec.append("ref")
+                else: rec.append("out")
+            self._log.append(tuple(rec))
+            return 0
+        return call
+
+
+def python_log(pkg, n, m, calls, density):
+    L, Q, QI = pkg._lib, pkg.qsim, pkg.qinfo
+    log = []
+    saved = L._lib
+    L._lib = FakeLib(log)
+    try:
+        s = Q.density_matrix(n, m) if density else Q.statevector(n, m)
+        for name, args in calls:
+            if name == "partial_trace": QI.partial_trace(s, *args)
+            else: getattr(Q, name)(s, *args)
+        # the recorder must not be asked to destroy anything after it has been taken away
+        for obj in ([s.vec] if density else [s]):
+            obj._h = None
+    finally:
+        L._lib = saved
+    return log
+
+
+def normalise(log, density):
+    out = []
+    for rec in log:
+        if rec[0] == "qm_destroy": continue
+        out.append(tuple("H" if (i in (1, 2) and x == "H") else x for i, x in enumerate(rec)))
+    return out
+
+
+@pytest.mark.parametrize("n,m,seed", [(5, 3, 1), (7, 0, 2), (4, 9, 3)])
+def test_shim_and_python_mirror_make_the_same_library_calls(pkg, n, m, seed):
+    calls = make_calls(n, 80, seed)
+    jl = normalise(julia_log(n, m, calls, False), False)
+    py = normalise(python_log(pkg, n, m, calls, False), False)
+    assert len(jl) == len(py) and len(jl) > 80
+    for a, b in zip(jl, py):
+        assert a == b, (a, b)
+
+
+@pytest.mark.parametrize("q,m,seed", [(3, 2, 4), (4, 0, 5)])
+def test_shim_and_python_mirror_agree_on_density_matrices(pkg, q, m, seed):
+    """Matrix{ComplexF64} methods: rho on q qubits is a 2q-qubit register holding vec(rho); op on the row bits, conj(op) on the column bits"""
+    calls = [c for c in make_calls(q, 70, seed) if c[0] != "partial_trace"]
+    jl = normalise(julia_log(q, m, calls, True), True)
+    py = normalise(python_log(pkg, q, m, calls, True), True)
+    assert len(jl) == len(py) and len(jl) > 70
+    for a, b in zip(jl, py):
+        assert a == b, (a, b)
+
+
+def test_shim_checks_arguments_like_the_reference(pkg):
+    """range first, then c == t (QSim.jl:177-178), as ErrorExceptions; the shim also rejects t < 1"""
+    import make_ref_exec_golden as MR
+    it = MR.load_reference()
+    it.modules["Quromorphic"] = it.globals
+    it.ccall_handler = lambda name, args: ([setattr(a, "value", HANDLE) for a in args if isinstance(a, J.JRef)], 0)[1]
+    it.current_dir = os.path.join(ROOT, "quromorphic.jl_b200", "julia")
+    it.load_file(os.path.join(it.current_dir, "B200QSim.jl"))
+    it.using("B200QSim")
+    it.run("s = B200State(3, 0)")
+    for src, msg in (("h!(s, 4)", "out of range"), ("h!(s, 0)", "out of range"), ("cnot!(s, 2, 2)", "same qubit"), ("cnot!(s, 4, 4)", "out of range"),
+                     ("crz!(s, 1, 5, 0.1)", "out of range"), ("swap!(s, 0, 1)", "out of range"), ("measure_z(s, 9)", "out of range"),
+                     ("B200State(2, 4)", "BoundsError")):
+        with pytest.raises(J.JuliaError, match=msg):
+            it.run(src)
+    assert it.run("swap!(s, 2, 2) === s") is True
