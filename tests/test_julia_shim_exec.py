@@ -31,7 +31,7 @@ def make_calls(n, count, seed):
     rng = np.random.default_rng(seed)
     calls = []
     for _ in range(count):
-        k = int(rng.integers(0, 15))
+        k = int(rng.integers(0, 18))
         t = int(rng.integers(1, n + 1))
         c = int(rng.integers(1, n))
         c = c + 1 if c >= t else c
@@ -43,6 +43,9 @@ def make_calls(n, count, seed):
         elif k == 11: calls.append(("swap", (c, t)))
         elif k == 12: calls.append((("measure_z", "measure_x", "measure_y")[int(rng.integers(0, 3))], (t,)))
         elif k == 13: calls.append(("mp", ()))
+        elif k == 15: calls.append(("expect_z_all", ()))
+        elif k == 16: calls.append(("expect_all", (("z", "x", "y")[int(rng.integers(0, 3))],)))
+        elif k == 17: calls.append(("sample", (int(rng.integers(1, 1 << 40)), int(rng.integers(1, 200)))))
         else: calls.append(("partial_trace", (1 << (n - 2), 4, 1) if rng.random() < 0.5 else (4, 1 << (n - 2), 2)))
     return calls
 
@@ -76,7 +79,7 @@ def julia_log(n, m, calls, density):
     it.using("B200QSim")
     lines = ["s = B200Density(%d, %d)" % (n, m) if density else "s = B200State(%d, %d)" % (n, m)]
     for name, args in calls:
-        a = ", ".join(repr(x) for x in args)
+        a = ", ".join((":" + x) if isinstance(x, str) else repr(x) for x in args)          # a str is a Symbol (:x)
         bang = "!" if name in ("h", "x", "y", "z", "rx", "ry", "rz", "cnot", "crx", "cry", "crz", "swap") else ""
         lines.append("%s%s(s%s)" % (name, bang, ", " + a if a else ""))
     it.run("\n".join(lines))
@@ -114,6 +117,7 @@ def python_log(pkg, n, m, calls, density):
         s = Q.density_matrix(n, m) if density else Q.statevector(n, m)
         for name, args in calls:
             if name == "partial_trace": QI.partial_trace(s, *args)
+            elif name in ("expect_z_all", "expect_all", "sample"): getattr(s, name)(*args)
             else: getattr(Q, name)(s, *args)
         # the recorder must not be asked to destroy anything after it has been taken away
         for obj in ([s.vec] if density else [s]):
@@ -144,10 +148,10 @@ def test_shim_and_python_mirror_make_the_same_library_calls(pkg, n, m, seed):
 @pytest.mark.parametrize("q,m,seed", [(3, 2, 4), (4, 0, 5)])
 def test_shim_and_python_mirror_agree_on_density_matrices(pkg, q, m, seed):
     """Matrix{ComplexF64} methods: rho on q qubits is a 2q-qubit register holding vec(rho); op on the row bits, conj(op) on the column bits"""
-    calls = [c for c in make_calls(q, 70, seed) if c[0] != "partial_trace"]
+    calls = [c for c in make_calls(q, 70, seed) if c[0] not in ("partial_trace", "expect_z_all", "expect_all", "sample")]
     jl = normalise(julia_log(q, m, calls, True), True)
     py = normalise(python_log(pkg, q, m, calls, True), True)
-    assert len(jl) == len(py) and len(jl) > 70
+    assert len(jl) == len(py) and len(jl) > 60
     for a, b in zip(jl, py):
         assert a == b, (a, b)
 
