@@ -42,6 +42,11 @@ class JRange:
         return len(self.values())
 
 
+class UniformScaling:
+    """c * I of LinearAlgebra: takes the size of the matrix it is added to"""
+    def __init__(self, c): self.c = c
+
+
 class Hermitian:
     def __init__(self, a):
         self.a = np.asarray(a)
@@ -74,7 +79,7 @@ class ContinueEx(Exception):
 
 
 # ------------------------------------------------------------------------------------------------ tokenizer
-OPS = [".==", ".!=", ".<=", ".>=", "...", "===", "!==", "==", "!=", "<=", ">=", "&&", "||", "<<", ">>", "+=", "-=", "*=", "/=", "->", "::", "=>",
+OPS = [".+=", ".-=", ".*=", "./=", ".==", ".!=", ".<=", ".>=", "...", "===", "!==", ".=", "==", "!=", "<=", ">=", "&&", "||", "<<", ">>", "+=", "-=", "*=", "/=", "->", "::", "=>",
        ".≈", ".+", ".-", ".*", "./", ".^", ".<", ".>", "+", "-", "*", "/", "\\", "^", "%", "÷", "<", ">", "=", "!", "&", "|", "?", ":", ",",
        ";", "(", ")", "[", "]", "{", "}", ".", "'", "@", "≈", "√", "≤", "≥", "≠", "$"]
 KEYWORDS = {"function", "end", "if", "elseif", "else", "for", "while", "return", "const", "module", "using", "import", "export", "begin", "in",
@@ -277,7 +282,7 @@ class Parser:
             self.next(); return ("nop",)
         e = self.expr_or_tuple()
         tok = self.peek()
-        if tok.kind == "op" and tok.val in ("=", "+=", "-=", "*=", "/="):
+        if tok.kind == "op" and tok.val in ("=", "+=", "-=", "*=", "/=", ".=", ".+=", ".-=", ".*=", "./="):
             self.next()
             while self.t[self.i].kind == "nl": self.i += 1
             rhs = self.statement_rhs()
@@ -991,11 +996,22 @@ class Interp:
             "axes": lambda a, d: JRange(1, int(a.shape[int(d) - 1])), "eachindex": lambda a: JRange(1, int(np.size(a))), "enumerate": lambda x: [(i + 1, v) for i, v in enumerate(self._iter(x))],
             "zip": lambda *xs: list(zip(*[list(self._iter(x)) for x in xs])), "keys": lambda d: list(d.keys()), "values": lambda d: list(d.values()),
             "dot": lambda a, b: self._scalar(np.vdot(np.asarray(a), np.asarray(b))),
+            "vcat": lambda *xs: np.vstack([np.atleast_2d(x) if np.ndim(x) == 2 else np.asarray(x).reshape(-1, 1) for x in xs]) if any(np.ndim(x) == 2 for x in xs) else np.concatenate([np.atleast_1d(x) for x in xs]),
+            "hcat": lambda *xs: np.hstack([x if np.ndim(x) == 2 else np.asarray(x).reshape(-1, 1) for x in xs]),
+            "mean": lambda x: self._scalar(np.mean(arr(x))), "tanh": lambda x: math.tanh(x), "view": self._view,
             "finalizer": lambda f, obj: obj, "pointer": lambda a: a, "C_NULL": 0, "undef": "undef", "ENV": dict(__import__("os").environ),
             "get": lambda d, k, default=None: d.get(k, default), "joinpath": lambda *a: __import__("os").path.join(*a),
             "throw": self._throw, "isnothing": lambda x: x is None,
             "rand": self._no_random, "randn": self._no_random,
         })
+
+    def _view(self, a, *idx):
+        key = []
+        for d, v in enumerate(idx):
+            if isinstance(v, str) and v == "colon": key.append(slice(None))
+            elif isinstance(v, JRange): key.append(slice(int(v.start) - 1, int(v.stop)))
+            else: key.append(int(v) - 1)
+        return a[tuple(key)]
 
     def _throw(self, ex):
         raise ex if isinstance(ex, JuliaError) else JuliaError(str(ex))
@@ -1196,6 +1212,18 @@ class Interp:
 
     def assign(self, op, target, rhs_node, env):
         rhs = self.eval(rhs_node, env) if rhs_node[0] != "assignx" else self.assign("=", rhs_node[1], rhs_node[2], env)
+        if op.startswith("."):                               # a .= b, a .*= b ...: element-wise INTO the array a names (no rebinding)
+            if target[0] == "index":
+                arr = self.eval(target[1], env)
+                key = self.index_key(arr, target[2], env)
+                cur = arr[key]
+                arr[key] = rhs if op == ".=" else self.binop(op[:2], cur, rhs)
+                return arr
+            dst = self.eval(target, env)
+            if not isinstance(dst, np.ndarray): raise JuliaError("jl_subset: broadcast assignment to a non-array")
+            val = rhs if op == ".=" else self.binop(op[:2], dst, rhs)
+            dst[...] = self._jl_broadcast_to(val, dst)
+            return dst
         if op != "=":
             cur = self.eval(target, env)
             b = op[0]
@@ -1383,8 +1411,17 @@ class Interp:
     def binop(self, op, a, b):
         if isinstance(a, JRange) and op in ("+", "-", "*", ".+", ".-", ".*", "./"): a = np.asarray(a.values())
         if isinstance(b, JRange) and op in ("+", "-", "*", ".+", ".-", ".*", "./"): b = np.asarray(b.values())
-        if isinstance(a, str) and a == "UniformScaling": a = np.eye(b.shape[0]) if isinstance(b, np.ndarray) else 1     # LinearAlgebra.I
-        if isinstance(b, str) and b == "UniformScaling": b = np.eye(a.shape[0]) if isinstance(a, np.ndarray) else 1
+        if isinstance(a, str) and a == "UniformScaling": a = UniformScaling(1)      # LinearAlgebra.I
+        if isinstance(b, str) and b == "UniformScaling": b = UniformScaling(1)
+        if isinstance(a, UniformScaling) or isinstance(b, UniformScaling):
+            if op == "*":
+                if isinstance(a, UniformScaling) and isinstance(b, UniformScaling): return UniformScaling(a.c * b.c)
+                if isinstance(a, UniformScaling): return UniformScaling(a.c * b) if not isinstance(b, np.ndarray) else a.c * b
+                return UniformScaling(a * b.c) if not isinstance(a, np.ndarray) else a * b.c
+            if op in ("+", "-"):
+                if isinstance(a, np.ndarray): b = b.c * np.eye(a.shape[0])
+                elif isinstance(b, np.ndarray): a = a.c * np.eye(b.shape[0])
+                else: raise JuliaError("MethodError: UniformScaling %s non-matrix" % op)
         if op == "+":
             if isinstance(a, Hermitian): a = a.a
             if isinstance(b, Hermitian): b = b.a
@@ -1413,12 +1450,26 @@ class Interp:
         if op == ">>": return int(a) >> int(b)
         if op in (".+", ".-", ".*", "./", ".^"):
             a_ = a.a if isinstance(a, Hermitian) else a; b_ = b.a if isinstance(b, Hermitian) else b
+            a_, b_ = self._jl_align(a_, b_)
             if op == ".+": return a_ + b_
             if op == ".-": return a_ - b_
             if op == ".*": return a_ * b_
             if op == "./": return a_ / b_
             return np.power(a_, b_)
         raise JuliaError("jl_subset: operator %s" % op)
+
+    @staticmethod
+    def _jl_broadcast_to(val, dst):
+        """a Julia Vector is a column: against a matrix it spreads along the columns (numpy would spread a 1-D array along rows)"""
+        if isinstance(val, np.ndarray) and val.ndim == 1 and dst.ndim == 2: return val.reshape(-1, 1)
+        return val
+
+    @staticmethod
+    def _jl_align(a, b):
+        if isinstance(a, np.ndarray) and isinstance(b, np.ndarray):
+            if a.ndim == 2 and b.ndim == 1: b = b.reshape(-1, 1)
+            elif a.ndim == 1 and b.ndim == 2: a = a.reshape(-1, 1)
+        return a, b
 
     def broadcast(self, f, args, kw):
         args = [np.asarray(a.values()) if isinstance(a, JRange) else (a.a if isinstance(a, Hermitian) else a) for a in args]

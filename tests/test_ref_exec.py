@@ -296,3 +296,35 @@ def test_host_qinfo_mirrors_agree_with_the_executed_reference(pkg, ref):
             assert abs(getattr(QI, name)(rho, dA, dB) - R(name, rho, dA, dB)) < 1e-9, (dA, dB, name)
         for sub in (1, 2):
             assert np.max(np.abs(QI.partial_trace_matrix(rho, dA, dB, sub) - R("partial_trace", rho, dA, dB, sub))) < 1e-14
+
+
+@needs_ref
+def test_lsm_driver_and_ridge_readout_agree_with_the_executed_reference(pkg):
+    """src/Neuromorphic/LSM.jl executed (struct, step!, collect_states, train_readout!, predict with INJECTED weights — its own
+    constructor draws them from Julia's MersenneTwister stream, which nothing here can reproduce) against the host mirrors
+    reservoir.LSMNet / ridge_readout that drive config C5 (LSM.jl:7-19, :39-72)"""
+    it = J.Interp()
+    it.load_file(os.path.join(REF, "src", "Neuromorphic", "LSM.jl"))
+    it.using("LSM")
+    g = it.globals.vars
+    rng = np.random.default_rng(5)
+    N, D, O, T = 24, 3, 2, 50
+    Win = rng.uniform(-1, 1, (N, D))
+    Wres = rng.uniform(-1, 1, (N, N)) * (rng.random((N, N)) < 0.2)
+    Wres *= 0.9 / max(abs(np.linalg.eigvals(Wres)))
+    inputs, targets = rng.uniform(0, 1, (D, T)), rng.normal(size=(O, T))
+    lsm = it.call(g["LSMNet"], [D, N, O, 0.2, 0.9, 0.3, Win.copy(), Wres.copy(), np.zeros((O, N)), np.zeros(O), np.zeros(N)])
+    states = it.call(g["collect_states"], [lsm, inputs])
+    assert abs(it.call(g["get_spectral_radius"], [lsm]) - 0.9) < 1e-12
+    R = pkg.reservoir
+    mirror = R.LSMNet(Win, Wres, leak_rate=0.3, output_dim=O)
+    st2 = mirror.collect_states(inputs)
+    assert states.shape == st2.shape == (N, T) and np.max(np.abs(states - st2)) < 1e-14
+    it.call(g["train_readout!"], [lsm, inputs, targets], {"reg": 1e-6})
+    pred = it.call(g["predict"], [lsm, inputs])
+    Wout, bout = R.ridge_readout(st2, targets, 1e-6)
+    scale = np.max(np.abs(Wout))
+    assert np.max(np.abs(Wout - lsm.fields["Wout"])) < 1e-8 * scale and np.max(np.abs(bout - lsm.fields["bout"])) < 1e-8 * scale
+    assert np.max(np.abs(Wout @ st2 + bout[:, None] - pred)) < 1e-9 * max(1.0, np.max(np.abs(pred)))
+    it.call(g["reset!"], [lsm])
+    assert not lsm.fields["state"].any()
