@@ -291,11 +291,11 @@ class Parser:
                 fname = callee[1] if callee[0] == "id" else (callee[2] if callee[0] == "field" else (callee if callee[0] == "interp" else None))   # Base.length(x) = ... / $f(x) = ...
                 params = []
                 for a in e[2]:
-                    if a[0] == "splat": params.append((a[1][1] if a[1][0] == "id" else "_", None, ("varkw",)))
+                    if a[0] == "splat": params.append((a[1][1] if a[1][0] == "id" else "_", None, ("varkw",), True))
                     elif a[0] == "eqarg": nm = self.param(a[1]); params.append((nm[0], nm[1], a[2]))
                     else: params.append(self.param(a))
-                for k_, v_ in e[3].items():
-                    params.append((k_, v_[1], v_[2]) if v_[0] == "kwtyped" else (k_, None, v_))
+                for k_, v_ in e[3].items():                  # after the semicolon: keyword-only
+                    params.append((k_, v_[1], v_[2], True) if v_[0] == "kwtyped" else (k_, None, v_, True))
                 return ("function", fname, params, ("block", [("return", rhs)]))
             return ("assign", tok.val, e, rhs)
         return ("expr", e)
@@ -324,16 +324,16 @@ class Parser:
                 if depth == 0: break
         self.expect("(")
         self.no_nl += 1
-        params = []
+        params, kwonly = [], False
         while not self.at(")"):
-            if self.accept(";"): continue
+            if self.accept(";"): kwonly = True; continue     # parameters after the semicolon can only be given by name
             a = self.expr()
-            if self.accept("..."):                          # kw... / args...: collected, never used by the files this runs
-                params.append((a[1] if a[0] == "id" else "_", None, ("varkw",)))
+            if self.accept("..."):                          # kw...: the keywords nobody named
+                params.append((a[1] if a[0] == "id" else "_", None, ("varkw",), True))
                 if not self.accept(","): break
                 continue
             if self.accept("="): a = ("kwarg", a, self.expr())
-            params.append(self.param(a))
+            params.append(self.param(a) + ((True,) if kwonly else ()))
             if not self.accept(","):
                 if self.at(";"): continue
                 break
@@ -1204,9 +1204,10 @@ class Interp:
         if not isinstance(gf, GenericFunction):
             base = self.globals.vars.get(name)
             gf = GenericFunction(name, base if not isinstance(base, GenericFunction) else None); env.set(name, gf)
-        ps = [(p[0], p[1], p[2]) for p in params]
-        sig = [repr(p[1]) for p in ps]
-        gf.methods = [m for m in gf.methods if [repr(p[1]) for p in m.params] != sig]
+        ps = [tuple(p) for p in params]
+        # a definition with the positional signature of an existing method REPLACES it (keyword parameters do not take part in dispatch)
+        sig = [repr(p[1]) for p in ps if len(p) < 4]
+        gf.methods = [m for m in gf.methods if [repr(p[1]) for p in m.params if len(p) < 4] != sig]
         gf.methods.append(Method(ps, body, env))
         return gf
 
@@ -1521,10 +1522,11 @@ class Interp:
         if isinstance(f, GenericFunction):
             best, best_score = None, -1
             for m in f.methods:
-                req = [p for p in m.params if p[2] is None]
-                if len(pos) < len(req) or len(pos) > len([p for p in m.params if p[2] != ("varkw",)]): continue
+                positional = [p for p in m.params if len(p) < 4]            # keyword-only parameters never take a positional argument
+                req = [p for p in positional if p[2] is None]
+                if len(pos) < len(req) or len(pos) > len(positional): continue
                 score, ok = 0, True
-                for p, v in zip(m.params, pos):
+                for p, v in zip(positional, pos):
                     s = type_match(v, p[1])
                     if s < 0: ok = False; break
                     score += s
@@ -1550,10 +1552,12 @@ class Interp:
         env = Env(m.env)
         env.is_function_root = True
         named = {p[0] for p in m.params}
-        for i, p in enumerate(m.params):
+        i = 0
+        for p in m.params:
             if p[2] == ("varkw",): env.set(p[0], {k_: v for k_, v in kw.items() if k_ not in named})      # kw...: the keywords nobody named
-            elif i < len(pos): env.set(p[0], pos[i])
+            elif len(p) < 4 and i < len(pos): env.set(p[0], pos[i]); i += 1
             elif p[0] in kw: env.set(p[0], kw[p[0]])
+            elif p[2] is None: raise JuliaError("UndefKeywordError: keyword argument %s not assigned" % p[0])
             else: env.set(p[0], self.eval(p[2], env))
         try:
             return self.exec_block(m.body, env)

@@ -118,6 +118,11 @@ def test_shim_methods_extend_real_reference_functions_with_matching_arity(shim_a
         mine = len([p for p in st[2] if p[2] is None])
         # QInfo functions take the matrix rho; the shim's methods take the state instead of rho: same positional count
         assert mine in ref_arities, "%s: the shim's method takes %d positional arguments, the reference's take %s" % (st[1], mine, sorted(ref_arities))
+        # ... and must not have the positional SIGNATURE of one of the reference's own methods: it would replace that method
+        # (keyword parameters do not take part in dispatch) — how `density_matrix(q::Int, m::Int; ...)` was caught
+        my_sig = [repr(p[1]) for p in st[2] if len(p) < 4]
+        for m in ref_fn.methods:
+            assert [repr(p[1]) for p in m.params if len(p) < 4] != my_sig, "%s%s would replace the reference's own method" % (st[1], tuple(my_sig))
         checked += 1
     assert checked >= 25
 

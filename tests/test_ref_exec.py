@@ -142,6 +142,52 @@ def test_adjoint_outer_product_broadcast_and_linear_algebra():
     assert np.allclose(g["vals"], [0.0, 1.0])
 
 
+def test_structs_refs_keywords_and_broadcast_assignment():
+    """what the shim and LSM.jl need on top of QSim.jl: (mutable) structs with outer constructors, Ref boxes, ccall through a hook,
+    optional positional against keyword parameters, kw... forwarding, `.=` / `.*=` into an existing array with a Vector spreading
+    along columns, I as UniformScaling"""
+    it = J.Interp()
+    log = []
+    it.ccall_handler = lambda name, args: (log.append((name, [a.value if isinstance(a, J.JRef) else a for a in args])),
+                                            [setattr(a, "value", 7) for a in args if isinstance(a, J.JRef)], 0)[2]
+    it.run("""
+    const LIB = "libsomething.so"
+    mutable struct Box
+        h::Ptr{Cvoid}
+        n::Int
+        mode::Symbol
+    end
+    function Box(n::Int, m::Int = 0; mode::Symbol = :reference, scale = 1)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        ccall((:make, LIB), Int32, (Int32, Int32, Ptr{Ptr{Cvoid}}), n * scale, m, r)
+        Box(r[], n, mode)
+    end
+    wrap(n; kw...) = Box(n, 1; kw...)
+    pick(c::Int, t::Int) = (b = max(c, t); c < t ? (b - 1, b) : (b, b - 1))
+    a = Box(3)
+    b = wrap(4; mode = :corrected, scale = 2)
+    b.n = 9
+    same = a.mode === :reference && b.mode === :corrected
+    p = pick(1, 4); q = pick(4, 1)
+    M = zeros(2, 3)
+    v = [1.0, 2.0]
+    M .= v
+    M .*= 2
+    M[:, 2] .= [5.0, 6.0]
+    A = [1.0 2.0; 3.0 4.0] + 0.5 * I
+    early(x) = (x > 0 && return "positive"; "other")
+    e1 = early(1); e2 = early(-1)
+    """, it.globals)
+    g = it.globals.vars
+    assert log == [("make", [3, 0, 0]), ("make", [8, 1, 0])]
+    assert g["a"].fields == {"h": 7, "n": 3, "mode": "reference"} and g["b"].fields["n"] == 9 and g["same"] is True
+    assert g["p"] == (3, 4) and g["q"] == (4, 3)
+    assert g["M"].tolist() == [[2.0, 5.0, 2.0], [4.0, 6.0, 4.0]] and g["A"].tolist() == [[1.5, 2.0], [3.0, 4.5]]
+    assert (g["e1"], g["e2"]) == ("positive", "other")
+    with pytest.raises(J.JuliaError, match="MethodError"):
+        it.run('Box("x")')
+
+
 # ---- the reference executed ----------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def ref():
