@@ -92,14 +92,16 @@ def test_c_oracle_reproduces_golden_vectors(src_case):
 def test_encoded_tma_programs_reproduce_the_12_qubit_golden_case(pkg, emu_mode):
     """planner + encoder of the fused TMA kernel against the literal algorithm, without a GPU: the 12-qubit golden
     case as a wire-format gate list, walked by the host emulator of the encoded pass programs (csrc/emulate.hpp)"""
-    case = next(c for c in REF_EXEC_CASES if c["n"] == 12)
-    gl = pkg.circuits.GateList(12, "reference")
-    replay_gl = lambda op: getattr(gl, op[0])(*op[1:-1], float.fromhex(op[-1])) if isinstance(op[-1], str) else getattr(gl, op[0])(*op[1:])
-    for op in case["ops"]:
-        replay_gl(op)
-    got, npass = emu.plan_emulate(12, gl.array(), O.statevector(12, case["m"]), max_cost=75.0)
-    want = unhexc(case["amps"])
-    assert npass >= 1 and np.max(np.abs(got - want)) <= RTOL * np.max(np.abs(want))
+    cases12 = [c for c in REF_EXEC_CASES if c["n"] == 12]
+    assert len(cases12) == 2                              # the mixed case and three time steps of config C1
+    for case in cases12:
+        gl = pkg.circuits.GateList(12, "reference")
+        replay_gl = lambda op: getattr(gl, op[0])(*op[1:-1], float.fromhex(op[-1])) if isinstance(op[-1], str) else getattr(gl, op[0])(*op[1:])
+        for op in case["ops"]:
+            replay_gl(op)
+        got, npass = emu.plan_emulate(12, gl.array(), O.statevector(12, case["m"]), max_cost=75.0)
+        want = unhexc(case["amps"])
+        assert npass >= 1 and np.max(np.abs(got - want)) <= RTOL * np.max(np.abs(want)), case["name"]
 
 
 @pytest.mark.gpu
