@@ -45,8 +45,13 @@ def replay(B, s, ops):
     return s
 
 
-def check_case(case, amps, mp, mz, mx, my, reduced, entropy):
+def check_case(case, amps, mp, mz, mx, my, reduced, entropy, all_qubits=None):
     n = case["n"]
+    # the all-qubit readouts (one call for every qubit: no reference counterpart of their own) against the per-qubit goldens
+    for basis, fn in (all_qubits or {}).items():
+        want = np.array([unhex(v) for v in case["measure_" + basis]])
+        got = np.asarray(fn())
+        assert got.shape == (n, 2) and np.max(np.abs(got - want)) <= RTOL, (case["name"], "all-qubit " + basis)
     want = unhexc(case["amps"])
     if case["name"].endswith("permutations_only"):
         assert np.array_equal(amps, want)
@@ -86,7 +91,8 @@ def test_c_oracle_reproduces_golden_vectors(src_case):
     check_case(case, s, O.mp(s),
                lambda t: O.measure_z(s, t, 1e-10, True), lambda t: O.measure_x(s, t, 1e-10, True),
                lambda t: O.measure_y(s, t, 1e-10, True),
-               lambda keep_low, k: O.reduced_density(np.ascontiguousarray(s), keep_low, k), LIT.von_neumann_entropy)
+               lambda keep_low, k: O.reduced_density(np.ascontiguousarray(s), keep_low, k), LIT.von_neumann_entropy,
+               all_qubits={"z": lambda: O.expect_z_all(s, 1e-10)})
 
 
 def test_encoded_tma_programs_reproduce_the_12_qubit_golden_case(pkg, emu_mode):
@@ -118,4 +124,5 @@ def test_cuda_path_reproduces_golden_vectors(pkg, src_case):
             return QI.partial_trace(s, 1 << (n - k), 1 << k, 1)
         return QI.partial_trace(s, 1 << k, 1 << (n - k), 2)
     check_case(case, s.to_numpy(), Q.mp(s), lambda t: Q.measure_z(s, t), lambda t: Q.measure_x(s, t),
-               lambda t: Q.measure_y(s, t), reduced, QI.von_neumann_entropy)
+               lambda t: Q.measure_y(s, t), reduced, QI.von_neumann_entropy,
+               all_qubits={"z": lambda: s.expect_z_all(), "x": lambda: s.expect_all("x"), "y": lambda: s.expect_all("y")})
