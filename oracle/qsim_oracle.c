@@ -20,9 +20,10 @@
  *       and every (c, t) pair on small registers, and
  *   (3) the committed golden vectors tests/golden/qsim_golden.json (written by tests/golden/make_golden.py
  *       from that literal transcription; tests/test_golden.py), which agree with the executed-source vectors to 2e-15.
- * What no reference test or literal counterpart pins ("parity unpinned"): the all-qubit
- * expectation call, fused/batched application, psi -> reduced rho without forming rho, and the sampler — there
- * this file is the definition.
+ * Calls without a reference counterpart of their own: the all-qubit expectation call is held to the executed reference's
+ * per-qubit measure_z of the golden cases, psi -> reduced rho to its partial_trace(s*s', ...) of the same cases, fused/batched
+ * application to gate-by-gate application.  "Parity unpinned" in the strict sense remains only the
+ * sampler — there this file is the definition.
  *
  * Conventions: qubit arguments are the reference's own 1-BASED indices (qubit t <-> bit t-1 of
  * the 0-based amplitude index, QSim.jl:56-58, :304).  States are interleaved (re, im) doubles.
