@@ -874,9 +874,11 @@ class TestLog:
 
 class Interp:
     ccall_handler = None
+    base_extensions = None
 
     def __init__(self):
         self.globals = Env()
+        self.base_extensions = {}
         self.modules = {}
         self.tests = TestLog()
         self.out = []
@@ -1204,6 +1206,7 @@ class Interp:
         if not isinstance(gf, GenericFunction):
             base = self.globals.vars.get(name)
             gf = GenericFunction(name, base if not isinstance(base, GenericFunction) else None); env.set(name, gf)
+            if gf.base is not None: self.base_extensions[name] = gf       # Base.length(x::MyType), Base.Vector{T}(x::MyType): seen from every scope
         ps = [tuple(p) for p in params]
         # a definition with the positional signature of an existing method REPLACES it (keyword parameters do not take part in dispatch)
         sig = [repr(p[1]) for p in ps if len(p) < 4]
@@ -1540,6 +1543,14 @@ class Interp:
                 raise JuliaError("MethodError: no method matching %s(%s)" % (f.name, ", ".join(repr(self._typeof(v)) for v in pos)))
             return self.invoke(best, pos, kw)
         if isinstance(f, Method): return self.invoke(f, pos, kw)
+        if any(isinstance(v, JObject) for v in pos):                # a builtin called on a struct instance: a module may have extended it
+            ext = self.base_extensions.get(f.name if isinstance(f, JType) else next((k_ for k_, v_ in self.globals.vars.items() if v_ is f), None))
+            if ext is not None and ext is not f:
+                g2 = GenericFunction(ext.name, None); g2.methods = ext.methods
+                try:
+                    return self.call(g2, pos, kw)
+                except JuliaError as ex:
+                    if "MethodError" not in str(ex): raise
         if isinstance(f, JType): return self.construct(f, pos, kw)
         if callable(f):
             try:

@@ -24,7 +24,7 @@ import Quromorphic.QSim: nb, u2!, h!, x!, y!, z!, rx!, ry!, rz!, controlled!, cn
 #  as `B200State(n, m)` stands for `statevector(n, m)`.  Found by executing this file: tests/test_julia_shim_exec.py)
 import Quromorphic.QInfo: partial_trace, entanglement_entropy, von_neumann_entropy
 
-export B200State, B200Density, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, apply_circuit_expect_z!, precompile_circuit!, jit_cache_dir, QMGate
+export B200State, B200Density, dist_unique_id, dist_ipc_export, dist_ipc_import!, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, apply_circuit_expect_z!, precompile_circuit!, jit_cache_dir, QMGate
 
 const LIB = get(ENV, "QM_B200_LIB", joinpath(@__DIR__, "..", "libqm_b200.so"))
 
@@ -76,6 +76,42 @@ function B200State(n::Int, m::Int = 0; batch::Int = 1, device::Int = 0, mode::Sy
     st
 end
 
+# ---- sharded registers: one Julia process per GPU (include/qm_b200.h, "sharded registers") ----------------------------------
+"128-byte id of a sharded register: rank 0 calls this and hands it to the other ranks (MPI.bcast, Distributed, a file ...)"
+function dist_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:qm_dist_unique_id, LIB), Int32, (Ptr{UInt8},), id))
+    id
+end
+
+"""
+    B200State(n, rank, world, id; m = 0, device = rank, mode = :reference, threshold = 1e-10)
+
+This rank's shard of an `n`-qubit register sharded over `world` GPUs (a power of two): the top log2(world) qubits select the
+rank.  Every gate and readout call of this file then works on the GLOBAL register as a collective call — all ranks make the same
+calls in the same order and get the same answers; `mp` and `Vector{ComplexF64}(st)` return this rank's contiguous slice.
+"""
+function B200State(n::Int, rank::Int, world::Int, id::Vector{UInt8}; m::Int = 0, device::Int = rank, mode::Symbol = :reference,
+                   threshold::Float64 = 1e-10)
+    length(id) == 128 || error("the id of a sharded register has 128 bytes (dist_unique_id)")
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qm_create_dist, LIB), Int32, (Int32, UInt64, Int32, Int32, Int32, Ptr{UInt8}, Ptr{Ptr{Cvoid}}),
+                n, m, device, rank, world, id, h))
+    st = B200State(h[], n, 1, mode, threshold, world)
+    finalizer(s -> (s.handle != C_NULL && ccall((:qm_destroy, LIB), Int32, (Ptr{Cvoid},), s.handle); s.handle = C_NULL), st)
+    st
+end
+
+"64 bytes every rank exports after creating its shard; all-gathered (world x 64 bytes, rank-major) they go to `dist_ipc_import!`"
+function dist_ipc_export(s::B200State)
+    hnd = Vector{UInt8}(undef, 64)
+    check(ccall((:qm_dist_ipc_export, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), s.handle, hnd))
+    hnd
+end
+"map the other ranks' shards into this process (peer memory over NVLink: the exchange runs beside the fused passes); false = the engine keeps NCCL"
+dist_ipc_import!(s::B200State, handles::Vector{UInt8}) =
+    ccall((:qm_dist_ipc_import, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), s.handle, handles) == 0
+
 "upload: `B200State(v)`"
 function B200State(v::Vector{ComplexF64}; kw...)
     n = round(Int, log2(length(v)))
@@ -85,9 +121,9 @@ function B200State(v::Vector{ComplexF64}; kw...)
     st
 end
 
-"download: `Vector{ComplexF64}(st)`"
+"download: `Vector{ComplexF64}(st)` (a sharded register: this rank's contiguous slice)"
 function Base.Vector{ComplexF64}(st::B200State; batch_idx::Int = 0)
-    v = Vector{ComplexF64}(undef, 1 << st.n)
+    v = Vector{ComplexF64}(undef, (1 << st.n) ÷ st.world)
     check(ccall((:qm_download, LIB), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, UInt64, Int32), st.handle, v, length(v), batch_idx))
     v
 end

@@ -172,3 +172,83 @@ def test_shim_checks_arguments_like_the_reference(pkg):
         with pytest.raises(J.JuliaError, match=msg):
             it.run(src)
     assert it.run("swap!(s, 2, 2) === s") is True
+
+
+def test_shim_sharded_register_calls_match_the_python_mirror(pkg):
+    """one rank of a sharded register: id, creation (argument ORDER of qm_create_dist), a few collective calls, the download of
+    this rank's slice (2^n / world amplitudes, not 2^n), the optional peer-memory export"""
+    import make_ref_exec_golden as MR
+    n, world, rank, m = 9, 4, 2, 5
+    it = MR.load_reference()
+    it.modules["Quromorphic"] = it.globals
+    jl = []
+
+    def handler(name, args):
+        rec = [name]
+        for i, a in enumerate(args):
+            if isinstance(a, J.JRef):
+                a.value = HANDLE; rec.append("ref")
+            elif isinstance(a, np.ndarray):
+                if i in MATRIX_ARGS.get(name, ()): rec.append("mat")
+                else: rec.append(("buf", int(a.size)))
+            elif a == HANDLE and i == 0: rec.append("H")
+            else: rec.append(a)
+        jl.append(tuple(rec))
+        return 0
+
+    it.ccall_handler = handler
+    it.current_dir = os.path.join(ROOT, "quromorphic.jl_b200", "julia")
+    it.load_file(os.path.join(it.current_dir, "B200QSim.jl"))
+    it.using("B200QSim")
+    it.run("""
+    id = dist_unique_id()
+    s = B200State(%d, %d, %d, id; m = %d, device = 1)
+    h!(s, 9); cnot!(s, 9, 1); crz!(s, 2, 8, 0.3)
+    z = expect_z_all(s)
+    p = measure_x(s, 9)
+    v = Vector{ComplexF64}(s)
+    pr = mp(s)
+    e = dist_ipc_export(s)
+    w = s.world
+    """ % (n, rank, world, m))
+    assert it.globals.vars["w"] == world and len(it.globals.vars["v"]) == (1 << n) // world == len(it.globals.vars["pr"])
+
+    L, Q = pkg._lib, pkg.qsim
+    py = []
+
+    class Rec:
+        def __getattr__(self, name):
+            def call(*args):
+                rec = [name]
+                for i, a in enumerate(args):
+                    if isinstance(a, C.c_void_p): rec.append("H")
+                    elif i in MATRIX_ARGS.get(name, ()): rec.append("mat" if a is not None else None)
+                    elif isinstance(a, (int, np.integer)): rec.append(int(a))
+                    elif isinstance(a, float): rec.append(a)
+                    elif type(a).__name__ == "CArgObject": rec.append("ref")
+                    elif isinstance(a, C.Array): rec.append(("buf", len(a)))
+                    else: rec.append(("buf", None))
+                py.append(tuple(rec))
+                return 0
+            return call
+
+    saved = L._lib
+    L._lib = Rec()
+    try:
+        idb = Q.B200State.unique_id()
+        s = Q.B200State.create_dist(n, rank, world, idb, m=m, device=1)
+        Q.h(s, 9); Q.cnot(s, 9, 1); Q.crz(s, 2, 8, 0.3)
+        s.expect_z_all()
+        Q.measure_x(s, 9)
+        v = s.to_numpy()
+        Q.mp(s)
+        s._h = None
+    finally:
+        L._lib = saved
+    assert len(v) == (1 << n) // world
+    # same symbols, same order, same scalars (buffers: only their presence; the Julia side also exported its IPC handle)
+    strip = lambda log: [tuple(x if not (isinstance(x, tuple) and x[0] == "buf") else "buf" for x in rec) for rec in log if rec[0] != "qm_destroy"]
+    a, b = strip(jl), strip(py)
+    assert a[-1][0] == "qm_dist_ipc_export" and a[:-1] == b, (a, b)
+    assert ("qm_create_dist", n, m, 1, rank, world, "buf", "ref") in a
+    assert ("qm_download", "H", "buf", (1 << n) // world, 0) in a
