@@ -25,7 +25,7 @@ class JType:
         self.name, self.params = name, tuple(params)
 
     def __repr__(self):
-        return self.name + ("{%s}" % ",".join(map(repr, self.params)) if self.params else "")
+        return str(self.name) + ("{%s}" % ",".join(map(repr, self.params)) if self.params else "")      # Array{Float64,3}: a parameter may be a number
 
 
 class JRange:

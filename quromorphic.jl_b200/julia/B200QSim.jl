@@ -24,7 +24,7 @@ import Quromorphic.QSim: nb, u2!, h!, x!, y!, z!, rx!, ry!, rz!, controlled!, cn
 #  as `B200State(n, m)` stands for `statevector(n, m)`.  Found by executing this file: tests/test_julia_shim_exec.py)
 import Quromorphic.QInfo: partial_trace, entanglement_entropy, von_neumann_entropy
 
-export B200State, B200Density, dist_unique_id, dist_ipc_export, dist_ipc_import!, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, apply_circuit_expect_z!, precompile_circuit!, jit_cache_dir, QMGate
+export B200State, B200Density, reset!, sync!, norm2, apply_batched!, expect_z_all_begin!, expect_z_all_end!, reduced_density_batch, entropy_batch, dist_unique_id, dist_ipc_export, dist_ipc_import!, expect_z_all, expect_all, reduced_density, sample, apply_circuit!, apply_circuit_expect_z!, precompile_circuit!, jit_cache_dir, QMGate
 
 const LIB = get(ENV, "QM_B200_LIB", joinpath(@__DIR__, "..", "libqm_b200.so"))
 
@@ -198,6 +198,56 @@ end
 function apply_circuit!(s::B200State, gates::Vector{QMGate})
     check(ccall((:qm_apply_circuit, LIB), Int32, (Ptr{Cvoid}, Ptr{QMGate}, Int32), s.handle, gates, length(gates)))
     s
+end
+
+# ---- what a reservoir loop needs beyond the reference's own API (no reference counterpart; same calls as the Python mirror) ----
+"back to |m> for every register of the batch (the reference allocates a new statevector(n, m) instead)"
+reset!(s::B200State, m::Int = 0) = (check(ccall((:qm_reset, LIB), Int32, (Ptr{Cvoid}, UInt64), s.handle, m)); s)
+"wait for everything queued on the register"
+sync!(s::B200State) = (check(ccall((:qm_sync, LIB), Int32, (Ptr{Cvoid},), s.handle)); s)
+"sum of abs2 of register `batch_idx` (no threshold)"
+function norm2(s::B200State; batch_idx::Int = 0)
+    v = Ref{Float64}(0.0)
+    check(ccall((:qm_norm2, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), s.handle, batch_idx, v))
+    v[]
+end
+
+"""
+    apply_batched!(s, gates, mats)
+
+One gate list for every register of the batch; a gate of kind QM_GATE_U2_SLOT takes ITS register's matrix from
+`mats[:, slot, b]` (8 x nslots x batch Float64: the 8 doubles of a Matrix{ComplexF64} 2x2, e.g. a per-register ry encoding).
+"""
+function apply_batched!(s::B200State, gates::Vector{QMGate}, mats::Array{Float64,3})
+    size(mats, 1) == 8 && size(mats, 3) == s.batch || error("mats must be 8 x nslots x batch")
+    check(ccall((:qm_apply_batched, LIB), Int32, (Ptr{Cvoid}, Ptr{QMGate}, Int32, Ptr{Float64}, Int32),
+                s.handle, gates, length(gates), mats, size(mats, 2)))
+    s
+end
+
+"first half of a split readout: enqueue the all-qubit measure_z of the state as it is NOW and return at once (at most two pending)"
+expect_z_all_begin!(s::B200State; threshold::Float64 = s.threshold) =
+    (check(ccall((:qm_expect_z_all_begin, LIB), Int32, (Ptr{Cvoid}, Float64), s.handle, threshold)); s)
+"second half: the oldest pending readout, 2 x n x batch"
+function expect_z_all_end!(s::B200State)
+    out = Array{Float64}(undef, 2, s.n, s.batch)
+    check(ccall((:qm_expect_z_all_end, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), s.handle, out))
+    out
+end
+
+"reduced density matrix of EVERY register of the batch: 2^k x 2^k x batch (QInfo.partial_trace of s*s', per register)"
+function reduced_density_batch(s::B200State, keep_low::Bool, k::Int)
+    d = 1 << k
+    out = Array{ComplexF64}(undef, d, d, s.batch)
+    check(ccall((:qm_reduced_density_batch, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{ComplexF64}), s.handle, keep_low ? 1 : 0, k, out))
+    out
+end
+"entropy of the reduced matrix of every register, on the device: kind = :von_neumann, :renyi (alpha), :min, :max (QInfo.jl:47-50, :199-204, :353-357, :332-337)"
+function entropy_batch(s::B200State, keep_low::Bool, k::Int; kind::Symbol = :von_neumann, alpha::Float64 = 2.0)
+    code = kind === :von_neumann ? 0 : kind === :renyi ? 1 : kind === :min ? 2 : kind === :max ? 3 : error("unknown entropy kind")
+    out = Vector{Float64}(undef, s.batch)
+    check(ccall((:qm_entropy_batch, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32, Float64, Ptr{Float64}), s.handle, keep_low ? 1 : 0, k, code, alpha, out))
+    out
 end
 
 "read a gate-list file written by circuits.save_gates (binary form: b\"QMGATES1\" | u32 n | u32 ngates | 80-byte records)"

@@ -252,3 +252,94 @@ def test_shim_sharded_register_calls_match_the_python_mirror(pkg):
     assert a[-1][0] == "qm_dist_ipc_export" and a[:-1] == b, (a, b)
     assert ("qm_create_dist", n, m, 1, rank, world, "buf", "ref") in a
     assert ("qm_download", "H", "buf", (1 << n) // world, 0) in a
+
+
+def test_shim_reservoir_loop_calls_match_the_python_mirror(pkg):
+    """reset!, norm2, the split readout, batched QInfo, the one-call step and the per-register batched application: symbols, order and
+    scalar arguments as the Python mirror's (buffers: presence only)"""
+    import make_ref_exec_golden as MR
+    n, batch = 6, 3
+    it = MR.load_reference()
+    it.modules["Quromorphic"] = it.globals
+    jl = []
+
+    def handler(name, args):
+        rec = [name]
+        for i, a in enumerate(args):
+            if isinstance(a, J.JRef):
+                if name == "qm_create": a.value = HANDLE
+                rec.append("ref")
+            elif isinstance(a, (np.ndarray, list)): rec.append("buf")
+            elif a == HANDLE and i == 0: rec.append("H")
+            else: rec.append(a)
+        jl.append(tuple(rec))
+        return 0
+
+    it.ccall_handler = handler
+    it.current_dir = os.path.join(ROOT, "quromorphic.jl_b200", "julia")
+    it.load_file(os.path.join(it.current_dir, "B200QSim.jl"))
+    it.using("B200QSim")
+    it.globals.vars["gates"] = []                      # a Vector{QMGate}: only its length crosses the recorder
+    it.globals.vars["mats"] = np.zeros((8, 2, batch))
+    it.run("""
+    s = B200State(%d, 0; batch = %d)
+    reset!(s, 5)
+    apply_batched!(s, gates, mats)
+    expect_z_all_begin!(s)
+    apply_circuit!(s, gates)
+    z = expect_z_all_end!(s)
+    z2 = apply_circuit_expect_z!(s, gates; threshold = -1.0)
+    nrm = norm2(s; batch_idx = 2)
+    rb = reduced_density_batch(s, true, 2)
+    e0 = entropy_batch(s, false, 2)
+    e1 = entropy_batch(s, true, 3; kind = :renyi, alpha = 0.5)
+    k = precompile_circuit!(s, gates)
+    sync!(s)
+    shapes = (size(z), size(z2), size(rb), length(e0))
+    """ % (n, batch))
+    assert it.globals.vars["shapes"] == ((2, n, batch), (2, n, batch), (4, 4, batch), batch)
+
+    L = pkg._lib
+    py = []
+
+    class Rec:
+        def __getattr__(self, name):
+            def call(*args):
+                rec = [name]
+                gate_array = name in ("qm_apply_batched", "qm_apply_circuit", "qm_apply_circuit_expect_z", "qm_precompile_circuit")
+                for i, a in enumerate(args):
+                    if isinstance(a, C.c_void_p): rec.append("H")
+                    elif gate_array and i == 1: rec.append("buf")              # gates.ctypes.data: an address
+                    elif isinstance(a, bool): rec.append(int(a))
+                    elif isinstance(a, (int, np.integer)): rec.append(int(a))
+                    elif isinstance(a, float): rec.append(a)
+                    elif type(a).__name__ == "CArgObject": rec.append("ref")
+                    else: rec.append("buf")
+                py.append(tuple(rec))
+                return 0
+            return call
+
+    saved = L._lib
+    L._lib = Rec()
+    try:
+        s = pkg.B200State(n, 0, batch=batch)
+        gates = np.zeros(0, dtype=L.GATE_DTYPE)
+        s.reset(5)
+        s.apply_batched(gates, np.zeros((batch, 2, 8)))
+        s.expect_z_all_begin()
+        s.apply_circuit(gates)
+        s.expect_z_all_end()
+        s.apply_circuit_expect_z(gates, -1.0)
+        s.norm2(2)
+        s.reduced_density_batch(True, 2)
+        s.entropy_batch(False, 2)
+        s.entropy_batch(True, 3, kind="renyi", alpha=0.5)
+        s.precompile_circuit(gates)
+        s.sync()
+        s._h = None
+    finally:
+        L._lib = saved
+    a = [r for r in jl if r[0] != "qm_destroy"]
+    b = [r for r in py if r[0] != "qm_destroy"]
+    assert a == b, [(x, y) for x, y in zip(a, b) if x != y]
+    assert ("qm_entropy_batch", "H", 1, 3, 1, 0.5, "buf") in a and ("qm_reset", "H", 5) in a
