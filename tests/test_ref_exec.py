@@ -374,3 +374,29 @@ def test_lsm_driver_and_ridge_readout_agree_with_the_executed_reference(pkg):
     assert np.max(np.abs(Wout @ st2 + bout[:, None] - pred)) < 1e-9 * max(1.0, np.max(np.abs(pred)))
     it.call(g["reset!"], [lsm])
     assert not lsm.fields["state"].any()
+
+
+@needs_ref
+def test_c_oracle_agrees_with_the_executed_reference_on_fresh_random_sequences(ref):
+    """beyond the committed fixtures: 40 new seeded call sequences (2-7 qubits, every gate kind, any ordered pair) through the
+    reference's own functions and through the C oracle — amplitudes, mp, measure_z/x/y of every qubit at 1e-12"""
+    from oracle import oracle as O
+    MR, it = ref
+    R = lambda name, *a: MR.ref_call(it, name, *a)
+    worst = 0.0
+    for seed in range(40):
+        n = 2 + seed % 6
+        m = (seed * 7) % (1 << n)
+        ops = MR.MG.make_ops(n, 30 + seed, 9000 + seed, None)
+        s_ref = R("statevector", n, m)
+        s_orc = O.statevector(n, m)
+        for op in ops:
+            MR.apply_op(it, s_ref, op)
+            name = op[0]
+            if isinstance(op[-1], str): getattr(O, name)(s_orc, *op[1:-1], float.fromhex(op[-1]))
+            else: getattr(O, name)(s_orc, *op[1:])
+        worst = max(worst, float(np.max(np.abs(s_ref - s_orc))), float(np.max(np.abs(R("mp", s_ref) - O.mp(s_orc)))))
+        for t in range(1, n + 1):
+            for name in ("measure_z", "measure_x", "measure_y"):
+                worst = max(worst, float(np.max(np.abs(np.array(R(name, s_ref, t)) - np.array(getattr(O, name)(s_orc, t))))))
+    assert worst < 1e-12, worst
